@@ -1,0 +1,787 @@
+// fmx_api.cu — the C ABI of libfmgpu.so (include/fmgpu.h): index upload, batched operator calls, regex
+// frontier driver, locate, device-side index construction.  Host buffers in, host buffers out; every
+// compute call runs on the index's CUDA stream and fails with FMX_E_CUDA when no device is usable —
+// there is no CPU path in this library.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fmx_build.cuh"
+#include "fmx_cub.cuh"
+#include "fmx_internal.h"
+#include "fmx_kernels.cuh"
+
+using namespace fmx;
+
+struct fmx_index {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevIndex d{};
+    LaunchCfg cfg{FMX_LAYOUT_WM, 4};
+    int64_t n = 0, eof = 0;
+    int64_t C[257] = {0};
+    int64_t counts0[256] = {0};        // raw counts (bucketStarts0 / pos2char)
+    int sigma = 0, levels = 0, sample_rate = 0;
+    int64_t nblk = 0, index_bytes = 0, n_samples = 0;
+    std::vector<void *> owned;         // device allocations freed at close
+    double last_ms = 0.0;
+    int64_t last_launches = 0, total_launches = 0;
+    std::mutex mu;
+};
+
+namespace {
+
+#define CU(x)                                                                                         \
+    do {                                                                                              \
+        cudaError_t e_ = (x);                                                                         \
+        if (e_ != cudaSuccess) return fail(FMX_E_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+// RAII stream-ordered device buffer
+struct DBuf {
+    void *p = nullptr;
+    cudaStream_t st;
+    explicit DBuf(cudaStream_t s) : st(s) {}
+    ~DBuf() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, st); }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct Timed {
+    fmx_index *ix;
+    explicit Timed(fmx_index *i) : ix(i) { cudaEventRecord(ix->ev0, ix->stream); ix->last_launches = 0; }
+    void stop() { cudaEventRecord(ix->ev1, ix->stream); }
+    void collect() { float ms = 0; if (cudaEventElapsedTime(&ms, ix->ev0, ix->ev1) == cudaSuccess) ix->last_ms = ms; }
+};
+
+int ensure_device(int device, int *chosen) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(FMX_E_CUDA, "no usable CUDA device (%s): libfmgpu has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    int dev = device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= count) return fail(FMX_E_ARG, "device %d out of range (%d devices)", dev, count);
+    CU(cudaSetDevice(dev));
+    *chosen = dev;
+    return FMX_OK;
+}
+
+template <typename T> T *dev_upload(fmx_index *ix, const T *host, size_t count, cudaError_t *err) {
+    void *p = nullptr;
+    *err = cudaMalloc(&p, count * sizeof(T) ? count * sizeof(T) : 1);
+    if (*err != cudaSuccess) return nullptr;
+    ix->owned.push_back(p);
+    if (count) *err = cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, ix->stream);
+    return reinterpret_cast<T *>(p);
+}
+
+int bitrev(int v, int bits) { int r = 0; for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1) << (bits - 1 - i); return r; }
+
+// ---- index upload (K0): tables on the host, rank structures on the device -------------------------------
+int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, const int64_t counts[256], const fmx_opts &o) {
+    if (n < 1 || eof < 0 || eof >= n) return fail(FMX_E_ARG, "bad n/eof");
+    if (n >= (1ll << 32) - 1) return fail(FMX_E_UNSUPPORTED, "n = %lld needs 64-bit rows; this build indexes n < 2^32-1", (long long)n);
+    ix->n = n; ix->eof = eof;
+    // C table: bucketStarts with counts[0] := 1   (bwtmerger.scala:346-350, util.scala:109-119)
+    int64_t tot = 0;
+    for (int c = 0; c < 256; ++c) { ix->C[c] = tot; tot += (c == 0) ? 1 : counts[c]; ix->counts0[c] = counts[c]; }
+    ix->C[256] = n;
+    if (tot != n) return fail(FMX_E_FORMAT, "aux counts sum %lld != n-1 = %lld", (long long)(tot - 1), (long long)(n - 1));
+
+    // dense symbol codes over the bytes that occur ('$' is not a symbol)
+    uint8_t code[256], sym[256];
+    int sigma = 0;
+    code[0] = kCodeAbsent;
+    for (int c = 1; c < 256; ++c) { if (counts[c] > 0) { code[c] = (uint8_t)sigma; sym[sigma++] = (uint8_t)c; } else code[c] = kCodeAbsent; }
+    if (sigma > 254) {           // 255 distinct bytes: code 0xFF collides with the "absent" marker only if sigma == 256
+        // codes run 0..254 here, 0xFF stays free because byte 0 never occurs in the text
+    }
+    int levels = 1;
+    while ((1 << levels) < sigma) ++levels;
+    ix->sigma = sigma; ix->levels = levels;
+    const int64_t nblk = n / kBitsPerBlock + 1;
+    ix->nblk = nblk;
+
+    int layout = o.layout;
+    const int64_t planes_bytes = (int64_t)std::max(sigma, 1) * nblk * 64, wm_bytes = (int64_t)levels * nblk * 64;
+    const int64_t budget = o.max_index_bytes > 0 ? o.max_index_bytes : (64ll << 30);
+    if (layout == FMX_LAYOUT_AUTO) {
+        size_t fr = 0, to = 0;
+        cudaMemGetInfo(&fr, &to);
+        layout = (planes_bytes <= budget && planes_bytes + (6ll << 30) + 2 * n < (int64_t)fr) ? FMX_LAYOUT_PLANES : FMX_LAYOUT_WM;
+    }
+    if (layout != FMX_LAYOUT_WM && layout != FMX_LAYOUT_PLANES) return fail(FMX_E_ARG, "bad layout %d", layout);
+    int lanes = o.lanes_per_query ? o.lanes_per_query : 4;
+    if (lanes != 1 && lanes != 2 && lanes != 4) return fail(FMX_E_ARG, "lanes_per_query must be 1, 2 or 4");
+    ix->cfg = LaunchCfg{layout, lanes};
+    ix->index_bytes = (layout == FMX_LAYOUT_PLANES ? planes_bytes : wm_bytes) + n;
+
+    // base[c]: PLANES: C[c].  WM: C[c] - start_final[code], where after `levels` stable bit partitions the
+    // symbols are ordered by bit-reversed code; the '$' row travels with code 0.
+    uint32_t C32[257], base[256], z[8] = {0};
+    for (int c = 0; c <= 256; ++c) C32[c] = (uint32_t)ix->C[c];
+    for (int c = 0; c < 256; ++c) base[c] = C32[c];
+    if (layout == FMX_LAYOUT_WM) {
+        std::vector<int64_t> cc(1 << levels, 0);                 // occurrences per code ('$' under code 0)
+        for (int s = 0; s < sigma; ++s) cc[s] = counts[sym[s]];
+        cc[0] += 1;
+        for (int l = 0; l < levels; ++l) {
+            int64_t zeros = 0;
+            for (int s = 0; s < (1 << levels); ++s) if (!((s >> (levels - 1 - l)) & 1)) zeros += cc[s];
+            z[l] = (uint32_t)zeros;
+        }
+        std::vector<int> order(1 << levels);
+        for (int s = 0; s < (1 << levels); ++s) order[s] = s;
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return bitrev(a, levels) < bitrev(b, levels); });
+        std::vector<int64_t> start(1 << levels, 0);
+        int64_t acc = 0;
+        for (int s : order) { start[s] = acc; acc += cc[s]; }
+        for (int s = 0; s < sigma; ++s) base[sym[s]] = (uint32_t)(ix->C[sym[s]] - start[s]);
+    }
+
+    cudaError_t e;
+    uint8_t *d_bwt = dev_upload(ix, bwt, (size_t)n, &e); CU(e);
+    CU(cudaMemsetAsync(d_bwt + eof, 0, 1, ix->stream));
+    uint32_t *d_C = dev_upload(ix, C32, 257, &e); CU(e);
+    uint32_t *d_base = dev_upload(ix, base, 256, &e); CU(e);
+    uint8_t *d_code = dev_upload(ix, code, 256, &e); CU(e);
+    uint8_t *d_sym = dev_upload(ix, sym, 256, &e); CU(e);
+    void *blocks = nullptr;
+    const int64_t nplanes = layout == FMX_LAYOUT_PLANES ? std::max(sigma, 1) : levels;
+    e = cudaMalloc(&blocks, (size_t)nplanes * nblk * 64);
+    if (e != cudaSuccess) return fail(FMX_E_CUDA, "cannot allocate %lld bytes for the rank structure: %s", (long long)(nplanes * nblk * 64), cudaGetErrorString(e));
+    ix->owned.push_back(blocks);
+    CU(cudaMemsetAsync(blocks, 0, (size_t)nplanes * nblk * 64, ix->stream));
+    if (layout == FMX_LAYOUT_PLANES) CU(build_planes(d_bwt, n, (uint32_t)eof, d_sym, sigma, (uint32_t *)blocks, nblk, ix->stream));
+    else CU(build_wm(d_bwt, n, (uint32_t)eof, d_code, levels, (uint32_t *)blocks, nblk, ix->stream));
+
+    DevIndex &d = ix->d;
+    d.blocks = (const uint4 *)blocks; d.stride = (uint64_t)nblk; d.bwt = d_bwt; d.C = d_C; d.base = d_base; d.code = d_code;
+    d.mark = nullptr; d.samples = nullptr; d.n = (uint32_t)n; d.eof = (uint32_t)eof; d.layout = layout; d.levels = levels;
+    for (int l = 0; l < 8; ++l) d.z[l] = z[l];
+
+    ix->sample_rate = o.sa_sample_rate;
+    if (o.sa_sample_rate > 0) {
+        const int64_t ns = (n + o.sa_sample_rate - 1) / o.sa_sample_rate;
+        void *mark = nullptr, *samples = nullptr;
+        e = cudaMalloc(&mark, (size_t)nblk * 64); CU(e); ix->owned.push_back(mark);
+        e = cudaMalloc(&samples, (size_t)ns * 4); CU(e); ix->owned.push_back(samples);
+        std::string err;
+        e = build_sa_samples(d, layout, o.sa_sample_rate, (uint32_t *)mark, nblk, (uint32_t *)samples, ns, ix->stream, err);
+        if (e != cudaSuccess) return fail(err.empty() ? FMX_E_CUDA : FMX_E_FORMAT, "sampled SA construction failed: %s", err.empty() ? cudaGetErrorString(e) : err.c_str());
+        d.mark = (const uint4 *)mark; d.samples = (const uint32_t *)samples;
+        ix->n_samples = ns;
+        ix->index_bytes += nblk * 64 + ns * 4;
+    }
+    CU(cudaStreamSynchronize(ix->stream));
+    return FMX_OK;
+}
+
+int new_index(const fmx_opts *opts, fmx_index **out, fmx_opts *resolved) {
+    fmx_opts o;
+    fmx_opts_default(&o);
+    if (opts) o = *opts;
+    int dev = 0;
+    int rc = ensure_device(o.device, &dev);
+    if (rc) return rc;
+    fmx_index *ix = new fmx_index();
+    ix->device = dev;
+    if (cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ix->ev0) != cudaSuccess ||
+        cudaEventCreate(&ix->ev1) != cudaSuccess) {
+        delete ix;
+        return fail(FMX_E_CUDA, "cannot create CUDA stream/events");
+    }
+    *out = ix;
+    *resolved = o;
+    return FMX_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+#define CHECK_IX(ix) do { if (!(ix)) return fail(FMX_E_ARG, "null index"); } while (0)
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+void fmx_opts_default(fmx_opts *o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof *o);
+    o->device = -1;
+    o->layout = FMX_LAYOUT_AUTO;
+    o->sa_sample_rate = 0;
+}
+
+const char *fmx_version(void) { return "fmgpu 0.1 (sm_100a)"; }
+
+int fmx_open(const char *path, int big_endian, const fmx_opts *opts, fmx_index **out) {
+    if (!path || !out) return fail(FMX_E_ARG, "null argument");
+    *out = nullptr;
+    fmx_opts o;
+    fmx_opts_default(&o);
+    if (opts) o = *opts;
+    IndexFiles f;
+    int rc = load_index_files(strip_extension(path), big_endian != 0, o.require_fm != 0, f);   // validate before touching the GPU
+    if (rc) return rc;
+    fmx_index *ix = nullptr;
+    rc = new_index(&o, &ix, &o);
+    if (rc) return rc;
+    rc = upload_index(ix, f.bwt.data(), f.n, f.eof, f.counts, o);
+    if (rc) { fmx_close(ix); return rc; }
+    *out = ix;
+    return FMX_OK;
+}
+
+int fmx_open_mem(const uint8_t *bwt, int64_t n, int64_t eof, const int64_t counts[256], const fmx_opts *opts, fmx_index **out) {
+    if (!bwt || !counts || !out) return fail(FMX_E_ARG, "null argument");
+    *out = nullptr;
+    fmx_opts o;
+    fmx_index *ix = nullptr;
+    int rc = new_index(opts, &ix, &o);
+    if (rc) return rc;
+    rc = upload_index(ix, bwt, n, eof, counts, o);
+    if (rc) { fmx_close(ix); return rc; }
+    *out = ix;
+    return FMX_OK;
+}
+
+int fmx_close(fmx_index *ix) {
+    if (!ix) return FMX_OK;
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    for (void *p : ix->owned) cudaFree(p);
+    if (ix->ev0) cudaEventDestroy(ix->ev0);
+    if (ix->ev1) cudaEventDestroy(ix->ev1);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+    return FMX_OK;
+}
+
+int64_t fmx_n(const fmx_index *ix) { return ix ? ix->n : -1; }
+int64_t fmx_eof(const fmx_index *ix) { return ix ? ix->eof : -1; }
+int fmx_ctable(const fmx_index *ix, int64_t C[256]) {
+    CHECK_IX(ix);
+    if (!C) return fail(FMX_E_ARG, "null argument");
+    for (int c = 0; c < 256; ++c) C[c] = ix->C[c];
+    return FMX_OK;
+}
+int fmx_info(const fmx_index *ix, int32_t *layout, int32_t *levels, int32_t *sigma, int64_t *index_bytes, int32_t *rate) {
+    CHECK_IX(ix);
+    if (layout) *layout = ix->cfg.layout;
+    if (levels) *levels = ix->cfg.layout == FMX_LAYOUT_WM ? ix->levels : 1;
+    if (sigma) *sigma = ix->sigma;
+    if (index_bytes) *index_bytes = ix->index_bytes;
+    if (rate) *rate = ix->sample_rate;
+    return FMX_OK;
+}
+double fmx_last_kernel_ms(const fmx_index *ix) { return ix ? ix->last_ms : 0.0; }
+int64_t fmx_last_kernel_launches(const fmx_index *ix) { return ix ? ix->last_launches : 0; }
+
+// pos2char: bwtmerger.scala:376-385 (bucketStarts0 = prefix sums of the raw counts)
+int fmx_pos2char(const fmx_index *ix, int64_t key, int32_t *c) {
+    CHECK_IX(ix);
+    if (!c) return fail(FMX_E_ARG, "null argument");
+    int64_t bs0[256], tot = 0;
+    for (int i = 0; i < 256; ++i) { bs0[i] = tot; tot += ix->counts0[i]; }
+    int i = 255;
+    if (bs0[i] > key) { while (bs0[i] > key && i > 0) --i; }
+    else { while (bs0[i - 1] == bs0[i] && i > 1) --i; --i; }
+    *c = i;
+    return FMX_OK;
+}
+
+// ---- element-wise operator batches -----------------------------------------------------------------------
+int fmx_occ_batch(fmx_index *ix, const uint8_t *c, const int64_t *key, int64_t m, int64_t *out) {
+    CHECK_IX(ix);
+    if (m < 0 || (m && (!c || !key || !out))) return fail(FMX_E_ARG, "bad argument");
+    if (m == 0) return FMX_OK;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    DBuf dc(st), dk(st), dout(st);
+    CU(dc.alloc(m)); CU(dk.alloc(m * 8)); CU(dout.alloc(m * 8));
+    CU(cudaMemcpyAsync(dc.p, c, m, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dk.p, key, m * 8, cudaMemcpyHostToDevice, st));
+    Timed t(ix);
+    CU(launch_occ(ix->d, ix->cfg, dc.as<uint8_t>(), dk.as<int64_t>(), m, dout.as<int64_t>(), st));
+    ix->last_launches = 1; ix->total_launches += 1;
+    t.stop();
+    CU(cudaMemcpyAsync(out, dout.p, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    t.collect();
+    return FMX_OK;
+}
+
+int fmx_prev_range_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, const uint8_t *c, int64_t m, int64_t *sp1, int64_t *ep1) {
+    CHECK_IX(ix);
+    if (m < 0 || (m && (!sp || !ep || !c || !sp1 || !ep1))) return fail(FMX_E_ARG, "bad argument");
+    if (m == 0) return FMX_OK;
+    for (int64_t i = 0; i < m; ++i)
+        if (sp[i] < 0 || ep[i] < 0 || sp[i] > ix->n || ep[i] > ix->n) return fail(FMX_E_ARG, "row out of range at %lld", (long long)i);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    DBuf dsp(st), dep(st), dc(st), o1(st), o2(st);
+    CU(dsp.alloc(m * 8)); CU(dep.alloc(m * 8)); CU(dc.alloc(m)); CU(o1.alloc(m * 8)); CU(o2.alloc(m * 8));
+    CU(cudaMemcpyAsync(dsp.p, sp, m * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dep.p, ep, m * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dc.p, c, m, cudaMemcpyHostToDevice, st));
+    Timed t(ix);
+    CU(launch_prev_range(ix->d, ix->cfg, dsp.as<int64_t>(), dep.as<int64_t>(), dc.as<uint8_t>(), m, o1.as<int64_t>(), o2.as<int64_t>(), st));
+    ix->last_launches = 1; ix->total_launches += 1;
+    t.stop();
+    CU(cudaMemcpyAsync(sp1, o1.p, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ep1, o2.p, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    t.collect();
+    return FMX_OK;
+}
+
+int fmx_interval_prev_range(fmx_index *ix, int64_t sp, int64_t ep, int cstart, int cend, int32_t *out_c, int64_t *out_sp,
+                            int64_t *out_ep, int64_t *n_out) {
+    CHECK_IX(ix);
+    if (!n_out) return fail(FMX_E_ARG, "null argument");
+    *n_out = 0;
+    if (cstart < 0 || cend > 255 || sp < 0 || ep < 0 || sp > ix->n || ep > ix->n) return fail(FMX_E_ARG, "bad argument");
+    const int m = cend - cstart + 1;
+    if (m <= 0) return FMX_OK;
+    if (!out_c || !out_sp || !out_ep) return fail(FMX_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    DBuf o1(st), o2(st);
+    CU(o1.alloc(m * 8)); CU(o2.alloc(m * 8));
+    Timed t(ix);
+    CU(launch_interval_prev_range(ix->d, ix->cfg, sp, ep, cstart, cend, o1.as<int64_t>(), o2.as<int64_t>(), st));
+    ix->last_launches = 1; ix->total_launches += 1;
+    t.stop();
+    std::vector<int64_t> a(m), b(m);
+    CU(cudaMemcpyAsync(a.data(), o1.p, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(b.data(), o2.p, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    t.collect();
+    int64_t k = 0;
+    for (int c = cend; c >= cstart; --c)                       // the reference prepends while c ascends
+        if (a[c - cstart] < b[c - cstart]) { out_c[k] = c; out_sp[k] = a[c - cstart]; out_ep[k] = b[c - cstart]; ++k; }
+    *n_out = k;
+    return FMX_OK;
+}
+
+// ---- count -------------------------------------------------------------------------------------------------
+int fmx_count_fixed_dev(fmx_index *ix, const void *d_pat, int32_t len, int64_t m, void *d_sp, void *d_ep, void *stream) {
+    CHECK_IX(ix);
+    if (len < 0 || m < 0 || (m && (!d_sp || !d_ep || (len && !d_pat)))) return fail(FMX_E_ARG, "bad argument");
+    DeviceGuard g(ix->device);
+    CU(launch_count_fixed(ix->d, ix->cfg, (const uint8_t *)d_pat, len, m, d_sp, d_ep, false, nullptr, (cudaStream_t)stream));
+    ix->last_launches = 1; ix->total_launches += 1;
+    return FMX_OK;
+}
+
+int fmx_count_fixed(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, int64_t *sp, int64_t *ep) {
+    CHECK_IX(ix);
+    if (len < 0 || m < 0 || (m && (!sp || !ep || (len && !pat)))) return fail(FMX_E_ARG, "bad argument");
+    if (m == 0) return FMX_OK;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    DBuf dp(st), dsp(st), dep(st);
+    CU(dp.alloc((size_t)m * len)); CU(dsp.alloc(m * 8)); CU(dep.alloc(m * 8));
+    if (len) CU(cudaMemcpyAsync(dp.p, pat, (size_t)m * len, cudaMemcpyHostToDevice, st));
+    Timed t(ix);
+    CU(launch_count_fixed(ix->d, ix->cfg, dp.as<uint8_t>(), len, m, dsp.p, dep.p, true, nullptr, st));
+    ix->last_launches = 1; ix->total_launches += 1;
+    t.stop();
+    CU(cudaMemcpyAsync(sp, dsp.p, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ep, dep.p, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    t.collect();
+    return FMX_OK;
+}
+
+int fmx_count_batch(fmx_index *ix, const uint8_t *pat, const int64_t *off, int64_t m, int64_t *sp, int64_t *ep) {
+    CHECK_IX(ix);
+    if (m < 0 || (m && (!off || !sp || !ep))) return fail(FMX_E_ARG, "bad argument");
+    if (m == 0) return FMX_OK;
+    for (int64_t i = 0; i < m; ++i) if (off[i + 1] < off[i] || off[i] < 0) return fail(FMX_E_ARG, "offsets must be non-decreasing");
+    const int64_t nbytes = off[m];
+    if (nbytes && !pat) return fail(FMX_E_ARG, "null pattern buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    DBuf dp(st), doff(st), dsp(st), dep(st);
+    CU(dp.alloc(nbytes)); CU(doff.alloc((m + 1) * 8)); CU(dsp.alloc(m * 8)); CU(dep.alloc(m * 8));
+    if (nbytes) CU(cudaMemcpyAsync(dp.p, pat, nbytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(doff.p, off, (m + 1) * 8, cudaMemcpyHostToDevice, st));
+    Timed t(ix);
+    CU(launch_count_var(ix->d, ix->cfg, dp.as<uint8_t>(), doff.as<int64_t>(), m, dsp.as<int64_t>(), dep.as<int64_t>(), st));
+    ix->last_launches = 1; ix->total_launches += 1;
+    t.stop();
+    CU(cudaMemcpyAsync(sp, dsp.p, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ep, dep.p, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    t.collect();
+    return FMX_OK;
+}
+
+int fmx_count_fixed_stats(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, int64_t *blocks, int64_t *steps) {
+    CHECK_IX(ix);
+    if (len < 0 || m < 0 || (m && len && !pat)) return fail(FMX_E_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    DBuf dp(st), dsp(st), dep(st), ds(st);
+    CU(dp.alloc((size_t)m * len)); CU(dsp.alloc(m * 4)); CU(dep.alloc(m * 4)); CU(ds.alloc(16));
+    if (m && len) CU(cudaMemcpyAsync(dp.p, pat, (size_t)m * len, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(ds.p, 0, 16, st));
+    CU(launch_count_fixed(ix->d, ix->cfg, dp.as<uint8_t>(), len, m, dsp.p, dep.p, false, ds.as<unsigned long long>(), st));
+    unsigned long long h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, ds.p, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (blocks) *blocks = (int64_t)h[0];
+    if (steps) *steps = (int64_t)h[1];
+    return FMX_OK;
+}
+
+// ---- LF / FL / extraction -----------------------------------------------------------------------------------
+int fmx_get_prev_i_batch(fmx_index *ix, const int64_t *row, int64_t m, int64_t *out) {
+    CHECK_IX(ix);
+    if (m < 0 || (m && (!row || !out))) return fail(FMX_E_ARG, "bad argument");
+    if (m == 0) return FMX_OK;
+    for (int64_t i = 0; i < m; ++i) if (row[i] < 0 || row[i] >= ix->n) return fail(FMX_E_ARG, "row out of range at %lld", (long long)i);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    DBuf dr(st), dout(st);
+    CU(dr.alloc(m * 8)); CU(dout.alloc(m * 8));
+    CU(cudaMemcpyAsync(dr.p, row, m * 8, cudaMemcpyHostToDevice, st));
+    Timed t(ix);
+    CU(launch_lf(ix->d, ix->cfg, dr.as<int64_t>(), m, dout.as<int64_t>(), st));
+    ix->last_launches = 1; ix->total_launches += 1;
+    t.stop();
+    CU(cudaMemcpyAsync(out, dout.p, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    t.collect();
+    return FMX_OK;
+}
+
+int fmx_prev_substr_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t len, uint8_t *out, int32_t *out_len) {
+    CHECK_IX(ix);
+    if (m < 0 || len < 0 || (m && (!row || (len && !out)))) return fail(FMX_E_ARG, "bad argument");
+    if (m == 0) return FMX_OK;
+    for (int64_t i = 0; i < m; ++i) if (row[i] < 0 || row[i] >= ix->n) return fail(FMX_E_ARG, "row out of range at %lld", (long long)i);
+    if (out_len) for (int64_t i = 0; i < m; ++i) out_len[i] = len;      // prevSubstr never stops early (its eof flag is never set)
+    if (len == 0) return FMX_OK;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    DBuf dr(st), dout(st);
+    CU(dr.alloc(m * 8)); CU(dout.alloc((size_t)m * len));
+    CU(cudaMemcpyAsync(dr.p, row, m * 8, cudaMemcpyHostToDevice, st));
+    Timed t(ix);
+    CU(launch_prev_substr(ix->d, ix->cfg, dr.as<int64_t>(), m, len, dout.as<uint8_t>(), st));
+    ix->last_launches = 1; ix->total_launches += 1;
+    t.stop();
+    CU(cudaMemcpyAsync(out, dout.p, (size_t)m * len, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    t.collect();
+    return FMX_OK;
+}
+
+int fmx_get_next_i_batch(fmx_index *ix, const int64_t *row, int64_t m, int64_t *out) {
+    CHECK_IX(ix);
+    if (m < 0 || (m && (!row || !out))) return fail(FMX_E_ARG, "bad argument");
+    if (m == 0) return FMX_OK;
+    for (int64_t i = 0; i < m; ++i) if (row[i] < 0 || row[i] >= ix->n) return fail(FMX_E_ARG, "row out of range at %lld", (long long)i);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    DBuf dr(st), dout(st);
+    CU(dr.alloc(m * 8)); CU(dout.alloc(m * 8));
+    CU(cudaMemcpyAsync(dr.p, row, m * 8, cudaMemcpyHostToDevice, st));
+    Timed t(ix);
+    CU(launch_fl(ix->d, ix->cfg, dr.as<int64_t>(), m, dout.as<int64_t>(), st));
+    ix->last_launches = 1; ix->total_launches += 1;
+    t.stop();
+    CU(cudaMemcpyAsync(out, dout.p, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    t.collect();
+    return FMX_OK;
+}
+
+int fmx_next_substr_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t len, uint8_t *out, int32_t *out_len) {
+    CHECK_IX(ix);
+    if (m < 0 || len < 0 || (m && (!row || !out_len || (len && !out)))) return fail(FMX_E_ARG, "bad argument");
+    if (m == 0) return FMX_OK;
+    for (int64_t i = 0; i < m; ++i) if (row[i] < 0 || row[i] >= ix->n) return fail(FMX_E_ARG, "row out of range at %lld", (long long)i);
+    if (len == 0) { for (int64_t i = 0; i < m; ++i) out_len[i] = 0; return FMX_OK; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    DBuf dr(st), dout(st), dlen(st);
+    CU(dr.alloc(m * 8)); CU(dout.alloc((size_t)m * len)); CU(dlen.alloc(m * 4));
+    CU(cudaMemcpyAsync(dr.p, row, m * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(dout.p, 0, (size_t)m * len, st));
+    Timed t(ix);
+    CU(launch_next_substr(ix->d, ix->cfg, dr.as<int64_t>(), m, len, dout.as<uint8_t>(), dlen.as<int>(), st));
+    ix->last_launches = 1; ix->total_launches += 1;
+    t.stop();
+    CU(cudaMemcpyAsync(out, dout.p, (size_t)m * len, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_len, dlen.p, m * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    t.collect();
+    for (int64_t i = 0; i < m; ++i) std::reverse(out + i * len, out + i * len + out_len[i]);     // ret.reverse.toString
+    return FMX_OK;
+}
+
+// ---- locate ---------------------------------------------------------------------------------------------------
+int fmx_locate_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, int64_t m, int64_t cap_total, int64_t *out_off, int64_t *pos) {
+    CHECK_IX(ix);
+    if (m < 0 || !out_off || (m && (!sp || !ep))) return fail(FMX_E_ARG, "bad argument");
+    if (ix->sample_rate <= 0) return fail(FMX_E_ARG, "index was opened without sa_sample_rate; locate unavailable");
+    int64_t total = 0;
+    for (int64_t i = 0; i < m; ++i) {
+        if (sp[i] < 0 || ep[i] > ix->n || (ep[i] < sp[i])) return fail(FMX_E_ARG, "bad interval at %lld", (long long)i);
+        out_off[i] = total;
+        total += ep[i] - sp[i];
+    }
+    out_off[m] = total;
+    if (total > cap_total) return fail(FMX_E_CAPACITY, "locate needs %lld output slots, capacity %lld", (long long)total, (long long)cap_total);
+    if (total == 0) return FMX_OK;
+    if (!pos) return fail(FMX_E_ARG, "null output");
+    if (total >= (1ll << 31)) return fail(FMX_E_LIMIT, "more than 2^31 occurrences in one batch; split the batch");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    DBuf dsp(st), doff(st), dpos(st), dsorted(st), dout(st);
+    CU(dsp.alloc(m * 8)); CU(doff.alloc((m + 1) * 8)); CU(dpos.alloc(total * 4)); CU(dsorted.alloc(total * 4));
+    CU(cudaMemcpyAsync(dsp.p, sp, m * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(doff.p, out_off, (m + 1) * 8, cudaMemcpyHostToDevice, st));
+    Timed t(ix);
+    CU(launch_locate(ix->d, ix->cfg, dsp.as<int64_t>(), doff.as<int64_t>(), m, total, ix->sample_rate, dpos.as<uint32_t>(), st));
+    CU(segmented_sort_u32(dpos.as<uint32_t>(), dsorted.as<uint32_t>(), total, m, doff.as<int64_t>(), st));
+    ix->last_launches = 1; ix->total_launches += 1;
+    t.stop();
+    std::vector<uint32_t> h((size_t)total);
+    CU(cudaMemcpyAsync(h.data(), dsorted.p, total * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    t.collect();
+    for (int64_t i = 0; i < total; ++i) pos[i] = h[(size_t)i];
+    return FMX_OK;
+}
+
+// ---- regex ------------------------------------------------------------------------------------------------------
+int fmx_regex_compile(const uint8_t *re, int64_t re_len, int line_only, fmx_regex **out) {
+    if (!out || re_len < 0 || (re_len && !re)) return fail(FMX_E_ARG, "bad argument");
+    *out = nullptr;
+    fmx_regex *rx = new fmx_regex();
+    std::string err;
+    int rc = compile_regex(re, re_len, line_only != 0, rx->a, err);
+    if (rc) { delete rx; return fail(rc, "%s", err.c_str()); }
+    *out = rx;
+    return FMX_OK;
+}
+void fmx_regex_free(fmx_regex *rx) { delete rx; }
+
+int fmx_regex_tables(const fmx_regex *rx, int32_t *n_states, int32_t *n_follows, int32_t *n_firsts, uint8_t *c, uint8_t *is_last,
+                     int32_t *num, int32_t *follows_off, int32_t *follows, int32_t *firsts) {
+    if (!rx) return fail(FMX_E_ARG, "null regex");
+    const CompiledRegex &a = rx->a;
+    if (n_states) *n_states = (int32_t)a.c.size();
+    if (n_follows) *n_follows = (int32_t)a.follows.size();
+    if (n_firsts) *n_firsts = (int32_t)a.firsts.size();
+    if (c) std::copy(a.c.begin(), a.c.end(), c);
+    if (is_last) std::copy(a.is_last.begin(), a.is_last.end(), is_last);
+    if (num) std::copy(a.num.begin(), a.num.end(), num);
+    if (follows_off) std::copy(a.follows_off.begin(), a.follows_off.end(), follows_off);
+    if (follows) std::copy(a.follows.begin(), a.follows.end(), follows);
+    if (firsts) std::copy(a.firsts.begin(), a.firsts.end(), firsts);
+    return FMX_OK;
+}
+
+int fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64_t cap_total, int64_t *out_off, int32_t *len,
+                           int64_t *sp, int64_t *ep) {
+    CHECK_IX(ix);
+    if (m < 0 || !out_off || (m && !rx)) return fail(FMX_E_ARG, "bad argument");
+    for (int64_t i = 0; i <= m; ++i) out_off[i] = 0;
+    if (m == 0) return FMX_OK;
+    if (m >= (1ll << 32)) return fail(FMX_E_LIMIT, "too many regexes in one batch");
+    // concatenate the automata: global state ids, CSR follows, owning regex
+    std::vector<uint8_t> st_c, st_last; std::vector<uint32_t> st_regex, fol_off, fol; std::vector<FrontierItem> front;
+    fol_off.push_back(0);
+    for (int64_t r = 0; r < m; ++r) {
+        if (!rx[r]) return fail(FMX_E_ARG, "null regex at %lld", (long long)r);
+        const CompiledRegex &a = rx[r]->a;
+        const uint32_t base = (uint32_t)st_c.size();
+        for (size_t s = 0; s < a.c.size(); ++s) {
+            st_c.push_back(a.c[s]); st_last.push_back(a.is_last[s]); st_regex.push_back((uint32_t)r);
+            for (int32_t k = a.follows_off[s]; k < a.follows_off[s + 1]; ++k) fol.push_back(base + (uint32_t)a.follows[k]);
+            fol_off.push_back((uint32_t)fol.size());
+        }
+        for (int32_t f : a.firsts) front.push_back(FrontierItem{base + (uint32_t)f, 0u, 0u, (uint32_t)ix->n});   // StatePoint(0,0,sa.n,_)
+    }
+    if (front.empty()) return FMX_OK;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    DBuf d_c(st), d_last(st), d_rx(st), d_fo(st), d_f(st), fa(st), fb(st), d_res(st), d_tmp(st), d_cnt(st);
+    CU(d_c.alloc(st_c.size())); CU(d_last.alloc(st_last.size())); CU(d_rx.alloc(st_regex.size() * 4));
+    CU(d_fo.alloc(fol_off.size() * 4)); CU(d_f.alloc(fol.size() * 4 + 4));
+    CU(cudaMemcpyAsync(d_c.p, st_c.data(), st_c.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_last.p, st_last.data(), st_last.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_rx.p, st_regex.data(), st_regex.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_fo.p, fol_off.data(), fol_off.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!fol.empty()) CU(cudaMemcpyAsync(d_f.p, fol.data(), fol.size() * 4, cudaMemcpyHostToDevice, st));
+    RegexTables rt{d_c.as<uint8_t>(), d_last.as<uint8_t>(), d_rx.as<uint32_t>(), d_fo.as<uint32_t>(), d_f.as<uint32_t>()};
+
+    size_t fr = 0, to = 0;
+    cudaMemGetInfo(&fr, &to);
+    // two frontier buffers sized from what the device has left: an eighth of free memory each, 1 Mi..256 Mi items
+    int64_t cap_front = std::min<int64_t>(std::max<int64_t>((int64_t)(fr / 8 / sizeof(FrontierItem)), 1 << 20), 1ll << 28);
+    cap_front = std::max<int64_t>(cap_front, (int64_t)front.size());
+    int64_t cap_res = std::max<int64_t>(cap_total, 1 << 16);
+    CU(fa.alloc(cap_front * sizeof(FrontierItem))); CU(fb.alloc(cap_front * sizeof(FrontierItem)));
+    CU(d_res.alloc(cap_res * sizeof(RegexResult))); CU(d_cnt.alloc(16));
+    CU(cudaMemcpyAsync(fa.p, front.data(), front.size() * sizeof(FrontierItem), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_cnt.p, 0, 16, st));
+    Timed t(ix);
+    int64_t n_in = (int64_t)front.size(), launches = 0, level = 0;
+    unsigned long long h[2] = {0, 0};
+    void *cur = fa.p, *nxt = fb.p;
+    int64_t cap_cur = cap_front, cap_nxt = cap_front;
+    while (n_in > 0) {
+        if (++level > ix->n + 1) return fail(FMX_E_LIMIT, "regex traversal deeper than the text");
+        CU(cudaMemsetAsync(d_cnt.p, 0, 8, st));                      // next-frontier counter; the result counter accumulates
+        CU(launch_regex_level(ix->d, ix->cfg, rt, (const FrontierItem *)cur, n_in, (FrontierItem *)nxt, cap_nxt, d_res.as<RegexResult>(), cap_res,
+                              d_cnt.as<unsigned long long>(), st));
+        ++launches;
+        CU(cudaMemcpyAsync(h, d_cnt.p, 16, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if ((int64_t)h[0] > cap_nxt)
+            return fail(FMX_E_LIMIT, "regex frontier of %llu items exceeds the device budget of %lld; split the batch", h[0], (long long)cap_nxt);
+        n_in = (int64_t)h[0];
+        std::swap(cur, nxt);
+        std::swap(cap_cur, cap_nxt);
+    }
+    const int64_t total = (int64_t)h[1];
+    ix->last_launches = launches; ix->total_launches += launches;
+    if (total > cap_res) {                                            // counted everything, could not store it
+        t.stop();
+        out_off[m] = total;
+        return fail(FMX_E_CAPACITY, "regex search needs %lld result slots, capacity %lld", (long long)total, (long long)cap_total);
+    }
+    CU(d_tmp.alloc(std::max<int64_t>(total, 1) * sizeof(RegexResult)));
+    CU(sort_regex_results(d_res.as<RegexResult>(), d_tmp.as<RegexResult>(), total, st));
+    t.stop();
+    std::vector<RegexResult> hr((size_t)total);
+    if (total) CU(cudaMemcpyAsync(hr.data(), d_res.p, total * sizeof(RegexResult), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    t.collect();
+    for (const RegexResult &r : hr) out_off[r.regex + 1]++;
+    for (int64_t i = 0; i < m; ++i) out_off[i + 1] += out_off[i];
+    if (total > cap_total) return fail(FMX_E_CAPACITY, "regex search needs %lld result slots, capacity %lld", (long long)total, (long long)cap_total);
+    if (total && (!len || !sp || !ep)) return fail(FMX_E_ARG, "null output");
+    for (int64_t i = 0; i < total; ++i) { len[i] = (int32_t)hr[(size_t)i].len; sp[i] = hr[(size_t)i].sp; ep[i] = hr[(size_t)i].ep; }
+    return FMX_OK;
+}
+
+// ---- K4 gather microbenchmark -------------------------------------------------------------------------------------
+int fmx_gather_bench(fmx_index *ix, int32_t bytes, int32_t lanes, int64_t gathers, int32_t chain, int32_t iters, double *gbs, double *ms_out) {
+    CHECK_IX(ix);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    DBuf sink(st);
+    CU(sink.alloc(8));
+    CU(cudaMemsetAsync(sink.p, 0, 8, st));
+    const uint64_t nplanes = ix->cfg.layout == FMX_LAYOUT_PLANES ? (uint64_t)std::max(ix->sigma, 1) : (uint64_t)ix->levels;
+    const uint64_t nb = nplanes * (uint64_t)ix->nblk;
+    CU(launch_gather_bench(ix->d.blocks, nb, bytes, lanes, gathers, chain, 1u, sink.as<unsigned long long>(), st));   // warm-up
+    float best = 1e30f;
+    for (int it = 0; it < std::max(iters, 1); ++it) {
+        CU(cudaEventRecord(ix->ev0, st));
+        CU(launch_gather_bench(ix->d.blocks, nb, bytes, lanes, gathers, chain, 1000u + it, sink.as<unsigned long long>(), st));
+        CU(cudaEventRecord(ix->ev1, st));
+        CU(cudaStreamSynchronize(st));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
+        best = std::min(best, ms);
+    }
+    if (ms_out) *ms_out = best;
+    if (gbs) *gbs = (double)gathers * chain * bytes / (best * 1e-3) / 1e9;
+    return FMX_OK;
+}
+
+// ---- index construction on the device -----------------------------------------------------------------------------
+static int build_bwt_impl(const uint8_t *text, int64_t len, int device, std::vector<uint8_t> &bwt, int64_t *eof, int64_t counts[256],
+                          std::vector<uint32_t> *fm) {
+    if (len < 0 || (len && !text)) return fail(FMX_E_ARG, "bad argument");
+    int dev = 0;
+    int rc = ensure_device(device, &dev);
+    if (rc) return rc;
+    // FileBWTReader.copyReverse (bwtreader.scala:196-211): 0x00 bytes are dropped, the text is reversed
+    std::vector<uint8_t> filtered;
+    const uint8_t *src = text;
+    int64_t flen = len;
+    if (len && std::memchr(text, 0, (size_t)len)) {
+        filtered.reserve((size_t)len);
+        for (int64_t i = 0; i < len; ++i) if (text[i]) filtered.push_back(text[i]);
+        src = filtered.data(); flen = (int64_t)filtered.size();
+    }
+    const int64_t n = flen + 1;
+    if (n >= (1ll << 32) - 1) return fail(FMX_E_UNSUPPORTED, "text too long for 32-bit rows");
+    cudaStream_t st;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    uint8_t *d_fwd = nullptr, *d_rev = nullptr, *d_bwt = nullptr;
+    CU(cudaMalloc(&d_fwd, flen + 16)); CU(cudaMalloc(&d_rev, flen + 16)); CU(cudaMalloc(&d_bwt, n));
+    if (flen) CU(cudaMemcpyAsync(d_fwd, src, flen, cudaMemcpyHostToDevice, st));
+    CU(reverse_bytes(d_fwd, flen, d_rev, st));
+    cudaError_t e = suffix_sort_bwt(d_rev, flen, d_bwt, eof, counts, nullptr, nullptr, st);
+    if (e != cudaSuccess) { cudaFree(d_fwd); cudaFree(d_rev); cudaFree(d_bwt); cudaStreamDestroy(st); return fail(FMX_E_CUDA, "suffix sort failed: %s", cudaGetErrorString(e)); }
+    bwt.resize((size_t)n);
+    CU(cudaMemcpyAsync(bwt.data(), d_bwt, n, cudaMemcpyDeviceToHost, st));
+    if (fm) {
+        uint32_t *d_fm = nullptr;
+        CU(cudaMalloc(&d_fm, n * 4));
+        CU(build_fm_array(d_bwt, n, d_fm, st));
+        fm->resize((size_t)n);
+        CU(cudaMemcpyAsync(fm->data(), d_fm, n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        cudaFree(d_fm);
+    }
+    CU(cudaStreamSynchronize(st));
+    cudaFree(d_fwd); cudaFree(d_rev); cudaFree(d_bwt);
+    cudaStreamDestroy(st);
+    return FMX_OK;
+}
+
+int fmx_build_bwt(const uint8_t *text, int64_t len, uint8_t *bwt_out, int64_t *n_out, int64_t *eof_out, int64_t counts_out[256], int device) {
+    if (!bwt_out || !n_out || !eof_out || !counts_out) return fail(FMX_E_ARG, "null argument");
+    std::vector<uint8_t> bwt;
+    int rc = build_bwt_impl(text, len, device, bwt, eof_out, counts_out, nullptr);
+    if (rc) return rc;
+    std::memcpy(bwt_out, bwt.data(), bwt.size());
+    *n_out = (int64_t)bwt.size();
+    return FMX_OK;
+}
+
+int fmx_build_index_files(const uint8_t *text, int64_t len, const char *base, int big_endian, int write_fm, int device) {
+    if (!base) return fail(FMX_E_ARG, "null argument");
+    std::vector<uint8_t> bwt; std::vector<uint32_t> fm;
+    int64_t eof = 0, counts[256];
+    int rc = build_bwt_impl(text, len, device, bwt, &eof, counts, write_fm ? &fm : nullptr);
+    if (rc) return rc;
+    return write_index_files(strip_extension(base), bwt.data(), (int64_t)bwt.size(), eof, counts, big_endian != 0, write_fm ? fm.data() : nullptr);
+}
+
+}  // extern "C"

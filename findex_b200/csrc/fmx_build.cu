@@ -1,0 +1,360 @@
+// fmx_build.cu — device-side construction: (a) the GPU rank structures from the BWT ("index upload", K0),
+// (b) sampled-suffix-array marks/samples by parallel LF chain walks, (c) suffix sorting of a text by prefix
+// doubling to produce .bwt/.aux for synthetic configs (replaces BWTMerger2.merge,
+// src/main/scala/org/fmindex/bwtmerger.scala:1085-1260, for texts that fit in HBM — any correct suffix
+// sorter yields the same, unique BWT).
+#include "fmx_build.cuh"
+
+#include "fmx_cub.cuh"
+
+namespace fmx {
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+// ======================================================================================================
+// (a) rank structures
+// ======================================================================================================
+__global__ void map_codes_kernel(const uint8_t *__restrict__ bwt, int64_t n, uint32_t eof, const uint8_t *__restrict__ code,
+                                 uint8_t *__restrict__ out) {
+    __shared__ uint8_t sc[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sc[i] = code[i];
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (i == eof) ? (uint8_t)0 : sc[bwt[i]];
+}
+
+// one thread per payload word of one bitvector: bit j of word w = (codes[32w + j] >> bit) & 1
+__global__ void pack_level_kernel(const uint8_t *__restrict__ codes, int64_t n, int bit, uint32_t *__restrict__ blocks,
+                                  int64_t nblk) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nblk * 15) return;
+    const int64_t p0 = w * 32;
+    uint32_t word = 0;
+    if (p0 + 32 <= n) {
+        const uint4 a = reinterpret_cast<const uint4 *>(codes + p0)[0], b = reinterpret_cast<const uint4 *>(codes + p0)[1];
+        const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t m = (v[k] >> bit) & 0x01010101u;                  // bit of each of 4 codes, at bit 0 of each byte
+            word |= (((m & 0x01u) | ((m >> 7) & 0x02u) | ((m >> 14) & 0x04u) | ((m >> 21) & 0x08u))) << (4 * k);
+        }
+    } else {
+        for (int j = 0; j < 32 && p0 + j < n; ++j) word |= (uint32_t)((codes[p0 + j] >> bit) & 1u) << j;
+    }
+    blocks[(w / 15) * 16 + 1 + (w % 15)] = word;
+}
+
+// PLANES: a CTA stages TB blocks' worth of BWT bytes in shared memory and emits that column of every plane
+template <int TB>
+__global__ void __launch_bounds__(256)
+pack_planes_kernel(const uint8_t *__restrict__ bwt, int64_t n, uint32_t eof, const uint8_t *__restrict__ sym, int sigma,
+                   uint32_t *__restrict__ blocks, int64_t nblk) {
+    __shared__ __align__(16) uint8_t tile[TB * 480];
+    const int64_t b0 = (int64_t)blockIdx.x * TB, pos0 = b0 * 480;
+    for (int i = threadIdx.x; i < TB * 480; i += 256) {
+        const int64_t p = pos0 + i;
+        tile[i] = (p < n && p != (int64_t)eof) ? bwt[p] : (uint8_t)0;       // 0 never equals a real symbol
+    }
+    __syncthreads();
+    constexpr int W = TB * 15;
+    for (int idx = threadIdx.x; idx < sigma * W; idx += 256) {
+        const int code = idx / W, w = idx % W;
+        const uint32_t pat = (uint32_t)sym[code] * 0x01010101u;
+        const uint4 a = reinterpret_cast<const uint4 *>(tile + w * 32)[0], b = reinterpret_cast<const uint4 *>(tile + w * 32)[1];
+        const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t word = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t eq = __vcmpeq4(v[k], pat);                           // 0xFF per equal byte
+            word |= (((eq & 0x08040201u) * 0x01010101u) >> 24) << (4 * k);
+        }
+        const int64_t blk = b0 + w / 15;
+        if (blk < nblk) blocks[((int64_t)code * nblk + blk) * 16 + 1 + (w % 15)] = word;
+    }
+}
+
+__global__ void block_popc_kernel(const uint32_t *__restrict__ blocks, int64_t nblk_total, uint32_t *__restrict__ cnt) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk_total) return;
+    const uint4 *p = reinterpret_cast<const uint4 *>(blocks + b * 16);
+    const uint4 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3];
+    cnt[b] = __popc(q0.y) + __popc(q0.z) + __popc(q0.w) + __popc(q1.x) + __popc(q1.y) + __popc(q1.z) + __popc(q1.w) +
+             __popc(q2.x) + __popc(q2.y) + __popc(q2.z) + __popc(q2.w) + __popc(q3.x) + __popc(q3.y) + __popc(q3.z) + __popc(q3.w);
+}
+
+// header of block b of plane p = ones before it inside plane p = pre[p*nblk+b] - pre[p*nblk]
+__global__ void write_headers_kernel(uint32_t *__restrict__ blocks, const uint32_t *__restrict__ pre, int64_t nblk, int64_t nplanes) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk * nplanes) return;
+    blocks[b * 16] = pre[b] - pre[(b / nblk) * nblk];
+}
+
+static cudaError_t finish_headers(uint32_t *d_blocks, int64_t nblk, int64_t nplanes, cudaStream_t st) {
+    const int64_t tot = nblk * nplanes;
+    uint32_t *cnt = nullptr, *pre = nullptr;
+    CK(cudaMallocAsync(&cnt, tot * 4, st));
+    CK(cudaMallocAsync(&pre, tot * 4, st));
+    block_popc_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_blocks, tot, cnt);
+    CK(exclusive_sum_u32(cnt, pre, tot, st));          // total ones over all planes <= n < 2^32: no overflow
+    write_headers_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_blocks, pre, nblk, nplanes);
+    cudaFreeAsync(cnt, st);
+    cudaFreeAsync(pre, st);
+    return cudaGetLastError();
+}
+
+cudaError_t build_wm(const uint8_t *d_bwt, int64_t n, uint32_t eof, const uint8_t *d_code, int levels, uint32_t *d_blocks,
+                     int64_t nblk, cudaStream_t st) {
+    uint8_t *cur = nullptr, *nxt = nullptr;
+    CK(cudaMallocAsync(&cur, n + 64, st));
+    CK(cudaMallocAsync(&nxt, n + 64, st));
+    map_codes_kernel<<<148 * 8, 256, 0, st>>>(d_bwt, n, eof, d_code, cur);
+    for (int l = 0; l < levels; ++l) {
+        const int bit = levels - 1 - l;
+        pack_level_kernel<<<(unsigned)((nblk * 15 + 255) / 256), 256, 0, st>>>(cur, n, bit, d_blocks + (int64_t)l * nblk * 16, nblk);
+        if (l + 1 < levels) {
+            CK(stable_partition_bit_u8(cur, nxt, n, bit, st));
+            uint8_t *t = cur; cur = nxt; nxt = t;
+        }
+    }
+    CK(finish_headers(d_blocks, nblk, levels, st));
+    cudaFreeAsync(cur, st);
+    cudaFreeAsync(nxt, st);
+    return cudaGetLastError();
+}
+
+cudaError_t build_planes(const uint8_t *d_bwt, int64_t n, uint32_t eof, const uint8_t *d_sym, int sigma, uint32_t *d_blocks,
+                         int64_t nblk, cudaStream_t st) {
+    constexpr int TB = 8;
+    pack_planes_kernel<TB><<<(unsigned)((nblk + TB - 1) / TB), 256, 0, st>>>(d_bwt, n, eof, d_sym, sigma, d_blocks, nblk);
+    CK(finish_headers(d_blocks, nblk, sigma, st));
+    return cudaGetLastError();
+}
+
+// ======================================================================================================
+// (b) sampled suffix array by parallel LF chain walks
+// ======================================================================================================
+// Rows k*S (and the eof row) are chain starts.  LF is one n-cycle, so walking from every start to the next
+// start partitions it; the host links the chains from sa[eof] = 0 (util.scala:213-224: sa[eof]=0, and
+// sa[LF(r)] = sa[r]-1 mod n), and a second walk stamps every row whose sa is a multiple of `rate`.
+template <int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+chain_len_kernel(const __grid_constant__ DevIndex ix, uint32_t S, uint32_t nchains, uint32_t eof_chain, uint32_t *__restrict__ next,
+                 uint32_t *__restrict__ len) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    const uint32_t j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= nchains) return;
+    uint32_t r = (j == eof_chain) ? ix.eof : j * S, steps = 0;
+    for (;;) {
+        r = lf_value<1, LAYOUT>(ix, tb, ix.bwt[r], r);
+        ++steps;
+        if (r == ix.eof) { next[j] = eof_chain; break; }
+        if (r % S == 0) { next[j] = r / S; break; }
+    }
+    len[j] = steps;
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+chain_mark_kernel(const __grid_constant__ DevIndex ix, uint32_t S, uint32_t nchains, uint32_t eof_chain, const uint32_t *__restrict__ start_sa,
+                  uint32_t rate, uint32_t *__restrict__ mark_blocks, uint2 *__restrict__ pairs, unsigned long long *n_pairs) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    const uint32_t j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= nchains) return;
+    uint32_t r = (j == eof_chain) ? ix.eof : j * S, v = start_sa[j];
+    for (;;) {
+        if (v % rate == 0) {
+            const uint32_t b = r / kBitsPerBlock, o = r - b * kBitsPerBlock;
+            atomicOr(&mark_blocks[(uint64_t)b * 16 + 1 + (o >> 5)], 1u << (o & 31));
+            pairs[atomicAdd(n_pairs, 1ull)] = make_uint2(r, v);
+        }
+        r = lf_value<1, LAYOUT>(ix, tb, ix.bwt[r], r);
+        v = (v == 0) ? ix.n - 1 : v - 1;
+        if (r == ix.eof || r % S == 0) break;
+    }
+}
+
+__global__ void scatter_samples_kernel(const uint4 *__restrict__ mark, const uint2 *__restrict__ pairs, int64_t np, uint32_t *__restrict__ samples) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    const uint2 p = pairs[i];
+    samples[rank_one<1>(mark, p.x, nullptr)] = p.y;
+}
+
+cudaError_t build_sa_samples(const DevIndex &ix, int layout, int rate, uint32_t *d_mark_blocks, int64_t nblk, uint32_t *d_samples,
+                             int64_t n_samples, cudaStream_t st, std::string &err) {
+    const uint64_t n = ix.n;
+    uint64_t target = n < (1u << 20) ? n : (1u << 20);
+    uint32_t S = (uint32_t)((n + target - 1) / target);
+    if (S == 0) S = 1;
+    const uint32_t base_chains = (uint32_t)((n + S - 1) / S);
+    const bool eof_is_grid = (ix.eof % S) == 0;
+    const uint32_t eof_chain = eof_is_grid ? ix.eof / S : base_chains;
+    const uint32_t nchains = eof_is_grid ? base_chains : base_chains + 1;
+
+    uint32_t *d_next, *d_len, *d_start;
+    CK(cudaMallocAsync(&d_next, nchains * 4ull, st));
+    CK(cudaMallocAsync(&d_len, nchains * 4ull, st));
+    CK(cudaMallocAsync(&d_start, nchains * 4ull, st));
+    const unsigned grid = (nchains + kThreads - 1) / kThreads;
+    if (layout == FMX_LAYOUT_PLANES) chain_len_kernel<FMX_LAYOUT_PLANES><<<grid, kThreads, 0, st>>>(ix, S, nchains, eof_chain, d_next, d_len);
+    else chain_len_kernel<FMX_LAYOUT_WM><<<grid, kThreads, 0, st>>>(ix, S, nchains, eof_chain, d_next, d_len);
+    std::vector<uint32_t> nx(nchains), ln(nchains), sv(nchains, 0);
+    CK(cudaMemcpyAsync(nx.data(), d_next, nchains * 4ull, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ln.data(), d_len, nchains * 4ull, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    {   // link the chains: sa[eof] = 0, each LF step decrements the text position (mod n)
+        uint64_t total = 0; uint32_t cur = eof_chain; uint64_t v = 0; uint32_t visited = 0;
+        do {
+            sv[cur] = (uint32_t)v;
+            total += ln[cur];
+            v = (v + n - (ln[cur] % n)) % n;
+            cur = nx[cur];
+            ++visited;
+        } while (cur != eof_chain && visited <= nchains);
+        if (cur != eof_chain || visited != nchains || total != n) {
+            err = "BWT is not a single LF cycle (corrupt .bwt/.aux?)";
+            cudaFreeAsync(d_next, st); cudaFreeAsync(d_len, st); cudaFreeAsync(d_start, st);
+            return cudaErrorInvalidValue;
+        }
+    }
+    CK(cudaMemcpyAsync(d_start, sv.data(), nchains * 4ull, cudaMemcpyHostToDevice, st));
+    uint2 *d_pairs; unsigned long long *d_np;
+    CK(cudaMallocAsync(&d_pairs, (size_t)n_samples * 8, st));
+    CK(cudaMallocAsync(&d_np, 8, st));
+    CK(cudaMemsetAsync(d_np, 0, 8, st));
+    CK(cudaMemsetAsync(d_mark_blocks, 0, (size_t)nblk * 64, st));
+    if (layout == FMX_LAYOUT_PLANES) chain_mark_kernel<FMX_LAYOUT_PLANES><<<grid, kThreads, 0, st>>>(ix, S, nchains, eof_chain, d_start, (uint32_t)rate, d_mark_blocks, d_pairs, d_np);
+    else chain_mark_kernel<FMX_LAYOUT_WM><<<grid, kThreads, 0, st>>>(ix, S, nchains, eof_chain, d_start, (uint32_t)rate, d_mark_blocks, d_pairs, d_np);
+    CK(finish_headers(d_mark_blocks, nblk, 1, st));
+    unsigned long long np = 0;
+    CK(cudaMemcpyAsync(&np, d_np, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if ((int64_t)np != n_samples) { err = "sample count mismatch"; return cudaErrorInvalidValue; }
+    scatter_samples_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(d_mark_blocks), d_pairs, (int64_t)np, d_samples);
+    cudaFreeAsync(d_pairs, st); cudaFreeAsync(d_np, st);
+    cudaFreeAsync(d_next, st); cudaFreeAsync(d_len, st); cudaFreeAsync(d_start, st);
+    return cudaGetLastError();
+}
+
+// ======================================================================================================
+// (c) suffix sorting by prefix doubling -> BWT
+// ======================================================================================================
+// t = T' without terminator (len bytes, none zero); suffix `len` is the '$' suffix.
+__global__ void init_keys_kernel(const uint8_t *__restrict__ t, int64_t len, uint64_t *__restrict__ key, uint32_t *__restrict__ sa) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > len) return;
+    uint64_t k = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) k = (k << 8) | (uint64_t)((i + j < len) ? t[i + j] : 0);
+    key[i] = k;
+    sa[i] = (uint32_t)i;
+}
+__global__ void head_flags_kernel(const uint64_t *__restrict__ key, int64_t n, uint32_t *__restrict__ head) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    head[j] = (j == 0 || key[j] != key[j - 1]) ? (uint32_t)j : 0u;
+}
+__global__ void assign_rank_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ grp, int64_t n, uint32_t *__restrict__ rank,
+                                   unsigned long long *n_singleton_breaks) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    rank[sa[j]] = grp[j];
+    if (grp[j] != (uint32_t)j) atomicAdd(n_singleton_breaks, 1ull);          // some group has more than one member
+}
+__global__ void doubled_keys_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ rank, int64_t n, int64_t h, uint64_t *__restrict__ key) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int64_t i = sa[j];
+    const uint64_t lo = (i + h < n) ? (uint64_t)rank[i + h] + 1ull : 0ull;
+    key[j] = ((uint64_t)rank[i] << 32) | lo;
+}
+__global__ void emit_bwt_kernel(const uint8_t *__restrict__ t, const uint32_t *__restrict__ sa, int64_t n, uint8_t *__restrict__ bwt, unsigned long long *eof) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t s = sa[j];
+    if (s == 0) { bwt[j] = 0; *eof = (unsigned long long)j; }
+    else bwt[j] = t[s - 1];
+}
+__global__ void histogram_kernel(const uint8_t *__restrict__ t, int64_t len, unsigned long long *__restrict__ counts) {
+    __shared__ unsigned int h[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) atomicAdd(&h[t[i]], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) if (h[i]) atomicAdd(&counts[i], (unsigned long long)h[i]);
+}
+__global__ void reverse_kernel(const uint8_t *__restrict__ src, int64_t len, uint8_t *__restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) dst[i] = src[len - 1 - i];
+}
+__global__ void fm_iota_kernel(uint32_t *v, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (uint32_t)i;
+}
+
+cudaError_t reverse_bytes(const uint8_t *d_src, int64_t len, uint8_t *d_dst, cudaStream_t st) {
+    if (len > 0) reverse_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(d_src, len, d_dst);
+    return cudaGetLastError();
+}
+
+cudaError_t suffix_sort_bwt(const uint8_t *d_t, int64_t len, uint8_t *d_bwt, int64_t *eof_out, int64_t counts_out[256],
+                            uint32_t *d_sa_out, int *rounds_out, cudaStream_t st) {
+    const int64_t n = len + 1;
+    if (n >= (1ll << 32)) return cudaErrorInvalidValue;
+    uint64_t *k0, *k1; uint32_t *s0, *s1, *rank, *grp; unsigned long long *d_flag, *d_counts;
+    CK(cudaMallocAsync(&k0, n * 8, st)); CK(cudaMallocAsync(&k1, n * 8, st));
+    CK(cudaMallocAsync(&s0, n * 4, st)); CK(cudaMallocAsync(&s1, n * 4, st));
+    CK(cudaMallocAsync(&rank, n * 4, st)); CK(cudaMallocAsync(&grp, n * 4, st));
+    CK(cudaMallocAsync(&d_flag, 16, st)); CK(cudaMallocAsync(&d_counts, 256 * 8, st));
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    init_keys_kernel<<<grid, 256, 0, st>>>(d_t, len, k0, s0);
+    CK(sort_pairs_u64_u32(k0, k1, s0, s1, n, 0, 64, st));
+    int64_t h = 8; int rounds = 1;
+    for (;;) {
+        // k1/s1 hold the sorted (key, suffix) pairs
+        head_flags_kernel<<<grid, 256, 0, st>>>(k1, n, grp);
+        CK(inclusive_max_u32(grp, grp, n, st));
+        CK(cudaMemsetAsync(d_flag, 0, 16, st));
+        assign_rank_kernel<<<grid, 256, 0, st>>>(s1, grp, n, rank, d_flag);
+        unsigned long long dup = 0;
+        CK(cudaMemcpyAsync(&dup, d_flag, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (dup == 0 || h >= n) break;
+        doubled_keys_kernel<<<grid, 256, 0, st>>>(s1, rank, n, h, k0);
+        CK(sort_pairs_u64_u32(k0, k1, s1, s0, n, 0, 64, st));
+        uint32_t *t = s0; s0 = s1; s1 = t;
+        h *= 2; ++rounds;
+    }
+    CK(cudaMemsetAsync(d_flag, 0, 16, st));
+    emit_bwt_kernel<<<grid, 256, 0, st>>>(d_t, s1, n, d_bwt, d_flag);
+    CK(cudaMemsetAsync(d_counts, 0, 256 * 8, st));
+    if (len > 0) histogram_kernel<<<148 * 4, 256, 0, st>>>(d_t, len, d_counts);
+    unsigned long long eof = 0, cnt[256];
+    CK(cudaMemcpyAsync(&eof, d_flag, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cnt, d_counts, 256 * 8, cudaMemcpyDeviceToHost, st));
+    if (d_sa_out) CK(cudaMemcpyAsync(d_sa_out, s1, n * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    *eof_out = (int64_t)eof;
+    for (int i = 0; i < 256; ++i) counts_out[i] = (int64_t)cnt[i];
+    if (rounds_out) *rounds_out = rounds;
+    cudaFreeAsync(k0, st); cudaFreeAsync(k1, st); cudaFreeAsync(s0, st); cudaFreeAsync(s1, st);
+    cudaFreeAsync(rank, st); cudaFreeAsync(grp, st); cudaFreeAsync(d_flag, st); cudaFreeAsync(d_counts, st);
+    return cudaGetLastError();
+}
+
+// FMCreator.create (bwtmerger.scala:452-532): fm = stable counting sort of rows by BWT byte (eof row -> 0)
+cudaError_t build_fm_array(const uint8_t *d_bwt, int64_t n, uint32_t *d_fm, cudaStream_t st) {
+    uint8_t *kout; uint32_t *iota;
+    CK(cudaMallocAsync(&kout, n, st));
+    CK(cudaMallocAsync(&iota, n * 4, st));
+    fm_iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(iota, n);
+    CK(sort_pairs_u8_u32(d_bwt, kout, iota, d_fm, n, st));
+    cudaFreeAsync(kout, st); cudaFreeAsync(iota, st);
+    return cudaGetLastError();
+}
+
+}  // namespace fmx

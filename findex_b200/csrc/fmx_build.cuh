@@ -1,0 +1,25 @@
+// fmx_build.cuh — device-side construction entry points (definitions in fmx_build.cu)
+#pragma once
+#include <string>
+#include <vector>
+
+#include "fmx_kernels.cuh"
+
+namespace fmx {
+
+// wavelet matrix: d_blocks holds levels*nblk rank blocks (64 B each), nblk = n/480 + 1
+cudaError_t build_wm(const uint8_t *d_bwt, int64_t n, uint32_t eof, const uint8_t *d_code, int levels, uint32_t *d_blocks,
+                     int64_t nblk, cudaStream_t st);
+// per-symbol planes: d_blocks holds sigma*nblk rank blocks; d_sym[code] = byte value
+cudaError_t build_planes(const uint8_t *d_bwt, int64_t n, uint32_t eof, const uint8_t *d_sym, int sigma, uint32_t *d_blocks,
+                         int64_t nblk, cudaStream_t st);
+// sampled SA: marks rows with sa % rate == 0 (rank blocks, nblk) and stores their sa values in mark-rank order
+cudaError_t build_sa_samples(const DevIndex &ix, int layout, int rate, uint32_t *d_mark_blocks, int64_t nblk, uint32_t *d_samples,
+                             int64_t n_samples, cudaStream_t st, std::string &err);
+// suffix sort of t+'$' (t has no zero bytes) -> BWT, eof row, byte counts; optionally the suffix array
+cudaError_t suffix_sort_bwt(const uint8_t *d_t, int64_t len, uint8_t *d_bwt, int64_t *eof_out, int64_t counts_out[256],
+                            uint32_t *d_sa_out, int *rounds_out, cudaStream_t st);
+cudaError_t reverse_bytes(const uint8_t *d_src, int64_t len, uint8_t *d_dst, cudaStream_t st);
+cudaError_t build_fm_array(const uint8_t *d_bwt, int64_t n, uint32_t *d_fm, cudaStream_t st);
+
+}  // namespace fmx

@@ -1,0 +1,213 @@
+// fmx_device.cuh — device-side view of the index and the rank primitives every kernel shares.
+//
+// Rank block (64 B = one aligned 2-sector fetch): word 0 = number of 1-bits before the block,
+// words 1..15 = 480 payload bits (bit j of the block lives in word 1 + j/32, bit j%32).
+// rank1(pos) therefore touches exactly one block: block = pos / 480, offset = pos % 480.
+//
+// Two layouts are built from those blocks:
+//   WM     : wavelet matrix over the dense symbol codes, `levels` = ceil(log2 sigma) bitvectors, one
+//            block per level per rank (the structure north_star names);
+//   PLANES : one bitvector per symbol, one block per rank — trades HBM capacity (sigma*n/7.5 bytes)
+//            for 1/levels of the random fetches.
+// The '$' row (eof) is not a symbol: WM stores it under code 0 and subtracts it back out, PLANES never
+// sets it; rank of byte 0 is (pos > eof).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/fmgpu.h"
+
+namespace fmx {
+
+constexpr uint32_t kBitsPerBlock = 480;
+constexpr int kCodeAbsent = 0xFF;
+
+struct DevIndex {
+    const uint4   *blocks;      // [levels | sigma][stride] rank blocks
+    uint64_t       stride;      // blocks per level / plane
+    const uint8_t *bwt;         // n bytes, eof -> 0
+    const uint32_t *C;          // 257: C[c] = cf(c), C[256] = n
+    const uint32_t *base;       // 256: PLANES: C[c] ; WM: C[c] - start_final[code[c]] (mod 2^32)
+    const uint8_t *code;        // 256: byte -> dense code, kCodeAbsent if the byte does not occur
+    const uint4   *mark;        // sampled-row marker bitvector (rank blocks) or nullptr
+    const uint32_t *samples;    // sa value of the k-th marked row
+    uint32_t n, eof;
+    int32_t  layout, levels;
+    uint32_t z[8];              // WM: zeros per level
+};
+
+struct SharedTables {
+    uint32_t C[257];
+    uint32_t base[256];
+    uint8_t  code[256];
+};
+
+__device__ __forceinline__ void load_tables(SharedTables &s, const DevIndex &ix) {
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) s.C[i] = ix.C[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s.base[i] = ix.base[i]; s.code[i] = ix.code[i]; }
+}
+
+__device__ __forceinline__ uint4 ldg128(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// popcount of the bits of a 64-bit lane word that lie below virtual bit `v` of the block, where this
+// word covers virtual bits [first, first+64).  Virtual bit 32+j is payload bit j (bits 0..31 = header).
+__device__ __forceinline__ uint32_t popc_below64(uint64_t w, int v, int first) {
+    int t = v - first;
+    t = t < 0 ? 0 : (t > 64 ? 64 : t);
+    uint64_t mask = (t >= 64) ? ~0ull : ((1ull << t) - 1ull);
+    return __popcll(w & mask);
+}
+
+// One lane's share of a block: WORDS = 16/G consecutive 32-bit words starting at word lane*WORDS.
+template <int G> struct LaneBlock { uint4 v[4 / G]; };
+
+template <int G>
+__device__ __forceinline__ LaneBlock<G> load_block(const uint4 *bv, uint32_t blk, int lane) {
+    LaneBlock<G> r;
+    const uint4 *p = bv + (uint64_t)blk * 4 + lane * (4 / G);
+#pragma unroll
+    for (int i = 0; i < 4 / G; ++i) r.v[i] = ldg128(p + i);
+    return r;
+}
+
+// lane-local part of rank: ones among payload bits [0, off) that this lane holds
+template <int G>
+__device__ __forceinline__ uint32_t lane_rank(const LaneBlock<G> &b, uint32_t off, int lane) {
+    const int v = (int)off + 32;
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 4 / G; ++i) {
+        int first = (lane * (4 / G) + i) * 128;
+        uint64_t lo = ((uint64_t)b.v[i].y << 32) | b.v[i].x;
+        uint64_t hi = ((uint64_t)b.v[i].w << 32) | b.v[i].z;
+        if (first == 0) lo &= ~0xFFFFFFFFull;                      // header word is not payload
+        s += popc_below64(lo, v, first) + popc_below64(hi, v, first + 64);
+    }
+    return s;
+}
+
+template <int G> __device__ __forceinline__ uint32_t group_mask() {
+    if (G == 1) return 0xFFFFFFFFu;          // unused
+    const uint32_t lane = threadIdx.x & 31;
+    return ((1u << G) - 1u) << (lane & ~(G - 1));
+}
+
+template <int G> __device__ __forceinline__ uint32_t group_sum(uint32_t x, uint32_t mask) {
+    if (G >= 2) x += __shfl_xor_sync(mask, x, 1);
+    if (G >= 4) x += __shfl_xor_sync(mask, x, 2);
+    return x;
+}
+
+// rank1 at two positions of the same bitvector; one block fetch when they share a block.
+// All G lanes of the group call this together (group-uniform control flow).  `touched` counts
+// distinct blocks for the roofline accounting when STATS.
+template <int G, bool STATS>
+__device__ __forceinline__ void rank_pair(const uint4 *bv, uint32_t pa, uint32_t pb, uint32_t &ra, uint32_t &rb,
+                                          uint32_t &touched) {
+    const int lane = (G == 1) ? 0 : (threadIdx.x & (G - 1));
+    const uint32_t mask = group_mask<G>();
+    const uint32_t ba = pa / kBitsPerBlock, oa = pa - ba * kBitsPerBlock;
+    const uint32_t bb = pb / kBitsPerBlock, ob = pb - bb * kBitsPerBlock;
+    LaneBlock<G> A = load_block<G>(bv, ba, lane);
+    LaneBlock<G> B = A;
+    if (bb != ba) B = load_block<G>(bv, bb, lane);
+    if (STATS) touched += (bb != ba) ? 2u : 1u;
+    uint32_t ha = A.v[0].x, hb = B.v[0].x;
+    uint32_t sa = lane_rank<G>(A, oa, lane), sb = lane_rank<G>(B, ob, lane);
+    if (G > 1) {
+        sa = group_sum<G>(sa, mask);
+        sb = group_sum<G>(sb, mask);
+        ha = __shfl_sync(mask, ha, 0, G);
+        hb = __shfl_sync(mask, hb, 0, G);
+    }
+    ra = ha + sa;
+    rb = hb + sb;
+}
+
+// single-position rank (+ optionally the bit at that position) — used by LF walks
+template <int G>
+__device__ __forceinline__ uint32_t rank_one(const uint4 *bv, uint32_t p, uint32_t *bit_out) {
+    const int lane = (G == 1) ? 0 : (threadIdx.x & (G - 1));
+    const uint32_t mask = group_mask<G>();
+    const uint32_t b = p / kBitsPerBlock, o = p - b * kBitsPerBlock;
+    LaneBlock<G> A = load_block<G>(bv, b, lane);
+    uint32_t h = A.v[0].x, s = lane_rank<G>(A, o, lane);
+    uint32_t bit = 0;
+    if (bit_out) {
+        const int w = 1 + (int)(o >> 5);                   // word holding payload bit o
+#pragma unroll
+        for (int i = 0; i < 4 / G; ++i) {
+            const int rel = w - (lane * (4 / G) + i) * 4;  // position inside this lane's i-th uint4
+            if (rel >= 0 && rel < 4) {
+                const uint4 q = A.v[i];
+                const uint32_t word = rel == 0 ? q.x : rel == 1 ? q.y : rel == 2 ? q.z : q.w;
+                bit = (word >> (o & 31)) & 1u;
+            }
+        }
+    }
+    if (G > 1) {
+        s = group_sum<G>(s, mask);
+        h = __shfl_sync(mask, h, 0, G);
+        if (bit_out) bit = group_sum<G>(bit, mask);
+    }
+    if (bit_out) *bit_out = bit;
+    return h + s;
+}
+
+// ---- one backward step: (sp,ep) -> (C[c]+rank_c(sp), C[c]+rank_c(ep))   findex.scala:32-36 ------------
+template <int G, int LAYOUT, bool STATS>
+__device__ __forceinline__ void backward_step(const DevIndex &ix, const SharedTables &t, uint32_t c, uint32_t &sp,
+                                              uint32_t &ep, uint32_t &touched) {
+    const uint32_t code = t.code[c];
+    if (c == 0) {                                   // '$': occurs once, at row eof; C[0] = 0
+        sp = sp > ix.eof ? 1u : 0u;
+        ep = ep > ix.eof ? 1u : 0u;
+        return;
+    }
+    if (code == kCodeAbsent) { sp = ep = t.C[c]; return; }
+    if (LAYOUT == FMX_LAYOUT_PLANES) {
+        uint32_t ra, rb;
+        rank_pair<G, STATS>(ix.blocks + (uint64_t)code * ix.stride * 4, sp, ep, ra, rb, touched);
+        sp = t.base[c] + ra;
+        ep = t.base[c] + rb;
+    } else {
+        uint32_t p = sp, q = ep;
+        const int L = ix.levels;
+        for (int l = 0; l < L; ++l) {
+            uint32_t ra, rb;
+            rank_pair<G, STATS>(ix.blocks + (uint64_t)l * ix.stride * 4, p, q, ra, rb, touched);
+            if ((code >> (L - 1 - l)) & 1u) { p = ix.z[l] + ra; q = ix.z[l] + rb; }
+            else { p -= ra; q -= rb; }
+        }
+        if (code == 0) { p -= (sp > ix.eof); q -= (ep > ix.eof); }     // the '$' row is filed under code 0
+        sp = t.base[c] + p;
+        ep = t.base[c] + q;
+    }
+}
+
+// rank_c(pos) for a single position (occ / LF).  Returns C[c] + rank.
+template <int G, int LAYOUT>
+__device__ __forceinline__ uint32_t lf_value(const DevIndex &ix, const SharedTables &t, uint32_t c, uint32_t pos) {
+    const uint32_t code = t.code[c];
+    if (c == 0) return pos > ix.eof ? 1u : 0u;
+    if (code == kCodeAbsent) return t.C[c];
+    if (LAYOUT == FMX_LAYOUT_PLANES) {
+        return t.base[c] + rank_one<G>(ix.blocks + (uint64_t)code * ix.stride * 4, pos, nullptr);
+    } else {
+        uint32_t p = pos;
+        const int L = ix.levels;
+        for (int l = 0; l < L; ++l) {
+            uint32_t r = rank_one<G>(ix.blocks + (uint64_t)l * ix.stride * 4, p, nullptr);
+            if ((code >> (L - 1 - l)) & 1u) p = ix.z[l] + r; else p -= r;
+        }
+        if (code == 0) p -= (pos > ix.eof);
+        return t.base[c] + p;
+    }
+}
+
+}  // namespace fmx

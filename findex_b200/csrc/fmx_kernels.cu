@@ -1,0 +1,520 @@
+// fmx_kernels.cu — the search kernels of libfmgpu (sm_100a).
+//
+//   K1 count         : SuffixAlgo.search            src/main/scala/org/fmindex/findex.scala:15-31
+//      prev_range    : SuffixAlgo.getPrevRange      findex.scala:32-36
+//      interval      : getIntervalPrevRange         findex.scala:37-51
+//      occ           : NaiveFMSearcher.occ          bwtmerger.scala:354-375
+//      lf/prev_substr: getPrevI / prevSubstr        bwtmerger.scala:386-389, 409-419
+//   K2 locate        : sa[] of bwtFm2sa             util.scala:213-224, via sampled rows + LF walk
+//   K3 regex level   : ReTree._matchSA loop body    re2/retree.scala:618-653, one BFS level per launch
+//   K4 gather bench  : the random-64-B-gather roofline denominator
+//
+// All of them are HBM-latency/bandwidth bound integer kernels: G (1, 2 or 4) lanes cooperate on one
+// query so that a 64-byte rank block arrives as one coalesced request; the two ends of the interval are
+// fetched together (two independent loads in flight per lane) and share the fetch when they fall into the
+// same block.  Nothing here is GEMM-shaped, so no tensor-core path exists by design.
+#include "fmx_kernels.cuh"
+
+namespace fmx {
+
+// =====================================================================================================
+// K1: count
+// =====================================================================================================
+template <int G, int LAYOUT, bool STATS, typename OutT>
+__global__ void __launch_bounds__(kThreads)
+count_fixed_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, int len, long long m,
+                   OutT *__restrict__ sp_out, OutT *__restrict__ ep_out, unsigned long long *stats) {
+    __shared__ SharedTables tb;
+    extern __shared__ __align__(16) uint8_t spat[];
+    constexpr int QPB = kThreads / G;                     // queries per CTA
+    load_tables(tb, ix);
+
+    const long long q0 = (long long)blockIdx.x * QPB;
+    const int nq = (int)((m - q0) < (long long)QPB ? (m - q0) : (long long)QPB);
+    {   // stage this CTA's patterns (contiguous bytes) into shared memory, 16 B per thread when aligned
+        const uint8_t *src = pat + q0 * len;
+        const int nbytes = nq * len;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            const int nvec = nbytes >> 4;
+            for (int i = threadIdx.x; i < nvec; i += kThreads)
+                reinterpret_cast<uint4 *>(spat)[i] = ldg128(reinterpret_cast<const uint4 *>(src) + i);
+            for (int i = (nvec << 4) + threadIdx.x; i < nbytes; i += kThreads) spat[i] = src[i];
+        } else {
+            for (int i = threadIdx.x; i < nbytes; i += kThreads) spat[i] = src[i];
+        }
+    }
+    __syncthreads();
+
+    const int g = threadIdx.x / G;
+    const bool active = g < nq;
+    const uint8_t *p = spat + g * len;
+    uint32_t sp = 0, ep = active ? ix.n : 0u, touched = 0, steps = 0;
+    int i = len - 1;
+    if (active && i >= 0) {            // first step from (0,n): rank_c(0) = 0 and rank_c(n) = count(c): no memory
+        const uint32_t c = p[i];
+        sp = tb.C[c];
+        ep = tb.C[c + 1];
+        --i;
+        if (STATS) ++steps;
+    }
+    for (; i >= 0; --i) {
+        if (sp < ep) {                 // findex.scala:20 — leave the loop as soon as the interval empties
+            backward_step<G, LAYOUT, STATS>(ix, tb, p[i], sp, ep, touched);
+            if (STATS) ++steps;
+        }
+        if (__all_sync(0xFFFFFFFFu, !(sp < ep))) break;
+    }
+    if (active && (threadIdx.x % G) == 0) {
+        const bool hit = sp < ep;
+        sp_out[q0 + g] = hit ? (OutT)sp : (OutT)0;
+        ep_out[q0 + g] = hit ? (OutT)ep : (OutT)0;
+    }
+    if (STATS) {
+        if ((threadIdx.x % G) != 0) { touched = 0; steps = 0; }
+        for (int o = 16; o; o >>= 1) {
+            touched += __shfl_xor_sync(0xFFFFFFFFu, touched, o);
+            steps += __shfl_xor_sync(0xFFFFFFFFu, steps, o);
+        }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&stats[0], (unsigned long long)touched); atomicAdd(&stats[1], (unsigned long long)steps); }
+    }
+}
+
+template <int G, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+count_var_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, const long long *__restrict__ off,
+                 long long m, long long *__restrict__ sp_out, long long *__restrict__ ep_out) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    constexpr int QPB = kThreads / G;
+    const long long q = (long long)blockIdx.x * QPB + threadIdx.x / G;
+    const bool active = q < m;
+    long long lo = 0, hi = 0;
+    if (active) { lo = off[q]; hi = off[q + 1]; }
+    uint32_t sp = 0, ep = active ? ix.n : 0u, touched = 0;
+    for (long long i = hi - 1; ; --i) {
+        const bool go = (i >= lo) && (sp < ep);
+        if (go) backward_step<G, LAYOUT, false>(ix, tb, __ldg(pat + i), sp, ep, touched);
+        if (__all_sync(0xFFFFFFFFu, !go)) break;
+    }
+    if (active && (threadIdx.x % G) == 0) {
+        const bool hit = sp < ep;
+        sp_out[q] = hit ? (long long)sp : 0;
+        ep_out[q] = hit ? (long long)ep : 0;
+    }
+}
+
+// =====================================================================================================
+// element-wise operator calls
+// =====================================================================================================
+template <int G, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+occ_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ c, const long long *__restrict__ key, long long m,
+           long long *__restrict__ out) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    const long long q = (long long)blockIdx.x * (kThreads / G) + threadIdx.x / G;
+    if (q >= m) return;                                   // group-uniform
+    long long k = key[q] + 1;                             // occ(c,key) = rank_c(key+1)
+    k = k < 0 ? 0 : (k > (long long)ix.n ? (long long)ix.n : k);
+    const uint32_t cc = c[q];
+    const uint32_t v = lf_value<G, LAYOUT>(ix, tb, cc, (uint32_t)k);
+    if ((threadIdx.x % G) == 0) out[q] = (long long)(v - tb.C[cc]);
+}
+
+template <int G, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+prev_range_kernel(const __grid_constant__ DevIndex ix, const long long *__restrict__ sp, const long long *__restrict__ ep,
+                  const uint8_t *__restrict__ c, long long m, long long *__restrict__ sp1, long long *__restrict__ ep1) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    const long long q = (long long)blockIdx.x * (kThreads / G) + threadIdx.x / G;
+    if (q >= m) return;
+    uint32_t a = (uint32_t)sp[q], b = (uint32_t)ep[q], touched = 0;
+    backward_step<G, LAYOUT, false>(ix, tb, c[q], a, b, touched);
+    if ((threadIdx.x % G) == 0) { sp1[q] = a; ep1[q] = b; }
+}
+
+template <int G, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+interval_prev_range_kernel(const __grid_constant__ DevIndex ix, uint32_t sp, uint32_t ep, int cstart, int cend,
+                           long long *__restrict__ sp1, long long *__restrict__ ep1) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    const int q = blockIdx.x * (kThreads / G) + threadIdx.x / G;
+    if (q > cend - cstart) return;
+    uint32_t a = sp, b = ep, touched = 0;
+    backward_step<G, LAYOUT, false>(ix, tb, (uint32_t)(cstart + q), a, b, touched);
+    if ((threadIdx.x % G) == 0) { sp1[q] = a; ep1[q] = b; }
+}
+
+template <int G, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+lf_kernel(const __grid_constant__ DevIndex ix, const long long *__restrict__ row, long long m, long long *__restrict__ out) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    const long long q = (long long)blockIdx.x * (kThreads / G) + threadIdx.x / G;
+    if (q >= m) return;
+    const uint32_t r = (uint32_t)row[q];
+    const uint32_t c = ix.bwt[r];                          // bwt[eof] is stored as 0
+    const uint32_t v = lf_value<G, LAYOUT>(ix, tb, c, r);
+    if ((threadIdx.x % G) == 0) out[q] = v;
+}
+
+template <int G, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+prev_substr_kernel(const __grid_constant__ DevIndex ix, const long long *__restrict__ row, long long m, int len,
+                   uint8_t *__restrict__ out) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    const long long q = (long long)blockIdx.x * (kThreads / G) + threadIdx.x / G;
+    if (q >= m) return;
+    uint32_t r = (uint32_t)row[q];
+    for (int k = 0; k < len; ++k) {
+        const uint32_t c = ix.bwt[r];
+        if ((threadIdx.x % G) == 0) out[q * len + k] = (uint8_t)c;
+        r = lf_value<G, LAYOUT>(ix, tb, c, r);
+    }
+}
+
+// FL step (getNextI, bwtmerger.scala:390-392: fm[i]) without the 4n-byte .fm array: the F-column symbol of row i
+// is the c with C[c] <= i < C[c+1]; the answer is the row of its (i-C[c])-th occurrence in the BWT, found by
+// binary search on rank_c.
+template <int G, int LAYOUT>
+__device__ __forceinline__ uint32_t fl_step(const DevIndex &ix, const SharedTables &tb, uint32_t i) {
+    int lo = 0, hi = 255;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tb.C[mid] <= i) lo = mid; else hi = mid - 1; }
+    const uint32_t c = (uint32_t)lo;
+    if (c == 0) return ix.eof;
+    const uint32_t want = i - tb.C[c] + 1;
+    uint32_t a = 0, b = ix.n - 1;
+    while (a < b) {
+        const uint32_t mid = a + ((b - a) >> 1);
+        const uint32_t r = lf_value<G, LAYOUT>(ix, tb, c, mid + 1) - tb.C[c];
+        if (r >= want) b = mid; else a = mid + 1;
+    }
+    return a;
+}
+
+template <int G, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+fl_kernel(const __grid_constant__ DevIndex ix, const long long *__restrict__ row, long long m, long long *__restrict__ out) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    const long long q = (long long)blockIdx.x * (kThreads / G) + threadIdx.x / G;
+    if (q >= m) return;
+    const uint32_t v = fl_step<G, LAYOUT>(ix, tb, (uint32_t)row[q]);
+    if ((threadIdx.x % G) == 0) out[q] = v;
+}
+
+// nextSubstr (bwtmerger.scala:394-405): bytes in walk order (the host reverses them), stops after the '\0'
+template <int G, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+next_substr_kernel(const __grid_constant__ DevIndex ix, const long long *__restrict__ row, long long m, int len,
+                   uint8_t *__restrict__ out, int *__restrict__ out_len) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    const long long q = (long long)blockIdx.x * (kThreads / G) + threadIdx.x / G;
+    if (q >= m) return;
+    uint32_t cp = fl_step<G, LAYOUT>(ix, tb, (uint32_t)row[q]);
+    int k = 0;
+    for (; k < len; ++k) {
+        const uint32_t b = ix.bwt[cp];
+        if ((threadIdx.x % G) == 0) out[q * len + k] = (uint8_t)b;
+        if (b == 0) { ++k; break; }
+        cp = fl_step<G, LAYOUT>(ix, tb, cp);
+    }
+    if ((threadIdx.x % G) == 0) out_len[q] = k;
+}
+
+// =====================================================================================================
+// K2: locate — one group per occurrence, LF-walk to the nearest sampled row
+// =====================================================================================================
+template <int G, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+locate_kernel(const __grid_constant__ DevIndex ix, const long long *__restrict__ sp, const long long *__restrict__ off,
+              long long m, long long total, uint32_t *__restrict__ pos) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    const long long t = (long long)blockIdx.x * (kThreads / G) + threadIdx.x / G;
+    if (t >= total) return;
+    // owning query: last q with off[q] <= t
+    long long lo = 0, hi = m;
+    while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (off[mid] <= t) lo = mid; else hi = mid; }
+    uint32_t r = (uint32_t)(sp[lo] + (t - off[lo]));
+    uint32_t k = 0;
+    for (;;) {
+        uint32_t bit;
+        const uint32_t mr = rank_one<G>(ix.mark, r, &bit);
+        if (bit) {                                         // row eof (sa = 0) is always sampled, so '$' is never stepped over
+            if ((threadIdx.x % G) == 0) pos[t] = ix.samples[mr] + k;
+            return;
+        }
+        r = lf_value<G, LAYOUT>(ix, tb, ix.bwt[r], r);
+        ++k;
+    }
+}
+
+// =====================================================================================================
+// K3: regex — one breadth-first level of the Glushkov traversal
+// =====================================================================================================
+template <int G, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+regex_level_kernel(const __grid_constant__ DevIndex ix, RegexTables rt, const FrontierItem *__restrict__ in, long long n_in,
+                   FrontierItem *__restrict__ out, long long cap_out, RegexResult *__restrict__ res, long long cap_res,
+                   unsigned long long *counters) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    const long long t = (long long)blockIdx.x * (kThreads / G) + threadIdx.x / G;
+    const bool leader = (threadIdx.x % G) == 0;
+    const uint32_t lane = threadIdx.x & 31;
+    FrontierItem it = {0, 0, 0, 0};
+    bool alive = t < n_in;
+    if (alive) {
+        it = in[t];
+        uint32_t touched = 0;
+        backward_step<G, LAYOUT, false>(ix, tb, rt.st_c[it.state], it.sp, it.ep, touched);   // getPrevRange
+        alive = it.sp < it.ep;
+    }
+    // ---- warp-aggregated emission --------------------------------------------------------------------
+    const bool last = alive && rt.st_last[it.state];
+    const uint32_t f0 = alive ? rt.fol_off[it.state] : 0u;
+    const uint32_t nf = (alive && !last && leader) ? (rt.fol_off[it.state + 1] - f0) : 0u;
+    // matches: ballot + one atomic per warp
+    const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, last && leader);
+    if (mmask) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&counters[1], (unsigned long long)__popc(mmask));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (last && leader) {
+            const unsigned long long idx = base + __popc(mmask & ((1u << lane) - 1u));
+            if (idx < (unsigned long long)cap_res) res[idx] = RegexResult{rt.st_regex[it.state], it.len + 1, it.sp, it.ep};
+        }
+    }
+    // expansions: exclusive prefix sum of follow counts over the warp, one atomic per warp
+    uint32_t incl = nf;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (total == 0) return;
+    unsigned long long wbase = 0;
+    if (lane == 0) wbase = atomicAdd(&counters[0], (unsigned long long)total);
+    wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+    const unsigned long long my = wbase + (incl - nf);
+    // wide follow lists (character classes) are written by the whole warp, short ones by their owner
+    constexpr uint32_t kWide = 16;
+    uint32_t wide = __ballot_sync(0xFFFFFFFFu, nf >= kWide);
+    if (nf > 0 && nf < kWide) {
+        for (uint32_t j = 0; j < nf; ++j) {
+            const unsigned long long idx = my + j;
+            if (idx < (unsigned long long)cap_out) out[idx] = FrontierItem{rt.fol[f0 + j], it.len + 1, it.sp, it.ep};
+        }
+    }
+    while (wide) {
+        const int src = __ffs(wide) - 1;
+        wide &= wide - 1;
+        const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, nf, src);
+        const uint32_t fs = __shfl_sync(0xFFFFFFFFu, f0, src);
+        const unsigned long long b = __shfl_sync(0xFFFFFFFFu, my, src);
+        const uint32_t ln = __shfl_sync(0xFFFFFFFFu, it.len, src) + 1;
+        const uint32_t a = __shfl_sync(0xFFFFFFFFu, it.sp, src), e = __shfl_sync(0xFFFFFFFFu, it.ep, src);
+        for (uint32_t j = lane; j < cnt; j += 32) {
+            const unsigned long long idx = b + j;
+            if (idx < (unsigned long long)cap_out) out[idx] = FrontierItem{rt.fol[fs + j], ln, a, e};
+        }
+    }
+}
+
+// =====================================================================================================
+// K4: random gather microbenchmark (pointer-chase of `chain` dependent gathers per group)
+// =====================================================================================================
+template <int LANES, int VEC>     // VEC uint4 per lane; bytes per gather = LANES*VEC*16
+__global__ void __launch_bounds__(kThreads)
+gather_kernel(const uint4 *__restrict__ base, unsigned long long n_units, long long gathers, int chain, uint32_t seed,
+              unsigned long long *sink) {
+    const long long gid = ((long long)blockIdx.x * kThreads + threadIdx.x) / LANES;
+    const int lane = threadIdx.x % LANES;
+    if (gid >= gathers) return;
+    unsigned long long x = (unsigned long long)gid * 0x9E3779B97F4A7C15ull + seed;
+    uint32_t acc = 0;
+    for (int s = 0; s < chain; ++s) {
+        x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull; x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ull; x ^= x >> 33;
+        const unsigned long long unit = __umul64hi(x, n_units);          // unit = one gather-sized aligned chunk
+        const uint4 *p = base + unit * (LANES * VEC) + lane * VEC;
+        uint32_t v = 0;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { const uint4 q = ldg128(p + i); v ^= q.x ^ q.y ^ q.z ^ q.w; }
+        if (LANES > 1) {
+            const uint32_t mask = ((LANES == 32) ? 0xFFFFFFFFu : ((1u << LANES) - 1u)) << ((threadIdx.x & 31) & ~(LANES - 1));
+            for (int o = 1; o < LANES; o <<= 1) v ^= __shfl_xor_sync(mask, v, o);
+        }
+        acc ^= v;
+        x += v;                                                       // next address depends on the loaded data
+    }
+    if (acc == 0x12345678u && lane == 0) atomicAdd(sink, 1ull);
+}
+
+// =====================================================================================================
+// launchers
+// =====================================================================================================
+#define FMX_DISPATCH(cfg, CALL)                                                                      \
+    do {                                                                                             \
+        if ((cfg).layout == FMX_LAYOUT_PLANES) {                                                     \
+            if ((cfg).lanes == 1) { CALL(1, FMX_LAYOUT_PLANES); }                                    \
+            else if ((cfg).lanes == 2) { CALL(2, FMX_LAYOUT_PLANES); }                               \
+            else { CALL(4, FMX_LAYOUT_PLANES); }                                                     \
+        } else {                                                                                     \
+            if ((cfg).lanes == 1) { CALL(1, FMX_LAYOUT_WM); }                                        \
+            else if ((cfg).lanes == 2) { CALL(2, FMX_LAYOUT_WM); }                                   \
+            else { CALL(4, FMX_LAYOUT_WM); }                                                         \
+        }                                                                                            \
+    } while (0)
+
+static inline unsigned grid_for(int64_t items, int lanes) {
+    const int64_t per = kThreads / lanes;
+    return (unsigned)((items + per - 1) / per);
+}
+
+cudaError_t launch_count_fixed(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_pat, int len, int64_t m, void *d_sp,
+                               void *d_ep, bool out64, unsigned long long *d_stats, cudaStream_t st) {
+    if (m <= 0) return cudaSuccess;
+    const size_t smem = (size_t)(kThreads / cfg.lanes) * (size_t)(len > 0 ? len : 1);
+    if (smem > 160 * 1024) return cudaErrorInvalidValue;
+#define CALL(G, LAY)                                                                                                  \
+    {                                                                                                                 \
+        if (d_stats) {                                                                                                \
+            auto k = count_fixed_kernel<G, LAY, true, uint32_t>;                                                      \
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
+            k<<<grid_for(m, G), kThreads, smem, st>>>(ix, d_pat, len, m, (uint32_t *)d_sp, (uint32_t *)d_ep, d_stats); \
+        } else if (out64) {                                                                                           \
+            auto k = count_fixed_kernel<G, LAY, false, long long>;                                                    \
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
+            k<<<grid_for(m, G), kThreads, smem, st>>>(ix, d_pat, len, m, (long long *)d_sp, (long long *)d_ep, nullptr); \
+        } else {                                                                                                      \
+            auto k = count_fixed_kernel<G, LAY, false, uint32_t>;                                                     \
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
+            k<<<grid_for(m, G), kThreads, smem, st>>>(ix, d_pat, len, m, (uint32_t *)d_sp, (uint32_t *)d_ep, nullptr); \
+        }                                                                                                             \
+    }
+    FMX_DISPATCH(cfg, CALL);
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count_var(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_pat, const int64_t *d_off, int64_t m,
+                             int64_t *d_sp, int64_t *d_ep, cudaStream_t st) {
+    if (m <= 0) return cudaSuccess;
+#define CALL(G, LAY) count_var_kernel<G, LAY><<<grid_for(m, G), kThreads, 0, st>>>(ix, d_pat, (const long long *)d_off, m, (long long *)d_sp, (long long *)d_ep)
+    FMX_DISPATCH(cfg, CALL);
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_occ(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_c, const int64_t *d_key, int64_t m, int64_t *d_out,
+                       cudaStream_t st) {
+    if (m <= 0) return cudaSuccess;
+#define CALL(G, LAY) occ_kernel<G, LAY><<<grid_for(m, G), kThreads, 0, st>>>(ix, d_c, (const long long *)d_key, m, (long long *)d_out)
+    FMX_DISPATCH(cfg, CALL);
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prev_range(const DevIndex &ix, LaunchCfg cfg, const int64_t *d_sp, const int64_t *d_ep, const uint8_t *d_c,
+                              int64_t m, int64_t *d_sp1, int64_t *d_ep1, cudaStream_t st) {
+    if (m <= 0) return cudaSuccess;
+#define CALL(G, LAY) prev_range_kernel<G, LAY><<<grid_for(m, G), kThreads, 0, st>>>(ix, (const long long *)d_sp, (const long long *)d_ep, d_c, m, (long long *)d_sp1, (long long *)d_ep1)
+    FMX_DISPATCH(cfg, CALL);
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_interval_prev_range(const DevIndex &ix, LaunchCfg cfg, int64_t sp, int64_t ep, int cstart, int cend,
+                                       int64_t *d_sp1, int64_t *d_ep1, cudaStream_t st) {
+    const int64_t m = cend - cstart + 1;
+    if (m <= 0) return cudaSuccess;
+#define CALL(G, LAY) interval_prev_range_kernel<G, LAY><<<grid_for(m, G), kThreads, 0, st>>>(ix, (uint32_t)sp, (uint32_t)ep, cstart, cend, (long long *)d_sp1, (long long *)d_ep1)
+    FMX_DISPATCH(cfg, CALL);
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lf(const DevIndex &ix, LaunchCfg cfg, const int64_t *d_row, int64_t m, int64_t *d_out, cudaStream_t st) {
+    if (m <= 0) return cudaSuccess;
+#define CALL(G, LAY) lf_kernel<G, LAY><<<grid_for(m, G), kThreads, 0, st>>>(ix, (const long long *)d_row, m, (long long *)d_out)
+    FMX_DISPATCH(cfg, CALL);
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prev_substr(const DevIndex &ix, LaunchCfg cfg, const int64_t *d_row, int64_t m, int len, uint8_t *d_out,
+                               cudaStream_t st) {
+    if (m <= 0 || len <= 0) return cudaSuccess;
+#define CALL(G, LAY) prev_substr_kernel<G, LAY><<<grid_for(m, G), kThreads, 0, st>>>(ix, (const long long *)d_row, m, len, d_out)
+    FMX_DISPATCH(cfg, CALL);
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fl(const DevIndex &ix, LaunchCfg cfg, const int64_t *d_row, int64_t m, int64_t *d_out, cudaStream_t st) {
+    if (m <= 0) return cudaSuccess;
+#define CALL(G, LAY) fl_kernel<G, LAY><<<grid_for(m, G), kThreads, 0, st>>>(ix, (const long long *)d_row, m, (long long *)d_out)
+    FMX_DISPATCH(cfg, CALL);
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_next_substr(const DevIndex &ix, LaunchCfg cfg, const int64_t *d_row, int64_t m, int len, uint8_t *d_out,
+                               int *d_out_len, cudaStream_t st) {
+    if (m <= 0) return cudaSuccess;
+#define CALL(G, LAY) next_substr_kernel<G, LAY><<<grid_for(m, G), kThreads, 0, st>>>(ix, (const long long *)d_row, m, len, d_out, d_out_len)
+    FMX_DISPATCH(cfg, CALL);
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_locate(const DevIndex &ix, LaunchCfg cfg, const int64_t *d_sp, const int64_t *d_off, int64_t m,
+                          int64_t total, int sample_rate, uint32_t *d_pos, cudaStream_t st) {
+    (void)sample_rate;
+    if (total <= 0) return cudaSuccess;
+#define CALL(G, LAY) locate_kernel<G, LAY><<<grid_for(total, G), kThreads, 0, st>>>(ix, (const long long *)d_sp, (const long long *)d_off, m, total, d_pos)
+    FMX_DISPATCH(cfg, CALL);
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_regex_level(const DevIndex &ix, LaunchCfg cfg, RegexTables rt, const FrontierItem *d_in, int64_t n_in,
+                               FrontierItem *d_out, int64_t cap_out, RegexResult *d_res, int64_t cap_res,
+                               unsigned long long *d_counters, cudaStream_t st) {
+    if (n_in <= 0) return cudaSuccess;
+#define CALL(G, LAY) regex_level_kernel<G, LAY><<<grid_for(n_in, G), kThreads, 0, st>>>(ix, rt, d_in, n_in, d_out, cap_out, d_res, cap_res, d_counters)
+    FMX_DISPATCH(cfg, CALL);
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_bench(const uint4 *base, uint64_t n_blocks64, int bytes, int lanes, int64_t gathers, int chain,
+                                uint32_t seed, unsigned long long *d_sink, cudaStream_t st) {
+    const int per_lane = bytes / lanes;                    // bytes each lane loads
+    if (per_lane < 16 || per_lane % 16 || (per_lane / 16) > 8 || lanes < 1 || lanes > 32 || (lanes & (lanes - 1))) return cudaErrorInvalidValue;
+    const int vec = per_lane / 16;
+    const unsigned long long units = n_blocks64 * 64ull / (unsigned long long)bytes;
+    const unsigned grid = (unsigned)((gathers * lanes + kThreads - 1) / kThreads);
+#define GK(L, V) gather_kernel<L, V><<<grid, kThreads, 0, st>>>(base, units, gathers, chain, seed, d_sink)
+    if (vec == 1) { switch (lanes) { case 1: GK(1, 1); break; case 2: GK(2, 1); break; case 4: GK(4, 1); break; case 8: GK(8, 1); break; case 16: GK(16, 1); break; default: GK(32, 1); } }
+    else if (vec == 2) { switch (lanes) { case 1: GK(1, 2); break; case 2: GK(2, 2); break; case 4: GK(4, 2); break; case 8: GK(8, 2); break; default: return cudaErrorInvalidValue; } }
+    else if (vec == 4) { switch (lanes) { case 1: GK(1, 4); break; case 2: GK(2, 4); break; case 4: GK(4, 4); break; default: return cudaErrorInvalidValue; } }
+    else if (vec == 8) { switch (lanes) { case 1: GK(1, 8); break; case 2: GK(2, 8); break; default: return cudaErrorInvalidValue; } }
+    else return cudaErrorInvalidValue;
+#undef GK
+    return cudaGetLastError();
+}
+
+}  // namespace fmx

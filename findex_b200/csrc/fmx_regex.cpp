@@ -1,0 +1,396 @@
+// fmx_regex.cpp — host-side regex front-end of libfmgpu: regex text -> Glushkov position automaton,
+// flattened into the tables the device frontier kernel walks.
+//
+// Behavioural contract = the reference's REParser.re2post (src/main/scala/org/fmindex/re2/re2.scala:50-185)
+// followed by ReTree.apply (re2/retree.scala:156-370) with node semantics :10-155, postProcess :439-482,
+// removeBorderNulls :371-385, setNums :393-423.  The reference engine is a partial prototype; what it
+// rejects (MatchError), mis-handles ('+' inside alternation, Q4; follows that do not climb, Q2)
+// or trims (border nullables, Q5; exclusive interval ends, Q1) is reproduced so that match sets are
+// identical.  Written from the behavioural description, as an index-based arena instead of the
+// reference's linked object graph.
+#include "fmx_internal.h"
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+namespace fmx {
+
+namespace {
+
+enum TokKind : uint8_t { T_CHAR, T_RANGE, T_SET, T_CAT, T_OR, T_STAR, T_PLUS, T_QUEST };
+struct Tok {
+    TokKind kind;
+    int a = 0, b = 0;               // T_CHAR: a ; T_RANGE: [a,b) as the tree builder reads it
+    std::vector<int> set;           // T_SET: members, front = most recently added (reference list order)
+};
+
+struct ParseError { int code; std::string msg; };
+[[noreturn]] void syntax() { throw ParseError{FMX_E_SYNTAX, "re2post syntax"}; }
+[[noreturn]] void unsupported(const std::string &m) { throw ParseError{FMX_E_UNSUPPORTED, m}; }
+
+// ---- infix -> postfix with explicit concatenation (re2.scala:50-185) ---------------------------------
+std::vector<Tok> to_postfix(const uint8_t *s, int64_t l, bool line_only) {
+    std::vector<Tok> out;
+    struct Frame { int nalt, natom; };
+    std::vector<Frame> frames;
+    int natom = 0, nalt = 0;
+    bool quoted = false;
+
+    auto emit = [&](TokKind k) { Tok t; t.kind = k; out.push_back(std::move(t)); };
+    auto before_atom = [&]() { if (natom > 1) { --natom; emit(T_CAT); } };
+    auto flush_cats = [&]() { --natom; while (natom > 0) { emit(T_CAT); --natom; } };
+    auto flush_ors = [&]() { while (nalt > 0) { emit(T_OR); --nalt; } };
+
+    auto atom_char = [&](int c, bool q) {
+        before_atom();
+        Tok t;
+        if (q && c == 'w')      { t.kind = T_RANGE; t.a = 'A'; t.b = 'z'; }
+        else if (q && c == 'd') { t.kind = T_RANGE; t.a = '0'; t.b = '9'; }
+        else if (!q && c == '.'){ t.kind = T_RANGE; t.a = line_only ? 0x20 : 2; t.b = 255; }
+        else                    { t.kind = T_CHAR;  t.a = c; }
+        out.push_back(std::move(t));
+        ++natom;
+    };
+
+    // "[...]" : returns index just past ']'   (re2.scala:76-119)
+    auto atom_set = [&](int64_t i) -> int64_t {
+        std::vector<int> members;            // front = head
+        bool q = false, closed = false, range = false;
+        auto add = [&](int c) {
+            if (range) {
+                if (members.empty()) syntax();
+                int from = members.front() + 1;
+                if (from > c) syntax();
+                for (int x = from; x <= c; ++x) members.insert(members.begin(), x);
+                range = false;
+            } else members.insert(members.begin(), c);
+        };
+        while (i < l && !closed) {
+            int c = s[i];
+            if (q) { add(c); q = false; }
+            else if (c == '\\') q = true;
+            else if (c == '-') range = true;
+            else if (c == ']') closed = true;
+            else add(c);
+            ++i;
+        }
+        if (!closed || range) syntax();
+        before_atom();
+        Tok t; t.kind = T_SET; t.set = std::move(members);
+        out.push_back(std::move(t));
+        ++natom;
+        return i;
+    };
+
+    for (int64_t i = 0; i < l; ++i) {
+        int c = s[i];
+        if (quoted) { atom_char(c, true); quoted = false; continue; }
+        switch (c) {
+        case '(':
+            before_atom();
+            frames.push_back({nalt, natom});
+            nalt = 0; natom = 0;
+            break;
+        case '|':
+            if (natom == 0) syntax();
+            flush_cats();
+            ++nalt;
+            break;
+        case ')':
+            if (natom == 0) syntax();
+            flush_cats();
+            flush_ors();
+            if (frames.empty()) unsupported("NoSuchElementException: unbalanced ')'");
+            nalt = frames.back().nalt; natom = frames.back().natom + 1;
+            frames.pop_back();
+            break;
+        case '[':
+            i = atom_set(i + 1) - 1;
+            break;
+        case '\\':
+            quoted = true;
+            break;
+        case '*': case '+': case '?':
+            if (natom == 0) syntax();
+            emit(c == '*' ? T_STAR : c == '+' ? T_PLUS : T_QUEST);
+            break;
+        default:
+            atom_char(c, false);
+        }
+    }
+    if (!frames.empty()) syntax();
+    flush_cats();
+    flush_ors();
+    return out;
+}
+
+// ---- tree arena --------------------------------------------------------------------------------------
+enum NodeKind : uint8_t { N_CHAR, N_OR, N_SEQ, N_STAR, N_QUEST, N_PLUS };
+struct Node {
+    NodeKind kind;
+    int c = 0, num = 0;
+    int parent = -1;                 // -1 = RootNode
+    std::vector<int> kids;           // front = head of the reference's child list
+};
+
+struct Tree {
+    std::vector<Node> nodes;
+    int make(NodeKind k, int c = 0) { Node n; n.kind = k; n.c = c; nodes.push_back(std::move(n)); return (int)nodes.size() - 1; }
+    Node &at(int i) { return nodes[i]; }
+    const Node &at(int i) const { return nodes[i]; }
+
+    static bool unary(NodeKind k) { return k == N_STAR || k == N_QUEST || k == N_PLUS; }
+    // shape class used by the builder's case tables: 0=Char 1=Or 2=Seq 3=Unary
+    int shape(int i) const { NodeKind k = at(i).kind; return k == N_CHAR ? 0 : k == N_OR ? 1 : k == N_SEQ ? 2 : 3; }
+
+    // append == prepend to the child list; an Or absorbing an Or splices its children in front
+    void adopt(int p, int ch) {
+        if (at(p).kind == N_OR && at(ch).kind == N_OR) {
+            std::vector<int> merged = at(ch).kids;
+            for (int k : merged) at(k).parent = p;
+            merged.insert(merged.end(), at(p).kids.begin(), at(p).kids.end());
+            at(p).kids = std::move(merged);
+        } else {
+            at(ch).parent = p;
+            at(p).kids.insert(at(p).kids.begin(), ch);
+        }
+    }
+
+    bool nullable(int i) const {
+        const Node &n = at(i);
+        switch (n.kind) {
+        case N_CHAR: return false;
+        case N_STAR: case N_QUEST: return true;
+        case N_OR:   return std::any_of(n.kids.begin(), n.kids.end(), [&](int k) { return nullable(k); });
+        default:     return std::all_of(n.kids.begin(), n.kids.end(), [&](int k) { return nullable(k); });  // Seq, Plus
+        }
+    }
+
+    static void prepend(std::vector<int> &dst, const std::vector<int> &src) { dst.insert(dst.begin(), src.begin(), src.end()); }
+
+    std::vector<int> firsts(int i) const {
+        const Node &n = at(i);
+        std::vector<int> r;
+        if (n.kind == N_CHAR) { r.push_back(i); return r; }
+        if (n.kind != N_SEQ) {
+            for (int k : n.kids) { auto f = firsts(k); r.insert(r.end(), f.begin(), f.end()); }
+            return r;
+        }
+        size_t p = 0;
+        while (p < n.kids.size() && nullable(n.kids[p])) { prepend(r, firsts(n.kids[p])); ++p; }
+        if (p < n.kids.size()) prepend(r, firsts(n.kids[p]));
+        return r;
+    }
+
+    size_t index_in_parent(int i) const {
+        const Node &p = at(at(i).parent);
+        return (size_t)(std::find(p.kids.begin(), p.kids.end(), i) - p.kids.begin());
+    }
+
+    std::vector<int> follows(int i) const {
+        int pi = at(i).parent;
+        if (pi < 0) return {};
+        const Node &p = at(pi);
+        switch (p.kind) {
+        case N_OR: case N_QUEST: return follows(pi);
+        case N_STAR: { auto r = firsts(i); auto f = follows(pi); r.insert(r.end(), f.begin(), f.end()); return r; }
+        case N_SEQ: {
+            size_t k = index_in_parent(i) + 1;
+            if (k >= p.kids.size()) return follows(pi);
+            std::vector<int> r = firsts(p.kids[k]);
+            if (nullable(p.kids[k])) {
+                ++k;
+                while (k < p.kids.size() && nullable(p.kids[k])) { prepend(r, firsts(p.kids[k])); ++k; }
+                if (k < p.kids.size()) prepend(r, firsts(p.kids[k]));     // siblings exhausted: no climb (Q2)
+            }
+            return r;
+        }
+        default: return {};          // under a Plus
+        }
+    }
+
+    bool is_last(int i) const {
+        int pi = at(i).parent;
+        if (pi < 0) return true;
+        const Node &p = at(pi);
+        if (p.kind == N_OR || unary(p.kind)) return is_last(pi);
+        if (p.kind == N_SEQ) {
+            for (size_t k = index_in_parent(i) + 1; k < p.kids.size(); ++k)
+                if (!nullable(p.kids[k])) return false;
+            return is_last(pi);
+        }
+        return true;
+    }
+};
+
+// case tables of the builder: [shape(a1)][shape(a2)] ; 0 = MatchError, 1 = fold into existing, 2 = new node
+//                      a2:  C  O  S  U
+const uint8_t OR_RULE[4][4] = {
+    /* a1=C */ {2, 1, 2, 0},
+    /* a1=O */ {0, 1, 0, 0},
+    /* a1=S */ {2, 1, 2, 0},
+    /* a1=U */ {2, 1, 2, 2},
+};
+const uint8_t CAT_RULE[4][4] = {
+    /* a1=C */ {2, 2, 0, 2},
+    /* a1=O */ {0, 2, 0, 0},
+    /* a1=S */ {1, 1, 0, 1},
+    /* a1=U */ {2, 2, 0, 2},
+};
+
+struct Builder {
+    Tree t;
+    std::vector<int> st;
+    int pop() { if (st.empty()) unsupported("NoSuchElementException: empty stack"); int x = st.back(); st.pop_back(); return x; }
+
+    int char_class(const std::vector<int> &members) {
+        int o = t.make(N_OR);
+        for (int c : members) t.adopt(o, t.make(N_CHAR, c));
+        return o;
+    }
+
+    int wrap(NodeKind k, int child) { int u = t.make(k); t.adopt(u, child); return u; }
+
+    void run(const std::vector<Tok> &post) {
+        for (const Tok &tk : post) {
+            switch (tk.kind) {
+            case T_CHAR: st.push_back(t.make(N_CHAR, tk.a)); break;
+            case T_RANGE: { std::vector<int> m; for (int j = tk.a; j < tk.b; ++j) m.push_back(j); st.push_back(char_class(m)); break; }   // end exclusive (Q1)
+            case T_SET: st.push_back(char_class(tk.set)); break;
+            case T_OR: {
+                int a2 = pop(), a1 = pop();
+                uint8_t r = OR_RULE[t.shape(a1)][t.shape(a2)];
+                if (r == 1) { t.adopt(a2, a1); st.push_back(a2); }
+                else if (r == 2) { int o = t.make(N_OR); t.adopt(o, a1); t.adopt(o, a2); st.push_back(o); }
+                else unsupported("MatchError: OrPoint have no match");
+                break;
+            }
+            case T_CAT: {
+                int a2 = pop(), a1 = pop();
+                uint8_t r = CAT_RULE[t.shape(a1)][t.shape(a2)];
+                if (r == 1) { t.adopt(a1, a2); st.push_back(a1); }
+                else if (r == 2) { int f = t.make(N_SEQ); t.adopt(f, a1); t.adopt(f, a2); st.push_back(f); }
+                else unsupported("MatchError: ConcatPoint have no match");
+                break;
+            }
+            case T_STAR: case T_PLUS: {
+                int a = pop();
+                NodeKind k = t.at(a).kind;
+                if (k == N_STAR) st.push_back(a);
+                else if (k == N_QUEST || k == N_PLUS) st.push_back(wrap(N_STAR, t.at(a).kids.front()));
+                else st.push_back(wrap(tk.kind == T_PLUS ? N_PLUS : N_STAR, a));
+                break;
+            }
+            case T_QUEST: {
+                int a = pop();
+                NodeKind k = t.at(a).kind;
+                if (k == N_STAR) st.push_back(a);
+                else if (k == N_QUEST) st.push_back(wrap(N_QUEST, t.at(a).kids.front()));
+                else if (k == N_PLUS) st.push_back(wrap(N_STAR, t.at(a).kids.front()));
+                else st.push_back(wrap(N_QUEST, a));
+                break;
+            }
+            }
+        }
+    }
+};
+
+// deep copy into `dst` restoring forward child order; every Plus child p becomes  p , Star(p)   (Q4)
+int normalise(const Tree &src, int i, Tree &dst) {
+    const Node &n = src.at(i);
+    if (n.kind == N_CHAR) return dst.make(N_CHAR, n.c);
+    if (n.kind == N_PLUS) unsupported("MatchError in postProcess");
+    int me = dst.make(n.kind);
+    std::vector<int> kids;
+    for (int k : n.kids) {                         // iterate the (reversed) list, prepending => forward order
+        if (src.at(k).kind == N_PLUS) {
+            int inner = src.at(k).kids.front();
+            int once = normalise(src, inner, dst);
+            int star = dst.make(N_STAR);
+            int again = normalise(src, inner, dst);
+            dst.at(star).kids.push_back(again);
+            kids.insert(kids.begin(), {once, star});
+        } else {
+            kids.insert(kids.begin(), normalise(src, k, dst));
+        }
+    }
+    dst.at(me).kids = std::move(kids);
+    return me;
+}
+
+void set_parents(Tree &t, int i, int parent) {
+    t.at(i).parent = parent;
+    for (int k : t.at(i).kids) set_parents(t, k, i);
+}
+
+// priority numbers (only relevant to the reference's capped PQ order; exported for parity checks)
+int number_from(Tree &t, int i, int start);
+int number_shared(Tree &t, int i, int &idx) {
+    Node &n = t.at(i);
+    if (n.kind == N_OR) {
+        int hi = idx;
+        for (int k : n.kids) {
+            if (t.at(k).kind == N_CHAR) { t.at(k).num = idx; hi = std::max(hi, idx + 1); }
+            else hi = std::max(hi, number_from(t, k, idx));
+        }
+        idx = hi;
+    } else {
+        for (int k : n.kids) {
+            if (t.at(k).kind == N_CHAR) { t.at(k).num = idx; ++idx; }
+            else number_shared(t, k, idx);
+        }
+    }
+    return idx;
+}
+int number_from(Tree &t, int i, int start) { int idx = start; return number_shared(t, i, idx); }
+
+}  // namespace
+
+int compile_regex(const uint8_t *re, int64_t len, bool line_only, CompiledRegex &out, std::string &err) {
+    try {
+        std::vector<Tok> post = to_postfix(re, len, line_only);
+        Builder b;
+        b.run(post);
+        int top = b.pop();
+        if (b.t.at(top).kind != N_SEQ) top = b.wrap(N_SEQ, top);
+
+        Tree t;
+        int root0 = normalise(b.t, top, t);
+        // trim nullable children at both borders of the root sequence (Q5)
+        std::vector<int> &rk = t.at(root0).kids;
+        size_t lo = 0, hi = rk.size();
+        while (lo < hi && t.nullable(rk[lo])) ++lo;
+        while (hi > lo && t.nullable(rk[hi - 1])) --hi;
+        int root = t.make(N_SEQ);
+        t.at(root).kids.assign(t.at(root0).kids.begin() + lo, t.at(root0).kids.begin() + hi);
+        set_parents(t, root, -1);
+        number_from(t, root, 1);
+
+        // flatten: positions in pre-order
+        std::vector<int> order, sid(t.nodes.size(), -1);
+        std::vector<int> stack{root};
+        while (!stack.empty()) {
+            int i = stack.back(); stack.pop_back();
+            if (t.at(i).kind == N_CHAR) { sid[i] = (int)order.size(); order.push_back(i); }
+            const auto &k = t.at(i).kids;
+            for (auto it = k.rbegin(); it != k.rend(); ++it) stack.push_back(*it);
+        }
+        out = CompiledRegex();
+        out.follows_off.push_back(0);
+        for (int i : order) {
+            out.c.push_back((uint8_t)t.at(i).c);
+            out.num.push_back(t.at(i).num);
+            out.is_last.push_back(t.is_last(i) ? 1 : 0);
+            for (int f : t.follows(i)) out.follows.push_back(sid[f]);
+            out.follows_off.push_back((int32_t)out.follows.size());
+        }
+        for (int f : t.firsts(root)) out.firsts.push_back(sid[f]);
+        return FMX_OK;
+    } catch (const ParseError &e) {
+        err = e.msg;
+        return e.code;
+    }
+}
+
+}  // namespace fmx

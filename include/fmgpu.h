@@ -1,0 +1,163 @@
+/*
+ * fmgpu.h — C ABI of libfmgpu.so: the B200-native FM-index search path behind findex's operator API.
+ *
+ * This is the drop-in boundary.  The reference (martende/findex, Scala) has no FFI
+ * layer; its operator interface for the path is the trait pair SuffixAlgo / SuffixWalkingAlgo
+ * (src/main/scala/org/fmindex/findex.scala:9-57, "M/findex.scala") implemented on disk by
+ * NaiveFMSearcher (M/bwtmerger.scala:335-421) and consumed by ReTree.matchSA (M/re2/retree.scala:570).
+ * Every entry point below cites the reference member it replaces.  A JVM host binds these with JNA
+ * direct mapping (see INTEGRATION.md for the Scala shim); tests bind them with ctypes.
+ *
+ * Conventions
+ *   - every function returns FMX_OK (0) or a negative FMX_E_* code; nothing throws across the ABI;
+ *     fmx_last_error() returns a thread-local message for the last failure on the calling thread.
+ *   - rows / positions are int64 at the ABI (the device works in uint32; n must be < 2^32).
+ *   - intervals are half-open [sp,ep) exactly as in the reference; "None" is reported as sp=ep=0
+ *     by the *_count_* calls and as sp1>=ep1 by the prev-range calls.
+ *   - the caller owns every input and output buffer.  "_batch" calls take HOST pointers and do the
+ *     H2D/D2H copies themselves; "_dev" calls take DEVICE pointers valid on the index's device and a
+ *     cudaStream_t (passed as void*; NULL = the legacy default stream) and are asynchronous.
+ *   - there is no CPU fallback: without a usable CUDA device every compute call returns FMX_E_CUDA.
+ */
+#ifndef FMGPU_H
+#define FMGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMX_OK              0
+#define FMX_E_IO           -1   /* file missing / unreadable                                            */
+#define FMX_E_FORMAT       -2   /* "File %s bad size" / bad elSize (M/bwtmerger.scala:153, :261-262)     */
+#define FMX_E_CUDA         -3   /* no device, out of memory, launch failure                             */
+#define FMX_E_ARG          -4   /* null pointer, negative size, row out of range                        */
+#define FMX_E_CAPACITY     -5   /* output buffer too small; required size is reported                   */
+#define FMX_E_SYNTAX       -6   /* Exception("re2post syntax") (M/re2/re2.scala:86-110, :134-182)        */
+#define FMX_E_UNSUPPORTED  -7   /* MatchError / NoSuchElementException of ReTree.apply (Q3), n >= 2^32   */
+#define FMX_E_LIMIT        -8   /* regex traversal exceeded the configured frontier / length limits     */
+
+/* Rank-structure layouts (fmx_opts.layout) */
+#define FMX_LAYOUT_AUTO     0   /* planes if it fits fmx_opts.max_index_bytes (default 64 GiB), else WM  */
+#define FMX_LAYOUT_WM       1   /* byte-alphabet wavelet matrix, ceil(log2 sigma) levels, 64-B rank blocks */
+#define FMX_LAYOUT_PLANES   2   /* one 64-B-rank-block bitvector per symbol (1 block fetch per rank)     */
+
+typedef struct fmx_index fmx_index;     /* opaque; library-owned until fmx_close  */
+typedef struct fmx_regex fmx_regex;     /* opaque; library-owned until fmx_regex_free */
+
+typedef struct fmx_opts {
+    int32_t  device;            /* CUDA device ordinal; -1 = current device                              */
+    int32_t  layout;            /* FMX_LAYOUT_*                                                          */
+    int32_t  sa_sample_rate;    /* 0 = no locate support; k>=1: rows with sa%k==0 are sampled (32 = cfg3) */
+    int32_t  require_fm;        /* 1 = fail like the reference when <base>.fm is absent                  */
+    int64_t  max_index_bytes;   /* budget for FMX_LAYOUT_AUTO; 0 = default                               */
+    int32_t  lanes_per_query;   /* 0 = default; 1, 2 or 4 lanes cooperate on one 64-B rank block         */
+    int32_t  reserved;
+} fmx_opts;
+
+void        fmx_opts_default(fmx_opts *o);
+const char *fmx_last_error(void);
+const char *fmx_version(void);
+
+/* ---- load: new NaiveFMSearcher(filename, bigEndian)  M/bwtmerger.scala:335-350 ----------------------
+ * `path` may carry any extension; it is stripped like BWTTempStorage.gen*Filename (:10-48) and
+ * .bwt/.aux(/.fm) are opened.  Validates BWTLoader (:153) and FMLoader (:261-262) size rules.  The
+ * occurrence structure is repacked into the GPU rank structure on the device.                         */
+int fmx_open(const char *path, int big_endian, const fmx_opts *opts, fmx_index **out);
+/* Same, from memory: bwt[n] (byte at eof ignored), eof row, counts[256] as stored in .aux.            */
+int fmx_open_mem(const uint8_t *bwt, int64_t n, int64_t eof, const int64_t counts[256],
+                 const fmx_opts *opts, fmx_index **out);
+int fmx_close(fmx_index *ix);
+
+int64_t fmx_n(const fmx_index *ix);                          /* SuffixAlgo.n          M/findex.scala:10  */
+int64_t fmx_eof(const fmx_index *ix);                        /* BWTLoader.eof         M/bwtmerger.scala:151 */
+int     fmx_ctable(const fmx_index *ix, int64_t C[256]);     /* cf(c) for all c       M/bwtmerger.scala:352 */
+int     fmx_info(const fmx_index *ix, int32_t *layout, int32_t *levels, int32_t *sigma,
+                 int64_t *index_bytes, int32_t *sa_sample_rate);
+
+/* ---- occ(c,key)  M/bwtmerger.scala:354-375  (number of c in BWT[0..key], key=-1 -> 0) --------------- */
+int fmx_occ_batch(fmx_index *ix, const uint8_t *c, const int64_t *key, int64_t m, int64_t *out);
+
+/* ---- getPrevRange(sp,ep,c)  M/findex.scala:32-36 ; empty <=> sp1>=ep1 ------------------------------- */
+int fmx_prev_range_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, const uint8_t *c, int64_t m,
+                         int64_t *sp1, int64_t *ep1);
+
+/* ---- getIntervalPrevRange(sp,ep,cstart,cend)  M/findex.scala:37-51 ---------------------------------
+ * One interval, every c in [cstart,cend]; non-empty results in the reference's order (descending c).
+ * out arrays must hold cend-cstart+1 entries; *n_out receives the number written.                      */
+int fmx_interval_prev_range(fmx_index *ix, int64_t sp, int64_t ep, int cstart, int cend,
+                            int32_t *out_c, int64_t *out_sp, int64_t *out_ep, int64_t *n_out);
+
+/* ---- search(in)  M/findex.scala:15-31 — batched count ----------------------------------------------
+ * pat = concatenated pattern bytes, off[m+1] = offsets; pattern q is pat[off[q]..off[q+1]).
+ * The pattern is consumed last byte first, with the reference's early exit.  Some((sp,ep)) -> sp<ep;
+ * None -> sp=ep=0.  Empty pattern -> (0,n).                                                            */
+int fmx_count_batch(fmx_index *ix, const uint8_t *pat, const int64_t *off, int64_t m, int64_t *sp, int64_t *ep);
+/* Fixed-length fast path: m patterns of `len` bytes, back to back.                                     */
+int fmx_count_fixed(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, int64_t *sp, int64_t *ep);
+/* Device-pointer variant (asynchronous on `stream`): d_pat holds m*len bytes, d_sp/d_ep are uint32[m]. */
+int fmx_count_fixed_dev(fmx_index *ix, const void *d_pat, int32_t len, int64_t m,
+                        void *d_sp_u32, void *d_ep_u32, void *stream);
+
+/* ---- locate: sorted { sa[r] : r in [sp,ep) }, sa as bwtFm2sa  M/util.scala:213-224 -----------------
+ * (== SACreator.create M/bwtmerger.scala:541-555).  Positions are in T' = reverse(file)+'$' coordinates;
+ * file offset of a length-k match = (n-1) - pos - k.  out_off[m+1] receives the per-query offsets;
+ * if the total exceeds cap_total, FMX_E_CAPACITY is returned and out_off[m] holds the required total.  */
+int fmx_locate_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, int64_t m, int64_t cap_total,
+                     int64_t *out_off, int64_t *pos);
+
+/* ---- LF / FL steps and extraction  M/bwtmerger.scala:376-419 --------------------------------------- */
+int fmx_get_prev_i_batch(fmx_index *ix, const int64_t *row, int64_t m, int64_t *out);   /* getPrevI :386 */
+int fmx_get_next_i_batch(fmx_index *ix, const int64_t *row, int64_t m, int64_t *out);   /* getNextI :390 */
+int fmx_pos2char(const fmx_index *ix, int64_t key, int32_t *c);                         /* pos2char :376 */
+/* prevSubstr(sp,len) :409-419 and nextSubstr(sp,len) :394-405; out is m*len bytes (row-major),
+ * out_len[m] the bytes written per row (nextSubstr stops after the '\0').                              */
+int fmx_prev_substr_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t len, uint8_t *out, int32_t *out_len);
+int fmx_next_substr_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t len, uint8_t *out, int32_t *out_len);
+
+/* ---- regex: REParser.re2post M/re2/re2.scala:50-185 + ReTree.apply M/re2/retree.scala:156-370 -------
+ * Compiles on the host to the reference's Glushkov position automaton, quirks included;
+ * FMX_E_SYNTAX / FMX_E_UNSUPPORTED exactly where the reference throws.                                  */
+int  fmx_regex_compile(const uint8_t *re, int64_t re_len, int line_only, fmx_regex **out);
+void fmx_regex_free(fmx_regex *rx);
+/* Introspection (used by the parity tests; mirrors CharNode.c/.num, isLast, follows, root.firsts).
+ * follows_off has n_states+1 entries.  Pass NULL to skip an output.                                    */
+int  fmx_regex_tables(const fmx_regex *rx, int32_t *n_states, int32_t *n_follows, int32_t *n_firsts,
+                      uint8_t *c, uint8_t *is_last, int32_t *num, int32_t *follows_off, int32_t *follows,
+                      int32_t *firsts);
+/* ReTree.matchSA M/re2/retree.scala:570-653 with the caps disabled (maxBranching=Int.MaxValue,
+ * maxIterations=0): per regex the sorted multiset of SAResult (len,sp,ep) M/re2/re2.scala:9-19.
+ * out_off[m+1]; FMX_E_CAPACITY with the required total in out_off[m] when cap_total is too small.      */
+int  fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64_t cap_total,
+                            int64_t *out_off, int32_t *len, int64_t *sp, int64_t *ep);
+
+/* ---- instrumentation for the roofline accounting (not on the timed path) ---------------------------
+ * Runs the same count kernel with block-touch counting: *blocks = number of distinct 64-B rank blocks
+ * the batch reads (a level whose sp and ep probes share a block counts once), *steps = executed
+ * backward steps.                                                                                      */
+int fmx_count_fixed_stats(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m,
+                          int64_t *blocks, int64_t *steps);
+/* K4: random 64-B-aligned gather microbenchmark over the index's own rank-block array.
+ * bytes_per_gather in {32,64,128}; returns achieved GB/s of useful bytes in *gbs.                       */
+int fmx_gather_bench(fmx_index *ix, int32_t bytes_per_gather, int32_t lanes, int64_t gathers, int32_t chain,
+                     int32_t iters, double *gbs, double *ms);
+/* Time of the last *_batch call's kernel section in ms (CUDA events on the library's stream).          */
+double fmx_last_kernel_ms(const fmx_index *ix);
+int64_t fmx_last_kernel_launches(const fmx_index *ix);
+
+/* ---- index construction on the device (tooling for synthetic configs) -----------
+ * text = FILE bytes (forward order).  Reproduces FileBWTReader (M/bwtreader.scala:196-211: 0x00 dropped,
+ * text reversed), suffix-sorts reverse(text)+'$' on the GPU and writes <base>.bwt/.aux in the
+ * reference's layout (BWTTempStorage :75-98, writeAuxFile :841-856); write_fm also writes <base>.fm
+ * (FMCreator.create :452-532).                                                                          */
+int fmx_build_index_files(const uint8_t *text, int64_t len, const char *base, int big_endian, int write_fm,
+                          int device);
+/* Same, to memory: bwt_out[n], *eof_out, counts_out[256]; n = (number of non-zero bytes) + 1.          */
+int fmx_build_bwt(const uint8_t *text, int64_t len, uint8_t *bwt_out, int64_t *n_out, int64_t *eof_out,
+                  int64_t counts_out[256], int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMGPU_H */

@@ -1,0 +1,145 @@
+"""
+CPU-only checks of the product's host side: the C-ABI library loads and exports every declared symbol, the regex
+compiler (C++) agrees table-for-table with the oracle's independent Python restatement, file validation mirrors the
+reference's exceptions, and compute calls fail loudly without a GPU (no CPU fallback).
+"""
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from findex_b200 import build as fbuild
+from findex_b200 import fmindex as fx
+from oracle import retree
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    fbuild.build()
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "fmgpu.h")).read()
+    names = set(re.findall(r"\b(fmx_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 30
+    L = fx.lib()
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+    assert b"sm_100a" in L.fmx_version()
+
+
+REGEXES = ["abcd", "abcd*", "abc*d", "a*bcd", "a*b*c*d*", "(ab)*", "(ab)*cd", "(ab)*(cd*)*", "(a|b)", "(a|b|d|c)",
+           "(a|b*|d|c)", "(a|b*|d|c)*|(abc)", "(a|b|c)|(c|d|e)", "[a-c]", "a[b-d]e", "a[b-d]*e", "a[x.]e", "a\\de",
+           "a+", "a****", "a+b", "a+((b|c)+|d)", "a*+", "a+*", "a+*+*++*", "a?", "(abc)?+|a?|bcd", "ab(cd|ef)+gh",
+           "(10\\.[0-9]|[1-9][0-9]|[1-2][0-5][0-5]\\.[0-9]|[1-9][0-9]|[1-2][0-5][0-5]\\.[0-9]|[1-9][0-9]|[1-2][0-5][0-5])",
+           "ab(cd)*ef", "ab*(cd)*(gh)*ij", "a(cd|ef)*j", ".*ab(cd)*(m(k|l)|tm*)(a|abc)(a*|(abc)*)ef(a*b*c*dg*)*gh",
+           "a.*(b|c)d.*f", "x(ab?|d)c", "abc(cde)*ef", "ab?j", "a*(b|a)*bB*cd*e*", "a*(b|a)*b?B*c?d*e*", "abcdef",
+           "(a|bX|cYZ)(a|b|c)", "(a|b|c)(a|b|c)", ".*(a|b)ca", "x(a|b|d|e)c", "ab?c[d-h]", "q(u|a)[a-m]z?k",
+           "th(e|a)(n|t)\\w", "b(oo|ee)+k", "z[aeiou][aeiou]?z", "a\\.b", "a[\\]x]b", "a.b", "\\w+x", "a[aa]b", "a\\"]
+
+
+@pytest.mark.parametrize("rx", REGEXES)
+@pytest.mark.parametrize("line_only", [False, True])
+def test_regex_compiler_matches_oracle_tables(rx, line_only):
+    want = retree.compile_regex(rx, line_only).tables()
+    got = fx.ReTree(rx, lineOnly=line_only).tables()
+    assert got == want
+
+
+BAD = ["*a", "(", "a(b", "|a", "()", "a||b", "[abc", "[a-", "[-a]", "[b-a]", "a(bc)d", "(a|b)c", "[a-c]d", "a|b*", "", "a|", "a)",
+       "(a|b)|c", "(ab)(cd)", "a(b)", "(a)(b)", "a|(b|c)d"]
+
+
+@pytest.mark.parametrize("rx", BAD)
+def test_regex_errors_match_oracle(rx):
+    try:
+        retree.compile_regex(rx)
+        want = None
+    except retree.ReSyntaxError:
+        want = fx.ReSyntaxError
+    except retree.ReUnsupported:
+        want = fx.ReUnsupported
+    if want is None:
+        fx.ReTree(rx)
+    else:
+        with pytest.raises(want):
+            fx.ReTree(rx)
+
+
+def _rand_regex(rng, depth=0):
+    r = rng.random()
+    if depth > 3 or r < 0.35:
+        return rng.choice("abcdxyz")
+    if r < 0.45:
+        return rng.choice(["[a-c]", "\\d", ".", "[xyz]", "\\w"])
+    if r < 0.65:
+        return "".join(_rand_regex(rng, depth + 1) for _ in range(rng.randint(2, 4)))
+    if r < 0.8:
+        return "(" + "|".join(_rand_regex(rng, depth + 1) for _ in range(rng.randint(2, 3))) + ")"
+    return _rand_regex(rng, depth + 1) + rng.choice("*+?")
+
+
+def test_regex_compiler_fuzz_against_oracle():
+    rng = random.Random(12345)
+    seen = {"ok": 0, "syntax": 0, "unsupported": 0}
+    for _ in range(3000):
+        rx = _rand_regex(rng)
+        try:
+            want = retree.compile_regex(rx).tables()
+            kind = "ok"
+        except retree.ReSyntaxError:
+            kind = "syntax"
+        except retree.ReUnsupported:
+            kind = "unsupported"
+        seen[kind] += 1
+        if kind == "ok":
+            assert fx.ReTree(rx).tables() == want, rx
+        else:
+            with pytest.raises(fx.ReSyntaxError if kind == "syntax" else fx.ReUnsupported):
+                fx.ReTree(rx)
+    assert seen["ok"] > 300 and seen["unsupported"] > 300
+
+
+def test_open_validates_files_like_the_reference(tmp_path, ref_dir):
+    raw = open(os.path.join(ref_dir, "test1024.cmp.bwt"), "rb").read()
+    aux = open(os.path.join(ref_dir, "test1024.cmp.aux"), "rb").read()
+    (tmp_path / "x.bwt").write_bytes(raw[:-1])
+    (tmp_path / "x.aux").write_bytes(aux)
+    with pytest.raises(fx.FmxError) as e:                                   # "File %s bad size" bwtmerger.scala:153
+        fx.GpuFMSearcher(str(tmp_path / "x.bwt"), bigEndian=False)
+    assert e.value.code == fx.FMX_E_FORMAT and "bad size" in str(e.value)
+    with pytest.raises(fx.FmxError) as e:                                   # wrong endianness flag
+        fx.GpuFMSearcher(os.path.join(ref_dir, "test1024.cmp.bwt"), bigEndian=True)
+    assert e.value.code == fx.FMX_E_FORMAT
+    with pytest.raises(fx.FmxError) as e:
+        fx.GpuFMSearcher(str(tmp_path / "missing.fm"))
+    assert e.value.code == fx.FMX_E_IO
+    (tmp_path / "y.bwt").write_bytes(raw)
+    (tmp_path / "y.aux").write_bytes(aux)
+    (tmp_path / "y.fm").write_bytes(bytes([8]) + b"\0" * 8)                 # elSize != 4, bwtmerger.scala:261
+    with pytest.raises(fx.FmxError) as e:
+        fx.GpuFMSearcher(str(tmp_path / "y.aux"), bigEndian=False)
+    assert e.value.code == fx.FMX_E_FORMAT and "elSize" in str(e.value)
+    (tmp_path / "y.fm").write_bytes(bytes([4]) + (1025).to_bytes(8, "little") + b"\0" * 7)     # size rule :262
+    with pytest.raises(fx.FmxError) as e:
+        fx.GpuFMSearcher(str(tmp_path / "y.aux"), bigEndian=False)
+    assert e.value.code == fx.FMX_E_FORMAT
+    os.remove(tmp_path / "y.fm")
+    with pytest.raises(fx.FmxError) as e:                                   # the reference needs the .fm; opt-in strictness
+        fx.GpuFMSearcher(str(tmp_path / "y.bwt"), bigEndian=False, require_fm=True)
+    assert e.value.code == fx.FMX_E_IO
+
+
+def test_no_gpu_means_loud_failure_not_cpu_fallback(ref_dir):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(fx.FmxError) as e:
+        fx.GpuFMSearcher(os.path.join(ref_dir, "test1024.cmp.bwt"), bigEndian=False)
+    assert e.value.code == fx.FMX_E_CUDA and "no CPU fallback" in str(e.value)
+    with pytest.raises(fx.FmxError):
+        fx.build_bwt(b"abracadabra")
