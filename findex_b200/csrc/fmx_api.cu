@@ -285,6 +285,13 @@ int fmx_info(const fmx_index *ix, int32_t *layout, int32_t *levels, int32_t *sig
     if (rate) *rate = ix->sample_rate;
     return FMX_OK;
 }
+int fmx_set_lanes(fmx_index *ix, int32_t lanes) {
+    CHECK_IX(ix);
+    if (lanes != 1 && lanes != 2 && lanes != 4) return fail(FMX_E_ARG, "lanes_per_query must be 1, 2 or 4");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->cfg.lanes = lanes;
+    return FMX_OK;
+}
 double fmx_last_kernel_ms(const fmx_index *ix) { return ix ? ix->last_ms : 0.0; }
 int64_t fmx_last_kernel_launches(const fmx_index *ix) { return ix ? ix->last_launches : 0; }
 

@@ -84,6 +84,7 @@ def lib():
     L.fmx_regex_search_batch.argtypes = [p, p, i64, i64, p, p, p, p]
     L.fmx_count_fixed_stats.argtypes = [p, p, i32, i64, C.POINTER(i64), C.POINTER(i64)]
     L.fmx_gather_bench.argtypes = [p, i32, i32, i64, i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.fmx_set_lanes.argtypes = [p, i32]
     L.fmx_last_kernel_ms.restype = C.c_double
     L.fmx_last_kernel_ms.argtypes = [p]
     L.fmx_last_kernel_launches.restype = i64
@@ -345,6 +346,9 @@ class GpuFMSearcher:
         gbs, ms = C.c_double(), C.c_double()
         _check(lib().fmx_gather_bench(self.h, bytes_per_gather, lanes, gathers, chain, iters, C.byref(gbs), C.byref(ms)))
         return gbs.value, ms.value
+
+    def set_lanes(self, lanes):
+        _check(lib().fmx_set_lanes(self.h, lanes))
 
     def last_kernel_ms(self):
         return lib().fmx_last_kernel_ms(self.h)

@@ -1,0 +1,369 @@
+"""
+GPU parity tests (run with -m gpu on a B200): every call goes through the C ABI (libfmgpu.so) and is compared
+bit-exactly with the CPU oracle on the same inputs, for both rank-structure layouts and every lanes-per-query
+setting.  Fixtures are the reference's own test files (tests/golden/ref) plus seeded synthetic texts.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from findex_b200 import fmindex as fx
+from oracle import fm_oracle as fo
+from oracle import retree
+
+pytestmark = pytest.mark.gpu
+
+LAYOUTS = [fx.LAYOUT_WM, fx.LAYOUT_PLANES]
+LANES = [1, 2, 4]
+CFGS = [(l, g) for l in LAYOUTS for g in LANES]
+
+
+def _ids(v):
+    return "%s-g%d" % ({1: "wm", 2: "planes"}[v[0]], v[1])
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a GPU; the product has no CPU path"
+    from findex_b200 import build
+    build.build()
+
+
+# ----------------------------------------------------------------------------------------------- fixtures
+@pytest.fixture(scope="module")
+def o1024(ref_dir):
+    return fo.OracleIndex.load(os.path.join(ref_dir, "test1024.cmp"), big_endian=False)
+
+
+def _open(path, cfg, big_endian=False, **kw):
+    return fx.GpuFMSearcher(path, bigEndian=big_endian, layout=cfg[0], lanes_per_query=cfg[1], **kw)
+
+
+# ----------------------------------------------------------------------------------------------- G4 on the GPU
+@pytest.mark.parametrize("cfg", CFGS, ids=_ids)
+def test_combined_indexing_test_on_gpu(ref_dir, cfg):
+    """T/Indexer.scala:1079-1124 verbatim, against the GPU searcher."""
+    sa = _open(os.path.join(ref_dir, "test1024.cmp.bwt"), cfg)
+    eof = sa.eof
+    assert sa.n == 1025 and eof == 462
+    assert sa.getPrevI(eof) == 0
+    assert sa.getNextI(eof) == 517
+    assert sa.getPrevI(1) == 48
+    assert sa.getPrevI(48) == 649
+    assert sa.nextSubstr(1, 3) == b"haa"
+    assert sa.nextSubstr(sa.getNextI(eof), 100) == \
+        b"zajrtzbeqwbxdfpwjflmmsseewuudgfbtzqenjqafwzcnfanycigwsflfvxojxpqhhzekjdkhgsptqveavquuoqujbezdkarayom"
+    assert sa.nextSubstr(eof, 100) == \
+        b"ajrtzbeqwbxdfpwjflmmsseewuudgfbtzqenjqafwzcnfanycigwsflfvxojxpqhhzekjdkhgsptqveavquuoqujbezdkarayoml"
+    assert sa.prevSubstr(1, 5) == b"bqxxa"
+    assert sa.prevSubstr(eof, 5) == b"\0uexm"
+    assert sa.prevSubstr(sa.getPrevI(eof), 4) == b"uexm"
+    sa.close()
+
+
+@pytest.mark.parametrize("cfg", CFGS, ids=_ids)
+def test_g1_g2_in_memory_goldens_on_gpu(cfg):
+    """T/Indexer.scala:203-351 (abracadabra, getPrevRange) through fmx_open_mem."""
+    bwt, eof, cnt = fo.build_bwt(b"abracadabra")
+    sa = fx.GpuFMSearcher(bwt=bwt, eof=eof, counts=cnt, layout=cfg[0], lanes_per_query=cfg[1])
+    assert sa.cf(0) == 0 and sa.cf(ord("a")) == 1 and sa.cf(ord("b")) == 6
+    rows = {0: [0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1], ord("a"): [1, 1, 1, 1, 1, 1, 2, 3, 4, 5, 5, 5],
+            ord("b"): [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 2], ord("c"): [0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1],
+            ord("d"): [0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1], ord("r"): [0, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2], ord("x"): [0] * 12}
+    for c, want in rows.items():
+        assert sa.occ_batch([c] * 12, list(range(12))).tolist() == want
+    assert sa.search(b"bra") == (6, 8)
+    assert sa.getPrevI(6) == 2 and sa.getNextI(6) == 10 and sa.getNextI(10) == 1
+    sa.close()
+    bwt, eof, cnt = fo.build_bwt(b"mmabcacadabbbca"[::-1])
+    sa = fx.GpuFMSearcher(bwt=bwt, eof=eof, counts=cnt, layout=cfg[0], lanes_per_query=cfg[1])
+    assert sa.occ(ord("b"), 6) == 3
+    assert sa.getPrevRange(0, 16, ord("a")) == (1, 6)
+    assert sa.getPrevRange(1, 6, ord("b")) == (6, 8)
+    sa.close()
+
+
+# ----------------------------------------------------------------------------------------------- operator parity
+@pytest.mark.parametrize("cfg", CFGS, ids=_ids)
+@pytest.mark.parametrize("name", ["test1024", "test3072", "test"])
+def test_operator_parity_small(ref_dir, cfg, name):
+    o = fo.OracleIndex.load(os.path.join(ref_dir, name + ".cmp"), big_endian=False)
+    g = _open(os.path.join(ref_dir, name + ".cmp.bwt"), cfg, sa_sample_rate=4)
+    n = o.n
+    assert g.n == n and g.eof == o.eof
+    assert [g.cf(c) for c in range(256)] == [o.cf(c) for c in range(256)]
+    # occ: every symbol of interest x every key in [-1, n-1] (+ out-of-text symbols)
+    chars = sorted(set(o.bwt().tolist()) | {0, 1, 96, 123, 255})
+    keys = np.arange(-1, n, dtype=np.int64)
+    for c in chars:
+        got = g.occ_batch(np.full(len(keys), c, np.uint8), keys)
+        want = np.array([o.occ(c, int(k)) for k in keys])
+        assert np.array_equal(got, want), c
+    # getPrevRange on random intervals
+    rng = np.random.default_rng(7)
+    sp = rng.integers(0, n + 1, 4000)
+    ep = rng.integers(0, n + 1, 4000)
+    lo, hi = np.minimum(sp, ep), np.maximum(sp, ep)
+    cc = rng.choice(chars, 4000).astype(np.uint8)
+    a, b = g.prev_range_batch(lo, hi, cc)
+    for i in range(4000):
+        assert (int(a[i]), int(b[i])) == o.prev_range_raw(int(lo[i]), int(hi[i]), int(cc[i]))
+    # getIntervalPrevRange incl. the reference's descending order
+    for (s, e) in [(0, n), (10, 500), (100, 101), (5, 5)]:
+        want, _ = o.getIntervalPrevRange(s, e, ord("a"), ord("z"))
+        assert g.getIntervalPrevRange(s, e, ord("a"), ord("z")) == want
+    # LF / FL for every row, pos2char for every key
+    rows = np.arange(n, dtype=np.int64)
+    assert g.get_prev_i_batch(rows).tolist() == [o.getPrevI(int(r)) for r in rows]
+    assert g.get_next_i_batch(rows).tolist() == [o.getNextI(int(r)) for r in rows]
+    assert [g.pos2char(int(k)) for k in range(0, n, 37)] == [o.pos2char(int(k)) for k in range(0, n, 37)]
+    # extraction
+    sub = rows[::17]
+    assert g.prev_substr_batch(sub, 9) == [o.prevSubstr(int(r), 9) for r in sub]
+    assert g.next_substr_batch(sub, 9) == [o.nextSubstr(int(r), 9) for r in sub]
+    # locate == sorted sa[sp..ep)
+    sa = o.sa().astype(np.int64)
+    ivs = [(0, n), (5, 5), (17, 400), (n - 1, n), (o.eof, o.eof + 1)]
+    off, pos = g.locate_batch([i[0] for i in ivs], [i[1] for i in ivs])
+    for k, (s, e) in enumerate(ivs):
+        assert np.array_equal(pos[off[k]:off[k + 1]], np.sort(sa[s:e]))
+    g.close()
+    o.close()
+
+
+def _patterns(text, rng, m, maxlen):
+    """hits (substrings of the file, reversed as search() wants), near-misses and random bytes"""
+    pats = []
+    for i in range(m):
+        ln = int(rng.integers(0, maxlen + 1))
+        r = i % 4
+        if r < 2 and ln and len(text) > ln:
+            s = int(rng.integers(0, len(text) - ln))
+            p = bytes(text[s:s + ln])[::-1]
+        elif r == 2 and ln and len(text) > ln:
+            s = int(rng.integers(0, len(text) - ln))
+            p = bytearray(bytes(text[s:s + ln])[::-1])
+            p[int(rng.integers(0, ln))] = int(rng.integers(1, 256))
+            p = bytes(p)
+        else:
+            p = bytes(rng.integers(1, 256, ln, dtype=np.uint8))
+        pats.append(p)
+    return pats
+
+
+@pytest.mark.parametrize("cfg", CFGS, ids=_ids)
+def test_count_parity_small(ref_dir, cfg):
+    text = open(os.path.join(ref_dir, "test.txt"), "rb").read()
+    o = fo.OracleIndex.load(os.path.join(ref_dir, "test.cmp"), big_endian=False)
+    g = _open(os.path.join(ref_dir, "test.cmp.bwt"), cfg)
+    rng = np.random.default_rng(11)
+    pats = _patterns(text, rng, 3000, 12) + [b"", b"\0", b"a\0", bytes([200]), b"zzzzzzzzzzzzzzzzzzzzzzzzz"]
+    sp, ep = g.count_batch(pats)
+    for i, p in enumerate(pats):
+        r = o.search(p)
+        assert (int(sp[i]), int(ep[i])) == (r if r else (0, 0)), p
+    assert g.search(b"") == (0, o.n)
+    # fixed-length fast path, incl. ragged tail of the last CTA and odd lengths
+    for ln in (1, 3, 16, 21):
+        arr = np.frombuffer(b"".join(p.ljust(ln, b"q")[:ln] for p in pats[:2999]), np.uint8).reshape(-1, ln)
+        sp, ep = g.count_fixed(arr)
+        osp, oep = o.count_batch(arr.reshape(-1), np.arange(0, arr.size + 1, ln, dtype=np.int64))
+        assert np.array_equal(sp, osp) and np.array_equal(ep, oep)
+    g.close()
+    o.close()
+
+
+# ----------------------------------------------------------------------------------------------- words (config 1)
+@pytest.fixture(scope="module")
+def words(words_base):
+    o = fo.OracleIndex.load(words_base)
+    sa = o.sa()
+    tp = np.zeros(o.n, np.uint8)
+    tp[(sa.astype(np.int64) - 1) % o.n] = o.bwt()
+    return o, bytes(tp[:-1][::-1])
+
+
+@pytest.mark.parametrize("cfg", [(fx.LAYOUT_WM, 4), (fx.LAYOUT_PLANES, 4), (fx.LAYOUT_PLANES, 1), (fx.LAYOUT_WM, 2)], ids=_ids)
+def test_config1_words_count_and_locate(words_base, words, cfg):
+    """BASELINE config 1: 1k word patterns, count + locate, vs the oracle and by brute force on words.txt."""
+    o, text = words
+    g = _open(words_base + ".bwt", cfg, big_endian=True, sa_sample_rate=32)
+    info = g.info()
+    assert info["sigma"] == 28 and (info["levels"] == 5 or info["layout"] == "planes")
+    lines = text.split(b"\r\n")
+    rng = np.random.default_rng(1)
+    pick = rng.choice(len(lines) - 1, 1000, replace=False)
+    ws = [lines[i] for i in pick]
+    pats = [w[::-1] for w in ws] + ws                       # hits, and the un-reversed words as a miss/partial set
+    sp, ep = g.count_batch(pats)
+    osp, oep = [], []
+    for p in pats:
+        r = o.search(p)
+        osp.append(r[0] if r else 0)
+        oep.append(r[1] if r else 0)
+    assert sp.tolist() == osp and ep.tolist() == oep
+    for w, a, b in list(zip(ws, sp, ep))[:100]:
+        assert b - a == text.count(w)
+    off, pos = g.locate_batch(sp, ep)
+    sa = o.sa().astype(np.int64)
+    for k in range(len(pats)):
+        assert np.array_equal(pos[off[k]:off[k + 1]], np.sort(sa[sp[k]:ep[k]]))
+    k = 5                                                   # file offset = (n-1) - pos - len
+    for q in pos[off[k]:off[k + 1]]:
+        f = (o.n - 1) - int(q) - len(ws[k])
+        assert text[f:f + len(ws[k])] == ws[k]
+    assert g.search(b"hello"[::-1]) == (1333929, 1333938)
+    assert g.search(b"ing\r\n"[::-1]) == (40318, 52882)
+    assert g.search(b"zzz") is None
+    g.close()
+
+
+WORDS_RX = [("x(a|b|d|e)c", 90), ("ab?c[d-h]", 1668), ("q(u|a)[a-m]z?k", 22), ("th(e|a)(n|t)\\w", 363), ("b(oo|ee)+k", 158),
+            ("z[aeiou][aeiou]?z", 21), ("a.*(b|c)da.*f", None), ("qu.k", None), ("q\\d", None), ("ab(cd)*ef", None), ("x[a-c]d", None)]
+
+
+@pytest.mark.parametrize("cfg", [(fx.LAYOUT_WM, 4), (fx.LAYOUT_PLANES, 4), (fx.LAYOUT_PLANES, 1)], ids=_ids)
+def test_regex_parity_words(words_base, words, cfg):
+    o, _ = words
+    g = _open(words_base + ".bwt", cfg, big_endian=True)
+    trees = [fx.ReTree(rx, lineOnly=(rx == "a.*(b|c)da.*f")) for rx, _ in WORDS_RX]
+    got = g.regex_search_batch(trees, cap_total=16)         # forces the FMX_E_CAPACITY retry path
+    for (rx, total), res in zip(WORDS_RX, got):
+        want = o.regex_match(rx, line_only=(rx == "a.*(b|c)da.*f"), max_expansions=50_000_000)
+        assert res == want, rx
+        if total is not None:
+            assert sum(e - s for _, s, e in res) == total
+    assert trees[0].matchSA(g) == got[0]
+    g.close()
+
+
+@pytest.mark.parametrize("cfg", CFGS, ids=_ids)
+def test_regex_parity_small(ref_dir, o1024, cfg):
+    g = _open(os.path.join(ref_dir, "test1024.cmp.bwt"), cfg)
+    rxs = ["a.*(b|c)d.*f", "a(a|b|d|e)c", "ab", "q[a-z]q", "a.b", "x\\wy", "a(bc)*d", "k(l|m)+n", "zz?z?", "a+b", "(ab|cd)", "\\w\\w\\wq"]
+    trees = [fx.ReTree(rx) for rx in rxs]
+    got = g.regex_search_batch(trees)
+    for rx, res in zip(rxs, got):
+        assert res == o1024.regex_match(rx), rx
+    # G10: .*(a|b)ca over the toy text -> exactly 2 results
+    bwt, eof, cnt = fo.build_bwt(b"mmabcacamabbbca"[::-1])
+    t = fx.GpuFMSearcher(bwt=bwt, eof=eof, counts=cnt, layout=cfg[0], lanes_per_query=cfg[1])
+    assert fx.ReTree(".*(a|b)ca").matchSA(t) == [(3, 1, 2), (3, 2, 4)]
+    t.close()
+    g.close()
+
+
+# ----------------------------------------------------------------------------------------------- device builder + synthetic texts
+def _english_like(words_text, n_words, seed):
+    rng = np.random.default_rng(seed)
+    vocab = [w for w in words_text.split(b"\r\n") if w]
+    perm = rng.permutation(len(vocab))
+    ranks = np.minimum(rng.zipf(1.0001, n_words) - 1, len(vocab) - 1)
+    out = []
+    for i, r in enumerate(ranks):
+        out.append(vocab[perm[r]])
+        out.append(b"\n" if i % 12 == 11 else b" ")
+    return b"".join(out)
+
+
+def test_device_builder_reproduces_reference_goldens(ref_dir, words_base, words):
+    """Any correct suffix sorter yields the unique BWT: the GPU builder must reproduce the bwtdisk goldens
+    (T/Indexer.scala:638-820) and the reference's own words.bwt/.aux from the raw text."""
+    for name in ["test1024", "test2048", "test2048-2", "test3072", "test", "test-part"]:
+        data = open(os.path.join(ref_dir, name + ".txt"), "rb").read()
+        o = fo.OracleIndex.load(os.path.join(ref_dir, name + ".cmp"), big_endian=False)
+        bwt, eof, cnt = fx.build_bwt(data)
+        assert eof == o.eof and np.array_equal(bwt, o.bwt())
+        aux = np.frombuffer(open(os.path.join(ref_dir, name + ".cmp.aux"), "rb").read(), dtype="<i8")
+        assert np.array_equal(cnt[1:], aux[1:])
+    o, text = words
+    bwt, eof, cnt = fx.build_bwt(text)
+    assert eof == o.eof and np.array_equal(bwt, o.bwt())
+    # zero bytes are dropped like FileBWTReader does; tiny / degenerate texts
+    for t in [b"", b"a", b"aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaa", b"ab\0ab\0ab", b"abababababababababab" * 50]:
+        bwt, eof, cnt = fx.build_bwt(t)
+        wb, weof, wcnt = fo.build_bwt(fo.file_to_text_rev(t))
+        assert eof == weof and np.array_equal(bwt, wb) and np.array_equal(cnt, wcnt)
+
+
+def test_index_files_roundtrip(tmp_path, ref_dir):
+    data = open(os.path.join(ref_dir, "test3072.txt"), "rb").read()
+    base = str(tmp_path / "t3072")
+    fx.build_index_files(data, base + ".txt", bigEndian=True, write_fm=True)
+    o = fo.OracleIndex.load(base)                          # reads the .fm we wrote (FMLoader rules)
+    ref = fo.OracleIndex.load(os.path.join(ref_dir, "test3072.cmp"), big_endian=False)
+    assert o.eof == ref.eof and np.array_equal(o.bwt(), ref.bwt()) and np.array_equal(o.fm(), ref.fm())
+    g = fx.GpuFMSearcher(base + ".fm", require_fm=True)
+    assert g.search(b"ab") == ref.search(b"ab")
+    g.close()
+
+
+@pytest.mark.parametrize("kind", ["random255", "dna", "english"])
+@pytest.mark.parametrize("cfg", [(fx.LAYOUT_WM, 4), (fx.LAYOUT_PLANES, 4), (fx.LAYOUT_WM, 1), (fx.LAYOUT_PLANES, 2)], ids=_ids)
+def test_synthetic_parity(kind, cfg, words, tmp_path):
+    """Scaled-down configs 2/3/5: seeded text -> GPU-built index files -> count / locate / regex vs oracle."""
+    rng = np.random.default_rng({"random255": 2, "dna": 7, "english": 4}[kind])
+    if kind == "random255":
+        text = rng.integers(1, 256, 600_000, dtype=np.uint8).tobytes()
+    elif kind == "dna":
+        text = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 900_000)].tobytes()
+    else:
+        text = _english_like(words[1], 90_000, 4)
+    base = str(tmp_path / kind)
+    fx.build_index_files(text, base, bigEndian=True)
+    o = fo.OracleIndex.load(base)
+    g = _open(base + ".bwt", cfg, big_endian=True, sa_sample_rate=32)
+    info = g.info()
+    if kind == "dna":
+        assert info["sigma"] == 4 and (info["levels"] == 2 or info["layout"] == "planes")
+    if kind == "random255":
+        assert info["sigma"] == 255
+    ln = {"random255": 16, "dna": 32, "english": 12}[kind]
+    m = 20_000
+    offs = rng.integers(0, len(text) - ln, m)
+    tarr = np.frombuffer(text, np.uint8)
+    pats = np.stack([tarr[s:s + ln][::-1] for s in offs])
+    miss = rng.random(m) < 0.1
+    pats[miss] = tarr[rng.integers(0, len(text), (int(miss.sum()), ln))] if kind != "random255" else rng.integers(1, 256, (int(miss.sum()), ln), dtype=np.uint8)
+    sp, ep = g.count_fixed(pats)
+    osp, oep = o.count_batch(pats.reshape(-1), np.arange(0, pats.size + 1, ln, dtype=np.int64), threads=4)
+    assert np.array_equal(sp, osp) and np.array_equal(ep, oep)
+    assert (ep > sp).sum() >= 0.85 * m
+    blocks, steps = g.count_fixed_stats(pats)
+    assert steps >= m and blocks > 0
+    # locate a subset (short prefixes have many occurrences)
+    sub = slice(0, 2000)
+    shortp = pats[sub, ln - 4:]
+    ssp, sep = g.count_fixed(shortp)
+    off, pos = g.locate_batch(ssp, sep)
+    sa = o.sa().astype(np.int64)
+    for k in range(0, 2000, 7):
+        assert np.array_equal(pos[off[k]:off[k + 1]], np.sort(sa[ssp[k]:sep[k]]))
+    # regexes from the config-4 templates
+    lit = lambda k: bytes(text[int(rng.integers(0, len(text) - k)):][:k])
+    esc = lambda b: b"".join((b"\\" + bytes([c])) if c in b"()[]|*+?.\\-" else bytes([c]) for c in b)
+    rxs = []
+    for _ in range(40):
+        a, b2 = sorted(rng.integers(97, 123, 2).tolist())
+        rxs.append(esc(lit(3)) + b"[" + bytes([a]) + b"-" + bytes([b2]) + b"]" + esc(lit(2)))
+        rxs.append(esc(lit(3)) + b"(" + esc(lit(2)) + b"|" + esc(lit(2)) + b"|" + esc(lit(1)) + b")" + esc(lit(1)))
+        rxs.append(esc(lit(2)) + esc(lit(1)) + b"?" + esc(lit(1)) + esc(lit(1)) + b"?" + esc(lit(2)))
+        rxs.append(esc(lit(3)) + b"\\d" + esc(lit(2)))
+        rxs.append(esc(lit(4)) + b"." + esc(lit(2)))
+    trees, keep = [], []
+    for rx in rxs:
+        try:
+            trees.append(fx.ReTree(rx))
+            keep.append(rx)
+        except fx.FmxError:
+            with pytest.raises((retree.ReUnsupported, retree.ReSyntaxError)):
+                retree.compile_regex(rx)
+    assert len(keep) > 100
+    got = g.regex_search_batch(trees)
+    for rx, res in zip(keep, got):
+        assert res == o.regex_match(rx), rx
+    g.close()
+    o.close()
