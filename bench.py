@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""
+bench.py — FM-index count throughput on B200 (BASELINE.json metric: FM count queries/s, len-16, 1 GB text).
+
+    python bench.py --gpus N --steps K --warmup W                (this repo's CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (the reference algorithm on the host CPU cores)
+
+Workload (BASELINE.json configs[1], SURVEY.md §8d cfg 2): 10^9 bytes i.i.d. uniform over 1..255 (seed 2), indexed as
+the reference does (reverse(text)+'$', .bwt/.aux files); per GPU 10 M len-16 patterns, 90 % substrings of the text
+(reversed, as search() consumes them) and 10 % uniform random bytes (seed 3).  A "step" is one pass of the batch
+through the count kernel.  With N GPUs the index is replicated, every rank owns its own 10 M-query shard (weak
+scaling) and the per-query counts are all-gathered over NCCL; time is the max over ranks of CUDA-event time.
+
+One JSON line on stdout (rank 0).  Everything else goes to stderr.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fm_count_queries_per_s_len16_1GB_text"
+UNIT = "queries/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def make_text(n, seed=2):
+    return np.random.default_rng(seed).integers(1, 256, n, dtype=np.uint8)
+
+
+def make_queries(text, m, ln, seed, rank, out=None):
+    """90 % hits (reversed substrings at uniform offsets), 10 % uniform random bytes; shuffled."""
+    rng = np.random.default_rng([seed, rank])
+    nh = int(m * 0.9)
+    pats = out if out is not None else np.empty((m, ln), np.uint8)
+    offs = rng.integers(0, len(text) - ln, nh)
+    idx = offs[:, None] + np.arange(ln - 1, -1, -1)[None, :]
+    hits = text[idx]
+    rnd = rng.integers(1, 256, (m - nh, ln), dtype=np.uint8)
+    perm = rng.permutation(m)
+    is_hit = np.zeros(m, bool)
+    is_hit[:nh] = True
+    allp = np.concatenate([hits, rnd])
+    pats[:] = allp[perm]
+    return pats, is_hit[perm], np.concatenate([offs, np.full(m - nh, -1)])[perm]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons, sampled every 50 ms from before the warm-up until after the timed region;
+    the summary uses the samples that fall inside the timed window (all samples under load if the window is shorter
+    than the sampling period)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.rows = []
+        self.proc = None
+        self.window = [None, None]
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception as e:                       # nvidia-smi missing: report that, do not fail the bench
+            log("clock sampler unavailable:", e)
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.window[0] = time.time()
+
+    def mark_end(self):
+        self.window[1] = time.time()
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        parsed = []
+        for ts, r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                parsed.append((ts, float(f[0]), float(f[1]), float(f[2]), [nme for nme, v in zip(names, f[3:7]) if v == "Active"]))
+            except ValueError:
+                continue
+        inside = [p for p in parsed if self.window[0] is not None and self.window[0] <= p[0] <= (self.window[1] or 1e18) + 0.06]
+        use = inside if inside else parsed
+        reasons = sorted({x for p in use for x in p[4]})
+        return {"sm_mhz": float(np.median([p[1] for p in use])) if use else None, "sm_max_mhz": max([p[2] for p in use]) if use else None,
+                "power_w_max": max([p[3] for p in use]) if use else None, "reasons": reasons, "samples": len(use),
+                "samples_in_timed_window": len(inside)}
+
+
+def index_base(n):
+    return "/tmp/fmx_bench_cfg2_%d" % n
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path: NaiveFMSearcher.occ = binary search in the in-memory .fm
+    array (bwtmerger.scala:354-375) driving SuffixAlgo.search (findex.scala:15-31) — the C restatement under oracle/
+    (no JVM exists in this image), all host threads, a bounded sample of the same workload per step."""
+    if rank != 0:
+        return
+    from oracle import fm_oracle as fo
+    cores = os.cpu_count() or 1
+    n, m, ln = args.text_bytes, args.queries, args.len
+    t0 = time.time()
+    text = make_text(n)
+    base = index_base(n)
+    if not (os.path.exists(base + ".bwt") and os.path.exists(base + ".aux")):
+        # index construction is setup, not the measured path; the device suffix sorter only writes the reference's files
+        from findex_b200 import build as fbuild, fmindex as fx
+        fbuild.build()
+        fx.build_index_files(text, base, bigEndian=True)
+    fo.build(native=True)
+    ix = fo.OracleIndex.load(base)
+    log("reference arm: index loaded + fm array materialised in %.1f s" % (time.time() - t0))
+    pats, _, _ = make_queries(text, m, ln, 3, 0)
+    probe = 20000
+    t1 = time.time()
+    ix.count_batch(pats[:probe].reshape(-1), np.arange(0, probe * ln + 1, ln, dtype=np.int64), threads=cores)
+    rate = probe / max(time.time() - t1, 1e-6)
+    budget_s = 120.0 / max(args.steps + args.warmup, 1)
+    sample = int(min(m, max(probe, rate * min(budget_s, 8.0))))
+    off = np.arange(0, sample * ln + 1, ln, dtype=np.int64)
+    flat = pats[:sample].reshape(-1)
+    for _ in range(args.warmup):
+        ix.count_batch(flat, off, threads=cores)
+    t1 = time.time()
+    for _ in range(args.steps):
+        ix.count_batch(flat, off, threads=cores)
+    dt = time.time() - t1
+    v = sample * args.steps / dt
+    sdesc = "first %d of the %d-query batch per step, %d threads" % (sample, m, cores)
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+           "data": "synthetic", "config": workload_config(args),
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sdesc,
+                            "note": "JVM unavailable - C restatement of the reference algorithm (binary search in .fm)"},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "cfg2: 1e9-byte uniform text over bytes 1..255 (seed 2), %d len-%d count queries per GPU, 90%% hits / 10%% random "
+                        "(seed 3)" % (args.queries, args.len),
+            "text_bytes": args.text_bytes, "queries_per_gpu": args.queries, "pattern_len": args.len, "parallelism": "dp%d (index replicated, "
+            "queries sharded)" % args.gpus, "l2": "inputs (160 MB patterns) and index (GBs) exceed the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from findex_b200 import build as fbuild, fmindex as fx
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    n, m, ln = args.text_bytes, args.queries, args.len
+    if rank == 0:
+        fbuild.build()
+    if world > 1:
+        dist.barrier()
+    t0 = time.time()
+    text = make_text(n)
+    base = index_base(n)
+    if rank == 0 and not (os.path.exists(base + ".bwt") and os.path.exists(base + ".aux")):
+        tb = time.time()
+        fx.build_index_files(text, base, bigEndian=True)
+        log("index files built on the GPU in %.1f s" % (time.time() - tb))
+    if world > 1:
+        dist.barrier()
+    layout = {"auto": fx.LAYOUT_AUTO, "wm": fx.LAYOUT_WM, "planes": fx.LAYOUT_PLANES}[args.layout]
+    g = fx.GpuFMSearcher(base + ".bwt", bigEndian=True, device=local_rank, layout=layout, lanes_per_query=args.lanes)
+    info = g.info()
+    log("rank %d: index open (%s, %.2f GB on device) after %.1f s" % (rank, info["layout"], info["index_bytes"] / 1e9, time.time() - t0))
+
+    h_pat = fx.PinnedArray((m, ln), np.uint8)
+    h_sp = fx.PinnedArray((m,), np.int64)
+    h_ep = fx.PinnedArray((m,), np.int64)
+    pats, is_hit, offs = make_queries(text, m, ln, 3, rank, out=h_pat.array)
+    d_pat = torch.from_numpy(pats).to(dev)
+    d_sp = torch.zeros(m, dtype=torch.int32, device=dev)
+    d_ep = torch.zeros(m, dtype=torch.int32, device=dev)
+    d_cnt = torch.zeros(m, dtype=torch.int32, device=dev)
+    d_all = torch.zeros(m * world, dtype=torch.int32, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        g.count_fixed_dev(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), stream)
+        if world > 1:                                   # the one exchange step: all-gather of the hit counts
+            torch.sub(d_ep, d_sp, out=d_cnt)
+            dist.all_gather_into_tensor(d_all, d_cnt)
+
+    # ---- sanity at full size (parity proper lives in tests/): hits are found, a few are verified by brute force
+    step()
+    torch.cuda.synchronize()
+    sp = d_sp.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    ep = d_ep.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    cnt = ep - sp
+    assert (cnt[is_hit] >= 1).all(), "a text substring was not found"
+    if rank == 0:
+        tb = text.tobytes()
+        for q in np.flatnonzero(is_hit)[:2]:
+            needle = pats[q][::-1].tobytes()
+            assert tb.count(needle) == cnt[q], "count mismatch vs brute force"
+        del tb
+    checksum = int((sp * 1315423911 + ep * 2654435761).sum() & 0xFFFFFFFFFFFF)
+
+    # ---- roofline inputs, outside the timed region
+    blocks, steps_exec = g.count_fixed_stats(pats)
+    alg_bytes = blocks * 64
+    r_rand, _ = g.gather_bench(64, 4, 1 << 25, 16, 3)
+
+    def timed_region(fn, label):
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        for _ in range(args.warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler.mark_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.time()
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.time() - t_wall
+        sampler.mark_end()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        ms = e0.elapsed_time(e1)
+        if label == "e2e":
+            ms = wall * 1e3                              # host API: the call returns when results are in host memory
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), clocks
+
+    ms_total, clocks = timed_region(step, "device")
+    # kernel-only time (same launches, no exchange) for the roofline
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in kev:
+        a.record()
+        g.count_fixed_dev(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), stream)
+        b.record()
+    torch.cuda.synchronize()
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+
+    def e2e_step():
+        g.count_fixed_into(h_pat.array, h_sp.array, h_ep.array)
+
+    ms_e2e, clocks_e2e = timed_region(e2e_step, "e2e")
+    assert np.array_equal(h_sp.array, np.where(cnt > 0, sp, 0)) and np.array_equal(h_ep.array, np.where(cnt > 0, ep, 0)), "host API result differs from device API"
+
+    value = world * m * args.steps / (ms_total * 1e-3)
+    e2e = world * m * args.steps / (ms_e2e * 1e-3)
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")          # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tp):
+        try:
+            rec = json.load(open(tp)).get("count_fixed_kernel", {})
+            if rec.get("queries") == m and rec.get("layout") == info["layout"]:
+                traffic = rec.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+           "data": "synthetic", "config": dict(workload_config(args), layout=info["layout"], lanes_per_query=args.lanes or 4,
+                                               index_bytes=info["index_bytes"], checksum=checksum),
+           "clocks": clocks,
+           "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": m * ln, "d2h_bytes_per_step": m * 16, "ms_per_step": ms_e2e / args.steps,
+                   "api": "fmx_count_fixed (host pinned buffers in/out, int64 sp/ep)", "clocks": clocks_e2e},
+           "gpu_launches": args.steps,
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                        "peak_source": peak_src, "kernel": "count_fixed_kernel", "kernel_ms": k_ms,
+                        "algorithmic_bytes_per_launch": alg_bytes, "distinct_blocks_per_query": blocks / m, "executed_steps_per_query": steps_exec / m,
+                        "r_rand_gbs": r_rand, "frac_of_r_rand": achieved / r_rand,
+                        "note": "achieved = distinct 64-B rank blocks the batch touches x 64 B / kernel time; r_rand = live K4 random 64-B gather "
+                                "bandwidth over the same index (the random-sector HBM roofline of north_star)"}}
+    if world == 1 and rank == 0 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(args, base, pats, sp, ep, cnt)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    g.close()
+
+
+def cpu_baseline(args, base, pats, sp, ep, cnt):
+    """The oracle (C restatement of the reference algorithm) on the box's host cores, on a bounded sample of the same batch;
+    doubles as the full-size parity check of that sample."""
+    from oracle import fm_oracle as fo
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    fo.build(native=True)
+    ix = fo.OracleIndex.load(base)
+    log("cpu_baseline: oracle index ready in %.1f s" % (time.time() - t0))
+    ln = args.len
+    probe = 20000
+    t1 = time.time()
+    ix.count_batch(pats[:probe].reshape(-1), np.arange(0, probe * ln + 1, ln, dtype=np.int64), threads=cores)
+    rate = probe / max(time.time() - t1, 1e-6)
+    sample = int(min(len(pats), max(probe, rate * 15.0)))
+    off = np.arange(0, sample * ln + 1, ln, dtype=np.int64)
+    t1 = time.time()
+    osp, oep = ix.count_batch(pats[:sample].reshape(-1), off, threads=cores)
+    dt = time.time() - t1
+    want_sp = np.where(cnt[:sample] > 0, sp[:sample], 0)
+    want_ep = np.where(cnt[:sample] > 0, ep[:sample], 0)
+    parity = bool(np.array_equal(osp, want_sp) and np.array_equal(oep, want_ep))
+    assert parity, "GPU (sp,ep) differ from the oracle on the CPU-baseline sample"
+    ix.close()
+    return {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "first %d of the %d-query batch, %d threads, %.1f s" % (sample, len(pats), cores, dt),
+            "parity_on_sample": parity, "note": "JVM unavailable - C restatement of the reference algorithm (binary search in .fm)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--text-bytes", type=int, default=1_000_000_000)
+    ap.add_argument("--queries", type=int, default=10_000_000)
+    ap.add_argument("--len", type=int, default=16)
+    ap.add_argument("--layout", default="auto", choices=["auto", "wm", "planes"])
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        log("note: contract asks for >= 3 warm-up steps; got", args.warmup)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -19,8 +19,9 @@ using namespace fmx;
 
 struct fmx_index {
     int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_alloc = nullptr;
+    int64_t chunk_queries = 0;
     DevIndex d{};
     LaunchCfg cfg{FMX_LAYOUT_WM, 4};
     int64_t n = 0, eof = 0;
@@ -192,10 +193,19 @@ int new_index(const fmx_opts *opts, fmx_index **out, fmx_opts *resolved) {
     if (rc) return rc;
     fmx_index *ix = new fmx_index();
     ix->device = dev;
-    if (cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ix->ev0) != cudaSuccess ||
-        cudaEventCreate(&ix->ev1) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ix->h2d, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ix->d2h, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ix->ev0) != cudaSuccess ||
+        cudaEventCreate(&ix->ev1) != cudaSuccess || cudaEventCreateWithFlags(&ix->ev_alloc, cudaEventDisableTiming) != cudaSuccess) {
         delete ix;
         return fail(FMX_E_CUDA, "cannot create CUDA stream/events");
+    }
+    {   // keep freed stream-ordered allocations cached in the pool: batch calls reuse them instead of re-mapping
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
     }
     *out = ix;
     *resolved = o;
@@ -263,6 +273,9 @@ int fmx_close(fmx_index *ix) {
     for (void *p : ix->owned) cudaFree(p);
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);
+    if (ix->ev_alloc) cudaEventDestroy(ix->ev_alloc);
+    if (ix->h2d) cudaStreamDestroy(ix->h2d);
+    if (ix->d2h) cudaStreamDestroy(ix->d2h);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
     return FMX_OK;
@@ -290,6 +303,25 @@ int fmx_set_lanes(fmx_index *ix, int32_t lanes) {
     if (lanes != 1 && lanes != 2 && lanes != 4) return fail(FMX_E_ARG, "lanes_per_query must be 1, 2 or 4");
     std::lock_guard<std::mutex> lk(ix->mu);
     ix->cfg.lanes = lanes;
+    return FMX_OK;
+}
+int fmx_set_chunk(fmx_index *ix, int64_t queries_per_chunk) {
+    CHECK_IX(ix);
+    if (queries_per_chunk < 0) return fail(FMX_E_ARG, "bad chunk");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->chunk_queries = queries_per_chunk;
+    return FMX_OK;
+}
+int fmx_host_alloc(void **p, int64_t bytes) {
+    if (!p || bytes < 0) return fail(FMX_E_ARG, "bad argument");
+    int dev = 0;
+    int rc = ensure_device(-1, &dev);
+    if (rc) return rc;
+    CU(cudaHostAlloc(p, (size_t)(bytes ? bytes : 1), cudaHostAllocPortable));
+    return FMX_OK;
+}
+int fmx_host_free(void *p) {
+    if (p) CU(cudaFreeHost(p));
     return FMX_OK;
 }
 double fmx_last_kernel_ms(const fmx_index *ix) { return ix ? ix->last_ms : 0.0; }
@@ -395,6 +427,10 @@ int fmx_count_fixed_dev(fmx_index *ix, const void *d_pat, int32_t len, int64_t m
     return FMX_OK;
 }
 
+// Host-buffer count: the batch is cut into chunks that flow through three streams — H2D of chunk k+1, the count
+// kernel on chunk k and the D2H of chunk k-1 overlap (PCIe is full duplex).  With pinned (fmx_host_alloc'ed or
+// cudaHostRegister'ed) caller buffers every copy is an asynchronous DMA; with pageable buffers the driver stages
+// the copies and the pipeline degrades gracefully to copy-then-compute.
 int fmx_count_fixed(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, int64_t *sp, int64_t *ep) {
     CHECK_IX(ix);
     if (len < 0 || m < 0 || (m && (!sp || !ep || (len && !pat)))) return fail(FMX_E_ARG, "bad argument");
@@ -404,16 +440,40 @@ int fmx_count_fixed(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, i
     cudaStream_t st = ix->stream;
     DBuf dp(st), dsp(st), dep(st);
     CU(dp.alloc((size_t)m * len)); CU(dsp.alloc(m * 8)); CU(dep.alloc(m * 8));
-    if (len) CU(cudaMemcpyAsync(dp.p, pat, (size_t)m * len, cudaMemcpyHostToDevice, st));
+    const int64_t chunk = ix->chunk_queries > 0 ? ix->chunk_queries : (1 << 20);
+    const int64_t nchunks = (m + chunk - 1) / chunk;
+    std::vector<cudaEvent_t> ev_in((size_t)nchunks), ev_k((size_t)nchunks);
+    for (int64_t k = 0; k < nchunks; ++k) {
+        CU(cudaEventCreateWithFlags(&ev_in[(size_t)k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ev_k[(size_t)k], cudaEventDisableTiming));
+    }
+    // the copy streams may touch the stream-ordered allocations only after the allocating stream reached this point
+    CU(cudaEventRecord(ix->ev_alloc, st));
+    CU(cudaStreamWaitEvent(ix->h2d, ix->ev_alloc, 0));
+    CU(cudaStreamWaitEvent(ix->d2h, ix->ev_alloc, 0));
     Timed t(ix);
-    CU(launch_count_fixed(ix->d, ix->cfg, dp.as<uint8_t>(), len, m, dsp.p, dep.p, true, nullptr, st));
-    ix->last_launches = 1; ix->total_launches += 1;
+    int rc = FMX_OK;
+    for (int64_t k = 0; k < nchunks && rc == FMX_OK; ++k) {
+        const int64_t q0 = k * chunk, nq = std::min(chunk, m - q0);
+        cudaError_t e = cudaSuccess;
+        if (len) e = cudaMemcpyAsync(dp.as<uint8_t>() + q0 * len, pat + q0 * len, (size_t)nq * len, cudaMemcpyHostToDevice, ix->h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_in[(size_t)k], ix->h2d);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev_in[(size_t)k], 0);
+        if (e == cudaSuccess) e = launch_count_fixed(ix->d, ix->cfg, dp.as<uint8_t>() + q0 * len, len, nq, dsp.as<int64_t>() + q0, dep.as<int64_t>() + q0, true, nullptr, st);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_k[(size_t)k], st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ix->d2h, ev_k[(size_t)k], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(sp + q0, dsp.as<int64_t>() + q0, (size_t)nq * 8, cudaMemcpyDeviceToHost, ix->d2h);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ep + q0, dep.as<int64_t>() + q0, (size_t)nq * 8, cudaMemcpyDeviceToHost, ix->d2h);
+        if (e != cudaSuccess) rc = fail(FMX_E_CUDA, "CUDA error %s in the count pipeline (%s)", cudaGetErrorName(e), cudaGetErrorString(e));
+    }
+    ix->last_launches = nchunks; ix->total_launches += nchunks;
     t.stop();
-    CU(cudaMemcpyAsync(sp, dsp.p, m * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(ep, dep.p, m * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    cudaError_t e1 = cudaStreamSynchronize(ix->h2d), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(ix->d2h);
+    for (int64_t k = 0; k < nchunks; ++k) { cudaEventDestroy(ev_in[(size_t)k]); cudaEventDestroy(ev_k[(size_t)k]); }
+    if (rc == FMX_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess))
+        rc = fail(FMX_E_CUDA, "CUDA error while draining the count pipeline");
     t.collect();
-    return FMX_OK;
+    return rc;
 }
 
 int fmx_count_batch(fmx_index *ix, const uint8_t *pat, const int64_t *off, int64_t m, int64_t *sp, int64_t *ep) {

@@ -85,6 +85,9 @@ def lib():
     L.fmx_count_fixed_stats.argtypes = [p, p, i32, i64, C.POINTER(i64), C.POINTER(i64)]
     L.fmx_gather_bench.argtypes = [p, i32, i32, i64, i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.fmx_set_lanes.argtypes = [p, i32]
+    L.fmx_set_chunk.argtypes = [p, i64]
+    L.fmx_host_alloc.argtypes = [pp, i64]
+    L.fmx_host_free.argtypes = [p]
     L.fmx_last_kernel_ms.restype = C.c_double
     L.fmx_last_kernel_ms.argtypes = [p]
     L.fmx_last_kernel_launches.restype = i64
@@ -347,6 +350,15 @@ class GpuFMSearcher:
         _check(lib().fmx_gather_bench(self.h, bytes_per_gather, lanes, gathers, chain, iters, C.byref(gbs), C.byref(ms)))
         return gbs.value, ms.value
 
+    def set_chunk(self, queries_per_chunk):
+        _check(lib().fmx_set_chunk(self.h, queries_per_chunk))
+
+    def count_fixed_into(self, pat2d, sp, ep):
+        """Like count_fixed but into caller-owned int64 arrays (pinned arrays make the copies asynchronous)."""
+        m, ln = pat2d.shape
+        assert pat2d.flags.c_contiguous and pat2d.dtype == np.uint8 and sp.dtype == np.int64 and ep.dtype == np.int64
+        _check(lib().fmx_count_fixed(self.h, _ptr(pat2d), ln, m, _ptr(sp), _ptr(ep)))
+
     def set_lanes(self, lanes):
         _check(lib().fmx_set_lanes(self.h, lanes))
 
@@ -355,6 +367,24 @@ class GpuFMSearcher:
 
     def last_kernel_launches(self):
         return lib().fmx_last_kernel_launches(self.h)
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory from fmx_host_alloc; keep the object alive while the view is used."""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _check(lib().fmx_host_alloc(C.byref(p), self.nbytes))
+        self.p = p
+        buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.p:
+            self.array = None
+            lib().fmx_host_free(self.p)
+            self.p = None
 
 
 def build_bwt(text, device=-1):

@@ -143,6 +143,13 @@ int fmx_count_fixed_stats(fmx_index *ix, const uint8_t *pat, int32_t len, int64_
 int fmx_gather_bench(fmx_index *ix, int32_t bytes_per_gather, int32_t lanes, int64_t gathers, int32_t chain,
                      int32_t iters, double *gbs, double *ms);
 /* Time of the last *_batch call's kernel section in ms (CUDA events on the library's stream).          */
+/* Page-locked host buffers: batch calls given such buffers copy by asynchronous DMA and overlap the copies
+ * with the kernels (a JVM host wraps the pointer as a direct ByteBuffer).  Any host pointer is accepted by the
+ * batch calls; pageable memory just copies slower.                                                      */
+int fmx_host_alloc(void **p, int64_t bytes);
+int fmx_host_free(void *p);
+/* Queries per pipeline chunk of the host-buffer count calls (0 = default 2^20).                          */
+int fmx_set_chunk(fmx_index *ix, int64_t queries_per_chunk);
 /* Re-selects how many lanes (1, 2 or 4) cooperate on one 64-B rank block for subsequent calls.           */
 int fmx_set_lanes(fmx_index *ix, int32_t lanes_per_query);
 double fmx_last_kernel_ms(const fmx_index *ix);

@@ -18,11 +18,18 @@ _SRC = os.path.join(_HERE, "fm_oracle.c")
 _SO = os.path.join(_HERE, "libfm_oracle.so")
 
 
-def build(force=False):
-    """gcc -O3 the C restatement into oracle/libfm_oracle.so (git-ignored; travels with gpurun)."""
-    if force or (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
-        subprocess.check_call(["gcc", "-O3", "-march=x86-64-v2", "-fPIC", "-shared", "-pthread", "-o", _SO, _SRC])
-    return _SO
+def build(force=False, native=False):
+    """gcc -O3 the C restatement into oracle/libfm_oracle.so (git-ignored; travels with gpurun).  native=True builds a
+    -march=native copy on the machine it will be timed on (bench.py's CPU legs) and makes lib() use it."""
+    global _SO, _lib
+    so = os.path.join(_HERE, "libfm_oracle_native.so" if native else "libfm_oracle.so")
+    if force or native or (not os.path.exists(so)) or os.path.getmtime(so) < os.path.getmtime(_SRC):
+        subprocess.check_call(["gcc", "-O3", "-march=native" if native else "-march=x86-64-v2", "-fPIC", "-shared", "-pthread",
+                               "-Wno-format-truncation", "-o", so, _SRC])
+    if so != _SO:
+        _SO = so
+        _lib = None
+    return so
 
 
 _lib = None
@@ -31,7 +38,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        L = C.CDLL(build())
+        L = C.CDLL(build() if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC) else _SO)
         p, i64, i32, u8p = C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_uint8)
         L.fmo_last_error.restype = C.c_char_p
         L.fmo_from_memory.restype = p
