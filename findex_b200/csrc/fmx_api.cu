@@ -312,6 +312,16 @@ int fmx_set_chunk(fmx_index *ix, int64_t queries_per_chunk) {
     ix->chunk_queries = queries_per_chunk;
     return FMX_OK;
 }
+int fmx_set_l2_fetch_granularity(int32_t bytes, int32_t *effective) {
+    int dev = 0;
+    int rc = ensure_device(-1, &dev);
+    if (rc) return rc;
+    if (bytes > 0) CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+    size_t v = 0;
+    CU(cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity));
+    if (effective) *effective = (int32_t)v;
+    return FMX_OK;
+}
 int fmx_host_alloc(void **p, int64_t bytes) {
     if (!p || bytes < 0) return fail(FMX_E_ARG, "bad argument");
     int dev = 0;

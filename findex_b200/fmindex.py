@@ -86,6 +86,7 @@ def lib():
     L.fmx_gather_bench.argtypes = [p, i32, i32, i64, i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.fmx_set_lanes.argtypes = [p, i32]
     L.fmx_set_chunk.argtypes = [p, i64]
+    L.fmx_set_l2_fetch_granularity.argtypes = [i32, C.POINTER(i32)]
     L.fmx_host_alloc.argtypes = [pp, i64]
     L.fmx_host_free.argtypes = [p]
     L.fmx_last_kernel_ms.restype = C.c_double
@@ -385,6 +386,12 @@ class PinnedArray:
             self.array = None
             lib().fmx_host_free(self.p)
             self.p = None
+
+
+def set_l2_fetch_granularity(nbytes=0):
+    eff = C.c_int32()
+    _check(lib().fmx_set_l2_fetch_granularity(nbytes, C.byref(eff)))
+    return eff.value
 
 
 def build_bwt(text, device=-1):

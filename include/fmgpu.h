@@ -148,6 +148,9 @@ int fmx_gather_bench(fmx_index *ix, int32_t bytes_per_gather, int32_t lanes, int
  * batch calls; pageable memory just copies slower.                                                      */
 int fmx_host_alloc(void **p, int64_t bytes);
 int fmx_host_free(void *p);
+/* cudaLimitMaxL2FetchGranularity of the current device (32/64/128; 0 = only query).  Random 64-B block fetches
+ * over-fetch from DRAM when the L2 promotes misses to 128 B; see DESIGN.md §5.                              */
+int fmx_set_l2_fetch_granularity(int32_t bytes, int32_t *effective);
 /* Queries per pipeline chunk of the host-buffer count calls (0 = default 2^20).                          */
 int fmx_set_chunk(fmx_index *ix, int64_t queries_per_chunk);
 /* Re-selects how many lanes (1, 2 or 4) cooperate on one 64-B rank block for subsequent calls.           */

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--layouts", default="wm,planes")
     ap.add_argument("--out", default="gpurun_out/microbench.jsonl")
     ap.add_argument("--gather", type=int, default=1)
+    ap.add_argument("--l2fetch", default="0")
     args = ap.parse_args()
     fbuild.build()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
@@ -70,6 +71,23 @@ def main():
         emit(what="open", open_s=time.time() - t0, **g.info())
         blocks, steps = g.count_fixed_stats(pats[:2_000_000])
         emit(what="stats", layout=lay, queries=2_000_000, blocks=blocks, steps=steps, bytes_per_query=blocks * 64 / 2e6)
+        for l2f in [int(x) for x in args.l2fetch.split(",")]:
+            eff = fx.set_l2_fetch_granularity(l2f)
+            for nbytes, lanes in ((32, 2), (64, 4), (128, 4)):
+                gbs, ms = g.gather_bench(nbytes, lanes, 1 << 25, 16, 3)
+                emit(what="gather_l2fetch", layout=lay, l2fetch_req=l2f, l2fetch_eff=eff, bytes=nbytes, lanes=lanes, gbs=gbs, ggathers_per_s=gbs / nbytes)
+            g.set_lanes(4)
+            st = torch.cuda.current_stream().cuda_stream
+            for _ in range(2):
+                g.count_fixed_dev(d_pat.data_ptr(), args.len, args.m, d_sp.data_ptr(), d_ep.data_ptr(), st)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                g.count_fixed_dev(d_pat.data_ptr(), args.len, args.m, d_sp.data_ptr(), d_ep.data_ptr(), st)
+            e1.record()
+            torch.cuda.synchronize()
+            emit(what="count_l2fetch", layout=lay, l2fetch_req=l2f, l2fetch_eff=eff, ms=e0.elapsed_time(e1) / 5)
         for lanes in (1, 2, 4):
             g.set_lanes(lanes)
             st = torch.cuda.current_stream().cuda_stream
