@@ -208,7 +208,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     layout = {"auto": fx.LAYOUT_AUTO, "wm": fx.LAYOUT_WM, "planes": fx.LAYOUT_PLANES}[args.layout]
-    g = fx.GpuFMSearcher(base + ".bwt", bigEndian=True, device=local_rank, layout=layout, lanes_per_query=args.lanes)
+    accel = {"auto": fx.ACCEL_AUTO, "none": fx.ACCEL_NONE, "kmer": fx.ACCEL_KMER, "text": fx.ACCEL_TEXT, "both": fx.ACCEL_KMER | fx.ACCEL_TEXT}[args.accel]
+    g = fx.GpuFMSearcher(base + ".bwt", bigEndian=True, device=local_rank, layout=layout, lanes_per_query=args.lanes, accel=accel)
     info = g.info()
     log("rank %d: index open (%s, %.2f GB on device) after %.1f s" % (rank, info["layout"], info["index_bytes"] / 1e9, time.time() - t0))
 
@@ -311,8 +312,8 @@ def run_ours(args, rank, world, local_rank):
             pass
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-           "data": "synthetic", "config": dict(workload_config(args), layout=info["layout"], lanes_per_query=args.lanes or 4,
-                                               index_bytes=info["index_bytes"], checksum=checksum),
+           "data": "synthetic", "config": dict(workload_config(args), layout=info["layout"], lanes_per_query=info["lanes_per_query"],
+                                               index_bytes=info["index_bytes"], kmer_k=info["kmer_k"], text_shortcut=info["text_shortcut"], checksum=checksum),
            "clocks": clocks,
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": m * ln, "d2h_bytes_per_step": m * 16, "ms_per_step": ms_e2e / args.steps,
                    "api": "fmx_count_fixed (host pinned buffers in/out, int64 sp/ep)", "clocks": clocks_e2e},
@@ -370,6 +371,7 @@ def main():
     ap.add_argument("--len", type=int, default=16)
     ap.add_argument("--layout", default="auto", choices=["auto", "wm", "planes"])
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--accel", default="auto", choices=["auto", "none", "kmer", "text", "both"])
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

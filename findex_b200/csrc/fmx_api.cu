@@ -22,6 +22,8 @@ struct fmx_index {
     cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_alloc = nullptr;
     int64_t chunk_queries = 0;
+    bool accel_text = false;
+    int kmer_k = 0;
     DevIndex d{};
     LaunchCfg cfg{FMX_LAYOUT_WM, 4};
     int64_t n = 0, eof = 0;
@@ -118,7 +120,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
         layout = (planes_bytes <= budget && planes_bytes + (6ll << 30) + 2 * n < (int64_t)fr) ? FMX_LAYOUT_PLANES : FMX_LAYOUT_WM;
     }
     if (layout != FMX_LAYOUT_WM && layout != FMX_LAYOUT_PLANES) return fail(FMX_E_ARG, "bad layout %d", layout);
-    int lanes = o.lanes_per_query ? o.lanes_per_query : 4;
+    int lanes = o.lanes_per_query ? o.lanes_per_query : 2;      // re-tuned below once the accelerators are known
     if (lanes != 1 && lanes != 2 && lanes != 4) return fail(FMX_E_ARG, "lanes_per_query must be 1, 2 or 4");
     ix->cfg = LaunchCfg{layout, lanes};
     ix->index_bytes = (layout == FMX_LAYOUT_PLANES ? planes_bytes : wm_bytes) + n;
@@ -164,6 +166,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
 
     DevIndex &d = ix->d;
     d.blocks = (const uint4 *)blocks; d.stride = (uint64_t)nblk; d.bwt = d_bwt; d.C = d_C; d.base = d_base; d.code = d_code;
+    d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isa = nullptr; d.text = nullptr;
     d.mark = nullptr; d.samples = nullptr; d.n = (uint32_t)n; d.eof = (uint32_t)eof; d.layout = layout; d.levels = levels;
     for (int l = 0; l < 8; ++l) d.z[l] = z[l];
 
@@ -180,6 +183,45 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
         ix->n_samples = ns;
         ix->index_bytes += nblk * 64 + ns * 4;
     }
+    // ---- optional accelerators ---------------------------------------------------------------------------
+    int accel = o.accel;
+    if (accel & FMX_ACCEL_NONE) accel = FMX_ACCEL_NONE;
+    size_t fr = 0, to = 0;
+    cudaMemGetInfo(&fr, &to);
+    const bool want_text = (accel & FMX_ACCEL_TEXT) || (accel == FMX_ACCEL_AUTO && 9 * n + (2ll << 30) < (int64_t)fr && ix->index_bytes + 9 * n <= budget + (16ll << 30));
+    const bool want_kmer = (accel & FMX_ACCEL_KMER) || accel == FMX_ACCEL_AUTO;
+    if (want_text && n > 2) {
+        void *sa = nullptr, *isa = nullptr, *text = nullptr;
+        e = cudaMalloc(&sa, (size_t)n * 4); CU(e); ix->owned.push_back(sa);
+        e = cudaMalloc(&isa, (size_t)n * 4); CU(e); ix->owned.push_back(isa);
+        e = cudaMalloc(&text, (size_t)n + 16); CU(e); ix->owned.push_back(text);
+        std::string err;
+        e = build_full_sa(d, layout, (uint32_t *)sa, (uint32_t *)isa, (uint8_t *)text, ix->stream, err);
+        if (e != cudaSuccess) return fail(err.empty() ? FMX_E_CUDA : FMX_E_FORMAT, "suffix array construction failed: %s", err.empty() ? cudaGetErrorString(e) : err.c_str());
+        CU(cudaStreamSynchronize(ix->stream));
+        d.sa = (const uint32_t *)sa; d.isa = (const uint32_t *)isa; d.text = (const uint8_t *)text;
+        ix->index_bytes += 9 * n;
+    }
+    if (want_kmer && sigma >= 1) {
+        const int64_t table_budget = 256ll << 20;
+        int K = 0;
+        int64_t entries = 1;
+        while (K < 16 && entries * sigma * 8 <= table_budget && entries * sigma <= (1ll << 31)) { entries *= sigma; ++K; }
+        if (sigma == 1) { K = std::min(K, 16); }
+        if (K >= 2) {
+            void *tab = nullptr;
+            e = cudaMalloc(&tab, (size_t)entries * 8); CU(e); ix->owned.push_back(tab);
+            CU(build_kmer_table(d, ix->cfg, d_sym, (uint32_t)sigma, K, (uint2 *)tab, ix->stream));
+            CU(cudaStreamSynchronize(ix->stream));
+            d.kmer = (const uint2 *)tab; d.kmer_k = K; d.kmer_sigma = (uint32_t)sigma;
+            ix->index_bytes += entries * 8;
+        }
+    }
+    // measured on B200 (profiles/r01_*): plain PLANES wants 4 lanes per 64-B block; WM, and PLANES once most fetches are the
+    // scalar SA/ISA/table loads of the accelerators, want 2 (more queries in flight per SM)
+    if (!o.lanes_per_query) ix->cfg.lanes = (layout == FMX_LAYOUT_PLANES && d.text == nullptr) ? 4 : 2;
+    ix->accel_text = d.text != nullptr;
+    ix->kmer_k = d.kmer ? d.kmer_k : 0;
     CU(cudaStreamSynchronize(ix->stream));
     return FMX_OK;
 }
@@ -289,6 +331,12 @@ int fmx_ctable(const fmx_index *ix, int64_t C[256]) {
     for (int c = 0; c < 256; ++c) C[c] = ix->C[c];
     return FMX_OK;
 }
+int fmx_accel_info(const fmx_index *ix, int32_t *kmer_k, int32_t *text_shortcut) {
+    CHECK_IX(ix);
+    if (kmer_k) *kmer_k = ix->kmer_k;
+    if (text_shortcut) *text_shortcut = ix->accel_text ? 1 : 0;
+    return FMX_OK;
+}
 int fmx_info(const fmx_index *ix, int32_t *layout, int32_t *levels, int32_t *sigma, int64_t *index_bytes, int32_t *rate) {
     CHECK_IX(ix);
     if (layout) *layout = ix->cfg.layout;
@@ -334,6 +382,7 @@ int fmx_host_free(void *p) {
     if (p) CU(cudaFreeHost(p));
     return FMX_OK;
 }
+int fmx_get_lanes(const fmx_index *ix) { return ix ? ix->cfg.lanes : 0; }
 double fmx_last_kernel_ms(const fmx_index *ix) { return ix ? ix->last_ms : 0.0; }
 int64_t fmx_last_kernel_launches(const fmx_index *ix) { return ix ? ix->last_launches : 0; }
 
@@ -625,7 +674,7 @@ int fmx_next_substr_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t 
 int fmx_locate_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, int64_t m, int64_t cap_total, int64_t *out_off, int64_t *pos) {
     CHECK_IX(ix);
     if (m < 0 || !out_off || (m && (!sp || !ep))) return fail(FMX_E_ARG, "bad argument");
-    if (ix->sample_rate <= 0) return fail(FMX_E_ARG, "index was opened without sa_sample_rate; locate unavailable");
+    if (ix->sample_rate <= 0 && !ix->accel_text) return fail(FMX_E_ARG, "index was opened without sa_sample_rate (and without FMX_ACCEL_TEXT); locate unavailable");
     int64_t total = 0;
     for (int64_t i = 0; i < m; ++i) {
         if (sp[i] < 0 || ep[i] > ix->n || (ep[i] < sp[i])) return fail(FMX_E_ARG, "bad interval at %lld", (long long)i);

@@ -184,51 +184,93 @@ __global__ void scatter_samples_kernel(const uint4 *__restrict__ mark, const uin
     samples[rank_one<1>(mark, p.x, nullptr)] = p.y;
 }
 
-cudaError_t build_sa_samples(const DevIndex &ix, int layout, int rate, uint32_t *d_mark_blocks, int64_t nblk, uint32_t *d_samples,
-                             int64_t n_samples, cudaStream_t st, std::string &err) {
+// full-SA variant of the second walk: every row gets its sa value; isa and T' fall out of the same walk
+template <int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+chain_fullsa_kernel(const __grid_constant__ DevIndex ix, uint32_t S, uint32_t nchains, uint32_t eof_chain, const uint32_t *__restrict__ start_sa,
+                    uint32_t *__restrict__ sa, uint32_t *__restrict__ isa, uint8_t *__restrict__ text) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    const uint32_t j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= nchains) return;
+    uint32_t r = (j == eof_chain) ? ix.eof : j * S, v = start_sa[j];
+    for (;;) {
+        const uint32_t c = ix.bwt[r];
+        sa[r] = v;
+        isa[v] = r;
+        if (v > 0) text[v - 1] = (uint8_t)c;          // BWT[r] = T'[sa[r]-1]
+        else text[ix.n - 1] = 0;                      // the '$'
+        r = lf_value<1, LAYOUT>(ix, tb, c, r);
+        v = (v == 0) ? ix.n - 1 : v - 1;
+        if (r == ix.eof || r % S == 0) break;
+    }
+}
+
+namespace {
+struct Chains {
+    uint32_t S = 1, nchains = 0, eof_chain = 0;
+    uint32_t *d_start = nullptr;     // sa value of every chain's first row
+};
+
+// first walk + host linking (sa[eof] = 0, each LF step decrements the text position mod n)
+cudaError_t prepare_chains(const DevIndex &ix, int layout, Chains &ch, cudaStream_t st, std::string &err) {
     const uint64_t n = ix.n;
-    uint64_t target = n < (1u << 20) ? n : (1u << 20);
+    const uint64_t target = n < (1u << 20) ? n : (1u << 20);
     uint32_t S = (uint32_t)((n + target - 1) / target);
     if (S == 0) S = 1;
     const uint32_t base_chains = (uint32_t)((n + S - 1) / S);
     const bool eof_is_grid = (ix.eof % S) == 0;
-    const uint32_t eof_chain = eof_is_grid ? ix.eof / S : base_chains;
-    const uint32_t nchains = eof_is_grid ? base_chains : base_chains + 1;
-
-    uint32_t *d_next, *d_len, *d_start;
+    ch.S = S;
+    ch.eof_chain = eof_is_grid ? ix.eof / S : base_chains;
+    ch.nchains = eof_is_grid ? base_chains : base_chains + 1;
+    const uint32_t nchains = ch.nchains;
+    uint32_t *d_next, *d_len;
     CK(cudaMallocAsync(&d_next, nchains * 4ull, st));
     CK(cudaMallocAsync(&d_len, nchains * 4ull, st));
-    CK(cudaMallocAsync(&d_start, nchains * 4ull, st));
+    CK(cudaMallocAsync(&ch.d_start, nchains * 4ull, st));
     const unsigned grid = (nchains + kThreads - 1) / kThreads;
-    if (layout == FMX_LAYOUT_PLANES) chain_len_kernel<FMX_LAYOUT_PLANES><<<grid, kThreads, 0, st>>>(ix, S, nchains, eof_chain, d_next, d_len);
-    else chain_len_kernel<FMX_LAYOUT_WM><<<grid, kThreads, 0, st>>>(ix, S, nchains, eof_chain, d_next, d_len);
+    if (layout == FMX_LAYOUT_PLANES) chain_len_kernel<FMX_LAYOUT_PLANES><<<grid, kThreads, 0, st>>>(ix, S, nchains, ch.eof_chain, d_next, d_len);
+    else chain_len_kernel<FMX_LAYOUT_WM><<<grid, kThreads, 0, st>>>(ix, S, nchains, ch.eof_chain, d_next, d_len);
     std::vector<uint32_t> nx(nchains), ln(nchains), sv(nchains, 0);
     CK(cudaMemcpyAsync(nx.data(), d_next, nchains * 4ull, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ln.data(), d_len, nchains * 4ull, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    {   // link the chains: sa[eof] = 0, each LF step decrements the text position (mod n)
-        uint64_t total = 0; uint32_t cur = eof_chain; uint64_t v = 0; uint32_t visited = 0;
-        do {
-            sv[cur] = (uint32_t)v;
-            total += ln[cur];
-            v = (v + n - (ln[cur] % n)) % n;
-            cur = nx[cur];
-            ++visited;
-        } while (cur != eof_chain && visited <= nchains);
-        if (cur != eof_chain || visited != nchains || total != n) {
-            err = "BWT is not a single LF cycle (corrupt .bwt/.aux?)";
-            cudaFreeAsync(d_next, st); cudaFreeAsync(d_len, st); cudaFreeAsync(d_start, st);
-            return cudaErrorInvalidValue;
-        }
+    cudaFreeAsync(d_next, st);
+    cudaFreeAsync(d_len, st);
+    uint64_t total = 0, v = 0;
+    uint32_t cur = ch.eof_chain, visited = 0;
+    do {
+        sv[cur] = (uint32_t)v;
+        total += ln[cur];
+        v = (v + n - (ln[cur] % n)) % n;
+        cur = nx[cur];
+        ++visited;
+    } while (cur != ch.eof_chain && visited <= nchains);
+    if (cur != ch.eof_chain || visited != nchains || total != n) {
+        err = "BWT is not a single LF cycle (corrupt .bwt/.aux?)";
+        cudaFreeAsync(ch.d_start, st);
+        ch.d_start = nullptr;
+        return cudaErrorInvalidValue;
     }
-    CK(cudaMemcpyAsync(d_start, sv.data(), nchains * 4ull, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ch.d_start, sv.data(), nchains * 4ull, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                  // sv is a local
+    return cudaSuccess;
+}
+}  // namespace
+
+cudaError_t build_sa_samples(const DevIndex &ix, int layout, int rate, uint32_t *d_mark_blocks, int64_t nblk, uint32_t *d_samples,
+                             int64_t n_samples, cudaStream_t st, std::string &err) {
+    Chains ch;
+    CK(prepare_chains(ix, layout, ch, st, err));
+    const unsigned grid = (ch.nchains + kThreads - 1) / kThreads;
     uint2 *d_pairs; unsigned long long *d_np;
     CK(cudaMallocAsync(&d_pairs, (size_t)n_samples * 8, st));
     CK(cudaMallocAsync(&d_np, 8, st));
     CK(cudaMemsetAsync(d_np, 0, 8, st));
     CK(cudaMemsetAsync(d_mark_blocks, 0, (size_t)nblk * 64, st));
-    if (layout == FMX_LAYOUT_PLANES) chain_mark_kernel<FMX_LAYOUT_PLANES><<<grid, kThreads, 0, st>>>(ix, S, nchains, eof_chain, d_start, (uint32_t)rate, d_mark_blocks, d_pairs, d_np);
-    else chain_mark_kernel<FMX_LAYOUT_WM><<<grid, kThreads, 0, st>>>(ix, S, nchains, eof_chain, d_start, (uint32_t)rate, d_mark_blocks, d_pairs, d_np);
+    if (layout == FMX_LAYOUT_PLANES) chain_mark_kernel<FMX_LAYOUT_PLANES><<<grid, kThreads, 0, st>>>(ix, ch.S, ch.nchains, ch.eof_chain, ch.d_start, (uint32_t)rate, d_mark_blocks, d_pairs, d_np);
+    else chain_mark_kernel<FMX_LAYOUT_WM><<<grid, kThreads, 0, st>>>(ix, ch.S, ch.nchains, ch.eof_chain, ch.d_start, (uint32_t)rate, d_mark_blocks, d_pairs, d_np);
     CK(finish_headers(d_mark_blocks, nblk, 1, st));
     unsigned long long np = 0;
     CK(cudaMemcpyAsync(&np, d_np, 8, cudaMemcpyDeviceToHost, st));
@@ -236,7 +278,52 @@ cudaError_t build_sa_samples(const DevIndex &ix, int layout, int rate, uint32_t 
     if ((int64_t)np != n_samples) { err = "sample count mismatch"; return cudaErrorInvalidValue; }
     scatter_samples_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(d_mark_blocks), d_pairs, (int64_t)np, d_samples);
     cudaFreeAsync(d_pairs, st); cudaFreeAsync(d_np, st);
-    cudaFreeAsync(d_next, st); cudaFreeAsync(d_len, st); cudaFreeAsync(d_start, st);
+    cudaFreeAsync(ch.d_start, st);
+    return cudaGetLastError();
+}
+
+cudaError_t build_full_sa(const DevIndex &ix, int layout, uint32_t *d_sa, uint32_t *d_isa, uint8_t *d_text, cudaStream_t st, std::string &err) {
+    Chains ch;
+    CK(prepare_chains(ix, layout, ch, st, err));
+    const unsigned grid = (ch.nchains + kThreads - 1) / kThreads;
+    if (layout == FMX_LAYOUT_PLANES) chain_fullsa_kernel<FMX_LAYOUT_PLANES><<<grid, kThreads, 0, st>>>(ix, ch.S, ch.nchains, ch.eof_chain, ch.d_start, d_sa, d_isa, d_text);
+    else chain_fullsa_kernel<FMX_LAYOUT_WM><<<grid, kThreads, 0, st>>>(ix, ch.S, ch.nchains, ch.eof_chain, ch.d_start, d_sa, d_isa, d_text);
+    cudaFreeAsync(ch.d_start, st);
+    return cudaGetLastError();
+}
+
+// k-mer table: entry idx <-> the K-byte pattern P with P[K-1-j] = sym[digit_j(idx)] (digit 0 most significant = the
+// byte search() consumes first, i.e. the LAST pattern byte)
+__global__ void gen_kmer_patterns_kernel(const uint8_t *__restrict__ sym, uint32_t sigma, int K, uint64_t first, uint64_t count,
+                                         uint8_t *__restrict__ out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    uint64_t x = first + t;
+    for (int j = K - 1; j >= 0; --j) { out[t * K + (K - 1 - j)] = sym[x % sigma]; x /= sigma; }
+}
+__global__ void zip_kmer_kernel(const uint32_t *__restrict__ sp, const uint32_t *__restrict__ ep, uint64_t count, uint2 *__restrict__ out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < count) out[t] = make_uint2(sp[t], ep[t]);
+}
+
+cudaError_t build_kmer_table(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, uint32_t sigma, int K, uint2 *d_table, cudaStream_t st) {
+    uint64_t total = 1;
+    for (int j = 0; j < K; ++j) total *= sigma;
+    const uint64_t slice = 1ull << 24;                  // bounded scratch: 16 Mi patterns at a time
+    uint8_t *d_pat; uint32_t *d_sp, *d_ep;
+    CK(cudaMallocAsync(&d_pat, slice * K, st));
+    CK(cudaMallocAsync(&d_sp, slice * 4, st));
+    CK(cudaMallocAsync(&d_ep, slice * 4, st));
+    DevIndex plain = ix;                                // the table is filled by ordinary backward steps
+    plain.kmer = nullptr;
+    plain.text = nullptr;
+    for (uint64_t o = 0; o < total; o += slice) {
+        const uint64_t cnt = total - o < slice ? total - o : slice;
+        gen_kmer_patterns_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_sym, sigma, K, o, cnt, d_pat);
+        CK(launch_count_fixed(plain, cfg, d_pat, K, (int64_t)cnt, d_sp, d_ep, false, nullptr, st));
+        zip_kmer_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_sp, d_ep, cnt, d_table + o);
+    }
+    cudaFreeAsync(d_pat, st); cudaFreeAsync(d_sp, st); cudaFreeAsync(d_ep, st);
     return cudaGetLastError();
 }
 

@@ -16,6 +16,10 @@ cudaError_t build_planes(const uint8_t *d_bwt, int64_t n, uint32_t eof, const ui
 // sampled SA: marks rows with sa % rate == 0 (rank blocks, nblk) and stores their sa values in mark-rank order
 cudaError_t build_sa_samples(const DevIndex &ix, int layout, int rate, uint32_t *d_mark_blocks, int64_t nblk, uint32_t *d_samples,
                              int64_t n_samples, cudaStream_t st, std::string &err);
+// full suffix array, its inverse and T' (text[n-1] = 0) by the same chain walks
+cudaError_t build_full_sa(const DevIndex &ix, int layout, uint32_t *d_sa, uint32_t *d_isa, uint8_t *d_text, cudaStream_t st, std::string &err);
+// (sp,ep) after the first K backward steps for every K-mer over the sigma occurring symbols
+cudaError_t build_kmer_table(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, uint32_t sigma, int K, uint2 *d_table, cudaStream_t st);
 // suffix sort of t+'$' (t has no zero bytes) -> BWT, eof row, byte counts; optionally the suffix array
 cudaError_t suffix_sort_bwt(const uint8_t *d_t, int64_t len, uint8_t *d_bwt, int64_t *eof_out, int64_t counts_out[256],
                             uint32_t *d_sa_out, int *rounds_out, cudaStream_t st);

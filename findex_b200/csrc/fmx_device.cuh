@@ -34,6 +34,13 @@ struct DevIndex {
     uint32_t n, eof;
     int32_t  layout, levels;
     uint32_t z[8];              // WM: zeros per level
+    // ---- optional accelerators (bit-exact shortcuts that spend HBM capacity) ----
+    const uint2   *kmer;        // sigma^kmer_k entries: (sp,ep) after the first kmer_k backward steps, (0,0) if empty
+    int32_t        kmer_k;
+    uint32_t       kmer_sigma;
+    const uint32_t *sa;         // full suffix array  sa[row]   (bwtFm2sa, util.scala:213-224)
+    const uint32_t *isa;        // its inverse        isa[pos]
+    const uint8_t  *text;       // T' bytes, text[n-1] = 0 ('$')
 };
 
 struct SharedTables {
@@ -187,6 +194,85 @@ __device__ __forceinline__ void backward_step(const DevIndex &ix, const SharedTa
         if (code == 0) { p -= (sp > ix.eof); q -= (ep > ix.eof); }     // the '$' row is filed under code 0
         sp = t.base[c] + p;
         ep = t.base[c] + q;
+    }
+}
+
+// ---- the whole backward search of one pattern: SuffixAlgo.search, findex.scala:15-31 -----------------------
+// pat(i) returns pattern byte i.  Every thread of the warp calls this together (inactive groups pass
+// active=false); groups leave the loop individually, the warp leaves when all are done.
+//   * k-mer table (optional): the first kmer_k steps are one lookup.
+//   * first step from (0,n) otherwise: (C[c], C[c+1]) without touching memory.
+//   * singleton shortcut (optional): once the interval is one row r and >= 3 bytes remain, the remaining bytes
+//     are compared with T' in front of position sa[r]; the answer row is isa[sa[r]-remaining].  Identical to
+//     stepping: from a singleton, a step succeeds iff BWT[r] = T'[sa[r]-1] equals the byte, and lands on
+//     LF(r) = isa[sa[r]-1].  Patterns containing byte 0 take the ordinary steps (the '$' row wraps the text).
+template <int G, int LAYOUT, bool STATS, typename PatFn>
+__device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedTables &tb, PatFn pat, int len, bool active,
+                                               uint32_t &sp, uint32_t &ep, uint32_t &touched, uint32_t &steps) {
+    const int lane = (G == 1) ? 0 : (threadIdx.x & (G - 1));
+    const uint32_t gmask = group_mask<G>();
+    sp = 0;
+    ep = active ? ix.n : 0u;
+    int i = len - 1;
+    bool noshort = (ix.text == nullptr);
+    if (active && i >= 0) {
+        bool done = false;
+        if (ix.kmer != nullptr && len >= ix.kmer_k) {
+            uint32_t idx = 0;
+            bool ok = true;
+            for (int j = 0; j < ix.kmer_k; ++j) {
+                const uint32_t c = pat(len - 1 - j), code = tb.code[c];
+                ok = ok && (code != (uint32_t)kCodeAbsent) && (c != 0);
+                idx = idx * ix.kmer_sigma + code;
+            }
+            if (ok) {
+                const uint2 v = ix.kmer[idx];
+                sp = v.x; ep = v.y;
+                i -= ix.kmer_k;
+                done = true;
+                if (STATS) { touched += 1; steps += ix.kmer_k; }
+            }
+        }
+        if (!done) {
+            const uint32_t c = pat(i);
+            sp = tb.C[c];
+            ep = tb.C[c + 1];
+            --i;
+            if (STATS) ++steps;
+        }
+    }
+    for (;;) {
+        const bool go = (i >= 0) && (sp < ep);
+        if (go) {
+            bool stepped = false;
+            if (!noshort && (ep - sp) == 1u && i >= 2) {
+                const int rem = i + 1;
+                const uint32_t q = ix.sa[sp];
+                const bool fits = q >= (uint32_t)rem;
+                const uint32_t b0 = fits ? q - (uint32_t)rem : 0u;
+                const uint32_t r = ix.isa[b0];                       // issued early: overlaps the text compare
+                bool eq = fits, zero = false;
+                for (int k = lane; k < rem; k += G) {
+                    const uint32_t pc = pat(k);
+                    zero = zero || (pc == 0);
+                    eq = eq && ((uint32_t)ix.text[b0 + k] == pc);
+                }
+                if (G > 1) { eq = __all_sync(gmask, eq); zero = __any_sync(gmask, zero); }
+                if (zero) noshort = true;
+                else {
+                    if (eq) { sp = r; ep = r + 1; } else { sp = 0; ep = 0; }
+                    i = -1;
+                    stepped = true;
+                    if (STATS) { touched += 3; steps += rem; }
+                }
+            }
+            if (!stepped) {
+                backward_step<G, LAYOUT, STATS>(ix, tb, pat(i), sp, ep, touched);
+                --i;
+                if (STATS) ++steps;
+            }
+        }
+        if (__all_sync(0xFFFFFFFFu, !go)) break;
     }
 }
 

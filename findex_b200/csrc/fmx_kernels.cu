@@ -21,7 +21,7 @@ namespace fmx {
 // K1: count
 // =====================================================================================================
 template <int G, int LAYOUT, bool STATS, typename OutT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (G == 1) ? 4 : 8)
 count_fixed_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, int len, long long m,
                    OutT *__restrict__ sp_out, OutT *__restrict__ ep_out, unsigned long long *stats) {
     __shared__ SharedTables tb;
@@ -48,22 +48,8 @@ count_fixed_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restric
     const int g = threadIdx.x / G;
     const bool active = g < nq;
     const uint8_t *p = spat + g * len;
-    uint32_t sp = 0, ep = active ? ix.n : 0u, touched = 0, steps = 0;
-    int i = len - 1;
-    if (active && i >= 0) {            // first step from (0,n): rank_c(0) = 0 and rank_c(n) = count(c): no memory
-        const uint32_t c = p[i];
-        sp = tb.C[c];
-        ep = tb.C[c + 1];
-        --i;
-        if (STATS) ++steps;
-    }
-    for (; i >= 0; --i) {
-        if (sp < ep) {                 // findex.scala:20 — leave the loop as soon as the interval empties
-            backward_step<G, LAYOUT, STATS>(ix, tb, p[i], sp, ep, touched);
-            if (STATS) ++steps;
-        }
-        if (__all_sync(0xFFFFFFFFu, !(sp < ep))) break;
-    }
+    uint32_t sp, ep, touched = 0, steps = 0;
+    search_pattern<G, LAYOUT, STATS>(ix, tb, [p](int i) { return (uint32_t)p[i]; }, len, active, sp, ep, touched, steps);
     if (active && (threadIdx.x % G) == 0) {
         const bool hit = sp < ep;
         sp_out[q0 + g] = hit ? (OutT)sp : (OutT)0;
@@ -91,12 +77,9 @@ count_var_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict_
     const bool active = q < m;
     long long lo = 0, hi = 0;
     if (active) { lo = off[q]; hi = off[q + 1]; }
-    uint32_t sp = 0, ep = active ? ix.n : 0u, touched = 0;
-    for (long long i = hi - 1; ; --i) {
-        const bool go = (i >= lo) && (sp < ep);
-        if (go) backward_step<G, LAYOUT, false>(ix, tb, __ldg(pat + i), sp, ep, touched);
-        if (__all_sync(0xFFFFFFFFu, !go)) break;
-    }
+    uint32_t sp, ep, touched = 0, steps = 0;
+    const uint8_t *p = pat + lo;
+    search_pattern<G, LAYOUT, false>(ix, tb, [p](int i) { return (uint32_t)__ldg(p + i); }, (int)(hi - lo), active, sp, ep, touched, steps);
     if (active && (threadIdx.x % G) == 0) {
         const bool hit = sp < ep;
         sp_out[q] = hit ? (long long)sp : 0;
@@ -250,6 +233,10 @@ locate_kernel(const __grid_constant__ DevIndex ix, const long long *__restrict__
     long long lo = 0, hi = m;
     while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (off[mid] <= t) lo = mid; else hi = mid; }
     uint32_t r = (uint32_t)(sp[lo] + (t - off[lo]));
+    if (ix.sa != nullptr) {                                    // full suffix array resident: one load per occurrence
+        if ((threadIdx.x % G) == 0) pos[t] = ix.sa[r];
+        return;
+    }
     uint32_t k = 0;
     for (;;) {
         uint32_t bit;

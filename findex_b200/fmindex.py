@@ -19,6 +19,7 @@ _SO = os.path.join(_HERE, "libfmgpu.so")
 FMX_OK, FMX_E_IO, FMX_E_FORMAT, FMX_E_CUDA, FMX_E_ARG = 0, -1, -2, -3, -4
 FMX_E_CAPACITY, FMX_E_SYNTAX, FMX_E_UNSUPPORTED, FMX_E_LIMIT = -5, -6, -7, -8
 LAYOUT_AUTO, LAYOUT_WM, LAYOUT_PLANES = 0, 1, 2
+ACCEL_AUTO, ACCEL_KMER, ACCEL_TEXT, ACCEL_NONE = 0, 1, 2, 8
 
 
 class FmxError(Exception):
@@ -37,7 +38,7 @@ class ReUnsupported(FmxError):
 
 class fmx_opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("layout", C.c_int32), ("sa_sample_rate", C.c_int32), ("require_fm", C.c_int32),
-                ("max_index_bytes", C.c_int64), ("lanes_per_query", C.c_int32), ("reserved", C.c_int32)]
+                ("max_index_bytes", C.c_int64), ("lanes_per_query", C.c_int32), ("accel", C.c_int32)]
 
 
 _lib = None
@@ -65,6 +66,8 @@ def lib():
     L.fmx_eof.argtypes = [p]
     L.fmx_ctable.argtypes = [p, p]
     L.fmx_info.argtypes = [p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(i32)]
+    L.fmx_accel_info.argtypes = [p, C.POINTER(i32), C.POINTER(i32)]
+    L.fmx_get_lanes.argtypes = [p]
     L.fmx_occ_batch.argtypes = [p, p, p, i64, p]
     L.fmx_prev_range_batch.argtypes = [p, p, p, p, i64, p, p]
     L.fmx_interval_prev_range.argtypes = [p, i64, i64, C.c_int, C.c_int, p, p, p, C.POINTER(i64)]
@@ -124,11 +127,11 @@ def _u8(a):
     return np.ascontiguousarray(a, dtype=np.uint8)
 
 
-def make_opts(device=-1, layout=LAYOUT_AUTO, sa_sample_rate=0, require_fm=False, max_index_bytes=0, lanes_per_query=0):
+def make_opts(device=-1, layout=LAYOUT_AUTO, sa_sample_rate=0, require_fm=False, max_index_bytes=0, lanes_per_query=0, accel=ACCEL_AUTO):
     o = fmx_opts()
     lib().fmx_opts_default(C.byref(o))
     o.device, o.layout, o.sa_sample_rate = device, layout, sa_sample_rate
-    o.require_fm, o.max_index_bytes, o.lanes_per_query = int(require_fm), max_index_bytes, lanes_per_query
+    o.require_fm, o.max_index_bytes, o.lanes_per_query, o.accel = int(require_fm), max_index_bytes, lanes_per_query, accel
     return o
 
 
@@ -204,8 +207,11 @@ class GpuFMSearcher:
     def info(self):
         lay, lev, sig, rate, nb = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
         _check(lib().fmx_info(self.h, C.byref(lay), C.byref(lev), C.byref(sig), C.byref(nb), C.byref(rate)))
+        k, t = C.c_int32(), C.c_int32()
+        _check(lib().fmx_accel_info(self.h, C.byref(k), C.byref(t)))
         return {"layout": {1: "wm", 2: "planes"}[lay.value], "levels": lev.value, "sigma": sig.value,
-                "index_bytes": nb.value, "sa_sample_rate": rate.value}
+                "index_bytes": nb.value, "sa_sample_rate": rate.value, "kmer_k": k.value, "text_shortcut": bool(t.value),
+                "lanes_per_query": lib().fmx_get_lanes(self.h)}
 
     # ---- scalar trait members (each is a batch of one) -------------------------------------------------
     def cf(self, c):

@@ -43,6 +43,12 @@ extern "C" {
 #define FMX_LAYOUT_WM       1   /* byte-alphabet wavelet matrix, ceil(log2 sigma) levels, 64-B rank blocks */
 #define FMX_LAYOUT_PLANES   2   /* one 64-B-rank-block bitvector per symbol (1 block fetch per rank)     */
 
+/* Bit-exact accelerators of the count path (fmx_opts.accel); they spend HBM capacity, never change results */
+#define FMX_ACCEL_AUTO      0
+#define FMX_ACCEL_KMER      1   /* table of (sp,ep) after the first k steps, k = max with sigma^k*8 B <= 256 MiB */
+#define FMX_ACCEL_TEXT      2   /* full SA + inverse SA + text (9n bytes): singleton intervals finish in 3 fetches; locate is 1 fetch */
+#define FMX_ACCEL_NONE      8   /* plain backward search only                                                */
+
 typedef struct fmx_index fmx_index;     /* opaque; library-owned until fmx_close  */
 typedef struct fmx_regex fmx_regex;     /* opaque; library-owned until fmx_regex_free */
 
@@ -53,7 +59,7 @@ typedef struct fmx_opts {
     int32_t  require_fm;        /* 1 = fail like the reference when <base>.fm is absent                  */
     int64_t  max_index_bytes;   /* budget for FMX_LAYOUT_AUTO; 0 = default                               */
     int32_t  lanes_per_query;   /* 0 = default; 1, 2 or 4 lanes cooperate on one 64-B rank block         */
-    int32_t  reserved;
+    int32_t  accel;             /* FMX_ACCEL_* bit mask; 0 = auto (both when they fit the memory budget)   */
 } fmx_opts;
 
 void        fmx_opts_default(fmx_opts *o);
@@ -75,6 +81,8 @@ int64_t fmx_eof(const fmx_index *ix);                        /* BWTLoader.eof   
 int     fmx_ctable(const fmx_index *ix, int64_t C[256]);     /* cf(c) for all c       M/bwtmerger.scala:352 */
 int     fmx_info(const fmx_index *ix, int32_t *layout, int32_t *levels, int32_t *sigma,
                  int64_t *index_bytes, int32_t *sa_sample_rate);
+
+int     fmx_accel_info(const fmx_index *ix, int32_t *kmer_k, int32_t *text_shortcut);   /* accelerators in effect */
 
 /* ---- occ(c,key)  M/bwtmerger.scala:354-375  (number of c in BWT[0..key], key=-1 -> 0) --------------- */
 int fmx_occ_batch(fmx_index *ix, const uint8_t *c, const int64_t *key, int64_t m, int64_t *out);
@@ -155,6 +163,7 @@ int fmx_set_l2_fetch_granularity(int32_t bytes, int32_t *effective);
 int fmx_set_chunk(fmx_index *ix, int64_t queries_per_chunk);
 /* Re-selects how many lanes (1, 2 or 4) cooperate on one 64-B rank block for subsequent calls.           */
 int fmx_set_lanes(fmx_index *ix, int32_t lanes_per_query);
+int fmx_get_lanes(const fmx_index *ix);
 double fmx_last_kernel_ms(const fmx_index *ix);
 int64_t fmx_last_kernel_launches(const fmx_index *ix);
 

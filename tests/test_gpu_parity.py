@@ -18,6 +18,7 @@ pytestmark = pytest.mark.gpu
 LAYOUTS = [fx.LAYOUT_WM, fx.LAYOUT_PLANES]
 LANES = [1, 2, 4]
 CFGS = [(l, g) for l in LAYOUTS for g in LANES]
+ACCELS = [fx.ACCEL_AUTO, fx.ACCEL_NONE, fx.ACCEL_KMER, fx.ACCEL_TEXT]
 
 
 def _ids(v):
@@ -154,13 +155,21 @@ def _patterns(text, rng, m, maxlen):
     return pats
 
 
+@pytest.mark.parametrize("accel", ACCELS, ids=lambda a: "accel%d" % a)
 @pytest.mark.parametrize("cfg", CFGS, ids=_ids)
-def test_count_parity_small(ref_dir, cfg):
+def test_count_parity_small(ref_dir, cfg, accel):
     text = open(os.path.join(ref_dir, "test.txt"), "rb").read()
     o = fo.OracleIndex.load(os.path.join(ref_dir, "test.cmp"), big_endian=False)
-    g = _open(os.path.join(ref_dir, "test.cmp.bwt"), cfg)
+    g = _open(os.path.join(ref_dir, "test.cmp.bwt"), cfg, accel=accel)
+    info = g.info()
+    assert info["text_shortcut"] == (accel in (fx.ACCEL_AUTO, fx.ACCEL_TEXT)) and (info["kmer_k"] >= 2) == (accel in (fx.ACCEL_AUTO, fx.ACCEL_KMER))
     rng = np.random.default_rng(11)
-    pats = _patterns(text, rng, 3000, 12) + [b"", b"\0", b"a\0", bytes([200]), b"zzzzzzzzzzzzzzzzzzzzzzzzz"]
+    tprime = text[::-1]
+    zero_cases = [b"", b"\0", b"a\0", bytes([200]), b"zzzzzzzzzzzzzzzzzzzzzzzzz",
+                  tprime[-9:] + b"\0",                    # end of T' followed by '$': a real hit at row 0's neighbourhood
+                  b"\0" + tprime[:9],                     # '$' then the start of T': the cyclic wrap the BWT allows -> row 0
+                  tprime[100:106] + b"\0" + tprime[107:113], b"\0\0\0\0\0", tprime[:12], tprime[-12:], tprime[1:14]]
+    pats = _patterns(text, rng, 3000, 16) + zero_cases
     sp, ep = g.count_batch(pats)
     for i, p in enumerate(pats):
         r = o.search(p)
@@ -302,7 +311,9 @@ def test_index_files_roundtrip(tmp_path, ref_dir):
 
 
 @pytest.mark.parametrize("kind", ["random255", "dna", "english"])
-@pytest.mark.parametrize("cfg", [(fx.LAYOUT_WM, 4), (fx.LAYOUT_PLANES, 4), (fx.LAYOUT_WM, 1), (fx.LAYOUT_PLANES, 2)], ids=_ids)
+@pytest.mark.parametrize("cfg", [(fx.LAYOUT_WM, 4, fx.ACCEL_AUTO), (fx.LAYOUT_PLANES, 4, fx.ACCEL_AUTO), (fx.LAYOUT_WM, 1, fx.ACCEL_NONE),
+                                 (fx.LAYOUT_PLANES, 2, fx.ACCEL_NONE), (fx.LAYOUT_PLANES, 4, fx.ACCEL_TEXT), (fx.LAYOUT_WM, 2, fx.ACCEL_KMER)],
+                         ids=lambda v: _ids(v) + "-accel%d" % v[2])
 def test_synthetic_parity(kind, cfg, words, tmp_path):
     """Scaled-down configs 2/3/5: seeded text -> GPU-built index files -> count / locate / regex vs oracle."""
     rng = np.random.default_rng({"random255": 2, "dna": 7, "english": 4}[kind])
@@ -315,7 +326,7 @@ def test_synthetic_parity(kind, cfg, words, tmp_path):
     base = str(tmp_path / kind)
     fx.build_index_files(text, base, bigEndian=True)
     o = fo.OracleIndex.load(base)
-    g = _open(base + ".bwt", cfg, big_endian=True, sa_sample_rate=32)
+    g = _open(base + ".bwt", cfg, big_endian=True, sa_sample_rate=32, accel=cfg[2])
     info = g.info()
     if kind == "dna":
         assert info["sigma"] == 4 and (info["levels"] == 2 or info["layout"] == "planes")
