@@ -698,12 +698,34 @@ int fmx_locate_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, int64_
     CU(segmented_sort_u32(dpos.as<uint32_t>(), dsorted.as<uint32_t>(), total, m, doff.as<int64_t>(), st));
     ix->last_launches = 1; ix->total_launches += 1;
     t.stop();
-    std::vector<uint32_t> h((size_t)total);
-    CU(cudaMemcpyAsync(h.data(), dsorted.p, total * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     t.collect();
-    for (int64_t i = 0; i < total; ++i) pos[i] = h[(size_t)i];
-    return FMX_OK;
+    // widen to the ABI's int64 on the device and stream the slabs straight into the caller's buffer: the widening of
+    // slab k+1 overlaps the D2H of slab k (asynchronous DMA when `pos` is page-locked)
+    const int64_t slab = 32ll << 20;
+    DBuf w0(st), w1(st);
+    CU(w0.alloc((size_t)std::min(slab, total) * 8)); CU(w1.alloc((size_t)std::min(slab, total) * 8));
+    CU(cudaEventRecord(ix->ev_alloc, st));
+    CU(cudaStreamWaitEvent(ix->d2h, ix->ev_alloc, 0));
+    cudaEvent_t done[2];
+    CU(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+    int rc = FMX_OK;
+    for (int64_t o = 0, k = 0; o < total && rc == FMX_OK; o += slab, ++k) {
+        const int64_t cnt = std::min(slab, total - o);
+        int64_t *w = (k & 1) ? w1.as<int64_t>() : w0.as<int64_t>();
+        cudaError_t e = cudaSuccess;
+        if (k >= 2) e = cudaStreamWaitEvent(st, done[k & 1], 0);              // the slab buffer is free again
+        if (e == cudaSuccess) e = widen_u32_i64(dsorted.as<uint32_t>() + o, w, cnt, st);
+        if (e == cudaSuccess) e = cudaEventRecord(ix->ev1, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ix->d2h, ix->ev1, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pos + o, w, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ix->d2h);
+        if (e == cudaSuccess) e = cudaEventRecord(done[k & 1], ix->d2h);
+        if (e != cudaSuccess) rc = fail(FMX_E_CUDA, "CUDA error %s in the locate copy-out (%s)", cudaGetErrorName(e), cudaGetErrorString(e));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(ix->d2h);
+    cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+    if (rc == FMX_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) rc = fail(FMX_E_CUDA, "CUDA error while draining the locate copy-out");
+    return rc;
 }
 
 // ---- regex ------------------------------------------------------------------------------------------------------
@@ -760,7 +782,7 @@ int fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t st = ix->stream;
-    DBuf d_c(st), d_last(st), d_rx(st), d_fo(st), d_f(st), fa(st), fb(st), d_res(st), d_tmp(st), d_cnt(st);
+    DBuf d_c(st), d_last(st), d_rx(st), d_fo(st), d_f(st), d_res(st), d_tmp(st), d_cnt(st);
     CU(d_c.alloc(st_c.size())); CU(d_last.alloc(st_last.size())); CU(d_rx.alloc(st_regex.size() * 4));
     CU(d_fo.alloc(fol_off.size() * 4)); CU(d_f.alloc(fol.size() * 4 + 4));
     CU(cudaMemcpyAsync(d_c.p, st_c.data(), st_c.size(), cudaMemcpyHostToDevice, st));
@@ -772,29 +794,40 @@ int fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64
 
     size_t fr = 0, to = 0;
     cudaMemGetInfo(&fr, &to);
-    // two frontier buffers sized from what the device has left: an eighth of free memory each, 1 Mi..256 Mi items
-    int64_t cap_front = std::min<int64_t>(std::max<int64_t>((int64_t)(fr / 8 / sizeof(FrontierItem)), 1 << 20), 1ll << 28);
-    cap_front = std::max<int64_t>(cap_front, (int64_t)front.size());
+    // frontier buffers start small and grow on demand (a level that overflows is replayed), bounded by an eighth of
+    // the free device memory each
+    const int64_t max_front = std::max<int64_t>(std::min<int64_t>((int64_t)(fr / 8 / sizeof(FrontierItem)), 1ll << 28), (int64_t)front.size());
+    int64_t cap_cur = std::min<int64_t>(max_front, std::max<int64_t>((int64_t)front.size(), 1 << 16));
+    int64_t cap_nxt = std::min<int64_t>(max_front, std::max<int64_t>((int64_t)front.size() * 4, 1 << 20));
     int64_t cap_res = std::max<int64_t>(cap_total, 1 << 16);
-    CU(fa.alloc(cap_front * sizeof(FrontierItem))); CU(fb.alloc(cap_front * sizeof(FrontierItem)));
+    void *cur = nullptr, *nxt = nullptr;
+    CU(cudaMallocAsync(&cur, cap_cur * sizeof(FrontierItem), st)); CU(cudaMallocAsync(&nxt, cap_nxt * sizeof(FrontierItem), st));
+    struct Guard { void **a, **b; cudaStream_t s; ~Guard() { if (*a) cudaFreeAsync(*a, s); if (*b) cudaFreeAsync(*b, s); } } guard{&cur, &nxt, st};
     CU(d_res.alloc(cap_res * sizeof(RegexResult))); CU(d_cnt.alloc(16));
-    CU(cudaMemcpyAsync(fa.p, front.data(), front.size() * sizeof(FrontierItem), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(cur, front.data(), front.size() * sizeof(FrontierItem), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(d_cnt.p, 0, 16, st));
     Timed t(ix);
     int64_t n_in = (int64_t)front.size(), launches = 0, level = 0;
-    unsigned long long h[2] = {0, 0};
-    void *cur = fa.p, *nxt = fb.p;
-    int64_t cap_cur = cap_front, cap_nxt = cap_front;
+    unsigned long long h[2] = {0, 0}, res_before = 0;
     while (n_in > 0) {
         if (++level > ix->n + 1) return fail(FMX_E_LIMIT, "regex traversal deeper than the text");
-        CU(cudaMemsetAsync(d_cnt.p, 0, 8, st));                      // next-frontier counter; the result counter accumulates
-        CU(launch_regex_level(ix->d, ix->cfg, rt, (const FrontierItem *)cur, n_in, (FrontierItem *)nxt, cap_nxt, d_res.as<RegexResult>(), cap_res,
-                              d_cnt.as<unsigned long long>(), st));
-        ++launches;
-        CU(cudaMemcpyAsync(h, d_cnt.p, 16, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if ((int64_t)h[0] > cap_nxt)
-            return fail(FMX_E_LIMIT, "regex frontier of %llu items exceeds the device budget of %lld; split the batch", h[0], (long long)cap_nxt);
+        for (;;) {
+            const unsigned long long reset[2] = {0ull, res_before};         // next-frontier counter := 0, results := value before this level
+            CU(cudaMemcpyAsync(d_cnt.p, reset, 16, cudaMemcpyHostToDevice, st));
+            CU(launch_regex_level(ix->d, ix->cfg, rt, (const FrontierItem *)cur, n_in, (FrontierItem *)nxt, cap_nxt, d_res.as<RegexResult>(), cap_res,
+                                  d_cnt.as<unsigned long long>(), st));
+            ++launches;
+            CU(cudaMemcpyAsync(h, d_cnt.p, 16, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if ((int64_t)h[0] <= cap_nxt) break;
+            if ((int64_t)h[0] > max_front)
+                return fail(FMX_E_LIMIT, "regex frontier of %llu items exceeds the device budget of %lld; split the batch", h[0], (long long)max_front);
+            CU(cudaFreeAsync(nxt, st));
+            nxt = nullptr;
+            cap_nxt = std::min<int64_t>(max_front, (int64_t)h[0] + (int64_t)h[0] / 4);
+            CU(cudaMallocAsync(&nxt, cap_nxt * sizeof(FrontierItem), st));
+        }
+        res_before = h[1];
         n_in = (int64_t)h[0];
         std::swap(cur, nxt);
         std::swap(cap_cur, cap_nxt);

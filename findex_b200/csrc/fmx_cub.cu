@@ -78,6 +78,15 @@ __global__ void gather_res_kernel(const RegexResult *src, const uint32_t *idx, i
     if (i < n) dst[i] = src[idx[i]];
 }
 
+__global__ void widen_kernel(const uint32_t *__restrict__ in, long long *__restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (long long)in[i];
+}
+cudaError_t widen_u32_i64(const uint32_t *d_in, int64_t *d_out, int64_t n, cudaStream_t st) {
+    if (n > 0) widen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_in, (long long *)d_out, n);
+    return cudaGetLastError();
+}
+
 cudaError_t sort_regex_results(RegexResult *d_res, RegexResult *d_tmp, int64_t n, cudaStream_t st) {
     if (n <= 1) return cudaSuccess;
     if (n >= (1ll << 32)) return cudaErrorInvalidValue;

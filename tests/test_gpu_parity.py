@@ -378,3 +378,18 @@ def test_synthetic_parity(kind, cfg, words, tmp_path):
         assert res == o.regex_match(rx), rx
     g.close()
     o.close()
+
+
+def test_regex_frontier_growth_and_replay(ref_dir, o1024):
+    """6000 '.'-regexes expand to > 2^20 frontier items in one level: the frontier buffer must grow and the level be replayed
+    without duplicating or losing results."""
+    g = _open(os.path.join(ref_dir, "test1024.cmp.bwt"), (fx.LAYOUT_PLANES, 2))
+    rxs = ["%c.%c" % (97 + i % 26, 97 + (i // 26) % 26) for i in range(6000)]
+    got = g.regex_search_batch([fx.ReTree(r) for r in rxs], cap_total=64)
+    memo = {}
+    for rx, res in zip(rxs, got):
+        if rx not in memo:
+            memo[rx] = o1024.regex_match(rx)
+        assert res == memo[rx], rx
+    assert sum(len(r) for r in got) > 1000
+    g.close()
