@@ -306,7 +306,8 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(tp):
         try:
             rec = json.load(open(tp)).get("count_fixed_kernel", {})
-            if rec.get("queries") == m and rec.get("layout") == info["layout"]:
+            if (rec.get("queries") == m and rec.get("layout") == info["layout"] and rec.get("lanes") == info["lanes_per_query"]
+                    and rec.get("kmer_k") == info["kmer_k"] and rec.get("text_shortcut") == info["text_shortcut"]):
                 traffic = rec.get("dram_bytes_per_launch")
         except Exception:
             pass

@@ -166,6 +166,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
 
     DevIndex &d = ix->d;
     d.blocks = (const uint4 *)blocks; d.stride = (uint64_t)nblk; d.bwt = d_bwt; d.C = d_C; d.base = d_base; d.code = d_code;
+    d.bm = nullptr;
     d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isa = nullptr; d.text = nullptr;
     d.mark = nullptr; d.samples = nullptr; d.n = (uint32_t)n; d.eof = (uint32_t)eof; d.layout = layout; d.levels = levels;
     for (int l = 0; l < 8; ++l) d.z[l] = z[l];
@@ -182,6 +183,14 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
         d.mark = (const uint4 *)mark; d.samples = (const uint32_t *)samples;
         ix->n_samples = ns;
         ix->index_bytes += nblk * 64 + ns * 4;
+        if (o.sa_sample_rate > 1) {                              // fused BWT+mark blocks: one fetch per LF step of the locate walk
+            const int64_t nwb = n / kRowsPerWalkBlock + 1;
+            void *bm = nullptr;
+            e = cudaMalloc(&bm, (size_t)nwb * 64); CU(e); ix->owned.push_back(bm);
+            CU(build_walk_blocks(d_bwt, (const uint32_t *)mark, n, (uint8_t *)bm, nwb, ix->stream));
+            d.bm = (const uint4 *)bm;
+            ix->index_bytes += nwb * 64;
+        }
     }
     // ---- optional accelerators ---------------------------------------------------------------------------
     int accel = o.accel;

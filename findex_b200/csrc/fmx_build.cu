@@ -282,6 +282,31 @@ cudaError_t build_sa_samples(const DevIndex &ix, int layout, int rate, uint32_t 
     return cudaGetLastError();
 }
 
+// fused walk blocks for locate: 56 BWT bytes + their 56 mark bits per 64-byte block
+__global__ void build_walk_blocks_kernel(const uint8_t *__restrict__ bwt, const uint32_t *__restrict__ mark_blocks, int64_t n, uint8_t *__restrict__ bm,
+                                         int64_t nwb) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nwb) return;
+    uint8_t out[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) out[i] = 0;
+    for (int o = 0; o < 56; ++o) {
+        const int64_t r = b * 56 + o;
+        if (r >= n) break;
+        out[o] = bwt[r];
+        const int64_t blk = r / kBitsPerBlock, off = r - blk * kBitsPerBlock;
+        const uint32_t bit = (mark_blocks[blk * 16 + 1 + (off >> 5)] >> (off & 31)) & 1u;
+        out[56 + (o >> 3)] |= (uint8_t)(bit << (o & 7));
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(bm + b * 64);
+    const uint4 *src = reinterpret_cast<const uint4 *>(out);
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+}
+cudaError_t build_walk_blocks(const uint8_t *d_bwt, const uint32_t *d_mark_blocks, int64_t n, uint8_t *d_bm, int64_t nwb, cudaStream_t st) {
+    build_walk_blocks_kernel<<<(unsigned)((nwb + 127) / 128), 128, 0, st>>>(d_bwt, d_mark_blocks, n, d_bm, nwb);
+    return cudaGetLastError();
+}
+
 cudaError_t build_full_sa(const DevIndex &ix, int layout, uint32_t *d_sa, uint32_t *d_isa, uint8_t *d_text, cudaStream_t st, std::string &err) {
     Chains ch;
     CK(prepare_chains(ix, layout, ch, st, err));

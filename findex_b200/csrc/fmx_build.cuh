@@ -16,6 +16,8 @@ cudaError_t build_planes(const uint8_t *d_bwt, int64_t n, uint32_t eof, const ui
 // sampled SA: marks rows with sa % rate == 0 (rank blocks, nblk) and stores their sa values in mark-rank order
 cudaError_t build_sa_samples(const DevIndex &ix, int layout, int rate, uint32_t *d_mark_blocks, int64_t nblk, uint32_t *d_samples,
                              int64_t n_samples, cudaStream_t st, std::string &err);
+// locate walk blocks (56 BWT bytes + 56 mark bits per 64 B); nwb = n/56 + 1
+cudaError_t build_walk_blocks(const uint8_t *d_bwt, const uint32_t *d_mark_blocks, int64_t n, uint8_t *d_bm, int64_t nwb, cudaStream_t st);
 // full suffix array, its inverse and T' (text[n-1] = 0) by the same chain walks
 cudaError_t build_full_sa(const DevIndex &ix, int layout, uint32_t *d_sa, uint32_t *d_isa, uint8_t *d_text, cudaStream_t st, std::string &err);
 // (sp,ep) after the first K backward steps for every K-mer over the sigma occurring symbols

@@ -31,6 +31,7 @@ struct DevIndex {
     const uint8_t *code;        // 256: byte -> dense code, kCodeAbsent if the byte does not occur
     const uint4   *mark;        // sampled-row marker bitvector (rank blocks) or nullptr
     const uint32_t *samples;    // sa value of the k-th marked row
+    const uint4   *bm;          // locate walk blocks: 56 BWT bytes + their 56 mark bits per 64 B (row r -> block r/56), or nullptr
     uint32_t n, eof;
     int32_t  layout, levels;
     uint32_t z[8];              // WM: zeros per level
@@ -164,6 +165,34 @@ __device__ __forceinline__ uint32_t rank_one(const uint4 *bv, uint32_t p, uint32
     }
     if (bit_out) *bit_out = bit;
     return h + s;
+}
+
+// BWT byte and sampled-row mark of row r from the fused walk blocks: one 64-B fetch per LF step instead of two
+constexpr uint32_t kRowsPerWalkBlock = 56;
+template <int G>
+__device__ __forceinline__ void walk_block(const uint4 *bm, uint32_t r, uint32_t &c, uint32_t &marked) {
+    const int lane = (G == 1) ? 0 : (threadIdx.x & (G - 1));
+    const uint32_t mask = group_mask<G>();
+    const uint32_t b = r / kRowsPerWalkBlock, o = r - b * kRowsPerWalkBlock;
+    LaneBlock<G> A = load_block<G>(bm, b, lane);
+    uint32_t cc = 0, mm = 0;
+    const uint32_t mbyte = 56 + (o >> 3);                       // byte holding the mark bit
+#pragma unroll
+    for (int i = 0; i < 4 / G; ++i) {
+        const uint32_t first = (uint32_t)(lane * (4 / G) + i) * 16u;   // first byte of this uint4 inside the block
+        const uint4 q = A.v[i];
+        if (o >= first && o < first + 16) {
+            const uint32_t rel = o - first, w = (rel >> 2) == 0 ? q.x : (rel >> 2) == 1 ? q.y : (rel >> 2) == 2 ? q.z : q.w;
+            cc = (w >> (8 * (rel & 3))) & 0xFFu;
+        }
+        if (mbyte >= first && mbyte < first + 16) {
+            const uint32_t rel = mbyte - first, w = (rel >> 2) == 0 ? q.x : (rel >> 2) == 1 ? q.y : (rel >> 2) == 2 ? q.z : q.w;
+            mm = (w >> (8 * (rel & 3) + (o & 7))) & 1u;
+        }
+    }
+    if (G > 1) { cc = group_sum<G>(cc, mask); mm = group_sum<G>(mm, mask); }   // exactly one lane holds each
+    c = cc;
+    marked = mm;
 }
 
 // ---- one backward step: (sp,ep) -> (C[c]+rank_c(sp), C[c]+rank_c(ep))   findex.scala:32-36 ------------

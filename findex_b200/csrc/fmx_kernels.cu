@@ -238,6 +238,19 @@ locate_kernel(const __grid_constant__ DevIndex ix, const long long *__restrict__
         return;
     }
     uint32_t k = 0;
+    if (ix.bm != nullptr) {                                    // fused walk blocks: BWT byte + mark bit in one fetch per step
+        for (;;) {
+            uint32_t c, marked;
+            walk_block<G>(ix.bm, r, c, marked);
+            if (marked) {
+                const uint32_t mr = rank_one<G>(ix.mark, r, nullptr);
+                if ((threadIdx.x % G) == 0) pos[t] = ix.samples[mr] + k;
+                return;
+            }
+            r = lf_value<G, LAYOUT>(ix, tb, c, r);
+            ++k;
+        }
+    }
     for (;;) {
         uint32_t bit;
         const uint32_t mr = rank_one<G>(ix.mark, r, &bit);
