@@ -221,7 +221,7 @@ def main():
             sp, ep = g.count_fixed(pats)
             ms = g.last_kernel_ms()
             blocks, steps = g.count_fixed_stats(pats)
-            emit(fh, what="cfg5_count_1gpu", layout=lay, queries=m, pipeline_ms=ms, hits=int((ep > sp).sum()), blocks_per_query=blocks / m,
+            emit(fh, what="cfg5_count_1gpu", queries=m, pipeline_ms=ms, hits=int((ep > sp).sum()), blocks_per_query=blocks / m,
                  steps_per_query=steps / m, **info)
             g.close()
 
