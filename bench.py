@@ -26,6 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+OUT = sys.stdout
 METRIC = "fm_count_queries_per_s_len16_1GB_text"
 UNIT = "queries/s"
 
@@ -174,7 +175,7 @@ def run_reference(args, rank, world):
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sdesc,
                             "note": "JVM unavailable - C restatement of the reference algorithm (binary search in .fm)"},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=OUT, flush=True)
 
 
 def workload_config(args):
@@ -224,15 +225,43 @@ def run_ours(args, rank, world, local_rank):
     d_all = torch.zeros(m * world, dtype=torch.int32, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream().cuda_stream
 
+    # N > 1: the batch is cut into chunks; the NCCL all-gather of chunk c's hit counts (the one exchange step of the path) runs on a
+    # side stream while the count kernel works on chunk c+1, so only the last chunk's gather is exposed.
+    nch = 4 if world > 1 else 1
+    csz = (m + nch - 1) // nch
+    bounds = [(c * csz, min(m, (c + 1) * csz)) for c in range(nch)]
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    ev_k = [torch.cuda.Event() for _ in range(nch)]
+    ev_c = [torch.cuda.Event() for _ in range(nch)]
+    d_all_c = [torch.zeros((hi - lo) * world, dtype=torch.int32, device=dev) for lo, hi in bounds] if world > 1 else None
+
     def step():
-        g.count_fixed_dev(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), stream)
-        if world > 1:                                   # the one exchange step: all-gather of the hit counts
-            torch.sub(d_ep, d_sp, out=d_cnt)
-            dist.all_gather_into_tensor(d_all, d_cnt)
+        if world == 1:
+            g.count_fixed_dev(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), stream)
+            return
+        cur = torch.cuda.current_stream()
+        for c, (lo, hi) in enumerate(bounds):
+            cur.wait_event(ev_c[c])                     # the previous step's read of this chunk's sp/ep is done
+            g.count_fixed_dev(d_pat.data_ptr() + lo * ln, ln, hi - lo, d_sp.data_ptr() + lo * 4, d_ep.data_ptr() + lo * 4, stream)
+            ev_k[c].record(cur)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev_k[c])
+                torch.sub(d_ep[lo:hi], d_sp[lo:hi], out=d_cnt[lo:hi])
+                ev_c[c].record(comm)
+                dist.all_gather_into_tensor(d_all_c[c], d_cnt[lo:hi])
+
+    def drain():
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(comm)
 
     # ---- sanity at full size (parity proper lives in tests/): hits are found, a few are verified by brute force
     step()
+    drain()
     torch.cuda.synchronize()
+    if world > 1:                                       # every rank holds every rank's counts after the gather
+        lo, hi = bounds[0]
+        mine = d_all_c[0].view(world, hi - lo)[rank]
+        assert torch.equal(mine, (d_ep[lo:hi] - d_sp[lo:hi])), "all-gathered counts differ from the local ones"
     sp = d_sp.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
     ep = d_ep.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
     cnt = ep - sp
@@ -255,6 +284,7 @@ def run_ours(args, rank, world, local_rank):
         sampler.start()
         for _ in range(args.warmup):
             fn()
+        drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -265,6 +295,7 @@ def run_ours(args, rank, world, local_rank):
         e0.record()
         for _ in range(args.steps):
             fn()
+        drain()
         e1.record()
         torch.cuda.synchronize()
         wall = time.time() - t_wall
@@ -318,7 +349,7 @@ def run_ours(args, rank, world, local_rank):
            "clocks": clocks,
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": m * ln, "d2h_bytes_per_step": m * 16, "ms_per_step": ms_e2e / args.steps,
                    "api": "fmx_count_fixed (host pinned buffers in/out, int64 sp/ep)", "clocks": clocks_e2e},
-           "gpu_launches": args.steps,
+           "gpu_launches": args.steps * nch,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                         "peak_source": peak_src, "kernel": "count_fixed_kernel", "kernel_ms": k_ms,
                         "algorithmic_bytes_per_launch": alg_bytes, "distinct_blocks_per_query": blocks / m, "executed_steps_per_query": steps_exec / m,
@@ -328,7 +359,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and rank == 0 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(args, base, pats, sp, ep, cnt)
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=OUT, flush=True)
     g.close()
 
 
@@ -361,6 +392,38 @@ def cpu_baseline(args, base, pats, sp, ep, cnt):
             "parity_on_sample": parity, "note": "JVM unavailable - C restatement of the reference algorithm (binary search in .fm)"}
 
 
+def protect_stdout():
+    """Libraries (NCCL prints its version) may write to fd 1; the contract is ONE JSON line on stdout.  Point fd 1 at stderr and
+    keep the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank (and allocate its pinned buffers) on the NUMA node its GPU hangs off."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:00.0/numa_node" % (dom, bus)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception as e:
+        log("numa binding skipped:", e)
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -380,6 +443,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    global OUT
+    OUT = protect_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -387,6 +452,8 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
+        node = bind_to_gpu_numa_node(local_rank)
+        log("rank %d: bound to NUMA node %s" % (rank, node))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
         run_ours(args, rank, world, local_rank)
