@@ -227,28 +227,65 @@ def run_ours(args, rank, world, local_rank):
 
     # N > 1: the batch is cut into chunks; the NCCL all-gather of chunk c's hit counts (the one exchange step of the path) runs on a
     # side stream while the count kernel works on chunk c+1, so only the last chunk's gather is exposed.
-    nch = 4 if world > 1 else 1
+    nch = max(1, args.gather_chunks) if world > 1 else 1
     csz = (m + nch - 1) // nch
     bounds = [(c * csz, min(m, (c + 1) * csz)) for c in range(nch)]
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
-    ev_k = [torch.cuda.Event() for _ in range(nch)]
-    ev_c = [torch.cuda.Event() for _ in range(nch)]
-    d_all_c = [torch.zeros((hi - lo) * world, dtype=torch.int32, device=dev) for lo, hi in bounds] if world > 1 else None
+    # two result sets, alternated per step, so that step k+1's kernel never waits for step k's gather to finish reading
+    sets = [dict(sp=d_sp, ep=d_ep, cnt=d_cnt)]
+    if world > 1:
+        sets.append(dict(sp=torch.zeros_like(d_sp), ep=torch.zeros_like(d_ep), cnt=torch.zeros_like(d_cnt)))
+        for st_ in sets:
+            st_["all"] = [torch.zeros((hi - lo) * world, dtype=torch.int32, device=dev) for lo, hi in bounds]
+            st_["ev_k"] = [torch.cuda.Event() for _ in range(nch)]
+            st_["ev_c"] = [torch.cuda.Event() for _ in range(nch)]
+    counter = [0]
+
+    p2p = world > 1 and args.exchange == "p2p"
+    if p2p:
+        # fused compute + exchange: every rank maps every rank's gathered buffer (CUDA IPC over NVLink/NVSwitch peer memory) and the
+        # count kernel stores its hit counts straight into all of them; NCCL is left with one 4-byte all-reduce per step as the
+        # cross-rank completion barrier.  Two buffer sets alternate so step k+1 never writes what step k's consumers read.
+        gath = [fx.SharedDeviceBuffer(m * world) for _ in range(2)]
+        mine = [gb.export_handle() for gb in gath]
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        sinks = [[gath[b].ptr if r == rank else gath[b].import_peer(r, everyone[r][b]) for r in range(world)] for b in range(2)]
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        pev_k = [torch.cuda.Event() for _ in range(2)]
+        pev_c = [torch.cuda.Event() for _ in range(2)]
 
     def step():
         if world == 1:
             g.count_fixed_dev(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), stream)
             return
         cur = torch.cuda.current_stream()
-        for c, (lo, hi) in enumerate(bounds):
-            cur.wait_event(ev_c[c])                     # the previous step's read of this chunk's sp/ep is done
-            g.count_fixed_dev(d_pat.data_ptr() + lo * ln, ln, hi - lo, d_sp.data_ptr() + lo * 4, d_ep.data_ptr() + lo * 4, stream)
-            ev_k[c].record(cur)
+        if p2p:
+            b = counter[0] & 1
+            counter[0] += 1
+            cur.wait_event(pev_c[b])                    # the barrier of the step that last wrote this buffer set has passed
+            g.count_fixed_dev_gather(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), sinks[b], rank * m, cur.cuda_stream)
+            pev_k[b].record(cur)
             with torch.cuda.stream(comm):
-                comm.wait_event(ev_k[c])
-                torch.sub(d_ep[lo:hi], d_sp[lo:hi], out=d_cnt[lo:hi])
-                ev_c[c].record(comm)
-                dist.all_gather_into_tensor(d_all_c[c], d_cnt[lo:hi])
+                comm.wait_event(pev_k[b])
+                dist.all_reduce(flag)                   # after this, every rank's stores of this step have landed everywhere
+                pev_c[b].record(comm)
+            return
+        b = sets[counter[0] & 1]
+        counter[0] += 1
+        for c, (lo, hi) in enumerate(bounds):
+            cur.wait_event(b["ev_c"][c])                # the gather that last used this result set has read it (two steps ago)
+            g.count_fixed_dev(d_pat.data_ptr() + lo * ln, ln, hi - lo, b["sp"].data_ptr() + lo * 4, b["ep"].data_ptr() + lo * 4, stream)
+            b["ev_k"][c].record(cur)
+            if args.diag == "nocomm":
+                continue
+            with torch.cuda.stream(comm):
+                comm.wait_event(b["ev_k"][c])
+                if args.diag != "nosub":
+                    torch.sub(b["ep"][lo:hi], b["sp"][lo:hi], out=b["cnt"][lo:hi])
+                if args.diag != "nogather":
+                    dist.all_gather_into_tensor(b["all"][c], b["cnt"][lo:hi])
+                b["ev_c"][c].record(comm)
 
     def drain():
         if world > 1:
@@ -258,10 +295,21 @@ def run_ours(args, rank, world, local_rank):
     step()
     drain()
     torch.cuda.synchronize()
-    if world > 1:                                       # every rank holds every rank's counts after the gather
-        lo, hi = bounds[0]
-        mine = d_all_c[0].view(world, hi - lo)[rank]
-        assert torch.equal(mine, (d_ep[lo:hi] - d_sp[lo:hi])), "all-gathered counts differ from the local ones"
+    if world > 1:                                       # every rank holds every rank's counts after the exchange
+        local = (d_ep - d_sp)
+        if p2p:
+            dist.barrier()
+            got = torch.from_numpy(gath[0].to_host().astype(np.int64)).to(dev)
+            assert torch.equal(got[rank * m:(rank + 1) * m], local.to(torch.int64) & 0xFFFFFFFF), "gathered counts differ from the local ones"
+            cs = (got * torch.arange(1, got.numel() + 1, device=dev) % 1000003).sum().reshape(1)
+            lo_, hi_ = cs.clone(), cs.clone()
+            dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+            assert int(lo_) == int(hi_), "ranks disagree on the gathered counts"
+        else:
+            lo, hi = bounds[0]
+            mine_ = sets[0]["all"][0].view(world, hi - lo)[rank]
+            assert args.diag != "none" or torch.equal(mine_, local[lo:hi]), "all-gathered counts differ from the local ones"
     sp = d_sp.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
     ep = d_ep.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
     cnt = ep - sp
@@ -344,12 +392,12 @@ def run_ours(args, rank, world, local_rank):
             pass
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-           "data": "synthetic", "config": dict(workload_config(args), layout=info["layout"], lanes_per_query=info["lanes_per_query"],
+           "data": "synthetic", "config": dict(workload_config(args), exchange=("none" if world == 1 else ("fused peer stores + 4-byte NCCL barrier" if p2p else "NCCL all_gather_into_tensor on a side stream")), layout=info["layout"], lanes_per_query=info["lanes_per_query"],
                                                index_bytes=info["index_bytes"], kmer_k=info["kmer_k"], text_shortcut=info["text_shortcut"], checksum=checksum),
            "clocks": clocks,
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": m * ln, "d2h_bytes_per_step": m * 16, "ms_per_step": ms_e2e / args.steps,
                    "api": "fmx_count_fixed (host pinned buffers in/out, int64 sp/ep)", "clocks": clocks_e2e},
-           "gpu_launches": args.steps * nch,
+           "gpu_launches": args.steps * (1 if (world == 1 or p2p) else nch),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                         "peak_source": peak_src, "kernel": "count_fixed_kernel", "kernel_ms": k_ms,
                         "algorithmic_bytes_per_launch": alg_bytes, "distinct_blocks_per_query": blocks / m, "executed_steps_per_query": steps_exec / m,
@@ -360,6 +408,16 @@ def run_ours(args, rank, world, local_rank):
         out["cpu_baseline"] = cpu_baseline(args, base, pats, sp, ep, cnt)
     if rank == 0:
         print(json.dumps(out), file=OUT, flush=True)
+    if p2p:
+        torch.cuda.synchronize()
+        dist.barrier()
+        for gb in gath:
+            for ptr in list(gb.peers.values()):
+                fx.lib().fmx_ipc_close(ptr)
+            gb.peers = {}
+        dist.barrier()
+        for gb in gath:
+            gb.close()
     g.close()
 
 
@@ -436,6 +494,9 @@ def main():
     ap.add_argument("--layout", default="auto", choices=["auto", "wm", "planes"])
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--accel", default="auto", choices=["auto", "none", "kmer", "text", "both"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory stores (default) or NCCL all-gather")
+    ap.add_argument("--gather-chunks", type=int, default=1)
+    ap.add_argument("--diag", default="none", choices=["none", "nocomm", "nosub", "nogather"], help="diagnostics only: drop parts of the exchange")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -499,6 +499,55 @@ int fmx_count_fixed_dev(fmx_index *ix, const void *d_pat, int32_t len, int64_t m
 // kernel on chunk k and the D2H of chunk k-1 overlap (PCIe is full duplex).  With pinned (fmx_host_alloc'ed or
 // cudaHostRegister'ed) caller buffers every copy is an asynchronous DMA; with pageable buffers the driver stages
 // the copies and the pipeline degrades gracefully to copy-then-compute.
+// Fused count + all-gather: every hit count is also stored into n_sinks gathered buffers (this rank's own and its peers',
+// opened with fmx_ipc_import) at element offset `offset`.  The caller orders the consumers behind the producers
+// (stream order on this GPU plus one tiny cross-rank barrier per step).
+int fmx_count_fixed_dev_gather(fmx_index *ix, const void *d_pat, int32_t len, int64_t m, void *d_sp, void *d_ep,
+                               void *const *sinks, int32_t n_sinks, int64_t offset, void *stream) {
+    CHECK_IX(ix);
+    if (len < 0 || m < 0 || n_sinks < 0 || n_sinks > 8 || offset < 0 || (n_sinks && !sinks) || (m && (!d_sp || !d_ep || (len && !d_pat))))
+        return fail(FMX_E_ARG, "bad argument");
+    PeerSinks ps{};
+    ps.n = n_sinks;
+    ps.offset = offset;
+    for (int j = 0; j < n_sinks; ++j) { if (!sinks[j]) return fail(FMX_E_ARG, "null sink %d", j); ps.p[j] = (uint32_t *)sinks[j]; }
+    DeviceGuard g(ix->device);
+    CU(launch_count_fixed(ix->d, ix->cfg, (const uint8_t *)d_pat, len, m, d_sp, d_ep, false, nullptr, (cudaStream_t)stream, &ps));
+    ix->last_launches = 1; ix->total_launches += 1;
+    return FMX_OK;
+}
+
+// ---- raw device buffers that can be shared between the ranks of one node (CUDA IPC) -----------------------------------
+int fmx_dev_alloc(void **p, int64_t bytes) {
+    if (!p || bytes < 0) return fail(FMX_E_ARG, "bad argument");
+    CU(cudaMalloc(p, (size_t)(bytes ? bytes : 1)));
+    CU(cudaMemset(*p, 0, (size_t)(bytes ? bytes : 1)));
+    return FMX_OK;
+}
+int fmx_dev_free(void *p) { if (p) CU(cudaFree(p)); return FMX_OK; }
+int fmx_ipc_export(void *p, uint8_t handle[64]) {
+    if (!p || !handle) return fail(FMX_E_ARG, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, p));
+    std::memcpy(handle, &h, 64);
+    return FMX_OK;
+}
+int fmx_ipc_import(const uint8_t handle[64], void **p) {
+    if (!p || !handle) return fail(FMX_E_ARG, "bad argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess));
+    return FMX_OK;
+}
+int fmx_ipc_close(void *p) { if (p) CU(cudaIpcCloseMemHandle(p)); return FMX_OK; }
+int fmx_memcpy_d2h(void *dst, const void *src, int64_t bytes) {
+    if (bytes < 0 || (bytes && (!dst || !src))) return fail(FMX_E_ARG, "bad argument");
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return FMX_OK;
+}
+
 int fmx_count_fixed(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, int64_t *sp, int64_t *ep) {
     CHECK_IX(ix);
     if (len < 0 || m < 0 || (m && (!sp || !ep || (len && !pat)))) return fail(FMX_E_ARG, "bad argument");

@@ -23,7 +23,7 @@ namespace fmx {
 template <int G, int LAYOUT, bool STATS, typename OutT>
 __global__ void __launch_bounds__(kThreads, (G == 1) ? 4 : 8)
 count_fixed_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, int len, long long m,
-                   OutT *__restrict__ sp_out, OutT *__restrict__ ep_out, unsigned long long *stats) {
+                   OutT *__restrict__ sp_out, OutT *__restrict__ ep_out, unsigned long long *stats, const __grid_constant__ PeerSinks sinks) {
     __shared__ SharedTables tb;
     extern __shared__ __align__(16) uint8_t spat[];
     constexpr int QPB = kThreads / G;                     // queries per CTA
@@ -54,6 +54,13 @@ count_fixed_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restric
         const bool hit = sp < ep;
         sp_out[q0 + g] = hit ? (OutT)sp : (OutT)0;
         ep_out[q0 + g] = hit ? (OutT)ep : (OutT)0;
+        // fused exchange: the hit count goes straight into every rank's gathered buffer (peer-mapped memory over
+        // NVLink/NVSwitch); consecutive queries of a warp form one contiguous 64-B (G=2) store segment per peer
+        if (sinks.n > 0) {
+            const uint32_t cnt = hit ? ep - sp : 0u;
+#pragma unroll 1
+            for (int j = 0; j < sinks.n; ++j) sinks.p[j][sinks.offset + q0 + g] = cnt;
+        }
     }
     if (STATS) {
         if ((threadIdx.x % G) != 0) { touched = 0; steps = 0; }
@@ -384,8 +391,10 @@ static inline unsigned grid_for(int64_t items, int lanes) {
 }
 
 cudaError_t launch_count_fixed(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_pat, int len, int64_t m, void *d_sp,
-                               void *d_ep, bool out64, unsigned long long *d_stats, cudaStream_t st) {
+                               void *d_ep, bool out64, unsigned long long *d_stats, cudaStream_t st, const PeerSinks *sinks_or_null) {
     if (m <= 0) return cudaSuccess;
+    PeerSinks sinks{};
+    if (sinks_or_null) sinks = *sinks_or_null;
     const size_t smem = (size_t)(kThreads / cfg.lanes) * (size_t)(len > 0 ? len : 1);
     if (smem > 160 * 1024) return cudaErrorInvalidValue;
 #define CALL(G, LAY)                                                                                                  \
@@ -393,15 +402,15 @@ cudaError_t launch_count_fixed(const DevIndex &ix, LaunchCfg cfg, const uint8_t 
         if (d_stats) {                                                                                                \
             auto k = count_fixed_kernel<G, LAY, true, uint32_t>;                                                      \
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
-            k<<<grid_for(m, G), kThreads, smem, st>>>(ix, d_pat, len, m, (uint32_t *)d_sp, (uint32_t *)d_ep, d_stats); \
+            k<<<grid_for(m, G), kThreads, smem, st>>>(ix, d_pat, len, m, (uint32_t *)d_sp, (uint32_t *)d_ep, d_stats, sinks); \
         } else if (out64) {                                                                                           \
             auto k = count_fixed_kernel<G, LAY, false, long long>;                                                    \
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
-            k<<<grid_for(m, G), kThreads, smem, st>>>(ix, d_pat, len, m, (long long *)d_sp, (long long *)d_ep, nullptr); \
+            k<<<grid_for(m, G), kThreads, smem, st>>>(ix, d_pat, len, m, (long long *)d_sp, (long long *)d_ep, nullptr, sinks); \
         } else {                                                                                                      \
             auto k = count_fixed_kernel<G, LAY, false, uint32_t>;                                                     \
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
-            k<<<grid_for(m, G), kThreads, smem, st>>>(ix, d_pat, len, m, (uint32_t *)d_sp, (uint32_t *)d_ep, nullptr); \
+            k<<<grid_for(m, G), kThreads, smem, st>>>(ix, d_pat, len, m, (uint32_t *)d_sp, (uint32_t *)d_ep, nullptr, sinks); \
         }                                                                                                             \
     }
     FMX_DISPATCH(cfg, CALL);

@@ -11,9 +11,17 @@ struct LaunchCfg {
     int lanes;           // 1, 2 or 4 lanes per query
 };
 
+// fused exchange: up to 8 gathered buffers (one per rank, peer-mapped) that receive this shard's hit counts
+struct PeerSinks {
+    uint32_t *p[8];
+    int32_t   n;
+    long long offset;            // element offset of this shard inside each gathered buffer
+};
+
 // count: fixed-length patterns (device pointers).  out64 selects int64 vs uint32 outputs.
 cudaError_t launch_count_fixed(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_pat, int len, int64_t m,
-                               void *d_sp, void *d_ep, bool out64, unsigned long long *d_stats, cudaStream_t st);
+                               void *d_sp, void *d_ep, bool out64, unsigned long long *d_stats, cudaStream_t st,
+                               const PeerSinks *sinks_or_null = nullptr);
 // count: variable-length patterns with int64 offsets.
 cudaError_t launch_count_var(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_pat, const int64_t *d_off, int64_t m,
                              int64_t *d_sp, int64_t *d_ep, cudaStream_t st);

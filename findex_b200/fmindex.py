@@ -74,6 +74,13 @@ def lib():
     L.fmx_count_batch.argtypes = [p, p, p, i64, p, p]
     L.fmx_count_fixed.argtypes = [p, p, i32, i64, p, p]
     L.fmx_count_fixed_dev.argtypes = [p, p, i32, i64, p, p, p]
+    L.fmx_count_fixed_dev_gather.argtypes = [p, p, i32, i64, p, p, p, i32, i64, p]
+    L.fmx_dev_alloc.argtypes = [pp, i64]
+    L.fmx_dev_free.argtypes = [p]
+    L.fmx_ipc_export.argtypes = [p, p]
+    L.fmx_ipc_import.argtypes = [p, pp]
+    L.fmx_ipc_close.argtypes = [p]
+    L.fmx_memcpy_d2h.argtypes = [p, p, i64]
     L.fmx_locate_batch.argtypes = [p, p, p, i64, i64, p, p]
     L.fmx_get_prev_i_batch.argtypes = [p, p, i64, p]
     L.fmx_get_next_i_batch.argtypes = [p, p, i64, p]
@@ -291,6 +298,12 @@ class GpuFMSearcher:
         """Raw device pointers (ints); asynchronous on `stream`."""
         _check(lib().fmx_count_fixed_dev(self.h, C.c_void_p(d_pat), ln, m, C.c_void_p(d_sp), C.c_void_p(d_ep), C.c_void_p(stream)))
 
+    def count_fixed_dev_gather(self, d_pat, ln, m, d_sp, d_ep, sinks, offset, stream=0):
+        """Fused count + exchange: `sinks` = device pointers (ints) of every rank's gathered uint32 buffer."""
+        arr = (C.c_void_p * max(len(sinks), 1))(*sinks)
+        _check(lib().fmx_count_fixed_dev_gather(self.h, C.c_void_p(d_pat), ln, m, C.c_void_p(d_sp), C.c_void_p(d_ep), arr, len(sinks), offset,
+                                                C.c_void_p(stream)))
+
     def count_fixed_stats(self, pat2d):
         pat2d = np.ascontiguousarray(pat2d, dtype=np.uint8)
         m, ln = pat2d.shape
@@ -392,6 +405,42 @@ class PinnedArray:
             self.array = None
             lib().fmx_host_free(self.p)
             self.p = None
+
+
+class SharedDeviceBuffer:
+    """A cudaMalloc'ed uint32 buffer that the ranks of one node map into each other through CUDA IPC."""
+
+    def __init__(self, n_elems):
+        self.n = n_elems
+        p = C.c_void_p()
+        _check(lib().fmx_dev_alloc(C.byref(p), n_elems * 4))
+        self.ptr = p.value
+        self.peers = {}
+
+    def export_handle(self):
+        h = (C.c_uint8 * 64)()
+        _check(lib().fmx_ipc_export(C.c_void_p(self.ptr), h))
+        return bytes(h)
+
+    def import_peer(self, rank, handle):
+        p = C.c_void_p()
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        _check(lib().fmx_ipc_import(buf, C.byref(p)))
+        self.peers[rank] = p.value
+        return p.value
+
+    def to_host(self):
+        out = np.zeros(self.n, np.uint32)
+        _check(lib().fmx_memcpy_d2h(_ptr(out), C.c_void_p(self.ptr), self.n * 4))
+        return out
+
+    def close(self):
+        for p in self.peers.values():
+            lib().fmx_ipc_close(C.c_void_p(p))
+        self.peers = {}
+        if self.ptr:
+            lib().fmx_dev_free(C.c_void_p(self.ptr))
+            self.ptr = None
 
 
 def set_l2_fetch_granularity(nbytes=0):

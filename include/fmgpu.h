@@ -108,6 +108,20 @@ int fmx_count_fixed(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, i
 int fmx_count_fixed_dev(fmx_index *ix, const void *d_pat, int32_t len, int64_t m,
                         void *d_sp_u32, void *d_ep_u32, void *stream);
 
+/* Fused count + exchange for the multi-GPU path (index replicated, batch sharded): besides d_sp/d_ep, the hit
+ * count (ep-sp, uint32) of local query q is stored to sinks[j][offset+q] for each of the n_sinks (<= 8) gathered
+ * buffers — this rank's and, via CUDA IPC, its peers' — so the all-gather of counts happens inside the kernel over
+ * NVLink/NVSwitch peer memory instead of in a separate collective.                                          */
+int fmx_count_fixed_dev_gather(fmx_index *ix, const void *d_pat, int32_t len, int64_t m, void *d_sp_u32, void *d_ep_u32,
+                               void *const *sinks, int32_t n_sinks, int64_t offset, void *stream);
+/* cudaMalloc'ed, zeroed buffers that the ranks of one node can map into each other (cudaIpc*).               */
+int fmx_dev_alloc(void **p, int64_t bytes);
+int fmx_dev_free(void *p);
+int fmx_ipc_export(void *p, uint8_t handle[64]);
+int fmx_ipc_import(const uint8_t handle[64], void **p);
+int fmx_ipc_close(void *p);
+int fmx_memcpy_d2h(void *dst, const void *src, int64_t bytes);
+
 /* ---- locate: sorted { sa[r] : r in [sp,ep) }, sa as bwtFm2sa  M/util.scala:213-224 -----------------
  * (== SACreator.create M/bwtmerger.scala:541-555).  Positions are in T' = reverse(file)+'$' coordinates;
  * file offset of a length-k match = (n-1) - pos - k.  out_off[m+1] receives the per-query offsets;
