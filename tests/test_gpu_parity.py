@@ -393,3 +393,35 @@ def test_regex_frontier_growth_and_replay(ref_dir, o1024):
         assert res == memo[rx], rx
     assert sum(len(r) for r in got) > 1000
     g.close()
+
+
+def test_fused_count_and_exchange_single_gpu(ref_dir):
+    """The fused count+all-gather entry point with this GPU playing every rank: three 'ranks' shard a batch and each stores its
+    hit counts into all three gathered buffers; every buffer must end up holding the counts of the whole batch."""
+    import torch
+    text = open(os.path.join(ref_dir, "test.txt"), "rb").read()
+    o = fo.OracleIndex.load(os.path.join(ref_dir, "test.cmp"), big_endian=False)
+    g = _open(os.path.join(ref_dir, "test.cmp.bwt"), (fx.LAYOUT_PLANES, 2))
+    rng = np.random.default_rng(3)
+    m, ln, world = 3000, 6, 3
+    offs = rng.integers(0, len(text) - ln, m)
+    tarr = np.frombuffer(text, np.uint8)
+    pats = np.stack([tarr[s:s + ln][::-1] for s in offs])
+    pats[::5] = rng.integers(97, 123, (len(pats[::5]), ln), dtype=np.uint8)
+    osp, oep = o.count_batch(pats.reshape(-1), np.arange(0, m * ln + 1, ln, dtype=np.int64))
+    bufs = [fx.SharedDeviceBuffer(m) for _ in range(world)]
+    d_pat = torch.from_numpy(pats).cuda()
+    d_sp = torch.zeros(m, dtype=torch.int32, device="cuda")
+    d_ep = torch.zeros(m, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    per = m // world
+    for r in range(world):
+        lo, hi = r * per, (r + 1) * per
+        g.count_fixed_dev_gather(d_pat.data_ptr() + lo * ln, ln, hi - lo, d_sp.data_ptr() + lo * 4, d_ep.data_ptr() + lo * 4,
+                                 [b.ptr for b in bufs], lo, st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sp.cpu().numpy(), osp) and np.array_equal(d_ep.cpu().numpy(), oep)
+    for b in bufs:
+        assert np.array_equal(b.to_host().astype(np.int64), oep - osp)
+        b.close()
+    g.close()
