@@ -84,6 +84,13 @@ template <typename T> T *dev_upload(fmx_index *ix, const T *host, size_t count, 
     return reinterpret_cast<T *>(p);
 }
 
+// The stream-ordered pool keeps freed blocks cached (release threshold = max) so that batch calls do not re-map memory;
+// after the large one-off constructions the cache is handed back.
+void trim_pool(int dev) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+}
+
 int bitrev(int v, int bits) { int r = 0; for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1) << (bits - 1 - i); return r; }
 
 // ---- index upload (K0): tables on the host, rank structures on the device -------------------------------
@@ -196,6 +203,8 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     int accel = o.accel;
     if (accel & FMX_ACCEL_NONE) accel = FMX_ACCEL_NONE;
     size_t fr = 0, to = 0;
+    CU(cudaStreamSynchronize(ix->stream));
+    trim_pool(ix->device);
     cudaMemGetInfo(&fr, &to);
     const bool want_text = (accel & FMX_ACCEL_TEXT) || (accel == FMX_ACCEL_AUTO && 9 * n + (2ll << 30) < (int64_t)fr && ix->index_bytes + 9 * n <= budget + (16ll << 30));
     const bool want_kmer = (accel & FMX_ACCEL_KMER) || accel == FMX_ACCEL_AUTO;
@@ -232,6 +241,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     ix->accel_text = d.text != nullptr;
     ix->kmer_k = d.kmer ? d.kmer_k : 0;
     CU(cudaStreamSynchronize(ix->stream));
+    trim_pool(ix->device);                              // construction scratch goes back to the device
     return FMX_OK;
 }
 
@@ -797,6 +807,18 @@ int fmx_regex_compile(const uint8_t *re, int64_t re_len, int line_only, fmx_rege
     *out = rx;
     return FMX_OK;
 }
+int fmx_regex_compile_engine(const uint8_t *re, int64_t re_len, int line_only, int engine, fmx_regex **out) {
+    if (engine == FMX_ENGINE_GLUSHKOV) return fmx_regex_compile(re, re_len, line_only, out);
+    if (engine != FMX_ENGINE_THOMPSON) return fail(FMX_E_ARG, "unknown regex engine %d", engine);
+    if (!out || re_len < 0 || (re_len && !re)) return fail(FMX_E_ARG, "bad argument");
+    *out = nullptr;
+    fmx_regex *rx = new fmx_regex();
+    std::string err;
+    int rc = compile_thompson(re, re_len, line_only != 0, rx->a, err);
+    if (rc) { delete rx; return fail(rc, "%s", err.c_str()); }
+    *out = rx;
+    return FMX_OK;
+}
 void fmx_regex_free(fmx_regex *rx) { delete rx; }
 
 int fmx_regex_tables(const fmx_regex *rx, int32_t *n_states, int32_t *n_follows, int32_t *n_firsts, uint8_t *c, uint8_t *is_last,
@@ -830,7 +852,7 @@ int fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64
         const CompiledRegex &a = rx[r]->a;
         const uint32_t base = (uint32_t)st_c.size();
         for (size_t s = 0; s < a.c.size(); ++s) {
-            st_c.push_back(a.c[s]); st_last.push_back(a.is_last[s]); st_regex.push_back((uint32_t)r);
+            st_c.push_back(a.c[s]); st_last.push_back((uint8_t)(a.is_last[s] | (a.stop_on_emit ? 2 : 0))); st_regex.push_back((uint32_t)r);
             for (int32_t k = a.follows_off[s]; k < a.follows_off[s + 1]; ++k) fol.push_back(base + (uint32_t)a.follows[k]);
             fol_off.push_back((uint32_t)fol.size());
         }
@@ -979,6 +1001,7 @@ static int build_bwt_impl(const uint8_t *text, int64_t len, int device, std::vec
     CU(cudaStreamSynchronize(st));
     cudaFree(d_fwd); cudaFree(d_rev); cudaFree(d_bwt);
     cudaStreamDestroy(st);
+    trim_pool(dev);
     return FMX_OK;
 }
 

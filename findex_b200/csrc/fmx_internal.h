@@ -31,8 +31,10 @@ struct CompiledRegex {
     std::vector<int32_t> follows_off;  // CSR, size n_states+1
     std::vector<int32_t> follows;
     std::vector<int32_t> firsts;       // start positions
+    bool stop_on_emit = true;          // Glushkov: a last position emits and is not expanded; Thompson: it emits and goes on
 };
 int compile_regex(const uint8_t *re, int64_t len, bool line_only, CompiledRegex &out, std::string &err);
+int compile_thompson(const uint8_t *re, int64_t len, bool line_only, CompiledRegex &out, std::string &err);
 
 }  // namespace fmx
 

@@ -293,9 +293,12 @@ regex_level_kernel(const __grid_constant__ DevIndex ix, RegexTables rt, const Fr
         alive = it.sp < it.ep;
     }
     // ---- warp-aggregated emission --------------------------------------------------------------------
-    const bool last = alive && rt.st_last[it.state];
+    // state flags: bit0 = emits a result, bit1 = stop after emitting (Glushkov last position; a Thompson position goes on)
+    const uint32_t flg = alive ? rt.st_last[it.state] : 0u;
+    const bool last = (flg & 1u) != 0;
+    const bool stop = last && (flg & 2u);
     const uint32_t f0 = alive ? rt.fol_off[it.state] : 0u;
-    const uint32_t nf = (alive && !last && leader) ? (rt.fol_off[it.state + 1] - f0) : 0u;
+    const uint32_t nf = (alive && !stop && leader) ? (rt.fol_off[it.state + 1] - f0) : 0u;
     // matches: ballot + one atomic per warp
     const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, last && leader);
     if (mmask) {

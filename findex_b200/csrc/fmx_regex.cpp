@@ -347,6 +347,112 @@ int number_from(Tree &t, int i, int start) { int idx = start; return number_shar
 
 }  // namespace
 
+// ---- Thompson engine: REParser.createNFA (re2.scala:264-334) + the traversal contract of REParser.matchSA (:568-693) ----
+// A state point of the reference carries a list of intervals that are expanded independently, so the result multiset equals an
+// item-wise traversal over positions: one per ConstState, one per char of an IntervalState (`start until end`, exclusive).
+// follows(p) = the non-match terminal states of the epsilon closure of p's successor; p emits when that closure holds the
+// MatchState — and, unlike a Glushkov last position, is still expanded.  Throws where the reference does: AltPoint has no case
+// in createNFA, a nullable regex puts MatchState into the start front (no case in StatePoint.expand), an epsilon cycle of split
+// states recurses forever in outStates, an operator without operand pops an empty stack.
+namespace {
+struct TNode {
+    int kind;                 // 0 const, 1 interval, 2 split, 3 match
+    int c = 0, lo = 0, hi = 0;
+    int out = -1, out1 = -1, out2 = -1;
+};
+struct TLink { int node; int which; };          // which: 0 out, 1 out1, 2 out2
+struct TFrag { int start; std::vector<TLink> outs; };
+
+struct TBuilder {
+    std::vector<TNode> n;
+    int match;
+    TBuilder() { n.push_back(TNode{3}); match = 0; }
+    int make(int kind) { n.push_back(TNode{kind}); return (int)n.size() - 1; }
+    void patch(const std::vector<TLink> &outs, int target) {
+        for (const TLink &l : outs) { TNode &x = n[l.node]; (l.which == 0 ? x.out : l.which == 1 ? x.out1 : x.out2) = target; }
+    }
+    void closure_rec(int s, std::vector<char> &seen, std::vector<char> &onstack, std::vector<int> &order) const {
+        if (s < 0 || seen[s]) return;
+        if (n[s].kind == 2) {
+            if (onstack[s]) unsupported("StackOverflowError: epsilon cycle in the Thompson NFA");
+            onstack[s] = 1;
+            closure_rec(n[s].out1, seen, onstack, order);
+            closure_rec(n[s].out2, seen, onstack, order);
+            onstack[s] = 0;
+        } else { seen[s] = 1; order.push_back(s); }
+    }
+    std::vector<int> closure(int s) const {
+        std::vector<char> seen(n.size(), 0), onstack(n.size(), 0);
+        std::vector<int> order;
+        closure_rec(s, seen, onstack, order);
+        return order;
+    }
+};
+}  // namespace
+
+int compile_thompson(const uint8_t *re, int64_t len, bool line_only, CompiledRegex &out, std::string &err) {
+    try {
+        std::vector<Tok> post = to_postfix(re, len, line_only);
+        TBuilder b;
+        std::vector<TFrag> st;
+        auto pop = [&]() { if (st.empty()) unsupported("NoSuchElementException: empty stack"); TFrag f = std::move(st.back()); st.pop_back(); return f; };
+        for (const Tok &tk : post) {
+            switch (tk.kind) {
+            case T_QUEST: { TFrag e = pop(); int ns = b.make(2); b.n[ns].out1 = e.start; std::vector<TLink> o{{ns, 2}}; o.insert(o.end(), e.outs.begin(), e.outs.end()); st.push_back({ns, o}); break; }
+            case T_STAR:  { TFrag e = pop(); int ns = b.make(2); b.n[ns].out1 = e.start; b.patch(e.outs, ns); st.push_back({ns, {{ns, 2}}}); break; }
+            case T_PLUS:  { TFrag e = pop(); int ns = b.make(2); b.n[ns].out1 = e.start; b.patch(e.outs, ns); st.push_back({e.start, {{ns, 2}}}); break; }
+            case T_CAT:   { TFrag e2 = pop(), e1 = pop(); b.patch(e1.outs, e2.start); st.push_back({e1.start, e2.outs}); break; }
+            case T_OR:    { TFrag e2 = pop(), e1 = pop(); int ns = b.make(2); b.n[ns].out1 = e1.start; b.n[ns].out2 = e2.start;
+                            std::vector<TLink> o = e1.outs; o.insert(o.end(), e2.outs.begin(), e2.outs.end()); st.push_back({ns, o}); break; }
+            case T_CHAR:  { int ns = b.make(0); b.n[ns].c = tk.a; st.push_back({ns, {{ns, 0}}}); break; }
+            case T_RANGE: { int ns = b.make(1); b.n[ns].lo = tk.a; b.n[ns].hi = tk.b; st.push_back({ns, {{ns, 0}}}); break; }
+            default: unsupported("MatchError: createNFA has no case for a character set");
+            }
+        }
+        TFrag e0 = pop();
+        b.patch(e0.outs, b.match);
+
+        std::vector<int> first_states = b.closure(e0.start);
+        for (int s : first_states) if (s == b.match) unsupported("MatchError: StatePoint.expand has no case for MatchState (nullable regex)");
+        std::vector<int> term, idx_of(b.n.size(), -1);
+        std::vector<std::vector<int>> nexts;
+        auto see = [&](int s) { if (s != b.match && idx_of[s] < 0) { idx_of[s] = (int)term.size(); term.push_back(s); } };
+        for (int s : first_states) see(s);
+        for (size_t q = 0; q < term.size(); ++q) {
+            nexts.push_back(b.closure(b.n[term[q]].out));
+            for (int x : nexts.back()) see(x);
+        }
+        std::vector<std::vector<int>> pos_of(term.size());
+        out = CompiledRegex();
+        out.stop_on_emit = false;
+        for (size_t q = 0; q < term.size(); ++q) {
+            const TNode &t = b.n[term[q]];
+            const bool emits = std::find(nexts[q].begin(), nexts[q].end(), b.match) != nexts[q].end();
+            const int lo = t.kind == 0 ? t.c : t.lo, hi = t.kind == 0 ? t.c + 1 : t.hi;
+            for (int ch = lo; ch < hi; ++ch) {
+                pos_of[q].push_back((int)out.c.size());
+                out.c.push_back((uint8_t)ch);
+                out.is_last.push_back(emits ? 1 : 0);
+                out.num.push_back(0);
+            }
+        }
+        out.follows_off.push_back(0);
+        for (size_t q = 0; q < term.size(); ++q) {
+            std::vector<int32_t> f;
+            for (int x : nexts[q]) if (x != b.match) for (int p : pos_of[idx_of[x]]) f.push_back(p);
+            for (size_t k = 0; k < pos_of[q].size(); ++k) {
+                out.follows.insert(out.follows.end(), f.begin(), f.end());
+                out.follows_off.push_back((int32_t)out.follows.size());
+            }
+        }
+        for (int s : first_states) for (int p : pos_of[idx_of[s]]) out.firsts.push_back(p);
+        return FMX_OK;
+    } catch (const ParseError &e) {
+        err = e.msg;
+        return e.code;
+    }
+}
+
 int compile_regex(const uint8_t *re, int64_t len, bool line_only, CompiledRegex &out, std::string &err) {
     try {
         std::vector<Tok> post = to_postfix(re, len, line_only);

@@ -88,6 +88,7 @@ def lib():
     L.fmx_prev_substr_batch.argtypes = [p, p, i64, i32, p, p]
     L.fmx_next_substr_batch.argtypes = [p, p, i64, i32, p, p]
     L.fmx_regex_compile.argtypes = [p, i64, C.c_int, pp]
+    L.fmx_regex_compile_engine.argtypes = [p, i64, C.c_int, C.c_int, pp]
     L.fmx_regex_free.argtypes = [p]
     L.fmx_regex_free.restype = None
     L.fmx_regex_tables.argtypes = [p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), p, p, p, p, p, p]
@@ -145,13 +146,15 @@ def make_opts(device=-1, layout=LAYOUT_AUTO, sa_sample_rate=0, require_fm=False,
 class ReTree:
     """ReTree(REParser.re2post(regex, lineOnly)) — re2.scala:50-185 + retree.scala:156-370, compiled by libfmgpu."""
 
+    ENGINE = 0
+
     def __init__(self, regex, lineOnly=False):
         if isinstance(regex, str):
             regex = regex.encode("latin-1")
         self.regex = bytes(regex)
         h = C.c_void_p()
         buf = _u8(self.regex) if self.regex else np.zeros(1, np.uint8)
-        _check(lib().fmx_regex_compile(_ptr(buf), len(self.regex), int(lineOnly), C.byref(h)))
+        _check(lib().fmx_regex_compile_engine(_ptr(buf), len(self.regex), int(lineOnly), self.ENGINE, C.byref(h)))
         self.h = h
 
     def __del__(self):
@@ -179,6 +182,11 @@ class ReTree:
     def matchSA(self, sa):
         """ReTree.matchSA with the caps disabled: sorted list of (len, sp, ep)."""
         return sa.regex_search_batch([self])[0]
+
+
+class ThompsonNFA(ReTree):
+    """REParser.createNFA(REParser.re2post(regex, lineOnly)) — re2.scala:264-334; matchSA = REParser.matchSA uncapped."""
+    ENGINE = 1
 
 
 class GpuFMSearcher:

@@ -142,6 +142,13 @@ int fmx_next_substr_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t 
  * Compiles on the host to the reference's Glushkov position automaton, quirks included;
  * FMX_E_SYNTAX / FMX_E_UNSUPPORTED exactly where the reference throws.                                  */
 int  fmx_regex_compile(const uint8_t *re, int64_t re_len, int line_only, fmx_regex **out);
+/* Same front-end, choice of automaton: FMX_ENGINE_GLUSHKOV = ReTree (above); FMX_ENGINE_THOMPSON = REParser.createNFA
+ * M/re2/re2.scala:264-334, whose search is REParser.matchSA :568-693 with maxIterations = maxLength = 0 (a position that
+ * reaches the MatchState emits and is still expanded; no border trimming; `[..]` sets, nullable regexes and epsilon cycles
+ * are FMX_E_UNSUPPORTED exactly where the reference throws).  fmx_regex_search_batch accepts both kinds, also mixed.   */
+#define FMX_ENGINE_GLUSHKOV 0
+#define FMX_ENGINE_THOMPSON 1
+int  fmx_regex_compile_engine(const uint8_t *re, int64_t re_len, int line_only, int engine, fmx_regex **out);
 void fmx_regex_free(fmx_regex *rx);
 /* Introspection (used by the parity tests; mirrors CharNode.c/.num, isLast, follows, root.firsts).
  * follows_off has n_states+1 entries.  Pass NULL to skip an output.                                    */

@@ -561,3 +561,156 @@ def build(post, remove_nulls=True):
 
 def compile_regex(s, line_only=False, remove_nulls=True):
     return build(re2post(s, line_only), remove_nulls)
+
+
+# ====================================================================================================================
+# Thompson engine: REParser.createNFA (M/re2/re2.scala:264-334) + REParser.matchSA (:568-693), restated.
+#
+# matchSA carries StatePoint(len, state, intervals): every interval of a state point is expanded independently and all
+# survivors are handed to every terminal state of the epsilon-closure of `next` (BaseState.outStates, :213-226); a
+# MatchState in that closure emits one SAResult(len+1, sp, ep) per interval, the other states are enqueued.  As a multiset
+# of (len, sp, ep) this equals an item-wise traversal over "positions", where an IntervalState(start, end) contributes one
+# position per char in `start until end` (exclusive end, :472).  Unlike the Glushkov engine a position may both emit and
+# go on.  Tables: flags bit0 = emits (MatchState in the closure of next), bit1 = stop after emitting (never set here).
+# What throws in the reference: AltPoint has no case in createNFA (MatchError); a nullable regex puts MatchState into the
+# start front and StatePoint.expand has no case for it (MatchError); stack underflow (NoSuchElementException).
+# ====================================================================================================================
+class _TState:
+    __slots__ = ("kind", "c", "start", "end", "out", "out1", "out2", "idx")
+
+    def __init__(self, kind, c=0, start=0, end=0):
+        self.kind, self.c, self.start, self.end = kind, c, start, end
+        self.out = [None]            # LinkState of Const / Interval
+        self.out1 = [None]           # LinkStates of Split
+        self.out2 = [None]
+
+
+_MATCH = _TState("match")
+
+
+def thompson_nfa(post):
+    """createNFA: returns the start state."""
+    st = []
+
+    def pop():
+        if not st:
+            raise ReUnsupported("NoSuchElementException: empty stack")
+        return st.pop()
+
+    def patch(outs, s):
+        for link in outs:
+            link[0] = s
+
+    for t in post:
+        k = t.kind
+        if k == "quest":
+            start, outs = pop()
+            ns = _TState("split")
+            ns.out1[0] = start
+            st.append((ns, [ns.out2] + outs))
+        elif k == "star":
+            start, outs = pop()
+            ns = _TState("split")
+            ns.out1[0] = start
+            patch(outs, ns)
+            st.append((ns, [ns.out2]))
+        elif k == "plus":
+            start, outs = pop()
+            ns = _TState("split")
+            ns.out1[0] = start
+            patch(outs, ns)
+            st.append((start, [ns.out2]))
+        elif k == "cat":
+            s2, o2 = pop()
+            s1, o1 = pop()
+            patch(o1, s2)
+            st.append((s1, o2))
+        elif k == "or":
+            s2, o2 = pop()
+            s1, o1 = pop()
+            ns = _TState("split")
+            ns.out1[0] = s1
+            ns.out2[0] = s2
+            st.append((ns, o1 + o2))
+        elif k == "char":
+            ns = _TState("const", c=t.c)
+            st.append((ns, [ns.out]))
+        elif k == "interval":
+            ns = _TState("interval", start=t.start, end=t.end)
+            st.append((ns, [ns.out]))
+        else:
+            raise ReUnsupported("MatchError: createNFA has no case for " + k)
+    start, outs = pop()
+    patch(outs, _MATCH)
+    return start
+
+
+def _closure(s):
+    """BaseState.outStates / liststates: terminal states reachable through Split states, each once, in visit order."""
+    seen, order, on_stack = set(), [], set()
+
+    def add(x):
+        if x is None or id(x) in seen:
+            return
+        if x.kind == "split":
+            # the reference adds only terminal states to the set; a split is re-walked whenever it is reached again, and a
+            # cycle made of splits only ((a*)* and friends) recurses forever there: StackOverflowError
+            if id(x) in on_stack:
+                raise ReUnsupported("StackOverflowError: epsilon cycle in the Thompson NFA")
+            on_stack.add(id(x))
+            add(x.out1[0])
+            add(x.out2[0])
+            on_stack.discard(id(x))
+        else:
+            seen.add(id(x))
+            order.append(x)
+    import sys
+    sys.setrecursionlimit(max(sys.getrecursionlimit(), 20000))
+    add(s)
+    return order
+
+
+def thompson_tables(post):
+    start = thompson_nfa(post)
+    # enumerate terminal states reachable from the start (BFS over closures), expand intervals into positions
+    term, queue = [], []
+    idx_of = {}
+
+    def see(s):
+        if id(s) not in idx_of and s.kind != "match":
+            idx_of[id(s)] = len(term)
+            term.append(s)
+            queue.append(s)
+
+    first_states = _closure(start)
+    if any(s.kind == "match" for s in first_states):
+        raise ReUnsupported("MatchError: StatePoint.expand has no case for MatchState (nullable regex)")
+    for s in first_states:
+        see(s)
+    nexts = {}
+    while queue:
+        s = queue.pop(0)
+        cl = _closure(s.out[0])
+        nexts[id(s)] = cl
+        for x in cl:
+            see(x)
+    # positions: Const -> 1, Interval -> one per char in [start, end)
+    pos_of, c, flags = {}, [], []
+    for s in term:
+        chars = [s.c] if s.kind == "const" else list(range(s.start, s.end))
+        pos_of[id(s)] = list(range(len(c), len(c) + len(chars)))
+        emits = 1 if any(x.kind == "match" for x in nexts[id(s)]) else 0
+        for ch in chars:
+            c.append(ch)
+            flags.append(emits)
+    follows = []
+    for s in term:
+        f = [p for x in nexts[id(s)] if x.kind != "match" for p in pos_of[id(x)]]
+        for _ in pos_of[id(s)]:
+            follows.append(list(f))
+    firsts = [p for s in first_states for p in pos_of[id(s)]]
+    return {"c": c, "last": flags, "num": [0] * len(c), "follows": follows, "firsts": firsts}
+
+
+def compile_thompson(s, line_only=False):
+    return thompson_tables(re2post(s, line_only))

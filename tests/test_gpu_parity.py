@@ -425,3 +425,41 @@ def test_fused_count_and_exchange_single_gpu(ref_dir):
         assert np.array_equal(b.to_host().astype(np.int64), oep - osp)
         b.close()
     g.close()
+
+
+# ----------------------------------------------------------------------------------------------- Thompson engine
+@pytest.mark.parametrize("cfg", [(fx.LAYOUT_WM, 4), (fx.LAYOUT_PLANES, 2), (fx.LAYOUT_PLANES, 1)], ids=_ids)
+def test_thompson_engine_goldens_and_parity(ref_dir, o1024, cfg):
+    g = _open(os.path.join(ref_dir, "test1024.cmp.bwt"), cfg)
+    # T/REParser.scala:292-307 on the GPU: Set("ec", "dc", "[2 Results] ac", "bc")
+    r = fx.ThompsonNFA("(((b|a)|d)|e)c").matchSA(g)
+    shown = {("[%d Results] " % (e - s) if e - s > 1 else "") + g.nextSubstr(s, l).decode() for l, s, e in r}
+    assert shown == {"ec", "dc", "[2 Results] ac", "bc"}
+    rxs = ["mab", "(b|a)c", "ab*", "ab*c", "a+b", "a(bc)*d", "(ab|cd)+e", "a.b", "a\\db", "x\\w+y", "a?b", "(a|b)*c", "a(b|c)?d", "q(u|a).z?k",
+           "a.?b", "((a|b)*aba*)*(a|b)(a|b)", "zz*", "a(b|c)(d|e)f?"]
+    got = g.regex_search_batch([fx.ThompsonNFA(rx) for rx in rxs])
+    for rx, res in zip(rxs, got):
+        assert res == o1024.regex_match_thompson(rx, max_expansions=30_000_000), rx
+    # both engines in one batch
+    mixed = [fx.ReTree("a(a|b|d|e)c"), fx.ThompsonNFA("a(a|b|d|e)c"), fx.ReTree("ab*"), fx.ThompsonNFA("ab*")]
+    res = g.regex_search_batch(mixed)
+    assert res[0] == o1024.regex_match("a(a|b|d|e)c") and res[1] == o1024.regex_match_thompson("a(a|b|d|e)c")
+    assert res[2] == o1024.regex_match("ab*") and res[3] == o1024.regex_match_thompson("ab*") and len(res[3]) > len(res[2])
+    g.close()
+    # T/REParser.scala:219-234 (toy SA)
+    bwt, eof, cnt = fo.build_bwt(b"mmabcacamabbbca"[::-1])
+    t = fx.GpuFMSearcher(bwt=bwt, eof=eof, counts=cnt, layout=cfg[0], lanes_per_query=cfg[1])
+    assert fx.ThompsonNFA("mab").matchSA(t) == [(3, 6, 8)]
+    assert fx.ThompsonNFA("(b|a)c").matchSA(t) == [(2, 10, 11), (2, 11, 13)]
+    t.close()
+
+
+def test_thompson_parity_words(words_base, words):
+    o, _ = words
+    g = _open(words_base + ".bwt", (fx.LAYOUT_PLANES, 2), big_endian=True)
+    rxs = ["x(a|b|d|e)c", "th(e|a)(n|t)\\w", "b(oo|ee)+k", "qu.k", "q\\d", "ab(cd)*ef", "ing\r\n", "z(a|e|i|o|u)(a|e|i|o|u)?z"]
+    got = g.regex_search_batch([fx.ThompsonNFA(rx) for rx in rxs])
+    for rx, res in zip(rxs, got):
+        assert res == o.regex_match_thompson(rx, max_expansions=50_000_000), rx
+    assert sum(e - s for _, s, e in got[0]) == 90
+    g.close()

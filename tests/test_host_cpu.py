@@ -143,3 +143,50 @@ def test_no_gpu_means_loud_failure_not_cpu_fallback(ref_dir):
     assert e.value.code == fx.FMX_E_CUDA and "no CPU fallback" in str(e.value)
     with pytest.raises(fx.FmxError):
         fx.build_bwt(b"abracadabra")
+
+
+# ---------------------------------------------------------------- Thompson engine: product compiler vs oracle tables
+T_REGEXES = ["mab", "(b|a)c", "(b|a|d|e)c", "ab*", "ab*c", "a+b", "a(bc)*d", "(ab|cd)+e", "a.b", "a\\db", "x\\w+y", "a?b", "(a|b)*c", "a(b|c)?d",
+             "ab(cd|ef)+gh", "q(u|a).z?k", ".*ab", "a.*b", "((a|b)*aba*)*(a|b)(a|b)", "a+((b|c)+|d)", "a\\.b", "(a)(b)", "a(bc)d"]
+
+
+@pytest.mark.parametrize("rx", T_REGEXES)
+def test_thompson_compiler_matches_oracle_tables(rx):
+    assert fx.ThompsonNFA(rx).tables() == retree.compile_thompson(rx)
+
+
+@pytest.mark.parametrize("rx", ["a*", "a?", "[ab]c", "a|", "", "(a*)*", "a**", "(", "*a", "a(b", "x[a-c]", "(a?)*b", "(abc)?+|a?|bcd"])
+def test_thompson_errors_match_oracle(rx):
+    try:
+        retree.compile_thompson(rx)
+        want = None
+    except retree.ReSyntaxError:
+        want = fx.ReSyntaxError
+    except retree.ReUnsupported:
+        want = fx.ReUnsupported
+    if want is None:
+        fx.ThompsonNFA(rx)
+    else:
+        with pytest.raises(want):
+            fx.ThompsonNFA(rx)
+
+
+def test_thompson_compiler_fuzz_against_oracle():
+    rng = random.Random(777)
+    seen = {"ok": 0, "bad": 0}
+    for _ in range(3000):
+        rx = _rand_regex(rng)
+        try:
+            want = retree.compile_thompson(rx)
+        except retree.ReSyntaxError:
+            want = fx.ReSyntaxError
+        except retree.ReUnsupported:
+            want = fx.ReUnsupported
+        if isinstance(want, dict):
+            seen["ok"] += 1
+            assert fx.ThompsonNFA(rx).tables() == want, rx
+        else:
+            seen["bad"] += 1
+            with pytest.raises(want):
+                fx.ThompsonNFA(rx)
+    assert seen["ok"] > 500 and seen["bad"] > 200

@@ -315,3 +315,36 @@ def test_locate_definition(words):
     for q in pos:                                     # file offset = (n-1) - q - m   (SURVEY §8a conventions)
         off = (n - 1) - int(q) - 5
         assert text[off:off + 5] == b"hello"
+
+
+# ---------------------------------------------------------------- G11 / G5: Thompson engine (REParser.matchSA)
+def test_g11_thompson_over_toy_sa():
+    """T/REParser.scala:219-234 — post2re("ma.b.") == re2post("mab"), post2re("ba|c.") == re2post("(b|a)c").  The strings are
+    printed by SAISBuilder.nextSubstr, the mirror image of NaiveFMSearcher's (see test_g1)."""
+    ix = _idx(b"mmabcacamabbbca"[::-1])
+    r = ix.regex_match_thompson("mab")
+    assert [(e - s, ix.nextSubstr(s, l)[::-1]) for l, s, e in r] == [(2, b"bam")]                   # "[2 Results] bam"
+    r = ix.regex_match_thompson("(b|a)c")
+    assert sorted((e - s, ix.nextSubstr(s, l)[::-1]) for l, s, e in r) == [(1, b"ca"), (2, b"cb")]    # List(ca, [2 Results] cb)
+
+
+def test_g5_thompson_over_disk_index(ix1024):
+    """T/REParser.scala:292-307 — the reference's only asserted regex-over-on-disk-index test:
+    post2re("ba|d|e|c.") over test1024 == Set("ec", "dc", "[2 Results] ac", "bc")."""
+    assert retree.re2poststr("(((b|a)|d)|e)c") == "ba|d|e|c·"                 # the test's postfix, as a regex
+    r = ix1024.regex_match_thompson("(((b|a)|d)|e)c")
+    assert r == ix1024.regex_match_thompson("(b|a|d|e)c")
+    shown = {("[%d Results] " % (e - s) if e - s > 1 else "") + ix1024.nextSubstr(s, l).decode() for l, s, e in r}
+    assert shown == {"ec", "dc", "[2 Results] ac", "bc"}
+    assert r == [(2, 83, 85), (2, 85, 86), (2, 86, 87), (2, 87, 88)]
+
+
+def test_thompson_differs_from_glushkov_where_the_reference_does(ix1024):
+    # a position that reaches the MatchState emits and is still expanded: ab* yields every prefix, Glushkov trims b* away
+    t = ix1024.regex_match_thompson("ab*")
+    g = ix1024.regex_match("ab*")
+    assert g == [(1,) + ix1024.search(b"a")] and set(g) <= set(t)
+    for rx in ["a*", "a?", "[ab]c", "a|", "", "(a*)*", "a**"]:
+        with pytest.raises(retree.ReUnsupported):
+            retree.compile_thompson(rx)
+    assert retree.compile_thompson("(a|b)c")["firsts"] == [0, 1]            # fine here, MatchError in ReTree (Q3)
