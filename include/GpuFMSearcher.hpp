@@ -122,10 +122,10 @@ inline std::string SAResult::toString() const {
     return "[no results]";
 }
 
-class ReTree {                          // ReTree(REParser.re2post(str, lineOnly))
+class ReTree {                          // ReTree(REParser.re2post(str, lineOnly)); engine 1 = REParser.createNFA(re2post(str))
 public:
-    explicit ReTree(const std::string &re, bool lineOnly = false) {
-        check(fmx_regex_compile(reinterpret_cast<const uint8_t *>(re.data()), (int64_t)re.size(), lineOnly ? 1 : 0, &h_));
+    explicit ReTree(const std::string &re, bool lineOnly = false, int engine = FMX_ENGINE_GLUSHKOV) {
+        check(fmx_regex_compile_engine(reinterpret_cast<const uint8_t *>(re.data()), (int64_t)re.size(), lineOnly ? 1 : 0, engine, &h_));
     }
     ~ReTree() { fmx_regex_free(h_); }
     ReTree(const ReTree &) = delete;
@@ -150,6 +150,11 @@ public:
 
 private:
     fmx_regex *h_ = nullptr;
+};
+
+// REParser.matchSA(REParser.createNFA(REParser.re2post(re)), sa)  — re2.scala:264-334, 568-693, uncapped
+struct ThompsonNFA : ReTree {
+    explicit ThompsonNFA(const std::string &re, bool lineOnly = false) : ReTree(re, lineOnly, FMX_ENGINE_THOMPSON) {}
 };
 
 }  // namespace fmx

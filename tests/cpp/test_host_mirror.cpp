@@ -58,6 +58,10 @@ int main(int argc, char **argv) {
     threw = false;
     try { fmx::GpuFMSearcher bad(dir + "/test1024.cmp.bwt", /*bigEndian=*/true); } catch (const std::runtime_error &e) { threw = std::string(e.what()).find("bad size") != std::string::npos; }
     REQUIRE(threw);
+    // "match SA FMindex" (REParser.scala:292-307) verbatim with the Thompson engine: post2re("ba|d|e|c.")
+    std::set<std::string> shown;
+    for (const auto &m : fmx::ThompsonNFA("(((b|a)|d)|e)c").matchSA(sa)) shown.insert(m.toString());
+    REQUIRE(shown == (std::set<std::string>{"ec", "dc", "[2 Results] ac", "bc"}));
     std::printf("cpp host mirror ok\n");
     return 0;
 }
