@@ -174,7 +174,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     DevIndex &d = ix->d;
     d.blocks = (const uint4 *)blocks; d.stride = (uint64_t)nblk; d.bwt = d_bwt; d.C = d_C; d.base = d_base; d.code = d_code;
     d.bm = nullptr;
-    d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isa = nullptr; d.text = nullptr;
+    d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isat = nullptr;
     d.mark = nullptr; d.samples = nullptr; d.n = (uint32_t)n; d.eof = (uint32_t)eof; d.layout = layout; d.levels = levels;
     for (int l = 0; l < 8; ++l) d.z[l] = z[l];
 
@@ -206,19 +206,25 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     CU(cudaStreamSynchronize(ix->stream));
     trim_pool(ix->device);
     cudaMemGetInfo(&fr, &to);
-    const bool want_text = (accel & FMX_ACCEL_TEXT) || (accel == FMX_ACCEL_AUTO && 9 * n + (2ll << 30) < (int64_t)fr && ix->index_bytes + 9 * n <= budget + (16ll << 30));
+    const bool want_text = (accel & FMX_ACCEL_TEXT) || (accel == FMX_ACCEL_AUTO && 25 * n + (2ll << 30) < (int64_t)fr && ix->index_bytes + 20 * n <= budget + (24ll << 30));
     const bool want_kmer = (accel & FMX_ACCEL_KMER) || accel == FMX_ACCEL_AUTO;
     if (want_text && n > 2) {
-        void *sa = nullptr, *isa = nullptr, *text = nullptr;
+        // sa stays; isa and the text are scratch that is folded into the 16-byte isat entries
+        void *sa = nullptr, *isat = nullptr;
+        uint32_t *isa = nullptr; uint8_t *text = nullptr;
         e = cudaMalloc(&sa, (size_t)n * 4); CU(e); ix->owned.push_back(sa);
-        e = cudaMalloc(&isa, (size_t)n * 4); CU(e); ix->owned.push_back(isa);
-        e = cudaMalloc(&text, (size_t)n + 16); CU(e); ix->owned.push_back(text);
+        e = cudaMalloc(&isat, (size_t)n * 16); CU(e); ix->owned.push_back(isat);
+        CU(cudaMallocAsync(&isa, (size_t)n * 4, ix->stream));
+        CU(cudaMallocAsync(&text, (size_t)n + 16, ix->stream));
         std::string err;
-        e = build_full_sa(d, layout, (uint32_t *)sa, (uint32_t *)isa, (uint8_t *)text, ix->stream, err);
+        e = build_full_sa(d, layout, (uint32_t *)sa, isa, text, ix->stream, err);
         if (e != cudaSuccess) return fail(err.empty() ? FMX_E_CUDA : FMX_E_FORMAT, "suffix array construction failed: %s", err.empty() ? cudaGetErrorString(e) : err.c_str());
+        CU(build_isat(isa, text, n, (uint4 *)isat, ix->stream));
+        CU(cudaFreeAsync(isa, ix->stream));
+        CU(cudaFreeAsync(text, ix->stream));
         CU(cudaStreamSynchronize(ix->stream));
-        d.sa = (const uint32_t *)sa; d.isa = (const uint32_t *)isa; d.text = (const uint8_t *)text;
-        ix->index_bytes += 9 * n;
+        d.sa = (const uint32_t *)sa; d.isat = (const uint4 *)isat;
+        ix->index_bytes += 20 * n;
     }
     if (want_kmer && sigma >= 1) {
         const int64_t table_budget = 256ll << 20;
@@ -237,8 +243,8 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     }
     // measured on B200 (profiles/r01_*): plain PLANES wants 4 lanes per 64-B block; WM, and PLANES once most fetches are the
     // scalar SA/ISA/table loads of the accelerators, want 2 (more queries in flight per SM)
-    if (!o.lanes_per_query) ix->cfg.lanes = (layout == FMX_LAYOUT_PLANES && d.text == nullptr) ? 4 : 2;
-    ix->accel_text = d.text != nullptr;
+    if (!o.lanes_per_query) ix->cfg.lanes = (layout == FMX_LAYOUT_PLANES && d.isat == nullptr) ? 4 : 2;
+    ix->accel_text = d.isat != nullptr;
     ix->kmer_k = d.kmer ? d.kmer_k : 0;
     CU(cudaStreamSynchronize(ix->stream));
     trim_pool(ix->device);                              // construction scratch goes back to the device

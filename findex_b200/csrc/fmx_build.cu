@@ -307,6 +307,20 @@ cudaError_t build_walk_blocks(const uint8_t *d_bwt, const uint32_t *d_mark_block
     return cudaGetLastError();
 }
 
+// isat[p] = { isa[p], T'[p..p+12) }  (bytes past the end read as 0)
+__global__ void build_isat_kernel(const uint32_t *__restrict__ isa, const uint8_t *__restrict__ text, int64_t n, uint4 *__restrict__ isat) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t w[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 12; ++k) if (p + k < n) w[k >> 2] |= (uint32_t)text[p + k] << (8 * (k & 3));
+    isat[p] = make_uint4(isa[p], w[0], w[1], w[2]);
+}
+cudaError_t build_isat(const uint32_t *d_isa, const uint8_t *d_text, int64_t n, uint4 *d_isat, cudaStream_t st) {
+    build_isat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_isa, d_text, n, d_isat);
+    return cudaGetLastError();
+}
+
 cudaError_t build_full_sa(const DevIndex &ix, int layout, uint32_t *d_sa, uint32_t *d_isa, uint8_t *d_text, cudaStream_t st, std::string &err) {
     Chains ch;
     CK(prepare_chains(ix, layout, ch, st, err));
@@ -341,7 +355,7 @@ cudaError_t build_kmer_table(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d
     CK(cudaMallocAsync(&d_ep, slice * 4, st));
     DevIndex plain = ix;                                // the table is filled by ordinary backward steps
     plain.kmer = nullptr;
-    plain.text = nullptr;
+    plain.isat = nullptr;
     for (uint64_t o = 0; o < total; o += slice) {
         const uint64_t cnt = total - o < slice ? total - o : slice;
         gen_kmer_patterns_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_sym, sigma, K, o, cnt, d_pat);

@@ -40,9 +40,10 @@ struct DevIndex {
     int32_t        kmer_k;
     uint32_t       kmer_sigma;
     const uint32_t *sa;         // full suffix array  sa[row]   (bwtFm2sa, util.scala:213-224)
-    const uint32_t *isa;        // its inverse        isa[pos]
-    const uint8_t  *text;       // T' bytes, text[n-1] = 0 ('$')
+    const uint4    *isat;       // per text position p: { isa[p], T'[p..p+12) } — inverse SA and the text behind it in one 16-B fetch
 };
+
+constexpr uint32_t kIsatText = 12;     // text bytes per isat entry
 
 struct SharedTables {
     uint32_t C[257];
@@ -231,7 +232,7 @@ __device__ __forceinline__ void backward_step(const DevIndex &ix, const SharedTa
 // active=false); groups leave the loop individually, the warp leaves when all are done.
 //   * k-mer table (optional): the first kmer_k steps are one lookup.
 //   * first step from (0,n) otherwise: (C[c], C[c+1]) without touching memory.
-//   * singleton shortcut (optional): once the interval is one row r and >= 3 bytes remain, the remaining bytes
+//   * singleton shortcut (optional): once the interval is one row r and 3..12 bytes remain, the remaining bytes
 //     are compared with T' in front of position sa[r]; the answer row is isa[sa[r]-remaining].  Identical to
 //     stepping: from a singleton, a step succeeds iff BWT[r] = T'[sa[r]-1] equals the byte, and lands on
 //     LF(r) = isa[sa[r]-1].  Patterns containing byte 0 take the ordinary steps (the '$' row wraps the text).
@@ -243,7 +244,7 @@ __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedT
     sp = 0;
     ep = active ? ix.n : 0u;
     int i = len - 1;
-    bool noshort = (ix.text == nullptr);
+    bool noshort = (ix.isat == nullptr);
     if (active && i >= 0) {
         bool done = false;
         if (ix.kmer != nullptr && len >= ix.kmer_k) {
@@ -274,25 +275,27 @@ __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedT
         const bool go = (i >= 0) && (sp < ep);
         if (go) {
             bool stepped = false;
-            if (!noshort && (ep - sp) == 1u && i >= 2) {
+            if (!noshort && (ep - sp) == 1u && i >= 2 && i < (int)kIsatText) {
+                // one 16-byte entry holds isa[p] and T'[p..p+12): the whole shortcut is sa[row] -> isat[sa[row]-rem]
                 const int rem = i + 1;
                 const uint32_t q = ix.sa[sp];
                 const bool fits = q >= (uint32_t)rem;
                 const uint32_t b0 = fits ? q - (uint32_t)rem : 0u;
-                const uint32_t r = ix.isa[b0];                       // issued early: overlaps the text compare
+                const uint4 e = ldg128(ix.isat + b0);
                 bool eq = fits, zero = false;
                 for (int k = lane; k < rem; k += G) {
                     const uint32_t pc = pat(k);
+                    const uint32_t w = (k >> 2) == 0 ? e.y : (k >> 2) == 1 ? e.z : e.w;
                     zero = zero || (pc == 0);
-                    eq = eq && ((uint32_t)ix.text[b0 + k] == pc);
+                    eq = eq && (((w >> (8 * (k & 3))) & 0xFFu) == pc);
                 }
                 if (G > 1) { eq = __all_sync(gmask, eq); zero = __any_sync(gmask, zero); }
                 if (zero) noshort = true;
                 else {
-                    if (eq) { sp = r; ep = r + 1; } else { sp = 0; ep = 0; }
+                    if (eq) { sp = e.x; ep = e.x + 1; } else { sp = 0; ep = 0; }
                     i = -1;
                     stepped = true;
-                    if (STATS) { touched += 3; steps += rem; }
+                    if (STATS) { touched += 2; steps += rem; }
                 }
             }
             if (!stepped) {

@@ -46,7 +46,7 @@ extern "C" {
 /* Bit-exact accelerators of the count path (fmx_opts.accel); they spend HBM capacity, never change results */
 #define FMX_ACCEL_AUTO      0
 #define FMX_ACCEL_KMER      1   /* table of (sp,ep) after the first k steps, k = max with sigma^k*8 B <= 256 MiB */
-#define FMX_ACCEL_TEXT      2   /* full SA + inverse SA + text (9n bytes): singleton intervals finish in 3 fetches; locate is 1 fetch */
+#define FMX_ACCEL_TEXT      2   /* full SA + {inverse SA, 12 text bytes} entries (20n bytes): singleton intervals finish in 2 fetches; locate is 1 fetch */
 #define FMX_ACCEL_NONE      8   /* plain backward search only                                                */
 
 typedef struct fmx_index fmx_index;     /* opaque; library-owned until fmx_close  */
