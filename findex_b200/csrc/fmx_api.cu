@@ -851,18 +851,29 @@ int fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64
     if (m == 0) return FMX_OK;
     if (m >= (1ll << 32)) return fail(FMX_E_LIMIT, "too many regexes in one batch");
     // concatenate the automata: global state ids, CSR follows, owning regex
-    std::vector<uint8_t> st_c, st_last; std::vector<uint32_t> st_regex, fol_off, fol; std::vector<FrontierItem> front;
-    fol_off.push_back(0);
+    size_t n_states = 0, n_fol = 0, n_first = 0;
     for (int64_t r = 0; r < m; ++r) {
         if (!rx[r]) return fail(FMX_E_ARG, "null regex at %lld", (long long)r);
-        const CompiledRegex &a = rx[r]->a;
-        const uint32_t base = (uint32_t)st_c.size();
-        for (size_t s = 0; s < a.c.size(); ++s) {
-            st_c.push_back(a.c[s]); st_last.push_back((uint8_t)(a.is_last[s] | (a.stop_on_emit ? 2 : 0))); st_regex.push_back((uint32_t)r);
-            for (int32_t k = a.follows_off[s]; k < a.follows_off[s + 1]; ++k) fol.push_back(base + (uint32_t)a.follows[k]);
-            fol_off.push_back((uint32_t)fol.size());
+        n_states += rx[r]->a.c.size(); n_fol += rx[r]->a.follows.size(); n_first += rx[r]->a.firsts.size();
+    }
+    if (n_states >= (1ull << 32) || n_fol >= (1ull << 32)) return fail(FMX_E_LIMIT, "regex batch has too many states; split the batch");
+    std::vector<uint8_t> st_c(n_states), st_last(n_states);
+    std::vector<uint32_t> st_regex(n_states), fol_off(n_states + 1), fol(n_fol);
+    std::vector<FrontierItem> front(n_first);
+    {
+        size_t so = 0, fo = 0, io = 0;
+        for (int64_t r = 0; r < m; ++r) {
+            const CompiledRegex &a = rx[r]->a;
+            const uint32_t base = (uint32_t)so, fbase = (uint32_t)fo;
+            const size_t ns = a.c.size();
+            const uint8_t stop = a.stop_on_emit ? 2 : 0;
+            std::memcpy(st_c.data() + so, a.c.data(), ns);
+            for (size_t s = 0; s < ns; ++s) { st_last[so + s] = (uint8_t)(a.is_last[s] | stop); st_regex[so + s] = (uint32_t)r; fol_off[so + s] = fbase + (uint32_t)a.follows_off[s]; }
+            for (size_t k = 0; k < a.follows.size(); ++k) fol[fo + k] = base + (uint32_t)a.follows[k];
+            for (int32_t f : a.firsts) front[io++] = FrontierItem{base + (uint32_t)f, 0u, 0u, (uint32_t)ix->n};   // StatePoint(0,0,sa.n,_)
+            so += ns; fo += a.follows.size();
         }
-        for (int32_t f : a.firsts) front.push_back(FrontierItem{base + (uint32_t)f, 0u, 0u, (uint32_t)ix->n});   // StatePoint(0,0,sa.n,_)
+        fol_off[n_states] = (uint32_t)fo;
     }
     if (front.empty()) return FMX_OK;
     std::lock_guard<std::mutex> lk(ix->mu);

@@ -463,3 +463,83 @@ def test_thompson_parity_words(words_base, words):
         assert res == o.regex_match_thompson(rx, max_expansions=50_000_000), rx
     assert sum(e - s for _, s, e in got[0]) == 90
     g.close()
+
+
+# ----------------------------------------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("accel", [fx.ACCEL_AUTO, fx.ACCEL_NONE], ids=["auto", "none"])
+@pytest.mark.parametrize("cfg", [(fx.LAYOUT_WM, 2), (fx.LAYOUT_PLANES, 4)], ids=_ids)
+@pytest.mark.parametrize("text", [b"", b"a", b"aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaa", b"ab" * 300, bytes(range(1, 256)) * 3,
+                                  b"\xff\xfe\xff\xfe\x01\x01\x02", b"abracadabra"], ids=["empty", "one", "run", "period2", "all255", "highbytes", "abra"])
+def test_degenerate_texts(text, cfg, accel):
+    """Empty text (n = 1), single symbol, periodic text, every byte value, bytes >= 0x80 (Q8: reference-undefined through search's
+    signed Byte, defined through getPrevRange; unsigned here): every operator vs the oracle, incl. locate and both regex engines."""
+    bwt, eof, cnt = fo.build_bwt(fo.file_to_text_rev(text))
+    o = fo.OracleIndex.from_bwt(bwt, eof, cnt)
+    g = fx.GpuFMSearcher(bwt=bwt, eof=eof, counts=cnt, layout=cfg[0], lanes_per_query=cfg[1], accel=accel, sa_sample_rate=4)
+    n = o.n
+    assert g.n == n and g.eof == eof
+    alphabet = sorted(set(text)) + [0, 1, 7, 255]
+    rng = np.random.default_rng(len(text))
+    pats = [b"", b"\0", bytes([alphabet[0]]) * 40] + [bytes(rng.choice(alphabet, int(rng.integers(0, 9))).astype(np.uint8)) for _ in range(300)]
+    tp = bytes(fo.file_to_text_rev(text))
+    pats += [tp[i:i + k] for i in range(0, max(len(tp) - 1, 1), 7) for k in (1, 3, 14) if tp[i:i + k]]
+    sp, ep = g.count_batch(pats)
+    for p, a, b in zip(pats, sp, ep):
+        r = o.search(p)
+        assert (int(a), int(b)) == (r if r else (0, 0)), p
+    rows = np.arange(n, dtype=np.int64)
+    assert g.get_prev_i_batch(rows).tolist() == [o.getPrevI(int(r)) for r in rows]
+    assert g.get_next_i_batch(rows).tolist() == [o.getNextI(int(r)) for r in rows]
+    for c in alphabet:
+        keys = np.arange(-1, n, dtype=np.int64)
+        assert g.occ_batch(np.full(len(keys), c, np.uint8), keys).tolist() == [o.occ(c, int(k)) for k in keys]
+    off, pos = g.locate_batch([0], [n])
+    assert pos.tolist() == sorted(o.sa().tolist())
+    if len(text) >= 2:
+        a, b = text[0], text[1]
+        rx = bytes([a]) + b"." if a not in b"()[]|*+?.\\-" else b"x."
+        assert fx.ReTree(rx).matchSA(g) == o.regex_match(rx)
+        assert fx.ThompsonNFA(rx).matchSA(g) == o.regex_match_thompson(rx)
+    g.close()
+    o.close()
+
+
+def test_empty_batches_and_argument_errors(ref_dir):
+    g = _open(os.path.join(ref_dir, "test1024.cmp.bwt"), (fx.LAYOUT_PLANES, 2), sa_sample_rate=8)
+    sp, ep = g.count_batch([])
+    assert len(sp) == 0 and len(ep) == 0
+    sp, ep = g.count_fixed(np.zeros((0, 16), np.uint8))
+    assert len(sp) == 0
+    sp, ep = g.count_fixed(np.zeros((5, 0), np.uint8))                  # five empty patterns -> (0, n) each
+    assert sp.tolist() == [0] * 5 and ep.tolist() == [g.n] * 5
+    off, pos = g.locate_batch([], [])
+    assert off.tolist() == [0] and len(pos) == 0
+    off, pos = g.locate_batch([5, 9], [5, 9])                           # empty intervals
+    assert off.tolist() == [0, 0, 0]
+    assert g.regex_search_batch([]) == []
+    assert g.getIntervalPrevRange(0, g.n, ord("z"), ord("a")) == []     # cstart > cend: the reference's loop does not run
+    for bad in ([-1], [g.n]):
+        with pytest.raises(fx.FmxError) as e:
+            g.get_prev_i_batch(bad)
+        assert e.value.code == fx.FMX_E_ARG
+    with pytest.raises(fx.FmxError) as e:
+        g.prev_range_batch([0], [g.n + 1], [97])
+    assert e.value.code == fx.FMX_E_ARG
+    with pytest.raises(fx.FmxError) as e:
+        g.locate_batch([10], [5])
+    assert e.value.code == fx.FMX_E_ARG
+    g2 = _open(os.path.join(ref_dir, "test1024.cmp.bwt"), (fx.LAYOUT_WM, 2), accel=fx.ACCEL_NONE)
+    with pytest.raises(fx.FmxError) as e:                               # no samples, no full SA
+        g2.locate_batch([0], [3])
+    assert e.value.code == fx.FMX_E_ARG
+    g2.close()
+    # capacity protocol of locate: too small -> FMX_E_CAPACITY and the required total
+    import ctypes as C
+    sp = np.array([0], np.int64)
+    ep = np.array([100], np.int64)
+    off = np.zeros(2, np.int64)
+    pos = np.zeros(10, np.int64)
+    rc = fx.lib().fmx_locate_batch(g.h, sp.ctypes.data_as(C.c_void_p), ep.ctypes.data_as(C.c_void_p), 1, 10, off.ctypes.data_as(C.c_void_p),
+                                   pos.ctypes.data_as(C.c_void_p))
+    assert rc == fx.FMX_E_CAPACITY and off[1] == 100
+    g.close()
