@@ -125,8 +125,8 @@ cudaError_t build_wm(const uint8_t *d_bwt, int64_t n, uint32_t eof, const uint8_
 cudaError_t build_planes(const uint8_t *d_bwt, int64_t n, uint32_t eof, const uint8_t *d_sym, int sigma, uint32_t *d_blocks,
                          int64_t nblk, cudaStream_t st) {
     constexpr int TB = 8;
-    pack_planes_kernel<TB><<<(unsigned)((nblk + TB - 1) / TB), 256, 0, st>>>(d_bwt, n, eof, d_sym, sigma, d_blocks, nblk);
-    CK(finish_headers(d_blocks, nblk, sigma, st));
+    if (sigma > 0) pack_planes_kernel<TB><<<(unsigned)((nblk + TB - 1) / TB), 256, 0, st>>>(d_bwt, n, eof, d_sym, sigma, d_blocks, nblk);
+    CK(finish_headers(d_blocks, nblk, sigma > 0 ? sigma : 1, st));       // an empty text still owns one (all-zero) plane
     return cudaGetLastError();
 }
 
