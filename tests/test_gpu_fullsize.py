@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from findex_b200 import fmindex as fx
+from findex_b200 import synth
 from oracle import fm_oracle as fo
 
 pytestmark = pytest.mark.gpu
@@ -22,15 +23,7 @@ def english(words_base, tmp_path_factory):
     tp = np.zeros(o.n, np.uint8)
     tp[(sa.astype(np.int64) - 1) % o.n] = o.bwt()
     vocab = [w for w in bytes(tp[:-1][::-1]).split(b"\r\n") if w]
-    rng = np.random.default_rng(4)
-    perm = rng.permutation(len(vocab))
-    p = 1.0 / np.arange(1, len(vocab) + 1)
-    r = np.minimum(np.searchsorted(np.cumsum(p / p.sum()), rng.random(NBYTES // 8)), len(vocab) - 1)
-    parts = []
-    for i, k in enumerate(r):
-        parts.append(vocab[perm[k]])
-        parts.append(b"\n" if i % 12 == 11 else b" ")
-    text = b"".join(parts)[:NBYTES]
+    text = synth.english_like(vocab, NBYTES, 4).tobytes()
     base = str(tmp_path_factory.mktemp("full") / "english")
     fx.build_index_files(text, base, bigEndian=True)
     return np.frombuffer(text, np.uint8), base, fo.OracleIndex.load(base)
@@ -51,9 +44,10 @@ def test_cfg3_cfg4_scaled(english, layout, accel, rate):
     occ = ep - sp
     small = np.flatnonzero(occ <= 2000)[:60_000]
     off, pos = g.locate_batch(sp[small], ep[small])
-    sa = o.sa().astype(np.int64)
-    for j in range(0, len(small), 97):
-        assert np.array_equal(pos[off[j]:off[j + 1]], np.sort(sa[sp[small[j]]:ep[small[j]]]))
+    if o.n <= 200_000_000:                                # the oracle's sa is a sequential n-step walk: skipped at full size,
+        sa = o.sa().astype(np.int64)                       # where the text property below is the (complete) check
+        for j in range(0, len(small), 97):
+            assert np.array_equal(pos[off[j]:off[j + 1]], np.sort(sa[sp[small[j]]:ep[small[j]]]))
     n1 = g.n
     for j in range(0, len(small), 11):
         q = pos[off[j]:off[j + 1]]

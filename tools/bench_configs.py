@@ -22,6 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from findex_b200 import build as fbuild  # noqa: E402
 from findex_b200 import fmindex as fx  # noqa: E402
+from findex_b200 import synth  # noqa: E402
 
 
 def vocabulary():
@@ -39,33 +40,7 @@ def vocabulary():
 
 
 def english_like(n_bytes, seed=4):
-    vocab = vocabulary()
-    rng = np.random.default_rng(seed)
-    perm = rng.permutation(len(vocab))
-    lens = np.array([len(vocab[i]) for i in perm], np.int64) + 1           # + separator
-    flat = np.frombuffer(b"".join(vocab[i] + b" " for i in perm), np.uint8)
-    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
-    p = 1.0 / np.arange(1, len(vocab) + 1)
-    cdf = np.cumsum(p / p.sum())
-    out = np.empty(n_bytes, np.uint8)
-    pos, widx = 0, 0
-    while pos < n_bytes:
-        k = 4_000_000
-        r = np.minimum(np.searchsorted(cdf, rng.random(k)), len(vocab) - 1)
-        wl = lens[r]
-        ends = np.cumsum(wl)
-        total = int(ends[-1])
-        src = np.repeat(starts[r] - (ends - wl), wl) + np.arange(total)
-        chunk = flat[src]
-        sep = ends - 1                                                        # separator positions: '\n' every 12 words
-        nl = sep[(np.arange(widx, widx + k) % 12) == 11]
-        chunk = chunk.copy()
-        chunk[nl] = 10
-        take = min(total, n_bytes - pos)
-        out[pos:pos + take] = chunk[:take]
-        pos += take
-        widx += k
-    return out
+    return synth.english_like(vocabulary(), n_bytes, seed)
 
 
 def emit(fh, **kw):
@@ -74,32 +49,7 @@ def emit(fh, **kw):
     fh.flush()
 
 
-def regex_templates(text, rng, m):
-    def lit(k):
-        s = int(rng.integers(0, len(text) - k))
-        return bytes(text[s:s + k])
-
-    def esc(b):
-        return b"".join((b"\\" + bytes([c])) if c in b"()[]|*+?.\\-" else bytes([c]) for c in b)
-    out = []
-    while len(out) < m:
-        t = len(out) % 5
-        if t == 0:
-            a, b = sorted(rng.integers(97, 123, 2).tolist())
-            if a == b:
-                b = min(a + 1, 122)
-                a = b - 1
-            out.append(esc(lit(3)) + b"[" + bytes([a]) + b"-" + bytes([b]) + b"]" + esc(lit(2)))
-        elif t == 1:
-            out.append(esc(lit(3)) + b"(" + esc(lit(2)) + b"|" + esc(lit(2)) + b"|" + esc(lit(3)) + b")" + esc(lit(1)))
-        elif t == 2:                                                          # L2 x? y{1,3} L2 desugared: y y? y?
-            x, y = esc(lit(1)), esc(lit(1))
-            out.append(esc(lit(2)) + x + b"?" + y + y + b"?" + y + b"?" + esc(lit(2)))
-        elif t == 3:
-            out.append(esc(lit(3)) + b"\\d" + esc(lit(2)))
-        else:
-            out.append(esc(lit(4)) + b"." + esc(lit(2)))
-    return out
+regex_templates = synth.regex_templates
 
 
 def main():
