@@ -376,6 +376,8 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e, clocks_e2e = timed_region(e2e_step, "e2e")
     assert np.array_equal(h_sp.array, np.where(cnt > 0, sp, 0)) and np.array_equal(h_ep.array, np.where(cnt > 0, ep, 0)), "host API result differs from device API"
 
+    regex = None if args.regexes <= 0 else regex_leg(args, g, text, world, rank, dev)
+
     value = world * m * args.steps / (ms_total * 1e-3)
     e2e = world * m * args.steps / (ms_e2e * 1e-3)
     peak, peak_src = measured_peaks()
@@ -404,8 +406,10 @@ def run_ours(args, rank, world, local_rank):
                         "r_rand_gbs": r_rand, "frac_of_r_rand": achieved / r_rand,
                         "note": "achieved = distinct 64-B rank blocks the batch touches x 64 B / kernel time; r_rand = live K4 random 64-B gather "
                                 "bandwidth over the same index (the random-sector HBM roofline of north_star)"}}
+    if regex is not None:
+        out["regex"] = regex["report"]
     if world == 1 and rank == 0 and not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(args, base, pats, sp, ep, cnt)
+        out["cpu_baseline"] = cpu_baseline(args, base, pats, sp, ep, cnt, regex)
     if rank == 0:
         print(json.dumps(out), file=OUT, flush=True)
     if p2p:
@@ -421,7 +425,60 @@ def run_ours(args, rank, world, local_rank):
     g.close()
 
 
-def cpu_baseline(args, base, pats, sp, ep, cnt):
+def regex_leg(args, g, text, world, rank, dev):
+    """Second half of BASELINE.json's metric ("regex queries/s"): `--regexes` template regexes (cfg 4: classes, alternation,
+    desugared bounded repeats, \\d, '.') per GPU over the same index, searched through fmx_regex_search_batch with host
+    buffers.  Compilation (host, once) is outside the timed region; the search call is timed end to end (wall clock, max over ranks)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from findex_b200 import fmindex as fx, synth
+    rxs = synth.regex_templates(text, np.random.default_rng([6, rank]), args.regexes)
+    t0 = time.time()
+    trees, kept = [], []
+    for r in rxs:
+        try:
+            trees.append(fx.ReTree(r))
+            kept.append(r)
+        except fx.FmxError:
+            pass
+    compile_s = time.time() - t0
+    mr = len(trees)
+    arr = (C.c_void_p * mr)(*[t.h for t in trees])
+    cap = 1 << 22
+    off = np.zeros(mr + 1, np.int64)
+    ln_, sp_, ep_ = np.zeros(cap, np.int32), np.zeros(cap, np.int64), np.zeros(cap, np.int64)
+
+    def call():
+        rc = fx.lib().fmx_regex_search_batch(g.h, arr, mr, cap, off.ctypes.data_as(C.c_void_p), ln_.ctypes.data_as(C.c_void_p),
+                                             sp_.ctypes.data_as(C.c_void_p), ep_.ctypes.data_as(C.c_void_p))
+        assert rc == 0, fx.lib().fmx_last_error()
+    steps = max(3, min(args.steps, 20))
+    for _ in range(3):
+        call()
+    if world > 1:
+        dist.barrier()
+    t0 = time.time()
+    kms = []
+    for _ in range(steps):
+        call()
+        kms.append(g.last_kernel_ms())
+    wall = time.time() - t0
+    tt = torch.tensor([wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    wall = float(tt.item())
+    total = int(off[mr])
+    res = [(kept[i], sorted(zip(ln_[off[i]:off[i + 1]].tolist(), sp_[off[i]:off[i + 1]].tolist(), ep_[off[i]:off[i + 1]].tolist())))
+           for i in np.random.default_rng(9).choice(mr, min(200, mr), replace=False)]
+    return {"sample": res,
+            "report": {"value": world * mr * steps / wall, "unit": "regexes/s", "what": "fmx_regex_search_batch end to end (host buffers), Glushkov engine, "
+                       "caps off; device time alone in device_value", "device_value": world * mr / (float(np.mean(kms)) * 1e-3), "regexes_per_gpu": mr,
+                       "rejected_by_compiler": len(rxs) - mr, "steps": steps, "ms_per_step": wall / steps * 1e3, "kernel_ms_per_step": float(np.mean(kms)),
+                       "level_launches_per_step": int(g.last_kernel_launches()), "result_triples": total, "compile_s_once": compile_s}}
+
+
+def cpu_baseline(args, base, pats, sp, ep, cnt, regex=None):
     """The oracle (C restatement of the reference algorithm) on the box's host cores, on a bounded sample of the same batch;
     doubles as the full-size parity check of that sample."""
     from oracle import fm_oracle as fo
@@ -444,10 +501,18 @@ def cpu_baseline(args, base, pats, sp, ep, cnt):
     want_ep = np.where(cnt[:sample] > 0, ep[:sample], 0)
     parity = bool(np.array_equal(osp, want_sp) and np.array_equal(oep, want_ep))
     assert parity, "GPU (sp,ep) differ from the oracle on the CPU-baseline sample"
+    extra = {}
+    if regex is not None:                                 # the oracle's uncapped ReTree._matchSA on a sample of the regex batch (1 thread)
+        t1 = time.time()
+        ok = all(ix.regex_match(rx, max_expansions=50_000_000) == want for rx, want in regex["sample"])
+        dtr = time.time() - t1
+        assert ok, "GPU regex results differ from the oracle on the sample"
+        extra = {"regex": {"value": len(regex["sample"]) / dtr, "unit": "regexes/s", "cores": 1, "sample": "%d regexes of the batch" % len(regex["sample"]),
+                           "parity_on_sample": bool(ok)}}
     ix.close()
-    return {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "first %d of the %d-query batch, %d threads, %.1f s" % (sample, len(pats), cores, dt),
-            "parity_on_sample": parity, "note": "JVM unavailable - C restatement of the reference algorithm (binary search in .fm)"}
+    return dict({"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                 "sample": "first %d of the %d-query batch, %d threads, %.1f s" % (sample, len(pats), cores, dt),
+                 "parity_on_sample": parity, "note": "JVM unavailable - C restatement of the reference algorithm (binary search in .fm)"}, **extra)
 
 
 def protect_stdout():
@@ -497,6 +562,7 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory stores (default) or NCCL all-gather")
     ap.add_argument("--gather-chunks", type=int, default=1)
     ap.add_argument("--diag", default="none", choices=["none", "nocomm", "nosub", "nogather"], help="diagnostics only: drop parts of the exchange")
+    ap.add_argument("--regexes", type=int, default=100_000, help="regexes per GPU for the secondary regex measurement (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

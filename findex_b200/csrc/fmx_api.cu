@@ -3,7 +3,9 @@
 // compute call runs on the index's CUDA stream and fails with FMX_E_CUDA when no device is usable —
 // there is no CPU path in this library.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -278,6 +280,20 @@ int new_index(const fmx_opts *opts, fmx_index **out, fmx_opts *resolved) {
     *resolved = o;
     return FMX_OK;
 }
+
+// FMX_TRACE=1: host-side phase times of the batch calls on stderr (where does an end-to-end call spend its time)
+struct Phases {
+    bool on = std::getenv("FMX_TRACE") != nullptr;
+    const char *what;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit Phases(const char *w) : what(w) {}
+    void mark(const char *phase) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[fmx trace] %s: %-22s %8.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 struct DeviceGuard {
     int prev = -1;
@@ -850,6 +866,7 @@ int fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64
     for (int64_t i = 0; i <= m; ++i) out_off[i] = 0;
     if (m == 0) return FMX_OK;
     if (m >= (1ll << 32)) return fail(FMX_E_LIMIT, "too many regexes in one batch");
+    Phases ph("regex_search_batch");
     // concatenate the automata: global state ids, CSR follows, owning regex
     size_t n_states = 0, n_fol = 0, n_first = 0;
     for (int64_t r = 0; r < m; ++r) {
@@ -875,6 +892,7 @@ int fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64
         }
         fol_off[n_states] = (uint32_t)fo;
     }
+    ph.mark("concatenate tables");
     if (front.empty()) return FMX_OK;
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
@@ -903,6 +921,8 @@ int fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64
     CU(d_res.alloc(cap_res * sizeof(RegexResult))); CU(d_cnt.alloc(16));
     CU(cudaMemcpyAsync(cur, front.data(), front.size() * sizeof(FrontierItem), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(d_cnt.p, 0, 16, st));
+    CU(cudaStreamSynchronize(st));
+    ph.mark("upload tables/alloc");
     Timed t(ix);
     int64_t n_in = (int64_t)front.size(), launches = 0, level = 0;
     unsigned long long h[2] = {0, 0}, res_before = 0;
@@ -930,6 +950,7 @@ int fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64
         std::swap(cap_cur, cap_nxt);
     }
     const int64_t total = (int64_t)h[1];
+    ph.mark("level loop");
     ix->last_launches = launches; ix->total_launches += launches;
     if (total > cap_res) {                                            // counted everything, could not store it
         t.stop();
@@ -943,11 +964,13 @@ int fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64
     if (total) CU(cudaMemcpyAsync(hr.data(), d_res.p, total * sizeof(RegexResult), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     t.collect();
+    ph.mark("sort + copy out");
     for (const RegexResult &r : hr) out_off[r.regex + 1]++;
     for (int64_t i = 0; i < m; ++i) out_off[i + 1] += out_off[i];
     if (total > cap_total) return fail(FMX_E_CAPACITY, "regex search needs %lld result slots, capacity %lld", (long long)total, (long long)cap_total);
     if (total && (!len || !sp || !ep)) return fail(FMX_E_ARG, "null output");
     for (int64_t i = 0; i < total; ++i) { len[i] = (int32_t)hr[(size_t)i].len; sp[i] = hr[(size_t)i].sp; ep[i] = hr[(size_t)i].ep; }
+    ph.mark("marshal results");
     return FMX_OK;
 }
 
