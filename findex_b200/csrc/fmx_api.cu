@@ -859,15 +859,28 @@ int fmx_regex_tables(const fmx_regex *rx, int32_t *n_states, int32_t *n_follows,
     return FMX_OK;
 }
 
-int fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64_t cap_total, int64_t *out_off, int32_t *len,
-                           int64_t *sp, int64_t *ep) {
+// A regex set = the automata of a batch concatenated (global state ids, CSR follows, owning regex) and resident on the device:
+// compile once, search many times — the batched form of `val t = ReTree(post); t.matchSA(sa)`.
+struct fmx_regex_set {
+    int device = 0;
+    int64_t m = 0;
+    size_t n_states = 0, n_fol = 0, n_first = 0;
+    void *d_c = nullptr, *d_last = nullptr, *d_rx = nullptr, *d_fo = nullptr, *d_f = nullptr, *d_first = nullptr;
+};
+
+void fmx_regex_set_free(fmx_regex_set *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaFree(s->d_c); cudaFree(s->d_last); cudaFree(s->d_rx); cudaFree(s->d_fo); cudaFree(s->d_f); cudaFree(s->d_first);
+    delete s;
+}
+
+int fmx_regex_set_create(fmx_index *ix, fmx_regex *const *rx, int64_t m, fmx_regex_set **out) {
     CHECK_IX(ix);
-    if (m < 0 || !out_off || (m && !rx)) return fail(FMX_E_ARG, "bad argument");
-    for (int64_t i = 0; i <= m; ++i) out_off[i] = 0;
-    if (m == 0) return FMX_OK;
+    if (m < 0 || !out || (m && !rx)) return fail(FMX_E_ARG, "bad argument");
+    *out = nullptr;
     if (m >= (1ll << 32)) return fail(FMX_E_LIMIT, "too many regexes in one batch");
-    Phases ph("regex_search_batch");
-    // concatenate the automata: global state ids, CSR follows, owning regex
+    Phases ph("regex_set_create");
     size_t n_states = 0, n_fol = 0, n_first = 0;
     for (int64_t r = 0; r < m; ++r) {
         if (!rx[r]) return fail(FMX_E_ARG, "null regex at %lld", (long long)r);
@@ -875,8 +888,7 @@ int fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64
     }
     if (n_states >= (1ull << 32) || n_fol >= (1ull << 32)) return fail(FMX_E_LIMIT, "regex batch has too many states; split the batch");
     std::vector<uint8_t> st_c(n_states), st_last(n_states);
-    std::vector<uint32_t> st_regex(n_states), fol_off(n_states + 1), fol(n_fol);
-    std::vector<FrontierItem> front(n_first);
+    std::vector<uint32_t> st_regex(n_states), fol_off(n_states + 1), fol(n_fol), first(n_first);
     {
         size_t so = 0, fo = 0, io = 0;
         for (int64_t r = 0; r < m; ++r) {
@@ -887,44 +899,62 @@ int fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64
             std::memcpy(st_c.data() + so, a.c.data(), ns);
             for (size_t s = 0; s < ns; ++s) { st_last[so + s] = (uint8_t)(a.is_last[s] | stop); st_regex[so + s] = (uint32_t)r; fol_off[so + s] = fbase + (uint32_t)a.follows_off[s]; }
             for (size_t k = 0; k < a.follows.size(); ++k) fol[fo + k] = base + (uint32_t)a.follows[k];
-            for (int32_t f : a.firsts) front[io++] = FrontierItem{base + (uint32_t)f, 0u, 0u, (uint32_t)ix->n};   // StatePoint(0,0,sa.n,_)
+            for (int32_t f : a.firsts) first[io++] = base + (uint32_t)f;
             so += ns; fo += a.follows.size();
         }
         fol_off[n_states] = (uint32_t)fo;
     }
     ph.mark("concatenate tables");
-    if (front.empty()) return FMX_OK;
+    DeviceGuard g(ix->device);
+    fmx_regex_set *s = new fmx_regex_set();
+    s->device = ix->device; s->m = m; s->n_states = n_states; s->n_fol = n_fol; s->n_first = n_first;
+    auto up = [&](void **d, const void *h, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(d, bytes ? bytes : 4);
+        if (e == cudaSuccess && bytes) e = cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+        return e;
+    };
+    cudaError_t e = up(&s->d_c, st_c.data(), n_states);
+    if (e == cudaSuccess) e = up(&s->d_last, st_last.data(), n_states);
+    if (e == cudaSuccess) e = up(&s->d_rx, st_regex.data(), n_states * 4);
+    if (e == cudaSuccess) e = up(&s->d_fo, fol_off.data(), (n_states + 1) * 4);
+    if (e == cudaSuccess) e = up(&s->d_f, fol.data(), n_fol * 4);
+    if (e == cudaSuccess) e = up(&s->d_first, first.data(), n_first * 4);
+    if (e != cudaSuccess) { fmx_regex_set_free(s); return fail(FMX_E_CUDA, "regex set upload failed: %s", cudaGetErrorString(e)); }
+    ph.mark("upload tables");
+    *out = s;
+    return FMX_OK;
+}
+
+int fmx_regex_set_search(fmx_index *ix, fmx_regex_set *set, int64_t cap_total, int64_t *out_off, int32_t *len, int64_t *sp, int64_t *ep) {
+    CHECK_IX(ix);
+    if (!set || !out_off) return fail(FMX_E_ARG, "bad argument");
+    if (set->device != ix->device) return fail(FMX_E_ARG, "regex set lives on device %d, index on device %d", set->device, ix->device);
+    const int64_t m = set->m;
+    for (int64_t i = 0; i <= m; ++i) out_off[i] = 0;
+    if (m == 0 || set->n_first == 0) return FMX_OK;
+    Phases ph("regex_set_search");
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t st = ix->stream;
-    DBuf d_c(st), d_last(st), d_rx(st), d_fo(st), d_f(st), d_res(st), d_tmp(st), d_cnt(st);
-    CU(d_c.alloc(st_c.size())); CU(d_last.alloc(st_last.size())); CU(d_rx.alloc(st_regex.size() * 4));
-    CU(d_fo.alloc(fol_off.size() * 4)); CU(d_f.alloc(fol.size() * 4 + 4));
-    CU(cudaMemcpyAsync(d_c.p, st_c.data(), st_c.size(), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_last.p, st_last.data(), st_last.size(), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_rx.p, st_regex.data(), st_regex.size() * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_fo.p, fol_off.data(), fol_off.size() * 4, cudaMemcpyHostToDevice, st));
-    if (!fol.empty()) CU(cudaMemcpyAsync(d_f.p, fol.data(), fol.size() * 4, cudaMemcpyHostToDevice, st));
-    RegexTables rt{d_c.as<uint8_t>(), d_last.as<uint8_t>(), d_rx.as<uint32_t>(), d_fo.as<uint32_t>(), d_f.as<uint32_t>()};
+    DBuf d_res(st), d_tmp(st), d_cnt(st);
+    RegexTables rt{(const uint8_t *)set->d_c, (const uint8_t *)set->d_last, (const uint32_t *)set->d_rx, (const uint32_t *)set->d_fo, (const uint32_t *)set->d_f};
 
     size_t fr = 0, to = 0;
     cudaMemGetInfo(&fr, &to);
     // frontier buffers start small and grow on demand (a level that overflows is replayed), bounded by an eighth of
     // the free device memory each
-    const int64_t max_front = std::max<int64_t>(std::min<int64_t>((int64_t)(fr / 8 / sizeof(FrontierItem)), 1ll << 28), (int64_t)front.size());
-    int64_t cap_cur = std::min<int64_t>(max_front, std::max<int64_t>((int64_t)front.size(), 1 << 16));
-    int64_t cap_nxt = std::min<int64_t>(max_front, std::max<int64_t>((int64_t)front.size() * 4, 1 << 20));
+    const int64_t n_first = (int64_t)set->n_first;
+    const int64_t max_front = std::max<int64_t>(std::min<int64_t>((int64_t)(fr / 8 / sizeof(FrontierItem)), 1ll << 28), n_first);
+    int64_t cap_cur = std::min<int64_t>(max_front, std::max<int64_t>(n_first, 1 << 16));
+    int64_t cap_nxt = std::min<int64_t>(max_front, std::max<int64_t>(n_first * 4, 1 << 20));
     int64_t cap_res = std::max<int64_t>(cap_total, 1 << 16);
     void *cur = nullptr, *nxt = nullptr;
     CU(cudaMallocAsync(&cur, cap_cur * sizeof(FrontierItem), st)); CU(cudaMallocAsync(&nxt, cap_nxt * sizeof(FrontierItem), st));
     struct Guard { void **a, **b; cudaStream_t s; ~Guard() { if (*a) cudaFreeAsync(*a, s); if (*b) cudaFreeAsync(*b, s); } } guard{&cur, &nxt, st};
     CU(d_res.alloc(cap_res * sizeof(RegexResult))); CU(d_cnt.alloc(16));
-    CU(cudaMemcpyAsync(cur, front.data(), front.size() * sizeof(FrontierItem), cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(d_cnt.p, 0, 16, st));
-    CU(cudaStreamSynchronize(st));
-    ph.mark("upload tables/alloc");
     Timed t(ix);
-    int64_t n_in = (int64_t)front.size(), launches = 0, level = 0;
+    CU(launch_init_frontier((const uint32_t *)set->d_first, n_first, (uint32_t)ix->n, (FrontierItem *)cur, st));   // StatePoint(0,0,sa.n,_)
+    int64_t n_in = n_first, launches = 1, level = 0;
     unsigned long long h[2] = {0, 0}, res_before = 0;
     while (n_in > 0) {
         if (++level > ix->n + 1) return fail(FMX_E_LIMIT, "regex traversal deeper than the text");
@@ -972,6 +1002,20 @@ int fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64
     for (int64_t i = 0; i < total; ++i) { len[i] = (int32_t)hr[(size_t)i].len; sp[i] = hr[(size_t)i].sp; ep[i] = hr[(size_t)i].ep; }
     ph.mark("marshal results");
     return FMX_OK;
+}
+
+int fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64_t cap_total, int64_t *out_off, int32_t *len,
+                           int64_t *sp, int64_t *ep) {
+    CHECK_IX(ix);
+    if (m < 0 || !out_off || (m && !rx)) return fail(FMX_E_ARG, "bad argument");
+    for (int64_t i = 0; i <= m; ++i) out_off[i] = 0;
+    if (m == 0) return FMX_OK;
+    fmx_regex_set *set = nullptr;
+    int rc = fmx_regex_set_create(ix, rx, m, &set);
+    if (rc) return rc;
+    rc = fmx_regex_set_search(ix, set, cap_total, out_off, len, sp, ep);
+    fmx_regex_set_free(set);
+    return rc;
 }
 
 // ---- K4 gather microbenchmark -------------------------------------------------------------------------------------

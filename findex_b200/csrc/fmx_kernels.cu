@@ -502,6 +502,15 @@ cudaError_t launch_locate(const DevIndex &ix, LaunchCfg cfg, const int64_t *d_sp
     return cudaGetLastError();
 }
 
+__global__ void init_frontier_kernel(const uint32_t *__restrict__ first, long long n_first, uint32_t n, FrontierItem *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_first) out[i] = FrontierItem{first[i], 0u, 0u, n};             // StatePoint(0, 0, sa.n, state)  retree.scala:576
+}
+cudaError_t launch_init_frontier(const uint32_t *d_first, int64_t n_first, uint32_t n, FrontierItem *d_out, cudaStream_t st) {
+    if (n_first > 0) init_frontier_kernel<<<(unsigned)((n_first + 255) / 256), 256, 0, st>>>(d_first, n_first, n, d_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_regex_level(const DevIndex &ix, LaunchCfg cfg, RegexTables rt, const FrontierItem *d_in, int64_t n_in,
                                FrontierItem *d_out, int64_t cap_out, RegexResult *d_res, int64_t cap_res,
                                unsigned long long *d_counters, cudaStream_t st) {

@@ -55,6 +55,7 @@ struct RegexTables {
 };
 struct FrontierItem { uint32_t state, len, sp, ep; };
 struct RegexResult  { uint32_t regex, len, sp, ep; };
+cudaError_t launch_init_frontier(const uint32_t *d_first, int64_t n_first, uint32_t n, FrontierItem *d_out, cudaStream_t st);
 // one BFS level: consumes `n_in` items, appends survivors' follows to d_out (capacity cap_out) and matches to
 // d_res (capacity cap_res).  d_counters[0] = next frontier size, [1] = results so far (both may exceed caps:
 // writes are dropped, counts keep growing so the host can size a retry).

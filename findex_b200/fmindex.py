@@ -93,6 +93,10 @@ def lib():
     L.fmx_regex_free.restype = None
     L.fmx_regex_tables.argtypes = [p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), p, p, p, p, p, p]
     L.fmx_regex_search_batch.argtypes = [p, p, i64, i64, p, p, p, p]
+    L.fmx_regex_set_create.argtypes = [p, p, i64, pp]
+    L.fmx_regex_set_search.argtypes = [p, p, i64, p, p, p, p]
+    L.fmx_regex_set_free.argtypes = [p]
+    L.fmx_regex_set_free.restype = None
     L.fmx_count_fixed_stats.argtypes = [p, p, i32, i64, C.POINTER(i64), C.POINTER(i64)]
     L.fmx_gather_bench.argtypes = [p, i32, i32, i64, i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.fmx_set_lanes.argtypes = [p, i32]
@@ -182,6 +186,42 @@ class ReTree:
     def matchSA(self, sa):
         """ReTree.matchSA with the caps disabled: sorted list of (len, sp, ep)."""
         return sa.regex_search_batch([self])[0]
+
+
+class RegexSet:
+    """fmx_regex_set: the concatenated automata of a batch, resident on the searcher's device."""
+
+    def __init__(self, searcher, trees):
+        self.m = len(trees)
+        arr = (C.c_void_p * max(self.m, 1))(*[t.h for t in trees])
+        h = C.c_void_p()
+        _check(lib().fmx_regex_set_create(searcher.h, arr, self.m, C.byref(h)))
+        self.h = h
+
+    def search(self, searcher, cap_total=1 << 20):
+        m = self.m
+        off = np.zeros(m + 1, np.int64)
+        while True:
+            ln = np.zeros(max(cap_total, 1), np.int32)
+            sp = np.zeros(max(cap_total, 1), np.int64)
+            ep = np.zeros(max(cap_total, 1), np.int64)
+            rc = lib().fmx_regex_set_search(searcher.h, self.h, cap_total, _ptr(off), _ptr(ln), _ptr(sp), _ptr(ep))
+            if rc == FMX_E_CAPACITY:
+                cap_total = int(off[m])
+                continue
+            _check(rc)
+            return off, ln[:off[m]], sp[:off[m]], ep[:off[m]]
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().fmx_regex_set_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class ThompsonNFA(ReTree):
@@ -372,6 +412,10 @@ class GpuFMSearcher:
             break
         return [list(zip(ln[off[i]:off[i + 1]].tolist(), sp[off[i]:off[i + 1]].tolist(), ep[off[i]:off[i + 1]].tolist()))
                 for i in range(m)]
+
+    def regex_set(self, trees):
+        """Device-resident batch of compiled regexes (compile once, search many times)."""
+        return RegexSet(self, trees)
 
     def gather_bench(self, bytes_per_gather=64, lanes=4, gathers=1 << 24, chain=16, iters=3):
         gbs, ms = C.c_double(), C.c_double()

@@ -161,6 +161,14 @@ int  fmx_regex_tables(const fmx_regex *rx, int32_t *n_states, int32_t *n_follows
 int  fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64_t cap_total,
                             int64_t *out_off, int32_t *len, int64_t *sp, int64_t *ep);
 
+/* Compile once, search many times: a regex set keeps the concatenated automata of a batch resident on the index's device
+ * (the batched form of `val t = ReTree(post)` ... `t.matchSA(sa)` ... `t.matchSA(sa2)`).  fmx_regex_search_batch is
+ * create + search + free.  A set may be searched against any index on the same device.                          */
+typedef struct fmx_regex_set fmx_regex_set;
+int  fmx_regex_set_create(fmx_index *ix, fmx_regex *const *rx, int64_t m, fmx_regex_set **out);
+int  fmx_regex_set_search(fmx_index *ix, fmx_regex_set *set, int64_t cap_total, int64_t *out_off, int32_t *len, int64_t *sp, int64_t *ep);
+void fmx_regex_set_free(fmx_regex_set *set);
+
 /* ---- instrumentation for the roofline accounting (not on the timed path) ---------------------------
  * Runs the same count kernel with block-touch counting: *blocks = number of distinct 64-B rank blocks
  * the batch reads (a level whose sp and ep probes share a block counts once), *steps = executed
