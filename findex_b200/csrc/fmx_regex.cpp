@@ -26,11 +26,14 @@ struct Tok {
 };
 
 struct ParseError { int code; std::string msg; };
+constexpr size_t kMaxNesting = 1000;       // the tree functions recurse over the nesting depth
+constexpr int64_t kMaxRegexBytes = 1 << 16;
 [[noreturn]] void syntax() { throw ParseError{FMX_E_SYNTAX, "re2post syntax"}; }
 [[noreturn]] void unsupported(const std::string &m) { throw ParseError{FMX_E_UNSUPPORTED, m}; }
 
 // ---- infix -> postfix with explicit concatenation (re2.scala:50-185) ---------------------------------
 std::vector<Tok> to_postfix(const uint8_t *s, int64_t l, bool line_only) {
+    if (l > kMaxRegexBytes) throw ParseError{FMX_E_LIMIT, "regex longer than 65536 bytes"};
     std::vector<Tok> out;
     struct Frame { int nalt, natom; };
     std::vector<Frame> frames;
@@ -89,6 +92,7 @@ std::vector<Tok> to_postfix(const uint8_t *s, int64_t l, bool line_only) {
         switch (c) {
         case '(':
             before_atom();
+            if (frames.size() >= kMaxNesting) throw ParseError{FMX_E_LIMIT, "regex nesting deeper than 1000 (the reference overflows its stack long before)"};
             frames.push_back({nalt, natom});
             nalt = 0; natom = 0;
             break;
@@ -131,6 +135,7 @@ struct Node {
     NodeKind kind;
     int c = 0, num = 0;
     int parent = -1;                 // -1 = RootNode
+    int slot = 0;                    // index inside the parent's child list (valid after set_parents)
     std::vector<int> kids;           // front = head of the reference's child list
 };
 
@@ -183,10 +188,7 @@ struct Tree {
         return r;
     }
 
-    size_t index_in_parent(int i) const {
-        const Node &p = at(at(i).parent);
-        return (size_t)(std::find(p.kids.begin(), p.kids.end(), i) - p.kids.begin());
-    }
+    size_t index_in_parent(int i) const { return (size_t)at(i).slot; }
 
     std::vector<int> follows(int i) const {
         int pi = at(i).parent;
@@ -321,7 +323,8 @@ int normalise(const Tree &src, int i, Tree &dst) {
 
 void set_parents(Tree &t, int i, int parent) {
     t.at(i).parent = parent;
-    for (int k : t.at(i).kids) set_parents(t, k, i);
+    const std::vector<int> &kids = t.at(i).kids;
+    for (size_t k = 0; k < kids.size(); ++k) { t.at(kids[k]).slot = (int)k; set_parents(t, kids[k], i); }
 }
 
 // priority numbers (only relevant to the reference's capped PQ order; exported for parity checks)

@@ -190,3 +190,19 @@ def test_thompson_compiler_fuzz_against_oracle():
             with pytest.raises(want):
                 fx.ThompsonNFA(rx)
     assert seen["ok"] > 500 and seen["bad"] > 200
+
+
+def test_regex_compiler_limits_do_not_crash():
+    deep = "(" * 5000 + "a" + ")" * 5000
+    with pytest.raises(fx.FmxError) as e:
+        fx.ReTree(deep)
+    assert e.value.code == fx.FMX_E_LIMIT
+    with pytest.raises(fx.FmxError) as e:
+        fx.ThompsonNFA("a" * 70000)
+    assert e.value.code == fx.FMX_E_LIMIT
+    long_lit = "ab" * 20000                                   # 40 k positions: follows must stay linear
+    t = fx.ReTree(long_lit).tables()
+    assert len(t["c"]) == 40000 and t["last"][-1] == 1 and t["follows"][0] == [1]
+    opt = "x" + "a?" * 400 + "y"                              # long nullable run: quadratic follows, deep Thompson closure
+    assert fx.ReTree(opt).tables() == retree.compile_regex(opt).tables()
+    assert fx.ThompsonNFA(opt).tables() == retree.compile_thompson(opt)
