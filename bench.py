@@ -46,19 +46,24 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def make_text(n, seed=2):
-    return np.random.default_rng(seed).integers(1, 256, n, dtype=np.uint8)
+def make_text(n, workload="cfg2"):
+    if workload == "cfg5":                                  # 4e9 bytes i.i.d. uniform over ACGT, seed 7 (SURVEY §8d cfg 5)
+        return np.frombuffer(b"ACGT", np.uint8)[np.random.default_rng(7).integers(0, 4, n, dtype=np.uint8)]
+    return np.random.default_rng(2).integers(1, 256, n, dtype=np.uint8)
 
 
-def make_queries(text, m, ln, seed, rank, out=None):
-    """90 % hits (reversed substrings at uniform offsets), 10 % uniform random bytes; shuffled."""
+def make_queries(text, m, ln, seed, rank, out=None, workload="cfg2"):
+    """90 % hits (reversed substrings at uniform offsets), 10 % uniform random symbols; shuffled."""
     rng = np.random.default_rng([seed, rank])
     nh = int(m * 0.9)
     pats = out if out is not None else np.empty((m, ln), np.uint8)
     offs = rng.integers(0, len(text) - ln, nh)
     idx = offs[:, None] + np.arange(ln - 1, -1, -1)[None, :]
     hits = text[idx]
-    rnd = rng.integers(1, 256, (m - nh, ln), dtype=np.uint8)
+    if workload == "cfg5":
+        rnd = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, (m - nh, ln), dtype=np.uint8)]
+    else:
+        rnd = rng.integers(1, 256, (m - nh, ln), dtype=np.uint8)
     perm = rng.permutation(m)
     is_hit = np.zeros(m, bool)
     is_hit[:nh] = True
@@ -127,8 +132,8 @@ class ClockSampler:
                 "samples_in_timed_window": len(inside)}
 
 
-def index_base(n):
-    return "/tmp/fmx_bench_cfg2_%d" % n
+def index_base(n, workload="cfg2"):
+    return "/tmp/fmx_bench_%s_%d" % (workload, n)
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -142,8 +147,8 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     n, m, ln = args.text_bytes, args.queries, args.len
     t0 = time.time()
-    text = make_text(n)
-    base = index_base(n)
+    text = make_text(n, args.workload)
+    base = index_base(n, args.workload)
     if not (os.path.exists(base + ".bwt") and os.path.exists(base + ".aux")):
         # index construction is setup, not the measured path; the device suffix sorter only writes the reference's files
         from findex_b200 import build as fbuild, fmindex as fx
@@ -152,7 +157,7 @@ def run_reference(args, rank, world):
     fo.build(native=True)
     ix = fo.OracleIndex.load(base)
     log("reference arm: index loaded + fm array materialised in %.1f s" % (time.time() - t0))
-    pats, _, _ = make_queries(text, m, ln, 3, 0)
+    pats, _, _ = make_queries(text, m, ln, 3, 0, workload=args.workload)
     probe = 20000
     t1 = time.time()
     ix.count_batch(pats[:probe].reshape(-1), np.arange(0, probe * ln + 1, ln, dtype=np.int64), threads=cores)
@@ -179,8 +184,9 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args):
-    return {"workload": "cfg2: 1e9-byte uniform text over bytes 1..255 (seed 2), %d len-%d count queries per GPU, 90%% hits / 10%% random "
-                        "(seed 3)" % (args.queries, args.len),
+    what = ("cfg5: %d-byte uniform DNA text (ACGT, seed 7)" % args.text_bytes) if args.workload == "cfg5" else \
+        ("cfg2: %d-byte uniform text over bytes 1..255 (seed 2)" % args.text_bytes)
+    return {"workload": "%s, %d len-%d count queries per GPU, 90%% hits / 10%% random (seed 3)" % (what, args.queries, args.len),
             "text_bytes": args.text_bytes, "queries_per_gpu": args.queries, "pattern_len": args.len, "parallelism": "dp%d (index replicated, "
             "queries sharded)" % args.gpus, "l2": "inputs (160 MB patterns) and index (GBs) exceed the 126 MB L2; no explicit flush"}
 
@@ -200,8 +206,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     t0 = time.time()
-    text = make_text(n)
-    base = index_base(n)
+    text = make_text(n, args.workload)
+    base = index_base(n, args.workload)
     if rank == 0 and not (os.path.exists(base + ".bwt") and os.path.exists(base + ".aux")):
         tb = time.time()
         fx.build_index_files(text, base, bigEndian=True)
@@ -217,7 +223,7 @@ def run_ours(args, rank, world, local_rank):
     h_pat = fx.PinnedArray((m, ln), np.uint8)
     h_sp = fx.PinnedArray((m,), np.int64)
     h_ep = fx.PinnedArray((m,), np.int64)
-    pats, is_hit, offs = make_queries(text, m, ln, 3, rank, out=h_pat.array)
+    pats, is_hit, offs = make_queries(text, m, ln, 3, rank, out=h_pat.array, workload=args.workload)
     d_pat = torch.from_numpy(pats).to(dev)
     d_sp = torch.zeros(m, dtype=torch.int32, device=dev)
     d_ep = torch.zeros(m, dtype=torch.int32, device=dev)
@@ -315,8 +321,8 @@ def run_ours(args, rank, world, local_rank):
     cnt = ep - sp
     assert (cnt[is_hit] >= 1).all(), "a text substring was not found"
     if rank == 0:
-        tb = text.tobytes()
-        for q in np.flatnonzero(is_hit)[:2]:
+        tb = text.tobytes() if n <= 1_500_000_000 else text[:1_000_000_000].tobytes()
+        for q in (np.flatnonzero(is_hit)[:2] if n <= 1_500_000_000 else []):
             needle = pats[q][::-1].tobytes()
             assert tb.count(needle) == cnt[q], "count mismatch vs brute force"
         del tb
@@ -555,9 +561,10 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--text-bytes", type=int, default=1_000_000_000)
-    ap.add_argument("--queries", type=int, default=10_000_000)
-    ap.add_argument("--len", type=int, default=16)
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"], help="cfg2 = the metric's config (default); cfg5 = 4 GB DNA, len-32")
+    ap.add_argument("--text-bytes", type=int, default=None)
+    ap.add_argument("--queries", type=int, default=None)
+    ap.add_argument("--len", type=int, default=None)
     ap.add_argument("--layout", default="auto", choices=["auto", "wm", "planes"])
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--accel", default="auto", choices=["auto", "none", "kmer", "text", "both"])
@@ -567,6 +574,14 @@ def main():
     ap.add_argument("--regexes", type=int, default=100_000, help="regexes per GPU for the secondary regex measurement (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    dflt = {"cfg2": (1_000_000_000, 10_000_000, 16), "cfg5": (4_000_000_000, 12_500_000, 32)}[args.workload]
+    args.text_bytes = args.text_bytes or dflt[0]
+    args.queries = args.queries or dflt[1]
+    args.len = args.len or dflt[2]
+    if args.workload == "cfg5":
+        args.regexes = 0
+        global METRIC
+        METRIC = "fm_count_queries_per_s_len32_4GB_dna_text"
     if args.warmup < 3:
         log("note: contract asks for >= 3 warm-up steps; got", args.warmup)
     rank = int(os.environ.get("RANK", "0"))
