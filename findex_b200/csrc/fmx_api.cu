@@ -176,7 +176,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     DevIndex &d = ix->d;
     d.blocks = (const uint4 *)blocks; d.stride = (uint64_t)nblk; d.bwt = d_bwt; d.C = d_C; d.base = d_base; d.code = d_code;
     d.bm = nullptr;
-    d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isat = nullptr;
+    d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isat = nullptr; d.isat_bits = 8; d.isat_syms = 12;
     d.mark = nullptr; d.samples = nullptr; d.n = (uint32_t)n; d.eof = (uint32_t)eof; d.layout = layout; d.levels = levels;
     for (int l = 0; l < 8; ++l) d.z[l] = z[l];
 
@@ -221,18 +221,26 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
         std::string err;
         e = build_full_sa(d, layout, (uint32_t *)sa, isa, text, ix->stream, err);
         if (e != cudaSuccess) return fail(err.empty() ? FMX_E_CUDA : FMX_E_FORMAT, "suffix array construction failed: %s", err.empty() ? cudaGetErrorString(e) : err.c_str());
-        CU(build_isat(isa, text, n, (uint4 *)isat, ix->stream));
+        int ibits = 1;
+        while ((1 << ibits) < sigma + 1) ++ibits;                 // values 0..sigma: dense code + 1, 0 = '$'
+        const int isyms = 96 / ibits;
+        CU(build_isat(isa, text, d_code, n, ibits, isyms, (uint4 *)isat, ix->stream));
         CU(cudaFreeAsync(isa, ix->stream));
         CU(cudaFreeAsync(text, ix->stream));
         CU(cudaStreamSynchronize(ix->stream));
-        d.sa = (const uint32_t *)sa; d.isat = (const uint4 *)isat;
+        d.sa = (const uint32_t *)sa; d.isat = (const uint4 *)isat; d.isat_bits = ibits; d.isat_syms = isyms;
         ix->index_bytes += 20 * n;
     }
     if (want_kmer && sigma >= 1) {
-        const int64_t table_budget = 256ll << 20;
+        // table budget: fmx_opts.kmer_table_bytes, else 256 MiB .. 16 GiB scaled to a sixteenth of what the device has left
+        size_t fr2 = 0, to2 = 0;
+        cudaMemGetInfo(&fr2, &to2);
+        const int64_t table_budget = o.kmer_table_bytes > 0 ? o.kmer_table_bytes
+                                                            : std::min<int64_t>(std::max<int64_t>(256ll << 20, (int64_t)(fr2 / 16)), 16ll << 30);
         int K = 0;
         int64_t entries = 1;
-        while (K < 16 && entries * sigma * 8 <= table_budget && entries * sigma <= (1ll << 31)) { entries *= sigma; ++K; }
+        const int64_t max_entries = std::min<int64_t>(1ll << 31, std::max<int64_t>(4 * n, 1 << 16));   // no point in far more entries than rows
+        while (K < 16 && entries * sigma * 8 <= table_budget && entries * sigma <= max_entries) { entries *= sigma; ++K; }
         if (sigma == 1) { K = std::min(K, 16); }
         if (K >= 2) {
             void *tab = nullptr;

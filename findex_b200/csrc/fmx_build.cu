@@ -307,17 +307,27 @@ cudaError_t build_walk_blocks(const uint8_t *d_bwt, const uint32_t *d_mark_block
     return cudaGetLastError();
 }
 
-// isat[p] = { isa[p], T'[p..p+12) }  (bytes past the end read as 0)
-__global__ void build_isat_kernel(const uint32_t *__restrict__ isa, const uint8_t *__restrict__ text, int64_t n, uint4 *__restrict__ isat) {
+// isat[p] = { isa[p], 96 bits holding the next `syms` symbols of T' at `bits` bits each }: stored value = dense code + 1,
+// 0 for the '$' and past the end
+__global__ void build_isat_kernel(const uint32_t *__restrict__ isa, const uint8_t *__restrict__ text, const uint8_t *__restrict__ code, int64_t n,
+                                  int bits, int syms, uint4 *__restrict__ isat) {
+    __shared__ uint8_t sc[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sc[i] = code[i];
+    __syncthreads();
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    uint32_t w[3] = {0, 0, 0};
-#pragma unroll
-    for (int k = 0; k < 12; ++k) if (p + k < n) w[k >> 2] |= (uint32_t)text[p + k] << (8 * (k & 3));
-    isat[p] = make_uint4(isa[p], w[0], w[1], w[2]);
+    unsigned long long lo = 0, hi = 0;                          // 96 bits: lo = bits 0..63, hi = bits 64..95
+    for (int k = 0; k < syms; ++k) {
+        unsigned long long v = 0;
+        if (p + k < n) { const uint8_t t = text[p + k]; v = t ? (unsigned long long)sc[t] + 1ull : 0ull; }
+        const int o = k * bits;
+        if (o < 64) { lo |= v << o; if (o + bits > 64) hi |= v >> (64 - o); }
+        else hi |= v << (o - 64);
+    }
+    isat[p] = make_uint4(isa[p], (uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi);
 }
-cudaError_t build_isat(const uint32_t *d_isa, const uint8_t *d_text, int64_t n, uint4 *d_isat, cudaStream_t st) {
-    build_isat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_isa, d_text, n, d_isat);
+cudaError_t build_isat(const uint32_t *d_isa, const uint8_t *d_text, const uint8_t *d_code, int64_t n, int bits, int syms, uint4 *d_isat, cudaStream_t st) {
+    build_isat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_isa, d_text, d_code, n, bits, syms, d_isat);
     return cudaGetLastError();
 }
 

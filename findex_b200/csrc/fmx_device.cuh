@@ -40,10 +40,10 @@ struct DevIndex {
     int32_t        kmer_k;
     uint32_t       kmer_sigma;
     const uint32_t *sa;         // full suffix array  sa[row]   (bwtFm2sa, util.scala:213-224)
-    const uint4    *isat;       // per text position p: { isa[p], T'[p..p+12) } — inverse SA and the text behind it in one 16-B fetch
+    const uint4    *isat;       // per text position p: { isa[p], 96 bits of T'[p..] } — inverse SA and the text behind it in one 16-B fetch
+    int32_t         isat_bits;  // bits per text symbol in isat: ceil(log2(sigma+1)); stored value = dense code + 1, 0 = '$' / past the end
+    int32_t         isat_syms;  // symbols per entry = 96 / isat_bits  (bytes: 12, sigma <= 31: 19, DNA: 32)
 };
-
-constexpr uint32_t kIsatText = 12;     // text bytes per isat entry
 
 struct SharedTables {
     uint32_t C[257];
@@ -232,7 +232,7 @@ __device__ __forceinline__ void backward_step(const DevIndex &ix, const SharedTa
 // active=false); groups leave the loop individually, the warp leaves when all are done.
 //   * k-mer table (optional): the first kmer_k steps are one lookup.
 //   * first step from (0,n) otherwise: (C[c], C[c+1]) without touching memory.
-//   * singleton shortcut (optional): once the interval is one row r and 3..12 bytes remain, the remaining bytes
+//   * singleton shortcut (optional): once the interval is one row r and 3..isat_syms bytes remain, the remaining bytes
 //     are compared with T' in front of position sa[r]; the answer row is isa[sa[r]-remaining].  Identical to
 //     stepping: from a singleton, a step succeeds iff BWT[r] = T'[sa[r]-1] equals the byte, and lands on
 //     LF(r) = isa[sa[r]-1].  Patterns containing byte 0 take the ordinary steps (the '$' row wraps the text).
@@ -275,19 +275,22 @@ __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedT
         const bool go = (i >= 0) && (sp < ep);
         if (go) {
             bool stepped = false;
-            if (!noshort && (ep - sp) == 1u && i >= 2 && i < (int)kIsatText) {
-                // one 16-byte entry holds isa[p] and T'[p..p+12): the whole shortcut is sa[row] -> isat[sa[row]-rem]
+            if (!noshort && (ep - sp) == 1u && i >= 2 && i < ix.isat_syms) {
+                // one 16-byte entry holds isa[p] and the next isat_syms symbols of T': the whole shortcut is sa[row] -> isat[sa[row]-rem]
                 const int rem = i + 1;
                 const uint32_t q = ix.sa[sp];
                 const bool fits = q >= (uint32_t)rem;
                 const uint32_t b0 = fits ? q - (uint32_t)rem : 0u;
                 const uint4 e = ldg128(ix.isat + b0);
+                const uint32_t bits = (uint32_t)ix.isat_bits, fmask = (1u << bits) - 1u;
                 bool eq = fits, zero = false;
                 for (int k = lane; k < rem; k += G) {
                     const uint32_t pc = pat(k);
-                    const uint32_t w = (k >> 2) == 0 ? e.y : (k >> 2) == 1 ? e.z : e.w;
+                    const uint32_t o = (uint32_t)k * bits, w = o >> 5;
+                    const uint32_t lo = w == 0 ? e.y : w == 1 ? e.z : e.w, hi = w == 0 ? e.z : w == 1 ? e.w : 0u;
+                    const uint32_t sym = __funnelshift_r(lo, hi, o & 31u) & fmask;      // dense code + 1 of T'[b0 + k]
                     zero = zero || (pc == 0);
-                    eq = eq && (((w >> (8 * (k & 3))) & 0xFFu) == pc);
+                    eq = eq && (sym == (uint32_t)tb.code[pc] + 1u);                     // an absent byte (code 0xFF) never matches
                 }
                 if (G > 1) { eq = __all_sync(gmask, eq); zero = __any_sync(gmask, zero); }
                 if (zero) noshort = true;

@@ -38,7 +38,7 @@ class ReUnsupported(FmxError):
 
 class fmx_opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("layout", C.c_int32), ("sa_sample_rate", C.c_int32), ("require_fm", C.c_int32),
-                ("max_index_bytes", C.c_int64), ("lanes_per_query", C.c_int32), ("accel", C.c_int32)]
+                ("max_index_bytes", C.c_int64), ("lanes_per_query", C.c_int32), ("accel", C.c_int32), ("kmer_table_bytes", C.c_int64)]
 
 
 _lib = None
@@ -139,11 +139,13 @@ def _u8(a):
     return np.ascontiguousarray(a, dtype=np.uint8)
 
 
-def make_opts(device=-1, layout=LAYOUT_AUTO, sa_sample_rate=0, require_fm=False, max_index_bytes=0, lanes_per_query=0, accel=ACCEL_AUTO):
+def make_opts(device=-1, layout=LAYOUT_AUTO, sa_sample_rate=0, require_fm=False, max_index_bytes=0, lanes_per_query=0, accel=ACCEL_AUTO,
+              kmer_table_bytes=0):
     o = fmx_opts()
     lib().fmx_opts_default(C.byref(o))
     o.device, o.layout, o.sa_sample_rate = device, layout, sa_sample_rate
     o.require_fm, o.max_index_bytes, o.lanes_per_query, o.accel = int(require_fm), max_index_bytes, lanes_per_query, accel
+    o.kmer_table_bytes = kmer_table_bytes
     return o
 
 

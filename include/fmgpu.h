@@ -45,8 +45,8 @@ extern "C" {
 
 /* Bit-exact accelerators of the count path (fmx_opts.accel); they spend HBM capacity, never change results */
 #define FMX_ACCEL_AUTO      0
-#define FMX_ACCEL_KMER      1   /* table of (sp,ep) after the first k steps, k = max with sigma^k*8 B <= 256 MiB */
-#define FMX_ACCEL_TEXT      2   /* full SA + {inverse SA, 12 text bytes} entries (20n bytes): singleton intervals finish in 2 fetches; locate is 1 fetch */
+#define FMX_ACCEL_KMER      1   /* table of (sp,ep) after the first k steps, k = max with sigma^k*8 B <= kmer_table_bytes */
+#define FMX_ACCEL_TEXT      2   /* full SA + {inverse SA, 96 bits of text} entries (20n bytes): singleton intervals finish in 2 fetches; locate is 1 fetch */
 #define FMX_ACCEL_NONE      8   /* plain backward search only                                                */
 
 typedef struct fmx_index fmx_index;     /* opaque; library-owned until fmx_close  */
@@ -60,6 +60,7 @@ typedef struct fmx_opts {
     int64_t  max_index_bytes;   /* budget for FMX_LAYOUT_AUTO; 0 = default                               */
     int32_t  lanes_per_query;   /* 0 = default; 1, 2 or 4 lanes cooperate on one 64-B rank block         */
     int32_t  accel;             /* FMX_ACCEL_* bit mask; 0 = auto (both when they fit the memory budget)   */
+    int64_t  kmer_table_bytes;  /* budget of the k-mer table; 0 = auto (256 MiB .. 16 GiB, a sixteenth of free memory) */
 } fmx_opts;
 
 void        fmx_opts_default(fmx_opts *o);
