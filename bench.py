@@ -382,6 +382,15 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e, clocks_e2e = timed_region(e2e_step, "e2e")
     assert np.array_equal(h_sp.array, np.where(cnt > 0, sp, 0)) and np.array_equal(h_ep.array, np.where(cnt > 0, ep, 0)), "host API result differs from device API"
 
+    # the same batch through the count-only call (uint32 ep-sp per query: 4 instead of 16 result bytes over PCIe)
+    h_cnt = fx.PinnedArray((m,), np.uint32)
+
+    def e2e_count_only_step():
+        g.count_only_fixed(h_pat.array, out=h_cnt.array)
+
+    ms_e2e_co, _ = timed_region(e2e_count_only_step, "e2e")
+    assert np.array_equal(h_cnt.array.astype(np.int64), np.where(cnt > 0, cnt, 0)), "count-only API differs from ep-sp"
+
     regex = None if args.regexes <= 0 else regex_leg(args, g, text, world, rank, dev)
 
     value = world * m * args.steps / (ms_total * 1e-3)
@@ -404,7 +413,9 @@ def run_ours(args, rank, world, local_rank):
                                                index_bytes=info["index_bytes"], kmer_k=info["kmer_k"], text_shortcut=info["text_shortcut"], checksum=checksum),
            "clocks": clocks,
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": m * ln, "d2h_bytes_per_step": m * 16, "ms_per_step": ms_e2e / args.steps,
-                   "api": "fmx_count_fixed (host pinned buffers in/out, int64 sp/ep)", "clocks": clocks_e2e},
+                   "api": "fmx_count_fixed (host pinned buffers in/out, int64 sp/ep)", "clocks": clocks_e2e,
+                   "count_only": {"value": world * m * args.steps / (ms_e2e_co * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_co / args.steps,
+                                  "h2d_bytes_per_step": m * ln, "d2h_bytes_per_step": m * 4, "api": "fmx_count_only_fixed (uint32 ep-sp)"}},
            "gpu_launches": args.steps * (1 if (world == 1 or p2p) else nch),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                         "peak_source": peak_src, "kernel": "count_fixed_kernel", "kernel_ms": k_ms,

@@ -73,6 +73,7 @@ def lib():
     L.fmx_interval_prev_range.argtypes = [p, i64, i64, C.c_int, C.c_int, p, p, p, C.POINTER(i64)]
     L.fmx_count_batch.argtypes = [p, p, p, i64, p, p]
     L.fmx_count_fixed.argtypes = [p, p, i32, i64, p, p]
+    L.fmx_count_only_fixed.argtypes = [p, p, i32, i64, p]
     L.fmx_count_fixed_dev.argtypes = [p, p, i32, i64, p, p, p]
     L.fmx_count_fixed_dev_gather.argtypes = [p, p, i32, i64, p, p, p, i32, i64, p]
     L.fmx_dev_alloc.argtypes = [pp, i64]
@@ -432,6 +433,15 @@ class GpuFMSearcher:
         m, ln = pat2d.shape
         assert pat2d.flags.c_contiguous and pat2d.dtype == np.uint8 and sp.dtype == np.int64 and ep.dtype == np.int64
         _check(lib().fmx_count_fixed(self.h, _ptr(pat2d), ln, m, _ptr(sp), _ptr(ep)))
+
+    def count_only_fixed(self, pat2d, out=None):
+        """Number of occurrences per pattern (ep - sp, uint32) without the interval."""
+        pat2d = np.ascontiguousarray(pat2d, dtype=np.uint8)
+        m, ln = pat2d.shape
+        cnt = out if out is not None else np.zeros(m, np.uint32)
+        assert cnt.dtype == np.uint32 and len(cnt) == m
+        _check(lib().fmx_count_only_fixed(self.h, _ptr(pat2d), ln, m, _ptr(cnt)))
+        return cnt
 
     def set_lanes(self, lanes):
         _check(lib().fmx_set_lanes(self.h, lanes))

@@ -181,6 +181,7 @@ def test_count_parity_small(ref_dir, cfg, accel):
         sp, ep = g.count_fixed(arr)
         osp, oep = o.count_batch(arr.reshape(-1), np.arange(0, arr.size + 1, ln, dtype=np.int64))
         assert np.array_equal(sp, osp) and np.array_equal(ep, oep)
+        assert np.array_equal(g.count_only_fixed(arr).astype(np.int64), oep - osp)
     g.close()
     o.close()
 
