@@ -217,6 +217,8 @@ def run_ours(args, rank, world, local_rank):
     layout = {"auto": fx.LAYOUT_AUTO, "wm": fx.LAYOUT_WM, "planes": fx.LAYOUT_PLANES}[args.layout]
     accel = {"auto": fx.ACCEL_AUTO, "none": fx.ACCEL_NONE, "kmer": fx.ACCEL_KMER, "text": fx.ACCEL_TEXT, "both": fx.ACCEL_KMER | fx.ACCEL_TEXT}[args.accel]
     g = fx.GpuFMSearcher(base + ".bwt", bigEndian=True, device=local_rank, layout=layout, lanes_per_query=args.lanes, accel=accel)
+    if args.chunk:
+        g.set_chunk(args.chunk)
     info = g.info()
     log("rank %d: index open (%s, %.2f GB on device) after %.1f s" % (rank, info["layout"], info["index_bytes"] / 1e9, time.time() - t0))
 
@@ -583,6 +585,7 @@ def main():
     ap.add_argument("--gather-chunks", type=int, default=1)
     ap.add_argument("--diag", default="none", choices=["none", "nocomm", "nosub", "nogather"], help="diagnostics only: drop parts of the exchange")
     ap.add_argument("--regexes", type=int, default=100_000, help="regexes per GPU for the secondary regex measurement (0 = skip)")
+    ap.add_argument("--chunk", type=int, default=0, help="queries per pipeline chunk of the host-buffer calls (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     dflt = {"cfg2": (1_000_000_000, 10_000_000, 16), "cfg5": (4_000_000_000, 12_500_000, 32)}[args.workload]
