@@ -567,3 +567,49 @@ def test_regex_set_is_reusable(ref_dir, o1024, words_base, words):
     rs.close()
     w.close()
     g.close()
+
+
+def test_concurrent_callers_and_two_indexes(ref_dir, words_base, words):
+    """An opened index is immutable; batch calls from several host threads (ctypes drops the GIL) and on several indexes at once
+    must not interfere (thread-safe batch calls)."""
+    import threading
+    o1 = fo.OracleIndex.load(os.path.join(ref_dir, "test.cmp"), big_endian=False)
+    o2, text2 = words
+    g1 = _open(os.path.join(ref_dir, "test.cmp.bwt"), (fx.LAYOUT_PLANES, 2), sa_sample_rate=8)
+    g2 = _open(words_base + ".bwt", (fx.LAYOUT_WM, 2), big_endian=True)
+    text1 = open(os.path.join(ref_dir, "test.txt"), "rb").read()
+    rng = np.random.default_rng(21)
+
+    def pats_of(text, m, ln):
+        t = np.frombuffer(text, np.uint8)
+        offs = rng.integers(0, len(t) - ln, m)
+        return np.stack([t[s:s + ln][::-1] for s in offs])
+    p1, p2 = pats_of(text1, 20000, 5), pats_of(text2, 20000, 7)
+    w1 = o1.count_batch(p1.reshape(-1), np.arange(0, p1.size + 1, 5, dtype=np.int64))
+    w2 = o2.count_batch(p2.reshape(-1), np.arange(0, p2.size + 1, 7, dtype=np.int64))
+    rx_want = o1.regex_match("a.b")
+    errors = []
+
+    def worker(k):
+        try:
+            for _ in range(10):
+                if k % 3 == 0:
+                    sp, ep = g1.count_fixed(p1)
+                    assert np.array_equal(sp, w1[0]) and np.array_equal(ep, w1[1])
+                elif k % 3 == 1:
+                    sp, ep = g2.count_fixed(p2)
+                    assert np.array_equal(sp, w2[0]) and np.array_equal(ep, w2[1])
+                else:
+                    assert fx.ReTree("a.b").matchSA(g1) == rx_want
+                    off, pos = g1.locate_batch(w1[0][:50], w1[1][:50])
+                    assert off[-1] == int((w1[1][:50] - w1[0][:50]).sum())
+        except Exception as e:                      # noqa: BLE001
+            errors.append(repr(e))
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    g1.close()
+    g2.close()
