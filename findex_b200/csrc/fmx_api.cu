@@ -79,7 +79,7 @@ int ensure_device(int device, int *chosen) {
 
 template <typename T> T *dev_upload(fmx_index *ix, const T *host, size_t count, cudaError_t *err) {
     void *p = nullptr;
-    *err = cudaMalloc(&p, count * sizeof(T) ? count * sizeof(T) : 1);
+    *err = cudaMalloc(&p, count ? count * sizeof(T) : 1);
     if (*err != cudaSuccess) return nullptr;
     ix->owned.push_back(p);
     if (count) *err = cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, ix->stream);
