@@ -9,6 +9,7 @@ constexpr int kThreads = 256;
 struct LaunchCfg {
     int layout;          // FMX_LAYOUT_WM / FMX_LAYOUT_PLANES
     int lanes;           // 1, 2 or 4 lanes per query
+    int persistent_ctas = 0;   // > 0: count kernels run persistently on this many CTAs (SMs x resident CTAs per SM)
 };
 
 // fused exchange: up to 8 gathered buffers (one per rank, peer-mapped) that receive this shard's hit counts
