@@ -215,7 +215,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     layout = {"auto": fx.LAYOUT_AUTO, "wm": fx.LAYOUT_WM, "planes": fx.LAYOUT_PLANES}[args.layout]
-    accel = {"auto": fx.ACCEL_AUTO, "none": fx.ACCEL_NONE, "kmer": fx.ACCEL_KMER, "text": fx.ACCEL_TEXT, "both": fx.ACCEL_KMER | fx.ACCEL_TEXT}[args.accel]
+    accel = {"auto": fx.ACCEL_AUTO, "none": fx.ACCEL_NONE, "kmer": fx.ACCEL_KMER, "text": fx.ACCEL_TEXT, "both": fx.ACCEL_KMER | fx.ACCEL_TEXT,
+             "ctx": fx.ACCEL_KMER | fx.ACCEL_CTX}[args.accel]
     g = fx.GpuFMSearcher(base + ".bwt", bigEndian=True, device=local_rank, layout=layout, lanes_per_query=args.lanes, accel=accel)
     if args.chunk:
         g.set_chunk(args.chunk)
@@ -405,14 +406,15 @@ def run_ours(args, rank, world, local_rank):
         try:
             rec = json.load(open(tp)).get("count_fixed_kernel", {})
             if (rec.get("queries") == m and rec.get("layout") == info["layout"] and rec.get("lanes") == info["lanes_per_query"]
-                    and rec.get("kmer_k") == info["kmer_k"] and rec.get("text_shortcut") == info["text_shortcut"]):
+                    and rec.get("kmer_k") == info["kmer_k"] and rec.get("text_shortcut") == info["text_shortcut"]
+                    and rec.get("ctx_depth", 0) == info["ctx_depth"]):
                 traffic = rec.get("dram_bytes_per_launch")
         except Exception:
             pass
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
            "data": "synthetic", "config": dict(workload_config(args), exchange=("none" if world == 1 else ("fused peer stores + 4-byte NCCL barrier" if p2p else "NCCL all_gather_into_tensor on a side stream")), layout=info["layout"], lanes_per_query=info["lanes_per_query"],
-                                               index_bytes=info["index_bytes"], kmer_k=info["kmer_k"], text_shortcut=info["text_shortcut"], checksum=checksum),
+                                               index_bytes=info["index_bytes"], kmer_k=info["kmer_k"], text_shortcut=info["text_shortcut"], ctx_depth=info["ctx_depth"], checksum=checksum),
            "clocks": clocks,
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": m * ln, "d2h_bytes_per_step": m * 16, "ms_per_step": ms_e2e / args.steps,
                    "api": "fmx_count_fixed (host pinned buffers in/out, int64 sp/ep)", "clocks": clocks_e2e,
@@ -580,7 +582,7 @@ def main():
     ap.add_argument("--len", type=int, default=None)
     ap.add_argument("--layout", default="auto", choices=["auto", "wm", "planes"])
     ap.add_argument("--lanes", type=int, default=0)
-    ap.add_argument("--accel", default="auto", choices=["auto", "none", "kmer", "text", "both"])
+    ap.add_argument("--accel", default="auto", choices=["auto", "none", "kmer", "text", "both", "ctx"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory stores (default) or NCCL all-gather")
     ap.add_argument("--gather-chunks", type=int, default=1)
     ap.add_argument("--diag", default="none", choices=["none", "nocomm", "nosub", "nogather"], help="diagnostics only: drop parts of the exchange")

@@ -135,8 +135,9 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
-        const char *env = std::getenv("FMX_PERSISTENT");                 // 0 disables; default on
-        if (!(env && env[0] == '0')) ix->cfg.persistent_ctas = sms * (lanes == 1 ? 4 : 8);
+        const char *env = std::getenv("FMX_PERSISTENT");                 // 1 enables the persistent form (measured slower: 7.97 vs 9.26 G q/s on cfg 2)
+        if (env && env[0] == '1') ix->cfg.persistent_ctas = sms * (lanes == 1 ? 4 : 8);
+        if (const char *mb = std::getenv("FMX_MINB")) ix->cfg.min_blocks = std::atoi(mb);
     }
     ix->index_bytes = (layout == FMX_LAYOUT_PLANES ? planes_bytes : wm_bytes) + n;
 
@@ -182,7 +183,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     DevIndex &d = ix->d;
     d.blocks = (const uint4 *)blocks; d.stride = (uint64_t)nblk; d.bwt = d_bwt; d.C = d_C; d.base = d_base; d.code = d_code;
     d.bm = nullptr;
-    d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isat = nullptr; d.isat_bits = 8; d.isat_syms = 12;
+    d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isat = nullptr; d.isat_bits = 8; d.isat_syms = 12; d.ctx = nullptr; d.ctx_J = 0;
     d.mark = nullptr; d.samples = nullptr; d.n = (uint32_t)n; d.eof = (uint32_t)eof; d.layout = layout; d.levels = levels;
     for (int l = 0; l < 8; ++l) d.z[l] = z[l];
 
@@ -208,16 +209,26 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
         }
     }
     // ---- optional accelerators ---------------------------------------------------------------------------
+    // Sizing rule (measured, tools/ldhint_bench.cu): random fetches run at ~46 G requests/s while the footprint a kernel touches stays
+    // inside the ~64 GB TLB reach and fall off a cliff beyond (36 G/s at 80 GB, 19 G/s at 100 GB).  So the structures the count
+    // kernel touches per query — k-mer table, row contexts, and the rank structure unless the table is deep enough that intervals
+    // are down to a few rows when it has been consulted — are kept inside `reach`; everything else may fill the rest of the HBM.
     int accel = o.accel;
     if (accel & FMX_ACCEL_NONE) accel = FMX_ACCEL_NONE;
     size_t fr = 0, to = 0;
     CU(cudaStreamSynchronize(ix->stream));
     trim_pool(ix->device);
     cudaMemGetInfo(&fr, &to);
-    const bool want_text = (accel & FMX_ACCEL_TEXT) || (accel == FMX_ACCEL_AUTO && 25 * n + (2ll << 30) < (int64_t)fr && ix->index_bytes + 20 * n <= budget + (24ll << 30));
+    double reach = 68e9;
+    if (const char *env = std::getenv("FMX_TLB_REACH_GB")) { const double v = std::atof(env); if (v > 0) reach = v * 1e9; }
+    const int64_t rank_bytes = (layout == FMX_LAYOUT_PLANES ? planes_bytes : wm_bytes);
+    const bool want_text = (accel & (FMX_ACCEL_TEXT | FMX_ACCEL_CTX)) ||
+                           (accel == FMX_ACCEL_AUTO && 25 * n + (2ll << 30) < (int64_t)fr && ix->index_bytes + 20 * n <= budget + (24ll << 30));
+    const bool want_ctx = n > 2 && ((accel & FMX_ACCEL_CTX) ||
+                                    (accel == FMX_ACCEL_AUTO && want_text && 32.0 * n + 4e9 <= reach && 57 * n + (8ll << 30) < (int64_t)fr));
     const bool want_kmer = (accel & FMX_ACCEL_KMER) || accel == FMX_ACCEL_AUTO;
     if (want_text && n > 2) {
-        // sa stays; isa and the text are scratch that is folded into the 16-byte isat entries
+        // sa stays; isa and the text are scratch that is folded into the 16-byte isat entries (and the 32-byte row contexts)
         void *sa = nullptr, *isat = nullptr;
         uint32_t *isa = nullptr; uint8_t *text = nullptr;
         e = cudaMalloc(&sa, (size_t)n * 4); CU(e); ix->owned.push_back(sa);
@@ -231,24 +242,50 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
         while ((1 << ibits) < sigma + 1) ++ibits;                 // values 0..sigma: dense code + 1, 0 = '$'
         const int isyms = 96 / ibits;
         CU(build_isat(isa, text, d_code, n, ibits, isyms, (uint4 *)isat, ix->stream));
+        d.sa = (const uint32_t *)sa; d.isat = (const uint4 *)isat; d.isat_bits = ibits; d.isat_syms = isyms;
+        ix->index_bytes += 20 * n;
+        if (want_ctx) {
+            void *ctx = nullptr;
+            e = cudaMalloc(&ctx, (size_t)n * 32);
+            if (e != cudaSuccess) { cudaGetLastError(); if (accel & FMX_ACCEL_CTX) return fail(FMX_E_CUDA, "cannot allocate %lld bytes for the row contexts", (long long)n * 32); }
+            else {
+                ix->owned.push_back(ctx);
+                CU(build_ctx((const uint32_t *)sa, isa, text, d_code, n, ibits, isyms, (uint4 *)ctx, ix->stream));
+                d.ctx = (const uint4 *)ctx; d.ctx_J = isyms;
+                ix->index_bytes += 32 * n;
+            }
+        }
         CU(cudaFreeAsync(isa, ix->stream));
         CU(cudaFreeAsync(text, ix->stream));
         CU(cudaStreamSynchronize(ix->stream));
-        d.sa = (const uint32_t *)sa; d.isat = (const uint4 *)isat; d.isat_bits = ibits; d.isat_syms = isyms;
-        ix->index_bytes += 20 * n;
+        trim_pool(ix->device);
     }
     if (want_kmer && sigma >= 1) {
-        // table budget: fmx_opts.kmer_table_bytes, else 256 MiB .. 16 GiB scaled to a sixteenth of what the device has left
         size_t fr2 = 0, to2 = 0;
         cudaMemGetInfo(&fr2, &to2);
-        const int64_t table_budget = o.kmer_table_bytes > 0 ? o.kmer_table_bytes
-                                                            : std::min<int64_t>(std::max<int64_t>(256ll << 20, (int64_t)(fr2 / 16)), 16ll << 30);
+        const int64_t max_entries = std::min<int64_t>((1ll << 32) - 1, std::max<int64_t>(8 * n, 1 << 16));   // no point in far more entries than rows
+        auto entries_of = [&](int k) { int64_t v = 1; for (int j = 0; j < k; ++j) { if (v > max_entries) return max_entries + 1; v *= sigma; } return v; };
         int K = 0;
-        int64_t entries = 1;
-        const int64_t max_entries = std::min<int64_t>(1ll << 31, std::max<int64_t>(4 * n, 1 << 16));   // no point in far more entries than rows
-        while (K < 16 && entries * sigma * 8 <= table_budget && entries * sigma <= max_entries) { entries *= sigma; ++K; }
-        if (sigma == 1) { K = std::min(K, 16); }
+        if (o.kmer_table_bytes > 0) {                                   // explicit budget
+            while (K < 16 && entries_of(K + 1) <= max_entries && entries_of(K + 1) * 8 <= o.kmer_table_bytes) ++K;
+        } else {
+            // the deepest table whose working set stays inside the TLB reach and a third of the free memory ...
+            for (int k = 16; k >= 2 && K == 0; --k) {
+                const int64_t en = entries_of(k);
+                if (en > max_entries || en * 8 > (int64_t)(fr2 / 3)) continue;
+                const bool saturating = d.ctx != nullptr && en >= n / 2;    // intervals are a few rows once the table has been consulted
+                const double ws = en * 8.0 + (d.ctx ? 32.0 * n : 0.0) + (saturating ? 0.0 : (double)rank_bytes + (d.isat && !d.ctx ? 20.0 * n : 0.0));
+                if (ws <= reach) K = k;
+            }
+            // ... else (the rest of the index is already beyond the reach) 256 MiB .. 16 GiB scaled to a sixteenth of the free memory
+            if (K == 0) {
+                const int64_t table_budget = std::min<int64_t>(std::max<int64_t>(256ll << 20, (int64_t)(fr2 / 16)), 16ll << 30);
+                while (K < 16 && entries_of(K + 1) <= std::min<int64_t>(max_entries, std::max<int64_t>(4 * n, 1 << 16)) && entries_of(K + 1) * 8 <= table_budget) ++K;
+            }
+        }
+        if (sigma == 1) K = std::min(K, 16);
         if (K >= 2) {
+            const int64_t entries = entries_of(K);
             void *tab = nullptr;
             e = cudaMalloc(&tab, (size_t)entries * 8); CU(e); ix->owned.push_back(tab);
             CU(build_kmer_table(d, ix->cfg, d_sym, (uint32_t)sigma, K, (uint2 *)tab, ix->stream));
@@ -257,9 +294,9 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
             ix->index_bytes += entries * 8;
         }
     }
-    // measured on B200 (profiles/r01_*): plain PLANES wants 4 lanes per 64-B block; WM, and PLANES once most fetches are the
-    // scalar SA/ISA/table loads of the accelerators, want 2 (more queries in flight per SM)
-    if (!o.lanes_per_query) ix->cfg.lanes = (layout == FMX_LAYOUT_PLANES && d.isat == nullptr) ? 4 : 2;
+    // two lanes per query: with the 256-bit load a 64-B rank block is one request from two lanes (as from four lanes with 128-bit
+    // loads), and twice as many queries are in flight per SM
+    if (!o.lanes_per_query) ix->cfg.lanes = 2;
     ix->accel_text = d.isat != nullptr;
     ix->kmer_k = d.kmer ? d.kmer_k : 0;
     CU(cudaStreamSynchronize(ix->stream));
@@ -392,6 +429,7 @@ int fmx_accel_info(const fmx_index *ix, int32_t *kmer_k, int32_t *text_shortcut)
     if (text_shortcut) *text_shortcut = ix->accel_text ? 1 : 0;
     return FMX_OK;
 }
+int fmx_ctx_depth(const fmx_index *ix) { return (ix && ix->d.ctx) ? ix->d.ctx_J : 0; }
 int fmx_info(const fmx_index *ix, int32_t *layout, int32_t *levels, int32_t *sigma, int64_t *index_bytes, int32_t *rate) {
     CHECK_IX(ix);
     if (layout) *layout = ix->cfg.layout;

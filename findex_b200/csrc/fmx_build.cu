@@ -331,6 +331,37 @@ cudaError_t build_isat(const uint32_t *d_isa, const uint8_t *d_text, const uint8
     return cudaGetLastError();
 }
 
+// ctx[r] (32 B) = { isa[sa[r]-j] for j = J-4..J, 96 bits = the J symbols T'[sa[r]-J .. sa[r]-1] in the isat packing }; positions before the
+// start of T' read as symbol 0 / row 0 (symbol 0 never equals a pattern symbol, which is dense code + 1 >= 1)
+__global__ void build_ctx_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ isa, const uint8_t *__restrict__ text,
+                                 const uint8_t *__restrict__ code, int64_t n, int bits, int J, uint4 *__restrict__ ctx) {
+    __shared__ uint8_t sc[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sc[i] = code[i];
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int64_t p = sa[r];
+    uint32_t row[5];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) { const int64_t q = p - (J - 4 + t); row[t] = q >= 0 ? isa[q] : 0u; }
+    unsigned long long lo = 0, hi = 0;
+    for (int k = 0; k < J; ++k) {
+        const int64_t q = p - J + k;
+        unsigned long long v = 0;
+        if (q >= 0) { const uint8_t t = text[q]; v = t ? (unsigned long long)sc[t] + 1ull : 0ull; }
+        const int o = k * bits;
+        if (o < 64) { lo |= v << o; if (o + bits > 64) hi |= v >> (64 - o); }
+        else hi |= v << (o - 64);
+    }
+    ctx[2 * r] = make_uint4(row[0], row[1], row[2], row[3]);
+    ctx[2 * r + 1] = make_uint4(row[4], (uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi);
+}
+cudaError_t build_ctx(const uint32_t *d_sa, const uint32_t *d_isa, const uint8_t *d_text, const uint8_t *d_code, int64_t n, int bits, int J,
+                      uint4 *d_ctx, cudaStream_t st) {
+    build_ctx_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_sa, d_isa, d_text, d_code, n, bits, J, d_ctx);
+    return cudaGetLastError();
+}
+
 cudaError_t build_full_sa(const DevIndex &ix, int layout, uint32_t *d_sa, uint32_t *d_isa, uint8_t *d_text, cudaStream_t st, std::string &err) {
     Chains ch;
     CK(prepare_chains(ix, layout, ch, st, err));
@@ -366,6 +397,7 @@ cudaError_t build_kmer_table(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d
     DevIndex plain = ix;                                // the table is filled by ordinary backward steps
     plain.kmer = nullptr;
     plain.isat = nullptr;
+    plain.ctx = nullptr;
     for (uint64_t o = 0; o < total; o += slice) {
         const uint64_t cnt = total - o < slice ? total - o : slice;
         gen_kmer_patterns_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_sym, sigma, K, o, cnt, d_pat);

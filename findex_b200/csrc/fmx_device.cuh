@@ -43,7 +43,16 @@ struct DevIndex {
     const uint4    *isat;       // per text position p: { isa[p], 96 bits of T'[p..] } — inverse SA and the text behind it in one 16-B fetch
     int32_t         isat_bits;  // bits per text symbol in isat: ceil(log2(sigma+1)); stored value = dense code + 1, 0 = '$' / past the end
     int32_t         isat_syms;  // symbols per entry = 96 / isat_bits  (bytes: 12, sigma <= 31: 19, DNA: 32)
+    // row-indexed context: ctx[r] = { isa[sa[r]-j] for j = ctx_J-4 .. ctx_J (5 words), 96 bits = the ctx_J symbols T'[sa[r]-ctx_J .. sa[r]-1]
+    // in the isat packing } — 32 B, one request: a row with ctx_J-4 <= remaining <= ctx_J pattern bytes finishes in ONE fetch, and a
+    // small interval is finished by looking at each of its rows (the rows whose text continues with the rest of the pattern map onto
+    // exactly the pattern's interval)
+    const uint4    *ctx;        // 2 x uint4 per row, or nullptr
+    int32_t         ctx_J;      // = isat_syms
 };
+
+constexpr uint32_t kCtxMaxRows = 8;    // intervals up to this many rows are finished through ctx instead of rank steps
+constexpr int      kCtxSpan = 5;       // remaining lengths ctx_J-4 .. ctx_J are covered
 
 struct SharedTables {
     uint32_t C[257];
@@ -56,10 +65,29 @@ __device__ __forceinline__ void load_tables(SharedTables &s, const DevIndex &ix)
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { s.base[i] = ix.base[i]; s.code[i] = ix.code[i]; }
 }
 
+// Index fetches.  Measured on B200 (tools/ldhint_bench.cu, profiles/r01_ldhint_*): what bounds random access is the number of
+// load REQUESTS (one per load instruction and 128-B line), ~46-47 G/s from 4 B up to 128 B per request, as long as the touched
+// footprint stays inside the ~64 GB TLB reach; a load without a prefetch-size hint makes the L2 pull 128 B from DRAM per miss,
+// `.L2::64B` pulls the 64 B that are used.  Hence: one request per fetched block (the 256-bit load moves 32 B per lane), 64-B hint.
 __device__ __forceinline__ uint4 ldg128(const uint4 *p) {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+// sm_100 256-bit load: 32 aligned bytes in one request
+__device__ __forceinline__ void ldg256(const uint4 *p, uint4 &a, uint4 &b) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ uint32_t ldg32(const uint32_t *p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg64(const uint2 *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
 }
 
@@ -79,8 +107,9 @@ template <int G>
 __device__ __forceinline__ LaneBlock<G> load_block(const uint4 *bv, uint32_t blk, int lane) {
     LaneBlock<G> r;
     const uint4 *p = bv + (uint64_t)blk * 4 + lane * (4 / G);
-#pragma unroll
-    for (int i = 0; i < 4 / G; ++i) r.v[i] = ldg128(p + i);
+    if constexpr (G == 4) r.v[0] = ldg128(p);                                   // four lanes x 16 B: one request
+    else if constexpr (G == 2) ldg256(p, r.v[0], r.v[1]);                         // two lanes x 32 B: one request
+    else { ldg256(p, r.v[0], r.v[1]); ldg256(p + 2, r.v[2], r.v[3]); }            // one lane: two requests
     return r;
 }
 
@@ -256,7 +285,7 @@ __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedT
                 idx = idx * ix.kmer_sigma + code;
             }
             if (ok) {
-                const uint2 v = ix.kmer[idx];
+                const uint2 v = ldg64(ix.kmer + idx);
                 sp = v.x; ep = v.y;
                 i -= ix.kmer_k;
                 done = true;
@@ -271,14 +300,61 @@ __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedT
             if (STATS) ++steps;
         }
     }
+    bool noctx = (ix.ctx == nullptr);
     for (;;) {
         const bool go = (i >= 0) && (sp < ep);
         if (go) {
             bool stepped = false;
-            if (!noshort && (ep - sp) == 1u && i >= 2 && i < ix.isat_syms) {
+            const int rem = i + 1;
+            if (!noctx && (ep - sp) <= kCtxMaxRows && rem <= ix.ctx_J && rem > ix.ctx_J - kCtxSpan) {
+                // every row of the interval is looked at through its 32-byte context entry: the rows whose text goes on with the
+                // remaining `rem` pattern bytes map onto exactly the pattern's interval (their targets isa[sa[r]-rem] are its rows)
+                const uint32_t bits = (uint32_t)ix.isat_bits;
+                unsigned long long qlo = 0, qhi = 0;                 // the remaining pattern bytes in the entry's packing
+                bool zero = false, absent = false;
+                for (int k = 0; k < rem; ++k) {
+                    const uint32_t pc = pat(k), cd = tb.code[pc];
+                    zero = zero || (pc == 0);
+                    absent = absent || (cd == (uint32_t)kCodeAbsent);
+                    const unsigned long long v = (unsigned long long)((cd + 1u) & ((1u << bits) - 1u));
+                    const uint32_t o = (uint32_t)k * bits;
+                    if (o < 64) { qlo |= v << o; if (o + bits > 64) qhi |= v >> (64 - o); }
+                    else qhi |= v << (o - 64);
+                }
+                if (zero) noctx = true;                               // byte 0: the '$' row wraps the text, take the ordinary steps
+                else {
+                    const uint32_t sh = (uint32_t)(ix.ctx_J - rem) * bits, nb = (uint32_t)rem * bits;   // nb >= 1
+                    const unsigned long long mlo = nb >= 64 ? ~0ull : ((1ull << nb) - 1ull);
+                    const unsigned long long mhi = nb <= 64 ? 0ull : ((1ull << (nb - 64)) - 1ull);
+                    const int rw = rem - (ix.ctx_J - kCtxSpan + 1);   // which of the five row words
+                    uint32_t best = 0xFFFFFFFFu, cnt = 0;
+                    if (!absent) {
+                        for (uint32_t r = sp + (uint32_t)lane; r < ep; r += G) {
+                            uint4 a, b;
+                            ldg256(ix.ctx + (uint64_t)r * 2, a, b);
+                            const unsigned long long elo = ((unsigned long long)b.z << 32) | b.y, ehi = b.w;
+                            unsigned long long lo, hi;
+                            if (sh == 0) { lo = elo; hi = ehi; }
+                            else if (sh < 64) { lo = (elo >> sh) | (ehi << (64 - sh)); hi = ehi >> sh; }
+                            else { lo = ehi >> (sh - 64); hi = 0; }
+                            if ((((lo ^ qlo) & mlo) | ((hi ^ qhi) & mhi)) == 0ull) {
+                                const uint32_t row = rw == 0 ? a.x : rw == 1 ? a.y : rw == 2 ? a.z : rw == 3 ? a.w : b.x;
+                                best = row < best ? row : best;
+                                ++cnt;
+                            }
+                        }
+                    }
+                    if (STATS && lane == 0) { touched += absent ? 0u : ep - sp; steps += rem; }
+                    if (G >= 2) { best = min(best, __shfl_xor_sync(gmask, best, 1)); cnt += __shfl_xor_sync(gmask, cnt, 1); }
+                    if (G >= 4) { best = min(best, __shfl_xor_sync(gmask, best, 2)); cnt += __shfl_xor_sync(gmask, cnt, 2); }
+                    if (cnt) { sp = best; ep = best + cnt; } else { sp = 0; ep = 0; }
+                    i = -1;
+                    stepped = true;
+                }
+            }
+            if (!stepped && !noshort && (ep - sp) == 1u && i >= 2 && i < ix.isat_syms) {
                 // one 16-byte entry holds isa[p] and the next isat_syms symbols of T': the whole shortcut is sa[row] -> isat[sa[row]-rem]
-                const int rem = i + 1;
-                const uint32_t q = ix.sa[sp];
+                const uint32_t q = ldg32(ix.sa + sp);
                 const bool fits = q >= (uint32_t)rem;
                 const uint32_t b0 = fits ? q - (uint32_t)rem : 0u;
                 const uint4 e = ldg128(ix.isat + b0);

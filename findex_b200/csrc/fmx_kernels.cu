@@ -22,8 +22,8 @@ namespace fmx {
 // =====================================================================================================
 // K1: count
 // =====================================================================================================
-template <int G, int LAYOUT, bool STATS, typename OutT>
-__global__ void __launch_bounds__(kThreads, (G == 1) ? 4 : 8)
+template <int G, int LAYOUT, bool STATS, typename OutT, int MINB = ((G == 1) ? 4 : 8)>
+__global__ void __launch_bounds__(kThreads, MINB)
 count_fixed_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, int len, long long m,
                    OutT *__restrict__ sp_out, OutT *__restrict__ ep_out, unsigned long long *stats, const __grid_constant__ PeerSinks sinks) {
     __shared__ SharedTables tb;
@@ -470,6 +470,10 @@ cudaError_t launch_count_fixed(const DevIndex &ix, LaunchCfg cfg, const uint8_t 
             auto k = count_fixed_kernel<G, LAY, false, long long>;                                                    \
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
             k<<<grid_for(m, G), kThreads, smem, st>>>(ix, d_pat, len, m, (long long *)d_sp, (long long *)d_ep, nullptr, sinks); \
+        } else if (cfg.min_blocks == 4 || cfg.min_blocks == 6) {            /* occupancy experiment (FMX_MINB) */          \
+            auto k = cfg.min_blocks == 4 ? count_fixed_kernel<G, LAY, false, uint32_t, 4> : count_fixed_kernel<G, LAY, false, uint32_t, 6>; \
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
+            k<<<grid_for(m, G), kThreads, smem, st>>>(ix, d_pat, len, m, (uint32_t *)d_sp, (uint32_t *)d_ep, nullptr, sinks); \
         } else {                                                                                                      \
             auto k = count_fixed_kernel<G, LAY, false, uint32_t>;                                                     \
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \

@@ -47,6 +47,8 @@ extern "C" {
 #define FMX_ACCEL_AUTO      0
 #define FMX_ACCEL_KMER      1   /* table of (sp,ep) after the first k steps, k = max with sigma^k*8 B <= kmer_table_bytes */
 #define FMX_ACCEL_TEXT      2   /* full SA + {inverse SA, 96 bits of text} entries (20n bytes): singleton intervals finish in 2 fetches; locate is 1 fetch */
+#define FMX_ACCEL_CTX       4   /* (implies TEXT) 32-byte row contexts { isa[sa[r]-j], j = J-4..J ; the J symbols before sa[r] }: an interval of <= 8 rows
+                                   with J-4..J pattern bytes left finishes in one fetch per row (J = 12 for byte alphabets, 19 for sigma <= 31, 32 for DNA) */
 #define FMX_ACCEL_NONE      8   /* plain backward search only                                                */
 
 typedef struct fmx_index fmx_index;     /* opaque; library-owned until fmx_close  */
@@ -59,8 +61,9 @@ typedef struct fmx_opts {
     int32_t  require_fm;        /* 1 = fail like the reference when <base>.fm is absent                  */
     int64_t  max_index_bytes;   /* budget for FMX_LAYOUT_AUTO; 0 = default                               */
     int32_t  lanes_per_query;   /* 0 = default; 1, 2 or 4 lanes cooperate on one 64-B rank block         */
-    int32_t  accel;             /* FMX_ACCEL_* bit mask; 0 = auto (both when they fit the memory budget)   */
-    int64_t  kmer_table_bytes;  /* budget of the k-mer table; 0 = auto (256 MiB .. 16 GiB, a sixteenth of free memory) */
+    int32_t  accel;             /* FMX_ACCEL_* bit mask; 0 = auto (all that fit the memory budget)          */
+    int64_t  kmer_table_bytes;  /* budget of the k-mer table; 0 = auto: the deepest table that keeps what a count query touches inside
+                                   the ~64 GB TLB reach, else 256 MiB .. 16 GiB (a sixteenth of free memory)     */
 } fmx_opts;
 
 void        fmx_opts_default(fmx_opts *o);
@@ -84,6 +87,7 @@ int     fmx_info(const fmx_index *ix, int32_t *layout, int32_t *levels, int32_t 
                  int64_t *index_bytes, int32_t *sa_sample_rate);
 
 int     fmx_accel_info(const fmx_index *ix, int32_t *kmer_k, int32_t *text_shortcut);   /* accelerators in effect */
+int     fmx_ctx_depth(const fmx_index *ix);                  /* J of the row contexts (FMX_ACCEL_CTX), 0 = not built */
 
 /* ---- occ(c,key)  M/bwtmerger.scala:354-375  (number of c in BWT[0..key], key=-1 -> 0) --------------- */
 int fmx_occ_batch(fmx_index *ix, const uint8_t *c, const int64_t *key, int64_t m, int64_t *out);

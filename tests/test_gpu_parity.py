@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 LAYOUTS = [fx.LAYOUT_WM, fx.LAYOUT_PLANES]
 LANES = [1, 2, 4]
 CFGS = [(l, g) for l in LAYOUTS for g in LANES]
-ACCELS = [fx.ACCEL_AUTO, fx.ACCEL_NONE, fx.ACCEL_KMER, fx.ACCEL_TEXT]
+ACCELS = [fx.ACCEL_AUTO, fx.ACCEL_NONE, fx.ACCEL_KMER, fx.ACCEL_TEXT, fx.ACCEL_CTX]
 
 
 def _ids(v):
@@ -162,22 +162,23 @@ def test_count_parity_small(ref_dir, cfg, accel):
     o = fo.OracleIndex.load(os.path.join(ref_dir, "test.cmp"), big_endian=False)
     g = _open(os.path.join(ref_dir, "test.cmp.bwt"), cfg, accel=accel)
     info = g.info()
-    assert info["text_shortcut"] == (accel in (fx.ACCEL_AUTO, fx.ACCEL_TEXT)) and (info["kmer_k"] >= 2) == (accel in (fx.ACCEL_AUTO, fx.ACCEL_KMER))
+    assert info["text_shortcut"] == (accel in (fx.ACCEL_AUTO, fx.ACCEL_TEXT, fx.ACCEL_CTX)) and (info["kmer_k"] >= 2) == (accel in (fx.ACCEL_AUTO, fx.ACCEL_KMER))
+    assert (info["ctx_depth"] > 0) == (accel in (fx.ACCEL_AUTO, fx.ACCEL_CTX))
     rng = np.random.default_rng(11)
     tprime = text[::-1]
     zero_cases = [b"", b"\0", b"a\0", bytes([200]), b"zzzzzzzzzzzzzzzzzzzzzzzzz",
                   tprime[-9:] + b"\0",                    # end of T' followed by '$': a real hit at row 0's neighbourhood
                   b"\0" + tprime[:9],                     # '$' then the start of T': the cyclic wrap the BWT allows -> row 0
                   tprime[100:106] + b"\0" + tprime[107:113], b"\0\0\0\0\0", tprime[:12], tprime[-12:], tprime[1:14]]
-    pats = _patterns(text, rng, 3000, 16) + zero_cases
+    pats = _patterns(text, rng, 3000, 16) + _patterns(text, rng, 1500, 40) + zero_cases
     sp, ep = g.count_batch(pats)
     for i, p in enumerate(pats):
         r = o.search(p)
         assert (int(sp[i]), int(ep[i])) == (r if r else (0, 0)), p
     assert g.search(b"") == (0, o.n)
     # fixed-length fast path, incl. ragged tail of the last CTA and odd lengths
-    for ln in (1, 3, 16, 21):
-        arr = np.frombuffer(b"".join(p.ljust(ln, b"q")[:ln] for p in pats[:2999]), np.uint8).reshape(-1, ln)
+    for ln in (1, 3, 12, 16, 21, 27):
+        arr = np.frombuffer(b"".join(p.ljust(ln, b"q")[:ln] for p in pats[:4499] if len(p) >= min(ln, 9)), np.uint8).reshape(-1, ln)
         sp, ep = g.count_fixed(arr)
         osp, oep = o.count_batch(arr.reshape(-1), np.arange(0, arr.size + 1, ln, dtype=np.int64))
         assert np.array_equal(sp, osp) and np.array_equal(ep, oep)
