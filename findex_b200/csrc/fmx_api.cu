@@ -183,7 +183,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     DevIndex &d = ix->d;
     d.blocks = (const uint4 *)blocks; d.stride = (uint64_t)nblk; d.bwt = d_bwt; d.C = d_C; d.base = d_base; d.code = d_code;
     d.bm = nullptr;
-    d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isat = nullptr; d.isat_bits = 8; d.isat_syms = 12; d.ctx = nullptr; d.ctx_J = 0;
+    d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isat = nullptr; d.isat_bits = 8; d.isat_syms = 12; d.ctx = nullptr; d.ctx_J = 0; d.ctx_raw = 0;
     d.mark = nullptr; d.samples = nullptr; d.n = (uint32_t)n; d.eof = (uint32_t)eof; d.layout = layout; d.levels = levels;
     for (int l = 0; l < 8; ++l) d.z[l] = z[l];
 
@@ -250,8 +250,9 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
             if (e != cudaSuccess) { cudaGetLastError(); if (accel & FMX_ACCEL_CTX) return fail(FMX_E_CUDA, "cannot allocate %lld bytes for the row contexts", (long long)n * 32); }
             else {
                 ix->owned.push_back(ctx);
-                CU(build_ctx((const uint32_t *)sa, isa, text, d_code, n, ibits, isyms, (uint4 *)ctx, ix->stream));
-                d.ctx = (const uint4 *)ctx; d.ctx_J = isyms;
+                const int raw = ibits == 8 ? 1 : 0;
+                CU(build_ctx((const uint32_t *)sa, isa, text, d_code, n, ibits, isyms, raw, (uint4 *)ctx, ix->stream));
+                d.ctx = (const uint4 *)ctx; d.ctx_J = isyms; d.ctx_raw = raw;
                 ix->index_bytes += 32 * n;
             }
         }
@@ -296,7 +297,13 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     }
     // two lanes per query: with the 256-bit load a 64-B rank block is one request from two lanes (as from four lanes with 128-bit
     // loads), and twice as many queries are in flight per SM
-    if (!o.lanes_per_query) ix->cfg.lanes = 2;
+    if (!o.lanes_per_query) {
+        ix->cfg.lanes = 2;
+        // count kernels: one lane per query once a deep table + row contexts answer most queries in two single-lane requests
+        // (measured on cfg 2: 19.96 vs 18.69 G q/s; the kernel at two lanes is issue-bound, 80 % of the issue slots)
+        const bool saturating = d.ctx != nullptr && d.kmer != nullptr && std::pow((double)sigma, d.kmer_k) >= n / 2.0;
+        ix->cfg.count_lanes = saturating ? 1 : 0;
+    }
     ix->accel_text = d.isat != nullptr;
     ix->kmer_k = d.kmer ? d.kmer_k : 0;
     CU(cudaStreamSynchronize(ix->stream));
@@ -444,6 +451,7 @@ int fmx_set_lanes(fmx_index *ix, int32_t lanes) {
     if (lanes != 1 && lanes != 2 && lanes != 4) return fail(FMX_E_ARG, "lanes_per_query must be 1, 2 or 4");
     std::lock_guard<std::mutex> lk(ix->mu);
     ix->cfg.lanes = lanes;
+    ix->cfg.count_lanes = 0;
     return FMX_OK;
 }
 int fmx_set_chunk(fmx_index *ix, int64_t queries_per_chunk) {
@@ -475,7 +483,7 @@ int fmx_host_free(void *p) {
     if (p) CU(cudaFreeHost(p));
     return FMX_OK;
 }
-int fmx_get_lanes(const fmx_index *ix) { return ix ? ix->cfg.lanes : 0; }
+int fmx_get_lanes(const fmx_index *ix) { return ix ? (ix->cfg.count_lanes ? ix->cfg.count_lanes : ix->cfg.lanes) : 0; }
 double fmx_last_kernel_ms(const fmx_index *ix) { return ix ? ix->last_ms : 0.0; }
 int64_t fmx_last_kernel_launches(const fmx_index *ix) { return ix ? ix->last_launches : 0; }
 

@@ -332,9 +332,10 @@ cudaError_t build_isat(const uint32_t *d_isa, const uint8_t *d_text, const uint8
 }
 
 // ctx[r] (32 B) = { isa[sa[r]-j] for j = J-4..J, 96 bits = the J symbols T'[sa[r]-J .. sa[r]-1] in the isat packing }; positions before the
-// start of T' read as symbol 0 / row 0 (symbol 0 never equals a pattern symbol, which is dense code + 1 >= 1)
+// start of T' read as symbol 0 / row 0 (symbol 0 never equals a pattern symbol, which is dense code + 1 >= 1); raw = 1 (8-bit symbols):
+// the text bytes themselves are stored (0 = '$' / before the start; patterns with a zero byte never take this path)
 __global__ void build_ctx_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ isa, const uint8_t *__restrict__ text,
-                                 const uint8_t *__restrict__ code, int64_t n, int bits, int J, uint4 *__restrict__ ctx) {
+                                 const uint8_t *__restrict__ code, int64_t n, int bits, int J, int raw, uint4 *__restrict__ ctx) {
     __shared__ uint8_t sc[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sc[i] = code[i];
     __syncthreads();
@@ -348,7 +349,7 @@ __global__ void build_ctx_kernel(const uint32_t *__restrict__ sa, const uint32_t
     for (int k = 0; k < J; ++k) {
         const int64_t q = p - J + k;
         unsigned long long v = 0;
-        if (q >= 0) { const uint8_t t = text[q]; v = t ? (unsigned long long)sc[t] + 1ull : 0ull; }
+        if (q >= 0) { const uint8_t t = text[q]; v = raw ? (unsigned long long)t : (t ? (unsigned long long)sc[t] + 1ull : 0ull); }
         const int o = k * bits;
         if (o < 64) { lo |= v << o; if (o + bits > 64) hi |= v >> (64 - o); }
         else hi |= v << (o - 64);
@@ -357,8 +358,8 @@ __global__ void build_ctx_kernel(const uint32_t *__restrict__ sa, const uint32_t
     ctx[2 * r + 1] = make_uint4(row[4], (uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi);
 }
 cudaError_t build_ctx(const uint32_t *d_sa, const uint32_t *d_isa, const uint8_t *d_text, const uint8_t *d_code, int64_t n, int bits, int J,
-                      uint4 *d_ctx, cudaStream_t st) {
-    build_ctx_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_sa, d_isa, d_text, d_code, n, bits, J, d_ctx);
+                      int raw, uint4 *d_ctx, cudaStream_t st) {
+    build_ctx_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_sa, d_isa, d_text, d_code, n, bits, J, raw, d_ctx);
     return cudaGetLastError();
 }
 

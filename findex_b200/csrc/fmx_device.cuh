@@ -49,6 +49,34 @@ struct DevIndex {
     // exactly the pattern's interval)
     const uint4    *ctx;        // 2 x uint4 per row, or nullptr
     int32_t         ctx_J;      // = isat_syms
+    int32_t         ctx_raw;    // 1 (byte alphabets, 8-bit symbols): the 12 symbols are the raw text bytes, so pattern words compare directly
+};
+
+// Pattern accessors handed to search_pattern: operator()(i) = byte i; word(w) = bytes 4w..4w+3 packed little-endian (bytes at or
+// beyond `len` read as anything — callers mask them).
+struct SmemPattern {                                   // pattern staged in shared memory
+    const uint8_t *p;
+    int len;
+    bool aligned;                                      // p is 4-byte aligned: words are single LDS.32
+    __device__ __forceinline__ uint32_t operator()(int i) const { return p[i]; }
+    __device__ __forceinline__ uint32_t word(int w) const {
+        if (aligned) return reinterpret_cast<const uint32_t *>(p)[w];
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { const int i = 4 * w + b; if (i < len) v |= (uint32_t)p[i] << (8 * b); }
+        return v;
+    }
+};
+struct GlobalPattern {                                 // pattern read from global memory (variable-length batches)
+    const uint8_t *p;
+    int len;
+    __device__ __forceinline__ uint32_t operator()(int i) const { return (uint32_t)__ldg(p + i); }
+    __device__ __forceinline__ uint32_t word(int w) const {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { const int i = 4 * w + b; if (i < len) v |= (uint32_t)__ldg(p + i) << (8 * b); }
+        return v;
+    }
 };
 
 constexpr uint32_t kCtxMaxRows = 8;    // intervals up to this many rows are finished through ctx instead of rank steps
@@ -312,14 +340,22 @@ __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedT
                 const uint32_t bits = (uint32_t)ix.isat_bits;
                 unsigned long long qlo = 0, qhi = 0;                 // the remaining pattern bytes in the entry's packing
                 bool zero = false, absent = false;
-                for (int k = 0; k < rem; ++k) {
-                    const uint32_t pc = pat(k), cd = tb.code[pc];
-                    zero = zero || (pc == 0);
-                    absent = absent || (cd == (uint32_t)kCodeAbsent);
-                    const unsigned long long v = (unsigned long long)((cd + 1u) & ((1u << bits) - 1u));
-                    const uint32_t o = (uint32_t)k * bits;
-                    if (o < 64) { qlo |= v << o; if (o + bits > 64) qhi |= v >> (64 - o); }
-                    else qhi |= v << (o - 64);
+                if (ix.ctx_raw) {                                     // raw bytes (rem is 8..12): three pattern words, no translation;
+                    qlo = ((unsigned long long)pat.word(1) << 32) | pat.word(0);      // a byte that is absent from the text just never matches
+                    qhi = rem > 8 ? pat.word(2) : 0u;
+                    const unsigned long long keep = rem >= 12 ? 0xFFFFFFFFull : ((1ull << (8 * (rem - 8))) - 1ull);
+                    const unsigned long long h = (qhi & keep) | ~keep;                  // bytes past the pattern must not look like zeros
+                    zero = (((qlo - 0x0101010101010101ull) & ~qlo) | ((h - 0x0101010101010101ull) & ~h)) & 0x8080808080808080ull;
+                } else {
+                    for (int k = 0; k < rem; ++k) {
+                        const uint32_t pc = pat(k), cd = tb.code[pc];
+                        zero = zero || (pc == 0);
+                        absent = absent || (cd == (uint32_t)kCodeAbsent);
+                        const unsigned long long v = (unsigned long long)((cd + 1u) & ((1u << bits) - 1u));
+                        const uint32_t o = (uint32_t)k * bits;
+                        if (o < 64) { qlo |= v << o; if (o + bits > 64) qhi |= v >> (64 - o); }
+                        else qhi |= v << (o - 64);
+                    }
                 }
                 if (zero) noctx = true;                               // byte 0: the '$' row wraps the text, take the ordinary steps
                 else {

@@ -22,7 +22,7 @@ namespace fmx {
 // =====================================================================================================
 // K1: count
 // =====================================================================================================
-template <int G, int LAYOUT, bool STATS, typename OutT, int MINB = ((G == 1) ? 4 : 8)>
+template <int G, int LAYOUT, bool STATS, typename OutT, int MINB = ((G == 1) ? 6 : 8)>
 __global__ void __launch_bounds__(kThreads, MINB)
 count_fixed_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, int len, long long m,
                    OutT *__restrict__ sp_out, OutT *__restrict__ ep_out, unsigned long long *stats, const __grid_constant__ PeerSinks sinks) {
@@ -49,9 +49,8 @@ count_fixed_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restric
 
     const int g = threadIdx.x / G;
     const bool active = g < nq;
-    const uint8_t *p = spat + g * len;
     uint32_t sp, ep, touched = 0, steps = 0;
-    search_pattern<G, LAYOUT, STATS>(ix, tb, [p](int i) { return (uint32_t)p[i]; }, len, active, sp, ep, touched, steps);
+    search_pattern<G, LAYOUT, STATS>(ix, tb, SmemPattern{spat + g * len, len, (len & 3) == 0}, len, active, sp, ep, touched, steps);
     if (active && (threadIdx.x % G) == 0) {
         const bool hit = sp < ep;
         sp_out[q0 + g] = hit ? (OutT)sp : (OutT)0;
@@ -105,9 +104,9 @@ count_fixed_persistent_kernel(const __grid_constant__ DevIndex ix, const uint8_t
         __syncwarp();
         const int g = lane / G;
         const bool active = g < nq;
-        const uint8_t *p = wpat + g * len;
         uint32_t sp, ep, touched = 0, steps = 0;
-        search_pattern<G, LAYOUT, false>(ix, tb, [p](int i) { return (uint32_t)p[i]; }, len, active, sp, ep, touched, steps);
+        search_pattern<G, LAYOUT, false>(ix, tb, SmemPattern{wpat + g * len, len, (len & 3) == 0 && (reinterpret_cast<uintptr_t>(wpat) & 3) == 0},
+                                         len, active, sp, ep, touched, steps);
         if (active && (lane % G) == 0) {
             const bool hit = sp < ep;
             sp_out[q0 + g] = hit ? (OutT)sp : (OutT)0;
@@ -135,8 +134,7 @@ count_var_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict_
     long long lo = 0, hi = 0;
     if (active) { lo = off[q]; hi = off[q + 1]; }
     uint32_t sp, ep, touched = 0, steps = 0;
-    const uint8_t *p = pat + lo;
-    search_pattern<G, LAYOUT, false>(ix, tb, [p](int i) { return (uint32_t)__ldg(p + i); }, (int)(hi - lo), active, sp, ep, touched, steps);
+    search_pattern<G, LAYOUT, false>(ix, tb, GlobalPattern{pat + lo, (int)(hi - lo)}, (int)(hi - lo), active, sp, ep, touched, steps);
     if (active && (threadIdx.x % G) == 0) {
         const bool hit = sp < ep;
         sp_out[q] = hit ? (long long)sp : 0;
@@ -446,6 +444,7 @@ static inline unsigned grid_for(int64_t items, int lanes) {
 cudaError_t launch_count_fixed(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_pat, int len, int64_t m, void *d_sp,
                                void *d_ep, bool out64, unsigned long long *d_stats, cudaStream_t st, const PeerSinks *sinks_or_null) {
     if (m <= 0) return cudaSuccess;
+    if (cfg.count_lanes) cfg.lanes = cfg.count_lanes;
     PeerSinks sinks{};
     if (sinks_or_null) sinks = *sinks_or_null;
     const size_t smem = (size_t)(kThreads / cfg.lanes) * (size_t)(len > 0 ? len : 1);
@@ -470,8 +469,10 @@ cudaError_t launch_count_fixed(const DevIndex &ix, LaunchCfg cfg, const uint8_t 
             auto k = count_fixed_kernel<G, LAY, false, long long>;                                                    \
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
             k<<<grid_for(m, G), kThreads, smem, st>>>(ix, d_pat, len, m, (long long *)d_sp, (long long *)d_ep, nullptr, sinks); \
-        } else if (cfg.min_blocks == 4 || cfg.min_blocks == 6) {            /* occupancy experiment (FMX_MINB) */          \
-            auto k = cfg.min_blocks == 4 ? count_fixed_kernel<G, LAY, false, uint32_t, 4> : count_fixed_kernel<G, LAY, false, uint32_t, 6>; \
+        } else if (cfg.min_blocks >= 4 && cfg.min_blocks <= 8) {            /* occupancy experiment (FMX_MINB) */          \
+            auto k = cfg.min_blocks == 4 ? count_fixed_kernel<G, LAY, false, uint32_t, 4> : cfg.min_blocks == 5 ? count_fixed_kernel<G, LAY, false, uint32_t, 5> : \
+                     cfg.min_blocks == 6 ? count_fixed_kernel<G, LAY, false, uint32_t, 6> : cfg.min_blocks == 7 ? count_fixed_kernel<G, LAY, false, uint32_t, 7> : \
+                     count_fixed_kernel<G, LAY, false, uint32_t, 8>;                                                  \
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
             k<<<grid_for(m, G), kThreads, smem, st>>>(ix, d_pat, len, m, (uint32_t *)d_sp, (uint32_t *)d_ep, nullptr, sinks); \
         } else {                                                                                                      \
@@ -488,6 +489,7 @@ cudaError_t launch_count_fixed(const DevIndex &ix, LaunchCfg cfg, const uint8_t 
 cudaError_t launch_count_var(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_pat, const int64_t *d_off, int64_t m,
                              int64_t *d_sp, int64_t *d_ep, cudaStream_t st) {
     if (m <= 0) return cudaSuccess;
+    if (cfg.count_lanes) cfg.lanes = cfg.count_lanes;
 #define CALL(G, LAY) count_var_kernel<G, LAY><<<grid_for(m, G), kThreads, 0, st>>>(ix, d_pat, (const long long *)d_off, m, (long long *)d_sp, (long long *)d_ep)
     FMX_DISPATCH(cfg, CALL);
 #undef CALL

@@ -199,7 +199,7 @@ int fmx_set_l2_fetch_granularity(int32_t bytes, int32_t *effective);
 int fmx_set_chunk(fmx_index *ix, int64_t queries_per_chunk);
 /* Re-selects how many lanes (1, 2 or 4) cooperate on one 64-B rank block for subsequent calls.           */
 int fmx_set_lanes(fmx_index *ix, int32_t lanes_per_query);
-int fmx_get_lanes(const fmx_index *ix);
+int fmx_get_lanes(const fmx_index *ix);                      /* lanes per query of the count kernels (may differ from the other kernels' by default) */
 double fmx_last_kernel_ms(const fmx_index *ix);
 int64_t fmx_last_kernel_launches(const fmx_index *ix);
 

@@ -65,7 +65,8 @@ def main():
         blocks, steps = g.count_fixed_stats(pats[:2_000_000])
         emit(what="stats", config=name, requests_per_query=blocks / 2e6, steps_per_query=steps / 2e6)
         for lanes in [int(x) for x in args.lanes.split(",")]:
-            g.set_lanes(lanes)
+            if lanes:
+                g.set_lanes(lanes)
             for _ in range(3):
                 g.count_fixed_dev(d_pat.data_ptr(), args.len, args.m, d_sp.data_ptr(), d_ep.data_ptr(), st)
             torch.cuda.synchronize()
