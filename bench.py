@@ -498,7 +498,7 @@ def regex_leg(args, g, text, world, rank, dev):
             "report": {"value": world * mr * steps / wall, "unit": "regexes/s", "what": "fmx_regex_set_search end to end (device-resident regex set, host result buffers), "
                        "Glushkov engine, caps off; device time alone in device_value", "device_value": world * mr / (float(np.mean(kms)) * 1e-3), "regexes_per_gpu": mr,
                        "rejected_by_compiler": len(rxs) - mr, "steps": steps, "ms_per_step": wall / steps * 1e3, "kernel_ms_per_step": float(np.mean(kms)),
-                       "level_launches_per_step": int(g.last_kernel_launches()), "result_triples": total, "compile_s_once": compile_s, "set_upload_s_once": upload_s}}
+                       "traversal_launches_per_step": int(g.last_kernel_launches()), "levels_per_step": int(g.last_regex_levels()), "result_triples": total, "compile_s_once": compile_s, "set_upload_s_once": upload_s}}
 
 
 def cpu_baseline(args, base, pats, sp, ep, cnt, regex=None):

@@ -35,7 +35,7 @@ struct fmx_index {
     int64_t nblk = 0, index_bytes = 0, n_samples = 0;
     std::vector<void *> owned;         // device allocations freed at close
     double last_ms = 0.0;
-    int64_t last_launches = 0, total_launches = 0;
+    int64_t last_launches = 0, total_launches = 0, last_levels = 0;
     std::mutex mu;
 };
 
@@ -486,6 +486,7 @@ int fmx_host_free(void *p) {
 int fmx_get_lanes(const fmx_index *ix) { return ix ? (ix->cfg.count_lanes ? ix->cfg.count_lanes : ix->cfg.lanes) : 0; }
 double fmx_last_kernel_ms(const fmx_index *ix) { return ix ? ix->last_ms : 0.0; }
 int64_t fmx_last_kernel_launches(const fmx_index *ix) { return ix ? ix->last_launches : 0; }
+int64_t fmx_last_regex_levels(const fmx_index *ix) { return ix ? ix->last_levels : 0; }
 
 // pos2char: bwtmerger.scala:376-385 (bucketStarts0 = prefix sums of the raw counts)
 int fmx_pos2char(const fmx_index *ix, int64_t key, int32_t *c) {
@@ -953,6 +954,8 @@ struct fmx_regex_set {
     int device = 0;
     int64_t m = 0;
     size_t n_states = 0, n_fol = 0, n_first = 0;
+    size_t free_bytes = 0;             // free device memory when the set was first searched (bounds the frontier buffers)
+    int64_t front_hint = 0;            // largest frontier the last search of this set saw: the next search sizes its buffers for it
     void *d_c = nullptr, *d_last = nullptr, *d_rx = nullptr, *d_fo = nullptr, *d_f = nullptr, *d_first = nullptr;
 };
 
@@ -1027,61 +1030,65 @@ int fmx_regex_set_search(fmx_index *ix, fmx_regex_set *set, int64_t cap_total, i
     DBuf d_res(st), d_tmp(st), d_cnt(st);
     RegexTables rt{(const uint8_t *)set->d_c, (const uint8_t *)set->d_last, (const uint32_t *)set->d_rx, (const uint32_t *)set->d_fo, (const uint32_t *)set->d_f};
 
-    size_t fr = 0, to = 0;
-    cudaMemGetInfo(&fr, &to);
-    // frontier buffers start small and grow on demand (a level that overflows is replayed), bounded by an eighth of
-    // the free device memory each
+    if (set->free_bytes == 0) { size_t fr0 = 0, to0 = 0; cudaMemGetInfo(&fr0, &to0); set->free_bytes = fr0; }   // once per set: the query costs ~0.1 ms
+    const size_t fr = set->free_bytes;
+    // two ping-pong frontier buffers; they start small and are regrown (and the traversal rerun) when a level outgrows them,
+    // bounded by an eighth of the free device memory each
     const int64_t n_first = (int64_t)set->n_first;
     const int64_t max_front = std::max<int64_t>(std::min<int64_t>((int64_t)(fr / 8 / sizeof(FrontierItem)), 1ll << 28), n_first);
-    int64_t cap_cur = std::min<int64_t>(max_front, std::max<int64_t>(n_first, 1 << 16));
-    int64_t cap_nxt = std::min<int64_t>(max_front, std::max<int64_t>(n_first * 4, 1 << 20));
+    int64_t cap = std::min<int64_t>(max_front, std::max<int64_t>(std::max<int64_t>(n_first * 16, 1 << 20), set->front_hint + set->front_hint / 8));
     int64_t cap_res = std::max<int64_t>(cap_total, 1 << 16);
     void *cur = nullptr, *nxt = nullptr;
-    CU(cudaMallocAsync(&cur, cap_cur * sizeof(FrontierItem), st)); CU(cudaMallocAsync(&nxt, cap_nxt * sizeof(FrontierItem), st));
+    CU(cudaMallocAsync(&cur, cap * sizeof(FrontierItem), st)); CU(cudaMallocAsync(&nxt, cap * sizeof(FrontierItem), st));
     struct Guard { void **a, **b; cudaStream_t s; ~Guard() { if (*a) cudaFreeAsync(*a, s); if (*b) cudaFreeAsync(*b, s); } } guard{&cur, &nxt, st};
-    CU(d_res.alloc(cap_res * sizeof(RegexResult))); CU(d_cnt.alloc(16));
+    CU(d_res.alloc(cap_res * sizeof(RegexResult))); CU(d_cnt.alloc(64));
     Timed t(ix);
-    CU(launch_init_frontier((const uint32_t *)set->d_first, n_first, (uint32_t)ix->n, (FrontierItem *)cur, st));   // StatePoint(0,0,sa.n,_)
-    int64_t n_in = n_first, launches = 1, level = 0;
-    unsigned long long h[2] = {0, 0}, res_before = 0;
-    while (n_in > 0) {
-        if (++level > ix->n + 1) return fail(FMX_E_LIMIT, "regex traversal deeper than the text");
-        for (;;) {
-            const unsigned long long reset[2] = {0ull, res_before};         // next-frontier counter := 0, results := value before this level
-            CU(cudaMemcpyAsync(d_cnt.p, reset, 16, cudaMemcpyHostToDevice, st));
-            CU(launch_regex_level(ix->d, ix->cfg, rt, (const FrontierItem *)cur, n_in, (FrontierItem *)nxt, cap_nxt, d_res.as<RegexResult>(), cap_res,
-                                  d_cnt.as<unsigned long long>(), st));
-            ++launches;
-            CU(cudaMemcpyAsync(h, d_cnt.p, 16, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            if ((int64_t)h[0] <= cap_nxt) break;
-            if ((int64_t)h[0] > max_front)
-                return fail(FMX_E_LIMIT, "regex frontier of %llu items exceeds the device budget of %lld; split the batch", h[0], (long long)max_front);
-            CU(cudaFreeAsync(nxt, st));
-            nxt = nullptr;
-            cap_nxt = std::min<int64_t>(max_front, (int64_t)h[0] + (int64_t)h[0] / 4);
-            CU(cudaMallocAsync(&nxt, cap_nxt * sizeof(FrontierItem), st));
-        }
-        res_before = h[1];
-        n_in = (int64_t)h[0];
-        std::swap(cur, nxt);
-        std::swap(cap_cur, cap_nxt);
+    int64_t launches = 0;
+    unsigned long long h[8] = {0};
+    for (;;) {
+        CU(cudaMemsetAsync(d_cnt.p, 0, 64, st));
+        CU(launch_regex_search(ix->d, ix->cfg, rt, (const uint32_t *)set->d_first, n_first, (FrontierItem *)cur, (FrontierItem *)nxt, cap,
+                               d_res.as<RegexResult>(), cap_res, d_cnt.as<unsigned long long>(), ix->n + 1, st));
+        ++launches;
+        CU(cudaMemcpyAsync(h, d_cnt.p, 64, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (h[4] == 0) break;
+        if (h[4] == 2) return fail(FMX_E_LIMIT, "regex traversal deeper than the text");
+        if ((int64_t)h[5] > max_front)
+            return fail(FMX_E_LIMIT, "regex frontier of %llu items exceeds the device budget of %lld; split the batch", h[5], (long long)max_front);
+        CU(cudaFreeAsync(cur, st)); cur = nullptr;
+        CU(cudaFreeAsync(nxt, st)); nxt = nullptr;
+        cap = std::min<int64_t>(max_front, std::max<int64_t>((int64_t)h[5] + (int64_t)h[5] / 4, cap * 2));
+        CU(cudaMallocAsync(&cur, cap * sizeof(FrontierItem), st)); CU(cudaMallocAsync(&nxt, cap * sizeof(FrontierItem), st));
     }
-    const int64_t total = (int64_t)h[1];
-    ph.mark("level loop");
+    ix->last_levels = (int64_t)h[6];
+    set->front_hint = (int64_t)h[7];
+    const int64_t total = (int64_t)h[3];
+    ph.mark("traversal");
     ix->last_launches = launches; ix->total_launches += launches;
     if (total > cap_res) {                                            // counted everything, could not store it
         t.stop();
         out_off[m] = total;
         return fail(FMX_E_CAPACITY, "regex search needs %lld result slots, capacity %lld", (long long)total, (long long)cap_total);
     }
-    CU(d_tmp.alloc(std::max<int64_t>(total, 1) * sizeof(RegexResult)));
-    CU(sort_regex_results(d_res.as<RegexResult>(), d_tmp.as<RegexResult>(), total, st));
+    // result order = (regex, len, sp, ep).  A handful of results is cheaper to order on the host than by two device radix sorts.
+    constexpr int64_t kHostSortMax = 1 << 14;
+    if (total > kHostSortMax) {
+        CU(d_tmp.alloc(total * sizeof(RegexResult)));
+        CU(sort_regex_results(d_res.as<RegexResult>(), d_tmp.as<RegexResult>(), total, st));
+    }
     t.stop();
     std::vector<RegexResult> hr((size_t)total);
     if (total) CU(cudaMemcpyAsync(hr.data(), d_res.p, total * sizeof(RegexResult), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     t.collect();
+    if (total <= kHostSortMax)
+        std::sort(hr.begin(), hr.end(), [](const RegexResult &a, const RegexResult &b) {
+            if (a.regex != b.regex) return a.regex < b.regex;
+            if (a.len != b.len) return a.len < b.len;
+            if (a.sp != b.sp) return a.sp < b.sp;
+            return a.ep < b.ep;
+        });
     ph.mark("sort + copy out");
     for (const RegexResult &r : hr) out_off[r.regex + 1]++;
     for (int64_t i = 0; i < m; ++i) out_off[i + 1] += out_off[i];

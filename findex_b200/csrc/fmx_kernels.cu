@@ -15,6 +15,8 @@
 // same block.  Nothing here is GEMM-shaped, so no tensor-core path exists by design.
 #include "fmx_kernels.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 namespace fmx {
@@ -319,28 +321,28 @@ locate_kernel(const __grid_constant__ DevIndex ix, const long long *__restrict__
 }
 
 // =====================================================================================================
-// K3: regex — one breadth-first level of the Glushkov traversal
+// K3: regex — breadth-first traversal of the position automata over SA intervals (ReTree._matchSA, retree.scala:618-653)
 // =====================================================================================================
+// One frontier item: backward step with the item's character, then emission of a match and/or of the follow positions.
+// Called by whole warps (inactive groups pass alive = false): matches and expansions are appended with one atomic per warp.
+// counters[0] += items appended to `out`, counters[1] += matches appended to `res`; both keep counting past the capacities
+// (writes are dropped) so the host can size a retry.
 template <int G, int LAYOUT>
-__global__ void __launch_bounds__(kThreads)
-regex_level_kernel(const __grid_constant__ DevIndex ix, RegexTables rt, const FrontierItem *__restrict__ in, long long n_in,
-                   FrontierItem *__restrict__ out, long long cap_out, RegexResult *__restrict__ res, long long cap_res,
-                   unsigned long long *counters) {
-    __shared__ SharedTables tb;
-    load_tables(tb, ix);
-    __syncthreads();
-    const long long t = (long long)blockIdx.x * (kThreads / G) + threadIdx.x / G;
+__device__ __forceinline__ void regex_expand(const DevIndex &ix, const SharedTables &tb, const RegexTables &rt, const FrontierItem *in,
+                                             long long t, bool alive, FrontierItem *__restrict__ out, long long cap_out,
+                                             RegexResult *__restrict__ res, long long cap_res, unsigned long long *c_out,
+                                             unsigned long long *c_res) {
     const bool leader = (threadIdx.x % G) == 0;
     const uint32_t lane = threadIdx.x & 31;
     FrontierItem it = {0, 0, 0, 0};
-    bool alive = t < n_in;
     if (alive) {
-        it = in[t];
+        // frontier buffers are rewritten by other SMs from level to level inside one launch: read them past the (non-coherent) L1
+        const uint4 raw = __ldcg(reinterpret_cast<const uint4 *>(in + t));
+        it = FrontierItem{raw.x, raw.y, raw.z, raw.w};
         uint32_t touched = 0;
         backward_step<G, LAYOUT, false>(ix, tb, rt.st_c[it.state], it.sp, it.ep, touched);   // getPrevRange
         alive = it.sp < it.ep;
     }
-    // ---- warp-aggregated emission --------------------------------------------------------------------
     // state flags: bit0 = emits a result, bit1 = stop after emitting (Glushkov last position; a Thompson position goes on)
     const uint32_t flg = alive ? rt.st_last[it.state] : 0u;
     const bool last = (flg & 1u) != 0;
@@ -351,27 +353,31 @@ regex_level_kernel(const __grid_constant__ DevIndex ix, RegexTables rt, const Fr
     const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, last && leader);
     if (mmask) {
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&counters[1], (unsigned long long)__popc(mmask));
+        if (lane == 0) base = atomicAdd(c_res, (unsigned long long)__popc(mmask));
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (last && leader) {
             const unsigned long long idx = base + __popc(mmask & ((1u << lane) - 1u));
             if (idx < (unsigned long long)cap_res) res[idx] = RegexResult{rt.st_regex[it.state], it.len + 1, it.sp, it.ep};
         }
     }
-    // expansions: exclusive prefix sum of follow counts over the warp, one atomic per warp
-    uint32_t incl = nf;
+    // expansions.  Short follow lists: exclusive prefix sum of their lengths over the warp, one atomic per warp, written by their owners.
+    // Longer lists (alternations, character classes, '.') are handled by the whole warp, one parent at a time, and filtered: a follow
+    // position with character c survives its backward step iff c occurs in BWT[sp..ep) (its new interval has rank_c(ep) - rank_c(sp) rows),
+    // so for a narrow interval only the positions whose character is actually there are appended — identical results, and a '.' after a
+    // one-row interval costs one item instead of 253.
+    constexpr uint32_t kWide = 4, kFilterRows = 32;
+    const bool is_wide = nf >= kWide;
+    const uint32_t nn = is_wide ? 0u : nf;
+    uint32_t incl = nn;
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    if (total == 0) return;
-    unsigned long long wbase = 0;
-    if (lane == 0) wbase = atomicAdd(&counters[0], (unsigned long long)total);
-    wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-    const unsigned long long my = wbase + (incl - nf);
-    // wide follow lists (character classes) are written by the whole warp, short ones by their owner
-    constexpr uint32_t kWide = 16;
-    uint32_t wide = __ballot_sync(0xFFFFFFFFu, nf >= kWide);
-    if (nf > 0 && nf < kWide) {
-        for (uint32_t j = 0; j < nf; ++j) {
+    uint32_t wide = __ballot_sync(0xFFFFFFFFu, is_wide);
+    if (total) {                                            // warp-uniform
+        unsigned long long wbase = 0;
+        if (lane == 0) wbase = atomicAdd(c_out, (unsigned long long)total);
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+        const unsigned long long my = wbase + (incl - nn);
+        for (uint32_t j = 0; j < nn; ++j) {
             const unsigned long long idx = my + j;
             if (idx < (unsigned long long)cap_out) out[idx] = FrontierItem{rt.fol[f0 + j], it.len + 1, it.sp, it.ep};
         }
@@ -381,13 +387,91 @@ regex_level_kernel(const __grid_constant__ DevIndex ix, RegexTables rt, const Fr
         wide &= wide - 1;
         const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, nf, src);
         const uint32_t fs = __shfl_sync(0xFFFFFFFFu, f0, src);
-        const unsigned long long b = __shfl_sync(0xFFFFFFFFu, my, src);
         const uint32_t ln = __shfl_sync(0xFFFFFFFFu, it.len, src) + 1;
         const uint32_t a = __shfl_sync(0xFFFFFFFFu, it.sp, src), e = __shfl_sync(0xFFFFFFFFu, it.ep, src);
-        for (uint32_t j = lane; j < cnt; j += 32) {
-            const unsigned long long idx = b + j;
-            if (idx < (unsigned long long)cap_out) out[idx] = FrontierItem{rt.fol[fs + j], ln, a, e};
+        const bool filt = (e - a) <= kFilterRows;
+        uint32_t present = 0;                               // lane w (0..7) holds bits 32w..32w+31 of the set of bytes in BWT[a..e)
+        if (filt) {
+            const bool has = lane < (e - a);
+            const uint32_t c = has ? (uint32_t)ix.bwt[a + lane] : 0u;
+#pragma unroll
+            for (uint32_t w = 0; w < 8; ++w) {
+                const uint32_t r = __reduce_or_sync(0xFFFFFFFFu, (has && (c >> 5) == w) ? (1u << (c & 31u)) : 0u);
+                if (lane == w) present = r;
+            }
         }
+        uint32_t kept_total = cnt;
+        if (filt) {
+            kept_total = 0;
+            for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                const uint32_t ch = j < cnt ? (uint32_t)rt.st_c[rt.fol[fs + j]] : 0u;
+                const uint32_t word = __shfl_sync(0xFFFFFFFFu, present, ch >> 5);
+                kept_total += __popc(__ballot_sync(0xFFFFFFFFu, j < cnt && ((word >> (ch & 31u)) & 1u)));
+            }
+        }
+        if (kept_total == 0) continue;                      // warp-uniform
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(c_out, (unsigned long long)kept_total);
+        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const uint32_t fstate = j < cnt ? rt.fol[fs + j] : 0u;
+            bool keep = j < cnt;
+            if (filt) {
+                const uint32_t ch = j < cnt ? (uint32_t)rt.st_c[fstate] : 0u;
+                const uint32_t word = __shfl_sync(0xFFFFFFFFu, present, ch >> 5);
+                keep = keep && ((word >> (ch & 31u)) & 1u);
+            }
+            const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+            if (keep) {
+                const unsigned long long idx = b + __popc(km & ((1u << lane) - 1u));
+                if (idx < (unsigned long long)cap_out) out[idx] = FrontierItem{fstate, ln, a, e};
+            }
+            b += __popc(km);
+        }
+    }
+}
+
+// The whole traversal in ONE cooperative launch: a persistent grid (one wave of CTAs) walks the levels, separated by grid-wide
+// barriers, ping-ponging between two frontier buffers.  ctrl: [0..2] = frontier counters rotating over the levels (level L reads
+// [L%3], appends to [(L+1)%3], clears [(L+2)%3]), [3] = matches, [4] = status (0 ok, 1 = a frontier outgrew its buffer: [5] = the
+// size it wanted, the host regrows and reruns; 2 = deeper than the text), [6] = levels run, [7] = largest frontier.
+template <int G, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+regex_search_kernel(const __grid_constant__ DevIndex ix, RegexTables rt, const uint32_t *__restrict__ first, long long n_first,
+                    FrontierItem *buf_a, FrontierItem *buf_b, long long cap, RegexResult *__restrict__ res, long long cap_res,
+                    unsigned long long *ctrl, long long max_levels) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    constexpr int QPB = kThreads / G;
+    // level 0 frontier: StatePoint(0, 0, sa.n, state) for every first position  (retree.scala:576)
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n_first; i += (long long)gridDim.x * kThreads)
+        buf_a[i] = FrontierItem{first[i], 0u, 0u, ix.n};
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl[0] = (unsigned long long)n_first; ctrl[1] = 0; ctrl[2] = 0; }
+    __syncthreads();
+    grid.sync();
+    FrontierItem *cur = buf_a, *nxt = buf_b;
+    for (long long level = 0;; ++level) {
+        const long long n_in = (long long)*reinterpret_cast<volatile unsigned long long *>(&ctrl[level % 3]);
+        if (n_in == 0) break;                               // grid-uniform: every thread reads the same counter after the barrier
+        if (n_in > cap || level >= max_levels) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl[4] = n_in > cap ? 1ull : 2ull; ctrl[5] = (unsigned long long)n_in; }
+            break;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            ctrl[(level + 2) % 3] = 0;
+            ctrl[6] = (unsigned long long)(level + 1);
+            if ((unsigned long long)n_in > ctrl[7]) ctrl[7] = (unsigned long long)n_in;
+        }
+        for (long long t0 = (long long)blockIdx.x * QPB; t0 < n_in; t0 += (long long)gridDim.x * QPB) {   // CTA-uniform trip count
+            const long long t = t0 + threadIdx.x / G;
+            regex_expand<G, LAYOUT>(ix, tb, rt, cur, t, t < n_in, nxt, cap, res, cap_res, &ctrl[(level + 1) % 3], &ctrl[3]);
+        }
+        grid.sync();
+        FrontierItem *tmp = cur; cur = nxt; nxt = tmp;
     }
 }
 
@@ -568,23 +652,28 @@ cudaError_t launch_locate(const DevIndex &ix, LaunchCfg cfg, const int64_t *d_sp
     return cudaGetLastError();
 }
 
-__global__ void init_frontier_kernel(const uint32_t *__restrict__ first, long long n_first, uint32_t n, FrontierItem *__restrict__ out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_first) out[i] = FrontierItem{first[i], 0u, 0u, n};             // StatePoint(0, 0, sa.n, state)  retree.scala:576
-}
-cudaError_t launch_init_frontier(const uint32_t *d_first, int64_t n_first, uint32_t n, FrontierItem *d_out, cudaStream_t st) {
-    if (n_first > 0) init_frontier_kernel<<<(unsigned)((n_first + 255) / 256), 256, 0, st>>>(d_first, n_first, n, d_out);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_regex_level(const DevIndex &ix, LaunchCfg cfg, RegexTables rt, const FrontierItem *d_in, int64_t n_in,
-                               FrontierItem *d_out, int64_t cap_out, RegexResult *d_res, int64_t cap_res,
-                               unsigned long long *d_counters, cudaStream_t st) {
-    if (n_in <= 0) return cudaSuccess;
-#define CALL(G, LAY) regex_level_kernel<G, LAY><<<grid_for(n_in, G), kThreads, 0, st>>>(ix, rt, d_in, n_in, d_out, cap_out, d_res, cap_res, d_counters)
+cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, RegexTables rt, const uint32_t *d_first, int64_t n_first,
+                                FrontierItem *d_a, FrontierItem *d_b, int64_t cap, RegexResult *d_res, int64_t cap_res,
+                                unsigned long long *d_ctrl, int64_t max_levels, cudaStream_t st) {
+    if (n_first <= 0) return cudaSuccess;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long nf = n_first, cp = cap, cr = cap_res, ml = max_levels;
+    void *args[] = {(void *)&ix, (void *)&rt, (void *)&d_first, (void *)&nf, (void *)&d_a, (void *)&d_b, (void *)&cp, (void *)&d_res, (void *)&cr,
+                    (void *)&d_ctrl, (void *)&ml};
+#define CALL(G, LAY)                                                                                                  \
+    {                                                                                                                 \
+        auto k = regex_search_kernel<G, LAY>;                                                                         \
+        int per_sm = 0;                                                                                               \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0);                                   \
+        if (e == cudaSuccess) e = per_sm > 0 ? cudaLaunchCooperativeKernel((void *)k, dim3((unsigned)(sms * per_sm)), dim3(kThreads), args, 0, st) \
+                                              : cudaErrorLaunchOutOfResources;                                       \
+    }
     FMX_DISPATCH(cfg, CALL);
 #undef CALL
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_gather_bench(const uint4 *base, uint64_t n_blocks64, int bytes, int lanes, int64_t gathers, int chain,

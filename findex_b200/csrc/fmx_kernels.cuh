@@ -59,13 +59,12 @@ struct RegexTables {
 };
 struct FrontierItem { uint32_t state, len, sp, ep; };
 struct RegexResult  { uint32_t regex, len, sp, ep; };
-cudaError_t launch_init_frontier(const uint32_t *d_first, int64_t n_first, uint32_t n, FrontierItem *d_out, cudaStream_t st);
-// one BFS level: consumes `n_in` items, appends survivors' follows to d_out (capacity cap_out) and matches to
-// d_res (capacity cap_res).  d_counters[0] = next frontier size, [1] = results so far (both may exceed caps:
-// writes are dropped, counts keep growing so the host can size a retry).
-cudaError_t launch_regex_level(const DevIndex &ix, LaunchCfg cfg, RegexTables rt, const FrontierItem *d_in, int64_t n_in,
-                               FrontierItem *d_out, int64_t cap_out, RegexResult *d_res, int64_t cap_res,
-                               unsigned long long *d_counters, cudaStream_t st);
+// the whole traversal in one cooperative launch (persistent grid, grid-wide barrier between levels).  d_ctrl: 8 x u64, zeroed by the caller:
+// [3] = matches found (may exceed cap_res: writes are dropped, the count keeps growing), [4] = status (0 ok; 1 = a frontier of [5] items
+// outgrew `cap`: regrow and rerun; 2 = more than max_levels levels), [6] = levels run.
+cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, RegexTables rt, const uint32_t *d_first, int64_t n_first,
+                                FrontierItem *d_a, FrontierItem *d_b, int64_t cap, RegexResult *d_res, int64_t cap_res,
+                                unsigned long long *d_ctrl, int64_t max_levels, cudaStream_t st);
 
 // K4 random gather microbenchmark
 cudaError_t launch_gather_bench(const uint4 *base, uint64_t n_blocks64, int bytes_per_gather, int lanes, int64_t gathers,

@@ -110,6 +110,8 @@ def lib():
     L.fmx_last_kernel_ms.argtypes = [p]
     L.fmx_last_kernel_launches.restype = i64
     L.fmx_last_kernel_launches.argtypes = [p]
+    L.fmx_last_regex_levels.restype = i64
+    L.fmx_last_regex_levels.argtypes = [p]
     L.fmx_build_index_files.argtypes = [p, i64, C.c_char_p, C.c_int, C.c_int, C.c_int]
     L.fmx_build_bwt.argtypes = [p, i64, p, C.POINTER(i64), C.POINTER(i64), p, C.c_int]
     _lib = L
@@ -453,6 +455,9 @@ class GpuFMSearcher:
 
     def last_kernel_launches(self):
         return lib().fmx_last_kernel_launches(self.h)
+
+    def last_regex_levels(self):
+        return lib().fmx_last_regex_levels(self.h)
 
 
 class PinnedArray:

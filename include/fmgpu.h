@@ -202,6 +202,8 @@ int fmx_set_lanes(fmx_index *ix, int32_t lanes_per_query);
 int fmx_get_lanes(const fmx_index *ix);                      /* lanes per query of the count kernels (may differ from the other kernels' by default) */
 double fmx_last_kernel_ms(const fmx_index *ix);
 int64_t fmx_last_kernel_launches(const fmx_index *ix);
+/* Breadth-first levels the last regex search walked (all inside one cooperative launch).                 */
+int64_t fmx_last_regex_levels(const fmx_index *ix);
 
 /* ---- index construction on the device (tooling for synthetic configs) -----------
  * text = FILE bytes (forward order).  Reproduces FileBWTReader (M/bwtreader.scala:196-211: 0x00 dropped,
