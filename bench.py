@@ -379,11 +379,23 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
 
+    # end to end through the host API: (sp, ep) per query at the reference's own width (Option[(Int, Int)], findex.scala:15-31) ...
+    narrow = g.n < 2 ** 31                                  # cfg 5 (n = 4e9) does not fit Int rows: int64 there
+    h_sp32 = fx.PinnedArray((m,), np.int32 if narrow else np.int64)
+    h_ep32 = fx.PinnedArray((m,), np.int32 if narrow else np.int64)
+
     def e2e_step():
-        g.count_fixed_into(h_pat.array, h_sp.array, h_ep.array)
+        g.count_fixed_into(h_pat.array, h_sp32.array, h_ep32.array)
 
     ms_e2e, clocks_e2e = timed_region(e2e_step, "e2e")
-    assert np.array_equal(h_sp.array, np.where(cnt > 0, sp, 0)) and np.array_equal(h_ep.array, np.where(cnt > 0, ep, 0)), "host API result differs from device API"
+    assert np.array_equal(h_sp32.array, np.where(cnt > 0, sp, 0)) and np.array_equal(h_ep32.array, np.where(cnt > 0, ep, 0)), "host API result differs from device API"
+
+    # ... and with int64 rows (twice the result bytes over PCIe)
+    def e2e64_step():
+        g.count_fixed_into(h_pat.array, h_sp.array, h_ep.array)
+
+    ms_e2e64, _ = timed_region(e2e64_step, "e2e")
+    assert np.array_equal(h_sp.array, np.where(cnt > 0, sp, 0)) and np.array_equal(h_ep.array, np.where(cnt > 0, ep, 0)), "host API (int64) result differs from device API"
 
     # the same batch through the count-only call (uint32 ep-sp per query: 4 instead of 16 result bytes over PCIe)
     h_cnt = fx.PinnedArray((m,), np.uint32)
@@ -416,8 +428,11 @@ def run_ours(args, rank, world, local_rank):
            "data": "synthetic", "config": dict(workload_config(args), exchange=("none" if world == 1 else ("fused peer stores + 4-byte NCCL barrier" if p2p else "NCCL all_gather_into_tensor on a side stream")), layout=info["layout"], lanes_per_query=info["lanes_per_query"],
                                                index_bytes=info["index_bytes"], kmer_k=info["kmer_k"], text_shortcut=info["text_shortcut"], ctx_depth=info["ctx_depth"], checksum=checksum),
            "clocks": clocks,
-           "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": m * ln, "d2h_bytes_per_step": m * 16, "ms_per_step": ms_e2e / args.steps,
-                   "api": "fmx_count_fixed (host pinned buffers in/out, int64 sp/ep)", "clocks": clocks_e2e,
+           "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": m * ln, "d2h_bytes_per_step": m * (8 if narrow else 16), "ms_per_step": ms_e2e / args.steps,
+                   "api": "fmx_count_fixed_i32 (host pinned buffers in/out, (sp, ep) as the reference's 32-bit Int rows)" if narrow else "fmx_count_fixed (host pinned buffers in/out, int64 sp/ep)",
+                   "clocks": clocks_e2e,
+                   "int64_rows": {"value": world * m * args.steps / (ms_e2e64 * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e64 / args.steps,
+                                  "h2d_bytes_per_step": m * ln, "d2h_bytes_per_step": m * 16, "api": "fmx_count_fixed (int64 sp/ep)"},
                    "count_only": {"value": world * m * args.steps / (ms_e2e_co * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_co / args.steps,
                                   "h2d_bytes_per_step": m * ln, "d2h_bytes_per_step": m * 4, "api": "fmx_count_only_fixed (uint32 ep-sp)"}},
            "gpu_launches": args.steps * (1 if (world == 1 or p2p) else nch),

@@ -641,14 +641,15 @@ int fmx_memcpy_d2h(void *dst, const void *src, int64_t bytes) {
     return FMX_OK;
 }
 
-static int count_fixed_pipeline(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, int64_t *sp, int64_t *ep, uint32_t *counts) {
+static int count_fixed_pipeline(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, int64_t *sp, int64_t *ep, uint32_t *counts,
+                                int32_t *sp32 = nullptr, int32_t *ep32 = nullptr) {
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t st = ix->stream;
-    const bool only_counts = counts != nullptr;
+    const bool only_counts = counts != nullptr, narrow = sp32 != nullptr;     // narrow: 32-bit rows out (the reference's Int)
     DBuf dp(st), dsp(st), dep(st), dcnt(st);
     CU(dp.alloc((size_t)m * len));
-    CU(dsp.alloc(m * (only_counts ? 4 : 8))); CU(dep.alloc(m * (only_counts ? 4 : 8)));
+    CU(dsp.alloc(m * ((only_counts || narrow) ? 4 : 8))); CU(dep.alloc(m * ((only_counts || narrow) ? 4 : 8)));
     if (only_counts) CU(dcnt.alloc(m * 4));
     const int64_t chunk = ix->chunk_queries > 0 ? ix->chunk_queries : (1 << 20);
     const int64_t nchunks = (m + chunk - 1) / chunk;
@@ -674,6 +675,8 @@ static int count_fixed_pipeline(fmx_index *ix, const uint8_t *pat, int32_t len, 
                 PeerSinks ps{};
                 ps.n = 1; ps.offset = q0; ps.p[0] = dcnt.as<uint32_t>();
                 e = launch_count_fixed(ix->d, ix->cfg, dp.as<uint8_t>() + q0 * len, len, nq, dsp.as<uint32_t>() + q0, dep.as<uint32_t>() + q0, false, nullptr, st, &ps);
+            } else if (narrow) {
+                e = launch_count_fixed(ix->d, ix->cfg, dp.as<uint8_t>() + q0 * len, len, nq, dsp.as<uint32_t>() + q0, dep.as<uint32_t>() + q0, false, nullptr, st);
             } else {
                 e = launch_count_fixed(ix->d, ix->cfg, dp.as<uint8_t>() + q0 * len, len, nq, dsp.as<int64_t>() + q0, dep.as<int64_t>() + q0, true, nullptr, st);
             }
@@ -682,6 +685,9 @@ static int count_fixed_pipeline(fmx_index *ix, const uint8_t *pat, int32_t len, 
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ix->d2h, ev_k[(size_t)k], 0);
         if (only_counts) {
             if (e == cudaSuccess) e = cudaMemcpyAsync(counts + q0, dcnt.as<uint32_t>() + q0, (size_t)nq * 4, cudaMemcpyDeviceToHost, ix->d2h);
+        } else if (narrow) {
+            if (e == cudaSuccess) e = cudaMemcpyAsync(sp32 + q0, dsp.as<uint32_t>() + q0, (size_t)nq * 4, cudaMemcpyDeviceToHost, ix->d2h);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(ep32 + q0, dep.as<uint32_t>() + q0, (size_t)nq * 4, cudaMemcpyDeviceToHost, ix->d2h);
         } else {
             if (e == cudaSuccess) e = cudaMemcpyAsync(sp + q0, dsp.as<int64_t>() + q0, (size_t)nq * 8, cudaMemcpyDeviceToHost, ix->d2h);
             if (e == cudaSuccess) e = cudaMemcpyAsync(ep + q0, dep.as<int64_t>() + q0, (size_t)nq * 8, cudaMemcpyDeviceToHost, ix->d2h);
@@ -703,6 +709,15 @@ int fmx_count_fixed(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, i
     if (len < 0 || m < 0 || (m && (!sp || !ep || (len && !pat)))) return fail(FMX_E_ARG, "bad argument");
     if (m == 0) return FMX_OK;
     return count_fixed_pipeline(ix, pat, len, m, sp, ep, nullptr);
+}
+
+// The reference's own result width: Option[(Int, Int)] (findex.scala:15-31) — 32-bit rows, half the result bytes over PCIe.
+int fmx_count_fixed_i32(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, int32_t *sp, int32_t *ep) {
+    CHECK_IX(ix);
+    if (len < 0 || m < 0 || (m && (!sp || !ep || (len && !pat)))) return fail(FMX_E_ARG, "bad argument");
+    if (ix->n > 0x7FFFFFFFll) return fail(FMX_E_UNSUPPORTED, "n = %lld does not fit the reference's Int rows; use fmx_count_fixed", (long long)ix->n);
+    if (m == 0) return FMX_OK;
+    return count_fixed_pipeline(ix, pat, len, m, nullptr, nullptr, nullptr, sp, ep);
 }
 
 // Count only: counts[q] = ep - sp of search(pattern q) (0 for None) — for callers that want the number of occurrences and not

@@ -75,6 +75,7 @@ def lib():
     L.fmx_count_batch.argtypes = [p, p, p, i64, p, p]
     L.fmx_count_fixed.argtypes = [p, p, i32, i64, p, p]
     L.fmx_count_only_fixed.argtypes = [p, p, i32, i64, p]
+    L.fmx_count_fixed_i32.argtypes = [p, p, i32, i64, p, p]
     L.fmx_count_fixed_dev.argtypes = [p, p, i32, i64, p, p, p]
     L.fmx_count_fixed_dev_gather.argtypes = [p, p, i32, i64, p, p, p, i32, i64, p]
     L.fmx_dev_alloc.argtypes = [pp, i64]
@@ -433,10 +434,15 @@ class GpuFMSearcher:
         _check(lib().fmx_set_chunk(self.h, queries_per_chunk))
 
     def count_fixed_into(self, pat2d, sp, ep):
-        """Like count_fixed but into caller-owned int64 arrays (pinned arrays make the copies asynchronous)."""
+        """Like count_fixed but into caller-owned arrays (pinned arrays make the copies asynchronous): int64, or int32 — the
+        reference's own Int rows, half the result bytes over PCIe."""
         m, ln = pat2d.shape
-        assert pat2d.flags.c_contiguous and pat2d.dtype == np.uint8 and sp.dtype == np.int64 and ep.dtype == np.int64
-        _check(lib().fmx_count_fixed(self.h, _ptr(pat2d), ln, m, _ptr(sp), _ptr(ep)))
+        assert pat2d.flags.c_contiguous and pat2d.dtype == np.uint8 and sp.dtype == ep.dtype and sp.dtype in (np.int64, np.int32)
+        assert len(sp) == m and len(ep) == m
+        if sp.dtype == np.int32:
+            _check(lib().fmx_count_fixed_i32(self.h, _ptr(pat2d), ln, m, _ptr(sp), _ptr(ep)))
+        else:
+            _check(lib().fmx_count_fixed(self.h, _ptr(pat2d), ln, m, _ptr(sp), _ptr(ep)))
 
     def count_only_fixed(self, pat2d, out=None):
         """Number of occurrences per pattern (ep - sp, uint32) without the interval."""

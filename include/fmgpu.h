@@ -109,6 +109,8 @@ int fmx_interval_prev_range(fmx_index *ix, int64_t sp, int64_t ep, int cstart, i
 int fmx_count_batch(fmx_index *ix, const uint8_t *pat, const int64_t *off, int64_t m, int64_t *sp, int64_t *ep);
 /* Fixed-length fast path: m patterns of `len` bytes, back to back.                                     */
 int fmx_count_fixed(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, int64_t *sp, int64_t *ep);
+/* Same with the reference's own result width, Option[(Int, Int)]: 32-bit rows (n must be < 2^31, else FMX_E_UNSUPPORTED).   */
+int fmx_count_fixed_i32(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, int32_t *sp, int32_t *ep);
 /* Count only: counts[q] = ep - sp (0 for None), uint32 — the number of occurrences without the interval.    */
 int fmx_count_only_fixed(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, uint32_t *counts);
 /* Device-pointer variant (asynchronous on `stream`): d_pat holds m*len bytes, d_sp/d_ep are uint32[m]. */

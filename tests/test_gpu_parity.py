@@ -183,6 +183,9 @@ def test_count_parity_small(ref_dir, cfg, accel):
         osp, oep = o.count_batch(arr.reshape(-1), np.arange(0, arr.size + 1, ln, dtype=np.int64))
         assert np.array_equal(sp, osp) and np.array_equal(ep, oep)
         assert np.array_equal(g.count_only_fixed(arr).astype(np.int64), oep - osp)
+        s32, e32 = np.full(len(arr), -1, np.int32), np.full(len(arr), -1, np.int32)      # the reference's Int-wide results
+        g.count_fixed_into(arr, s32, e32)
+        assert np.array_equal(s32, osp) and np.array_equal(e32, oep)
     g.close()
     o.close()
 
