@@ -947,6 +947,45 @@ int fmx_regex_compile_engine(const uint8_t *re, int64_t re_len, int line_only, i
 }
 void fmx_regex_free(fmx_regex *rx) { delete rx; }
 
+// ---- DFA engine (dfa.scala) ---------------------------------------------------------------------------------------------
+int fmx_dfa_create(int32_t n_states, const uint8_t *kind, const int32_t *link_off, const int32_t *link_to, const int32_t *link_chr, fmx_regex **out) {
+    if (!out) return fail(FMX_E_ARG, "null output");
+    *out = nullptr;
+    if (n_states > 0 && link_off && link_off[n_states] > 0 && (!link_to || !link_chr)) return fail(FMX_E_ARG, "null link arrays");
+    fmx_regex *rx = new fmx_regex();
+    std::string err;
+    int rc = compile_dfa(n_states, kind, link_off, link_to, link_chr, rx->dfa, rx->a, err);
+    if (rc) { delete rx; return fail(rc, "%s", err.c_str()); }
+    *out = rx;
+    return FMX_OK;
+}
+int fmx_dfa_info(const fmx_regex *dfa, int32_t *n_states, int32_t *moves, uint8_t *finish, int32_t *number, int32_t n_number) {
+    if (!dfa || dfa->dfa.n_states == 0) return fail(FMX_E_ARG, "not a DFA handle");
+    const CompiledDfa &d = dfa->dfa;
+    if (n_states) *n_states = d.n_states;
+    if (moves) std::copy(d.moves.begin(), d.moves.end(), moves);
+    if (finish) std::copy(d.finish.begin(), d.finish.end(), finish);
+    if (number) std::copy(d.number.begin(), d.number.begin() + std::min<size_t>(d.number.size(), (size_t)std::max(n_number, 0)), number);
+    return FMX_OK;
+}
+int fmx_dfa_buckets(const fmx_regex *dfa, int32_t state, char *buf, int64_t cap, int64_t *needed) {
+    if (!dfa || dfa->dfa.n_states == 0) return fail(FMX_E_ARG, "not a DFA handle");
+    if (state < 0 || state >= dfa->dfa.n_states) return fail(FMX_E_ARG, "state %d out of range", state);
+    const std::string s = dfa_bucket_string(dfa->dfa, state);
+    if (needed) *needed = (int64_t)s.size() + 1;
+    if (!buf || cap < (int64_t)s.size() + 1) return fail(FMX_E_CAPACITY, "bucket string needs %lld bytes", (long long)s.size() + 1);
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return FMX_OK;
+}
+int fmx_dfa_match_string(const fmx_regex *dfa, const uint8_t *s, int64_t len, int32_t *matched) {
+    if (!dfa || dfa->dfa.n_states == 0 || !matched || len < 0 || (len && !s)) return fail(FMX_E_ARG, "bad argument");
+    const CompiledDfa &d = dfa->dfa;
+    int cur = 0;
+    for (int64_t i = 0; i < len && cur >= 0; ++i) cur = d.moves[(size_t)cur * 256 + s[i]];
+    *matched = (cur >= 0 && d.finish[(size_t)cur]) ? 1 : 0;
+    return FMX_OK;
+}
+
 int fmx_regex_tables(const fmx_regex *rx, int32_t *n_states, int32_t *n_follows, int32_t *n_firsts, uint8_t *c, uint8_t *is_last,
                      int32_t *num, int32_t *follows_off, int32_t *follows, int32_t *firsts) {
     if (!rx) return fail(FMX_E_ARG, "null regex");

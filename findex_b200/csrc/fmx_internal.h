@@ -36,8 +36,25 @@ struct CompiledRegex {
 int compile_regex(const uint8_t *re, int64_t len, bool line_only, CompiledRegex &out, std::string &err);
 int compile_thompson(const uint8_t *re, int64_t len, bool line_only, CompiledRegex &out, std::string &err);
 
+
+// ---- DFA engine (dfa.scala), compiled next to the regex engines in fmx_regex.cpp ----------------------------
+struct DfaAction { int state, c1, c2; };       // c1 == c2: DFAChar, else DFABucket
+struct CompiledDfa {
+    int n_states = 0;                  // reachable states, numbered like DFA.processLinkList (start = 0)
+    std::vector<int32_t> number;       // caller's state index -> DFA state (-1 = unreachable)
+    std::vector<int32_t> moves;        // n_states x 256, -1 = no move
+    std::vector<uint8_t> finish;       // n_states
+    std::vector<DfaAction> buckets;    // compileBuckets, concatenated
+    std::vector<int32_t> bucket_off;   // n_states + 1
+};
+// link_off[n_states+1] / link_to / link_chr: every state's links in the reference's list order (most recently added first)
+int compile_dfa(int32_t n_states, const uint8_t *kind, const int32_t *link_off, const int32_t *link_to, const int32_t *link_chr,
+                CompiledDfa &dfa, CompiledRegex &out, std::string &err);
+std::string dfa_bucket_string(const CompiledDfa &dfa, int state);
+
 }  // namespace fmx
 
 struct fmx_regex {
     fmx::CompiledRegex a;
+    fmx::CompiledDfa dfa;              // filled by fmx_dfa_create only
 };

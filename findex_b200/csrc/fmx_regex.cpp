@@ -11,6 +11,7 @@
 #include "fmx_internal.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <string>
 #include <vector>
 
@@ -500,6 +501,122 @@ int compile_regex(const uint8_t *re, int64_t len, bool line_only, CompiledRegex 
         err = e.msg;
         return e.code;
     }
+}
+
+// =====================================================================================================
+// DFA engine  (src/main/scala/org/fmindex/dfa.scala)
+// =====================================================================================================
+// DFA.processLinkList (:391-407): states reachable from the start state, numbered in the order the reference's `visited` set grows
+// (start = 0), moves[state][char] from the links, then compileBuckets (:198-223).  For the search the automaton is handed to the
+// frontier kernel as a position automaton over its DFAChar EDGES: edge (s --c--> t) consumes c, emits iff t is a finish state and is
+// followed by t's DFAChar edges — StatePoint.expand (:238-256) follows DFAChar actions only, a DFABucket (two or more consecutive
+// characters with one target) is never traversed, and a finish state emits and is expanded all the same (:272-274).
+int compile_dfa(int32_t n_states, const uint8_t *kind, const int32_t *link_off, const int32_t *link_to, const int32_t *link_chr,
+                CompiledDfa &dfa, CompiledRegex &out, std::string &err) {
+    if (n_states <= 0 || !kind || !link_off) { err = "bad DFA description"; return FMX_E_ARG; }
+    int start = -1;
+    for (int i = 0; i < n_states; ++i) {
+        if (kind[i] > 2) { err = "state kind must be 0 (start), 1 (state) or 2 (finish)"; return FMX_E_ARG; }
+        if (kind[i] == 0) { if (start >= 0) { err = "Start state already taken"; return FMX_E_ARG; } start = i; }
+    }
+    if (start < 0) { err = "no start state"; return FMX_E_ARG; }
+    for (int i = 0; i < n_states; ++i)
+        for (int k = link_off[i]; k < link_off[i + 1]; ++k)
+            if (link_to[k] < 0 || link_to[k] >= n_states || link_chr[k] < 0 || link_chr[k] > 255) { err = "link out of range"; return FMX_E_ARG; }
+
+    // _processLinkList(s, visited): v = visited + s; for (l <- s.links if !visited(l.to)) v = v ++ rec(l.to, v)   — the membership test
+    // looks at the set that was passed in.  `order` is an insertion-ordered set.
+    struct Walk {
+        int32_t n; const int32_t *off, *to;
+        std::vector<int> rec(int s, const std::vector<int> &visited) const {
+            std::vector<int> v = visited;
+            std::vector<char> in_visited((size_t)n, 0), in_v((size_t)n, 0);
+            for (int x : visited) { in_visited[(size_t)x] = 1; in_v[(size_t)x] = 1; }
+            if (!in_v[(size_t)s]) { v.push_back(s); in_v[(size_t)s] = 1; }
+            for (int k = off[s]; k < off[s + 1]; ++k) {
+                if (in_visited[(size_t)to[k]]) continue;
+                for (int x : rec(to[k], v)) if (!in_v[(size_t)x]) { v.push_back(x); in_v[(size_t)x] = 1; }
+            }
+            return v;
+        }
+    } walk{n_states, link_off, link_to};
+    const std::vector<int> order = walk.rec(start, {});
+
+    dfa = CompiledDfa();
+    dfa.number.assign((size_t)n_states, -1);
+    int idx = 1;
+    for (int s : order) dfa.number[(size_t)s] = (kind[s] == 0) ? 0 : idx++;
+    const int ns = (int)order.size();
+    dfa.n_states = ns;
+    dfa.moves.assign((size_t)ns * 256, -1);
+    dfa.finish.assign((size_t)ns, 0);
+    for (int s : order) {
+        if (kind[s] == 2) dfa.finish[(size_t)dfa.number[(size_t)s]] = 1;
+        for (int k = link_off[s]; k < link_off[s + 1]; ++k)                       // addLink: a later link for the same char overwrites
+            dfa.moves[(size_t)dfa.number[(size_t)s] * 256 + (size_t)link_chr[k]] = dfa.number[(size_t)link_to[k]];
+    }
+    // the reference applies links in `for (v <- visited; l <- v.links)` order, i.e. list order (most recently added first), so the
+    // OLDEST link for a character wins; callers pass links in list order and the loop above keeps the last one it sees — the same.
+
+    // compileBuckets
+    dfa.bucket_off.assign(1, 0);
+    for (int i = 0; i < ns; ++i) {
+        int last = -1, start_bucket = -1;
+        for (int j = 0; j < 256; ++j) {
+            const int v = dfa.moves[(size_t)i * 256 + (size_t)j];
+            if (last != v) {
+                if (last != -1) dfa.buckets.push_back({last, start_bucket, j - 1});
+                start_bucket = j;
+                last = v;
+            }
+        }
+        if (last != -1) dfa.buckets.push_back({last, start_bucket, 255});
+        dfa.bucket_off.push_back((int32_t)dfa.buckets.size());
+    }
+
+    // position automaton over the DFAChar edges
+    std::vector<int32_t> first_edge((size_t)ns + 1, 0);
+    std::vector<int32_t> edge_target;
+    out = CompiledRegex();
+    out.stop_on_emit = false;
+    for (int i = 0; i < ns; ++i) {
+        first_edge[(size_t)i] = (int32_t)out.c.size();
+        for (int b = dfa.bucket_off[(size_t)i]; b < dfa.bucket_off[(size_t)i + 1]; ++b) {
+            const DfaAction &a = dfa.buckets[(size_t)b];
+            if (a.c1 != a.c2) continue;                                        // DFABucket: never traversed
+            out.c.push_back((uint8_t)a.c1);
+            out.num.push_back(0);
+            out.is_last.push_back(dfa.finish[(size_t)a.state]);
+            edge_target.push_back(a.state);
+        }
+    }
+    first_edge[(size_t)ns] = (int32_t)out.c.size();
+    out.follows_off.push_back(0);
+    for (size_t e = 0; e < edge_target.size(); ++e) {
+        const int t = edge_target[e];
+        for (int32_t f = first_edge[(size_t)t]; f < first_edge[(size_t)t + 1]; ++f) out.follows.push_back(f);
+        out.follows_off.push_back((int32_t)out.follows.size());
+    }
+    for (int32_t f = first_edge[0]; f < first_edge[1]; ++f) out.firsts.push_back(f);
+    return FMX_OK;
+}
+
+static std::string pretty_chr(int c) {
+    char buf[8];
+    if (c < 0x20 || c > 0x7e) std::snprintf(buf, sizeof buf, "\\x%x", c); else std::snprintf(buf, sizeof buf, "%c", c);
+    return buf;
+}
+
+// buckets(state).mkString(",") with the reference's DFAChar / DFABucket toString (:190-196)
+std::string dfa_bucket_string(const CompiledDfa &dfa, int state) {
+    std::string s;
+    for (int b = dfa.bucket_off[(size_t)state]; b < dfa.bucket_off[(size_t)state + 1]; ++b) {
+        const DfaAction &a = dfa.buckets[(size_t)b];
+        if (!s.empty()) s += ",";
+        if (a.c1 == a.c2) s += "DFAChar('" + pretty_chr(a.c1) + "'->" + std::to_string(a.state) + ")";
+        else s += "DFABucket('" + pretty_chr(a.c1) + "-" + pretty_chr(a.c2) + "' ->" + std::to_string(a.state) + ")";
+    }
+    return s;
 }
 
 }  // namespace fmx

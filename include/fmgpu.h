@@ -170,6 +170,24 @@ int  fmx_regex_tables(const fmx_regex *rx, int32_t *n_states, int32_t *n_follows
 int  fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int64_t cap_total,
                             int64_t *out_off, int32_t *len, int64_t *sp, int64_t *ep);
 
+/* ---- DFA engine  M/dfa.scala --------------------------------------------------------------------------
+ * fmx_dfa_create = DFA.processLinkList(startState) (:391-407) + compileBuckets (:198-223) for an automaton the caller built from
+ * StartState / State / FinishState objects and link(to, chr) calls (:291-336).  kind[i] = 0 start (exactly one), 1 state, 2 finish;
+ * state i's links are link_to/link_chr[link_off[i] .. link_off[i+1]) in the reference's LIST order (link() prepends: most recently
+ * added first).  Unreachable states are dropped; reachable ones are numbered as the reference's `visited` set grows (start = 0).
+ * The handle is an fmx_regex: fmx_regex_search_batch / fmx_regex_set_* run DFA.matchSA (:261-289) with the 500-iteration cap off —
+ * per automaton the sorted multiset of DFAResult (len, sp, ep); only DFAChar actions are followed (a DFABucket, i.e. two or more
+ * consecutive characters with one target, is never traversed: StatePoint.expand :238-256), and a finish state emits and is still
+ * expanded.  Free with fmx_regex_free.                                                                                   */
+int fmx_dfa_create(int32_t n_states, const uint8_t *kind, const int32_t *link_off, const int32_t *link_to,
+                   const int32_t *link_chr, fmx_regex **out);
+/* moves (n_states x 256, -1 = none), finishStates, and number[i] = DFA index of the caller's state i (-1 = unreachable).    */
+int fmx_dfa_info(const fmx_regex *dfa, int32_t *n_states, int32_t *moves, uint8_t *finish, int32_t *number, int32_t n_number);
+/* buckets(state).mkString(",") with the reference's toString, e.g. "DFABucket('c-d' ->1),DFAChar('f'->1)"  (:190-196)        */
+int fmx_dfa_buckets(const fmx_regex *dfa, int32_t state, char *buf, int64_t cap, int64_t *needed);
+/* DFA.matchString (:160-171), bytes unsigned                                                                               */
+int fmx_dfa_match_string(const fmx_regex *dfa, const uint8_t *s, int64_t len, int32_t *matched);
+
 /* Compile once, search many times: a regex set keeps the concatenated automata of a batch resident on the index's device
  * (the batched form of `val t = ReTree(post)` ... `t.matchSA(sa)` ... `t.matchSA(sa2)`).  fmx_regex_search_batch is
  * create + search + free.  A set may be searched against any index on the same device.                          */

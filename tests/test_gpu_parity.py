@@ -470,6 +470,55 @@ def test_thompson_parity_words(words_base, words):
     g.close()
 
 
+# ----------------------------------------------------------------------------------------------- DFA engine (dfa.scala)
+@pytest.mark.parametrize("cfg", [(fx.LAYOUT_WM, 2), (fx.LAYOUT_PLANES, 2), (fx.LAYOUT_PLANES, 1)], ids=_ids)
+def test_dfa_match_sa(cfg, words_base, words):
+    """DFA.matchSA on the GPU: the reference's asserted toy case (T/dfa.scala:108-120) verbatim, the bucket quirk, random automata over
+    the toy text and over words.*, and DFA handles mixed with ReTree / Thompson handles in one batch."""
+    import random
+    from dfa_cases import ab_star_c, class_b_star_c
+    from findex_b200 import dfa as pd
+    from oracle import dfa as od
+    bwt, eof, cnt = fo.build_bwt(b"mmabcacadabbbca"[::-1])
+    o = fo.OracleIndex.from_bwt(bwt, eof, cnt)
+    g = fx.GpuFMSearcher(bwt=bwt, eof=eof, counts=cnt, layout=cfg[0], lanes_per_query=cfg[1])
+    res = pd.DFA.processLinkList(ab_star_c(pd)).matchSA(g)
+    assert res == od.DFA(ab_star_c(od)).matchSA(o) and len(res) == 2
+    assert sorted(g.nextSubstr(sp, ln)[::-1] for ln, sp, ep in res) == [b"cba", b"cbbba"]          # results(1), results(0) of the reference test
+    assert pd.DFA(class_b_star_c(pd, ["c", "d"])).matchSA(g) == []                                  # DFABucket actions are never followed
+
+    def rand(m, rng, alphabet):
+        s = m.StartState()
+        st = [s] + [m.FinishState() if rng.random() < 0.4 else m.State(str(i)) for i in range(rng.randrange(1, 7))]
+        for _ in range(rng.randrange(1, 25)):
+            st[rng.randrange(len(st))].link(st[rng.randrange(len(st))], rng.choice(alphabet))
+        return s
+    for seed in range(40):
+        a = pd.DFA(rand(pd, random.Random(seed), list(b"abcdm")))
+        b = od.DFA(rand(od, random.Random(seed), list(b"abcdm")))
+        assert a.matchSA(g) == b.matchSA(o), seed
+    g.close()
+    o.close()
+
+    ow, _ = words
+    gw = _open(words_base + ".bwt", cfg, big_endian=True)
+    autos_p, autos_o = [], []
+    for seed in range(12):
+        alphabet = list(b"aeitn\r\n")
+        autos_p.append(pd.DFA(rand(pd, random.Random(100 + seed), alphabet)))
+        autos_o.append(od.DFA(rand(od, random.Random(100 + seed), alphabet)))
+    batch = autos_p + [fx.ReTree("th(e|a)(n|t)\\w"), fx.ThompsonNFA("qu.k")]
+    got = gw.regex_search_batch(batch)
+    nonempty = 0
+    for a, b in zip(got[:12], autos_o):
+        # a cyclic automaton matches ever longer strings until the text runs out of them: bounded here by the text, not by a cap
+        assert a == b.matchSA(ow)
+        nonempty += bool(a)
+    assert nonempty >= 3
+    assert got[12] == ow.regex_match("th(e|a)(n|t)\\w") and got[13] == ow.regex_match_thompson("qu.k", max_expansions=50_000_000)
+    gw.close()
+
+
 # ----------------------------------------------------------------------------------------------- edge cases
 @pytest.mark.parametrize("accel", [fx.ACCEL_AUTO, fx.ACCEL_NONE], ids=["auto", "none"])
 @pytest.mark.parametrize("cfg", [(fx.LAYOUT_WM, 2), (fx.LAYOUT_PLANES, 4)], ids=_ids)

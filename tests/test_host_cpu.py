@@ -206,3 +206,64 @@ def test_regex_compiler_limits_do_not_crash():
     opt = "x" + "a?" * 400 + "y"                              # long nullable run: quadratic follows, deep Thompson closure
     assert fx.ReTree(opt).tables() == retree.compile_regex(opt).tables()
     assert fx.ThompsonNFA(opt).tables() == retree.compile_thompson(opt)
+
+
+# ---------------------------------------------------------------------------------------------- DFA engine (dfa.scala), host side
+def _random_automaton(m, rng, n_states, n_links, alphabet):
+    s = m.StartState()
+    states = [s] + [m.FinishState() if rng.random() < 0.3 else m.State(str(i)) for i in range(n_states - 1)]
+    for _ in range(n_links):
+        states[rng.randrange(n_states)].link(states[rng.randrange(n_states)], rng.choice(alphabet))
+    return s, states
+
+
+def test_dfa_host_side_matches_oracle():
+    """fmx_dfa_create (numbering, moves, finish states, compileBuckets strings) and fmx_dfa_match_string against the oracle's
+    restatement: the reference's three asserted automata (T/dfa.scala:13-105) and 300 random ones.  No GPU involved."""
+    from findex_b200 import dfa as pd
+    from oracle import dfa as od
+    from dfa_cases import CDFKLM, DFA1, ab_star_c as _dfa_ab_star_c, class_b_star_c as _dfa_class_b_star_c
+    fbuild.build()
+    cases = [lambda m: _dfa_ab_star_c(m), lambda m: _dfa_class_b_star_c(m, CDFKLM), lambda m: _dfa_class_b_star_c(m, DFA1)]
+    for mk in cases:
+        p, o = pd.DFA.processLinkList(mk(pd)), od.DFA(mk(od))
+        assert p.n_states == o.n_states and p.moves.tolist() == o.moves and p.finishStates == o.finish
+        assert p.buckets == [o.bucket_string(i) for i in range(o.n_states)]
+    p = pd.DFA(_dfa_ab_star_c(pd))
+    assert p.buckets == ["DFAChar('a'->1)", "DFAChar('b'->2)", "DFAChar('b'->2),DFAChar('c'->3)", ""]      # T/dfa.scala:93-96 verbatim
+    assert not p.matchString("absbc") and p.matchString("abbc") and p.matchString("abc")                 # :65-67
+    for seed in range(300):
+        ns, nl = 1 + seed % 9, seed % 40
+        alphabet = [0, 1, 97, 98, 99, 100, 101, 200, 254, 255][: 2 + seed % 9]
+        sp_, states_p = _random_automaton(pd, random.Random(seed), ns, nl, alphabet)
+        so_, states_o = _random_automaton(od, random.Random(seed), ns, nl, alphabet)
+        p, o = pd.DFA(sp_), od.DFA(so_)
+        assert p.n_states == o.n_states and p.moves.tolist() == o.moves and p.finishStates == o.finish, seed
+        assert [s.dfaIdx for s in states_p] == [s.dfaIdx for s in states_o], seed              # same numbering, unreachable = -1
+        assert p.buckets == [o.bucket_string(i) for i in range(o.n_states)], seed
+        rng = random.Random(1000 + seed)
+        for _ in range(20):
+            w = bytes(rng.choice(alphabet) for _ in range(rng.randrange(0, 7)))
+            assert p.matchString(w) == o.matchString(w), (seed, w)
+        # the position automaton handed to the frontier kernel: one position per DFAChar action
+        tb = p.tables()
+        n_char = sum(1 for b in o.buckets for a in b if a[0] == "char")
+        assert len(tb["c"]) == n_char and len(tb["firsts"]) == sum(1 for a in o.buckets[0] if a[0] == "char")
+
+
+def test_dfa_create_rejects_bad_descriptions():
+    import ctypes as C
+    from findex_b200 import dfa as pd
+    L = fx.lib()
+    pd._declare(L)
+    h = C.c_void_p()
+    kind = np.array([1, 1], np.uint8)
+    off = np.zeros(3, np.int32)
+    z = np.zeros(1, np.int32)
+    assert L.fmx_dfa_create(2, fx._ptr(kind), fx._ptr(off), fx._ptr(z), fx._ptr(z), C.byref(h)) == fx.FMX_E_ARG      # no start state
+    kind = np.array([0, 0], np.uint8)
+    assert L.fmx_dfa_create(2, fx._ptr(kind), fx._ptr(off), fx._ptr(z), fx._ptr(z), C.byref(h)) == fx.FMX_E_ARG      # two start states
+    kind = np.array([0, 2], np.uint8)
+    off = np.array([0, 1, 1], np.int32)
+    to, ch = np.array([5], np.int32), np.array([97], np.int32)
+    assert L.fmx_dfa_create(2, fx._ptr(kind), fx._ptr(off), fx._ptr(to), fx._ptr(ch), C.byref(h)) == fx.FMX_E_ARG    # link target out of range

@@ -348,3 +348,33 @@ def test_thompson_differs_from_glushkov_where_the_reference_does(ix1024):
         with pytest.raises(retree.ReUnsupported):
             retree.compile_thompson(rx)
     assert retree.compile_thompson("(a|b)c")["firsts"] == [0, 1]            # fine here, MatchError in ReTree (Q3)
+
+
+# ---------------------------------------------------------------- DFA engine  T/dfa.scala:13-122
+from dfa_cases import CDFKLM, DFA1, ab_star_c as _dfa_ab_star_c, class_b_star_c as _dfa_class_b_star_c  # noqa: E402
+
+
+def test_dfa_match_string_and_buckets():
+    from oracle import dfa as od
+    d = od.DFA(_dfa_ab_star_c(od))                                                  # T/dfa.scala:62-68
+    assert not d.matchString(b"absbc") and d.matchString(b"abbc") and d.matchString(b"abc")
+    assert d.n_states == 4                                                          # :89-96
+    assert [d.bucket_string(i) for i in range(4)] == ["DFAChar('a'->1)", "DFAChar('b'->2)", "DFAChar('b'->2),DFAChar('c'->3)", ""]
+    d2 = od.DFA(_dfa_class_b_star_c(od, CDFKLM))            # :97-103
+    assert [d2.bucket_string(i) for i in range(4)] == ["DFABucket('c-d' ->1),DFAChar('f'->1),DFABucket('k-m' ->1)", "DFAChar('b'->2)",
+                                                       "DFAChar('b'->2),DFAChar('c'->3)", ""]
+    d3 = od.DFA(_dfa_class_b_star_c(od, DFA1))   # :104-105
+    assert d3.bucket_string(0) == "DFABucket('c-d' ->1),DFAChar('f'->1),DFABucket('l-m' ->1),DFABucket('\\xfa-\\xff' ->1)"
+
+
+def test_dfa_match_sa_basics():
+    """T/dfa.scala:108-120: `ab*c` over reverse("mmabcacadabbbca") gives exactly "cbbba" and "cba" (SAISBuilder.nextSubstr renders the
+    mirrored string, as in G1/G2)."""
+    from oracle import dfa as od
+    ix = _idx(b"mmabcacadabbbca"[::-1])
+    res = od.DFA(_dfa_ab_star_c(od)).matchSA(ix)
+    assert len(res) == 2
+    assert sorted(ix.nextSubstr(sp, ln)[::-1] for ln, sp, ep in res) == [b"cba", b"cbbba"]
+    assert all(ep - sp == 1 for _, sp, ep in res)
+    # a bucketed first step is never traversed: `[cd]b*c` finds nothing although "cb..." occurs (StatePoint.expand, M/dfa.scala:247-249)
+    assert od.DFA(_dfa_class_b_star_c(od, ["c", "d"])).matchSA(ix) == []
