@@ -183,7 +183,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     DevIndex &d = ix->d;
     d.blocks = (const uint4 *)blocks; d.stride = (uint64_t)nblk; d.bwt = d_bwt; d.C = d_C; d.base = d_base; d.code = d_code;
     d.bm = nullptr;
-    d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isat = nullptr; d.isat_bits = 8; d.isat_syms = 12; d.ctx = nullptr; d.ctx_J = 0; d.ctx_raw = 0;
+    d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isat = nullptr; d.isat_bits = 8; d.isat_syms = 12; d.ctx = nullptr; d.ctx_J = 0; d.ctx_raw = 0; d.ctx8 = nullptr; d.ctx8_J = 0;
     d.mark = nullptr; d.samples = nullptr; d.n = (uint32_t)n; d.eof = (uint32_t)eof; d.layout = layout; d.levels = levels;
     for (int l = 0; l < 8; ++l) d.z[l] = z[l];
 
@@ -222,28 +222,39 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     double reach = 68e9;
     if (const char *env = std::getenv("FMX_TLB_REACH_GB")) { const double v = std::atof(env); if (v > 0) reach = v * 1e9; }
     const int64_t rank_bytes = (layout == FMX_LAYOUT_PLANES ? planes_bytes : wm_bytes);
-    const bool want_text = (accel & (FMX_ACCEL_TEXT | FMX_ACCEL_CTX)) ||
-                           (accel == FMX_ACCEL_AUTO && 25 * n + (2ll << 30) < (int64_t)fr && ix->index_bytes + 20 * n <= budget + (24ll << 30));
-    const bool want_ctx = n > 2 && ((accel & FMX_ACCEL_CTX) ||
-                                    (accel == FMX_ACCEL_AUTO && want_text && 32.0 * n + 4e9 <= reach && 57 * n + (8ll << 30) < (int64_t)fr));
+    const bool auto_text = accel == FMX_ACCEL_AUTO && 25 * n + (2ll << 30) < (int64_t)fr && ix->index_bytes + 20 * n <= budget + (24ll << 30);
+    // row contexts: the 32-byte form when it fits the reach; for alphabets of <= 4 symbols on larger texts the compact 8-byte form
+    const bool fits32 = 32.0 * n + 4e9 <= reach && 57 * n + (8ll << 30) < (int64_t)fr;
+    const bool fits8 = sigma <= 4 && 8.0 * n + 4e9 <= reach && 33 * n + (8ll << 30) < (int64_t)fr;
+    const bool want_ctx = n > 2 && ((accel & FMX_ACCEL_CTX) || (accel == FMX_ACCEL_AUTO && auto_text && fits32));
+    const bool want_ctx8 = n > 2 && sigma <= 4 && !want_ctx && ((accel & FMX_ACCEL_CTX8) || (accel == FMX_ACCEL_AUTO && fits8));
+    // isat (16n bytes) is skipped when the compact contexts were chosen automatically: a text that large does not have the room
+    const bool want_isat = (accel & FMX_ACCEL_TEXT) || (accel == FMX_ACCEL_AUTO && auto_text && !want_ctx8) || ((accel & FMX_ACCEL_CTX) && !(accel & FMX_ACCEL_CTX8));
+    const bool want_sa = want_isat || want_ctx || want_ctx8;
     const bool want_kmer = (accel & FMX_ACCEL_KMER) || accel == FMX_ACCEL_AUTO;
-    if (want_text && n > 2) {
-        // sa stays; isa and the text are scratch that is folded into the 16-byte isat entries (and the 32-byte row contexts)
-        void *sa = nullptr, *isat = nullptr;
+    if (want_sa && n > 2) {
+        // sa stays (locate is one load per occurrence); isa and the text are scratch that is folded into the isat / context entries
+        void *sa = nullptr;
         uint32_t *isa = nullptr; uint8_t *text = nullptr;
         e = cudaMalloc(&sa, (size_t)n * 4); CU(e); ix->owned.push_back(sa);
-        e = cudaMalloc(&isat, (size_t)n * 16); CU(e); ix->owned.push_back(isat);
         CU(cudaMallocAsync(&isa, (size_t)n * 4, ix->stream));
         CU(cudaMallocAsync(&text, (size_t)n + 16, ix->stream));
         std::string err;
         e = build_full_sa(d, layout, (uint32_t *)sa, isa, text, ix->stream, err);
         if (e != cudaSuccess) return fail(err.empty() ? FMX_E_CUDA : FMX_E_FORMAT, "suffix array construction failed: %s", err.empty() ? cudaGetErrorString(e) : err.c_str());
+        d.sa = (const uint32_t *)sa;
+        ix->index_bytes += 4 * n;
         int ibits = 1;
         while ((1 << ibits) < sigma + 1) ++ibits;                 // values 0..sigma: dense code + 1, 0 = '$'
         const int isyms = 96 / ibits;
-        CU(build_isat(isa, text, d_code, n, ibits, isyms, (uint4 *)isat, ix->stream));
-        d.sa = (const uint32_t *)sa; d.isat = (const uint4 *)isat; d.isat_bits = ibits; d.isat_syms = isyms;
-        ix->index_bytes += 20 * n;
+        d.isat_bits = ibits; d.isat_syms = isyms;
+        if (want_isat) {
+            void *isat = nullptr;
+            e = cudaMalloc(&isat, (size_t)n * 16); CU(e); ix->owned.push_back(isat);
+            CU(build_isat(isa, text, d_code, n, ibits, isyms, (uint4 *)isat, ix->stream));
+            d.isat = (const uint4 *)isat;
+            ix->index_bytes += 16 * n;
+        }
         if (want_ctx) {
             void *ctx = nullptr;
             e = cudaMalloc(&ctx, (size_t)n * 32);
@@ -256,6 +267,17 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
                 ix->index_bytes += 32 * n;
             }
         }
+        if (want_ctx8) {
+            void *ctx8 = nullptr;
+            e = cudaMalloc(&ctx8, (size_t)n * 8);
+            if (e != cudaSuccess) { cudaGetLastError(); if (accel & FMX_ACCEL_CTX8) return fail(FMX_E_CUDA, "cannot allocate %lld bytes for the compact row contexts", (long long)n * 8); }
+            else {
+                ix->owned.push_back(ctx8);
+                CU(build_ctx8((const uint32_t *)sa, isa, text, d_code, n, 16, (uint2 *)ctx8, ix->stream));
+                d.ctx8 = (const uint2 *)ctx8; d.ctx8_J = 16;
+                ix->index_bytes += 8 * n;
+            }
+        }
         CU(cudaFreeAsync(isa, ix->stream));
         CU(cudaFreeAsync(text, ix->stream));
         CU(cudaStreamSynchronize(ix->stream));
@@ -264,7 +286,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     if (want_kmer && sigma >= 1) {
         size_t fr2 = 0, to2 = 0;
         cudaMemGetInfo(&fr2, &to2);
-        const int64_t max_entries = std::min<int64_t>((1ll << 32) - 1, std::max<int64_t>(8 * n, 1 << 16));   // no point in far more entries than rows
+        const int64_t max_entries = std::min<int64_t>(1ll << 32, std::max<int64_t>(8 * n, 1 << 16));   // no point in far more entries than rows
         auto entries_of = [&](int k) { int64_t v = 1; for (int j = 0; j < k; ++j) { if (v > max_entries) return max_entries + 1; v *= sigma; } return v; };
         int K = 0;
         if (o.kmer_table_bytes > 0) {                                   // explicit budget
@@ -274,8 +296,10 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
             for (int k = 16; k >= 2 && K == 0; --k) {
                 const int64_t en = entries_of(k);
                 if (en > max_entries || en * 8 > (int64_t)(fr2 / 3)) continue;
-                const bool saturating = d.ctx != nullptr && en >= n / 2;    // intervals are a few rows once the table has been consulted
-                const double ws = en * 8.0 + (d.ctx ? 32.0 * n : 0.0) + (saturating ? 0.0 : (double)rank_bytes + (d.isat && !d.ctx ? 20.0 * n : 0.0));
+                const bool have_ctx = d.ctx != nullptr || d.ctx8 != nullptr;
+                const bool saturating = have_ctx && en >= n / 2;            // intervals are a few rows once the table has been consulted
+                const double ws = en * 8.0 + (d.ctx ? 32.0 * n : 0.0) + (d.ctx8 ? 8.0 * n : 0.0) +
+                                  (saturating ? 0.0 : (double)rank_bytes + (d.isat && !have_ctx ? 20.0 * n : 0.0));
                 if (ws <= reach) K = k;
             }
             // ... else (the rest of the index is already beyond the reach) 256 MiB .. 16 GiB scaled to a sixteenth of the free memory
@@ -301,7 +325,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
         ix->cfg.lanes = 2;
         // count kernels: one lane per query once a deep table + row contexts answer most queries in two single-lane requests
         // (measured on cfg 2: 19.96 vs 18.69 G q/s; the kernel at two lanes is issue-bound, 80 % of the issue slots)
-        const bool saturating = d.ctx != nullptr && d.kmer != nullptr && std::pow((double)sigma, d.kmer_k) >= n / 2.0;
+        const bool saturating = (d.ctx != nullptr || d.ctx8 != nullptr) && d.kmer != nullptr && std::pow((double)sigma, d.kmer_k) >= n / 2.0;
         ix->cfg.count_lanes = saturating ? 1 : 0;
     }
     ix->accel_text = d.isat != nullptr;
@@ -436,7 +460,8 @@ int fmx_accel_info(const fmx_index *ix, int32_t *kmer_k, int32_t *text_shortcut)
     if (text_shortcut) *text_shortcut = ix->accel_text ? 1 : 0;
     return FMX_OK;
 }
-int fmx_ctx_depth(const fmx_index *ix) { return (ix && ix->d.ctx) ? ix->d.ctx_J : 0; }
+int fmx_ctx_depth(const fmx_index *ix) { return !ix ? 0 : ix->d.ctx ? ix->d.ctx_J : ix->d.ctx8 ? ix->d.ctx8_J : 0; }
+int fmx_ctx_entry_bytes(const fmx_index *ix) { return !ix ? 0 : ix->d.ctx ? 32 : ix->d.ctx8 ? 8 : 0; }
 int fmx_info(const fmx_index *ix, int32_t *layout, int32_t *levels, int32_t *sigma, int64_t *index_bytes, int32_t *rate) {
     CHECK_IX(ix);
     if (layout) *layout = ix->cfg.layout;
@@ -868,7 +893,7 @@ int fmx_next_substr_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t 
 int fmx_locate_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, int64_t m, int64_t cap_total, int64_t *out_off, int64_t *pos) {
     CHECK_IX(ix);
     if (m < 0 || !out_off || (m && (!sp || !ep))) return fail(FMX_E_ARG, "bad argument");
-    if (ix->sample_rate <= 0 && !ix->accel_text) return fail(FMX_E_ARG, "index was opened without sa_sample_rate (and without FMX_ACCEL_TEXT); locate unavailable");
+    if (ix->sample_rate <= 0 && ix->d.sa == nullptr) return fail(FMX_E_ARG, "index was opened without sa_sample_rate (and without a full-SA accelerator); locate unavailable");
     int64_t total = 0;
     for (int64_t i = 0; i < m; ++i) {
         if (sp[i] < 0 || ep[i] > ix->n || (ep[i] < sp[i])) return fail(FMX_E_ARG, "bad interval at %lld", (long long)i);

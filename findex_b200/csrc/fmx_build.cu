@@ -363,6 +363,26 @@ cudaError_t build_ctx(const uint32_t *d_sa, const uint32_t *d_isa, const uint8_t
     return cudaGetLastError();
 }
 
+// ctx8[r] (8 B) = { isa[sa[r]-J], the J <= 16 symbols T'[sa[r]-J .. sa[r]-1] as 2-bit dense codes }; row 0xFFFFFFFF when sa[r] < J
+__global__ void build_ctx8_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ isa, const uint8_t *__restrict__ text,
+                                  const uint8_t *__restrict__ code, int64_t n, int J, uint2 *__restrict__ ctx8) {
+    __shared__ uint8_t sc[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sc[i] = code[i];
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int64_t q = (int64_t)sa[r] - J;
+    if (q < 0) { ctx8[r] = make_uint2(0xFFFFFFFFu, 0u); return; }
+    uint32_t syms = 0;
+    for (int k = 0; k < J; ++k) syms |= ((uint32_t)sc[text[q + k]] & 3u) << (2 * k);
+    ctx8[r] = make_uint2(isa[q], syms);
+}
+cudaError_t build_ctx8(const uint32_t *d_sa, const uint32_t *d_isa, const uint8_t *d_text, const uint8_t *d_code, int64_t n, int J,
+                       uint2 *d_ctx8, cudaStream_t st) {
+    build_ctx8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_sa, d_isa, d_text, d_code, n, J, d_ctx8);
+    return cudaGetLastError();
+}
+
 cudaError_t build_full_sa(const DevIndex &ix, int layout, uint32_t *d_sa, uint32_t *d_isa, uint8_t *d_text, cudaStream_t st, std::string &err) {
     Chains ch;
     CK(prepare_chains(ix, layout, ch, st, err));
@@ -373,39 +393,51 @@ cudaError_t build_full_sa(const DevIndex &ix, int layout, uint32_t *d_sa, uint32
     return cudaGetLastError();
 }
 
-// k-mer table: entry idx <-> the K-byte pattern P with P[K-1-j] = sym[digit_j(idx)] (digit 0 most significant = the
-// byte search() consumes first, i.e. the LAST pattern byte)
-__global__ void gen_kmer_patterns_kernel(const uint8_t *__restrict__ sym, uint32_t sigma, int K, uint64_t first, uint64_t count,
-                                         uint8_t *__restrict__ out) {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    uint64_t x = first + t;
-    for (int j = K - 1; j >= 0; --j) { out[t * K + (K - 1 - j)] = sym[x % sigma]; x /= sigma; }
+// k-mer table: entry idx <-> the K-byte pattern P with P[K-1-j] = sym[digit_j(idx)] (digit 0 most significant = the byte search()
+// consumes first, i.e. the LAST pattern byte); entry = (sp,ep) after those K backward steps, (0,0) when the interval is empty.
+// Built level by level: level 1 is (C[c], C[c+1]); an entry of level j+1 is one backward step from its parent idx/sigma of level j
+// with symbol idx%sigma — sigma^K * sigma/(sigma-1) steps in all instead of sigma^K * (K-1).
+__global__ void kmer_level1_kernel(const DevIndex ix, const uint8_t *__restrict__ sym, uint32_t sigma, uint2 *__restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= sigma) return;
+    const uint32_t c = sym[t], a = ix.C[c], b = ix.C[c + 1];
+    out[t] = a < b ? make_uint2(a, b) : make_uint2(0u, 0u);
 }
-__global__ void zip_kmer_kernel(const uint32_t *__restrict__ sp, const uint32_t *__restrict__ ep, uint64_t count, uint2 *__restrict__ out) {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < count) out[t] = make_uint2(sp[t], ep[t]);
+template <int G, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+kmer_extend_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ sym, uint32_t sigma, const uint2 *__restrict__ prev,
+                   unsigned long long count, uint2 *__restrict__ out) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    const unsigned long long t = (unsigned long long)blockIdx.x * (kThreads / G) + threadIdx.x / G;
+    if (t >= count) return;                                // group-uniform
+    const uint2 p = prev[t / sigma];
+    uint32_t sp = p.x, ep = p.y, touched = 0;
+    if (sp < ep) backward_step<G, LAYOUT, false>(ix, tb, (uint32_t)sym[t % sigma], sp, ep, touched);
+    if ((threadIdx.x % G) == 0) out[t] = sp < ep ? make_uint2(sp, ep) : make_uint2(0u, 0u);
 }
 
 cudaError_t build_kmer_table(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, uint32_t sigma, int K, uint2 *d_table, cudaStream_t st) {
-    uint64_t total = 1;
-    for (int j = 0; j < K; ++j) total *= sigma;
-    const uint64_t slice = 1ull << 24;                  // bounded scratch: 16 Mi patterns at a time
-    uint8_t *d_pat; uint32_t *d_sp, *d_ep;
-    CK(cudaMallocAsync(&d_pat, slice * K, st));
-    CK(cudaMallocAsync(&d_sp, slice * 4, st));
-    CK(cudaMallocAsync(&d_ep, slice * 4, st));
-    DevIndex plain = ix;                                // the table is filled by ordinary backward steps
-    plain.kmer = nullptr;
-    plain.isat = nullptr;
-    plain.ctx = nullptr;
-    for (uint64_t o = 0; o < total; o += slice) {
-        const uint64_t cnt = total - o < slice ? total - o : slice;
-        gen_kmer_patterns_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_sym, sigma, K, o, cnt, d_pat);
-        CK(launch_count_fixed(plain, cfg, d_pat, K, (int64_t)cnt, d_sp, d_ep, false, nullptr, st));
-        zip_kmer_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_sp, d_ep, cnt, d_table + o);
+    if (K < 1 || sigma < 1) return cudaErrorInvalidValue;
+    std::vector<unsigned long long> size((size_t)K + 1, 1);
+    for (int j = 1; j <= K; ++j) size[(size_t)j] = size[(size_t)j - 1] * sigma;
+    uint2 *d_tmp = nullptr;
+    if (K >= 2) CK(cudaMallocAsync(&d_tmp, size[(size_t)K - 1] * sizeof(uint2), st));
+    auto buf = [&](int level) { return ((K - level) % 2 == 0) ? d_table : d_tmp; };      // level K lands in d_table
+    kmer_level1_kernel<<<(sigma + 255) / 256, 256, 0, st>>>(ix, d_sym, sigma, buf(1));
+    const int G = (cfg.lanes == 1 || cfg.lanes == 2 || cfg.lanes == 4) ? cfg.lanes : 2;
+    for (int j = 2; j <= K; ++j) {
+        const unsigned long long cnt = size[(size_t)j];
+        const unsigned long long per = kThreads / G;
+        const unsigned grid = (unsigned)((cnt + per - 1) / per);
+#define CALL(GG, LAY) kmer_extend_kernel<GG, LAY><<<grid, kThreads, 0, st>>>(ix, d_sym, sigma, buf(j - 1), cnt, buf(j))
+        if (ix.layout == FMX_LAYOUT_PLANES) { if (G == 1) CALL(1, FMX_LAYOUT_PLANES); else if (G == 2) CALL(2, FMX_LAYOUT_PLANES); else CALL(4, FMX_LAYOUT_PLANES); }
+        else { if (G == 1) CALL(1, FMX_LAYOUT_WM); else if (G == 2) CALL(2, FMX_LAYOUT_WM); else CALL(4, FMX_LAYOUT_WM); }
+#undef CALL
+        CK(cudaGetLastError());
     }
-    cudaFreeAsync(d_pat, st); cudaFreeAsync(d_sp, st); cudaFreeAsync(d_ep, st);
+    if (d_tmp) cudaFreeAsync(d_tmp, st);
     return cudaGetLastError();
 }
 

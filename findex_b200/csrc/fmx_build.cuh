@@ -24,6 +24,8 @@ cudaError_t build_isat(const uint32_t *d_isa, const uint8_t *d_text, const uint8
 // row-indexed 32-byte context entries (DevIndex::ctx)
 cudaError_t build_ctx(const uint32_t *d_sa, const uint32_t *d_isa, const uint8_t *d_text, const uint8_t *d_code, int64_t n, int bits, int J,
                       int raw, uint4 *d_ctx, cudaStream_t st);
+cudaError_t build_ctx8(const uint32_t *d_sa, const uint32_t *d_isa, const uint8_t *d_text, const uint8_t *d_code, int64_t n, int J,
+                       uint2 *d_ctx8, cudaStream_t st);
 // (sp,ep) after the first K backward steps for every K-mer over the sigma occurring symbols
 cudaError_t build_kmer_table(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, uint32_t sigma, int K, uint2 *d_table, cudaStream_t st);
 // suffix sort of t+'$' (t has no zero bytes) -> BWT, eof row, byte counts; optionally the suffix array

@@ -50,6 +50,11 @@ struct DevIndex {
     const uint4    *ctx;        // 2 x uint4 per row, or nullptr
     int32_t         ctx_J;      // = isat_syms
     int32_t         ctx_raw;    // 1 (byte alphabets, 8-bit symbols): the 12 symbols are the raw text bytes, so pattern words compare directly
+    // compact row contexts for alphabets of <= 4 symbols on texts too large for the 32-byte form (4e9 rows: 32 GB instead of 128):
+    // ctx8[r] = { isa[sa[r]-J], the J = 16 symbols T'[sa[r]-16 .. sa[r]-1] as 2-bit dense codes } — usable when exactly J bytes remain;
+    // rows with fewer than J text positions before them hold row 0xFFFFFFFF
+    const uint2    *ctx8;
+    int32_t         ctx8_J;
 };
 
 // Pattern accessors handed to search_pattern: operator()(i) = byte i; word(w) = bytes 4w..4w+3 packed little-endian (bytes at or
@@ -328,13 +333,40 @@ __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedT
             if (STATS) ++steps;
         }
     }
-    bool noctx = (ix.ctx == nullptr);
+    bool noctx = (ix.ctx == nullptr && ix.ctx8 == nullptr);
     for (;;) {
         const bool go = (i >= 0) && (sp < ep);
         if (go) {
             bool stepped = false;
             const int rem = i + 1;
-            if (!noctx && (ep - sp) <= kCtxMaxRows && rem <= ix.ctx_J && rem > ix.ctx_J - kCtxSpan) {
+            if (!noctx && ix.ctx8 != nullptr && (ep - sp) <= kCtxMaxRows && rem == ix.ctx8_J) {
+                // compact form: 8 bytes per row, exactly ctx8_J symbols left
+                uint32_t q = 0;
+                bool zero = false, absent = false;
+                for (int k = 0; k < rem; ++k) {
+                    const uint32_t pc = pat(k), cd = tb.code[pc];
+                    zero = zero || (pc == 0);
+                    absent = absent || (cd == (uint32_t)kCodeAbsent);
+                    q |= (cd & 3u) << (2 * k);
+                }
+                if (zero) noctx = true;
+                else {
+                    uint32_t best = 0xFFFFFFFFu, cnt = 0;
+                    if (!absent) {
+                        for (uint32_t r = sp + (uint32_t)lane; r < ep; r += G) {
+                            const uint2 e = ldg64(ix.ctx8 + r);
+                            if (e.y == q && e.x != 0xFFFFFFFFu) { best = e.x < best ? e.x : best; ++cnt; }
+                        }
+                    }
+                    if (STATS && lane == 0) { touched += absent ? 0u : ep - sp; steps += rem; }
+                    if (G >= 2) { best = min(best, __shfl_xor_sync(gmask, best, 1)); cnt += __shfl_xor_sync(gmask, cnt, 1); }
+                    if (G >= 4) { best = min(best, __shfl_xor_sync(gmask, best, 2)); cnt += __shfl_xor_sync(gmask, cnt, 2); }
+                    if (cnt) { sp = best; ep = best + cnt; } else { sp = 0; ep = 0; }
+                    i = -1;
+                    stepped = true;
+                }
+            }
+            if (!stepped && !noctx && ix.ctx != nullptr && (ep - sp) <= kCtxMaxRows && rem <= ix.ctx_J && rem > ix.ctx_J - kCtxSpan) {
                 // every row of the interval is looked at through its 32-byte context entry: the rows whose text goes on with the
                 // remaining `rem` pattern bytes map onto exactly the pattern's interval (their targets isa[sa[r]-rem] are its rows)
                 const uint32_t bits = (uint32_t)ix.isat_bits;

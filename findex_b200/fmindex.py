@@ -19,7 +19,7 @@ _SO = os.path.join(_HERE, "libfmgpu.so")
 FMX_OK, FMX_E_IO, FMX_E_FORMAT, FMX_E_CUDA, FMX_E_ARG = 0, -1, -2, -3, -4
 FMX_E_CAPACITY, FMX_E_SYNTAX, FMX_E_UNSUPPORTED, FMX_E_LIMIT = -5, -6, -7, -8
 LAYOUT_AUTO, LAYOUT_WM, LAYOUT_PLANES = 0, 1, 2
-ACCEL_AUTO, ACCEL_KMER, ACCEL_TEXT, ACCEL_CTX, ACCEL_NONE = 0, 1, 2, 4, 8
+ACCEL_AUTO, ACCEL_KMER, ACCEL_TEXT, ACCEL_CTX, ACCEL_NONE, ACCEL_CTX8 = 0, 1, 2, 4, 8, 16
 
 
 class FmxError(Exception):
@@ -69,6 +69,7 @@ def lib():
     L.fmx_accel_info.argtypes = [p, C.POINTER(i32), C.POINTER(i32)]
     L.fmx_get_lanes.argtypes = [p]
     L.fmx_ctx_depth.argtypes = [p]
+    L.fmx_ctx_entry_bytes.argtypes = [p]
     L.fmx_occ_batch.argtypes = [p, p, p, i64, p]
     L.fmx_prev_range_batch.argtypes = [p, p, p, p, i64, p, p]
     L.fmx_interval_prev_range.argtypes = [p, i64, i64, C.c_int, C.c_int, p, p, p, C.POINTER(i64)]
@@ -273,7 +274,7 @@ class GpuFMSearcher:
         _check(lib().fmx_accel_info(self.h, C.byref(k), C.byref(t)))
         return {"layout": {1: "wm", 2: "planes"}[lay.value], "levels": lev.value, "sigma": sig.value,
                 "index_bytes": nb.value, "sa_sample_rate": rate.value, "kmer_k": k.value, "text_shortcut": bool(t.value),
-                "ctx_depth": lib().fmx_ctx_depth(self.h),
+                "ctx_depth": lib().fmx_ctx_depth(self.h), "ctx_entry_bytes": lib().fmx_ctx_entry_bytes(self.h),
                 "lanes_per_query": lib().fmx_get_lanes(self.h)}
 
     # ---- scalar trait members (each is a batch of one) -------------------------------------------------

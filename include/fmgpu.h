@@ -49,6 +49,8 @@ extern "C" {
 #define FMX_ACCEL_TEXT      2   /* full SA + {inverse SA, 96 bits of text} entries (20n bytes): singleton intervals finish in 2 fetches; locate is 1 fetch */
 #define FMX_ACCEL_CTX       4   /* (implies TEXT) 32-byte row contexts { isa[sa[r]-j], j = J-4..J ; the J symbols before sa[r] }: an interval of <= 8 rows
                                    with J-4..J pattern bytes left finishes in one fetch per row (J = 12 for byte alphabets, 19 for sigma <= 31, 32 for DNA) */
+#define FMX_ACCEL_CTX8     16   /* (alphabets of <= 4 symbols) compact 8-byte row contexts { isa[sa[r]-16], 16 two-bit symbols }: the same one-fetch-per-row
+                                   finish when exactly 16 pattern bytes remain; chosen automatically when the 32-byte form does not fit (4e9-row DNA index) */
 #define FMX_ACCEL_NONE      8   /* plain backward search only                                                */
 
 typedef struct fmx_index fmx_index;     /* opaque; library-owned until fmx_close  */
@@ -87,7 +89,8 @@ int     fmx_info(const fmx_index *ix, int32_t *layout, int32_t *levels, int32_t 
                  int64_t *index_bytes, int32_t *sa_sample_rate);
 
 int     fmx_accel_info(const fmx_index *ix, int32_t *kmer_k, int32_t *text_shortcut);   /* accelerators in effect */
-int     fmx_ctx_depth(const fmx_index *ix);                  /* J of the row contexts (FMX_ACCEL_CTX), 0 = not built */
+int     fmx_ctx_depth(const fmx_index *ix);                  /* J of the row contexts (FMX_ACCEL_CTX / _CTX8), 0 = not built */
+int     fmx_ctx_entry_bytes(const fmx_index *ix);            /* 32, 8 or 0 */
 
 /* ---- occ(c,key)  M/bwtmerger.scala:354-375  (number of c in BWT[0..key], key=-1 -> 0) --------------- */
 int fmx_occ_batch(fmx_index *ix, const uint8_t *c, const int64_t *key, int64_t m, int64_t *out);

@@ -162,7 +162,7 @@ def test_count_parity_small(ref_dir, cfg, accel):
     o = fo.OracleIndex.load(os.path.join(ref_dir, "test.cmp"), big_endian=False)
     g = _open(os.path.join(ref_dir, "test.cmp.bwt"), cfg, accel=accel)
     info = g.info()
-    assert info["text_shortcut"] == (accel in (fx.ACCEL_AUTO, fx.ACCEL_TEXT, fx.ACCEL_CTX)) and (info["kmer_k"] >= 2) == (accel in (fx.ACCEL_AUTO, fx.ACCEL_KMER))
+    assert info["text_shortcut"] == (accel in (fx.ACCEL_AUTO, fx.ACCEL_TEXT, fx.ACCEL_CTX)) and info["ctx_entry_bytes"] in (0, 32) and (info["kmer_k"] >= 2) == (accel in (fx.ACCEL_AUTO, fx.ACCEL_KMER))
     assert (info["ctx_depth"] > 0) == (accel in (fx.ACCEL_AUTO, fx.ACCEL_CTX))
     rng = np.random.default_rng(11)
     tprime = text[::-1]
@@ -517,6 +517,85 @@ def test_dfa_match_sa(cfg, words_base, words):
     assert nonempty >= 3
     assert got[12] == ow.regex_match("th(e|a)(n|t)\\w") and got[13] == ow.regex_match_thompson("qu.k", max_expansions=50_000_000)
     gw.close()
+
+
+# ----------------------------------------------------------------------------------------------- row contexts
+@pytest.mark.parametrize("sigma,form", [(2, 32), (4, 32), (20, 32), (200, 32), (2, 8), (3, 8), (4, 8)])
+@pytest.mark.parametrize("cfg", [(fx.LAYOUT_WM, 4), (fx.LAYOUT_PLANES, 2), (fx.LAYOUT_PLANES, 1), (fx.LAYOUT_WM, 1)], ids=_ids)
+def test_row_context_small_intervals(cfg, sigma, form):
+    """FMX_ACCEL_CTX / _CTX8: intervals of 1..8 rows (and larger ones) with every remaining length around the covered window, on texts
+    whose chunks repeat 2..12 times; all three symbol packings of the 32-byte form (3, 5 and 8 bits) and the compact 8-byte form"""
+    rng = np.random.default_rng(100 + sigma)
+    alpha = rng.choice(np.arange(1, 256), sigma, replace=False).astype(np.uint8)
+    chunks = [alpha[rng.integers(0, sigma, int(rng.integers(20, 70)))] for _ in range(40)]
+    parts = []
+    for _ in range(300):
+        parts.append(chunks[int(rng.integers(0, len(chunks)))] if rng.random() < 0.6 else alpha[rng.integers(0, sigma, int(rng.integers(1, 50)))])
+    text = np.concatenate(parts).tobytes()
+    tp = bytes(fo.file_to_text_rev(text))
+    bwt, eof, cnt = fo.build_bwt(fo.file_to_text_rev(text))
+    o = fo.OracleIndex.from_bwt(bwt, eof, cnt)
+    g = fx.GpuFMSearcher(bwt=bwt, eof=eof, counts=cnt, layout=cfg[0], lanes_per_query=cfg[1],
+                         accel=(fx.ACCEL_CTX if form == 32 else fx.ACCEL_CTX8) | fx.ACCEL_KMER, kmer_table_bytes=8 * sigma * sigma)
+    info = g.info()
+    J = info["ctx_depth"]
+    assert info["ctx_entry_bytes"] == form and info["kmer_k"] == 2
+    assert J == ({2: 48, 4: 32, 20: 19, 200: 12}[sigma] if form == 32 else 16)
+    assert info["text_shortcut"] == (form == 32)            # the compact form is built without the 16-byte isat entries
+    pats = []
+    for ln in list(range(1, J + 8)) + [J + 20]:
+        for _ in range(60):
+            s = int(rng.integers(0, len(tp) - ln))
+            p = bytearray(tp[s:s + ln])
+            if rng.random() < 0.3:
+                p[int(rng.integers(0, ln))] = int(alpha[rng.integers(0, sigma)])       # near miss
+            pats.append(bytes(p))
+    pats += [tp[:J], tp[:J + 2], tp[1:J + 1], tp[-J - 1:-1], bytes([int(alpha[0])]) * (J + 2), tp[:J + 1] + b"\0", b"\0" + tp[:J + 1]]
+    sp, ep = g.count_batch(pats)
+    sizes = set()
+    for i, p in enumerate(pats):
+        r = o.search(p)
+        assert (int(sp[i]), int(ep[i])) == (r if r else (0, 0)), p
+        sizes.add(int(ep[i] - sp[i]))
+    assert len(sizes & {1, 2, 3, 4, 5, 6, 7, 8}) >= (3 if sigma > 2 else 1) and max(sizes) > 8
+    for ln in (J - 4, J, J + 2, J + 3):
+        arr = np.frombuffer(b"".join(p[:ln] for p in pats if len(p) >= ln), np.uint8).reshape(-1, ln)
+        s2, e2 = g.count_fixed(arr)
+        osp, oep = o.count_batch(arr.reshape(-1), np.arange(0, arr.size + 1, ln, dtype=np.int64))
+        assert np.array_equal(s2, osp) and np.array_equal(e2, oep)
+    off, pos = g.locate_batch(sp[:40], ep[:40])             # the full SA stays resident with either form
+    sa = o.sa().astype(np.int64)
+    for k in range(40):
+        assert np.array_equal(pos[off[k]:off[k + 1]], np.sort(sa[sp[k]:ep[k]]))
+    g.close()
+    o.close()
+
+
+def test_compact_contexts_are_chosen_when_the_wide_form_does_not_fit(monkeypatch):
+    """FMX_ACCEL_AUTO on a 4-symbol text whose 32-byte contexts would not fit the (here artificially small) TLB reach: the compact form
+    is built, isat is not, the k-mer table saturates, and count/locate still equal the oracle."""
+    rng = np.random.default_rng(5)
+    text = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 200_000)].tobytes()
+    bwt, eof, cnt = fo.build_bwt(fo.file_to_text_rev(text))
+    o = fo.OracleIndex.from_bwt(bwt, eof, cnt)
+    monkeypatch.setenv("FMX_TLB_REACH_GB", "%.6f" % ((4e9 + 20 * len(bwt)) / 1e9))      # 8n fits, 32n does not
+    g = fx.GpuFMSearcher(bwt=bwt, eof=eof, counts=cnt)
+    info = g.info()
+    assert info["ctx_entry_bytes"] == 8 and info["ctx_depth"] == 16 and not info["text_shortcut"] and 4 ** info["kmer_k"] >= len(bwt) // 2
+    tp = bytes(fo.file_to_text_rev(text))
+    for ln in (12, 16 + info["kmer_k"], 32, 40):
+        offs = rng.integers(0, len(tp) - ln, 3000)
+        arr = np.stack([np.frombuffer(tp[s:s + ln], np.uint8) for s in offs]).copy()
+        arr[::7, ln // 2] = ord("A")                        # some near misses
+        sp, ep = g.count_fixed(arr)
+        osp, oep = o.count_batch(arr.reshape(-1), np.arange(0, arr.size + 1, ln, dtype=np.int64))
+        assert np.array_equal(sp, osp) and np.array_equal(ep, oep)
+    off, pos = g.locate_batch(sp[:50], ep[:50])
+    sa = o.sa().astype(np.int64)
+    for k in range(50):
+        assert np.array_equal(pos[off[k]:off[k + 1]], np.sort(sa[sp[k]:ep[k]]))
+    g.close()
+    o.close()
 
 
 # ----------------------------------------------------------------------------------------------- edge cases
