@@ -3,6 +3,7 @@
 // compute call runs on the index's CUDA stream and fails with FMX_E_CUDA when no device is usable —
 // there is no CPU path in this library.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -1033,8 +1034,8 @@ struct fmx_regex_set {
     int device = 0;
     int64_t m = 0;
     size_t n_states = 0, n_fol = 0, n_first = 0;
-    size_t free_bytes = 0;             // free device memory when the set was first searched (bounds the frontier buffers)
-    int64_t front_hint = 0;            // largest frontier the last search of this set saw: the next search sizes its buffers for it
+    std::atomic<size_t> free_bytes{0}; // free device memory when the set was first searched (bounds the frontier buffers)
+    std::atomic<int64_t> front_hint{0};           // largest frontier the last search of this set saw: the next search sizes its buffers for it
     void *d_c = nullptr, *d_last = nullptr, *d_rx = nullptr, *d_fo = nullptr, *d_f = nullptr, *d_first = nullptr;
 };
 
@@ -1110,12 +1111,13 @@ int fmx_regex_set_search(fmx_index *ix, fmx_regex_set *set, int64_t cap_total, i
     RegexTables rt{(const uint8_t *)set->d_c, (const uint8_t *)set->d_last, (const uint32_t *)set->d_rx, (const uint32_t *)set->d_fo, (const uint32_t *)set->d_f};
 
     if (set->free_bytes == 0) { size_t fr0 = 0, to0 = 0; cudaMemGetInfo(&fr0, &to0); set->free_bytes = fr0; }   // once per set: the query costs ~0.1 ms
-    const size_t fr = set->free_bytes;
+    const size_t fr = set->free_bytes.load();
     // two ping-pong frontier buffers; they start small and are regrown (and the traversal rerun) when a level outgrows them,
     // bounded by an eighth of the free device memory each
     const int64_t n_first = (int64_t)set->n_first;
     const int64_t max_front = std::max<int64_t>(std::min<int64_t>((int64_t)(fr / 8 / sizeof(FrontierItem)), 1ll << 28), n_first);
-    int64_t cap = std::min<int64_t>(max_front, std::max<int64_t>(std::max<int64_t>(n_first * 16, 1 << 20), set->front_hint + set->front_hint / 8));
+    const int64_t hint = set->front_hint.load();
+    int64_t cap = std::min<int64_t>(max_front, std::max<int64_t>(std::max<int64_t>(n_first * 16, 1 << 20), hint + hint / 8));
     int64_t cap_res = std::max<int64_t>(cap_total, 1 << 16);
     void *cur = nullptr, *nxt = nullptr;
     CU(cudaMallocAsync(&cur, cap * sizeof(FrontierItem), st)); CU(cudaMallocAsync(&nxt, cap * sizeof(FrontierItem), st));
@@ -1280,6 +1282,49 @@ int fmx_build_index_files(const uint8_t *text, int64_t len, const char *base, in
     int rc = build_bwt_impl(text, len, device, bwt, &eof, counts, write_fm ? &fm : nullptr);
     if (rc) return rc;
     return write_index_files(strip_extension(base), bwt.data(), (int64_t)bwt.size(), eof, counts, big_endian != 0, write_fm ? fm.data() : nullptr);
+}
+
+// SACreator.create (bwtmerger.scala:535-556): <base>.sa = n x int32 big-endian, no header, sa[r] as bwtFm2sa (util.scala:213-224).
+// The reference walks the .fm array with one seek+write per row; here the suffix array the index already holds (or one built for
+// the occasion by the parallel LF chain walks) is copied out.
+int fmx_write_sa_file(fmx_index *ix, const char *path) {
+    CHECK_IX(ix);
+    if (!path) return fail(FMX_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    const int64_t n = ix->n;
+    std::vector<uint32_t> h((size_t)n);
+    if (ix->d.sa != nullptr) {
+        CU(cudaMemcpyAsync(h.data(), ix->d.sa, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    } else if (n <= 2) {
+        for (int64_t r = 0; r < n; ++r) h[(size_t)r] = (uint32_t)(r == ix->eof ? 0 : n - 1);      // n = 1: sa = [0]; n = 2: sa[eof] = 0, sa[0] = 1
+    } else {
+        DBuf sa(st), isa(st), text(st);
+        CU(sa.alloc((size_t)n * 4)); CU(isa.alloc((size_t)n * 4)); CU(text.alloc((size_t)n + 16));
+        std::string err;
+        cudaError_t e = build_full_sa(ix->d, ix->cfg.layout, sa.as<uint32_t>(), isa.as<uint32_t>(), text.as<uint8_t>(), st, err);
+        if (e != cudaSuccess) return fail(err.empty() ? FMX_E_CUDA : FMX_E_FORMAT, "suffix array construction failed: %s", err.empty() ? cudaGetErrorString(e) : err.c_str());
+        CU(cudaMemcpyAsync(h.data(), sa.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    const std::string file = strip_extension(path) + ".sa";
+    FILE *f = std::fopen(file.c_str(), "wb");
+    if (!f) return fail(FMX_E_IO, "cannot create %s", file.c_str());
+    std::vector<uint8_t> buf(1 << 20);
+    bool ok = true;
+    for (int64_t i = 0; ok && i < n;) {
+        size_t k = 0;
+        for (; k + 4 <= buf.size() && i < n; ++i, k += 4) {
+            const uint32_t v = h[(size_t)i];
+            buf[k] = (uint8_t)(v >> 24); buf[k + 1] = (uint8_t)(v >> 16); buf[k + 2] = (uint8_t)(v >> 8); buf[k + 3] = (uint8_t)v;
+        }
+        ok = std::fwrite(buf.data(), 1, k, f) == k;
+    }
+    std::fclose(f);
+    if (!ok) return fail(FMX_E_IO, "short write %s", file.c_str());
+    return FMX_OK;
 }
 
 }  // extern "C"

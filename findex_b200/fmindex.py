@@ -454,6 +454,11 @@ class GpuFMSearcher:
         _check(lib().fmx_count_only_fixed(self.h, _ptr(pat2d), ln, m, _ptr(cnt)))
         return cnt
 
+    def write_sa_file(self, path):
+        """SACreator(path).create(): <base>.sa, n x int32 big-endian"""
+        lib().fmx_write_sa_file.argtypes = [C.c_void_p, C.c_char_p]
+        _check(lib().fmx_write_sa_file(self.h, os.fsencode(path)))
+
     def set_lanes(self, lanes):
         _check(lib().fmx_set_lanes(self.h, lanes))
 

@@ -239,6 +239,10 @@ int fmx_build_index_files(const uint8_t *text, int64_t len, const char *base, in
 int fmx_build_bwt(const uint8_t *text, int64_t len, uint8_t *bwt_out, int64_t *n_out, int64_t *eof_out,
                   int64_t counts_out[256], int device);
 
+/* SACreator(filename).create()  M/bwtmerger.scala:535-556: writes <base>.sa (n x int32 big-endian, no header; SALoader :214-249 reads it),
+ * sa[r] as bwtFm2sa (M/util.scala:213-224).  Uses the resident suffix array when the index has one, else builds it for the call.      */
+int fmx_write_sa_file(fmx_index *ix, const char *path);
+
 #ifdef __cplusplus
 }
 #endif

@@ -598,6 +598,19 @@ def test_compact_contexts_are_chosen_when_the_wide_form_does_not_fit(monkeypatch
     o.close()
 
 
+@pytest.mark.parametrize("accel", [fx.ACCEL_AUTO, fx.ACCEL_NONE], ids=["resident_sa", "built_for_the_call"])
+def test_write_sa_file_is_sacreator_output(ref_dir, tmp_path, accel):
+    """SACreator.create (bwtmerger.scala:535-556): <base>.sa = n x int32 big-endian, no header, == bwtFm2sa (G7, T/Indexer.scala:1043-1068)"""
+    o = fo.OracleIndex.load(os.path.join(ref_dir, "test1024.cmp"), big_endian=False)
+    g = fx.GpuFMSearcher(os.path.join(ref_dir, "test1024.cmp.bwt"), bigEndian=False, accel=accel)
+    g.write_sa_file(str(tmp_path / "t.whatever"))
+    raw = (tmp_path / "t.sa").read_bytes()
+    assert len(raw) == 4 * o.n
+    assert np.array_equal(np.frombuffer(raw, ">i4").astype(np.int64), o.sa().astype(np.int64))
+    g.close()
+    o.close()
+
+
 # ----------------------------------------------------------------------------------------------- edge cases
 @pytest.mark.parametrize("accel", [fx.ACCEL_AUTO, fx.ACCEL_NONE], ids=["auto", "none"])
 @pytest.mark.parametrize("cfg", [(fx.LAYOUT_WM, 2), (fx.LAYOUT_PLANES, 4)], ids=_ids)
