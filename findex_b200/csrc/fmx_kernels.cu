@@ -53,16 +53,33 @@ count_fixed_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restric
     const bool active = g < nq;
     uint32_t sp, ep, touched = 0, steps = 0;
     search_pattern<G, LAYOUT, STATS>(ix, tb, SmemPattern{spat + g * len, len, (len & 3) == 0}, len, active, sp, ep, touched, steps);
+    const bool hit = sp < ep;
+    const uint32_t cnt = hit ? ep - sp : 0u;
     if (active && (threadIdx.x % G) == 0) {
-        const bool hit = sp < ep;
         sp_out[q0 + g] = hit ? (OutT)sp : (OutT)0;
         ep_out[q0 + g] = hit ? (OutT)ep : (OutT)0;
-        // fused exchange: the hit count goes straight into every rank's gathered buffer (peer-mapped memory over
-        // NVLink/NVSwitch); consecutive queries of a warp form one contiguous 64-B (G=2) store segment per peer
-        if (sinks.n > 0) {
-            const uint32_t cnt = hit ? ep - sp : 0u;
-#pragma unroll 1
-            for (int j = 0; j < sinks.n; ++j) sinks.p[j][sinks.offset + q0 + g] = cnt;
+        if (sinks.n == 1) sinks.p[0][sinks.offset + q0 + g] = cnt;          // count-only host call: one local sink
+    }
+    // fused exchange: the CTA's hit counts go straight into every rank's gathered buffer (peer-mapped memory over NVLink/NVSwitch).
+    // They are transposed through shared memory so that a warp stores 512 contiguous bytes (32 lanes x 16 B) to ONE peer: per CTA
+    // 2 store instructions per peer instead of one 128-byte store per warp and peer (each remote store instruction costs the kernel
+    // about as much as a local request; measured +1.6 % of the step per peer before).
+    if (sinks.n > 1) {                                                       // grid-uniform
+        __shared__ __align__(16) uint32_t scnt[kThreads];
+        if ((threadIdx.x % G) == 0) scnt[g] = active ? cnt : 0u;
+        __syncthreads();
+        const long long base = sinks.offset + q0;
+        if (nq == QPB && (base & 3) == 0) {
+            constexpr int V = QPB / 4;                                       // 16-byte pieces per peer
+            for (int w = threadIdx.x; w < sinks.n * V; w += kThreads) {
+                const int j = w / V, k = w - j * V;
+                reinterpret_cast<uint4 *>(sinks.p[j] + base)[k] = reinterpret_cast<const uint4 *>(scnt)[k];
+            }
+        } else {
+            for (int w = threadIdx.x; w < sinks.n * nq; w += kThreads) {
+                const int j = w / nq, k = w - j * nq;
+                sinks.p[j][base + k] = scnt[k];
+            }
         }
     }
     if (STATS) {

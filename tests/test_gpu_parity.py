@@ -400,15 +400,16 @@ def test_regex_frontier_growth_and_replay(ref_dir, o1024):
     g.close()
 
 
-def test_fused_count_and_exchange_single_gpu(ref_dir):
+@pytest.mark.parametrize("m,lanes", [(3000, 2), (3003, 2), (3000, 1), (3003, 4)])
+def test_fused_count_and_exchange_single_gpu(ref_dir, m, lanes):
     """The fused count+all-gather entry point with this GPU playing every rank: three 'ranks' shard a batch and each stores its
     hit counts into all three gathered buffers; every buffer must end up holding the counts of the whole batch."""
     import torch
     text = open(os.path.join(ref_dir, "test.txt"), "rb").read()
     o = fo.OracleIndex.load(os.path.join(ref_dir, "test.cmp"), big_endian=False)
-    g = _open(os.path.join(ref_dir, "test.cmp.bwt"), (fx.LAYOUT_PLANES, 2))
+    g = _open(os.path.join(ref_dir, "test.cmp.bwt"), (fx.LAYOUT_PLANES, lanes))
     rng = np.random.default_rng(3)
-    m, ln, world = 3000, 6, 3
+    ln, world = 6, 3                                        # m = 3003: shard offsets 1001, 2002 are not 16-byte aligned (scalar stores)
     offs = rng.integers(0, len(text) - ln, m)
     tarr = np.frombuffer(text, np.uint8)
     pats = np.stack([tarr[s:s + ln][::-1] for s in offs])
