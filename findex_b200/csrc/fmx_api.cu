@@ -28,7 +28,7 @@ struct fmx_index {
     bool accel_text = false;
     int kmer_k = 0;
     DevIndex d{};
-    LaunchCfg cfg{FMX_LAYOUT_WM, 4, 0};
+    LaunchCfg cfg{FMX_LAYOUT_WM, 4};
     int64_t n = 0, eof = 0;
     int64_t C[257] = {0};
     int64_t counts0[256] = {0};        // raw counts (bucketStarts0 / pos2char)
@@ -132,14 +132,8 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     if (layout != FMX_LAYOUT_WM && layout != FMX_LAYOUT_PLANES) return fail(FMX_E_ARG, "bad layout %d", layout);
     int lanes = o.lanes_per_query ? o.lanes_per_query : 2;      // re-tuned below once the accelerators are known
     if (lanes != 1 && lanes != 2 && lanes != 4) return fail(FMX_E_ARG, "lanes_per_query must be 1, 2 or 4");
-    ix->cfg = LaunchCfg{layout, lanes, 0};
-    {
-        int sms = 0;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
-        const char *env = std::getenv("FMX_PERSISTENT");                 // 1 enables the persistent form (measured slower: 7.97 vs 9.26 G q/s on cfg 2)
-        if (env && env[0] == '1') ix->cfg.persistent_ctas = sms * (lanes == 1 ? 4 : 8);
-        if (const char *mb = std::getenv("FMX_MINB")) ix->cfg.min_blocks = std::atoi(mb);
-    }
+    ix->cfg = LaunchCfg{layout, lanes};
+    if (const char *mb = std::getenv("FMX_MINB")) ix->cfg.min_blocks = std::atoi(mb);      // occupancy experiment (profiles/r01_count_design_sweep.jsonl)
     ix->index_bytes = (layout == FMX_LAYOUT_PLANES ? planes_bytes : wm_bytes) + n;
 
     // base[c]: PLANES: C[c].  WM: C[c] - start_final[code], where after `levels` stable bit partitions the

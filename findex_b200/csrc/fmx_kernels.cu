@@ -92,54 +92,6 @@ count_fixed_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restric
     }
 }
 
-// Persistent form of the same kernel: the grid is sized to the machine (SMs x resident CTAs), the operator tables are staged once
-// per CTA, and every warp walks its own sequence of 32/G-query tiles (stage patterns -> search -> store) without CTA-wide barriers, so
-// a warp whose queries die early moves on instead of idling until its CTA drains.
-template <int G, int LAYOUT, typename OutT>
-__global__ void __launch_bounds__(kThreads, (G == 1) ? 4 : 8)
-count_fixed_persistent_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, int len, long long m,
-                              OutT *__restrict__ sp_out, OutT *__restrict__ ep_out, const __grid_constant__ PeerSinks sinks) {
-    __shared__ SharedTables tb;
-    extern __shared__ __align__(16) uint8_t spat[];
-    constexpr int QPW = 32 / G;                            // queries per warp tile
-    load_tables(tb, ix);
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *wpat = spat + (size_t)warp * QPW * len;       // this warp's staging area (16-byte aligned when len % 16 == 0 or QPW*len % 16 == 0)
-    const long long ntiles = (m + QPW - 1) / QPW;
-    const long long nwarps = (long long)gridDim.x * (kThreads / 32);
-    for (long long tile = (long long)blockIdx.x * (kThreads / 32) + warp; tile < ntiles; tile += nwarps) {
-        const long long q0 = tile * QPW;
-        const int nq = (int)((m - q0) < (long long)QPW ? (m - q0) : (long long)QPW);
-        const uint8_t *src = pat + q0 * len;
-        const int nbytes = nq * len;
-        if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(wpat)) & 15) == 0) {
-            const int nvec = nbytes >> 4;
-            for (int i = lane; i < nvec; i += 32) reinterpret_cast<uint4 *>(wpat)[i] = ldg128(reinterpret_cast<const uint4 *>(src) + i);
-            for (int i = (nvec << 4) + lane; i < nbytes; i += 32) wpat[i] = src[i];
-        } else {
-            for (int i = lane; i < nbytes; i += 32) wpat[i] = src[i];
-        }
-        __syncwarp();
-        const int g = lane / G;
-        const bool active = g < nq;
-        uint32_t sp, ep, touched = 0, steps = 0;
-        search_pattern<G, LAYOUT, false>(ix, tb, SmemPattern{wpat + g * len, len, (len & 3) == 0 && (reinterpret_cast<uintptr_t>(wpat) & 3) == 0},
-                                         len, active, sp, ep, touched, steps);
-        if (active && (lane % G) == 0) {
-            const bool hit = sp < ep;
-            sp_out[q0 + g] = hit ? (OutT)sp : (OutT)0;
-            ep_out[q0 + g] = hit ? (OutT)ep : (OutT)0;
-            if (sinks.n > 0) {
-                const uint32_t cnt = hit ? ep - sp : 0u;
-#pragma unroll 1
-                for (int j = 0; j < sinks.n; ++j) sinks.p[j][sinks.offset + q0 + g] = cnt;
-            }
-        }
-        __syncwarp();                                      // the staging area is reused by the next tile
-    }
-}
-
 template <int G, int LAYOUT>
 __global__ void __launch_bounds__(kThreads)
 count_var_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, const long long *__restrict__ off,
@@ -550,22 +502,12 @@ cudaError_t launch_count_fixed(const DevIndex &ix, LaunchCfg cfg, const uint8_t 
     if (sinks_or_null) sinks = *sinks_or_null;
     const size_t smem = (size_t)(kThreads / cfg.lanes) * (size_t)(len > 0 ? len : 1);
     if (smem > 160 * 1024) return cudaErrorInvalidValue;
-    const bool persistent = cfg.persistent_ctas > 0 && !d_stats;
-    const unsigned pgrid = (unsigned)std::min<int64_t>((m + kThreads / cfg.lanes - 1) / (kThreads / cfg.lanes), (int64_t)cfg.persistent_ctas);
 #define CALL(G, LAY)                                                                                                  \
     {                                                                                                                 \
         if (d_stats) {                                                                                                \
             auto k = count_fixed_kernel<G, LAY, true, uint32_t>;                                                      \
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
             k<<<grid_for(m, G), kThreads, smem, st>>>(ix, d_pat, len, m, (uint32_t *)d_sp, (uint32_t *)d_ep, d_stats, sinks); \
-        } else if (persistent && out64) {                                                                             \
-            auto k = count_fixed_persistent_kernel<G, LAY, long long>;                                                \
-            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
-            k<<<pgrid, kThreads, smem, st>>>(ix, d_pat, len, m, (long long *)d_sp, (long long *)d_ep, sinks);        \
-        } else if (persistent) {                                                                                      \
-            auto k = count_fixed_persistent_kernel<G, LAY, uint32_t>;                                                 \
-            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
-            k<<<pgrid, kThreads, smem, st>>>(ix, d_pat, len, m, (uint32_t *)d_sp, (uint32_t *)d_ep, sinks);          \
         } else if (out64) {                                                                                           \
             auto k = count_fixed_kernel<G, LAY, false, long long>;                                                    \
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \

@@ -9,7 +9,6 @@ constexpr int kThreads = 256;
 struct LaunchCfg {
     int layout;          // FMX_LAYOUT_WM / FMX_LAYOUT_PLANES
     int lanes;           // 1, 2 or 4 lanes per query
-    int persistent_ctas = 0;   // > 0: count kernels run persistently on this many CTAs (SMs x resident CTAs per SM)
     int count_lanes = 0;       // > 0: lanes per query of the count kernels only (one lane once row contexts answer most queries in a
                                // single 32-byte request each: twice the queries in flight, half the instructions per query)
     int min_blocks = 0;        // 4 or 6: the device-pointer count kernel compiled for that many resident CTAs per SM (0 = default: 8, 6 at one lane)

@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <optional>
 #include <stdexcept>
+#include <memory>
 #include <string>
 #include <utility>
 #include <vector>
@@ -104,6 +105,11 @@ public:
         sp.assign(pats.size(), 0); ep.assign(pats.size(), 0);
         check(fmx_count_batch(h_, reinterpret_cast<const uint8_t *>(flat.data()), off.data(), (int64_t)pats.size(), sp.data(), ep.data()));
     }
+    // m patterns of `len` bytes back to back; (sp, ep) as the reference's Int rows (fmx_count_fixed_i32; None = (0, 0))
+    void searchFixed(const uint8_t *pat, int32_t len, int64_t m, std::vector<int32_t> &sp, std::vector<int32_t> &ep) const {
+        sp.assign((size_t)m, 0); ep.assign((size_t)m, 0);
+        check(fmx_count_fixed_i32(h_, pat, len, m, sp.data(), ep.data()));
+    }
     std::vector<int64_t> locate(int64_t sp, int64_t ep) const {
         std::vector<int64_t> pos((size_t)(ep > sp ? ep - sp : 1)); int64_t off[2];
         check(fmx_locate_batch(h_, &sp, &ep, 1, ep > sp ? ep - sp : 0, off, pos.data()));
@@ -124,6 +130,7 @@ inline std::string SAResult::toString() const {
 
 class ReTree {                          // ReTree(REParser.re2post(str, lineOnly)); engine 1 = REParser.createNFA(re2post(str))
 public:
+    explicit ReTree(fmx_regex *adopted) : h_(adopted) {}
     explicit ReTree(const std::string &re, bool lineOnly = false, int engine = FMX_ENGINE_GLUSHKOV) {
         check(fmx_regex_compile_engine(reinterpret_cast<const uint8_t *>(re.data()), (int64_t)re.size(), lineOnly ? 1 : 0, engine, &h_));
     }
@@ -148,6 +155,8 @@ public:
         return r;
     }
 
+    fmx_regex *handle() const { return h_; }
+
 private:
     fmx_regex *h_ = nullptr;
 };
@@ -155,6 +164,46 @@ private:
 // REParser.matchSA(REParser.createNFA(REParser.re2post(re)), sa)  — re2.scala:264-334, 568-693, uncapped
 struct ThompsonNFA : ReTree {
     explicit ThompsonNFA(const std::string &re, bool lineOnly = false) : ReTree(re, lineOnly, FMX_ENGINE_THOMPSON) {}
+};
+
+// DFA engine (dfa.scala): states are added with addState(kind) and linked with link(from, to, chr) in the order the reference's
+// s.link(...) calls were made; build() = DFA.processLinkList(start): numbering, moves, compileBuckets.  matchSA = DFA.matchSA, cap off.
+class DFABuilder {
+public:
+    enum Kind { Start = 0, Plain = 1, Finish = 2 };        // StartState / State / FinishState  (dfa.scala:325-336)
+    int addState(Kind k) { kind_.push_back((uint8_t)k); links_.emplace_back(); return (int)kind_.size() - 1; }
+    void link(int from, int to, int chr) { links_[(size_t)from].insert(links_[(size_t)from].begin(), {to, chr}); }    // link() prepends (:299)
+    struct DFA : ReTree {
+        using ReTree::ReTree;
+        std::string buckets(int state) const {             // buckets(state).mkString(",")
+            int64_t need = 0;
+            fmx_dfa_buckets(handle(), state, nullptr, 0, &need);
+            std::string s((size_t)(need > 0 ? need : 1), '\0');
+            check(fmx_dfa_buckets(handle(), state, &s[0], (int64_t)s.size(), nullptr));
+            s.resize(std::char_traits<char>::length(s.c_str()));
+            return s;
+        }
+        bool matchString(const std::string &w) const {
+            int32_t m = 0;
+            check(fmx_dfa_match_string(handle(), reinterpret_cast<const uint8_t *>(w.data()), (int64_t)w.size(), &m));
+            return m != 0;
+        }
+    };
+    std::unique_ptr<DFA> build() const {
+        std::vector<int32_t> off(kind_.size() + 1, 0), to, chr;
+        for (size_t i = 0; i < kind_.size(); ++i) {
+            for (const auto &l : links_[i]) { to.push_back(l.first); chr.push_back(l.second); }
+            off[i + 1] = (int32_t)to.size();
+        }
+        if (to.empty()) { to.push_back(0); chr.push_back(0); }
+        fmx_regex *h = nullptr;
+        check(fmx_dfa_create((int32_t)kind_.size(), kind_.data(), off.data(), to.data(), chr.data(), &h));
+        return std::unique_ptr<DFA>(new DFA(h));
+    }
+
+private:
+    std::vector<uint8_t> kind_;
+    std::vector<std::vector<std::pair<int, int>>> links_;
 };
 
 }  // namespace fmx

@@ -62,6 +62,35 @@ int main(int argc, char **argv) {
     std::set<std::string> shown;
     for (const auto &m : fmx::ThompsonNFA("(((b|a)|d)|e)c").matchSA(sa)) shown.insert(m.toString());
     REQUIRE(shown == (std::set<std::string>{"ec", "dc", "[2 Results] ac", "bc"}));
+    // DFATests (T/dfa.scala:62-105) through the C++ mirror: `ab*c`
+    {
+        fmx::DFABuilder b;
+        const int s = b.addState(fmx::DFABuilder::Start), a = b.addState(fmx::DFABuilder::Plain), bb = b.addState(fmx::DFABuilder::Plain),
+                  f = b.addState(fmx::DFABuilder::Finish);
+        b.link(s, a, 'a'); b.link(a, bb, 'b'); b.link(bb, bb, 'b'); b.link(bb, f, 'c');
+        auto dfa = b.build();
+        REQUIRE(!dfa->matchString("absbc") && dfa->matchString("abbc") && dfa->matchString("abc"));
+        REQUIRE(dfa->buckets(0) == "DFAChar('a'->1)" && dfa->buckets(1) == "DFAChar('b'->2)");
+        REQUIRE(dfa->buckets(2) == "DFAChar('b'->2),DFAChar('c'->3)" && dfa->buckets(3).empty());
+        for (const auto &m : dfa->matchSA(sa)) {           // every result renders as a string of the language
+            const std::string w = sa.nextSubstr(m.sp, m.len);
+            REQUIRE(w.size() >= 3 && w.front() == 'a' && w.back() == 'c' && w.find_first_not_of('b', 1) == w.size() - 1);
+        }
+        fmx::DFABuilder b2;                                 // `ac`: the index holds it twice ("[2 Results] ac" above)
+        const int s2 = b2.addState(fmx::DFABuilder::Start), a2 = b2.addState(fmx::DFABuilder::Plain), f2 = b2.addState(fmx::DFABuilder::Finish);
+        b2.link(s2, a2, 'a'); b2.link(a2, f2, 'c');
+        const auto r2 = b2.build()->matchSA(sa);
+        REQUIRE(r2.size() == 1 && r2[0].len == 2 && r2[0].cnt() == 2 && r2[0].toString() == "[2 Results] ac");
+    }
+    // fixed-length batch with the reference's Int rows
+    {
+        const std::string pats = "bqxxa" "zzzzz";          // prevSubstr(1,5) of the index (T/Indexer.scala:1119) reversed is a hit; zzzzz is not
+        std::vector<int32_t> sp32, ep32;
+        sa.searchFixed(reinterpret_cast<const uint8_t *>(pats.data()), 5, 2, sp32, ep32);
+        auto one = sa.search("bqxxa");
+        REQUIRE((one ? (sp32[0] == one->first && ep32[0] == one->second) : (sp32[0] == 0 && ep32[0] == 0)));
+        REQUIRE(sp32[1] == 0 && ep32[1] == 0);
+    }
     std::printf("cpp host mirror ok\n");
     return 0;
 }
