@@ -217,6 +217,8 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     double reach = 68e9;
     if (const char *env = std::getenv("FMX_TLB_REACH_GB")) { const double v = std::atof(env); if (v > 0) reach = v * 1e9; }
     const int64_t rank_bytes = (layout == FMX_LAYOUT_PLANES ? planes_bytes : wm_bytes);
+    if ((accel & FMX_ACCEL_CTX8) && accel != FMX_ACCEL_NONE && sigma > 4)
+        return fail(FMX_E_UNSUPPORTED, "FMX_ACCEL_CTX8 stores 2-bit symbols: the text has %d distinct symbols (at most 4 fit)", sigma);
     const bool auto_text = accel == FMX_ACCEL_AUTO && 25 * n + (2ll << 30) < (int64_t)fr && ix->index_bytes + 20 * n <= budget + (24ll << 30);
     // row contexts: the 32-byte form when it fits the reach; for alphabets of <= 4 symbols on larger texts the compact 8-byte form
     const bool fits32 = 32.0 * n + 4e9 <= reach && 57 * n + (8ll << 30) < (int64_t)fr;

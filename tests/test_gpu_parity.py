@@ -572,6 +572,11 @@ def test_row_context_small_intervals(cfg, sigma, form):
     o.close()
 
 
+def test_compact_contexts_refuse_larger_alphabets(ref_dir):
+    with pytest.raises(fx.FmxError, match="2-bit symbols"):
+        fx.GpuFMSearcher(os.path.join(ref_dir, "test1024.cmp.bwt"), bigEndian=False, accel=fx.ACCEL_CTX8)
+
+
 def test_compact_contexts_are_chosen_when_the_wide_form_does_not_fit(monkeypatch):
     """FMX_ACCEL_AUTO on a 4-symbol text whose 32-byte contexts would not fit the (here artificially small) TLB reach: the compact form
     is built, isat is not, the k-mer table saturates, and count/locate still equal the oracle."""
