@@ -6,11 +6,12 @@
 //      occ           : NaiveFMSearcher.occ          bwtmerger.scala:354-375
 //      lf/prev_substr: getPrevI / prevSubstr        bwtmerger.scala:386-389, 409-419
 //   K2 locate        : sa[] of bwtFm2sa             util.scala:213-224, via sampled rows + LF walk
-//   K3 regex level   : ReTree._matchSA loop body    re2/retree.scala:618-653, one BFS level per launch
+//   K3 regex         : ReTree._matchSA              re2/retree.scala:618-653 (also REParser.matchSA, DFA.matchSA): the whole
+//                      breadth-first traversal in one cooperative launch, grid barrier between levels
 //   K4 gather bench  : the random-64-B-gather roofline denominator
 //
-// All of them are HBM-latency/bandwidth bound integer kernels: G (1, 2 or 4) lanes cooperate on one
-// query so that a 64-byte rank block arrives as one coalesced request; the two ends of the interval are
+// All of them are bound by the rate of random HBM requests: G (1, 2 or 4) lanes cooperate on one
+// query so that a 64-byte rank block arrives as ONE request (256-bit loads at G <= 2); the two ends of the interval are
 // fetched together (two independent loads in flight per lane) and share the fetch when they fall into the
 // same block.  Nothing here is GEMM-shaped, so no tensor-core path exists by design.
 #include "fmx_kernels.cuh"
