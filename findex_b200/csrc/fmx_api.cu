@@ -981,6 +981,19 @@ int fmx_dfa_create(int32_t n_states, const uint8_t *kind, const int32_t *link_of
     *out = rx;
     return FMX_OK;
 }
+int fmx_dfa_from_nfa(int32_t n_states, const uint8_t *is_finish, int32_t initial, const int32_t *link_off, const int32_t *link_to,
+                     const int32_t *link_chr, fmx_regex **out) {
+    if (!out) return fail(FMX_E_ARG, "null output");
+    *out = nullptr;
+    if (n_states > 0 && link_off && link_off[n_states] > 0 && (!link_to || !link_chr)) return fail(FMX_E_ARG, "null link arrays");
+    std::vector<uint8_t> kind;
+    std::vector<int32_t> off, to, chr;
+    std::string err;
+    int rc = dfa_from_nfa(n_states, is_finish, initial, link_off, link_to, link_chr, kind, off, to, chr, err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    if (to.empty()) { to.push_back(0); chr.push_back(0); }
+    return fmx_dfa_create((int32_t)kind.size(), kind.data(), off.data(), to.data(), chr.data(), out);
+}
 int fmx_dfa_info(const fmx_regex *dfa, int32_t *n_states, int32_t *moves, uint8_t *finish, int32_t *number, int32_t n_number) {
     if (!dfa || dfa->dfa.n_states == 0) return fail(FMX_E_ARG, "not a DFA handle");
     const CompiledDfa &d = dfa->dfa;

@@ -51,6 +51,10 @@ struct CompiledDfa {
 int compile_dfa(int32_t n_states, const uint8_t *kind, const int32_t *link_off, const int32_t *link_to, const int32_t *link_chr,
                 CompiledDfa &dfa, CompiledRegex &out, std::string &err);
 std::string dfa_bucket_string(const CompiledDfa &dfa, int state);
+// DFA.fromNFA: NFA (link_chr = -1 for an EpsilonLink) -> the state kinds and list-ordered links compile_dfa takes
+int dfa_from_nfa(int32_t n_states, const uint8_t *is_finish, int32_t initial, const int32_t *link_off, const int32_t *link_to,
+                 const int32_t *link_chr, std::vector<uint8_t> &kind, std::vector<int32_t> &d_off, std::vector<int32_t> &d_to,
+                 std::vector<int32_t> &d_chr, std::string &err);
 
 }  // namespace fmx
 

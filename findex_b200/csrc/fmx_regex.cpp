@@ -601,6 +601,69 @@ int compile_dfa(int32_t n_states, const uint8_t *kind, const int32_t *link_off, 
     return FMX_OK;
 }
 
+// DFA.fromNFA(initialState) (dfa.scala:343-389): subset construction over an NFA of NfaBaseState objects with NfaLink(to, chr) and
+// EpsilonLink(to) links (:5-37), then processLinkList.  A DFA state is a set of NFA states closed under epsilon links; the set of the
+// initial state becomes the StartState — also when it contains an NfaFinishState, and also when it is reached again later (:353-359:
+// `if (x == initialStateSet) startState`), so it never accepts; any other set with an NfaFinishState is a FinishState.  The reference
+// adds the DFA links in the iteration order of a hash map, which decides the numbering of automata with more than four states and
+// nothing else; here sets are discovered breadth-first with characters ascending, and links are added in (source, character) order.
+int dfa_from_nfa(int32_t n_states, const uint8_t *is_finish, int32_t initial, const int32_t *link_off, const int32_t *link_to,
+                 const int32_t *link_chr, std::vector<uint8_t> &kind, std::vector<int32_t> &d_off, std::vector<int32_t> &d_to,
+                 std::vector<int32_t> &d_chr, std::string &err) {
+    if (n_states <= 0 || !is_finish || !link_off || initial < 0 || initial >= n_states) { err = "bad NFA description"; return FMX_E_ARG; }
+    for (int i = 0; i < n_states; ++i)
+        for (int k = link_off[i]; k < link_off[i + 1]; ++k)
+            if (link_to[k] < 0 || link_to[k] >= n_states || link_chr[k] < -1 || link_chr[k] > 255) { err = "link out of range"; return FMX_E_ARG; }
+    typedef std::vector<int32_t> Set;                                   // sorted, unique
+    auto closure = [&](const Set &in) {                                 // NFA.epsilons(set): union of s.epsilons
+        std::vector<char> seen((size_t)n_states, 0);
+        std::vector<int32_t> stack(in.begin(), in.end());
+        for (int32_t s : in) seen[(size_t)s] = 1;
+        while (!stack.empty()) {
+            const int32_t s = stack.back(); stack.pop_back();
+            for (int k = link_off[s]; k < link_off[s + 1]; ++k)
+                if (link_chr[k] < 0 && !seen[(size_t)link_to[k]]) { seen[(size_t)link_to[k]] = 1; stack.push_back(link_to[k]); }
+        }
+        Set out;
+        for (int32_t s = 0; s < n_states; ++s) if (seen[(size_t)s]) out.push_back(s);
+        return out;
+    };
+    std::vector<Set> sets;                                              // DFA states in discovery order; sets[0] = closure({initial})
+    std::vector<std::vector<std::pair<int, int>>> trans;               // per DFA state: (chr, target), chr ascending
+    auto find_or_add = [&](const Set &x) {
+        for (size_t i = 0; i < sets.size(); ++i) if (sets[i] == x) return (int)i;
+        sets.push_back(x); trans.emplace_back();
+        return (int)sets.size() - 1;
+    };
+    find_or_add(closure(Set{initial}));
+    for (size_t cur = 0; cur < sets.size(); ++cur) {                    // the queue of psc: every set is expanded once
+        if (sets.size() > 100000) { err = "subset construction exceeds 100000 DFA states"; return FMX_E_LIMIT; }
+        const Set here = sets[cur];
+        for (int c = 0; c < 256; ++c) {                                 // NFA.epsilonTransitions: chr -> union of target closures
+            Set raw;
+            for (int32_t s : here)
+                for (int k = link_off[s]; k < link_off[s + 1]; ++k) if (link_chr[k] == c) raw.push_back(link_to[k]);
+            if (raw.empty()) continue;
+            std::sort(raw.begin(), raw.end());
+            raw.erase(std::unique(raw.begin(), raw.end()), raw.end());
+            const int t = find_or_add(closure(raw));
+            trans[cur].push_back({c, t});
+        }
+    }
+    const int nd = (int)sets.size();
+    kind.assign((size_t)nd, 1);
+    kind[0] = 0;
+    for (int i = 1; i < nd; ++i)
+        for (int32_t s : sets[(size_t)i]) if (is_finish[s]) { kind[(size_t)i] = 2; break; }
+    // link() prepends: after adding a state's links with characters ascending, its list reads characters descending
+    d_off.assign(1, 0); d_to.clear(); d_chr.clear();
+    for (int i = 0; i < nd; ++i) {
+        for (auto it = trans[(size_t)i].rbegin(); it != trans[(size_t)i].rend(); ++it) { d_chr.push_back(it->first); d_to.push_back(it->second); }
+        d_off.push_back((int32_t)d_to.size());
+    }
+    return FMX_OK;
+}
+
 static std::string pretty_chr(int c) {
     char buf[8];
     if (c < 0x20 || c > 0x7e) std::snprintf(buf, sizeof buf, "\\x%x", c); else std::snprintf(buf, sizeof buf, "%c", c);

@@ -127,3 +127,71 @@ class DFA(ReTree):
     def matchSA(self, sa):
         """DFA.matchSA(sa) with the iteration cap off: sorted list of (len, sp, ep)."""
         return sa.regex_search_batch([self])[0]
+
+
+# ---- NFA side: NfaBaseState / NfaState / NfaStartState / NfaFinishState with link() and epsilon() (dfa.scala:5-37, 90-95) and
+# DFA.fromNFA(initialState) (:343-389); the subset construction runs in the library (fmx_dfa_from_nfa).
+class NfaBaseState:
+    FINISH = False
+
+    def __init__(self):
+        self.links = []                     # (to, chr); chr = -1 for an EpsilonLink
+
+    def link(self, to, chr_):
+        self.links.insert(0, (to, chr_ if isinstance(chr_, int) else ord(chr_)))
+
+    def epsilon(self, to):
+        self.links.append((to, -1))
+
+
+class NfaState(NfaBaseState):
+    pass
+
+
+class NfaStartState(NfaBaseState):
+    pass
+
+
+class NfaFinishState(NfaBaseState):
+    FINISH = True
+
+
+def _from_nfa(cls, initial):
+    L = lib()
+    _declare(L)
+    L.fmx_dfa_from_nfa.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    states, seen, todo = [], {}, [initial]
+    while todo:
+        s = todo.pop()
+        if id(s) in seen:
+            continue
+        seen[id(s)] = len(states)
+        states.append(s)
+        todo.extend(to for to, _ in s.links)
+    fin = np.array([1 if s.FINISH else 0 for s in states], np.uint8)
+    off = np.zeros(len(states) + 1, np.int32)
+    to, ch = [], []
+    for i, s in enumerate(states):
+        for t, c in s.links:
+            to.append(seen[id(t)])
+            ch.append(c)
+        off[i + 1] = len(to)
+    to = np.array(to if to else [0], np.int32)
+    ch = np.array(ch if ch else [0], np.int32)
+    h = C.c_void_p()
+    _check(L.fmx_dfa_from_nfa(len(states), _ptr(fin), seen[id(initial)], _ptr(off), _ptr(to), _ptr(ch), C.byref(h)))
+    self = cls.__new__(cls)
+    self.h = h
+    self.regex = b"<dfa from nfa>"
+    n = C.c_int32()
+    _check(L.fmx_dfa_info(h, C.byref(n), None, None, None, 0))
+    self.n_states = n.value
+    moves = np.zeros((self.n_states, 256), np.int32)
+    f = np.zeros(self.n_states, np.uint8)
+    _check(L.fmx_dfa_info(h, None, _ptr(moves), _ptr(f), None, 0))
+    self.moves = moves
+    self.finishStates = set(np.flatnonzero(f).tolist())
+    return self
+
+
+DFA.fromNFA = classmethod(_from_nfa)

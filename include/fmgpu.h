@@ -184,6 +184,12 @@ int  fmx_regex_search_batch(fmx_index *ix, fmx_regex *const *rx, int64_t m, int6
  * expanded.  Free with fmx_regex_free.                                                                                   */
 int fmx_dfa_create(int32_t n_states, const uint8_t *kind, const int32_t *link_off, const int32_t *link_to,
                    const int32_t *link_chr, fmx_regex **out);
+/* DFA.fromNFA(initialState)  M/dfa.scala:343-389: subset construction over an NFA of NfaBaseState objects (:5-37) — state i's links are
+ * link_to/link_chr[link_off[i] .. link_off[i+1]), link_chr = -1 for an EpsilonLink; is_finish[i] marks the NfaFinishState(s).  The set of
+ * the initial state becomes the StartState and never accepts, also when it holds a finish state or is reached again (:353-359); every
+ * other set with a finish state is a FinishState.  Then as fmx_dfa_create.  FMX_E_LIMIT beyond 100000 DFA states.                    */
+int fmx_dfa_from_nfa(int32_t n_states, const uint8_t *is_finish, int32_t initial, const int32_t *link_off, const int32_t *link_to,
+                     const int32_t *link_chr, fmx_regex **out);
 /* moves (n_states x 256, -1 = none), finishStates, and number[i] = DFA index of the caller's state i (-1 = unreachable).    */
 int fmx_dfa_info(const fmx_regex *dfa, int32_t *n_states, int32_t *moves, uint8_t *finish, int32_t *number, int32_t n_number);
 /* buckets(state).mkString(",") with the reference's toString, e.g. "DFABucket('c-d' ->1),DFAChar('f'->1)"  (:190-196)        */

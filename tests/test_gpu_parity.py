@@ -498,6 +498,12 @@ def test_dfa_match_sa(cfg, words_base, words):
         a = pd.DFA(rand(pd, random.Random(seed), list(b"abcdm")))
         b = od.DFA(rand(od, random.Random(seed), list(b"abcdm")))
         assert a.matchSA(g) == b.matchSA(o), seed
+    # DFA.fromNFA (dfa.scala:343-389): `a(b|c)*` + `c` as an NFA with epsilon links, determinised in the library
+    def nfa(m):
+        s, x, y, f = m.NfaStartState(), m.NfaState(), m.NfaState(), m.NfaFinishState()
+        s.link(x, "a"); x.epsilon(y); y.link(y, "b"); y.link(y, "c"); y.link(f, "c")
+        return s
+    assert pd.DFA.fromNFA(nfa(pd)).matchSA(g) == od.DFA(od.from_nfa(nfa(od))).matchSA(o)
     g.close()
     o.close()
 

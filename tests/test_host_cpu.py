@@ -267,3 +267,115 @@ def test_dfa_create_rejects_bad_descriptions():
     off = np.array([0, 1, 1], np.int32)
     to, ch = np.array([5], np.int32), np.array([97], np.int32)
     assert L.fmx_dfa_create(2, fx._ptr(kind), fx._ptr(off), fx._ptr(to), fx._ptr(ch), C.byref(h)) == fx.FMX_E_ARG    # link target out of range
+
+
+# ---------------------------------------------------------------------------------------------- DFA.fromNFA (dfa.scala:343-389), host side
+def _random_nfa(m, rng, n_states, n_links, alphabet):
+    st = [m.NfaStartState()] + [m.NfaFinishState() if rng.random() < 0.25 else m.NfaState() for _ in range(n_states - 1)]
+    for _ in range(n_links):
+        a, b = st[rng.randrange(n_states)], st[rng.randrange(n_states)]
+        if rng.random() < 0.3:
+            a.epsilon(b)
+        else:
+            a.link(b, rng.choice(alphabet))
+    return st[0]
+
+
+def _thompson(m, rx):
+    """Thompson construction of a tiny regex grammar (letters, concatenation, |, *, parentheses) out of the reference's NFA objects"""
+    pos = [0]
+
+    def atom():
+        c = rx[pos[0]]
+        if c == "(":
+            pos[0] += 1
+            s, e = alt()
+            assert rx[pos[0]] == ")"
+            pos[0] += 1
+        else:
+            s, e = m.NfaState(), m.NfaState()
+            s.link(e, c)
+            pos[0] += 1
+        while pos[0] < len(rx) and rx[pos[0]] == "*":
+            pos[0] += 1
+            s2, e2 = m.NfaState(), m.NfaState()
+            s2.epsilon(s); s2.epsilon(e2); e.epsilon(s); e.epsilon(e2)
+            s, e = s2, e2
+        return s, e
+
+    def cat():
+        s, e = atom()
+        while pos[0] < len(rx) and rx[pos[0]] not in "|)":
+            s2, e2 = atom()
+            e.epsilon(s2)
+            e = e2
+        return s, e
+
+    def alt():
+        s, e = cat()
+        while pos[0] < len(rx) and rx[pos[0]] == "|":
+            pos[0] += 1
+            s2, e2 = cat()
+            a, b = m.NfaState(), m.NfaState()
+            a.epsilon(s); a.epsilon(s2); e.epsilon(b); e2.epsilon(b)
+            s, e = a, b
+        return s, e
+
+    s, e = alt()
+    start, fin = m.NfaStartState(), m.NfaFinishState()
+    start.epsilon(s)
+    e.epsilon(fin)
+    return start
+
+
+def test_dfa_from_nfa_matches_oracle_and_the_nfa_language():
+    """fmx_dfa_from_nfa against the oracle's restatement (same moves / finish states / bucket strings) on 200 random NFAs, and against
+    what the NFA itself accepts: direct simulation under the reference's rule that the initial set never accepts, and Python's re for
+    Thompson-built automata (words whose run comes back to the initial set are the documented exception)."""
+    from findex_b200 import dfa as pd
+    from oracle import dfa as od
+    fbuild.build()
+    for seed in range(200):
+        ns, nl = 1 + seed % 8, seed % 30
+        alphabet = [97, 98, 99, 100, 200, 255][: 2 + seed % 5]
+        p = pd.DFA.fromNFA(_random_nfa(pd, random.Random(seed), ns, nl, alphabet))
+        nfa_o = _random_nfa(od, random.Random(seed), ns, nl, alphabet)
+        o = od.DFA(od.from_nfa(nfa_o))
+        assert p.n_states == o.n_states and p.moves.tolist() == o.moves and p.finishStates == o.finish, seed
+        assert p.buckets == [o.bucket_string(i) for i in range(o.n_states)], seed
+        assert 0 not in p.finishStates
+        rng = random.Random(5000 + seed)
+        for _ in range(30):
+            w = bytes(rng.choice(alphabet) for _ in range(rng.randrange(0, 8)))
+            assert p.matchString(w) == od.nfa_accepts(nfa_o, w), (seed, w)
+    rng = random.Random(7)
+    for rx in ["ab*c", "(a|b)*c", "a(b|c)*d", "(ab|cd)*e", "a*b*c", "((a|b)(c|d))*a", "abc", "a|b|c", "(a*b)*c"]:
+        p = pd.DFA.fromNFA(_thompson(pd, rx))
+        nfa_o = _thompson(od, rx)
+        for _ in range(300):
+            w = "".join(rng.choice("abcde") for _ in range(rng.randrange(0, 7)))
+            got = p.matchString(w)
+            assert got == od.nfa_accepts(nfa_o, w.encode()), (rx, w)
+            if got:
+                assert re.fullmatch(rx, w), (rx, w)              # never accepts outside the language
+    # the initial set is the StartState and never accepts: `a*` as an NFA accepts "" and "a...", its DFA accepts nothing that returns there
+    p = pd.DFA.fromNFA(_thompson(pd, "a*"))
+    assert not p.matchString("") and 0 not in p.finishStates
+
+
+def test_dfa_from_nfa_rejects_bad_descriptions():
+    import ctypes as C
+    from findex_b200 import dfa as pd
+    L = fx.lib()
+    pd._declare(L)
+    L.fmx_dfa_from_nfa.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    h = C.c_void_p()
+    fin = np.array([0, 1], np.uint8)
+    off = np.array([0, 1, 1], np.int32)
+    to, ch = np.array([1], np.int32), np.array([97], np.int32)
+    assert L.fmx_dfa_from_nfa(2, fx._ptr(fin), 5, fx._ptr(off), fx._ptr(to), fx._ptr(ch), C.byref(h)) == fx.FMX_E_ARG     # initial out of range
+    ch = np.array([300], np.int32)
+    assert L.fmx_dfa_from_nfa(2, fx._ptr(fin), 0, fx._ptr(off), fx._ptr(to), fx._ptr(ch), C.byref(h)) == fx.FMX_E_ARG     # character out of range
+    ch = np.array([97], np.int32)
+    assert L.fmx_dfa_from_nfa(2, fx._ptr(fin), 0, fx._ptr(off), fx._ptr(to), fx._ptr(ch), C.byref(h)) == fx.FMX_OK
+    L.fmx_regex_free(h)
