@@ -13,6 +13,9 @@ Pinned: every assertion of the reference's DFATests (src/test/scala/org/fmindex/
 (tests/test_oracle_golden.py::test_dfa_*): matchString on `ab*c`, the three compileBuckets strings, and the two results "cbbba" / "cba"
 of matchSA over reverse("mmabcacadabbbca").
 
+PARITY UNPINNED for `from_nfa` (DFA.fromNFA, M/dfa.scala:343-389, at the end of this file): no reference test touches it; it is checked
+against direct NFA simulation instead.
+
 Behaviour kept on purpose:
   * a run of two or more consecutive characters with the same target becomes a DFABucket, and StatePoint.expand only follows
     DFAChar actions (`case _ => None`, :247-249): character ranges are never traversed by matchSA.
