@@ -546,14 +546,19 @@ def cpu_baseline(args, base, pats, sp, ep, cnt, regex=None):
     want_ep = np.where(cnt[:sample] > 0, ep[:sample], 0)
     parity = bool(np.array_equal(osp, want_sp) and np.array_equal(oep, want_ep))
     assert parity, "GPU (sp,ep) differ from the oracle on the CPU-baseline sample"
-    extra = {}
+    # single-thread figure: the same algorithm on one core, about two seconds of it
+    one = int(min(sample, max(2000, rate / max(cores, 1) * 2.0)))
+    t1 = time.time()
+    ix.count_batch(pats[:one].reshape(-1), off[:one + 1], threads=1)
+    dt1 = time.time() - t1
+    extra = {"single_thread": {"value": one / max(dt1, 1e-9), "unit": UNIT, "cores": 1, "sample": "first %d queries, %.1f s" % (one, dt1)}}
     if regex is not None:                                 # the oracle's uncapped ReTree._matchSA on a sample of the regex batch (1 thread)
         t1 = time.time()
         ok = all(ix.regex_match(rx, max_expansions=50_000_000) == want for rx, want in regex["sample"])
         dtr = time.time() - t1
         assert ok, "GPU regex results differ from the oracle on the sample"
-        extra = {"regex": {"value": len(regex["sample"]) / dtr, "unit": "regexes/s", "cores": 1, "sample": "%d regexes of the batch" % len(regex["sample"]),
-                           "parity_on_sample": bool(ok)}}
+        extra["regex"] = {"value": len(regex["sample"]) / dtr, "unit": "regexes/s", "cores": 1, "sample": "%d regexes of the batch" % len(regex["sample"]),
+                          "parity_on_sample": bool(ok)}
     ix.close()
     return dict({"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
                  "sample": "first %d of the %d-query batch, %d threads, %.1f s" % (sample, len(pats), cores, dt),
