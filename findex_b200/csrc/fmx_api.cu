@@ -886,6 +886,11 @@ int fmx_next_substr_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t 
     return FMX_OK;
 }
 
+// One name for both walks (the sketch of SURVEY §8b): direction > 0 = nextSubstr, else prevSubstr.
+int fmx_extract_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t len, int32_t direction, uint8_t *out, int32_t *out_len) {
+    return direction > 0 ? fmx_next_substr_batch(ix, row, m, len, out, out_len) : fmx_prev_substr_batch(ix, row, m, len, out, out_len);
+}
+
 // ---- locate ---------------------------------------------------------------------------------------------------
 int fmx_locate_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, int64_t m, int64_t cap_total, int64_t *out_off, int64_t *pos) {
     CHECK_IX(ix);

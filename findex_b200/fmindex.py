@@ -404,6 +404,15 @@ class GpuFMSearcher:
         _check(lib().fmx_next_substr_batch(self.h, _ptr(rows), len(rows), ln, _ptr(out), _ptr(olen)))
         return [out[i, :olen[i]].tobytes() for i in range(len(rows))]
 
+    def extract_batch(self, rows, ln, direction):
+        """fmx_extract_batch: nextSubstr (direction > 0) or prevSubstr for a batch of rows"""
+        rows = _i64(rows)
+        out = np.zeros((len(rows), max(ln, 1)), np.uint8)
+        olen = np.zeros(len(rows), np.int32)
+        lib().fmx_extract_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        _check(lib().fmx_extract_batch(self.h, _ptr(rows), len(rows), ln, direction, _ptr(out), _ptr(olen)))
+        return [out[i, :olen[i]].tobytes() for i in range(len(rows))]
+
     def regex_search_batch(self, trees, cap_total=1 << 20):
         """trees: list of ReTree.  Returns per regex the sorted list of (len, sp, ep)."""
         m = len(trees)

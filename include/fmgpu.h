@@ -149,6 +149,8 @@ int fmx_pos2char(const fmx_index *ix, int64_t key, int32_t *c);                 
  * out_len[m] the bytes written per row (nextSubstr stops after the '\0').                              */
 int fmx_prev_substr_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t len, uint8_t *out, int32_t *out_len);
 int fmx_next_substr_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t len, uint8_t *out, int32_t *out_len);
+/* Both walks under one name: direction > 0 = nextSubstr, else prevSubstr.                              */
+int fmx_extract_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t len, int32_t direction, uint8_t *out, int32_t *out_len);
 
 /* ---- regex: REParser.re2post M/re2/re2.scala:50-185 + ReTree.apply M/re2/retree.scala:156-370 -------
  * Compiles on the host to the reference's Glushkov position automaton, quirks included;

@@ -125,6 +125,7 @@ def test_operator_parity_small(ref_dir, cfg, name):
     sub = rows[::17]
     assert g.prev_substr_batch(sub, 9) == [o.prevSubstr(int(r), 9) for r in sub]
     assert g.next_substr_batch(sub, 9) == [o.nextSubstr(int(r), 9) for r in sub]
+    assert g.extract_batch(sub, 9, +1) == g.next_substr_batch(sub, 9) and g.extract_batch(sub, 9, -1) == g.prev_substr_batch(sub, 9)
     # locate == sorted sa[sp..ep)
     sa = o.sa().astype(np.int64)
     ivs = [(0, n), (5, 5), (17, 400), (n - 1, n), (o.eof, o.eof + 1)]
