@@ -27,7 +27,9 @@ struct fmx_index {
     int64_t chunk_queries = 0;
     bool accel_text = false;
     int kmer_k = 0;
-    DevIndex d{};
+    DevIndex d{};                      // what the kernels see (fmx_set_accel_mask may hide accelerators)
+    DevIndex d_full{};                 // everything that was built
+    int count_lanes_full = 0;
     LaunchCfg cfg{FMX_LAYOUT_WM, 4};
     int64_t n = 0, eof = 0;
     int64_t C[257] = {0};
@@ -55,6 +57,12 @@ struct DBuf {
     explicit DBuf(cudaStream_t s) : st(s) {}
     ~DBuf() { if (p) cudaFreeAsync(p, st); }
     cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, st); }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct SaBuf {
+    void *p = nullptr;
+    ~SaBuf() { if (p) cudaFree(p); }
     template <typename T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
@@ -124,10 +132,15 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     int layout = o.layout;
     const int64_t planes_bytes = (int64_t)std::max(sigma, 1) * nblk * 64, wm_bytes = (int64_t)levels * nblk * 64;
     const int64_t budget = o.max_index_bytes > 0 ? o.max_index_bytes : (64ll << 30);
+    // max_total_bytes bounds EVERYTHING resident for this index (rank structure, BWT, sampled SA, accelerators); 0 = what the device holds
+    const int64_t total_cap = o.max_total_bytes > 0 ? o.max_total_bytes : (1ll << 62);
+    if (o.max_total_bytes > 0 && wm_bytes + n > total_cap && layout != FMX_LAYOUT_PLANES)
+        return fail(FMX_E_ARG, "max_total_bytes = %lld is below the smallest index of this text (%lld bytes: wavelet matrix + BWT)", (long long)total_cap, (long long)(wm_bytes + n));
     if (layout == FMX_LAYOUT_AUTO) {
         size_t fr = 0, to = 0;
         cudaMemGetInfo(&fr, &to);
-        layout = (planes_bytes <= budget && planes_bytes + (6ll << 30) + 2 * n < (int64_t)fr) ? FMX_LAYOUT_PLANES : FMX_LAYOUT_WM;
+        const int64_t sampled = o.sa_sample_rate > 0 ? nblk * 64 + (n / o.sa_sample_rate + 1) * 4 + (n / kRowsPerWalkBlock + 1) * 64 : 0;
+        layout = (planes_bytes <= budget && planes_bytes + n + sampled <= total_cap && planes_bytes + (6ll << 30) + 2 * n < (int64_t)fr) ? FMX_LAYOUT_PLANES : FMX_LAYOUT_WM;
     }
     if (layout != FMX_LAYOUT_WM && layout != FMX_LAYOUT_PLANES) return fail(FMX_E_ARG, "bad layout %d", layout);
     int lanes = o.lanes_per_query ? o.lanes_per_query : 2;      // re-tuned below once the accelerators are known
@@ -162,6 +175,14 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     cudaError_t e;
     uint8_t *d_bwt = dev_upload(ix, bwt, (size_t)n, &e); CU(e);
     CU(cudaMemsetAsync(d_bwt + eof, 0, 1, ix->stream));
+    {   // the BWT must hold exactly the .aux counts (and one '$'): otherwise LF is not a permutation of the rows and the chain walks,
+        // locate walks and table fills below would run off the index (a corrupt or mismatched .bwt/.aux pair)
+        int64_t hist[256];
+        CU(byte_histogram(d_bwt, n, hist, ix->stream));
+        for (int c = 0; c < 256; ++c)
+            if (hist[c] != (c == 0 ? 1 : counts[c]))
+                return fail(FMX_E_FORMAT, "the BWT holds %lld bytes of value %d, the .aux counts say %lld: .bwt and .aux do not belong together", (long long)hist[c], c, (long long)(c == 0 ? 1 : counts[c]));
+    }
     uint32_t *d_C = dev_upload(ix, C32, 257, &e); CU(e);
     uint32_t *d_base = dev_upload(ix, base, 256, &e); CU(e);
     uint8_t *d_code = dev_upload(ix, code, 256, &e); CU(e);
@@ -178,7 +199,8 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     DevIndex &d = ix->d;
     d.blocks = (const uint4 *)blocks; d.stride = (uint64_t)nblk; d.bwt = d_bwt; d.C = d_C; d.base = d_base; d.code = d_code;
     d.bm = nullptr;
-    d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isat = nullptr; d.isat_bits = 8; d.isat_syms = 12; d.ctx = nullptr; d.ctx_J = 0; d.ctx_raw = 0; d.ctx8 = nullptr; d.ctx8_J = 0;
+    d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isat = nullptr; d.isat_bits = 8; d.isat_syms = 12; d.ctx = nullptr; d.ctx_J = 0; d.ctx_raw = 0; d.ctx_plan = nullptr; d.ctx8 = nullptr; d.ctx8_J = 0;
+    for (int t = 0; t < 8; ++t) d.ctx_S[t] = 0;
     d.mark = nullptr; d.samples = nullptr; d.n = (uint32_t)n; d.eof = (uint32_t)eof; d.layout = layout; d.levels = levels;
     for (int l = 0; l < 8; ++l) d.z[l] = z[l];
 
@@ -208,6 +230,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     // inside the ~64 GB TLB reach and fall off a cliff beyond (36 G/s at 80 GB, 19 G/s at 100 GB).  So the structures the count
     // kernel touches per query — k-mer table, row contexts, and the rank structure unless the table is deep enough that intervals
     // are down to a few rows when it has been consulted — are kept inside `reach`; everything else may fill the rest of the HBM.
+    // fmx_opts.max_total_bytes caps the sum of everything resident.
     int accel = o.accel;
     if (accel & FMX_ACCEL_NONE) accel = FMX_ACCEL_NONE;
     size_t fr = 0, to = 0;
@@ -219,28 +242,27 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     const int64_t rank_bytes = (layout == FMX_LAYOUT_PLANES ? planes_bytes : wm_bytes);
     if ((accel & FMX_ACCEL_CTX8) && accel != FMX_ACCEL_NONE && sigma > 4)
         return fail(FMX_E_UNSUPPORTED, "FMX_ACCEL_CTX8 stores 2-bit symbols: the text has %d distinct symbols (at most 4 fit)", sigma);
-    const bool auto_text = accel == FMX_ACCEL_AUTO && 25 * n + (2ll << 30) < (int64_t)fr && ix->index_bytes + 20 * n <= budget + (24ll << 30);
-    // row contexts: the 32-byte form when it fits the reach; for alphabets of <= 4 symbols on larger texts the compact 8-byte form
-    const bool fits32 = 32.0 * n + 4e9 <= reach && 57 * n + (8ll << 30) < (int64_t)fr;
-    const bool fits8 = sigma <= 4 && 8.0 * n + 4e9 <= reach && 33 * n + (8ll << 30) < (int64_t)fr;
-    const bool want_ctx = n > 2 && ((accel & FMX_ACCEL_CTX) || (accel == FMX_ACCEL_AUTO && auto_text && fits32));
-    const bool want_ctx8 = n > 2 && sigma <= 4 && !want_ctx && ((accel & FMX_ACCEL_CTX8) || (accel == FMX_ACCEL_AUTO && fits8));
-    // isat (16n bytes) is skipped when the compact contexts were chosen automatically: a text that large does not have the room
-    const bool want_isat = (accel & FMX_ACCEL_TEXT) || (accel == FMX_ACCEL_AUTO && auto_text && !want_ctx8) || ((accel & FMX_ACCEL_CTX) && !(accel & FMX_ACCEL_CTX8));
-    const bool want_sa = want_isat || want_ctx || want_ctx8;
-    const bool want_kmer = (accel & FMX_ACCEL_KMER) || accel == FMX_ACCEL_AUTO;
-    if (want_sa && n > 2) {
-        // sa stays (locate is one load per occurrence); isa and the text are scratch that is folded into the isat / context entries
-        void *sa = nullptr;
-        uint32_t *isa = nullptr; uint8_t *text = nullptr;
-        e = cudaMalloc(&sa, (size_t)n * 4); CU(e); ix->owned.push_back(sa);
-        CU(cudaMallocAsync(&isa, (size_t)n * 4, ix->stream));
-        CU(cudaMallocAsync(&text, (size_t)n + 16, ix->stream));
+    auto room = [&]() { return total_cap - ix->index_bytes; };          // bytes the cap still allows
+    const bool is_auto = accel == FMX_ACCEL_AUTO;
+    // row contexts: the 32-byte form when it fits the reach (and leaves a quarter of the cap to the table); for alphabets of <= 4
+    // symbols on larger texts the compact 8-byte form.  Construction needs sa + isa + text (9n) next to the entries.
+    const bool fits32 = 32.0 * n + 4e9 <= reach && 41 * n + (8ll << 30) < (int64_t)fr && 32 * n <= room() - room() / 4;
+    const bool fits8 = sigma <= 4 && 8.0 * n + 4e9 <= reach && 17 * n + (8ll << 30) < (int64_t)fr && 8 * n <= room() - room() / 4;
+    const bool want_ctx = n > 2 && ((accel & FMX_ACCEL_CTX) || (is_auto && fits32));
+    const bool want_ctx8 = n > 2 && sigma <= 4 && !want_ctx && ((accel & FMX_ACCEL_CTX8) || (is_auto && fits8));
+    // isat (16n bytes, the singleton shortcut) only where no row contexts exist: a context entry does the same in one fetch
+    const bool want_isat = n > 2 && ((accel & FMX_ACCEL_TEXT) || (is_auto && !want_ctx && !want_ctx8 && 25 * n + (2ll << 30) < (int64_t)fr &&
+                                                                 ix->index_bytes + 20 * n <= budget + (24ll << 30) && 20 * n <= room() / 2));
+    const bool build_sa = want_isat || want_ctx || want_ctx8;
+    const bool want_kmer = (accel & FMX_ACCEL_KMER) || is_auto;
+    if (build_sa) {
+        // isa and the text are scratch that is folded into the isat / context entries; sa stays when it is wanted for locate
+        SaBuf sa;                                                 // plain cudaMalloc: it may become a resident part of the index
+        DBuf isa(ix->stream), text(ix->stream);
+        CU(cudaMalloc(&sa.p, (size_t)n * 4)); CU(isa.alloc((size_t)n * 4)); CU(text.alloc((size_t)n + 16));
         std::string err;
-        e = build_full_sa(d, layout, (uint32_t *)sa, isa, text, ix->stream, err);
+        e = build_full_sa(d, layout, sa.as<uint32_t>(), isa.as<uint32_t>(), text.as<uint8_t>(), ix->stream, err);
         if (e != cudaSuccess) return fail(err.empty() ? FMX_E_CUDA : FMX_E_FORMAT, "suffix array construction failed: %s", err.empty() ? cudaGetErrorString(e) : err.c_str());
-        d.sa = (const uint32_t *)sa;
-        ix->index_bytes += 4 * n;
         int ibits = 1;
         while ((1 << ibits) < sigma + 1) ++ibits;                 // values 0..sigma: dense code + 1, 0 = '$'
         const int isyms = 96 / ibits;
@@ -248,7 +270,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
         if (want_isat) {
             void *isat = nullptr;
             e = cudaMalloc(&isat, (size_t)n * 16); CU(e); ix->owned.push_back(isat);
-            CU(build_isat(isa, text, d_code, n, ibits, isyms, (uint4 *)isat, ix->stream));
+            CU(build_isat(isa.as<uint32_t>(), text.as<uint8_t>(), d_code, n, ibits, isyms, (uint4 *)isat, ix->stream));
             d.isat = (const uint4 *)isat;
             ix->index_bytes += 16 * n;
         }
@@ -259,8 +281,14 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
             else {
                 ix->owned.push_back(ctx);
                 const int raw = ibits == 8 ? 1 : 0;
-                CU(build_ctx((const uint32_t *)sa, isa, text, d_code, n, ibits, isyms, raw, (uint4 *)ctx, ix->stream));
-                d.ctx = (const uint4 *)ctx; d.ctx_J = isyms; d.ctx_raw = raw;
+                CtxHops hops;
+                uint8_t plan[256];
+                ctx_hop_plan(isyms, hops, plan);
+                uint8_t *d_plan = dev_upload(ix, plan, 256, &e); CU(e);
+                CU(build_ctx(sa.as<uint32_t>(), isa.as<uint32_t>(), text.as<uint8_t>(), d_code, n, ibits, isyms, raw, hops, (uint4 *)ctx, ix->stream));
+                CU(cudaStreamSynchronize(ix->stream));             // `plan` is a local
+                d.ctx = (const uint4 *)ctx; d.ctx_J = isyms; d.ctx_raw = raw; d.ctx_plan = d_plan;
+                for (int t = 0; t < 8; ++t) d.ctx_S[t] = (uint8_t)hops.h[t];
                 ix->index_bytes += 32 * n;
             }
         }
@@ -270,16 +298,23 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
             if (e != cudaSuccess) { cudaGetLastError(); if (accel & FMX_ACCEL_CTX8) return fail(FMX_E_CUDA, "cannot allocate %lld bytes for the compact row contexts", (long long)n * 8); }
             else {
                 ix->owned.push_back(ctx8);
-                CU(build_ctx8((const uint32_t *)sa, isa, text, d_code, n, 16, (uint2 *)ctx8, ix->stream));
+                CU(build_ctx8(sa.as<uint32_t>(), isa.as<uint32_t>(), text.as<uint8_t>(), d_code, n, 16, (uint2 *)ctx8, ix->stream));
                 d.ctx8 = (const uint2 *)ctx8; d.ctx8_J = 16;
                 ix->index_bytes += 8 * n;
             }
         }
-        CU(cudaFreeAsync(isa, ix->stream));
-        CU(cudaFreeAsync(text, ix->stream));
+        // the full suffix array stays resident (locate = one load per occurrence) when the singleton shortcut needs it, or when no sampled
+        // SA was asked for and neither the cap nor FMX_ACCEL_NO_SA forbids it; otherwise it was scratch
+        const bool keep_sa = want_isat || (o.sa_sample_rate == 0 && !(accel & FMX_ACCEL_NO_SA) && 4 * n <= room() - (want_kmer ? room() / 4 : 0));
         CU(cudaStreamSynchronize(ix->stream));
-        trim_pool(ix->device);
+        if (keep_sa) {
+            ix->owned.push_back(sa.p);
+            d.sa = (const uint32_t *)sa.p;
+            sa.p = nullptr;
+            ix->index_bytes += 4 * n;
+        }
     }
+    trim_pool(ix->device);
     if (want_kmer && sigma >= 1) {
         size_t fr2 = 0, to2 = 0;
         cudaMemGetInfo(&fr2, &to2);
@@ -287,12 +322,12 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
         auto entries_of = [&](int k) { int64_t v = 1; for (int j = 0; j < k; ++j) { if (v > max_entries) return max_entries + 1; v *= sigma; } return v; };
         int K = 0;
         if (o.kmer_table_bytes > 0) {                                   // explicit budget
-            while (K < 16 && entries_of(K + 1) <= max_entries && entries_of(K + 1) * 8 <= o.kmer_table_bytes) ++K;
+            while (K < 16 && entries_of(K + 1) <= max_entries && entries_of(K + 1) * 8 <= o.kmer_table_bytes && entries_of(K + 1) * 8 <= room()) ++K;
         } else {
-            // the deepest table whose working set stays inside the TLB reach and a third of the free memory ...
+            // the deepest table whose working set stays inside the TLB reach, a third of the free memory and the cap ...
             for (int k = 16; k >= 2 && K == 0; --k) {
                 const int64_t en = entries_of(k);
-                if (en > max_entries || en * 8 > (int64_t)(fr2 / 3)) continue;
+                if (en > max_entries || en * 8 > (int64_t)(fr2 / 3) || en * 8 > room()) continue;
                 const bool have_ctx = d.ctx != nullptr || d.ctx8 != nullptr;
                 const bool saturating = have_ctx && en >= n / 2;            // intervals are a few rows once the table has been consulted
                 const double ws = en * 8.0 + (d.ctx ? 32.0 * n : 0.0) + (d.ctx8 ? 8.0 * n : 0.0) +
@@ -301,7 +336,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
             }
             // ... else (the rest of the index is already beyond the reach) 256 MiB .. 16 GiB scaled to a sixteenth of the free memory
             if (K == 0) {
-                const int64_t table_budget = std::min<int64_t>(std::max<int64_t>(256ll << 20, (int64_t)(fr2 / 16)), 16ll << 30);
+                const int64_t table_budget = std::min<int64_t>(std::min<int64_t>(std::max<int64_t>(256ll << 20, (int64_t)(fr2 / 16)), 16ll << 30), room());
                 while (K < 16 && entries_of(K + 1) <= std::min<int64_t>(max_entries, std::max<int64_t>(4 * n, 1 << 16)) && entries_of(K + 1) * 8 <= table_budget) ++K;
             }
         }
@@ -327,6 +362,8 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     }
     ix->accel_text = d.isat != nullptr;
     ix->kmer_k = d.kmer ? d.kmer_k : 0;
+    ix->d_full = d;
+    ix->count_lanes_full = ix->cfg.count_lanes;
     CU(cudaStreamSynchronize(ix->stream));
     trim_pool(ix->device);                              // construction scratch goes back to the device
     return FMX_OK;
@@ -476,6 +513,24 @@ int fmx_set_lanes(fmx_index *ix, int32_t lanes) {
     ix->cfg.count_lanes = 0;
     return FMX_OK;
 }
+// Hides built accelerators from subsequent calls (FMX_ACCEL_* bits to keep; FMX_ACCEL_NONE = plain backward search over the rank
+// structure, FMX_ACCEL_AUTO = everything that was built): measures the same index with and without them, without a second open.
+int fmx_set_accel_mask(fmx_index *ix, int32_t mask) {
+    CHECK_IX(ix);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DevIndex d = ix->d_full;
+    if (mask != FMX_ACCEL_AUTO) {
+        if ((mask & FMX_ACCEL_NONE) || !(mask & FMX_ACCEL_KMER)) { d.kmer = nullptr; d.kmer_k = 0; }
+        if ((mask & FMX_ACCEL_NONE) || !(mask & FMX_ACCEL_TEXT)) d.isat = nullptr;
+        if ((mask & FMX_ACCEL_NONE) || !(mask & FMX_ACCEL_CTX)) d.ctx = nullptr;
+        if ((mask & FMX_ACCEL_NONE) || !(mask & FMX_ACCEL_CTX8)) d.ctx8 = nullptr;
+    }
+    ix->d = d;
+    ix->cfg.count_lanes = (d.kmer && (d.ctx || d.ctx8)) ? ix->count_lanes_full : 0;
+    ix->accel_text = d.isat != nullptr;
+    ix->kmer_k = d.kmer ? d.kmer_k : 0;
+    return FMX_OK;
+}
 int fmx_set_chunk(fmx_index *ix, int64_t queries_per_chunk) {
     CHECK_IX(ix);
     if (queries_per_chunk < 0) return fail(FMX_E_ARG, "bad chunk");
@@ -604,6 +659,7 @@ int fmx_interval_prev_range(fmx_index *ix, int64_t sp, int64_t ep, int cstart, i
 int fmx_count_fixed_dev(fmx_index *ix, const void *d_pat, int32_t len, int64_t m, void *d_sp, void *d_ep, void *stream) {
     CHECK_IX(ix);
     if (len < 0 || m < 0 || (m && (!d_sp || !d_ep || (len && !d_pat)))) return fail(FMX_E_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(ix->mu);                    // cfg and the launch counters are shared with the host-buffer calls; the launch is asynchronous
     DeviceGuard g(ix->device);
     CU(launch_count_fixed(ix->d, ix->cfg, (const uint8_t *)d_pat, len, m, d_sp, d_ep, false, nullptr, (cudaStream_t)stream));
     ix->last_launches = 1; ix->total_launches += 1;
@@ -626,6 +682,7 @@ int fmx_count_fixed_dev_gather(fmx_index *ix, const void *d_pat, int32_t len, in
     ps.n = n_sinks;
     ps.offset = offset;
     for (int j = 0; j < n_sinks; ++j) { if (!sinks[j]) return fail(FMX_E_ARG, "null sink %d", j); ps.p[j] = (uint32_t *)sinks[j]; }
+    std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     CU(launch_count_fixed(ix->d, ix->cfg, (const uint8_t *)d_pat, len, m, d_sp, d_ep, false, nullptr, (cudaStream_t)stream, &ps));
     ix->last_launches = 1; ix->total_launches += 1;
@@ -675,11 +732,13 @@ static int count_fixed_pipeline(fmx_index *ix, const uint8_t *pat, int32_t len, 
     if (only_counts) CU(dcnt.alloc(m * 4));
     const int64_t chunk = ix->chunk_queries > 0 ? ix->chunk_queries : (1 << 20);
     const int64_t nchunks = (m + chunk - 1) / chunk;
-    std::vector<cudaEvent_t> ev_in((size_t)nchunks), ev_k((size_t)nchunks);
-    for (int64_t k = 0; k < nchunks; ++k) {
-        CU(cudaEventCreateWithFlags(&ev_in[(size_t)k], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&ev_k[(size_t)k], cudaEventDisableTiming));
-    }
+    struct Events {                                            // destroyed on every exit path
+        std::vector<cudaEvent_t> v;
+        ~Events() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+        cudaError_t make(size_t k) { v.assign(k, nullptr); for (auto &e : v) { cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming); if (r != cudaSuccess) return r; } return cudaSuccess; }
+    } evs_in, evs_k;
+    CU(evs_in.make((size_t)nchunks)); CU(evs_k.make((size_t)nchunks));
+    std::vector<cudaEvent_t> &ev_in = evs_in.v, &ev_k = evs_k.v;
     // the copy streams may touch the stream-ordered allocations only after the allocating stream reached this point
     CU(cudaEventRecord(ix->ev_alloc, st));
     CU(cudaStreamWaitEvent(ix->h2d, ix->ev_alloc, 0));
@@ -719,7 +778,6 @@ static int count_fixed_pipeline(fmx_index *ix, const uint8_t *pat, int32_t len, 
     ix->last_launches = nchunks; ix->total_launches += nchunks;
     t.stop();
     cudaError_t e1 = cudaStreamSynchronize(ix->h2d), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(ix->d2h);
-    for (int64_t k = 0; k < nchunks; ++k) { cudaEventDestroy(ev_in[(size_t)k]); cudaEventDestroy(ev_k[(size_t)k]); }
     if (rc == FMX_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess))
         rc = fail(FMX_E_CUDA, "CUDA error while draining the count pipeline");
     t.collect();

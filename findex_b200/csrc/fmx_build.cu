@@ -151,6 +151,9 @@ chain_len_kernel(const __grid_constant__ DevIndex ix, uint32_t S, uint32_t nchai
         ++steps;
         if (r == ix.eof) { next[j] = eof_chain; break; }
         if (r % S == 0) { next[j] = r / S; break; }
+        // LF of a consistent index is one n-cycle: a walk that leaves the rows or outlives n steps is on a corrupt index.  The chain is
+        // closed on itself with an impossible length, which fails the host's single-cycle check (prepare_chains) instead of hanging.
+        if (r >= ix.n || steps > ix.n) { next[j] = j; steps = 0xFFFFFFFFu; break; }
     }
     len[j] = steps;
 }
@@ -173,7 +176,7 @@ chain_mark_kernel(const __grid_constant__ DevIndex ix, uint32_t S, uint32_t ncha
         }
         r = lf_value<1, LAYOUT>(ix, tb, ix.bwt[r], r);
         v = (v == 0) ? ix.n - 1 : v - 1;
-        if (r == ix.eof || r % S == 0) break;
+        if (r == ix.eof || r % S == 0 || r >= ix.n) break;
     }
 }
 
@@ -203,7 +206,7 @@ chain_fullsa_kernel(const __grid_constant__ DevIndex ix, uint32_t S, uint32_t nc
         else text[ix.n - 1] = 0;                      // the '$'
         r = lf_value<1, LAYOUT>(ix, tb, c, r);
         v = (v == 0) ? ix.n - 1 : v - 1;
-        if (r == ix.eof || r % S == 0) break;
+        if (r == ix.eof || r % S == 0 || r >= ix.n) break;
     }
 }
 
@@ -331,11 +334,11 @@ cudaError_t build_isat(const uint32_t *d_isa, const uint8_t *d_text, const uint8
     return cudaGetLastError();
 }
 
-// ctx[r] (32 B) = { isa[sa[r]-j] for j = J-4..J, 96 bits = the J symbols T'[sa[r]-J .. sa[r]-1] in the isat packing }; positions before the
-// start of T' read as symbol 0 / row 0 (symbol 0 never equals a pattern symbol, which is dense code + 1 >= 1); raw = 1 (8-bit symbols):
-// the text bytes themselves are stored (0 = '$' / before the start; patterns with a zero byte never take this path)
+// ctx[r] (32 B) = { isa[sa[r]-j] for the five hop lengths j = hops.h[0..4] (hops.h[4] = J), 96 bits = the J symbols T'[sa[r]-J .. sa[r]-1] in the
+// isat packing }; positions before the start of T' read as symbol 0 / row 0 (symbol 0 never equals a pattern symbol, which is dense code + 1
+// >= 1); raw = 1 (8-bit symbols): the text bytes themselves are stored (0 = '$' / before the start; patterns with a zero byte never take this path)
 __global__ void build_ctx_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ isa, const uint8_t *__restrict__ text,
-                                 const uint8_t *__restrict__ code, int64_t n, int bits, int J, int raw, uint4 *__restrict__ ctx) {
+                                 const uint8_t *__restrict__ code, int64_t n, int bits, int J, int raw, CtxHops hops, uint4 *__restrict__ ctx) {
     __shared__ uint8_t sc[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sc[i] = code[i];
     __syncthreads();
@@ -344,7 +347,7 @@ __global__ void build_ctx_kernel(const uint32_t *__restrict__ sa, const uint32_t
     const int64_t p = sa[r];
     uint32_t row[5];
 #pragma unroll
-    for (int t = 0; t < 5; ++t) { const int64_t q = p - (J - 4 + t); row[t] = q >= 0 ? isa[q] : 0u; }
+    for (int t = 0; t < 5; ++t) { const int64_t q = p - hops.h[t]; row[t] = q >= 0 ? isa[q] : 0u; }
     unsigned long long lo = 0, hi = 0;
     for (int k = 0; k < J; ++k) {
         const int64_t q = p - J + k;
@@ -358,9 +361,32 @@ __global__ void build_ctx_kernel(const uint32_t *__restrict__ sa, const uint32_t
     ctx[2 * r + 1] = make_uint4(row[4], (uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi);
 }
 cudaError_t build_ctx(const uint32_t *d_sa, const uint32_t *d_isa, const uint8_t *d_text, const uint8_t *d_code, int64_t n, int bits, int J,
-                      int raw, uint4 *d_ctx, cudaStream_t st) {
-    build_ctx_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_sa, d_isa, d_text, d_code, n, bits, J, raw, d_ctx);
+                      int raw, const CtxHops &hops, uint4 *d_ctx, cudaStream_t st) {
+    build_ctx_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_sa, d_isa, d_text, d_code, n, bits, J, raw, hops, d_ctx);
     return cudaGetLastError();
+}
+
+// Hop lengths stored per context depth J = 96 / bits: the 5-subset of 1..J (with 1 and J) that minimises the worst excess of fetches over
+// ceil(rem / J), then the mean, over rem <= 4J (offline exhaustive search); J = 12 prefers multiples of 4 (k-mer lengths 8/12/16/20/24/32
+// after a depth-4 table finish in ceil(rem / 12) fetches).  plan[rem] = index of the first hop of a fewest-fetches decomposition of rem,
+// plan[128 + rem] = that number of fetches (rem <= 127).
+void ctx_hop_plan(int J, CtxHops &hops, uint8_t plan[256]) {
+    static const int known[][6] = {{12, 1, 3, 4, 8, 12},  {13, 1, 3, 5, 6, 13},   {16, 1, 4, 6, 15, 16},  {19, 1, 4, 5, 16, 19},
+                                   {24, 1, 4, 6, 15, 24}, {32, 1, 4, 9, 21, 32}, {48, 1, 5, 12, 33, 48}, {96, 1, 6, 16, 48, 96}};
+    int S[5] = {1, (J + 7) / 8, (J + 3) / 4, (J + 1) / 2, J};
+    for (const auto &k : known) if (k[0] == J) for (int t = 0; t < 5; ++t) S[t] = k[1 + t];
+    for (int t = 0; t < 8; ++t) hops.h[t] = t < 5 ? S[t] : 0;
+    int cost[128];
+    cost[0] = 0;
+    plan[0] = 0; plan[128] = 0;
+    for (int r = 1; r < 128; ++r) {
+        int best = 1 << 20, bt = 0;
+        for (int t = 4; t >= 0; --t)                            // ties go to the longer hop
+            if (S[t] <= r && cost[r - S[t]] + 1 < best) { best = cost[r - S[t]] + 1; bt = t; }
+        cost[r] = best;
+        plan[r] = (uint8_t)bt;
+        plan[128 + r] = (uint8_t)best;
+    }
 }
 
 // ctx8[r] (8 B) = { isa[sa[r]-J], the J <= 16 symbols T'[sa[r]-J .. sa[r]-1] as 2-bit dense codes }; row 0xFFFFFFFF when sa[r] < J
@@ -495,6 +521,18 @@ __global__ void reverse_kernel(const uint8_t *__restrict__ src, int64_t len, uin
 __global__ void fm_iota_kernel(uint32_t *v, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] = (uint32_t)i;
+}
+
+cudaError_t byte_histogram(const uint8_t *d_bytes, int64_t n, int64_t counts_out[256], cudaStream_t st) {
+    unsigned long long *d_counts = nullptr, h[256];
+    CK(cudaMallocAsync(&d_counts, 256 * 8, st));
+    CK(cudaMemsetAsync(d_counts, 0, 256 * 8, st));
+    if (n > 0) histogram_kernel<<<148 * 4, 256, 0, st>>>(d_bytes, n, d_counts);
+    CK(cudaMemcpyAsync(h, d_counts, 256 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFreeAsync(d_counts, st);
+    for (int i = 0; i < 256; ++i) counts_out[i] = (int64_t)h[i];
+    return cudaGetLastError();
 }
 
 cudaError_t reverse_bytes(const uint8_t *d_src, int64_t len, uint8_t *d_dst, cudaStream_t st) {

@@ -21,9 +21,11 @@ cudaError_t build_walk_blocks(const uint8_t *d_bwt, const uint32_t *d_mark_block
 // full suffix array, its inverse and T' (text[n-1] = 0) by the same chain walks
 cudaError_t build_full_sa(const DevIndex &ix, int layout, uint32_t *d_sa, uint32_t *d_isa, uint8_t *d_text, cudaStream_t st, std::string &err);
 cudaError_t build_isat(const uint32_t *d_isa, const uint8_t *d_text, const uint8_t *d_code, int64_t n, int bits, int syms, uint4 *d_isat, cudaStream_t st);
-// row-indexed 32-byte context entries (DevIndex::ctx)
+// row-indexed 32-byte context entries (DevIndex::ctx): hop lengths + plan table for a context depth J (host), then the entries
+struct CtxHops { int h[8]; };
+void ctx_hop_plan(int J, CtxHops &hops, uint8_t plan[256]);
 cudaError_t build_ctx(const uint32_t *d_sa, const uint32_t *d_isa, const uint8_t *d_text, const uint8_t *d_code, int64_t n, int bits, int J,
-                      int raw, uint4 *d_ctx, cudaStream_t st);
+                      int raw, const CtxHops &hops, uint4 *d_ctx, cudaStream_t st);
 cudaError_t build_ctx8(const uint32_t *d_sa, const uint32_t *d_isa, const uint8_t *d_text, const uint8_t *d_code, int64_t n, int J,
                        uint2 *d_ctx8, cudaStream_t st);
 // (sp,ep) after the first K backward steps for every K-mer over the sigma occurring symbols
@@ -31,6 +33,8 @@ cudaError_t build_kmer_table(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d
 // suffix sort of t+'$' (t has no zero bytes) -> BWT, eof row, byte counts; optionally the suffix array
 cudaError_t suffix_sort_bwt(const uint8_t *d_t, int64_t len, uint8_t *d_bwt, int64_t *eof_out, int64_t counts_out[256],
                             uint32_t *d_sa_out, int *rounds_out, cudaStream_t st);
+// counts_out[c] = number of bytes of value c among d_bytes[0..n)
+cudaError_t byte_histogram(const uint8_t *d_bytes, int64_t n, int64_t counts_out[256], cudaStream_t st);
 cudaError_t reverse_bytes(const uint8_t *d_src, int64_t len, uint8_t *d_dst, cudaStream_t st);
 cudaError_t build_fm_array(const uint8_t *d_bwt, int64_t n, uint32_t *d_fm, cudaStream_t st);
 

@@ -43,16 +43,19 @@ struct DevIndex {
     const uint4    *isat;       // per text position p: { isa[p], 96 bits of T'[p..] } — inverse SA and the text behind it in one 16-B fetch
     int32_t         isat_bits;  // bits per text symbol in isat: ceil(log2(sigma+1)); stored value = dense code + 1, 0 = '$' / past the end
     int32_t         isat_syms;  // symbols per entry = 96 / isat_bits  (bytes: 12, sigma <= 31: 19, DNA: 32)
-    // row-indexed context: ctx[r] = { isa[sa[r]-j] for j = ctx_J-4 .. ctx_J (5 words), 96 bits = the ctx_J symbols T'[sa[r]-ctx_J .. sa[r]-1]
-    // in the isat packing } — 32 B, one request: a row with ctx_J-4 <= remaining <= ctx_J pattern bytes finishes in ONE fetch, and a
-    // small interval is finished by looking at each of its rows (the rows whose text continues with the rest of the pattern map onto
-    // exactly the pattern's interval)
+    // row-indexed context: ctx[r] = { isa[sa[r]-j] for the five hop lengths j in ctx_S (ascending, ctx_S[4] = ctx_J), 96 bits = the ctx_J symbols
+    // T'[sa[r]-ctx_J .. sa[r]-1] in the isat packing } — 32 B, one request.  A row whose text goes on (backwards) with the next j pattern
+    // bytes HOPS to row isa[sa[r]-j] — j backward steps in one fetch — and a small interval is advanced by looking at each of its rows
+    // (the rows whose text continues with those j bytes map onto exactly the next interval, contiguously).  ctx_plan picks, for every
+    // remaining length, the hop that reaches the pattern's start in the fewest fetches (any length is a sum of hop lengths: 1 is one).
     const uint4    *ctx;        // 2 x uint4 per row, or nullptr
     int32_t         ctx_J;      // = isat_syms
     int32_t         ctx_raw;    // 1 (byte alphabets, 8-bit symbols): the 12 symbols are the raw text bytes, so pattern words compare directly
+    const uint8_t  *ctx_plan;   // 256 bytes: [rem] = index into ctx_S of the hop to take with rem <= 127 symbols left, [128 + rem] = fetches per row to finish
+    uint8_t         ctx_S[8];   // hop lengths (5 used)
     // compact row contexts for alphabets of <= 4 symbols on texts too large for the 32-byte form (4e9 rows: 32 GB instead of 128):
-    // ctx8[r] = { isa[sa[r]-J], the J = 16 symbols T'[sa[r]-16 .. sa[r]-1] as 2-bit dense codes } — usable when exactly J bytes remain;
-    // rows with fewer than J text positions before them hold row 0xFFFFFFFF
+    // ctx8[r] = { isa[sa[r]-J], the J = 16 symbols T'[sa[r]-16 .. sa[r]-1] as 2-bit dense codes } — a hop of exactly J symbols, usable while
+    // at least J bytes remain; rows with fewer than J text positions before them hold row 0xFFFFFFFF
     const uint2    *ctx8;
     int32_t         ctx8_J;
 };
@@ -71,6 +74,20 @@ struct SmemPattern {                                   // pattern staged in shar
         for (int b = 0; b < 4; ++b) { const int i = 4 * w + b; if (i < len) v |= (uint32_t)p[i] << (8 * b); }
         return v;
     }
+    // pattern bytes o .. o+11 as three little-endian words (bytes at or beyond `len` read as anything; the staging buffer is padded)
+    __device__ __forceinline__ void bytes12(int o, uint32_t &w0, uint32_t &w1, uint32_t &w2) const {
+        if (aligned) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(p) + (o >> 2);
+            const uint32_t a = q[0], b = q[1], c = q[2], s = (uint32_t)(o & 3) * 8u;
+            if (s == 0) { w0 = a; w1 = b; w2 = c; }
+            else { const uint32_t d = q[3]; w0 = __funnelshift_r(a, b, s); w1 = __funnelshift_r(b, c, s); w2 = __funnelshift_r(c, d, s); }
+        } else {
+            uint32_t v[3] = {0, 0, 0};
+#pragma unroll
+            for (int b = 0; b < 12; ++b) { const int i = o + b; if (i < len) v[b >> 2] |= (uint32_t)p[i] << (8 * (b & 3)); }
+            w0 = v[0]; w1 = v[1]; w2 = v[2];
+        }
+    }
 };
 struct GlobalPattern {                                 // pattern read from global memory (variable-length batches)
     const uint8_t *p;
@@ -82,20 +99,33 @@ struct GlobalPattern {                                 // pattern read from glob
         for (int b = 0; b < 4; ++b) { const int i = 4 * w + b; if (i < len) v |= (uint32_t)__ldg(p + i) << (8 * b); }
         return v;
     }
+    __device__ __forceinline__ void bytes12(int o, uint32_t &w0, uint32_t &w1, uint32_t &w2) const {
+        uint32_t v[3] = {0, 0, 0};
+#pragma unroll
+        for (int b = 0; b < 12; ++b) { const int i = o + b; if (i < len) v[b >> 2] |= (uint32_t)__ldg(p + i) << (8 * (b & 3)); }
+        w0 = v[0]; w1 = v[1]; w2 = v[2];
+    }
 };
 
-constexpr uint32_t kCtxMaxRows = 8;    // intervals up to this many rows are finished through ctx instead of rank steps
-constexpr int      kCtxSpan = 5;       // remaining lengths ctx_J-4 .. ctx_J are covered
+constexpr uint32_t kCtxMaxRows = 8;    // intervals up to this many rows are advanced through ctx instead of rank steps
+constexpr int      kCtxHops = 5;       // hop lengths per 32-byte entry
+constexpr int      kCtxPlanMax = 127;  // remaining lengths covered by ctx_plan; longer ones take the full-depth hop
 
 struct SharedTables {
     uint32_t C[257];
     uint32_t base[256];
     uint8_t  code[256];
+    uint8_t  plan[256];         // DevIndex::ctx_plan (only when row contexts exist)
+    uint8_t  hops[8];           // DevIndex::ctx_S
 };
 
 __device__ __forceinline__ void load_tables(SharedTables &s, const DevIndex &ix) {
     for (int i = threadIdx.x; i < 257; i += blockDim.x) s.C[i] = ix.C[i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { s.base[i] = ix.base[i]; s.code[i] = ix.code[i]; }
+    if (ix.ctx != nullptr) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s.plan[i] = ix.ctx_plan[i];
+        if (threadIdx.x < 8) s.hops[threadIdx.x] = ix.ctx_S[threadIdx.x];
+    }
 }
 
 // Index fetches.  Measured on B200 (tools/ldhint_bench.cu, profiles/r01_ldhint_*): what bounds random access is the number of
@@ -339,12 +369,13 @@ __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedT
         if (go) {
             bool stepped = false;
             const int rem = i + 1;
-            if (!noctx && ix.ctx8 != nullptr && (ep - sp) <= kCtxMaxRows && rem == ix.ctx8_J) {
-                // compact form: 8 bytes per row, exactly ctx8_J symbols left
+            if (!noctx && ix.ctx8 != nullptr && (ep - sp) <= kCtxMaxRows && rem >= ix.ctx8_J) {
+                // compact form: 8 bytes per row, a hop of exactly ctx8_J symbols — the pattern bytes rem-J .. rem-1
+                const int J = ix.ctx8_J, o = rem - J;
                 uint32_t q = 0;
                 bool zero = false, absent = false;
-                for (int k = 0; k < rem; ++k) {
-                    const uint32_t pc = pat(k), cd = tb.code[pc];
+                for (int k = 0; k < J; ++k) {
+                    const uint32_t pc = pat(o + k), cd = tb.code[pc];
                     zero = zero || (pc == 0);
                     absent = absent || (cd == (uint32_t)kCodeAbsent);
                     q |= (cd & 3u) << (2 * k);
@@ -358,66 +389,74 @@ __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedT
                             if (e.y == q && e.x != 0xFFFFFFFFu) { best = e.x < best ? e.x : best; ++cnt; }
                         }
                     }
-                    if (STATS && lane == 0) { touched += absent ? 0u : ep - sp; steps += rem; }
+                    if (STATS && lane == 0) { touched += absent ? 0u : ep - sp; steps += J; }
                     if (G >= 2) { best = min(best, __shfl_xor_sync(gmask, best, 1)); cnt += __shfl_xor_sync(gmask, cnt, 1); }
                     if (G >= 4) { best = min(best, __shfl_xor_sync(gmask, best, 2)); cnt += __shfl_xor_sync(gmask, cnt, 2); }
                     if (cnt) { sp = best; ep = best + cnt; } else { sp = 0; ep = 0; }
-                    i = -1;
+                    i -= J;
                     stepped = true;
                 }
             }
-            if (!stepped && !noctx && ix.ctx != nullptr && (ep - sp) <= kCtxMaxRows && rem <= ix.ctx_J && rem > ix.ctx_J - kCtxSpan) {
-                // every row of the interval is looked at through its 32-byte context entry: the rows whose text goes on with the
-                // remaining `rem` pattern bytes map onto exactly the pattern's interval (their targets isa[sa[r]-rem] are its rows)
-                const uint32_t bits = (uint32_t)ix.isat_bits;
-                unsigned long long qlo = 0, qhi = 0;                 // the remaining pattern bytes in the entry's packing
-                bool zero = false, absent = false;
-                if (ix.ctx_raw) {                                     // raw bytes (rem is 8..12): three pattern words, no translation;
-                    qlo = ((unsigned long long)pat.word(1) << 32) | pat.word(0);      // a byte that is absent from the text just never matches
-                    qhi = rem > 8 ? pat.word(2) : 0u;
-                    const unsigned long long keep = rem >= 12 ? 0xFFFFFFFFull : ((1ull << (8 * (rem - 8))) - 1ull);
-                    const unsigned long long h = (qhi & keep) | ~keep;                  // bytes past the pattern must not look like zeros
-                    zero = (((qlo - 0x0101010101010101ull) & ~qlo) | ((h - 0x0101010101010101ull) & ~h)) & 0x8080808080808080ull;
-                } else {
-                    for (int k = 0; k < rem; ++k) {
-                        const uint32_t pc = pat(k), cd = tb.code[pc];
-                        zero = zero || (pc == 0);
-                        absent = absent || (cd == (uint32_t)kCodeAbsent);
-                        const unsigned long long v = (unsigned long long)((cd + 1u) & ((1u << bits) - 1u));
-                        const uint32_t o = (uint32_t)k * bits;
-                        if (o < 64) { qlo |= v << o; if (o + bits > 64) qhi |= v >> (64 - o); }
-                        else qhi |= v << (o - 64);
-                    }
-                }
-                if (zero) noctx = true;                               // byte 0: the '$' row wraps the text, take the ordinary steps
-                else {
-                    const uint32_t sh = (uint32_t)(ix.ctx_J - rem) * bits, nb = (uint32_t)rem * bits;   // nb >= 1
+            if (!stepped && !noctx && ix.ctx != nullptr && (ep - sp) <= kCtxMaxRows) {
+                // every row of the interval is looked at through its 32-byte context entry: the rows whose text goes on with the next
+                // j pattern bytes map onto exactly the next interval (their targets isa[sa[r]-j] are its rows, contiguous) — j backward
+                // steps for one fetch per row.  The plan table names the hop that finishes `rem` symbols in the fewest fetches; rank
+                // steps are kept when they are cheaper (a wide interval with a few symbols left).
+                const uint32_t rows = ep - sp;
+                const int t = rem <= kCtxPlanMax ? (int)tb.plan[rem] : kCtxHops - 1;
+                const uint32_t need = rem <= kCtxPlanMax ? (uint32_t)tb.plan[128 + rem] : (uint32_t)(rem / ix.ctx_J + 3);
+                if (rows == 1u || rows * need <= (uint32_t)rem) {
+                    const int j = (int)tb.hops[t], o = rem - j;      // this hop consumes pattern bytes o .. rem-1
+                    const uint32_t bits = (uint32_t)ix.isat_bits;
+                    unsigned long long qlo = 0, qhi = 0;                  // those bytes in the entry's packing
+                    const uint32_t sh = (uint32_t)(ix.ctx_J - j) * bits, nb = (uint32_t)j * bits;       // nb >= 1
                     const unsigned long long mlo = nb >= 64 ? ~0ull : ((1ull << nb) - 1ull);
                     const unsigned long long mhi = nb <= 64 ? 0ull : ((1ull << (nb - 64)) - 1ull);
-                    const int rw = rem - (ix.ctx_J - kCtxSpan + 1);   // which of the five row words
-                    uint32_t best = 0xFFFFFFFFu, cnt = 0;
-                    if (!absent) {
-                        for (uint32_t r = sp + (uint32_t)lane; r < ep; r += G) {
-                            uint4 a, b;
-                            ldg256(ix.ctx + (uint64_t)r * 2, a, b);
-                            const unsigned long long elo = ((unsigned long long)b.z << 32) | b.y, ehi = b.w;
-                            unsigned long long lo, hi;
-                            if (sh == 0) { lo = elo; hi = ehi; }
-                            else if (sh < 64) { lo = (elo >> sh) | (ehi << (64 - sh)); hi = ehi >> sh; }
-                            else { lo = ehi >> (sh - 64); hi = 0; }
-                            if ((((lo ^ qlo) & mlo) | ((hi ^ qhi) & mhi)) == 0ull) {
-                                const uint32_t row = rw == 0 ? a.x : rw == 1 ? a.y : rw == 2 ? a.z : rw == 3 ? a.w : b.x;
-                                best = row < best ? row : best;
-                                ++cnt;
-                            }
+                    bool zero = false, absent = false;
+                    if (ix.ctx_raw) {                                     // raw bytes: pattern words compare directly, no translation;
+                        uint32_t w0, w1, w2;                              // a byte that is absent from the text just never matches
+                        pat.bytes12(o, w0, w1, w2);
+                        qlo = ((unsigned long long)w1 << 32) | w0;
+                        qhi = w2;
+                        const unsigned long long l = qlo | ~mlo, h = (qhi & mhi) | ~mhi;   // bytes past the hop must not look like zeros
+                        zero = (((l - 0x0101010101010101ull) & ~l) | ((h - 0x0101010101010101ull) & ~h)) & 0x8080808080808080ull;
+                    } else {
+                        for (int k = 0; k < j; ++k) {
+                            const uint32_t pc = pat(o + k), cd = tb.code[pc];
+                            zero = zero || (pc == 0);
+                            absent = absent || (cd == (uint32_t)kCodeAbsent);
+                            const unsigned long long v = (unsigned long long)((cd + 1u) & ((1u << bits) - 1u));
+                            const uint32_t ob = (uint32_t)k * bits;
+                            if (ob < 64) { qlo |= v << ob; if (ob + bits > 64) qhi |= v >> (64 - ob); }
+                            else qhi |= v << (ob - 64);
                         }
                     }
-                    if (STATS && lane == 0) { touched += absent ? 0u : ep - sp; steps += rem; }
-                    if (G >= 2) { best = min(best, __shfl_xor_sync(gmask, best, 1)); cnt += __shfl_xor_sync(gmask, cnt, 1); }
-                    if (G >= 4) { best = min(best, __shfl_xor_sync(gmask, best, 2)); cnt += __shfl_xor_sync(gmask, cnt, 2); }
-                    if (cnt) { sp = best; ep = best + cnt; } else { sp = 0; ep = 0; }
-                    i = -1;
-                    stepped = true;
+                    if (zero) noctx = true;                               // byte 0: the '$' row wraps the text, take the ordinary steps
+                    else {
+                        uint32_t best = 0xFFFFFFFFu, cnt = 0;
+                        if (!absent) {
+                            for (uint32_t r = sp + (uint32_t)lane; r < ep; r += G) {
+                                uint4 a, b;
+                                ldg256(ix.ctx + (uint64_t)r * 2, a, b);
+                                const unsigned long long elo = ((unsigned long long)b.z << 32) | b.y, ehi = b.w;
+                                unsigned long long lo, hi;
+                                if (sh == 0) { lo = elo; hi = ehi; }
+                                else if (sh < 64) { lo = (elo >> sh) | (ehi << (64 - sh)); hi = ehi >> sh; }
+                                else { lo = ehi >> (sh - 64); hi = 0; }
+                                if ((((lo ^ qlo) & mlo) | ((hi ^ qhi) & mhi)) == 0ull) {
+                                    const uint32_t row = t == 0 ? a.x : t == 1 ? a.y : t == 2 ? a.z : t == 3 ? a.w : b.x;
+                                    best = row < best ? row : best;
+                                    ++cnt;
+                                }
+                            }
+                        }
+                        if (STATS && lane == 0) { touched += absent ? 0u : rows; steps += j; }
+                        if (G >= 2) { best = min(best, __shfl_xor_sync(gmask, best, 1)); cnt += __shfl_xor_sync(gmask, cnt, 1); }
+                        if (G >= 4) { best = min(best, __shfl_xor_sync(gmask, best, 2)); cnt += __shfl_xor_sync(gmask, cnt, 2); }
+                        if (cnt) { sp = best; ep = best + cnt; } else { sp = 0; ep = 0; }
+                        i -= j;
+                        stepped = true;
+                    }
                 }
             }
             if (!stepped && !noshort && (ep - sp) == 1u && i >= 2 && i < ix.isat_syms) {

@@ -93,6 +93,27 @@ count_fixed_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restric
     }
 }
 
+// Fixed-length patterns too long to stage a CTA's worth of them in shared memory: read from global memory, same outputs
+template <int G, int LAYOUT, typename OutT>
+__global__ void __launch_bounds__(kThreads)
+count_fixed_gmem_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, int len, long long m, OutT *__restrict__ sp_out,
+                        OutT *__restrict__ ep_out, const __grid_constant__ PeerSinks sinks) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    constexpr int QPB = kThreads / G;
+    const long long q = (long long)blockIdx.x * QPB + threadIdx.x / G;
+    const bool active = q < m;
+    uint32_t sp, ep, touched = 0, steps = 0;
+    search_pattern<G, LAYOUT, false>(ix, tb, GlobalPattern{pat + (active ? q : 0) * len, len}, len, active, sp, ep, touched, steps);
+    if (active && (threadIdx.x % G) == 0) {
+        const bool hit = sp < ep;
+        sp_out[q] = hit ? (OutT)sp : (OutT)0;
+        ep_out[q] = hit ? (OutT)ep : (OutT)0;
+        for (int j = 0; j < sinks.n; ++j) sinks.p[j][sinks.offset + q] = hit ? ep - sp : 0u;
+    }
+}
+
 template <int G, int LAYOUT>
 __global__ void __launch_bounds__(kThreads)
 count_var_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, const long long *__restrict__ off,
@@ -275,7 +296,7 @@ locate_kernel(const __grid_constant__ DevIndex ix, const long long *__restrict__
                 return;
             }
             r = lf_value<G, LAYOUT>(ix, tb, c, r);
-            ++k;
+            if (++k > ix.n) { if ((threadIdx.x % G) == 0) pos[t] = 0xFFFFFFFFu; return; }      // cannot happen on a consistent index (fmx_open checks)
         }
     }
     for (;;) {
@@ -286,7 +307,7 @@ locate_kernel(const __grid_constant__ DevIndex ix, const long long *__restrict__
             return;
         }
         r = lf_value<G, LAYOUT>(ix, tb, ix.bwt[r], r);
-        ++k;
+        if (++k > ix.n) { if ((threadIdx.x % G) == 0) pos[t] = 0xFFFFFFFFu; return; }
     }
 }
 
@@ -501,11 +522,17 @@ cudaError_t launch_count_fixed(const DevIndex &ix, LaunchCfg cfg, const uint8_t 
     if (cfg.count_lanes) cfg.lanes = cfg.count_lanes;
     PeerSinks sinks{};
     if (sinks_or_null) sinks = *sinks_or_null;
-    const size_t smem = (size_t)(kThreads / cfg.lanes) * (size_t)(len > 0 ? len : 1);
-    if (smem > 160 * 1024) return cudaErrorInvalidValue;
+    // + 16: the 12-byte pattern windows of the row-context hops are read as whole words and may run past the last pattern
+    const size_t smem = (size_t)(kThreads / cfg.lanes) * (size_t)(len > 0 ? len : 1) + 16;
+    const bool too_long = smem > 160 * 1024;             // patterns of more than ~640 bytes per lane: read them from global memory
 #define CALL(G, LAY)                                                                                                  \
     {                                                                                                                 \
-        if (d_stats) {                                                                                                \
+        if (too_long && !d_stats) {                                                                                   \
+            if (out64) count_fixed_gmem_kernel<G, LAY, long long><<<grid_for(m, G), kThreads, 0, st>>>(ix, d_pat, len, m, (long long *)d_sp, (long long *)d_ep, sinks); \
+            else count_fixed_gmem_kernel<G, LAY, uint32_t><<<grid_for(m, G), kThreads, 0, st>>>(ix, d_pat, len, m, (uint32_t *)d_sp, (uint32_t *)d_ep, sinks); \
+        } else if (too_long) {                                                                                        \
+            return cudaErrorInvalidValue;                                                                             \
+        } else if (d_stats) {                                                                                                \
             auto k = count_fixed_kernel<G, LAY, true, uint32_t>;                                                      \
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
             k<<<grid_for(m, G), kThreads, smem, st>>>(ix, d_pat, len, m, (uint32_t *)d_sp, (uint32_t *)d_ep, d_stats, sinks); \

@@ -19,7 +19,7 @@ _SO = os.path.join(_HERE, "libfmgpu.so")
 FMX_OK, FMX_E_IO, FMX_E_FORMAT, FMX_E_CUDA, FMX_E_ARG = 0, -1, -2, -3, -4
 FMX_E_CAPACITY, FMX_E_SYNTAX, FMX_E_UNSUPPORTED, FMX_E_LIMIT = -5, -6, -7, -8
 LAYOUT_AUTO, LAYOUT_WM, LAYOUT_PLANES = 0, 1, 2
-ACCEL_AUTO, ACCEL_KMER, ACCEL_TEXT, ACCEL_CTX, ACCEL_NONE, ACCEL_CTX8 = 0, 1, 2, 4, 8, 16
+ACCEL_AUTO, ACCEL_KMER, ACCEL_TEXT, ACCEL_CTX, ACCEL_NONE, ACCEL_CTX8, ACCEL_NO_SA = 0, 1, 2, 4, 8, 16, 32
 
 
 class FmxError(Exception):
@@ -38,7 +38,8 @@ class ReUnsupported(FmxError):
 
 class fmx_opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("layout", C.c_int32), ("sa_sample_rate", C.c_int32), ("require_fm", C.c_int32),
-                ("max_index_bytes", C.c_int64), ("lanes_per_query", C.c_int32), ("accel", C.c_int32), ("kmer_table_bytes", C.c_int64)]
+                ("max_index_bytes", C.c_int64), ("lanes_per_query", C.c_int32), ("accel", C.c_int32), ("kmer_table_bytes", C.c_int64),
+                ("max_total_bytes", C.c_int64)]
 
 
 _lib = None
@@ -105,6 +106,7 @@ def lib():
     L.fmx_gather_bench.argtypes = [p, i32, i32, i64, i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.fmx_set_lanes.argtypes = [p, i32]
     L.fmx_set_chunk.argtypes = [p, i64]
+    L.fmx_set_accel_mask.argtypes = [p, i32]
     L.fmx_set_l2_fetch_granularity.argtypes = [i32, C.POINTER(i32)]
     L.fmx_host_alloc.argtypes = [pp, i64]
     L.fmx_host_free.argtypes = [p]
@@ -146,12 +148,13 @@ def _u8(a):
 
 
 def make_opts(device=-1, layout=LAYOUT_AUTO, sa_sample_rate=0, require_fm=False, max_index_bytes=0, lanes_per_query=0, accel=ACCEL_AUTO,
-              kmer_table_bytes=0):
+              kmer_table_bytes=0, max_total_bytes=0):
     o = fmx_opts()
     lib().fmx_opts_default(C.byref(o))
     o.device, o.layout, o.sa_sample_rate = device, layout, sa_sample_rate
     o.require_fm, o.max_index_bytes, o.lanes_per_query, o.accel = int(require_fm), max_index_bytes, lanes_per_query, accel
     o.kmer_table_bytes = kmer_table_bytes
+    o.max_total_bytes = max_total_bytes
     return o
 
 
@@ -467,6 +470,10 @@ class GpuFMSearcher:
         """SACreator(path).create(): <base>.sa, n x int32 big-endian"""
         lib().fmx_write_sa_file.argtypes = [C.c_void_p, C.c_char_p]
         _check(lib().fmx_write_sa_file(self.h, os.fsencode(path)))
+
+    def set_accel_mask(self, mask):
+        """keep only the accelerators in `mask` (ACCEL_* bits; ACCEL_NONE = plain rank steps, ACCEL_AUTO = all built) for later calls"""
+        _check(lib().fmx_set_accel_mask(self.h, mask))
 
     def set_lanes(self, lanes):
         _check(lib().fmx_set_lanes(self.h, lanes))

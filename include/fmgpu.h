@@ -47,11 +47,14 @@ extern "C" {
 #define FMX_ACCEL_AUTO      0
 #define FMX_ACCEL_KMER      1   /* table of (sp,ep) after the first k steps, k = max with sigma^k*8 B <= kmer_table_bytes */
 #define FMX_ACCEL_TEXT      2   /* full SA + {inverse SA, 96 bits of text} entries (20n bytes): singleton intervals finish in 2 fetches; locate is 1 fetch */
-#define FMX_ACCEL_CTX       4   /* (implies TEXT) 32-byte row contexts { isa[sa[r]-j], j = J-4..J ; the J symbols before sa[r] }: an interval of <= 8 rows
-                                   with J-4..J pattern bytes left finishes in one fetch per row (J = 12 for byte alphabets, 19 for sigma <= 31, 32 for DNA) */
-#define FMX_ACCEL_CTX8     16   /* (alphabets of <= 4 symbols) compact 8-byte row contexts { isa[sa[r]-16], 16 two-bit symbols }: the same one-fetch-per-row
-                                   finish when exactly 16 pattern bytes remain; chosen automatically when the 32-byte form does not fit (4e9-row DNA index) */
+#define FMX_ACCEL_CTX       4   /* 32-byte row contexts { isa[sa[r]-j] for five hop lengths j (1 .. J) ; the J symbols before sa[r] } (32n bytes): an interval
+                                   of <= 8 rows advances j symbols in one fetch per row, any remaining length is a sum of hops — a pattern costs about
+                                   1 + ceil((len-k)/J) fetches (J = 12 for byte alphabets, 19 for sigma <= 31, 32 for DNA)                       */
+#define FMX_ACCEL_CTX8     16   /* (alphabets of <= 4 symbols) compact 8-byte row contexts { isa[sa[r]-16], 16 two-bit symbols }: hops of exactly 16 symbols,
+                                   the last < 16 by rank steps; chosen automatically when the 32-byte form does not fit (4e9-row DNA index)         */
 #define FMX_ACCEL_NONE      8   /* plain backward search only                                                */
+#define FMX_ACCEL_NO_SA    32   /* count-only deployment: do not keep the full suffix array (4n bytes) that the context/shortcut construction produces;
+                                   without it locate needs sa_sample_rate > 0                                                         */
 
 typedef struct fmx_index fmx_index;     /* opaque; library-owned until fmx_close  */
 typedef struct fmx_regex fmx_regex;     /* opaque; library-owned until fmx_regex_free */
@@ -66,6 +69,8 @@ typedef struct fmx_opts {
     int32_t  accel;             /* FMX_ACCEL_* bit mask; 0 = auto (all that fit the memory budget)          */
     int64_t  kmer_table_bytes;  /* budget of the k-mer table; 0 = auto: the deepest table that keeps what a count query touches inside
                                    the ~64 GB TLB reach, else 256 MiB .. 16 GiB (a sixteenth of free memory)     */
+    int64_t  max_total_bytes;   /* cap on EVERYTHING resident for this index (rank structure + BWT + sampled SA + accelerators); 0 = no cap.
+                                   FMX_LAYOUT_AUTO / FMX_ACCEL_AUTO pick the fastest combination under it; fmx_info reports what was built  */
 } fmx_opts;
 
 void        fmx_opts_default(fmx_opts *o);
@@ -226,6 +231,9 @@ int fmx_host_free(void *p);
 /* cudaLimitMaxL2FetchGranularity of the current device (32/64/128; 0 = only query).  Random 64-B block fetches
  * over-fetch from DRAM when the L2 promotes misses to 128 B; see DESIGN.md §5.                              */
 int fmx_set_l2_fetch_granularity(int32_t bytes, int32_t *effective);
+/* Hides accelerators that were built from subsequent calls: `mask` = FMX_ACCEL_* bits to keep (FMX_ACCEL_NONE = plain backward
+ * search over the rank structure; FMX_ACCEL_AUTO = all that were built).  Results never change; for measuring one index both ways. */
+int fmx_set_accel_mask(fmx_index *ix, int32_t mask);
 /* Queries per pipeline chunk of the host-buffer count calls (0 = default 2^20).                          */
 int fmx_set_chunk(fmx_index *ix, int64_t queries_per_chunk);
 /* Re-selects how many lanes (1, 2 or 4) cooperate on one 64-B rank block for subsequent calls.           */

@@ -163,7 +163,8 @@ def test_count_parity_small(ref_dir, cfg, accel):
     o = fo.OracleIndex.load(os.path.join(ref_dir, "test.cmp"), big_endian=False)
     g = _open(os.path.join(ref_dir, "test.cmp.bwt"), cfg, accel=accel)
     info = g.info()
-    assert info["text_shortcut"] == (accel in (fx.ACCEL_AUTO, fx.ACCEL_TEXT, fx.ACCEL_CTX)) and info["ctx_entry_bytes"] in (0, 32) and (info["kmer_k"] >= 2) == (accel in (fx.ACCEL_AUTO, fx.ACCEL_KMER))
+    # the 16-byte isat entries (singleton shortcut) exist only where asked for: row contexts do the same in one fetch
+    assert info["text_shortcut"] == (accel == fx.ACCEL_TEXT) and info["ctx_entry_bytes"] in (0, 32) and (info["kmer_k"] >= 2) == (accel in (fx.ACCEL_AUTO, fx.ACCEL_KMER))
     assert (info["ctx_depth"] > 0) == (accel in (fx.ACCEL_AUTO, fx.ACCEL_CTX))
     rng = np.random.default_rng(11)
     tprime = text[::-1]
@@ -178,7 +179,7 @@ def test_count_parity_small(ref_dir, cfg, accel):
         assert (int(sp[i]), int(ep[i])) == (r if r else (0, 0)), p
     assert g.search(b"") == (0, o.n)
     # fixed-length fast path, incl. ragged tail of the last CTA and odd lengths
-    for ln in (1, 3, 12, 16, 21, 27):
+    for ln in (1, 3, 12, 16, 21, 27, 40):
         arr = np.frombuffer(b"".join(p.ljust(ln, b"q")[:ln] for p in pats[:4499] if len(p) >= min(ln, 9)), np.uint8).reshape(-1, ln)
         sp, ep = g.count_fixed(arr)
         osp, oep = o.count_batch(arr.reshape(-1), np.arange(0, arr.size + 1, ln, dtype=np.int64))
@@ -549,9 +550,9 @@ def test_row_context_small_intervals(cfg, sigma, form):
     J = info["ctx_depth"]
     assert info["ctx_entry_bytes"] == form and info["kmer_k"] == 2
     assert J == ({2: 48, 4: 32, 20: 19, 200: 12}[sigma] if form == 32 else 16)
-    assert info["text_shortcut"] == (form == 32)            # the compact form is built without the 16-byte isat entries
+    assert not info["text_shortcut"]                        # row contexts are built without the 16-byte isat entries
     pats = []
-    for ln in list(range(1, J + 8)) + [J + 20]:
+    for ln in list(range(1, J + 8)) + [J + 20, 2 * J + 1, 2 * J + 5, 3 * J + 2, 131, 150]:      # every hop plan, and beyond the plan table
         for _ in range(60):
             s = int(rng.integers(0, len(tp) - ln))
             p = bytearray(tp[s:s + ln])
@@ -566,7 +567,7 @@ def test_row_context_small_intervals(cfg, sigma, form):
         assert (int(sp[i]), int(ep[i])) == (r if r else (0, 0)), p
         sizes.add(int(ep[i] - sp[i]))
     assert len(sizes & {1, 2, 3, 4, 5, 6, 7, 8}) >= (3 if sigma > 2 else 1) and max(sizes) > 8
-    for ln in (J - 4, J, J + 2, J + 3):
+    for ln in (J - 4, J, J + 2, J + 3, 2 * J + 4, 2 * J + 5, 132):
         arr = np.frombuffer(b"".join(p[:ln] for p in pats if len(p) >= ln), np.uint8).reshape(-1, ln)
         s2, e2 = g.count_fixed(arr)
         osp, oep = o.count_batch(arr.reshape(-1), np.arange(0, arr.size + 1, ln, dtype=np.int64))
@@ -576,6 +577,98 @@ def test_row_context_small_intervals(cfg, sigma, form):
     for k in range(40):
         assert np.array_equal(pos[off[k]:off[k + 1]], np.sort(sa[sp[k]:ep[k]]))
     g.close()
+    o.close()
+
+
+@pytest.mark.parametrize("sigma", [4, 26, 255])
+def test_every_length_hops(sigma):
+    """Row-context hops: patterns of every length 1..100 (hits, near misses, interval sizes 1..8 and wider) cost the same (sp, ep) as
+    stepping, for the three symbol packings, with a k-mer table in front (AUTO) and without (CTX alone)."""
+    rng = np.random.default_rng(7 + sigma)
+    alpha = np.arange(1, 256, dtype=np.uint8) if sigma == 255 else rng.choice(np.arange(1, 256), sigma, replace=False).astype(np.uint8)
+    unit = alpha[rng.integers(0, sigma, 3000)]
+    text = np.concatenate([unit, alpha[rng.integers(0, sigma, 500)], unit[500:2500], alpha[rng.integers(0, sigma, 300)], unit[1000:1400],
+                           unit[1000:1400], unit[1000:1400]]).tobytes()
+    tp = bytes(fo.file_to_text_rev(text))
+    bwt, eof, cnt = fo.build_bwt(fo.file_to_text_rev(text))
+    o = fo.OracleIndex.from_bwt(bwt, eof, cnt)
+    for accel, lanes in ((fx.ACCEL_AUTO, 0), (fx.ACCEL_CTX, 1), (fx.ACCEL_CTX, 4)):
+        g = fx.GpuFMSearcher(bwt=bwt, eof=eof, counts=cnt, accel=accel, lanes_per_query=lanes)
+        assert g.info()["ctx_entry_bytes"] == 32
+        for ln in range(1, 101):
+            offs = rng.integers(0, len(tp) - ln, 64)
+            arr = np.stack([np.frombuffer(tp[s:s + ln], np.uint8) for s in offs]).copy()
+            arr[::5, int(rng.integers(0, ln))] = alpha[rng.integers(0, sigma)]           # near misses
+            sp, ep = g.count_fixed(arr)
+            osp, oep = o.count_batch(arr.reshape(-1), np.arange(0, arr.size + 1, ln, dtype=np.int64))
+            assert np.array_equal(sp, osp) and np.array_equal(ep, oep), ln
+        g.close()
+    o.close()
+
+
+def test_long_fixed_patterns_leave_shared_memory(ref_dir):
+    """fixed-length patterns too long to stage a CTA's worth in shared memory (> ~640 bytes per lane) take the global-memory kernel"""
+    text = open(os.path.join(ref_dir, "test.txt"), "rb").read()
+    o = fo.OracleIndex.load(os.path.join(ref_dir, "test.cmp"), big_endian=False)
+    tp = text[::-1]
+    for lanes in (1, 4):
+        g = fx.GpuFMSearcher(os.path.join(ref_dir, "test.cmp.bwt"), bigEndian=False, lanes_per_query=lanes)
+        for ln in (700, 2600):
+            arr = np.stack([np.frombuffer(tp[s:s + ln], np.uint8) for s in range(0, 3000, 100)]).copy()
+            arr[::3, ln // 2] = ord("!")
+            sp, ep = g.count_fixed(arr)
+            osp, oep = o.count_batch(arr.reshape(-1), np.arange(0, arr.size + 1, ln, dtype=np.int64))
+            assert np.array_equal(sp, osp) and np.array_equal(ep, oep) and (ep > sp).sum() >= 10
+            assert np.array_equal(g.count_only_fixed(arr).astype(np.int64), oep - osp)
+        g.close()
+    o.close()
+
+
+def test_mismatched_bwt_and_aux_are_refused(ref_dir):
+    """.aux counts that do not describe the .bwt (LF would not be a permutation): FMX_E_FORMAT at open instead of a runaway walk"""
+    o = fo.OracleIndex.load(os.path.join(ref_dir, "test1024.cmp"), big_endian=False)
+    bwt = np.array(o.bwt(), np.uint8)
+    counts = np.bincount(bwt, minlength=256).astype(np.int64)
+    counts[0] = 0
+    a, b = int(bwt[10]), int(bwt[10]) % 255 + 1
+    bad = bwt.copy()
+    bad[bad == a] = b                                       # same length, different histogram
+    with pytest.raises(fx.FmxError, match="do not belong together") as ei:
+        fx.GpuFMSearcher(bwt=bad, eof=o.eof, counts=counts, sa_sample_rate=4)
+    assert ei.value.code == fx.FMX_E_FORMAT
+    # right histogram, wrong order: LF is a permutation but not one cycle -> refused by the chain walk's own check, no hang
+    perm = bwt.copy()
+    i, j = [k for k in range(len(perm)) if k != o.eof][:2]
+    k2 = next(k for k in range(len(perm) - 1, 0, -1) if k != o.eof and perm[k] != perm[i])
+    perm[i], perm[k2] = perm[k2], perm[i]
+    try:
+        g = fx.GpuFMSearcher(bwt=perm, eof=o.eof, counts=counts, sa_sample_rate=4)
+        g.close()                                           # a swap may by chance keep one cycle; then the index is simply another text's
+    except fx.FmxError as e:
+        assert e.code == fx.FMX_E_FORMAT
+    o.close()
+
+
+def test_total_footprint_cap(ref_dir):
+    """fmx_opts.max_total_bytes: everything resident stays under the cap, whatever that leaves out, and results do not change"""
+    text = open(os.path.join(ref_dir, "test.txt"), "rb").read()
+    o = fo.OracleIndex.load(os.path.join(ref_dir, "test.cmp"), big_endian=False)
+    rng = np.random.default_rng(3)
+    pats = _patterns(text, rng, 600, 16) + _patterns(text, rng, 300, 30)
+    want = [o.search(p) or (0, 0) for p in pats]
+    n = o.n
+    seen = set()
+    for cap in (0, 60 * n, 40 * n, 12 * n, 3 * n, 2 * n):
+        g = fx.GpuFMSearcher(os.path.join(ref_dir, "test.cmp.bwt"), bigEndian=False, max_total_bytes=cap)
+        info = g.info()
+        assert cap == 0 or info["index_bytes"] <= cap, (cap, info)
+        seen.add((info["layout"], info["ctx_depth"] > 0, info["kmer_k"]))
+        sp, ep = g.count_batch(pats)
+        assert [(int(a), int(b)) for a, b in zip(sp, ep)] == want
+        g.close()
+    assert len(seen) >= 3                                   # the cap really changed what was built
+    with pytest.raises(fx.FmxError):
+        fx.GpuFMSearcher(os.path.join(ref_dir, "test.cmp.bwt"), bigEndian=False, max_total_bytes=n // 2)
     o.close()
 
 
@@ -596,7 +689,7 @@ def test_compact_contexts_are_chosen_when_the_wide_form_does_not_fit(monkeypatch
     info = g.info()
     assert info["ctx_entry_bytes"] == 8 and info["ctx_depth"] == 16 and not info["text_shortcut"] and 4 ** info["kmer_k"] >= len(bwt) // 2
     tp = bytes(fo.file_to_text_rev(text))
-    for ln in (12, 16 + info["kmer_k"], 32, 40):
+    for ln in (12, 16 + info["kmer_k"], 32, 40, 32 + info["kmer_k"], 75):
         offs = rng.integers(0, len(tp) - ln, 3000)
         arr = np.stack([np.frombuffer(tp[s:s + ln], np.uint8) for s in offs]).copy()
         arr[::7, ln // 2] = ord("A")                        # some near misses
