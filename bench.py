@@ -1,25 +1,34 @@
 #!/usr/bin/env python
 """
-bench.py — FM-index count throughput on B200 (BASELINE.json metric: FM count queries/s, len-16, 1 GB text).
+bench.py — FM-index search throughput on B200 (BASELINE.json metric: FM count queries/s, len-16, 1 GB text; regex queries/s).
 
-    python bench.py --gpus N --steps K --warmup W                (this repo's CUDA path through the C ABI)
-    python bench.py --impl reference --gpus N --steps K --warmup W   (the reference algorithm on the host CPU cores)
+    python bench.py --gpus N --steps K --warmup W                       this repo's CUDA path through the C ABI (libfmgpu.so)
+    python bench.py --impl reference --gpus N --steps K --warmup W      the reference algorithm on the host CPU cores (oracle/)
+    python bench.py --workload cfg3|cfg4|cfg5 ...                       the other BASELINE configs as top-level lines
 
-Workload (BASELINE.json configs[1], SURVEY.md §8d cfg 2): 10^9 bytes i.i.d. uniform over 1..255 (seed 2), indexed as
-the reference does (reverse(text)+'$', .bwt/.aux files); per GPU 10 M len-16 patterns, 90 % substrings of the text
-(reversed, as search() consumes them) and 10 % uniform random bytes (seed 3).  A "step" is one pass of the batch
-through the count kernel.  With N GPUs the index is replicated, every rank owns its own 10 M-query shard (weak
-scaling) and the per-query counts are all-gathered over NCCL; time is the max over ranks of CUDA-event time.
+Default line = BASELINE configs[1] (SURVEY.md §8d cfg 2): 10^9 bytes i.i.d. uniform over 1..255 (seed 2), indexed as the reference
+does (reverse(text)+'$', .bwt/.aux files); per GPU 10 M len-16 patterns, 90 % reversed text substrings, 10 % random (seed 3).  A "step"
+is one pass of the batch through the count kernel.  With N GPUs the index is replicated, every rank owns its own 10 M-query shard
+(weak scaling) and the per-query counts are exchanged by the count kernel itself (peer-memory stores) + a 4-byte NCCL barrier.
+The same line carries, as extra keys, what bounds and qualifies that number:
+
+    sweep      cfg-2 index at len 8..64, plain PLANES and the wavelet matrix at len 16, each with requests/query and oracle parity
+    sustained  >= 2 s of back-to-back launches with the in-window clock / power record
+    pcie       the box's concurrent pinned H2D+D2H copy ceiling for this step's bytes (what bounds e2e)
+    english    cfg 3/4: 10^9-byte English-like text — count at len 12 and 16, locate (SA sample rate 32), 100 k Glushkov regexes
+    cfg5       4*10^9-byte DNA text, len-32 count queries (2-bit packed upload for e2e)
 
 One JSON line on stdout (rank 0).  Everything else goes to stderr.
 """
 import argparse
 import json
+import lzma
 import os
 import subprocess
 import sys
 import threading
 import time
+import traceback
 
 import numpy as np
 
@@ -27,8 +36,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 OUT = sys.stdout
-METRIC = "fm_count_queries_per_s_len16_1GB_text"
 UNIT = "queries/s"
+METRICS = {"cfg2": "fm_count_queries_per_s_len16_1GB_text", "cfg3": "fm_locate_queries_per_s_len12_1GB_english_text_sa32",
+           "cfg4": "glushkov_regex_queries_per_s_1GB_english_text", "cfg5": "fm_count_queries_per_s_len32_4GB_dna_text"}
+DEFAULTS = {"cfg2": (1_000_000_000, 10_000_000, 16), "cfg3": (1_000_000_000, 1_000_000, 12), "cfg4": (1_000_000_000, 100_000, 0),
+            "cfg5": (4_000_000_000, 12_500_000, 32)}
 
 
 def log(*a):
@@ -45,21 +57,50 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-# ------------------------------------------------------------------------------------------------ workload
-def make_text(n, workload="cfg2"):
-    if workload == "cfg5":                                  # 4e9 bytes i.i.d. uniform over ACGT, seed 7 (SURVEY §8d cfg 5)
-        return np.frombuffer(b"ACGT", np.uint8)[np.random.default_rng(7).integers(0, 4, n, dtype=np.uint8)]
-    return np.random.default_rng(2).integers(1, 256, n, dtype=np.uint8)
+# ------------------------------------------------------------------------------------------------ workloads
+def vocabulary(via):
+    """words.txt vocabulary from the committed words.bwt fixture: through the GPU searcher (prevSubstr(eof, n) walks the whole file,
+    T/Indexer.scala:1120) in our arm, through the oracle in the reference arm."""
+    d = "/tmp/fmx_words"
+    os.makedirs(d, exist_ok=True)
+    with lzma.open(os.path.join(ROOT, "tests", "golden", "ref", "words.bwt.xz"), "rb") as f:
+        open(os.path.join(d, "words.bwt"), "wb").write(f.read())
+    open(os.path.join(d, "words.aux"), "wb").write(open(os.path.join(ROOT, "tests", "golden", "ref", "words.aux"), "rb").read())
+    if via == "gpu":
+        from findex_b200 import fmindex as fx
+        g = fx.GpuFMSearcher(os.path.join(d, "words.bwt"), accel=fx.ACCEL_NONE)
+        text = g.prevSubstr(g.eof, g.n)[1:]
+        g.close()
+    else:
+        from oracle import fm_oracle as fo
+        o = fo.OracleIndex.load(os.path.join(d, "words"))
+        sa = o.sa()
+        tp = np.zeros(o.n, np.uint8)
+        tp[(sa.astype(np.int64) - 1) % o.n] = o.bwt()
+        text = bytes(tp[:-1][::-1])
+        o.close()
+    return [w for w in text.split(b"\r\n") if w]
+
+
+def make_text(n, workload, via="gpu"):
+    from findex_b200 import synth
+    if workload == "cfg5":
+        return synth.dna(n, 7)
+    if workload in ("cfg3", "cfg4"):
+        return synth.english_like(vocabulary(via), n, 4)
+    return synth.uniform_bytes(n, 2)
 
 
 def make_queries(text, m, ln, seed, rank, out=None, workload="cfg2"):
-    """90 % hits (reversed substrings at uniform offsets), 10 % uniform random symbols; shuffled."""
+    """cfg 2/5: 90 % hits (reversed substrings at uniform offsets), 10 % uniform random symbols, shuffled.  cfg 3: substrings only."""
     rng = np.random.default_rng([seed, rank])
-    nh = int(m * 0.9)
+    nh = m if workload in ("cfg3", "cfg4") else int(m * 0.9)
     pats = out if out is not None else np.empty((m, ln), np.uint8)
     offs = rng.integers(0, len(text) - ln, nh)
-    idx = offs[:, None] + np.arange(ln - 1, -1, -1)[None, :]
-    hits = text[idx]
+    hits = text[offs[:, None] + np.arange(ln - 1, -1, -1)[None, :]]
+    if nh == m:
+        pats[:] = hits
+        return pats, np.ones(m, bool)
     if workload == "cfg5":
         rnd = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, (m - nh, ln), dtype=np.uint8)]
     else:
@@ -67,23 +108,35 @@ def make_queries(text, m, ln, seed, rank, out=None, workload="cfg2"):
     perm = rng.permutation(m)
     is_hit = np.zeros(m, bool)
     is_hit[:nh] = True
-    allp = np.concatenate([hits, rnd])
-    pats[:] = allp[perm]
-    return pats, is_hit[perm], np.concatenate([offs, np.full(m - nh, -1)])[perm]
+    pats[:] = np.concatenate([hits, rnd])[perm]
+    return pats, is_hit[perm]
+
+
+def index_base(n, workload):
+    return "/tmp/fmx_bench_%s_%d" % ({"cfg4": "cfg3"}.get(workload, workload), n)
+
+
+def workload_config(args, workload=None, n=None, m=None, ln=None):
+    """identical in both arms (the driver compares the dicts)"""
+    w = workload or args.workload
+    n, m, ln = n or args.text_bytes, m or args.queries, args.len if ln is None else ln
+    what = {"cfg2": "cfg2: %d-byte uniform text over bytes 1..255 (seed 2), %d len-%d count queries per GPU, 90%% hits / 10%% random (seed 3)" % (n, m, ln),
+            "cfg3": "cfg3: %d-byte English-like text (Zipf words, seed 4), %d len-%d locate queries in all (text substrings, seed 5), SA sample rate 32" % (n, m, ln),
+            "cfg4": "cfg4: %d-byte English-like text (Zipf words, seed 4), %d template regexes per GPU (classes, alternation, bounded repeats, \\d, '.'; seed 6)" % (n, m),
+            "cfg5": "cfg5: %d-byte uniform DNA text (ACGT, seed 7), %d len-%d count queries per GPU, 90%% hits / 10%% random (seed 8)" % (n, m, ln)}[w]
+    return {"workload": what, "text_bytes": n, "queries_per_gpu": m, "pattern_len": ln,
+            "parallelism": "dp%d (index replicated, queries sharded)" % args.gpus,
+            "l2": "inputs and index (GBs) exceed the 126 MB L2; no explicit flush"}
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons, sampled every 50 ms from before the warm-up until after the timed region;
-    the summary uses the samples that fall inside the timed window (all samples under load if the window is shorter
-    than the sampling period)."""
+    """nvidia-smi clocks / throttle reasons, sampled every 50 ms from before the warm-up until after the timed region; the summary uses
+    the samples inside the timed window (all samples under load if the window is shorter than the sampling period)."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu):
-        self.gpu = gpu
-        self.rows = []
-        self.proc = None
-        self.window = [None, None]
+        self.gpu, self.rows, self.proc, self.window = gpu, [], None, [None, None]
 
     def start(self):
         try:
@@ -127,28 +180,27 @@ class ClockSampler:
         inside = [p for p in parsed if self.window[0] is not None and self.window[0] <= p[0] <= (self.window[1] or 1e18) + 0.06]
         use = inside if inside else parsed
         reasons = sorted({x for p in use for x in p[4]})
-        return {"sm_mhz": float(np.median([p[1] for p in use])) if use else None, "sm_max_mhz": max([p[2] for p in use]) if use else None,
-                "power_w_max": max([p[3] for p in use]) if use else None, "reasons": reasons, "samples": len(use),
+        return {"sm_mhz": float(np.median([p[1] for p in use])) if use else None, "sm_mhz_min": min([p[1] for p in use]) if use else None,
+                "sm_max_mhz": max([p[2] for p in use]) if use else None, "power_w_max": max([p[3] for p in use]) if use else None,
+                "power_w_median": float(np.median([p[3] for p in use])) if use else None, "reasons": reasons, "samples": len(use),
                 "samples_in_timed_window": len(inside)}
-
-
-def index_base(n, workload="cfg2"):
-    return "/tmp/fmx_bench_%s_%d" % (workload, n)
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path: NaiveFMSearcher.occ = binary search in the in-memory .fm
-    array (bwtmerger.scala:354-375) driving SuffixAlgo.search (findex.scala:15-31) — the C restatement under oracle/
-    (no JVM exists in this image), all host threads, a bounded sample of the same workload per step."""
+    """The reference's own CPU implementation of the path: NaiveFMSearcher.occ = binary search in the in-memory .fm array
+    (bwtmerger.scala:354-375) driving SuffixAlgo.search (findex.scala:15-31), sorted sa[sp..ep) for locate (util.scala:213-224) and
+    ReTree._matchSA (retree.scala:618-653) — the C restatement under oracle/ (no JVM exists in this image), all host threads, a bounded
+    sample of the same workload per step."""
     if rank != 0:
         return
     from oracle import fm_oracle as fo
     cores = os.cpu_count() or 1
+    w = args.workload
     n, m, ln = args.text_bytes, args.queries, args.len
     t0 = time.time()
-    text = make_text(n, args.workload)
-    base = index_base(n, args.workload)
+    text = make_text(n, w, via="oracle")
+    base = index_base(n, w)
     if not (os.path.exists(base + ".bwt") and os.path.exists(base + ".aux")):
         # index construction is setup, not the measured path; the device suffix sorter only writes the reference's files
         from findex_b200 import build as fbuild, fmindex as fx
@@ -164,319 +216,667 @@ def run_reference(args, rank, world):
     fo.build(native=True)
     ix = fo.OracleIndex.load(base)
     log("reference arm: index loaded + fm array materialised in %.1f s" % (time.time() - t0))
-    pats, _, _ = make_queries(text, m, ln, 3, 0, workload=args.workload)
-    probe = 20000
-    t1 = time.time()
-    ix.count_batch(pats[:probe].reshape(-1), np.arange(0, probe * ln + 1, ln, dtype=np.int64), threads=cores)
-    rate = probe / max(time.time() - t1, 1e-6)
-    budget_s = 120.0 / max(args.steps + args.warmup, 1)
-    sample = int(min(m, max(probe, rate * min(budget_s, 8.0))))
-    off = np.arange(0, sample * ln + 1, ln, dtype=np.int64)
-    flat = pats[:sample].reshape(-1)
+    budget_s = min(8.0, 120.0 / max(args.steps + args.warmup, 1))
+    unit = UNIT
+    if w == "cfg4":
+        from findex_b200 import synth
+        rxs = synth.regex_templates(text, np.random.default_rng([6, 0]), min(m, 5000))
+        rxs = [t for t in (_oracle_compile(r) for r in rxs) if t is not None]       # ReTree(post): compiled once, outside the timed traversal
+        rate = _probe(lambda k: _oracle_regex(ix, rxs[:k], cores), 64)
+        sample = int(min(len(rxs), max(64, rate * budget_s)))
+        run = lambda: _oracle_regex(ix, rxs[:sample], cores)          # noqa: E731
+        unit = "regexes/s"
+        sdesc = "first %d regexes of the %d-regex batch per step, %d threads" % (sample, m, cores)
+    else:
+        pats, _ = make_queries(text, m, ln, {"cfg2": 3, "cfg3": 5, "cfg5": 8}[w], 0, workload=w)
+        if w == "cfg3":
+            t1 = time.time()
+            ix.sa()                                                    # SACreator.create: the reference's one-off .sa (n FL steps)
+            log("reference arm: suffix array materialised in %.1f s (setup, as SACreator.create)" % (time.time() - t1))
+        fn = (lambda k: _oracle_locate(ix, pats[:k], ln, cores)) if w == "cfg3" else \
+            (lambda k: ix.count_batch(pats[:k].reshape(-1), np.arange(0, k * ln + 1, ln, dtype=np.int64), threads=cores))
+        rate = _probe(fn, 20000 if w != "cfg3" else 2000)
+        sample = int(min(m, max(2000, rate * budget_s)))
+        run = lambda: fn(sample)                                       # noqa: E731
+        sdesc = "first %d of the %d-query batch per step, %d threads" % (sample, m, cores)
     for _ in range(args.warmup):
-        ix.count_batch(flat, off, threads=cores)
+        run()
     t1 = time.time()
     for _ in range(args.steps):
-        ix.count_batch(flat, off, threads=cores)
+        run()
     dt = time.time() - t1
     v = sample * args.steps / dt
-    sdesc = "first %d of the %d-query batch per step, %d threads" % (sample, m, cores)
-    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-           "data": "synthetic", "config": workload_config(args),
-           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sdesc,
+    out = {"impl": "reference", "metric": METRICS[w], "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if w == "cfg3" else "weak", "vs_baseline": None,
+           "dtype": "u32", "data": "synthetic", "config": workload_config(args),
+           "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sdesc,
                             "note": "JVM unavailable - C restatement of the reference algorithm (binary search in .fm)"},
-           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+           "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(out), file=OUT, flush=True)
 
 
-def workload_config(args):
-    what = ("cfg5: %d-byte uniform DNA text (ACGT, seed 7)" % args.text_bytes) if args.workload == "cfg5" else \
-        ("cfg2: %d-byte uniform text over bytes 1..255 (seed 2)" % args.text_bytes)
-    return {"workload": "%s, %d len-%d count queries per GPU, 90%% hits / 10%% random (seed 3)" % (what, args.queries, args.len),
-            "text_bytes": args.text_bytes, "queries_per_gpu": args.queries, "pattern_len": args.len, "parallelism": "dp%d (index replicated, "
-            "queries sharded)" % args.gpus, "l2": "inputs (160 MB patterns) and index (GBs) exceed the 126 MB L2; no explicit flush"}
+def _probe(fn, k):
+    t1 = time.time()
+    fn(k)
+    return k / max(time.time() - t1, 1e-6)
 
 
-# ------------------------------------------------------------------------------------------------ our arm
-def run_ours(args, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
-    from findex_b200 import build as fbuild, fmindex as fx
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    n, m, ln = args.text_bytes, args.queries, args.len
-    if rank == 0:
-        fbuild.build()
-    if world > 1:
+def _oracle_compile(rx):
+    from oracle import retree
+    try:
+        return retree.compile_regex(rx).tables()
+    except Exception:
+        return None
+
+
+def _oracle_regex(ix, tables, threads):
+    """ReTree._matchSA (caps off) of precompiled automata, one regex per task on `threads` host threads"""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max(threads, 1)) as ex:
+        return list(ex.map(lambda t: ix.regex_match_tables(t, 50_000_000)[0], tables))
+
+
+def _oracle_locate(ix, pats, ln, threads):
+    """count (all threads) + sorted sa[sp..ep) per query"""
+    k = len(pats)
+    sp, ep = ix.count_batch(pats.reshape(-1), np.arange(0, k * ln + 1, ln, dtype=np.int64), threads=threads)
+    sa = ix.sa()
+    from concurrent.futures import ThreadPoolExecutor
+
+    def part(r):
+        return [np.sort(sa[a:b]) for a, b in zip(sp[r::threads], ep[r::threads])]
+    with ThreadPoolExecutor(max(threads, 1)) as ex:
+        return list(ex.map(part, range(threads)))
+
+
+# ------------------------------------------------------------------------------------------------ our arm: shared plumbing
+class Ctx:
+    """torch / distributed plumbing of one rank"""
+
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        from findex_b200 import build as fbuild, fmindex as fx, synth
+        self.torch, self.dist, self.fx, self.synth = torch, dist, fx, synth
+        self.args, self.rank, self.world, self.local = args, rank, world, local_rank
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        if rank == 0:
+            fbuild.build()
+        self.barrier()
+        self.launches = 0
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def ensure_index(self, workload, n):
+        """text (every rank) + index files (rank 0 builds them on the GPU when absent)"""
+        t0 = time.time()
+        text = make_text(n, workload)
+        base = index_base(n, workload)
+        if self.rank == 0 and not (os.path.exists(base + ".bwt") and os.path.exists(base + ".aux")):
+            tb = time.time()
+            self.fx.build_index_files(text, base, bigEndian=True)
+            log("%s: index files built on the GPU in %.1f s" % (workload, time.time() - tb))
+        self.barrier()
+        log("rank %d: %s text + index files ready after %.1f s" % (self.rank, workload, time.time() - t0))
+        return text, base
+
+    def timed(self, fn, steps, warmup, wall=False, drain=None, sample_clocks=True):
+        """warm-up, barrier + synchronize, `steps` calls between CUDA events on the current stream, barrier + synchronize; max over ranks.
+        wall=True: host wall clock (host-API calls that return when the results are in host memory)."""
+        torch = self.torch
+        sampler = ClockSampler(self.local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        for _ in range(warmup):
+            fn()
+        if drain:
+            drain()
+        torch.cuda.synchronize()
+        self.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.mark_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.time()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        if drain:
+            drain()
+        e1.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.time() - t_wall) * 1e3
+        if sampler:
+            sampler.mark_end()
+        self.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        ms = wall_ms if wall else e0.elapsed_time(e1)
+        return self.max_over_ranks(ms), clocks
+
+
+def device_count_rate(cx, g, pats, reps=5):
+    """device-resident count of one batch: best-of-`reps` CUDA-event time, (sp, ep) as int64 arrays"""
+    torch = cx.torch
+    m, ln = pats.shape
+    d_pat = torch.from_numpy(pats).to(cx.dev)
+    d_sp = torch.zeros(m, dtype=torch.int32, device=cx.dev)
+    d_ep = torch.zeros(m, dtype=torch.int32, device=cx.dev)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        g.count_fixed_dev(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), st)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.count_fixed_dev(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), st)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    cx.launches += 3 + reps
+    sp = d_sp.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    ep = d_ep.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    return best, sp, ep
+
+
+def oracle_parity(orc, pats, sp, ep, k):
+    """GPU (sp, ep) of the first k queries == the oracle's (None reported as (0, 0))"""
+    k = min(k, len(pats))
+    ln = pats.shape[1]
+    osp, oep = orc.count_batch(pats[:k].reshape(-1), np.arange(0, k * ln + 1, ln, dtype=np.int64), threads=os.cpu_count())
+    hit = ep[:k] > sp[:k]
+    return bool(np.array_equal(np.where(hit, sp[:k], 0), osp) and np.array_equal(np.where(hit, ep[:k], 0), oep)), k
+
+
+def sweep_leg(cx, g, text, lens, m, seed, orc, label, workload="cfg2", sample=100_000):
+    """count throughput vs pattern length on one index: device q/s, requests/query, steps skipped, oracle parity on a sample"""
+    out = []
+    for ln in lens:
+        pats, _ = make_queries(text, m, ln, seed * 1000 + ln, cx.rank, workload=workload)
+        ms, sp, ep = device_count_rate(cx, g, pats)
+        req, steps = g.count_fixed_stats(pats)
+        rec = {"index": label, "len": ln, "queries": m, "kernel_ms": ms, "queries_per_s": m / (ms * 1e-3), "requests_per_query": req / m,
+               "steps_per_query": steps / m, "hits": int((ep > sp).sum())}
+        if orc is not None:
+            rec["parity_on_sample"], rec["parity_sample"] = oracle_parity(orc, pats, sp, ep, sample)
+            assert rec["parity_on_sample"], "GPU (sp,ep) differ from the oracle: %s len %d" % (label, ln)
+        out.append(rec)
+    return out
+
+
+def pcie_ceiling(cx, h2d_bytes, d2h_bytes, steps=10):
+    """The box's copy ceiling for one step's bytes: pinned H2D and D2H on two streams, concurrently on every rank, no kernel.
+    cudaMemcpyAsync one buffer per direction and step, as the host API does per chunk."""
+    torch = cx.torch
+    hin = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8).pin_memory()
+    hout = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8).pin_memory()
+    din = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8, device=cx.dev)
+    dout = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, device=cx.dev)
+    s1, s2 = torch.cuda.Stream(device=cx.dev), torch.cuda.Stream(device=cx.dev)
+
+    def step():
+        with torch.cuda.stream(s1):
+            din.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hout.copy_(dout, non_blocking=True)
+
+    def drain():
+        torch.cuda.current_stream().wait_stream(s1)
+        torch.cuda.current_stream().wait_stream(s2)
+    ms, _ = cx.timed(step, steps, 3, wall=True, drain=drain, sample_clocks=False)
+    per = ms / steps
+    return {"ms_per_step": per, "h2d_gbs_per_gpu": h2d_bytes / per / 1e6, "d2h_gbs_per_gpu": d2h_bytes / per / 1e6,
+            "aggregate_h2d_gbs": cx.world * h2d_bytes / per / 1e6, "what": "concurrent pinned cudaMemcpyAsync H2D %d B + D2H %d B per rank and step, "
+            "all %d ranks at once, no kernel" % (h2d_bytes, d2h_bytes, cx.world)}
+
+
+def numa_report(local_rank):
+    """Where this rank's GPU hangs in the host topology, and the binding taken (none when the box exposes no NUMA topology)."""
+    rep = {"bound_node": None}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, getattr(p, "pci_device_id", 0))
+        rep["pci"] = bdf
+        path = "/sys/bus/pci/devices/%s/numa_node" % bdf
+        node = int(open(path).read().strip()) if os.path.exists(path) else None
+        rep["numa_node"] = node
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")] if os.path.isdir("/sys/devices/system/node") else []
+        rep["host_numa_nodes"] = len(nodes)
+        if node is not None and node >= 0 and len(nodes) > 1:
+            cpus = set()
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            allowed = cpus & os.sched_getaffinity(0)
+            if allowed:
+                os.sched_setaffinity(0, allowed)                      # before any pinned allocation: first touch lands on this node
+                rep["bound_node"] = node
+        elif node is None or node < 0:
+            rep["note"] = "the box exposes no NUMA topology for the GPU (numa_node = %s, %d host node(s)): nothing to bind to" % (node, len(nodes))
+    except Exception as e:
+        rep["error"] = str(e)
+    return rep
+
+
+# ------------------------------------------------------------------------------------------------ cfg 2 / cfg 5: count
+class FusedExchange:
+    """N > 1: the count kernel stores its hit counts straight into every rank's gathered buffer (CUDA IPC peer memory over
+    NVLink/NVSwitch); NCCL is left with one 4-byte all-reduce per step as the cross-rank "all stores landed" barrier.  Three buffer
+    sets rotate: kernel s (set s mod 3) is launched behind the barrier of step s-2, whose completion proves that every rank had
+    enqueued — ahead of its kernel s-2 — the consumers of step s-3, the last user of that set."""
+
+    def __init__(self, cx, m):
+        fx, torch, dist = cx.fx, cx.torch, cx.dist
+        self.cx, self.m = cx, m
+        self.gath = [fx.SharedDeviceBuffer(m * cx.world) for _ in range(3)]
+        mine = [gb.export_handle() for gb in self.gath]
+        everyone = [None] * cx.world
+        dist.all_gather_object(everyone, mine)
+        self.sinks = [[self.gath[b].ptr if r == cx.rank else self.gath[b].import_peer(r, everyone[r][b]) for r in range(cx.world)] for b in range(3)]
+        self.flag = torch.zeros(1, dtype=torch.int32, device=cx.dev)
+        self.ev_k = [torch.cuda.Event() for _ in range(3)]
+        self.ev_c = [torch.cuda.Event() for _ in range(3)]
+        self.comm = torch.cuda.Stream(device=cx.dev)
+        self.s = 0
+
+    def step(self, g, d_pat, ln, d_sp, d_ep):
+        torch, dist = self.cx.torch, self.cx.dist
+        cur = torch.cuda.current_stream()
+        b = self.s % 3
+        if self.s >= 2:
+            cur.wait_event(self.ev_c[(self.s - 2) % 3])
+        g.count_fixed_dev_gather(d_pat.data_ptr(), ln, self.m, d_sp.data_ptr(), d_ep.data_ptr(), self.sinks[b], self.cx.rank * self.m, cur.cuda_stream)
+        self.ev_k[b].record(cur)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.ev_k[b])
+            dist.all_reduce(self.flag)                   # after this, every rank's stores of this step have landed everywhere
+            self.ev_c[b].record(self.comm)
+        self.s += 1
+
+    def drain(self):
+        self.cx.torch.cuda.current_stream().wait_stream(self.comm)
+
+    def check(self, local_counts):
+        """every rank holds every rank's counts of the last step, and all ranks agree"""
+        torch, dist, cx = self.cx.torch, self.cx.dist, self.cx
+        torch.cuda.synchronize()
         dist.barrier()
+        got = torch.from_numpy(self.gath[(self.s - 1) % 3].to_host().astype(np.int64)).to(cx.dev)
+        assert torch.equal(got[cx.rank * self.m:(cx.rank + 1) * self.m], local_counts.to(torch.int64) & 0xFFFFFFFF), "gathered counts differ from the local ones"
+        cs = (got * torch.arange(1, got.numel() + 1, device=cx.dev) % 1000003).sum().reshape(1)
+        lo_, hi_ = cs.clone(), cs.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        assert int(lo_) == int(hi_), "ranks disagree on the gathered counts"
+
+    def close(self):
+        cx = self.cx
+        cx.torch.cuda.synchronize()
+        cx.dist.barrier()
+        for gb in self.gath:
+            for ptr in list(gb.peers.values()):
+                cx.fx.lib().fmx_ipc_close(ptr)
+            gb.peers = {}
+        cx.dist.barrier()
+        for gb in self.gath:
+            gb.close()
+
+
+def count_workload(cx, workload, n, m, ln, extras):
+    """cfg 2 (default line) and cfg 5: device-resident count throughput, e2e through the host API, roofline, cpu baseline"""
+    args, fx, torch = cx.args, cx.fx, cx.torch
+    world, rank = cx.world, cx.rank
+    text, base = cx.ensure_index(workload, n)
     t0 = time.time()
-    text = make_text(n, args.workload)
-    base = index_base(n, args.workload)
-    if rank == 0 and not (os.path.exists(base + ".bwt") and os.path.exists(base + ".aux")):
-        tb = time.time()
-        fx.build_index_files(text, base, bigEndian=True)
-        log("index files built on the GPU in %.1f s" % (time.time() - tb))
-    if world > 1:
-        dist.barrier()
     layout = {"auto": fx.LAYOUT_AUTO, "wm": fx.LAYOUT_WM, "planes": fx.LAYOUT_PLANES}[args.layout]
     accel = {"auto": fx.ACCEL_AUTO, "none": fx.ACCEL_NONE, "kmer": fx.ACCEL_KMER, "text": fx.ACCEL_TEXT, "both": fx.ACCEL_KMER | fx.ACCEL_TEXT,
              "ctx": fx.ACCEL_KMER | fx.ACCEL_CTX}[args.accel]
-    g = fx.GpuFMSearcher(base + ".bwt", bigEndian=True, device=local_rank, layout=layout, lanes_per_query=args.lanes, accel=accel)
+    g = fx.GpuFMSearcher(base + ".bwt", bigEndian=True, device=cx.local, layout=layout, lanes_per_query=args.lanes, accel=accel,
+                         max_total_bytes=args.max_total_bytes)
     if args.chunk:
         g.set_chunk(args.chunk)
     info = g.info()
-    log("rank %d: index open (%s, %.2f GB on device) after %.1f s" % (rank, info["layout"], info["index_bytes"] / 1e9, time.time() - t0))
+    open_s = time.time() - t0
+    log("rank %d: %s index open (%s, %.2f GB on device) after %.1f s" % (rank, workload, info["layout"], info["index_bytes"] / 1e9, open_s))
 
+    seed = 8 if workload == "cfg5" else 3
     h_pat = fx.PinnedArray((m, ln), np.uint8)
-    h_sp = fx.PinnedArray((m,), np.int64)
-    h_ep = fx.PinnedArray((m,), np.int64)
-    pats, is_hit, offs = make_queries(text, m, ln, 3, rank, out=h_pat.array, workload=args.workload)
-    d_pat = torch.from_numpy(pats).to(dev)
-    d_sp = torch.zeros(m, dtype=torch.int32, device=dev)
-    d_ep = torch.zeros(m, dtype=torch.int32, device=dev)
-    d_cnt = torch.zeros(m, dtype=torch.int32, device=dev)
-    d_all = torch.zeros(m * world, dtype=torch.int32, device=dev) if world > 1 else None
+    pats, is_hit = make_queries(text, m, ln, seed, rank, out=h_pat.array, workload=workload)
+    d_pat = torch.from_numpy(pats).to(cx.dev)
+    d_sp = torch.zeros(m, dtype=torch.int32, device=cx.dev)
+    d_ep = torch.zeros(m, dtype=torch.int32, device=cx.dev)
     stream = torch.cuda.current_stream().cuda_stream
-
-    # N > 1: the batch is cut into chunks; the NCCL all-gather of chunk c's hit counts (the one exchange step of the path) runs on a
-    # side stream while the count kernel works on chunk c+1, so only the last chunk's gather is exposed.
-    nch = max(1, args.gather_chunks) if world > 1 else 1
-    csz = (m + nch - 1) // nch
-    bounds = [(c * csz, min(m, (c + 1) * csz)) for c in range(nch)]
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
-    # two result sets, alternated per step, so that step k+1's kernel never waits for step k's gather to finish reading
-    sets = [dict(sp=d_sp, ep=d_ep, cnt=d_cnt)]
-    if world > 1:
-        sets.append(dict(sp=torch.zeros_like(d_sp), ep=torch.zeros_like(d_ep), cnt=torch.zeros_like(d_cnt)))
-        for st_ in sets:
-            st_["all"] = [torch.zeros((hi - lo) * world, dtype=torch.int32, device=dev) for lo, hi in bounds]
-            st_["ev_k"] = [torch.cuda.Event() for _ in range(nch)]
-            st_["ev_c"] = [torch.cuda.Event() for _ in range(nch)]
-    counter = [0]
-
-    p2p = world > 1 and args.exchange == "p2p"
-    if p2p:
-        # fused compute + exchange: every rank maps every rank's gathered buffer (CUDA IPC over NVLink/NVSwitch peer memory) and the
-        # count kernel stores its hit counts straight into all of them; NCCL is left with one 4-byte all-reduce per step as the
-        # cross-rank completion barrier.  Two buffer sets alternate so step k+1 never writes what step k's consumers read.
-        gath = [fx.SharedDeviceBuffer(m * world) for _ in range(2)]
-        mine = [gb.export_handle() for gb in gath]
-        everyone = [None] * world
-        dist.all_gather_object(everyone, mine)
-        sinks = [[gath[b].ptr if r == rank else gath[b].import_peer(r, everyone[r][b]) for r in range(world)] for b in range(2)]
-        flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        pev_k = [torch.cuda.Event() for _ in range(2)]
-        pev_c = [torch.cuda.Event() for _ in range(2)]
+    fused = FusedExchange(cx, m) if (world > 1 and args.exchange == "p2p") else None
+    nccl_all = torch.zeros(m * world, dtype=torch.int32, device=cx.dev) if (world > 1 and fused is None) else None
+    nccl_cnt = torch.zeros(m, dtype=torch.int32, device=cx.dev) if nccl_all is not None else None
 
     def step():
-        if world == 1:
-            g.count_fixed_dev(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), stream)
-            return
-        cur = torch.cuda.current_stream()
-        if p2p:
-            b = counter[0] & 1
-            counter[0] += 1
-            cur.wait_event(pev_c[b])                    # the barrier of the step that last wrote this buffer set has passed
-            g.count_fixed_dev_gather(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), sinks[b], rank * m, cur.cuda_stream)
-            pev_k[b].record(cur)
-            with torch.cuda.stream(comm):
-                comm.wait_event(pev_k[b])
-                dist.all_reduce(flag)                   # after this, every rank's stores of this step have landed everywhere
-                pev_c[b].record(comm)
-            return
-        b = sets[counter[0] & 1]
-        counter[0] += 1
-        for c, (lo, hi) in enumerate(bounds):
-            cur.wait_event(b["ev_c"][c])                # the gather that last used this result set has read it (two steps ago)
-            g.count_fixed_dev(d_pat.data_ptr() + lo * ln, ln, hi - lo, b["sp"].data_ptr() + lo * 4, b["ep"].data_ptr() + lo * 4, stream)
-            b["ev_k"][c].record(cur)
-            if args.diag == "nocomm":
-                continue
-            with torch.cuda.stream(comm):
-                comm.wait_event(b["ev_k"][c])
-                if args.diag != "nosub":
-                    torch.sub(b["ep"][lo:hi], b["sp"][lo:hi], out=b["cnt"][lo:hi])
-                if args.diag != "nogather":
-                    dist.all_gather_into_tensor(b["all"][c], b["cnt"][lo:hi])
-                b["ev_c"][c].record(comm)
-
-    def drain():
-        if world > 1:
-            torch.cuda.current_stream().wait_stream(comm)
-
-    # ---- sanity at full size (parity proper lives in tests/): hits are found, a few are verified by brute force
-    step()
-    drain()
-    torch.cuda.synchronize()
-    if world > 1:                                       # every rank holds every rank's counts after the exchange
-        local = (d_ep - d_sp)
-        if p2p:
-            dist.barrier()
-            got = torch.from_numpy(gath[0].to_host().astype(np.int64)).to(dev)
-            assert torch.equal(got[rank * m:(rank + 1) * m], local.to(torch.int64) & 0xFFFFFFFF), "gathered counts differ from the local ones"
-            cs = (got * torch.arange(1, got.numel() + 1, device=dev) % 1000003).sum().reshape(1)
-            lo_, hi_ = cs.clone(), cs.clone()
-            dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
-            dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
-            assert int(lo_) == int(hi_), "ranks disagree on the gathered counts"
+        if fused is not None:
+            fused.step(g, d_pat, ln, d_sp, d_ep)
         else:
-            lo, hi = bounds[0]
-            mine_ = sets[0]["all"][0].view(world, hi - lo)[rank]
-            assert args.diag != "none" or torch.equal(mine_, local[lo:hi]), "all-gathered counts differ from the local ones"
+            g.count_fixed_dev(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), stream)
+            if nccl_all is not None:
+                torch.sub(d_ep, d_sp, out=nccl_cnt)
+                cx.dist.all_gather_into_tensor(nccl_all, nccl_cnt)
+
+    drain = fused.drain if fused is not None else None
+    # ---- sanity at full size (parity proper lives in tests/ and in the cpu_baseline leg): hits are found, a few are verified by brute force
+    step()
+    if drain:
+        drain()
+    torch.cuda.synchronize()
+    if fused is not None:
+        fused.check(d_ep - d_sp)
     sp = d_sp.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
     ep = d_ep.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
     cnt = ep - sp
     assert (cnt[is_hit] >= 1).all(), "a text substring was not found"
-    if rank == 0:
-        tb = text.tobytes() if n <= 1_500_000_000 else text[:1_000_000_000].tobytes()
-        for q in (np.flatnonzero(is_hit)[:2] if n <= 1_500_000_000 else []):
-            needle = pats[q][::-1].tobytes()
-            assert tb.count(needle) == cnt[q], "count mismatch vs brute force"
+    if rank == 0 and n <= 1_500_000_000:
+        tb = text.tobytes()
+        for q in np.flatnonzero(is_hit)[:2]:
+            assert tb.count(pats[q][::-1].tobytes()) == cnt[q], "count mismatch vs brute force"
         del tb
     checksum = int((sp * 1315423911 + ep * 2654435761).sum() & 0xFFFFFFFFFFFF)
 
     # ---- roofline inputs, outside the timed region
-    blocks, steps_exec = g.count_fixed_stats(pats)
-    alg_bytes = blocks * 64
-    r_rand, _ = g.gather_bench(64, 4, 1 << 25, 16, 3)
+    requests, steps_exec = g.count_fixed_stats(pats)
+    r_rand_gbs, _ = g.gather_bench(64, 2, 1 << 25, 16, 3)            # K4: random 64-B requests (two lanes x one 256-bit load) over this index
+    r_rand_req = r_rand_gbs * 1e9 / 64
 
-    def timed_region(fn, label):
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        for _ in range(args.warmup):
-            fn()
-        drain()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sampler.mark_begin()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_wall = time.time()
-        e0.record()
-        for _ in range(args.steps):
-            fn()
-        drain()
-        e1.record()
-        torch.cuda.synchronize()
-        wall = time.time() - t_wall
-        sampler.mark_end()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        clocks = sampler.stop()
-        ms = e0.elapsed_time(e1)
-        if label == "e2e":
-            ms = wall * 1e3                              # host API: the call returns when results are in host memory
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), clocks
-
-    ms_total, clocks = timed_region(step, "device")
-    # kernel-only time (same launches, no exchange) for the roofline
+    ms_total, clocks = cx.timed(step, args.steps, args.warmup, drain=drain)
+    cx.launches += args.steps + args.warmup + 1
+    # kernel-only time of the same launches (no exchange), per-launch events, for the roofline
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in kev:
         a.record()
         g.count_fixed_dev(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), stream)
         b.record()
     torch.cuda.synchronize()
+    cx.launches += args.steps
     k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
 
-    # end to end through the host API: (sp, ep) per query at the reference's own width (Option[(Int, Int)], findex.scala:15-31) ...
+    sustained = None
+    if "sustained" in extras:
+        # >= 2 s of back-to-back launches: what the clocks and the power cap do to the number over time
+        est = max(ms_total / args.steps, 1e-3)
+        nlaunch = int(min(20000, max(200, 2200.0 / est)))
+        ms_s, clocks_s = cx.timed(step, nlaunch, 3, drain=drain)
+        cx.launches += nlaunch + 3
+        sustained = {"launches": nlaunch, "seconds": ms_s / 1e3, "ms_per_step": ms_s / nlaunch, "value": world * m * nlaunch / (ms_s * 1e-3), "unit": UNIT,
+                     "ratio_to_value": (ms_total / args.steps) / (ms_s / nlaunch), "clocks": clocks_s}
+
+    # ---- end to end through the host API: (sp, ep) per query at the reference's own width (Option[(Int, Int)], findex.scala:15-31)
     narrow = g.n < 2 ** 31                                  # cfg 5 (n = 4e9) does not fit Int rows: int64 there
-    h_sp32 = fx.PinnedArray((m,), np.int32 if narrow else np.int64)
-    h_ep32 = fx.PinnedArray((m,), np.int32 if narrow else np.int64)
+    rdt = np.int32 if narrow else np.int64
+    h_sp, h_ep = fx.PinnedArray((m,), rdt), fx.PinnedArray((m,), rdt)
+    e2e_steps = max(3, min(args.steps, 20))
 
     def e2e_step():
-        g.count_fixed_into(h_pat.array, h_sp32.array, h_ep32.array)
-
-    ms_e2e, clocks_e2e = timed_region(e2e_step, "e2e")
-    assert np.array_equal(h_sp32.array, np.where(cnt > 0, sp, 0)) and np.array_equal(h_ep32.array, np.where(cnt > 0, ep, 0)), "host API result differs from device API"
-
-    # ... and with int64 rows (twice the result bytes over PCIe)
-    def e2e64_step():
         g.count_fixed_into(h_pat.array, h_sp.array, h_ep.array)
-
-    ms_e2e64, _ = timed_region(e2e64_step, "e2e")
-    assert np.array_equal(h_sp.array, np.where(cnt > 0, sp, 0)) and np.array_equal(h_ep.array, np.where(cnt > 0, ep, 0)), "host API (int64) result differs from device API"
-
-    # the same batch through the count-only call (uint32 ep-sp per query: 4 instead of 16 result bytes over PCIe)
+    ms_e2e, clocks_e2e = cx.timed(e2e_step, e2e_steps, 3, wall=True)
+    nchunks = (m + (args.chunk or (1 << 20)) - 1) // (args.chunk or (1 << 20))
+    cx.launches += (e2e_steps + 3) * nchunks
+    assert np.array_equal(h_sp.array, np.where(cnt > 0, sp, 0)) and np.array_equal(h_ep.array, np.where(cnt > 0, ep, 0)), "host API result differs from device API"
+    e2e = {"value": world * m * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": m * ln, "d2h_bytes_per_step": m * 2 * np.dtype(rdt).itemsize,
+           "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "clocks": clocks_e2e,
+           "api": "fmx_count_fixed_i32 (host pinned buffers in/out, (sp, ep) as the reference's 32-bit Int rows)" if narrow else "fmx_count_fixed (host pinned buffers in/out, int64 sp/ep)"}
+    # the same batch through the count-only call (uint32 ep-sp per query: 4 instead of 8/16 result bytes over PCIe)
     h_cnt = fx.PinnedArray((m,), np.uint32)
 
     def e2e_count_only_step():
         g.count_only_fixed(h_pat.array, out=h_cnt.array)
-
-    ms_e2e_co, _ = timed_region(e2e_count_only_step, "e2e")
+    ms_co, _ = cx.timed(e2e_count_only_step, e2e_steps, 2, wall=True, sample_clocks=False)
+    cx.launches += (e2e_steps + 2) * nchunks
     assert np.array_equal(h_cnt.array.astype(np.int64), np.where(cnt > 0, cnt, 0)), "count-only API differs from ep-sp"
+    e2e["count_only"] = {"value": world * m * e2e_steps / (ms_co * 1e-3), "unit": UNIT, "ms_per_step": ms_co / e2e_steps, "h2d_bytes_per_step": m * ln,
+                         "d2h_bytes_per_step": m * 4, "api": "fmx_count_only_fixed (uint32 ep-sp)"}
+    if info["sigma"] <= 4:
+        # <= 4-symbol alphabets: the patterns cross PCIe as 2-bit codes (a quarter of the bytes) and are expanded on the device; rows come
+        # back as uint32 (n < 2^32).  This is the call a DNA host makes, so it is the headline form of e2e where it applies.
+        codes = g.pack2(pats)
+        h_pk = fx.PinnedArray(codes.shape, np.uint8)
+        h_pk.array[:] = codes
+        h_sp4, h_ep4 = fx.PinnedArray((m,), np.uint32), fx.PinnedArray((m,), np.uint32)
 
-    regex = None if args.regexes <= 0 else regex_leg(args, g, text, world, rank, dev)
+        def e2e_packed_step():
+            g.count_packed2_into(h_pk.array, ln, h_sp4.array, h_ep4.array)
+        ms_pk, _ = cx.timed(e2e_packed_step, e2e_steps, 2, wall=True, sample_clocks=False)
+        cx.launches += (e2e_steps + 2) * nchunks * 2
+        assert np.array_equal(h_sp4.array.astype(np.int64), np.where(cnt > 0, sp, 0)) and np.array_equal(h_ep4.array.astype(np.int64), np.where(cnt > 0, ep, 0)), "packed host API result differs"
+        unpacked = {k: e2e[k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "api")}
+        e2e.update({"value": world * m * e2e_steps / (ms_pk * 1e-3), "ms_per_step": ms_pk / e2e_steps, "h2d_bytes_per_step": int(codes.size), "d2h_bytes_per_step": m * 8,
+                    "api": "fmx_count_fixed_packed2 (2-bit symbol codes in, expanded on the device; uint32 (sp, ep) out)", "unpacked_bytes": unpacked})
+    if "pcie" in extras:
+        pc = pcie_ceiling(cx, e2e["h2d_bytes_per_step"], e2e["d2h_bytes_per_step"])
+        e2e["pcie_ceiling"] = pc
+        e2e["frac_of_pcie_ceiling"] = pc["ms_per_step"] / e2e["ms_per_step"]
 
     value = world * m * args.steps / (ms_total * 1e-3)
-    e2e = world * m * args.steps / (ms_e2e * 1e-3)
     peak, peak_src = measured_peaks()
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")          # dram bytes per launch from the committed ncu --set full capture
+    # DRAM bytes one launch has to move at the 64-byte granule of a hinted random request: every request (table entry, row context, rank
+    # block) is one granule, plus the streamed patterns and results
+    granule_bytes = requests * 64 + m * (ln + 8)
+    achieved = granule_bytes / (k_ms * 1e-3) / 1e9
+    L = max(1, int(np.ceil(np.log2(max(info["sigma"], 2)))))
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(m, info),
+            "peak_source": peak_src, "kernel": "count_fixed_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": granule_bytes,
+            "requests_per_query": requests / m, "steps_skipped_per_query": steps_exec / m - (requests / m),
+            "request_rate": {"achieved_requests_per_s": requests / (k_ms * 1e-3), "r_rand_requests_per_s": r_rand_req,
+                             "frac": requests / (k_ms * 1e-3) / r_rand_req, "r_rand_gbs": r_rand_gbs,
+                             "note": "r_rand = live K4: dependent random 64-B requests over this index's rank blocks; what bounds a gather kernel on B200 is requests/s, not bytes"},
+            "bytes_needed_per_query": {"table_entry": 8 if info["kmer_k"] else 0, "row_context": info["ctx_entry_bytes"], "pattern": ln, "result": 8},
+            "survey_units": {"levels_L": L, "nominal_bytes_per_query": float(steps_exec / m * 2 * L * 64),
+                             "note": "SURVEY 8(d): executed steps x 2 x L x 64 B of a wavelet-matrix search; this kernel answers the same queries bit-exactly "
+                                     "from a k-mer table entry + row-context hops instead (steps skipped, not executed), so its bytes are the granules above"},
+            "note": "achieved = (requests x 64-B granule + streamed pattern/result bytes) per launch / mean CUDA-event kernel time; frac vs the stream peak"}
+    out = {"metric": METRICS[workload], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+           "config": workload_config(args, workload, n, m, ln),
+           "impl_config": {"exchange": "none" if world == 1 else ("count kernel stores into peer gathered buffers + 4-byte NCCL barrier" if fused else "NCCL all_gather_into_tensor"),
+                           "layout": info["layout"], "lanes_per_query": info["lanes_per_query"], "index_bytes": info["index_bytes"],
+                           "index_bytes_per_text_byte": info["index_bytes"] / n, "kmer_k": info["kmer_k"], "ctx_depth": info["ctx_depth"],
+                           "ctx_entry_bytes": info["ctx_entry_bytes"], "text_shortcut": info["text_shortcut"], "sigma": info["sigma"], "open_s": open_s, "checksum": checksum},
+           "clocks": clocks, "e2e": e2e, "roofline": roof}
+    if sustained:
+        out["sustained"] = sustained
+    state = {"g": g, "text": text, "base": base, "pats": pats, "sp": sp, "ep": ep, "cnt": cnt, "info": info, "fused": fused}
+    return out, state
+
+
+def ncu_traffic(m, info):
+    """dram bytes per launch of the matching configuration from the committed ncu --set full capture (profiles/ncu_traffic.json)"""
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         try:
-            rec = json.load(open(tp)).get("count_fixed_kernel", {})
-            if (rec.get("queries") == m and rec.get("layout") == info["layout"] and rec.get("lanes") == info["lanes_per_query"]
-                    and rec.get("kmer_k") == info["kmer_k"] and rec.get("text_shortcut") == info["text_shortcut"]
-                    and rec.get("ctx_depth", 0) == info["ctx_depth"]):
-                traffic = rec.get("dram_bytes_per_launch")
+            for rec in json.load(open(tp)).get("count_fixed_kernel_captures", []):
+                if (rec.get("queries") == m and rec.get("layout") == info["layout"] and rec.get("lanes") == info["lanes_per_query"]
+                        and rec.get("kmer_k") == info["kmer_k"] and rec.get("ctx_depth", 0) == info["ctx_depth"] and rec.get("sigma") == info["sigma"]):
+                    return rec.get("dram_bytes_per_launch")
         except Exception:
             pass
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-           "data": "synthetic", "config": dict(workload_config(args), exchange=("none" if world == 1 else ("fused peer stores + 4-byte NCCL barrier" if p2p else "NCCL all_gather_into_tensor on a side stream")), layout=info["layout"], lanes_per_query=info["lanes_per_query"],
-                                               index_bytes=info["index_bytes"], kmer_k=info["kmer_k"], text_shortcut=info["text_shortcut"], ctx_depth=info["ctx_depth"], checksum=checksum),
-           "clocks": clocks,
-           "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": m * ln, "d2h_bytes_per_step": m * (8 if narrow else 16), "ms_per_step": ms_e2e / args.steps,
-                   "api": "fmx_count_fixed_i32 (host pinned buffers in/out, (sp, ep) as the reference's 32-bit Int rows)" if narrow else "fmx_count_fixed (host pinned buffers in/out, int64 sp/ep)",
-                   "clocks": clocks_e2e,
-                   "int64_rows": {"value": world * m * args.steps / (ms_e2e64 * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e64 / args.steps,
-                                  "h2d_bytes_per_step": m * ln, "d2h_bytes_per_step": m * 16, "api": "fmx_count_fixed (int64 sp/ep)"},
-                   "count_only": {"value": world * m * args.steps / (ms_e2e_co * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_co / args.steps,
-                                  "h2d_bytes_per_step": m * ln, "d2h_bytes_per_step": m * 4, "api": "fmx_count_only_fixed (uint32 ep-sp)"}},
-           "gpu_launches": args.steps * (1 if (world == 1 or p2p) else nch),
-           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                        "peak_source": peak_src, "kernel": "count_fixed_kernel", "kernel_ms": k_ms,
-                        "algorithmic_bytes_per_launch": alg_bytes, "distinct_blocks_per_query": blocks / m, "executed_steps_per_query": steps_exec / m,
-                        "r_rand_gbs": r_rand, "frac_of_r_rand": achieved / r_rand,
-                        "note": "achieved = distinct 64-B rank blocks the batch touches x 64 B / kernel time; r_rand = live K4 random 64-B gather "
-                                "bandwidth over the same index (the random-sector HBM roofline of north_star)"}}
-    if regex is not None:
-        out["regex"] = regex["report"]
-    if world == 1 and rank == 0 and not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(args, base, pats, sp, ep, cnt, regex)
-    if rank == 0:
-        print(json.dumps(out), file=OUT, flush=True)
-    if p2p:
-        torch.cuda.synchronize()
-        dist.barrier()
-        for gb in gath:
-            for ptr in list(gb.peers.values()):
-                fx.lib().fmx_ipc_close(ptr)
-            gb.peers = {}
-        dist.barrier()
-        for gb in gath:
-            gb.close()
-    g.close()
+    return None
 
 
-def regex_leg(args, g, text, world, rank, dev):
-    """Second half of BASELINE.json's metric ("regex queries/s"): `--regexes` template regexes (cfg 4: classes, alternation,
-    desugared bounded repeats, \\d, '.') per GPU over the same index, searched through fmx_regex_search_batch with host
-    buffers.  Compilation (host, once) is outside the timed region; the search call is timed end to end (wall clock, max over ranks)."""
+def cpu_count_baseline(orc, pats, sp, ep, cnt, unit=UNIT):
+    """The oracle (C restatement of the reference algorithm) on the box's host cores, on a bounded sample of the same batch; doubles as
+    the full-size parity check of that sample."""
+    cores = os.cpu_count() or 1
+    ln = pats.shape[1]
+    rate = _probe(lambda k: orc.count_batch(pats[:k].reshape(-1), np.arange(0, k * ln + 1, ln, dtype=np.int64), threads=cores), 20000)
+    sample = int(min(len(pats), max(20000, rate * 12.0)))
+    off = np.arange(0, sample * ln + 1, ln, dtype=np.int64)
+    t1 = time.time()
+    osp, oep = orc.count_batch(pats[:sample].reshape(-1), off, threads=cores)
+    dt = time.time() - t1
+    parity = bool(np.array_equal(osp, np.where(cnt[:sample] > 0, sp[:sample], 0)) and np.array_equal(oep, np.where(cnt[:sample] > 0, ep[:sample], 0)))
+    assert parity, "GPU (sp,ep) differ from the oracle on the CPU-baseline sample"
+    one = int(min(sample, max(2000, rate / max(cores, 1) * 2.0)))     # single-thread figure (SURVEY §8d), about two seconds
+    t1 = time.time()
+    orc.count_batch(pats[:one].reshape(-1), off[:one + 1], threads=1)
+    dt1 = time.time() - t1
+    return {"value": sample / dt, "unit": unit, "cores": cores, "kind": "port",
+            "sample": "first %d of the %d-query batch, %d threads, %.1f s" % (sample, len(pats), cores, dt), "parity_on_sample": parity,
+            "note": "JVM unavailable - C restatement of the reference algorithm (binary search in .fm)",
+            "single_thread": {"value": one / max(dt1, 1e-9), "unit": unit, "cores": 1, "sample": "first %d queries, %.1f s" % (one, dt1)}}
+
+
+def load_oracle(base, what):
+    from oracle import fm_oracle as fo
+    t0 = time.time()
+    fo.build(native=True)
+    orc = fo.OracleIndex.load(base)
+    log("%s: oracle index ready in %.1f s" % (what, time.time() - t0))
+    return orc
+
+
+# ------------------------------------------------------------------------------------------------ cfg 3 / cfg 4 on the English-like index
+def english_open(cx, n):
+    fx = cx.fx
+    text, base = cx.ensure_index("cfg3", n)
+    t0 = time.time()
+    g = fx.GpuFMSearcher(base + ".bwt", bigEndian=True, device=cx.local, sa_sample_rate=32, max_total_bytes=cx.args.max_total_bytes)
+    info = g.info()
+    log("rank %d: cfg3 index open (%s, %.2f GB on device, k = %d, context depth %d) after %.1f s" % (cx.rank, info["layout"], info["index_bytes"] / 1e9,
+                                                                                             info["kmer_k"], info["ctx_depth"], time.time() - t0))
+    return text, base, g, dict(info, open_s=time.time() - t0)
+
+
+def locate_leg(cx, g, text, n, m_total, ln, orc, steps, full_e2e):
+    """cfg 3: m_total len-`ln` text substrings (seed 5) in all, sharded over the ranks (strong scaling); count -> locate every occurrence
+    (sampled SA, rate 32) -> positions ascending per query.  Device-resident: counts, scanned offsets and positions stay in HBM and are
+    exchanged by kernel stores into every rank's gathered buffers (sharded.GpuExchange)."""
+    from findex_b200 import sharded
+    torch, fx, world, rank = cx.torch, cx.fx, cx.world, cx.rank
+    pats_all, _ = make_queries(text, m_total, ln, 5, 0, workload="cfg3")
+    lo, hi = sharded.shard_bounds(m_total, rank, world)
+    pats = np.ascontiguousarray(pats_all[lo:hi])
+    m = hi - lo
+    d_pat = torch.from_numpy(pats).to(cx.dev)
+    d_sp = torch.zeros(m, dtype=torch.int32, device=cx.dev)
+    d_ep = torch.zeros(m, dtype=torch.int32, device=cx.dev)
+    d_off = torch.zeros(m + 1, dtype=torch.int64, device=cx.dev)
+    st = torch.cuda.current_stream().cuda_stream
+    g.count_fixed_dev(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), st)
+    torch.cuda.synchronize()
+    sp = d_sp.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    ep = d_ep.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    occ = ep - sp
+    assert (occ >= 1).all(), "a text substring was not found"
+    total_local = int(occ.sum())
+    total_all = int(cx.sum_over_ranks(total_local))
+    d_pos = torch.zeros(total_local + 16, dtype=torch.int32, device=cx.dev)
+    ex = sharded.GpuExchange(g, rank, world, m_total, total_all + 16, cx.dev) if world > 1 else None
+
+    def step():
+        if ex is not None:
+            ex.locate(d_pat, ln, lo, hi, total_local + 16)
+        else:
+            g.count_fixed_dev(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), st)
+            g.locate_dev(d_sp.data_ptr(), d_ep.data_ptr(), m, d_off.data_ptr(), d_pos.data_ptr(), total_local + 16, st)
+    g.set_stats(True)
+    step()
+    torch.cuda.synchronize()
+    lf_steps = g.last_steps()
+    g.set_stats(False)
+    ms, clocks = cx.timed(step, steps, 2)
+    walk_ms, sort_ms = g.last_locate_ms()
+    launches = int(g.last_kernel_launches())
+    cx.launches += (steps + 3) * (launches * 4 + 1)
+    # ---- parity: count vs the oracle on a sample; positions: complete (count matches), ascending, and every one a real occurrence of the
+    # pattern in the text — which makes them exactly sorted { sa[r] : r in [sp, ep) } (util.scala:213-224)
+    if ex is not None:
+        off_all = ex.offsets().cpu().numpy()
+        pos_view = ex.gathered_values(int(off_all[-1]))
+        off_local = off_all[lo:hi + 1] - off_all[lo]
+        pos_local = pos_view[int(off_all[lo]):int(off_all[hi])]
+    else:
+        off_local = d_off.cpu().numpy()
+        pos_local = d_pos[:total_local]
+    assert off_local[-1] == total_local and np.array_equal(np.diff(off_local), occ)
+    rng = np.random.default_rng(99)
+    bad = 0
+    chk = rng.choice(m, min(3000, m), replace=False)
+    n1 = g.n
+    for j in chk:
+        q = pos_local[int(off_local[j]):int(off_local[j]) + min(int(occ[j]), 4096)].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+        if len(q) > 1 and not (np.diff(q) > 0).all():
+            bad += 1
+            continue
+        qq = q[:: max(1, len(q) // 64)]
+        fo_ = (n1 - 1) - qq - ln                                      # file offset = (n-1) - pos - len
+        if not (text[fo_[:, None] + np.arange(ln)[None, :]] == pats[j][::-1][None, :]).all():
+            bad += 1
+    assert bad == 0, "located positions are not the pattern's occurrences"
+    parity = {"positions_verified_queries": int(len(chk)), "mismatches": bad}
+    if orc is not None:
+        parity["count_parity_on_sample"], parity["count_parity_sample"] = oracle_parity(orc, pats, sp, ep, 100_000)
+        assert parity["count_parity_on_sample"]
+    # ---- e2e: host (sp, ep) in, host int64 positions out through fmx_locate_batch (pinned buffers), on a time-bounded slice unless asked
+    k = m if full_e2e else min(m, max(1000, int(m * min(1.0, 150e6 / max(total_local, 1)))))
+    tot_k = int(occ[:k].sum())
+    h_pos = fx.PinnedArray((max(tot_k, 1),), np.int64)
+    h_off = np.zeros(k + 1, np.int64)
+    sp_k, ep_k = np.ascontiguousarray(sp[:k]), np.ascontiguousarray(ep[:k])
+
+    def e2e_step():
+        rc = fx.lib().fmx_locate_batch(g.h, sp_k.ctypes.data, ep_k.ctypes.data, k, tot_k, h_off.ctypes.data, h_pos.array.ctypes.data)
+        assert rc == 0, fx.lib().fmx_last_error()
+    ms_e2e, _ = cx.timed(e2e_step, max(2, min(steps, 5)), 1, wall=True, sample_clocks=False)
+    e2e_steps = max(2, min(steps, 5))
+    if ex is None:
+        assert np.array_equal(h_pos.array[:tot_k], pos_local[:tot_k].cpu().numpy().astype(np.int64) & 0xFFFFFFFF), "host locate differs from device locate"
+    h_pos.free()
+    per = ms / steps
+    # one LF step of the sampled walk = one walk block (BWT byte + mark bit) + one rank block; plus the mark-rank block and the sample
+    req_occ = 2.0 * lf_steps / max(total_local, 1) + 2.0
+    r_rand_gbs, _ = g.gather_bench(64, 2, 1 << 25, 16, 3)
+    peak, peak_src = measured_peaks()
+    L = max(1, int(np.ceil(np.log2(max(g.info()["sigma"], 2)))))
+    out = {"value": m_total / (per * 1e-3), "unit": UNIT, "positions_per_s": total_all / (per * 1e-3), "ms_per_step": per, "steps": steps, "queries": m_total,
+           "occurrences": total_all, "pattern_len": ln, "sa_sample_rate": 32, "scaling": "strong", "walk_ms": walk_ms, "sort_ms": sort_ms,
+           "sort_share_of_locate": sort_ms / max(walk_ms + sort_ms, 1e-9), "clocks": clocks, "parity_on_sample": bad == 0 and parity.get("count_parity_on_sample", True),
+           "parity": parity,
+           "exchange": "none" if ex is None else "kernel stores of counts + position slabs into every rank's gathered buffer (CUDA IPC) + 2 x 4-byte NCCL barrier",
+           "e2e": {"value": cx.world * k / (ms_e2e / e2e_steps * 1e-3), "unit": UNIT, "positions_per_s": cx.world * tot_k / (ms_e2e / e2e_steps * 1e-3),
+                   "ms_per_step": ms_e2e / e2e_steps, "queries": k, "h2d_bytes_per_step": k * 16, "d2h_bytes_per_step": tot_k * 8 + (k + 1) * 8,
+                   "api": "fmx_locate_batch (host int64 intervals in, pinned int64 positions out)", "slice": "all queries" if k == m else "first %d queries of the shard (time-bounded)" % k},
+           "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": req_occ * 64 * total_local / ((walk_ms + sort_ms) * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src,
+                        "frac": req_occ * 64 * total_local / ((walk_ms + sort_ms) * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "locate_kernel (+ per-query sort)",
+                        "kernel_ms": walk_ms + sort_ms, "lf_steps_per_occurrence": lf_steps / max(total_local, 1), "requests_per_occurrence": req_occ,
+                        "request_rate": {"achieved_requests_per_s": req_occ * total_local / (walk_ms * 1e-3), "r_rand_requests_per_s": r_rand_gbs * 1e9 / 64,
+                                         "frac": req_occ * total_local / (walk_ms * 1e-3) / (r_rand_gbs * 1e9 / 64)},
+                        "survey_units": {"bytes_per_occurrence": 15.5 * L * 64 + 32, "note": "SURVEY 8(d): (rate-1)/2 LF steps x L x 64 B + one 32-B sample"}}}
+    if ex is not None:
+        ex.close()
+    return out
+
+
+def regex_leg(cx, g, text, n_regexes, orc, steps):
+    """cfg 4: `n_regexes` template regexes per GPU (classes, alternation, desugared bounded repeats, \\d, '.') over the index,
+    compiled once into a device-resident set.  value: device-resident search (traversal + ordering, results left in HBM); e2e: the host
+    call fmx_regex_set_search (results to host buffers)."""
     import ctypes as C
-    import torch
-    import torch.distributed as dist
-    from findex_b200 import fmindex as fx, synth
-    rxs = synth.regex_templates(text, np.random.default_rng([6, rank]), args.regexes)
+    torch, fx = cx.torch, cx.fx
+    rxs = cx.synth.regex_templates(text, np.random.default_rng([6, cx.rank]), n_regexes)
     t0 = time.time()
     trees, kept = [], []
     for r in rxs:
@@ -488,81 +888,244 @@ def regex_leg(args, g, text, world, rank, dev):
     compile_s = time.time() - t0
     mr = len(trees)
     t0 = time.time()
-    rset = g.regex_set(trees)                               # concatenated automata, uploaded once (compile once, search many times)
+    rset = g.regex_set(trees)
     upload_s = time.time() - t0
     cap = 1 << 22
     off = np.zeros(mr + 1, np.int64)
-    ln_, sp_, ep_ = np.zeros(cap, np.int32), np.zeros(cap, np.int64), np.zeros(cap, np.int64)
+    ln_, sp_, ep_ = fx.PinnedArray((cap,), np.int32), fx.PinnedArray((cap,), np.int64), fx.PinnedArray((cap,), np.int64)
+    d_res = torch.zeros((cap, 4), dtype=torch.int32, device=cx.dev)
+    d_off = torch.zeros(mr + 1, dtype=torch.int64, device=cx.dev)
+    totals = []
 
-    def call():
-        rc = fx.lib().fmx_regex_set_search(g.h, rset.h, cap, off.ctypes.data_as(C.c_void_p), ln_.ctypes.data_as(C.c_void_p),
-                                           sp_.ctypes.data_as(C.c_void_p), ep_.ctypes.data_as(C.c_void_p))
+    def dev_step():
+        totals.append(rset.search_dev(g, d_res.data_ptr(), cap, d_off.data_ptr()))
+
+    def host_step():
+        rc = fx.lib().fmx_regex_set_search(g.h, rset.h, cap, off.ctypes.data_as(C.c_void_p), C.c_void_p(ln_.array.ctypes.data),
+                                           C.c_void_p(sp_.array.ctypes.data), C.c_void_p(ep_.array.ctypes.data))
         assert rc == 0, fx.lib().fmx_last_error()
-    steps = max(3, min(args.steps, 20))
-    for _ in range(3):
-        call()
-    if world > 1:
-        dist.barrier()
-    t0 = time.time()
+    steps = max(3, min(steps, 20))
     kms = []
-    for _ in range(steps):
-        call()
+
+    def dev_step_timed():
+        dev_step()
         kms.append(g.last_kernel_ms())
-    wall = time.time() - t0
-    tt = torch.tensor([wall], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    wall = float(tt.item())
+    ms_dev, clocks = cx.timed(dev_step_timed, steps, 3, wall=True)
+    kms = kms[-steps:]
+    items = g.last_steps()
+    launches = int(g.last_kernel_launches())
+    max_len = int(g.last_regex_levels())
+    ms_e2e, _ = cx.timed(host_step, steps, 2, wall=True, sample_clocks=False)
+    cx.launches += (2 * steps + 5) * launches
     total = int(off[mr])
-    res = [(kept[i], sorted(zip(ln_[off[i]:off[i + 1]].tolist(), sp_[off[i]:off[i + 1]].tolist(), ep_[off[i]:off[i + 1]].tolist())))
-           for i in np.random.default_rng(9).choice(mr, min(200, mr), replace=False)]
-    return {"sample": res,
-            "report": {"value": world * mr * steps / wall, "unit": "regexes/s", "what": "fmx_regex_set_search end to end (device-resident regex set, host result buffers), "
-                       "Glushkov engine, caps off; device time alone in device_value", "device_value": world * mr / (float(np.mean(kms)) * 1e-3), "regexes_per_gpu": mr,
-                       "rejected_by_compiler": len(rxs) - mr, "steps": steps, "ms_per_step": wall / steps * 1e3, "kernel_ms_per_step": float(np.mean(kms)),
-                       "traversal_launches_per_step": int(g.last_kernel_launches()), "levels_per_step": int(g.last_regex_levels()), "result_triples": total, "compile_s_once": compile_s, "set_upload_s_once": upload_s}}
-
-
-def cpu_baseline(args, base, pats, sp, ep, cnt, regex=None):
-    """The oracle (C restatement of the reference algorithm) on the box's host cores, on a bounded sample of the same batch;
-    doubles as the full-size parity check of that sample."""
-    from oracle import fm_oracle as fo
-    cores = os.cpu_count() or 1
-    t0 = time.time()
-    fo.build(native=True)
-    ix = fo.OracleIndex.load(base)
-    log("cpu_baseline: oracle index ready in %.1f s" % (time.time() - t0))
-    ln = args.len
-    probe = 20000
-    t1 = time.time()
-    ix.count_batch(pats[:probe].reshape(-1), np.arange(0, probe * ln + 1, ln, dtype=np.int64), threads=cores)
-    rate = probe / max(time.time() - t1, 1e-6)
-    sample = int(min(len(pats), max(probe, rate * 15.0)))
-    off = np.arange(0, sample * ln + 1, ln, dtype=np.int64)
-    t1 = time.time()
-    osp, oep = ix.count_batch(pats[:sample].reshape(-1), off, threads=cores)
-    dt = time.time() - t1
-    want_sp = np.where(cnt[:sample] > 0, sp[:sample], 0)
-    want_ep = np.where(cnt[:sample] > 0, ep[:sample], 0)
-    parity = bool(np.array_equal(osp, want_sp) and np.array_equal(oep, want_ep))
-    assert parity, "GPU (sp,ep) differ from the oracle on the CPU-baseline sample"
-    # single-thread figure (SURVEY §8d): the same algorithm on one core, about two seconds of it
-    one = int(min(sample, max(2000, rate / max(cores, 1) * 2.0)))
-    t1 = time.time()
-    ix.count_batch(pats[:one].reshape(-1), off[:one + 1], threads=1)
-    dt1 = time.time() - t1
-    extra = {"single_thread": {"value": one / max(dt1, 1e-9), "unit": UNIT, "cores": 1, "sample": "first %d queries, %.1f s" % (one, dt1)}}
-    if regex is not None:                                 # the oracle's uncapped ReTree._matchSA on a sample of the regex batch (1 thread)
+    assert total == totals[-1], "device-resident and host searches disagree on the number of results"
+    rec = d_res[:total].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    assert np.array_equal(rec[:, 1], ln_.array[:total]) and np.array_equal(rec[:, 2], sp_.array[:total]) and np.array_equal(rec[:, 3], ep_.array[:total])
+    occurrences = int((ep_.array[:total] - sp_.array[:total]).sum())
+    sample = [(kept[i], sorted(zip(ln_.array[off[i]:off[i + 1]].tolist(), sp_.array[off[i]:off[i + 1]].tolist(), ep_.array[off[i]:off[i + 1]].tolist())))
+              for i in np.random.default_rng(9).choice(mr, min(200, mr), replace=False)]
+    out = {"value": cx.world * mr / (float(np.mean(kms)) * 1e-3), "unit": "regexes/s", "ms_per_step": float(np.mean(kms)), "steps": steps,
+           "what": "fmx_regex_set_search_dev: Glushkov engine, caps off, device-resident regex set; traversal (work-queue kernel) + ordering on the device, CUDA-event time",
+           "call_value": cx.world * mr * steps / (ms_dev * 1e-3), "call_ms_per_step": ms_dev / steps,
+           "regexes_per_gpu": mr, "rejected_by_compiler": len(rxs) - mr, "result_triples": total, "occurrences_covered": occurrences, "items_processed": int(items),
+           "longest_match": max_len, "kernel_launches_per_step": launches, "clocks": clocks, "compile_s_once": compile_s, "set_upload_s_once": upload_s,
+           "e2e": {"value": cx.world * mr * steps / (ms_e2e * 1e-3), "unit": "regexes/s", "ms_per_step": ms_e2e / steps, "h2d_bytes_per_step": 0,
+                   "d2h_bytes_per_step": total * 20 + (mr + 1) * 8, "api": "fmx_regex_set_search (device-resident set, host result buffers)"}}
+    # one item = one backward step = at most two rank-block requests + the 16-byte state record and the ring slot
+    r_rand_gbs, _ = g.gather_bench(64, 2, 1 << 25, 16, 3)
+    peak, peak_src = measured_peaks()
+    out["roofline"] = {"bound": "hbm", "unit": "GB/s", "achieved": items * 2 * 64 / (float(np.mean(kms)) * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src,
+                       "frac": items * 2 * 64 / (float(np.mean(kms)) * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "regex_queue_kernel", "kernel_ms": float(np.mean(kms)),
+                       "items_per_regex": items / max(mr, 1), "request_rate": {"achieved_requests_per_s": items * 2 / (float(np.mean(kms)) * 1e-3),
+                                                                              "r_rand_requests_per_s": r_rand_gbs * 1e9 / 64,
+                                                                              "frac": items * 2 / (float(np.mean(kms)) * 1e-3) / (r_rand_gbs * 1e9 / 64)},
+                       "note": "algorithmic bytes = items x one backward step (2 x 64-B rank blocks, SURVEY 8(d): 'one frontier expansion = one backward step')"}
+    if orc is not None:
+        cores = os.cpu_count() or 1
+        tabs = [_oracle_compile(rx) for rx, _ in sample]
         t1 = time.time()
-        ok = all(ix.regex_match(rx, max_expansions=50_000_000) == want for rx, want in regex["sample"])
+        got = _oracle_regex(orc, tabs, cores)
         dtr = time.time() - t1
+        ok = all(a == want for a, (_, want) in zip(got, sample))
         assert ok, "GPU regex results differ from the oracle on the sample"
-        extra["regex"] = {"value": len(regex["sample"]) / dtr, "unit": "regexes/s", "cores": 1, "sample": "%d regexes of the batch" % len(regex["sample"]),
-                          "parity_on_sample": bool(ok)}
-    ix.close()
-    return dict({"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                 "sample": "first %d of the %d-query batch, %d threads, %.1f s" % (sample, len(pats), cores, dt),
-                 "parity_on_sample": parity, "note": "JVM unavailable - C restatement of the reference algorithm (binary search in .fm)"}, **extra)
+        out["parity_on_sample"] = bool(ok)
+        out["cpu_baseline"] = {"value": len(sample) / dtr, "unit": "regexes/s", "cores": cores, "kind": "port",
+                               "sample": "%d regexes of the batch (ReTree._matchSA, caps off, automata precompiled), %d threads, %.2f s" % (len(sample), cores, dtr),
+                               "parity_on_sample": bool(ok)}
+    rset.close()
+    for a in (ln_, sp_, ep_):
+        a.free()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ drivers
+def guarded(name, fn):
+    """a secondary leg must not take the headline down with it"""
+    try:
+        t0 = time.time()
+        r = fn()
+        log("leg %s done in %.1f s" % (name, time.time() - t0))
+        return r
+    except Exception as e:                                           # noqa: BLE001
+        log("leg %s FAILED:\n%s" % (name, traceback.format_exc()))
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
+def run_default(cx):
+    args, fx = cx.args, cx.fx
+    extras = set(args.legs.split(",")) if args.legs else set()
+    if cx.world > 1:
+        extras -= {"sweep"}                                  # single-GPU characterisation; the scaling runs carry the multi-GPU legs
+    n, m, ln = args.text_bytes, args.queries, args.len
+    numa = numa_report(cx.local)
+    out, stt = count_workload(cx, "cfg2", n, m, ln, extras)
+    out["host"] = {"numa": numa, "cores": os.cpu_count()}
+    g, text, base = stt["g"], stt["text"], stt["base"]
+    scale = n / DEFAULTS["cfg2"][0]
+    orc = None
+    if cx.world == 1 and cx.rank == 0 and not args.no_cpu:
+        orc = load_oracle(base, "cfg2")
+        out["cpu_baseline"] = guarded("cpu_baseline", lambda: cpu_count_baseline(orc, stt["pats"], stt["sp"], stt["ep"], stt["cnt"]))
+    if "sweep" in extras:
+        def sweep():
+            ms = max(1000, min(m, int(4_000_000 * min(1.0, scale * 10))))
+            recs = sweep_leg(cx, g, text, [8, 12, 16, 20, 24, 32, 64], ms, 3, orc, "cfg2, all accelerators (k-mer table + row-context hops)")
+            g.set_accel_mask(fx.ACCEL_NONE)
+            recs += sweep_leg(cx, g, text, [16], ms, 3, orc, "cfg2, %s rank structure alone (no accelerators)" % stt["info"]["layout"].upper())
+            g.set_accel_mask(fx.ACCEL_AUTO)
+            return recs
+        out["sweep"] = guarded("sweep", sweep)
+    if stt["fused"] is not None:
+        stt["fused"].close()
+    g.close()
+    if "sweep" in extras and cx.rank == 0:
+        def wm():
+            gw = fx.GpuFMSearcher(base + ".bwt", bigEndian=True, device=cx.local, layout=fx.LAYOUT_WM, accel=fx.ACCEL_NONE)
+            try:
+                info = gw.info()
+                recs = sweep_leg(cx, gw, text, [16], max(1000, min(m, int(2_000_000 * min(1.0, scale * 10)))), 3, orc,
+                                 "cfg2, wavelet matrix alone (north_star's structure, %.2f GB)" % (info["index_bytes"] / 1e9))
+                for r in recs:
+                    r["index_bytes"] = info["index_bytes"]
+                    r["dedup_bytes_per_query"] = r["requests_per_query"] * 64          # SURVEY 8(d)'s dedup figure: distinct 64-B blocks of a WM search
+                return recs
+            finally:
+                gw.close()
+        wm_recs = guarded("wm", wm)
+        if isinstance(out.get("sweep"), list) and isinstance(wm_recs, list):
+            out["sweep"] += wm_recs
+            out["roofline"]["survey_units"]["dedup_bytes_per_query"] = wm_recs[0]["dedup_bytes_per_query"]
+    if orc is not None:
+        orc.close()
+        orc = None
+    del stt, text
+    cx.barrier()
+    if "english" in extras and args.regexes > 0:
+        def english():
+            ne = max(100_000, int(DEFAULTS["cfg3"][0] * scale))
+            text_e, base_e, ge, info_e = english_open(cx, ne)
+            try:
+                orc_e = load_oracle(base_e, "cfg3") if (cx.world == 1 and cx.rank == 0 and not args.no_cpu) else None
+                res = {"index": {k: info_e[k] for k in ("layout", "index_bytes", "kmer_k", "ctx_depth", "sigma", "sa_sample_rate", "open_s")}}
+                mq = max(1000, min(m, int(4_000_000 * min(1.0, scale * 10))))
+                res["count"] = guarded("english count", lambda: sweep_leg(cx, ge, text_e, [12, 16], mq, 5, orc_e, "cfg3 English-like, all accelerators", workload="cfg3"))
+                ml = max(1000, int(200_000 * min(1.0, scale * 10)))
+                res["locate"] = guarded("locate", lambda: locate_leg(cx, ge, text_e, ne, ml * cx.world if args.locate_weak else ml, 12, orc_e, max(2, min(args.steps, 5)), False))
+                res["regex"] = guarded("regex", lambda: regex_leg(cx, ge, text_e, args.regexes, orc_e, args.steps))
+                if orc_e is not None:
+                    orc_e.close()
+                return res
+            finally:
+                ge.close()
+        eng = guarded("english", english)
+        out["english"] = eng
+        for k in ("locate", "regex"):                                 # the two halves BASELINE names, also at the top level
+            if isinstance(eng, dict) and k in eng:
+                out[k] = eng[k]
+    cx.barrier()
+    if "cfg5" in extras:
+        def cfg5():
+            n5 = max(100_000, int(DEFAULTS["cfg5"][0] * scale))
+            m5 = max(1000, int(DEFAULTS["cfg5"][1] * min(1.0, scale * 10)))
+            sub = argparse.Namespace(**vars(args))
+            sub.steps, sub.warmup = max(3, min(args.steps, 20)), 3
+            cx5 = cx
+            old = cx.args
+            cx.args = sub
+            try:
+                o5, st5 = count_workload(cx5, "cfg5", n5, m5, 32, {"pcie"} & extras)
+            finally:
+                cx.args = old
+            try:
+                if cx.world == 1 and cx.rank == 0 and not args.no_cpu:
+                    orc5 = load_oracle(st5["base"], "cfg5")
+                    o5["parity_on_sample"], o5["parity_sample"] = oracle_parity(orc5, st5["pats"], st5["sp"], st5["ep"], 200_000)
+                    assert o5["parity_on_sample"], "cfg5: GPU (sp,ep) differ from the oracle"
+                    orc5.close()
+                else:
+                    # without the oracle (N > 1): the accelerated answers equal plain rank stepping over the same index, on the whole batch
+                    st5["g"].set_accel_mask(fx.ACCEL_NONE)
+                    _, sp2, ep2 = device_count_rate(cx, st5["g"], st5["pats"], reps=1)
+                    o5["parity_vs_plain_steps"] = bool(np.array_equal(sp2, st5["sp"]) and np.array_equal(ep2, st5["ep"]))
+                    assert o5["parity_vs_plain_steps"]
+            finally:
+                if st5["fused"] is not None:
+                    st5["fused"].close()
+                st5["g"].close()
+            keep = ("value", "unit", "ms_per_step", "steps", "config", "impl_config", "e2e", "roofline", "clocks", "parity_on_sample", "parity_sample", "parity_vs_plain_steps")
+            return {k: o5[k] for k in keep if k in o5}
+        out["cfg5"] = guarded("cfg5", cfg5)
+    out["gpu_launches"] = cx.launches
+    return out
+
+
+def run_workload(cx):
+    """--workload cfg3 | cfg4 | cfg5 as top-level lines"""
+    args, fx = cx.args, cx.fx
+    w, n, m, ln = args.workload, args.text_bytes, args.queries, args.len
+    extras = set(args.legs.split(",")) if args.legs else set()
+    if w == "cfg5":
+        out, stt = count_workload(cx, "cfg5", n, m, ln, extras)
+        if cx.world == 1 and cx.rank == 0 and not args.no_cpu:
+            orc = load_oracle(stt["base"], "cfg5")
+            out["cpu_baseline"] = cpu_count_baseline(orc, stt["pats"], stt["sp"], stt["ep"], stt["cnt"])
+            orc.close()
+        if stt["fused"] is not None:
+            stt["fused"].close()
+        stt["g"].close()
+        out["gpu_launches"] = cx.launches
+        return out
+    text, base, g, info = english_open(cx, n)
+    orc = load_oracle(base, w) if (cx.world == 1 and cx.rank == 0 and not args.no_cpu) else None
+    common = {"n_gpus": cx.world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+              "config": workload_config(args), "impl_config": {k: info[k] for k in ("layout", "index_bytes", "kmer_k", "ctx_depth", "sigma", "sa_sample_rate", "open_s")}}
+    if w == "cfg3":
+        leg = locate_leg(cx, g, text, n, m, ln, orc, max(2, args.steps), True)
+        out = dict(common, metric=METRICS[w], value=leg["value"], unit=UNIT, ms_per_step=leg["ms_per_step"], scaling="strong", clocks=leg["clocks"], e2e=leg["e2e"],
+                   roofline=leg["roofline"], locate={k: v for k, v in leg.items() if k not in ("e2e", "roofline", "clocks")})
+        if orc is not None:
+            cores = os.cpu_count() or 1
+            pats, _ = make_queries(text, m, ln, 5, 0, workload="cfg3")
+            t1 = time.time()
+            orc.sa()
+            sa_s = time.time() - t1
+            k = int(min(m, max(2000, _probe(lambda kk: _oracle_locate(orc, pats[:kk], ln, cores), 2000) * 10.0)))
+            t1 = time.time()
+            _oracle_locate(orc, pats[:k], ln, cores)
+            dt = time.time() - t1
+            out["cpu_baseline"] = {"value": k / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": "first %d queries: count + sorted sa[sp..ep), %d threads, %.1f s "
+                                   "(+ %.1f s one-off suffix array walk = SACreator.create)" % (k, cores, dt, sa_s)}
+    else:
+        leg = regex_leg(cx, g, text, m, orc, args.steps)
+        out = dict(common, metric=METRICS[w], value=leg["value"], unit="regexes/s", ms_per_step=leg["ms_per_step"], scaling="weak", clocks=leg["clocks"], e2e=leg["e2e"],
+                   roofline=leg["roofline"], regex={k: v for k, v in leg.items() if k not in ("e2e", "roofline", "clocks", "cpu_baseline")})
+        if "cpu_baseline" in leg:
+            out["cpu_baseline"] = leg["cpu_baseline"]
+    if orc is not None:
+        orc.close()
+    g.close()
+    out["gpu_launches"] = cx.launches
+    return out
 
 
 def protect_stdout():
@@ -574,57 +1137,32 @@ def protect_stdout():
     return os.fdopen(real, "w")
 
 
-def bind_to_gpu_numa_node(local_rank):
-    """Run this rank (and allocate its pinned buffers) on the NUMA node its GPU hangs off."""
-    try:
-        import torch
-        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
-        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
-        path = "/sys/bus/pci/devices/%04x:%02x:00.0/numa_node" % (dom, bus)
-        node = int(open(path).read().strip())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        allowed = cpus & os.sched_getaffinity(0)
-        if allowed:
-            os.sched_setaffinity(0, allowed)
-            return node
-    except Exception as e:
-        log("numa binding skipped:", e)
-    return None
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"], help="cfg2 = the metric's config (default); cfg5 = 4 GB DNA, len-32")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="cfg2 = the metric's config (default line, carries the other configs as extra legs); cfg3 locate, cfg4 regex, cfg5 DNA count as their own lines")
+    ap.add_argument("--legs", default="sweep,sustained,pcie,english,cfg5", help="extra legs of the default line (comma separated; empty = headline only)")
     ap.add_argument("--text-bytes", type=int, default=None)
     ap.add_argument("--queries", type=int, default=None)
     ap.add_argument("--len", type=int, default=None)
     ap.add_argument("--layout", default="auto", choices=["auto", "wm", "planes"])
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--accel", default="auto", choices=["auto", "none", "kmer", "text", "both", "ctx"])
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory stores (default) or NCCL all-gather")
-    ap.add_argument("--gather-chunks", type=int, default=1)
-    ap.add_argument("--diag", default="none", choices=["none", "nocomm", "nosub", "nogather"], help="diagnostics only: drop parts of the exchange")
-    ap.add_argument("--regexes", type=int, default=100_000, help="regexes per GPU for the secondary regex measurement (0 = skip)")
+    ap.add_argument("--max-total-bytes", type=int, default=0, help="fmx_opts.max_total_bytes: cap on everything resident for an index")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1 count: fused peer-memory stores (default) or NCCL all-gather")
+    ap.add_argument("--regexes", type=int, default=100_000, help="regexes per GPU of the regex leg")
+    ap.add_argument("--locate-weak", action="store_true", help="default line's locate leg: the same number of queries per GPU instead of in all")
     ap.add_argument("--chunk", type=int, default=0, help="queries per pipeline chunk of the host-buffer calls (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    dflt = {"cfg2": (1_000_000_000, 10_000_000, 16), "cfg5": (4_000_000_000, 12_500_000, 32)}[args.workload]
+    dflt = DEFAULTS[args.workload]
     args.text_bytes = args.text_bytes or dflt[0]
     args.queries = args.queries or dflt[1]
-    args.len = args.len or dflt[2]
-    if args.workload == "cfg5":
-        args.regexes = 0
-        global METRIC
-        METRIC = "fm_count_queries_per_s_len32_4GB_dna_text"
+    args.len = dflt[2] if args.len is None else args.len
     if args.warmup < 3:
         log("note: contract asks for >= 3 warm-up steps; got", args.warmup)
     rank = int(os.environ.get("RANK", "0"))
@@ -635,15 +1173,18 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     if world > 1:
-        import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        node = bind_to_gpu_numa_node(local_rank)
-        log("rank %d: bound to NUMA node %s" % (rank, node))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        cx = Ctx(args, rank, world, local_rank)
+        out = run_default(cx) if args.workload == "cfg2" else run_workload(cx)
+        if rank == 0:
+            print(json.dumps(out), file=OUT, flush=True)
     finally:
         if world > 1:
             import torch.distributed as dist

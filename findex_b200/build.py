@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfmgpu.so")
 OBJ = os.path.join(HERE, "_build")
-SOURCES = ["fmx_files.cpp", "fmx_regex.cpp", "fmx_kernels.cu", "fmx_cub.cu", "fmx_build.cu", "fmx_api.cu"]
+SOURCES = ["fmx_files.cpp", "fmx_regex.cpp", "fmx_kernels.cu", "fmx_regex_kernel.cu", "fmx_cub.cu", "fmx_build.cu", "fmx_api.cu"]
 HEADERS = ["fmx_internal.h", "fmx_device.cuh", "fmx_kernels.cuh", "fmx_cub.cuh", "fmx_build.cuh", "../../include/fmgpu.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",

@@ -37,7 +37,9 @@ struct fmx_index {
     int sigma = 0, levels = 0, sample_rate = 0;
     int64_t nblk = 0, index_bytes = 0, n_samples = 0;
     std::vector<void *> owned;         // device allocations freed at close
-    double last_ms = 0.0;
+    double last_ms = 0.0, locate_walk_ms = 0.0, locate_sort_ms = 0.0;
+    bool stats = false;                // fmx_set_stats: the next locate / regex calls also count their LF steps / items
+    int64_t last_steps = 0;
     int64_t last_launches = 0, total_launches = 0, last_levels = 0;
     std::mutex mu;
 };
@@ -720,14 +722,21 @@ int fmx_memcpy_d2h(void *dst, const void *src, int64_t bytes) {
     return FMX_OK;
 }
 
+// packed2_alphabet != nullptr: `pat` holds 2-bit symbol codes, (len+3)/4 bytes per pattern (symbol j = bits 2(j%4) of byte j/4), which are
+// expanded to the alphabet's bytes on the device after crossing PCIe at a quarter of the size
 static int count_fixed_pipeline(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, int64_t *sp, int64_t *ep, uint32_t *counts,
-                                int32_t *sp32 = nullptr, int32_t *ep32 = nullptr) {
+                                int32_t *sp32 = nullptr, int32_t *ep32 = nullptr, const uint8_t *packed2_alphabet = nullptr) {
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t st = ix->stream;
-    const bool only_counts = counts != nullptr, narrow = sp32 != nullptr;     // narrow: 32-bit rows out (the reference's Int)
-    DBuf dp(st), dsp(st), dep(st), dcnt(st);
-    CU(dp.alloc((size_t)m * len));
+    const bool only_counts = counts != nullptr, narrow = sp32 != nullptr;     // narrow: 32-bit rows out (the reference's Int / uint32 rows)
+    const bool packed = packed2_alphabet != nullptr;
+    const int64_t wire_len = packed ? (len + 3) / 4 : len;                    // bytes per pattern on the wire
+    uint32_t alpha4 = 0;
+    if (packed) alpha4 = (uint32_t)packed2_alphabet[0] | ((uint32_t)packed2_alphabet[1] << 8) | ((uint32_t)packed2_alphabet[2] << 16) | ((uint32_t)packed2_alphabet[3] << 24);
+    DBuf dp(st), dsp(st), dep(st), dcnt(st), dwire(st);
+    CU(dp.alloc((size_t)m * len + 16));
+    if (packed) CU(dwire.alloc((size_t)m * wire_len));
     CU(dsp.alloc(m * ((only_counts || narrow) ? 4 : 8))); CU(dep.alloc(m * ((only_counts || narrow) ? 4 : 8)));
     if (only_counts) CU(dcnt.alloc(m * 4));
     const int64_t chunk = ix->chunk_queries > 0 ? ix->chunk_queries : (1 << 20);
@@ -748,9 +757,11 @@ static int count_fixed_pipeline(fmx_index *ix, const uint8_t *pat, int32_t len, 
     for (int64_t k = 0; k < nchunks && rc == FMX_OK; ++k) {
         const int64_t q0 = k * chunk, nq = std::min(chunk, m - q0);
         cudaError_t e = cudaSuccess;
-        if (len) e = cudaMemcpyAsync(dp.as<uint8_t>() + q0 * len, pat + q0 * len, (size_t)nq * len, cudaMemcpyHostToDevice, ix->h2d);
+        uint8_t *wire_dst = packed ? dwire.as<uint8_t>() + q0 * wire_len : dp.as<uint8_t>() + q0 * len;
+        if (len) e = cudaMemcpyAsync(wire_dst, pat + q0 * wire_len, (size_t)nq * wire_len, cudaMemcpyHostToDevice, ix->h2d);
         if (e == cudaSuccess) e = cudaEventRecord(ev_in[(size_t)k], ix->h2d);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev_in[(size_t)k], 0);
+        if (e == cudaSuccess && packed && len) e = launch_unpack2(wire_dst, len, nq, alpha4, dp.as<uint8_t>() + q0 * len, st);
         if (e == cudaSuccess) {
             if (only_counts) {                       // ep-sp lands in dcnt through the kernel's fused-exchange sink; only that goes back
                 PeerSinks ps{};
@@ -775,7 +786,7 @@ static int count_fixed_pipeline(fmx_index *ix, const uint8_t *pat, int32_t len, 
         }
         if (e != cudaSuccess) rc = fail(FMX_E_CUDA, "CUDA error %s in the count pipeline (%s)", cudaGetErrorName(e), cudaGetErrorString(e));
     }
-    ix->last_launches = nchunks; ix->total_launches += nchunks;
+    ix->last_launches = nchunks * (packed ? 2 : 1); ix->total_launches += nchunks * (packed ? 2 : 1);
     t.stop();
     cudaError_t e1 = cudaStreamSynchronize(ix->h2d), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(ix->d2h);
     if (rc == FMX_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess))
@@ -807,6 +818,17 @@ int fmx_count_only_fixed(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t
     if (len < 0 || m < 0 || (m && (!counts || (len && !pat)))) return fail(FMX_E_ARG, "bad argument");
     if (m == 0) return FMX_OK;
     return count_fixed_pipeline(ix, pat, len, m, nullptr, nullptr, counts);
+}
+
+// Patterns over an alphabet of <= 4 symbols as 2-bit codes on the wire (a DNA read of 32 bases = 8 bytes instead of 32): pattern q occupies
+// bytes [q * ceil(len/4), (q+1) * ceil(len/4)), symbol j = alphabet[(byte[j/4] >> 2(j%4)) & 3].  Rows come back as uint32 (n < 2^32 always
+// holds on this build) when row_bytes = 4, as int64 when 8.  Same (sp, ep) as fmx_count_fixed on the expanded patterns.
+int fmx_count_fixed_packed2(fmx_index *ix, const uint8_t *codes, const uint8_t alphabet[4], int32_t len, int64_t m, void *sp, void *ep, int32_t row_bytes) {
+    CHECK_IX(ix);
+    if (len < 0 || m < 0 || !alphabet || (row_bytes != 4 && row_bytes != 8) || (m && (!sp || !ep || (len && !codes)))) return fail(FMX_E_ARG, "bad argument");
+    if (m == 0) return FMX_OK;
+    if (row_bytes == 4) return count_fixed_pipeline(ix, codes, len, m, nullptr, nullptr, nullptr, (int32_t *)sp, (int32_t *)ep, alphabet);
+    return count_fixed_pipeline(ix, codes, len, m, (int64_t *)sp, (int64_t *)ep, nullptr, nullptr, nullptr, alphabet);
 }
 
 int fmx_count_batch(fmx_index *ix, const uint8_t *pat, const int64_t *off, int64_t m, int64_t *sp, int64_t *ep) {
@@ -950,35 +972,139 @@ int fmx_extract_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t len,
 }
 
 // ---- locate ---------------------------------------------------------------------------------------------------
+namespace {
+// Occurrences are processed in slabs of whole queries (<= 2^30 occurrences each, or one query of any size): LF walks into a
+// slab-sized scratch, then an ascending sort inside each query straight into d_pos (indexed by the batch-wide offsets).  No limit on
+// the number of occurrences of a batch other than the caller's buffer.
+std::atomic<int64_t> g_locate_slab{1ll << 30};               // occurrences per slab (fmx_set_locate_slab: tests exercise the slab seams)
+int64_t locate_slab() { return g_locate_slab.load(); }
+
+int locate_core(fmx_index *ix, const uint32_t *d_sp, const int64_t *d_off, const int64_t *h_off, int64_t m, int64_t total, uint32_t *d_pos,
+                cudaStream_t st) {
+    ix->locate_walk_ms = ix->locate_sort_ms = 0.0;
+    if (total <= 0) return FMX_OK;
+    const int64_t kLocateSlab = locate_slab();
+    std::vector<int64_t> cuts{0};                              // query indices where slabs begin
+    if (total > kLocateSlab) {
+        for (int64_t q = 0, t0 = 0; q < m; ++q)
+            if (h_off[q + 1] - t0 > kLocateSlab && q > cuts.back()) { cuts.push_back(q); t0 = h_off[q]; }
+    }
+    cuts.push_back(m);
+    int64_t largest = 0;
+    std::vector<int64_t> hb(cuts.size());
+    for (size_t k = 0; k < cuts.size(); ++k) hb[k] = (total > kLocateSlab) ? h_off[cuts[k]] : (k == 0 ? 0 : total);
+    for (size_t k = 0; k + 1 < cuts.size(); ++k) largest = std::max(largest, hb[k + 1] - hb[k]);
+    DBuf tmp(st), dsteps(st);
+    CU(tmp.alloc((size_t)largest * 4));
+    if (ix->stats) { CU(dsteps.alloc(8)); CU(cudaMemsetAsync(dsteps.p, 0, 8, st)); }
+    cudaEvent_t ev[3];
+    for (auto &e : ev) CU(cudaEventCreate(&e));
+    struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 3; ++i) cudaEventDestroy(e[i]); } } eg{ev};
+    for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+        const int64_t q0 = cuts[k], q1 = cuts[k + 1], t0 = hb[k], cnt = hb[k + 1] - t0;
+        if (cnt <= 0) continue;
+        CU(cudaEventRecord(ev[0], st));
+        CU(launch_locate(ix->d, ix->cfg, d_sp, d_off, q0, q1, t0, cnt, tmp.as<uint32_t>(), ix->stats ? dsteps.as<unsigned long long>() : nullptr, st));
+        CU(cudaEventRecord(ev[1], st));
+        // the sort reads/writes through the batch-wide offsets: both key pointers are biased by the slab's first occurrence
+        if (q1 - q0 == 1 || cnt >= (1ll << 31)) {
+            if (q1 - q0 != 1) return fail(FMX_E_LIMIT, "internal: slab of %lld occurrences over several queries", (long long)cnt);
+            CU(radix_sort_u32(tmp.as<uint32_t>(), d_pos + t0, cnt, st));
+        } else {
+            CU(segmented_sort_u32(tmp.as<uint32_t>() - t0, d_pos, cnt, q1 - q0, d_off + q0, st));
+        }
+        CU(cudaEventRecord(ev[2], st));
+        CU(cudaStreamSynchronize(st));
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]);
+        ix->locate_walk_ms += a; ix->locate_sort_ms += b;
+        ix->last_launches += 1; ix->total_launches += 1;
+    }
+    ix->last_ms = ix->locate_walk_ms + ix->locate_sort_ms;
+    if (ix->stats) {
+        unsigned long long hs = 0;
+        CU(cudaMemcpyAsync(&hs, dsteps.p, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        ix->last_steps = (int64_t)hs;
+    }
+    return FMX_OK;
+}
+}  // namespace
+
+// Device-resident locate: d_sp/d_ep = uint32 rows of m intervals (as fmx_count_fixed_dev leaves them; an empty interval has sp >= ep),
+// d_off[m+1] receives the exclusive offsets, d_pos[cap] the positions (uint32, ascending inside each query).  Synchronises `stream`
+// once to learn the total.  FMX_E_CAPACITY with *total_out set when cap is too small.
+int fmx_locate_dev(fmx_index *ix, const void *d_sp, const void *d_ep, int64_t m, void *d_off, void *d_pos, int64_t cap, int64_t *total_out, void *stream) {
+    CHECK_IX(ix);
+    if (m < 0 || !d_off || !total_out || (m && (!d_sp || !d_ep))) return fail(FMX_E_ARG, "bad argument");
+    if (ix->sample_rate <= 0 && ix->d.sa == nullptr) return fail(FMX_E_ARG, "index was opened without sa_sample_rate (and without a resident suffix array); locate unavailable");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ix->last_launches = 0;
+    DBuf len(st);
+    CU(len.alloc((size_t)(m + 1) * 8));
+    CU(launch_interval_len((const uint32_t *)d_sp, (const uint32_t *)d_ep, m, len.as<int64_t>(), st));
+    CU(exclusive_sum_i64(len.as<int64_t>(), (int64_t *)d_off, m + 1, st));
+    int64_t total = 0;
+    CU(cudaMemcpyAsync(&total, (const int64_t *)d_off + m, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *total_out = total;
+    if (total > cap) return fail(FMX_E_CAPACITY, "locate needs %lld output slots, capacity %lld", (long long)total, (long long)cap);
+    if (total == 0) return FMX_OK;
+    if (!d_pos) return fail(FMX_E_ARG, "null output");
+    std::vector<int64_t> h_off;
+    if (total > locate_slab()) {
+        h_off.resize((size_t)m + 1);
+        CU(cudaMemcpyAsync(h_off.data(), d_off, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return locate_core(ix, (const uint32_t *)d_sp, (const int64_t *)d_off, h_off.empty() ? nullptr : h_off.data(), m, total, (uint32_t *)d_pos, st);
+}
+
+// Instrumentation for the roofline accounting: with stats on, locate calls also count the LF steps of their walks (one atomic per
+// occurrence — not for timed runs); regex searches always count their items.  fmx_last_steps returns the count of the last such call.
+int fmx_set_stats(fmx_index *ix, int32_t on) { CHECK_IX(ix); std::lock_guard<std::mutex> lk(ix->mu); ix->stats = on != 0; return FMX_OK; }
+int64_t fmx_last_steps(const fmx_index *ix) { return ix ? ix->last_steps : 0; }
+
+int fmx_set_locate_slab(int64_t occurrences) {
+    g_locate_slab = occurrences > 0 ? occurrences : (1ll << 30);
+    return FMX_OK;
+}
+
+int fmx_last_locate_ms(const fmx_index *ix, double *walk_ms, double *sort_ms) {
+    CHECK_IX(ix);
+    if (walk_ms) *walk_ms = ix->locate_walk_ms;
+    if (sort_ms) *sort_ms = ix->locate_sort_ms;
+    return FMX_OK;
+}
+
 int fmx_locate_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, int64_t m, int64_t cap_total, int64_t *out_off, int64_t *pos) {
     CHECK_IX(ix);
     if (m < 0 || !out_off || (m && (!sp || !ep))) return fail(FMX_E_ARG, "bad argument");
-    if (ix->sample_rate <= 0 && ix->d.sa == nullptr) return fail(FMX_E_ARG, "index was opened without sa_sample_rate (and without a full-SA accelerator); locate unavailable");
+    if (ix->sample_rate <= 0 && ix->d.sa == nullptr) return fail(FMX_E_ARG, "index was opened without sa_sample_rate (and without a resident suffix array); locate unavailable");
     int64_t total = 0;
+    std::vector<uint32_t> sp32((size_t)m);
     for (int64_t i = 0; i < m; ++i) {
         if (sp[i] < 0 || ep[i] > ix->n || (ep[i] < sp[i])) return fail(FMX_E_ARG, "bad interval at %lld", (long long)i);
         out_off[i] = total;
         total += ep[i] - sp[i];
+        sp32[(size_t)i] = (uint32_t)sp[i];
     }
     out_off[m] = total;
     if (total > cap_total) return fail(FMX_E_CAPACITY, "locate needs %lld output slots, capacity %lld", (long long)total, (long long)cap_total);
     if (total == 0) return FMX_OK;
     if (!pos) return fail(FMX_E_ARG, "null output");
-    if (total >= (1ll << 31)) return fail(FMX_E_LIMIT, "more than 2^31 occurrences in one batch; split the batch");
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t st = ix->stream;
-    DBuf dsp(st), doff(st), dpos(st), dsorted(st), dout(st);
-    CU(dsp.alloc(m * 8)); CU(doff.alloc((m + 1) * 8)); CU(dpos.alloc(total * 4)); CU(dsorted.alloc(total * 4));
-    CU(cudaMemcpyAsync(dsp.p, sp, m * 8, cudaMemcpyHostToDevice, st));
+    ix->last_launches = 0;
+    DBuf dsp(st), doff(st), dsorted(st);
+    CU(dsp.alloc(m * 4)); CU(doff.alloc((m + 1) * 8)); CU(dsorted.alloc(total * 4));
+    CU(cudaMemcpyAsync(dsp.p, sp32.data(), m * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(doff.p, out_off, (m + 1) * 8, cudaMemcpyHostToDevice, st));
-    Timed t(ix);
-    CU(launch_locate(ix->d, ix->cfg, dsp.as<int64_t>(), doff.as<int64_t>(), m, total, ix->sample_rate, dpos.as<uint32_t>(), st));
-    CU(segmented_sort_u32(dpos.as<uint32_t>(), dsorted.as<uint32_t>(), total, m, doff.as<int64_t>(), st));
-    ix->last_launches = 1; ix->total_launches += 1;
-    t.stop();
-    CU(cudaStreamSynchronize(st));
-    t.collect();
+    int rc = locate_core(ix, dsp.as<uint32_t>(), doff.as<int64_t>(), out_off, m, total, dsorted.as<uint32_t>(), st);
+    if (rc) return rc;
     // widen to the ABI's int64 on the device and stream the slabs straight into the caller's buffer: the widening of
     // slab k+1 overlaps the D2H of slab k (asynchronous DMA when `pos` is page-locked)
     const int64_t slab = 32ll << 20;
@@ -988,7 +1114,6 @@ int fmx_locate_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, int64_
     CU(cudaStreamWaitEvent(ix->d2h, ix->ev_alloc, 0));
     cudaEvent_t done[2];
     CU(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
-    int rc = FMX_OK;
     for (int64_t o = 0, k = 0; o < total && rc == FMX_OK; o += slab, ++k) {
         const int64_t cnt = std::min(slab, total - o);
         int64_t *w = (k & 1) ? w1.as<int64_t>() : w0.as<int64_t>();
@@ -1005,6 +1130,18 @@ int fmx_locate_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, int64_
     cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
     if (rc == FMX_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) rc = fail(FMX_E_CUDA, "CUDA error while draining the locate copy-out");
     return rc;
+}
+
+// Exchange step for variable-length results: `count` 4-byte words of this rank go into every sink (this rank's and, via CUDA IPC, its
+// peers' gathered buffers) at word offset `offset` + (*d_dst_off) * dst_scale; d_dst_off is a DEVICE int64 (e.g. the scanned offset of
+// this rank's first result) or NULL.  Asynchronous on `stream`.
+int fmx_scatter_dev(const void *d_src, int64_t count, void *const *sinks, int32_t n_sinks, int64_t offset, const void *d_dst_off, int64_t dst_scale, void *stream) {
+    if (count < 0 || n_sinks < 0 || n_sinks > 8 || (n_sinks && !sinks) || (count && !d_src)) return fail(FMX_E_ARG, "bad argument");
+    PeerSinks ps{};
+    ps.n = n_sinks; ps.offset = offset;
+    for (int j = 0; j < n_sinks; ++j) { if (!sinks[j]) return fail(FMX_E_ARG, "null sink %d", j); ps.p[j] = (uint32_t *)sinks[j]; }
+    CU(launch_scatter_words((const uint32_t *)d_src, count, ps, (const int64_t *)d_dst_off, dst_scale, (cudaStream_t)stream));
+    return FMX_OK;
 }
 
 // ---- regex ------------------------------------------------------------------------------------------------------
@@ -1100,21 +1237,23 @@ int fmx_regex_tables(const fmx_regex *rx, int32_t *n_states, int32_t *n_follows,
     return FMX_OK;
 }
 
-// A regex set = the automata of a batch concatenated (global state ids, CSR follows, owning regex) and resident on the device:
-// compile once, search many times — the batched form of `val t = ReTree(post); t.matchSA(sa)`.
+// A regex set = the automata of a batch concatenated (global state ids, 16-byte state records, follow lists, owning regex) and resident
+// on the device together with the work ring of its traversals: compile once, search many times — the batched form of
+// `val t = ReTree(post); t.matchSA(sa)`.
 struct fmx_regex_set {
     int device = 0;
     int64_t m = 0;
     size_t n_states = 0, n_fol = 0, n_first = 0;
-    std::atomic<size_t> free_bytes{0}; // free device memory when the set was first searched (bounds the frontier buffers)
-    std::atomic<int64_t> front_hint{0};           // largest frontier the last search of this set saw: the next search sizes its buffers for it
-    void *d_c = nullptr, *d_last = nullptr, *d_rx = nullptr, *d_fo = nullptr, *d_f = nullptr, *d_first = nullptr;
+    void *d_rec = nullptr, *d_rx = nullptr, *d_f = nullptr, *d_first = nullptr;
+    void *d_ring = nullptr, *d_ctrl = nullptr;     // work ring (all slots empty between searches) and the traversal's control words
+    int64_t ring_cap = 0;
+    std::mutex mu;                                 // one traversal at a time per set (they share the ring)
 };
 
 void fmx_regex_set_free(fmx_regex_set *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    cudaFree(s->d_c); cudaFree(s->d_last); cudaFree(s->d_rx); cudaFree(s->d_fo); cudaFree(s->d_f); cudaFree(s->d_first);
+    cudaFree(s->d_rec); cudaFree(s->d_rx); cudaFree(s->d_f); cudaFree(s->d_first); cudaFree(s->d_ring); cudaFree(s->d_ctrl);
     delete s;
 }
 
@@ -1129,126 +1268,180 @@ int fmx_regex_set_create(fmx_index *ix, fmx_regex *const *rx, int64_t m, fmx_reg
         if (!rx[r]) return fail(FMX_E_ARG, "null regex at %lld", (long long)r);
         n_states += rx[r]->a.c.size(); n_fol += rx[r]->a.follows.size(); n_first += rx[r]->a.firsts.size();
     }
-    if (n_states >= (1ull << 32) || n_fol >= (1ull << 32)) return fail(FMX_E_LIMIT, "regex batch has too many states; split the batch");
-    std::vector<uint8_t> st_c(n_states), st_last(n_states);
-    std::vector<uint32_t> st_regex(n_states), fol_off(n_states + 1), fol(n_fol), first(n_first);
+    if (n_states >= (1ull << 32) - 1 || n_fol >= (1ull << 32)) return fail(FMX_E_LIMIT, "regex batch has too many states; split the batch");
+    std::vector<uint4> rec(n_states);
+    std::vector<uint32_t> st_regex(n_states), fol(n_fol), first(n_first);
     {
         size_t so = 0, fo = 0, io = 0;
         for (int64_t r = 0; r < m; ++r) {
             const CompiledRegex &a = rx[r]->a;
             const uint32_t base = (uint32_t)so, fbase = (uint32_t)fo;
             const size_t ns = a.c.size();
-            const uint8_t stop = a.stop_on_emit ? 2 : 0;
-            std::memcpy(st_c.data() + so, a.c.data(), ns);
-            for (size_t s = 0; s < ns; ++s) { st_last[so + s] = (uint8_t)(a.is_last[s] | stop); st_regex[so + s] = (uint32_t)r; fol_off[so + s] = fbase + (uint32_t)a.follows_off[s]; }
+            const uint32_t stop = a.stop_on_emit ? 2u : 0u;
             for (size_t k = 0; k < a.follows.size(); ++k) fol[fo + k] = base + (uint32_t)a.follows[k];
+            for (size_t s = 0; s < ns; ++s) {
+                const uint32_t f0 = (uint32_t)a.follows_off[s], nf = (uint32_t)(a.follows_off[s + 1] - a.follows_off[s]);
+                rec[so + s] = make_uint4((uint32_t)a.c[s] | (((uint32_t)a.is_last[s] | stop) << 8), fbase + f0, nf, nf ? fol[fo + f0] : 0u);
+                st_regex[so + s] = (uint32_t)r;
+            }
             for (int32_t f : a.firsts) first[io++] = base + (uint32_t)f;
             so += ns; fo += a.follows.size();
         }
-        fol_off[n_states] = (uint32_t)fo;
     }
     ph.mark("concatenate tables");
     DeviceGuard g(ix->device);
     fmx_regex_set *s = new fmx_regex_set();
     s->device = ix->device; s->m = m; s->n_states = n_states; s->n_fol = n_fol; s->n_first = n_first;
     auto up = [&](void **d, const void *h, size_t bytes) -> cudaError_t {
-        cudaError_t e = cudaMalloc(d, bytes ? bytes : 4);
+        cudaError_t e = cudaMalloc(d, bytes ? bytes : 16);
         if (e == cudaSuccess && bytes) e = cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
         return e;
     };
-    cudaError_t e = up(&s->d_c, st_c.data(), n_states);
-    if (e == cudaSuccess) e = up(&s->d_last, st_last.data(), n_states);
+    cudaError_t e = up(&s->d_rec, rec.data(), n_states * sizeof(uint4));
     if (e == cudaSuccess) e = up(&s->d_rx, st_regex.data(), n_states * 4);
-    if (e == cudaSuccess) e = up(&s->d_fo, fol_off.data(), (n_states + 1) * 4);
     if (e == cudaSuccess) e = up(&s->d_f, fol.data(), n_fol * 4);
     if (e == cudaSuccess) e = up(&s->d_first, first.data(), n_first * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_ctrl, 64);
     if (e != cudaSuccess) { fmx_regex_set_free(s); return fail(FMX_E_CUDA, "regex set upload failed: %s", cudaGetErrorString(e)); }
     ph.mark("upload tables");
     *out = s;
     return FMX_OK;
 }
 
-int fmx_regex_set_search(fmx_index *ix, fmx_regex_set *set, int64_t cap_total, int64_t *out_off, int32_t *len, int64_t *sp, int64_t *ep) {
-    CHECK_IX(ix);
-    if (!set || !out_off) return fail(FMX_E_ARG, "bad argument");
-    if (set->device != ix->device) return fail(FMX_E_ARG, "regex set lives on device %d, index on device %d", set->device, ix->device);
-    const int64_t m = set->m;
-    for (int64_t i = 0; i <= m; ++i) out_off[i] = 0;
-    if (m == 0 || set->n_first == 0) return FMX_OK;
-    Phases ph("regex_set_search");
-    std::lock_guard<std::mutex> lk(ix->mu);
-    DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
-    DBuf d_res(st), d_tmp(st), d_cnt(st);
-    RegexTables rt{(const uint8_t *)set->d_c, (const uint8_t *)set->d_last, (const uint32_t *)set->d_rx, (const uint32_t *)set->d_fo, (const uint32_t *)set->d_f};
+// Pre-sizes (or shrinks) the set's work ring to `slots` (rounded up to a power of two, at least the number of start items): a ring that
+// turns out too small is abandoned and the traversal rerun with a 4x larger one, which this lets tests and memory-tight callers provoke.
+int fmx_regex_set_ring(fmx_regex_set *set, int64_t slots) {
+    if (!set || slots < 0) return fail(FMX_E_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(set->mu);
+    cudaSetDevice(set->device);
+    int64_t cap = 1024;
+    while (cap < slots || cap < (int64_t)set->n_first) cap <<= 1;
+    if (set->d_ring) { CU(cudaDeviceSynchronize()); CU(cudaFree(set->d_ring)); set->d_ring = nullptr; set->ring_cap = 0; }
+    CU(cudaMalloc(&set->d_ring, (size_t)cap * sizeof(FrontierItem)));
+    CU(cudaMemset(set->d_ring, 0xFF, (size_t)cap * sizeof(FrontierItem)));
+    set->ring_cap = cap;
+    return FMX_OK;
+}
 
-    if (set->free_bytes == 0) { size_t fr0 = 0, to0 = 0; cudaMemGetInfo(&fr0, &to0); set->free_bytes = fr0; }   // once per set: the query costs ~0.1 ms
-    const size_t fr = set->free_bytes.load();
-    // two ping-pong frontier buffers; they start small and are regrown (and the traversal rerun) when a level outgrows them,
-    // bounded by an eighth of the free device memory each
+namespace {
+// Runs the traversal of a set and leaves its results, ordered by (regex, len, sp, ep), in d_res (capacity cap_res).  *total_out = number of
+// results (also when it exceeds cap_res: then nothing is ordered and FMX_E_CAPACITY is returned).  Caller holds ix->mu and set->mu.
+int regex_search_core(fmx_index *ix, fmx_regex_set *set, RegexResult *d_res, int64_t cap_res, int64_t *total_out, cudaStream_t st) {
     const int64_t n_first = (int64_t)set->n_first;
-    const int64_t max_front = std::max<int64_t>(std::min<int64_t>((int64_t)(fr / 8 / sizeof(FrontierItem)), 1ll << 28), n_first);
-    const int64_t hint = set->front_hint.load();
-    int64_t cap = std::min<int64_t>(max_front, std::max<int64_t>(std::max<int64_t>(n_first * 16, 1 << 20), hint + hint / 8));
-    int64_t cap_res = std::max<int64_t>(cap_total, 1 << 16);
-    void *cur = nullptr, *nxt = nullptr;
-    CU(cudaMallocAsync(&cur, cap * sizeof(FrontierItem), st)); CU(cudaMallocAsync(&nxt, cap * sizeof(FrontierItem), st));
-    struct Guard { void **a, **b; cudaStream_t s; ~Guard() { if (*a) cudaFreeAsync(*a, s); if (*b) cudaFreeAsync(*b, s); } } guard{&cur, &nxt, st};
-    CU(d_res.alloc(cap_res * sizeof(RegexResult))); CU(d_cnt.alloc(64));
+    *total_out = 0;
+    if (set->m == 0 || n_first == 0) return FMX_OK;
+    size_t fr = 0, to = 0;
+    RegexTables rt{(const uint4 *)set->d_rec, (const uint32_t *)set->d_rx, (const uint32_t *)set->d_f};
+    auto grow_ring = [&](int64_t want) -> int {
+        int64_t cap = 1 << 20;
+        while (cap < want) cap <<= 1;
+        cudaMemGetInfo(&fr, &to);
+        if (cap > set->ring_cap && (size_t)cap * sizeof(FrontierItem) > fr / 2 + (size_t)set->ring_cap * sizeof(FrontierItem))
+            return fail(FMX_E_LIMIT, "regex traversal needs a work ring of %lld items, more than half of the free device memory; split the batch", (long long)cap);
+        if (cap > set->ring_cap) {
+            if (set->d_ring) { CU(cudaStreamSynchronize(st)); CU(cudaFree(set->d_ring)); set->d_ring = nullptr; set->ring_cap = 0; }
+            CU(cudaMalloc(&set->d_ring, (size_t)cap * sizeof(FrontierItem)));
+            set->ring_cap = cap;
+        }
+        CU(cudaMemsetAsync(set->d_ring, 0xFF, (size_t)set->ring_cap * sizeof(FrontierItem), st));      // every slot empty
+        return FMX_OK;
+    };
+    if (set->ring_cap < n_first || set->d_ring == nullptr) { int rc = grow_ring(4 * n_first); if (rc) return rc; }
     Timed t(ix);
     int64_t launches = 0;
     unsigned long long h[8] = {0};
     for (;;) {
-        CU(cudaMemsetAsync(d_cnt.p, 0, 64, st));
-        CU(launch_regex_search(ix->d, ix->cfg, rt, (const uint32_t *)set->d_first, n_first, (FrontierItem *)cur, (FrontierItem *)nxt, cap,
-                               d_res.as<RegexResult>(), cap_res, d_cnt.as<unsigned long long>(), ix->n + 1, st));
-        ++launches;
-        CU(cudaMemcpyAsync(h, d_cnt.p, 64, cudaMemcpyDeviceToHost, st));
+        CU(launch_regex_search(ix->d, ix->cfg, rt, (const uint32_t *)set->d_first, n_first, (FrontierItem *)set->d_ring, set->ring_cap, d_res, cap_res,
+                               (unsigned long long *)set->d_ctrl, st));
+        launches += 2;
+        CU(cudaMemcpyAsync(h, set->d_ctrl, 64, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        if (h[4] == 0) break;
-        if (h[4] == 2) return fail(FMX_E_LIMIT, "regex traversal deeper than the text");
-        if ((int64_t)h[5] > max_front)
-            return fail(FMX_E_LIMIT, "regex frontier of %llu items exceeds the device budget of %lld; split the batch", h[5], (long long)max_front);
-        CU(cudaFreeAsync(cur, st)); cur = nullptr;
-        CU(cudaFreeAsync(nxt, st)); nxt = nullptr;
-        cap = std::min<int64_t>(max_front, std::max<int64_t>((int64_t)h[5] + (int64_t)h[5] / 4, cap * 2));
-        CU(cudaMallocAsync(&cur, cap * sizeof(FrontierItem), st)); CU(cudaMallocAsync(&nxt, cap * sizeof(FrontierItem), st));
+        if (h[kRxStatus] == 0) break;
+        if (h[kRxStatus] == 2) { grow_ring(set->ring_cap); return fail(FMX_E_LIMIT, "regex traversal deeper than the text"); }
+        int rc = grow_ring(set->ring_cap * 4);              // the ring overflowed: abandon, re-empty a larger one, rerun
+        if (rc) return rc;
     }
-    ix->last_levels = (int64_t)h[6];
-    set->front_hint = (int64_t)h[7];
-    const int64_t total = (int64_t)h[3];
-    ph.mark("traversal");
+    ix->last_levels = (int64_t)h[kRxMaxLen];
+    ix->last_steps = (int64_t)h[kRxSteps];
+    const int64_t total = (int64_t)h[kRxMatches];
+    *total_out = total;
     ix->last_launches = launches; ix->total_launches += launches;
-    if (total > cap_res) {                                            // counted everything, could not store it
-        t.stop();
+    if (total > cap_res) { t.stop(); return fail(FMX_E_CAPACITY, "regex search needs %lld result slots, capacity %lld", (long long)total, (long long)cap_res); }
+    // result order = (regex, len, sp, ep), on the device: one CTA's bitonic network for a handful, radix passes beyond
+    if (total > kSmallSort) {
+        DBuf tmp(st);
+        CU(tmp.alloc(total * sizeof(RegexResult)));
+        CU(sort_regex_results(d_res, tmp.as<RegexResult>(), total, st));
+        ix->last_launches += 6; ix->total_launches += 6;
+    } else if (total > 1) {
+        CU(sort_results_small(d_res, total, st));
+        ix->last_launches += 1; ix->total_launches += 1;
+    }
+    t.stop();
+    CU(cudaStreamSynchronize(st));
+    t.collect();
+    return FMX_OK;
+}
+}  // namespace
+
+// Device-resident search: results stay on the device as RegexResult {regex, len, sp, ep} (4 x uint32) ordered by (regex, len, sp, ep),
+// d_off (int64[m+1], may be NULL) = first result of every regex.
+int fmx_regex_set_search_dev(fmx_index *ix, fmx_regex_set *set, void *d_res, int64_t cap, void *d_off, int64_t *total_out) {
+    CHECK_IX(ix);
+    if (!set || !total_out || cap < 0 || (cap && !d_res)) return fail(FMX_E_ARG, "bad argument");
+    if (set->device != ix->device) return fail(FMX_E_ARG, "regex set lives on device %d, index on device %d", set->device, ix->device);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    std::lock_guard<std::mutex> lk2(set->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    DBuf dummy(st);
+    RegexResult *res = (RegexResult *)d_res;
+    if (!res) { CU(dummy.alloc(sizeof(RegexResult))); res = dummy.as<RegexResult>(); }
+    int rc = regex_search_core(ix, set, res, cap, total_out, st);
+    if (rc) return rc;
+    if (d_off) {
+        CU(launch_result_offsets(res, *total_out, set->m, (int64_t *)d_off, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return FMX_OK;
+}
+
+int fmx_regex_set_search(fmx_index *ix, fmx_regex_set *set, int64_t cap_total, int64_t *out_off, int32_t *len, int64_t *sp, int64_t *ep) {
+    CHECK_IX(ix);
+    if (!set || !out_off || cap_total < 0) return fail(FMX_E_ARG, "bad argument");
+    if (set->device != ix->device) return fail(FMX_E_ARG, "regex set lives on device %d, index on device %d", set->device, ix->device);
+    const int64_t m = set->m;
+    if (m == 0 || set->n_first == 0) { for (int64_t i = 0; i <= m; ++i) out_off[i] = 0; return FMX_OK; }
+    Phases ph("regex_set_search");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    std::lock_guard<std::mutex> lk2(set->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    const int64_t cap_res = std::max<int64_t>(cap_total, 1 << 16);
+    DBuf d_res(st), d_off(st), d_len(st), d_sp(st), d_ep(st);
+    CU(d_res.alloc(cap_res * sizeof(RegexResult))); CU(d_off.alloc((m + 1) * 8));
+    int64_t total = 0;
+    int rc = regex_search_core(ix, set, d_res.as<RegexResult>(), cap_res, &total, st);
+    ph.mark("traversal + order");
+    if (rc == FMX_E_CAPACITY || total > cap_total) {
+        for (int64_t i = 0; i < m; ++i) out_off[i] = 0;
         out_off[m] = total;
         return fail(FMX_E_CAPACITY, "regex search needs %lld result slots, capacity %lld", (long long)total, (long long)cap_total);
     }
-    // result order = (regex, len, sp, ep).  A handful of results is cheaper to order on the host than by two device radix sorts.
-    constexpr int64_t kHostSortMax = 1 << 14;
-    if (total > kHostSortMax) {
-        CU(d_tmp.alloc(total * sizeof(RegexResult)));
-        CU(sort_regex_results(d_res.as<RegexResult>(), d_tmp.as<RegexResult>(), total, st));
-    }
-    t.stop();
-    std::vector<RegexResult> hr((size_t)total);
-    if (total) CU(cudaMemcpyAsync(hr.data(), d_res.p, total * sizeof(RegexResult), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    t.collect();
-    if (total <= kHostSortMax)
-        std::sort(hr.begin(), hr.end(), [](const RegexResult &a, const RegexResult &b) {
-            if (a.regex != b.regex) return a.regex < b.regex;
-            if (a.len != b.len) return a.len < b.len;
-            if (a.sp != b.sp) return a.sp < b.sp;
-            return a.ep < b.ep;
-        });
-    ph.mark("sort + copy out");
-    for (const RegexResult &r : hr) out_off[r.regex + 1]++;
-    for (int64_t i = 0; i < m; ++i) out_off[i + 1] += out_off[i];
-    if (total > cap_total) return fail(FMX_E_CAPACITY, "regex search needs %lld result slots, capacity %lld", (long long)total, (long long)cap_total);
+    if (rc) return rc;
     if (total && (!len || !sp || !ep)) return fail(FMX_E_ARG, "null output");
-    for (int64_t i = 0; i < total; ++i) { len[i] = (int32_t)hr[(size_t)i].len; sp[i] = hr[(size_t)i].sp; ep[i] = hr[(size_t)i].ep; }
-    ph.mark("marshal results");
+    // offsets and the three output columns are produced on the device and copied straight into the caller's buffers
+    CU(launch_result_offsets(d_res.as<RegexResult>(), total, m, d_off.as<int64_t>(), st));
+    CU(cudaMemcpyAsync(out_off, d_off.p, (m + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (total) {
+        CU(d_len.alloc(total * 4)); CU(d_sp.alloc(total * 8)); CU(d_ep.alloc(total * 8));
+        CU(launch_split_results(d_res.as<RegexResult>(), total, d_len.as<int32_t>(), d_sp.as<int64_t>(), d_ep.as<int64_t>(), st));
+        CU(cudaMemcpyAsync(len, d_len.p, total * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(sp, d_sp.p, total * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ep, d_ep.p, total * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    ph.mark("offsets + copy out");
     return FMX_OK;
 }
 

@@ -60,6 +60,10 @@ cudaError_t segmented_sort_u32(const uint32_t *k_in, uint32_t *k_out, int64_t n,
     FMX_CUB2(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, k_in, k_out, (int)n, (int)nseg, o, o + 1, st),
              cub::DeviceSegmentedSort::SortKeys(tp, bytes, k_in, k_out, (int)n, (int)nseg, o, o + 1, st));
 }
+cudaError_t radix_sort_u32(const uint32_t *k_in, uint32_t *k_out, int64_t n, cudaStream_t st) {
+    FMX_CUB2(cub::DeviceRadixSort::SortKeys(nullptr, bytes, k_in, k_out, n, 0, 32, st),
+             cub::DeviceRadixSort::SortKeys(tp, bytes, k_in, k_out, n, 0, 32, st));
+}
 // ---- regex result ordering: LSD radix over the two 64-bit halves of (regex,len | sp,ep) ------------------
 __global__ void split_keys_kernel(const RegexResult *r, int64_t n, uint64_t *hi, uint64_t *lo, uint32_t *idx) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

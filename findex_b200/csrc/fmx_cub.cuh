@@ -21,6 +21,8 @@ cudaError_t sort_pairs_u8_u32(const uint8_t *k_in, uint8_t *k_out, const uint32_
 // ascending sort inside each segment; offsets has nseg+1 int64 entries
 cudaError_t segmented_sort_u32(const uint32_t *k_in, uint32_t *k_out, int64_t n, int64_t nseg, const int64_t *d_off,
                                cudaStream_t st);
+// plain ascending sort (one segment of any size)
+cudaError_t radix_sort_u32(const uint32_t *k_in, uint32_t *k_out, int64_t n, cudaStream_t st);
 cudaError_t widen_u32_i64(const uint32_t *d_in, int64_t *d_out, int64_t n, cudaStream_t st);
 // sort regex results by (regex, len, sp, ep); d_tmp is scratch of the same size
 cudaError_t sort_regex_results(RegexResult *d_res, RegexResult *d_tmp, int64_t n, cudaStream_t st);

@@ -6,8 +6,7 @@
 //      occ           : NaiveFMSearcher.occ          bwtmerger.scala:354-375
 //      lf/prev_substr: getPrevI / prevSubstr        bwtmerger.scala:386-389, 409-419
 //   K2 locate        : sa[] of bwtFm2sa             util.scala:213-224, via sampled rows + LF walk
-//   K3 regex         : ReTree._matchSA              re2/retree.scala:618-653 (also REParser.matchSA, DFA.matchSA): the whole
-//                      breadth-first traversal in one cooperative launch, grid barrier between levels
+//   K3 regex         : ReTree._matchSA              re2/retree.scala:618-653 — fmx_regex_kernel.cu
 //   K4 gather bench  : the random-64-B-gather roofline denominator
 //
 // All of them are bound by the rate of random HBM requests: G (1, 2 or 4) lanes cooperate on one
@@ -15,8 +14,6 @@
 // fetched together (two independent loads in flight per lane) and share the fetch when they fall into the
 // same block.  Nothing here is GEMM-shaped, so no tensor-core path exists by design.
 #include "fmx_kernels.cuh"
-
-#include <cooperative_groups.h>
 
 #include <algorithm>
 
@@ -270,17 +267,18 @@ next_substr_kernel(const __grid_constant__ DevIndex ix, const long long *__restr
 // =====================================================================================================
 template <int G, int LAYOUT>
 __global__ void __launch_bounds__(kThreads)
-locate_kernel(const __grid_constant__ DevIndex ix, const long long *__restrict__ sp, const long long *__restrict__ off,
-              long long m, long long total, uint32_t *__restrict__ pos) {
+locate_kernel(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ sp, const long long *__restrict__ off,
+              long long q0, long long q1, long long t0, long long count, uint32_t *__restrict__ pos, unsigned long long *steps_out) {
     __shared__ SharedTables tb;
     load_tables(tb, ix);
     __syncthreads();
-    const long long t = (long long)blockIdx.x * (kThreads / G) + threadIdx.x / G;
-    if (t >= total) return;
-    // owning query: last q with off[q] <= t
-    long long lo = 0, hi = m;
-    while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (off[mid] <= t) lo = mid; else hi = mid; }
-    uint32_t r = (uint32_t)(sp[lo] + (t - off[lo]));
+    const long long t = (long long)blockIdx.x * (kThreads / G) + threadIdx.x / G;      // slab-local occurrence
+    if (t >= count) return;
+    const long long T = t0 + t;                                                          // its place in the whole batch
+    // owning query: last q in [q0, q1) with off[q] <= T (queries without occurrences share their offset with the next one)
+    long long lo = q0, hi = q1;
+    while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (off[mid] <= T) lo = mid; else hi = mid; }
+    uint32_t r = sp[lo] + (uint32_t)(T - off[lo]);
     if (ix.sa != nullptr) {                                    // full suffix array resident: one load per occurrence
         if ((threadIdx.x % G) == 0) pos[t] = ix.sa[r];
         return;
@@ -292,7 +290,7 @@ locate_kernel(const __grid_constant__ DevIndex ix, const long long *__restrict__
             walk_block<G>(ix.bm, r, c, marked);
             if (marked) {
                 const uint32_t mr = rank_one<G>(ix.mark, r, nullptr);
-                if ((threadIdx.x % G) == 0) pos[t] = ix.samples[mr] + k;
+                if ((threadIdx.x % G) == 0) { pos[t] = ix.samples[mr] + k; if (steps_out) atomicAdd(steps_out, (unsigned long long)k); }
                 return;
             }
             r = lf_value<G, LAYOUT>(ix, tb, c, r);
@@ -303,7 +301,7 @@ locate_kernel(const __grid_constant__ DevIndex ix, const long long *__restrict__
         uint32_t bit;
         const uint32_t mr = rank_one<G>(ix.mark, r, &bit);
         if (bit) {                                         // row eof (sa = 0) is always sampled, so '$' is never stepped over
-            if ((threadIdx.x % G) == 0) pos[t] = ix.samples[mr] + k;
+            if ((threadIdx.x % G) == 0) { pos[t] = ix.samples[mr] + k; if (steps_out) atomicAdd(steps_out, (unsigned long long)k); }
             return;
         }
         r = lf_value<G, LAYOUT>(ix, tb, ix.bwt[r], r);
@@ -311,159 +309,60 @@ locate_kernel(const __grid_constant__ DevIndex ix, const long long *__restrict__
     }
 }
 
-// =====================================================================================================
-// K3: regex — breadth-first traversal of the position automata over SA intervals (ReTree._matchSA, retree.scala:618-653)
-// =====================================================================================================
-// One frontier item: backward step with the item's character, then emission of a match and/or of the follow positions.
-// Called by whole warps (inactive groups pass alive = false): matches and expansions are appended with one atomic per warp.
-// counters[0] += items appended to `out`, counters[1] += matches appended to `res`; both keep counting past the capacities
-// (writes are dropped) so the host can size a retry.
-template <int G, int LAYOUT>
-__device__ __forceinline__ void regex_expand(const DevIndex &ix, const SharedTables &tb, const RegexTables &rt, const FrontierItem *in,
-                                             long long t, bool alive, FrontierItem *__restrict__ out, long long cap_out,
-                                             RegexResult *__restrict__ res, long long cap_res, unsigned long long *c_out,
-                                             unsigned long long *c_res) {
-    const bool leader = (threadIdx.x % G) == 0;
-    const uint32_t lane = threadIdx.x & 31;
-    FrontierItem it = {0, 0, 0, 0};
-    if (alive) {
-        // frontier buffers are rewritten by other SMs from level to level inside one launch: read them past the (non-coherent) L1
-        const uint4 raw = __ldcg(reinterpret_cast<const uint4 *>(in + t));
-        it = FrontierItem{raw.x, raw.y, raw.z, raw.w};
-        uint32_t touched = 0;
-        backward_step<G, LAYOUT, false>(ix, tb, rt.st_c[it.state], it.sp, it.ep, touched);   // getPrevRange
-        alive = it.sp < it.ep;
-    }
-    // state flags: bit0 = emits a result, bit1 = stop after emitting (Glushkov last position; a Thompson position goes on)
-    const uint32_t flg = alive ? rt.st_last[it.state] : 0u;
-    const bool last = (flg & 1u) != 0;
-    const bool stop = last && (flg & 2u);
-    const uint32_t f0 = alive ? rt.fol_off[it.state] : 0u;
-    const uint32_t nf = (alive && !stop && leader) ? (rt.fol_off[it.state + 1] - f0) : 0u;
-    // matches: ballot + one atomic per warp
-    const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, last && leader);
-    if (mmask) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(c_res, (unsigned long long)__popc(mmask));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (last && leader) {
-            const unsigned long long idx = base + __popc(mmask & ((1u << lane) - 1u));
-            if (idx < (unsigned long long)cap_res) res[idx] = RegexResult{rt.st_regex[it.state], it.len + 1, it.sp, it.ep};
-        }
-    }
-    // expansions.  Short follow lists: exclusive prefix sum of their lengths over the warp, one atomic per warp, written by their owners.
-    // Longer lists (alternations, character classes, '.') are handled by the whole warp, one parent at a time, and filtered: a follow
-    // position with character c survives its backward step iff c occurs in BWT[sp..ep) (its new interval has rank_c(ep) - rank_c(sp) rows),
-    // so for a narrow interval only the positions whose character is actually there are appended — identical results, and a '.' after a
-    // one-row interval costs one item instead of 253.
-    constexpr uint32_t kWide = 4, kFilterRows = 32;
-    const bool is_wide = nf >= kWide;
-    const uint32_t nn = is_wide ? 0u : nf;
-    uint32_t incl = nn;
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
-    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    uint32_t wide = __ballot_sync(0xFFFFFFFFu, is_wide);
-    if (total) {                                            // warp-uniform
-        unsigned long long wbase = 0;
-        if (lane == 0) wbase = atomicAdd(c_out, (unsigned long long)total);
-        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-        const unsigned long long my = wbase + (incl - nn);
-        for (uint32_t j = 0; j < nn; ++j) {
-            const unsigned long long idx = my + j;
-            if (idx < (unsigned long long)cap_out) out[idx] = FrontierItem{rt.fol[f0 + j], it.len + 1, it.sp, it.ep};
-        }
-    }
-    while (wide) {
-        const int src = __ffs(wide) - 1;
-        wide &= wide - 1;
-        const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, nf, src);
-        const uint32_t fs = __shfl_sync(0xFFFFFFFFu, f0, src);
-        const uint32_t ln = __shfl_sync(0xFFFFFFFFu, it.len, src) + 1;
-        const uint32_t a = __shfl_sync(0xFFFFFFFFu, it.sp, src), e = __shfl_sync(0xFFFFFFFFu, it.ep, src);
-        const bool filt = (e - a) <= kFilterRows;
-        uint32_t present = 0;                               // lane w (0..7) holds bits 32w..32w+31 of the set of bytes in BWT[a..e)
-        if (filt) {
-            const bool has = lane < (e - a);
-            const uint32_t c = has ? (uint32_t)ix.bwt[a + lane] : 0u;
+// 2-bit symbol codes -> pattern bytes: thread t writes four consecutive bytes of one pattern (its packed byte t % ceil(len/4))
+__global__ void unpack2_kernel(const uint8_t *__restrict__ codes, int len, long long m, uint32_t alpha4, uint8_t *__restrict__ out) {
+    const int pb = (len + 3) >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * pb) return;
+    const long long q = t / pb;
+    const int b = (int)(t - q * pb);
+    const uint32_t c = codes[t];
+    uint8_t *dst = out + q * len + 4 * b;
 #pragma unroll
-            for (uint32_t w = 0; w < 8; ++w) {
-                const uint32_t r = __reduce_or_sync(0xFFFFFFFFu, (has && (c >> 5) == w) ? (1u << (c & 31u)) : 0u);
-                if (lane == w) present = r;
-            }
-        }
-        uint32_t kept_total = cnt;
-        if (filt) {
-            kept_total = 0;
-            for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
-                const uint32_t j = j0 + lane;
-                const uint32_t ch = j < cnt ? (uint32_t)rt.st_c[rt.fol[fs + j]] : 0u;
-                const uint32_t word = __shfl_sync(0xFFFFFFFFu, present, ch >> 5);
-                kept_total += __popc(__ballot_sync(0xFFFFFFFFu, j < cnt && ((word >> (ch & 31u)) & 1u)));
-            }
-        }
-        if (kept_total == 0) continue;                      // warp-uniform
-        unsigned long long b = 0;
-        if (lane == 0) b = atomicAdd(c_out, (unsigned long long)kept_total);
-        b = __shfl_sync(0xFFFFFFFFu, b, 0);
-        for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            const uint32_t fstate = j < cnt ? rt.fol[fs + j] : 0u;
-            bool keep = j < cnt;
-            if (filt) {
-                const uint32_t ch = j < cnt ? (uint32_t)rt.st_c[fstate] : 0u;
-                const uint32_t word = __shfl_sync(0xFFFFFFFFu, present, ch >> 5);
-                keep = keep && ((word >> (ch & 31u)) & 1u);
-            }
-            const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
-            if (keep) {
-                const unsigned long long idx = b + __popc(km & ((1u << lane) - 1u));
-                if (idx < (unsigned long long)cap_out) out[idx] = FrontierItem{fstate, ln, a, e};
-            }
-            b += __popc(km);
-        }
-    }
+    for (int j = 0; j < 4; ++j)
+        if (4 * b + j < len) dst[j] = (uint8_t)(alpha4 >> (8 * ((c >> (2 * j)) & 3u)));
+}
+cudaError_t launch_unpack2(const uint8_t *d_codes, int len, int64_t m, uint32_t alpha4, uint8_t *d_out, cudaStream_t st) {
+    const int64_t total = m * ((len + 3) / 4);
+    if (total > 0) unpack2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_codes, len, m, alpha4, d_out);
+    return cudaGetLastError();
 }
 
-// The whole traversal in ONE cooperative launch: a persistent grid (one wave of CTAs) walks the levels, separated by grid-wide
-// barriers, ping-ponging between two frontier buffers.  ctrl: [0..2] = frontier counters rotating over the levels (level L reads
-// [L%3], appends to [(L+1)%3], clears [(L+2)%3]), [3] = matches, [4] = status (0 ok, 1 = a frontier outgrew its buffer: [5] = the
-// size it wanted, the host regrows and reruns; 2 = deeper than the text), [6] = levels run, [7] = largest frontier.
-template <int G, int LAYOUT>
-__global__ void __launch_bounds__(kThreads)
-regex_search_kernel(const __grid_constant__ DevIndex ix, RegexTables rt, const uint32_t *__restrict__ first, long long n_first,
-                    FrontierItem *buf_a, FrontierItem *buf_b, long long cap, RegexResult *__restrict__ res, long long cap_res,
-                    unsigned long long *ctrl, long long max_levels) {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
-    __shared__ SharedTables tb;
-    load_tables(tb, ix);
-    constexpr int QPB = kThreads / G;
-    // level 0 frontier: StatePoint(0, 0, sa.n, state) for every first position  (retree.scala:576)
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n_first; i += (long long)gridDim.x * kThreads)
-        buf_a[i] = FrontierItem{first[i], 0u, 0u, ix.n};
-    if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl[0] = (unsigned long long)n_first; ctrl[1] = 0; ctrl[2] = 0; }
-    __syncthreads();
-    grid.sync();
-    FrontierItem *cur = buf_a, *nxt = buf_b;
-    for (long long level = 0;; ++level) {
-        const long long n_in = (long long)*reinterpret_cast<volatile unsigned long long *>(&ctrl[level % 3]);
-        if (n_in == 0) break;                               // grid-uniform: every thread reads the same counter after the barrier
-        if (n_in > cap || level >= max_levels) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl[4] = n_in > cap ? 1ull : 2ull; ctrl[5] = (unsigned long long)n_in; }
-            break;
+// occurrences per query (0 for an empty interval), as the scan input of the locate offsets; element m is 0
+__global__ void interval_len_kernel(const uint32_t *__restrict__ sp, const uint32_t *__restrict__ ep, long long m, long long *__restrict__ out) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > m) return;
+    out[q] = (q < m && ep[q] > sp[q]) ? (long long)(ep[q] - sp[q]) : 0ll;
+}
+cudaError_t launch_interval_len(const uint32_t *d_sp, const uint32_t *d_ep, int64_t m, int64_t *d_out, cudaStream_t st) {
+    interval_len_kernel<<<(unsigned)((m + 1 + 255) / 256), 256, 0, st>>>(d_sp, d_ep, m, (long long *)d_out);
+    return cudaGetLastError();
+}
+
+// Exchange step of the variable-length results (located positions, regex triples): this rank's slab of `count` 4-byte words goes
+// straight into every rank's gathered buffer (peer-mapped memory over NVLink/NVSwitch) at word offset *d_dst_off — the scanned
+// offset of this rank's first result, read on the device so no host round trip sits between the scan and the stores.
+__global__ void __launch_bounds__(256)
+scatter_words_kernel(const uint32_t *__restrict__ src, long long count, const __grid_constant__ PeerSinks sinks, const long long *__restrict__ d_dst_off,
+                     long long dst_scale) {
+    const long long dst0 = sinks.offset + (d_dst_off ? *d_dst_off * dst_scale : 0ll);
+    const long long stride = (long long)gridDim.x * blockDim.x, tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)(dst0 * 4)) & 15) == 0) {       // 16-byte pieces (peer buffers are cudaMalloc-aligned)
+        const long long nv = count >> 2;
+        for (long long i = tid; i < nv; i += stride) {
+            const uint4 v = reinterpret_cast<const uint4 *>(src)[i];
+            for (int j = 0; j < sinks.n; ++j) reinterpret_cast<uint4 *>(sinks.p[j] + dst0)[i] = v;
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            ctrl[(level + 2) % 3] = 0;
-            ctrl[6] = (unsigned long long)(level + 1);
-            if ((unsigned long long)n_in > ctrl[7]) ctrl[7] = (unsigned long long)n_in;
-        }
-        for (long long t0 = (long long)blockIdx.x * QPB; t0 < n_in; t0 += (long long)gridDim.x * QPB) {   // CTA-uniform trip count
-            const long long t = t0 + threadIdx.x / G;
-            regex_expand<G, LAYOUT>(ix, tb, rt, cur, t, t < n_in, nxt, cap, res, cap_res, &ctrl[(level + 1) % 3], &ctrl[3]);
-        }
-        grid.sync();
-        FrontierItem *tmp = cur; cur = nxt; nxt = tmp;
+        for (long long i = (nv << 2) + tid; i < count; i += stride) { const uint32_t v = src[i]; for (int j = 0; j < sinks.n; ++j) sinks.p[j][dst0 + i] = v; }
+    } else {
+        for (long long i = tid; i < count; i += stride) { const uint32_t v = src[i]; for (int j = 0; j < sinks.n; ++j) sinks.p[j][dst0 + i] = v; }
     }
+}
+cudaError_t launch_scatter_words(const uint32_t *d_src, int64_t count, const PeerSinks &sinks, const int64_t *d_dst_off, int64_t dst_scale, cudaStream_t st) {
+    if (count <= 0 || sinks.n <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<int64_t>((count / 4 + 255) / 256 + 1, 148 * 8);
+    scatter_words_kernel<<<grid, 256, 0, st>>>(d_src, count, sinks, (const long long *)d_dst_off, dst_scale);
+    return cudaGetLastError();
 }
 
 // =====================================================================================================
@@ -629,38 +528,13 @@ cudaError_t launch_next_substr(const DevIndex &ix, LaunchCfg cfg, const int64_t 
     return cudaGetLastError();
 }
 
-cudaError_t launch_locate(const DevIndex &ix, LaunchCfg cfg, const int64_t *d_sp, const int64_t *d_off, int64_t m,
-                          int64_t total, int sample_rate, uint32_t *d_pos, cudaStream_t st) {
-    (void)sample_rate;
-    if (total <= 0) return cudaSuccess;
-#define CALL(G, LAY) locate_kernel<G, LAY><<<grid_for(total, G), kThreads, 0, st>>>(ix, (const long long *)d_sp, (const long long *)d_off, m, total, d_pos)
+cudaError_t launch_locate(const DevIndex &ix, LaunchCfg cfg, const uint32_t *d_sp, const int64_t *d_off, int64_t q0, int64_t q1,
+                          int64_t t0, int64_t count, uint32_t *d_pos, unsigned long long *d_steps, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+#define CALL(G, LAY) locate_kernel<G, LAY><<<grid_for(count, G), kThreads, 0, st>>>(ix, d_sp, (const long long *)d_off, q0, q1, t0, count, d_pos, d_steps)
     FMX_DISPATCH(cfg, CALL);
 #undef CALL
     return cudaGetLastError();
-}
-
-cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, RegexTables rt, const uint32_t *d_first, int64_t n_first,
-                                FrontierItem *d_a, FrontierItem *d_b, int64_t cap, RegexResult *d_res, int64_t cap_res,
-                                unsigned long long *d_ctrl, int64_t max_levels, cudaStream_t st) {
-    if (n_first <= 0) return cudaSuccess;
-    int dev = 0, sms = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long nf = n_first, cp = cap, cr = cap_res, ml = max_levels;
-    void *args[] = {(void *)&ix, (void *)&rt, (void *)&d_first, (void *)&nf, (void *)&d_a, (void *)&d_b, (void *)&cp, (void *)&d_res, (void *)&cr,
-                    (void *)&d_ctrl, (void *)&ml};
-#define CALL(G, LAY)                                                                                                  \
-    {                                                                                                                 \
-        auto k = regex_search_kernel<G, LAY>;                                                                         \
-        int per_sm = 0;                                                                                               \
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0);                                   \
-        if (e == cudaSuccess) e = per_sm > 0 ? cudaLaunchCooperativeKernel((void *)k, dim3((unsigned)(sms * per_sm)), dim3(kThreads), args, 0, st) \
-                                              : cudaErrorLaunchOutOfResources;                                       \
-    }
-    FMX_DISPATCH(cfg, CALL);
-#undef CALL
-    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_gather_bench(const uint4 *base, uint64_t n_blocks64, int bytes, int lanes, int64_t gathers, int chain,

@@ -44,26 +44,39 @@ cudaError_t launch_next_substr(const DevIndex &ix, LaunchCfg cfg, const int64_t 
 // prevSubstr: len LF steps per row, emitting the BWT byte at each visited row
 cudaError_t launch_prev_substr(const DevIndex &ix, LaunchCfg cfg, const int64_t *d_row, int64_t m, int len,
                                uint8_t *d_out, cudaStream_t st);
-// locate: one work item per occurrence; d_off[m+1] exclusive offsets, writes unsorted sa values
-cudaError_t launch_locate(const DevIndex &ix, LaunchCfg cfg, const int64_t *d_sp, const int64_t *d_off, int64_t m,
-                          int64_t total, int sample_rate, uint32_t *d_pos, cudaStream_t st);
+// locate: one work item per occurrence of the queries [q0, q1) — occurrences [t0, t0 + count) of the batch, d_off[m+1] = exclusive
+// offsets over the whole batch; writes the unsorted sa values of the slab to d_pos[0 .. count)
+cudaError_t launch_locate(const DevIndex &ix, LaunchCfg cfg, const uint32_t *d_sp, const int64_t *d_off, int64_t q0, int64_t q1,
+                          int64_t t0, int64_t count, uint32_t *d_pos, unsigned long long *d_steps_or_null, cudaStream_t st);
+// m patterns of `len` 2-bit codes ((len+3)/4 bytes each) -> m x len bytes; alpha4 = the four symbols, symbol i in byte i
+cudaError_t launch_unpack2(const uint8_t *d_codes, int len, int64_t m, uint32_t alpha4, uint8_t *d_out, cudaStream_t st);
+// d_out[q] = ep[q] - sp[q] (0 when empty) for q < m, d_out[m] = 0
+cudaError_t launch_interval_len(const uint32_t *d_sp, const uint32_t *d_ep, int64_t m, int64_t *d_out, cudaStream_t st);
+// copies `count` 4-byte words to every sink at word offset sinks.offset + (*d_dst_off) * dst_scale (d_dst_off may be null)
+cudaError_t launch_scatter_words(const uint32_t *d_src, int64_t count, const PeerSinks &sinks, const int64_t *d_dst_off, int64_t dst_scale, cudaStream_t st);
 
-// regex frontier
+// regex traversal (fmx_regex_kernel.cu)
 struct RegexTables {
-    const uint8_t  *st_c;        // per global state
-    const uint8_t  *st_last;
+    const uint4    *rec;         // per global state: { c | flags << 8, first index into fol, number of follows, first follow state };
+                                 // flags bit0 = emits a result, bit1 = stops after emitting (Glushkov last position)
     const uint32_t *st_regex;    // owning regex index in the batch
-    const uint32_t *fol_off;     // CSR over global states
-    const uint32_t *fol;         // global state ids
+    const uint32_t *fol;         // follow lists, global state ids
 };
-struct FrontierItem { uint32_t state, len, sp, ep; };
+struct FrontierItem { uint32_t state, len, sp, ep; };   // a ring slot; state 0xFFFFFFFF = empty
 struct RegexResult  { uint32_t regex, len, sp, ep; };
-// the whole traversal in one cooperative launch (persistent grid, grid-wide barrier between levels).  d_ctrl: 8 x u64, zeroed by the caller:
-// [3] = matches found (may exceed cap_res: writes are dropped, the count keeps growing), [4] = status (0 ok; 1 = a frontier of [5] items
-// outgrew `cap`: regrow and rerun; 2 = more than max_levels levels), [6] = levels run.
-cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, RegexTables rt, const uint32_t *d_first, int64_t n_first,
-                                FrontierItem *d_a, FrontierItem *d_b, int64_t cap, RegexResult *d_res, int64_t cap_res,
-                                unsigned long long *d_ctrl, int64_t max_levels, cudaStream_t st);
+// control words of one traversal (8 x u64 on the device, initialised by the seed kernel)
+enum { kRxHead = 0, kRxTail = 1, kRxPending = 2, kRxMatches = 3, kRxStatus = 4, kRxDone = 5, kRxMaxLen = 6, kRxSteps = 7 };
+// The whole traversal: seed kernel + one persistent work-queue kernel.  d_ring: ring_cap (power of two, >= n_first) slots, every state word
+// 0xFFFFFFFF on entry and again on a clean exit.  d_ctrl[kRxMatches] = matches found (may exceed cap_res: writes are dropped, the count
+// keeps growing), [kRxStatus] = 0 ok, 1 = the ring was too small (rerun with a larger, re-emptied ring), 2 = an item grew longer than the
+// text, [kRxMaxLen] = longest item, [kRxSteps] = items processed (one backward step each).
+cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, const RegexTables &rt, const uint32_t *d_first, int64_t n_first,
+                                FrontierItem *d_ring, int64_t ring_cap, RegexResult *d_res, int64_t cap_res, unsigned long long *d_ctrl,
+                                cudaStream_t st);
+constexpr int64_t kSmallSort = 4096;                    // results ordered by one CTA in shared memory up to here
+cudaError_t sort_results_small(RegexResult *d_res, int64_t n, cudaStream_t st);
+cudaError_t launch_result_offsets(const RegexResult *d_res, int64_t n, int64_t m, int64_t *d_off, cudaStream_t st);
+cudaError_t launch_split_results(const RegexResult *d_res, int64_t n, int32_t *d_len, int64_t *d_sp, int64_t *d_ep, cudaStream_t st);
 
 // K4 random gather microbenchmark
 cudaError_t launch_gather_bench(const uint4 *base, uint64_t n_blocks64, int bytes_per_gather, int lanes, int64_t gathers,

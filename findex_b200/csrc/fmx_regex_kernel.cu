@@ -1,0 +1,348 @@
+// fmx_regex_kernel.cu — K3: traversal of the position automata over SA intervals.
+//
+//   ReTree._matchSA      re2/retree.scala:618-653   (StatePoint :562-567, start items :576)
+//   REParser.matchSA     re2/re2.scala:568-693      (Thompson positions: emit and go on)
+//   DFA.matchSA          dfa.scala:261-289
+//
+// The reference pops (len, sp, ep, state) items from a priority queue, takes one getPrevRange step (findex.scala:32-36) with the
+// state's character and either emits a result or pushes the state's follow positions.  With the caps off the result is a multiset
+// that does not depend on the order in which items are taken, so nothing here is level-synchronous:
+//
+//   * a persistent grid of workers (G lanes per item) owns a global RING of items in HBM.  Consumers take tickets from `head` with one
+//     warp-aggregated atomic and wait for their slot to be filled; producers reserve tickets from `tail` the same way, write the
+//     payload and publish it with a release exchange on the slot's state word (an occupied slot = the ring is too small: the run is
+//     abandoned and the host reruns it with a larger ring).  `pending` counts live items; the worker that brings it to zero raises `done`.
+//   * depth first where it is free: an item whose state has 1..3 follow positions goes on with the first one in its own registers
+//     (a literal run never touches the ring) and pushes only the others; the per-state record (character, flags, follow list) is one
+//     16-byte load, and the record of the first follow is fetched together with the rank blocks of the step.
+//   * wide follow lists (classes, '.', big alternations) are expanded by the whole warp, one parent at a time, and filtered: a follow
+//     position with character c survives its backward step iff c occurs in BWT[sp..ep), so for an interval of <= 32 rows only the
+//     positions whose character is there are pushed — identical results, and a '.' after a one-row interval costs 1 item, not 253.
+//   * matches are appended to the result array with one atomic per warp; the caller sorts them by (regex, len, sp, ep).
+//
+// There is no grid barrier and no cooperative launch; a lane that runs out of work refills from the ring while its neighbours go on.
+#include "fmx_kernels.cuh"
+
+#include <algorithm>
+
+namespace fmx {
+
+namespace {
+
+constexpr uint32_t kSlotEmpty = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t exch_release(uint32_t *p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.release.gpu.global.exch.b32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint4 ld_cg(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// publish one item at ticket `t`: payload first, then the state word with release semantics.  Returns false if the slot still held
+// an item nobody has read (ring too small).
+__device__ __forceinline__ bool ring_publish(FrontierItem *ring, unsigned long long mask, unsigned long long t, uint32_t state, uint32_t len,
+                                             uint32_t sp, uint32_t ep) {
+    FrontierItem *s = ring + (t & mask);
+    s->len = len; s->sp = sp; s->ep = ep;
+    return exch_release(&s->state, state) == kSlotEmpty;
+}
+
+}  // namespace
+
+// ctrl (8 x u64, zeroed by the caller): see RegexCtrl in fmx_kernels.cuh
+__global__ void regex_seed_kernel(const uint32_t *__restrict__ first, long long n_first, uint32_t n, FrontierItem *ring, unsigned long long *ctrl) {
+    // level-0 items: StatePoint(0, 0, sa.n, state) for every first position  (retree.scala:576)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_first; i += (long long)gridDim.x * blockDim.x)
+        ring[i] = FrontierItem{first[i], 0u, 0u, n};
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctrl[kRxHead] = 0; ctrl[kRxTail] = (unsigned long long)n_first; ctrl[kRxPending] = (unsigned long long)n_first;
+        ctrl[kRxMatches] = 0; ctrl[kRxStatus] = 0; ctrl[kRxDone] = n_first == 0 ? 1ull : 0ull; ctrl[kRxMaxLen] = 0; ctrl[kRxSteps] = 0;
+    }
+}
+
+template <int G, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ RegexTables rt, FrontierItem *ring, unsigned long long ring_mask,
+                   RegexResult *__restrict__ res, long long cap_res, unsigned long long *ctrl) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    const bool leader = (threadIdx.x % G) == 0;
+    const int lead_lane = (int)(lane & ~(uint32_t)(G - 1));
+    constexpr uint32_t kWide = 4, kFilterRows = 32;
+    constexpr unsigned long long kNoTicket = ~0ull;
+
+    bool have = false, have_rec = false;                   // an item in registers / its state record already loaded
+    unsigned long long ticket = kNoTicket;
+    FrontierItem it = {0, 0, 0, 0};
+    uint4 rec = {0, 0, 0, 0};
+    uint32_t max_len = 0, idle_rounds = 0, nsteps = 0;
+    bool ring_ok = true;
+
+    for (;;) {
+        // ---- refill: groups without an item take a ticket (one atomic per warp) and look at their slot
+        const uint32_t want = __ballot_sync(0xFFFFFFFFu, leader && !have && ticket == kNoTicket);
+        if (want) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&ctrl[kRxHead], (unsigned long long)__popc(want));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (leader && !have && ticket == kNoTicket) ticket = base + __popc(want & ((1u << lane) - 1u));
+        }
+        if (leader && !have && ticket != kNoTicket) {
+            FrontierItem *s = ring + (ticket & ring_mask);
+            const uint32_t st = ld_acquire(&s->state);
+            if (st != kSlotEmpty) {
+                const uint4 raw = ld_cg(reinterpret_cast<const uint4 *>(s));
+                it = FrontierItem{st, raw.y, raw.z, raw.w};
+                st_release(&s->state, kSlotEmpty);         // the slot may be written again (after this rank's reads of it)
+                have = true;
+                have_rec = false;
+                ticket = kNoTicket;
+            }
+        }
+        if (G > 1) {                                       // the group works on its leader's item
+            have = __shfl_sync(0xFFFFFFFFu, (int)have, lead_lane) != 0;
+            it.state = __shfl_sync(0xFFFFFFFFu, it.state, lead_lane); it.len = __shfl_sync(0xFFFFFFFFu, it.len, lead_lane);
+            it.sp = __shfl_sync(0xFFFFFFFFu, it.sp, lead_lane); it.ep = __shfl_sync(0xFFFFFFFFu, it.ep, lead_lane);
+            have_rec = __shfl_sync(0xFFFFFFFFu, (int)have_rec, lead_lane) != 0;
+        }
+        if (!__any_sync(0xFFFFFFFFu, have)) {              // nothing to do in this warp: done, or wait for producers
+            if (ld_volatile_u64(&ctrl[kRxDone]) != 0) break;
+            if (++idle_rounds > 4) __nanosleep(idle_rounds > 64 ? 400 : 100);
+            continue;
+        }
+        idle_rounds = 0;
+
+        // ---- one backward step per item: getPrevRange(sp, ep, c)
+        if (have && !have_rec) rec = ldg128(rt.rec + it.state);
+        const uint32_t c = rec.x & 0xFFu, flags = (rec.x >> 8) & 0xFFu, fo = rec.y, nf_all = rec.z, f0 = rec.w;
+        uint4 nrec = {0, 0, 0, 0};
+        if (have && nf_all >= 1 && nf_all < kWide) nrec = ldg128(rt.rec + f0);      // in flight together with the rank blocks
+        bool alive = have;
+        if (have && leader) ++nsteps;
+        if (have) {
+            uint32_t touched = 0;
+            backward_step<G, LAYOUT, false>(ix, tb, c, it.sp, it.ep, touched);
+            alive = it.sp < it.ep;
+        }
+        const uint32_t nlen = it.len + 1;
+        const bool emits = alive && (flags & 1u);
+        const bool stop = emits && (flags & 2u);            // Glushkov: a last position emits and is not expanded (retree.scala:640-643)
+        const bool too_deep = alive && nlen > ix.n;         // cannot happen for a match inside the text; guards runaway automata
+        const uint32_t nf = (alive && !stop && !too_deep) ? nf_all : 0u;
+        if (too_deep && leader) atomicMax(&ctrl[kRxStatus], 2ull);
+        if (alive && nlen > max_len) max_len = nlen;
+
+        // matches: ballot + one atomic per warp
+        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, emits && leader);
+        if (mm) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&ctrl[kRxMatches], (unsigned long long)__popc(mm));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (emits && leader) {
+                const unsigned long long idx = base + __popc(mm & ((1u << lane) - 1u));
+                if (idx < (unsigned long long)cap_res) res[idx] = RegexResult{rt.st_regex[it.state], nlen, it.sp, it.ep};
+            }
+        }
+
+        // ---- wide follow lists: the whole warp expands one parent at a time, filtered by the bytes present in BWT[sp..ep)
+        uint32_t wide = __ballot_sync(0xFFFFFFFFu, leader && nf >= kWide);
+        while (wide) {
+            const int src = __ffs(wide) - 1;
+            wide &= wide - 1;
+            const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, nf, src), fs = __shfl_sync(0xFFFFFFFFu, fo, src);
+            const uint32_t a = __shfl_sync(0xFFFFFFFFu, it.sp, src), e = __shfl_sync(0xFFFFFFFFu, it.ep, src), ln = __shfl_sync(0xFFFFFFFFu, nlen, src);
+            const bool filt = (e - a) <= kFilterRows;
+            uint32_t present = 0;                           // lane w (0..7) holds bits 32w..32w+31 of the set of bytes in BWT[a..e)
+            if (filt) {
+                const bool has = lane < (e - a);
+                const uint32_t ch = has ? (uint32_t)ix.bwt[a + lane] : 0u;
+#pragma unroll
+                for (uint32_t w = 0; w < 8; ++w) {
+                    const uint32_t r = __reduce_or_sync(0xFFFFFFFFu, (has && (ch >> 5) == w) ? (1u << (ch & 31u)) : 0u);
+                    if (lane == w) present = r;
+                }
+            }
+            uint32_t kept_total = cnt;
+            if (filt) {
+                kept_total = 0;
+                for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+                    const uint32_t j = j0 + lane;
+                    const uint32_t ch = j < cnt ? (ldg128(rt.rec + rt.fol[fs + j]).x & 0xFFu) : 0u;
+                    const uint32_t word = __shfl_sync(0xFFFFFFFFu, present, ch >> 5);
+                    kept_total += __popc(__ballot_sync(0xFFFFFFFFu, j < cnt && ((word >> (ch & 31u)) & 1u)));
+                }
+            }
+            if (kept_total == 0) continue;                  // warp-uniform
+            unsigned long long b = 0;
+            if (lane == 0) {                                // children are counted before they can be seen
+                atomicAdd(&ctrl[kRxPending], (unsigned long long)kept_total);
+                b = atomicAdd(&ctrl[kRxTail], (unsigned long long)kept_total);
+            }
+            b = __shfl_sync(0xFFFFFFFFu, b, 0);
+            for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                const uint32_t fstate = j < cnt ? rt.fol[fs + j] : 0u;
+                bool keep = j < cnt;
+                if (filt) {
+                    const uint32_t ch = j < cnt ? (ldg128(rt.rec + fstate).x & 0xFFu) : 0u;
+                    const uint32_t word = __shfl_sync(0xFFFFFFFFu, present, ch >> 5);
+                    keep = keep && ((word >> (ch & 31u)) & 1u);
+                }
+                const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+                if (keep) ring_ok = ring_publish(ring, ring_mask, b + __popc(km & ((1u << lane) - 1u)), fstate, ln, a, e) && ring_ok;
+                b += __popc(km);
+            }
+        }
+
+        // ---- short follow lists: go on with the first follow in registers, push the others; account for finished items
+        const bool narrow = leader && nf >= 1 && nf < kWide;
+        const uint32_t np = narrow ? nf - 1 : 0u;            // items this group pushes
+        uint32_t incl = np;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+        const uint32_t pushes = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const uint32_t finished = __popc(__ballot_sync(0xFFFFFFFFu, leader && have && !(nf >= 1 && nf < kWide)));
+        unsigned long long tbase = 0;
+        if (lane == 0) {
+            if (pushes != finished) {
+                const long long delta = (long long)pushes - (long long)finished;
+                const unsigned long long old = atomicAdd(&ctrl[kRxPending], (unsigned long long)delta);
+                if (old + (unsigned long long)delta == 0ull) atomicExch(&ctrl[kRxDone], 1ull);      // the last live item just ended
+            }
+            if (pushes) tbase = atomicAdd(&ctrl[kRxTail], (unsigned long long)pushes);
+        }
+        if (pushes) {
+            tbase = __shfl_sync(0xFFFFFFFFu, tbase, 0);
+            const unsigned long long my = tbase + (incl - np);
+            for (uint32_t j = 0; j < np; ++j)
+                ring_ok = ring_publish(ring, ring_mask, my + j, rt.fol[fo + 1 + j], nlen, it.sp, it.ep) && ring_ok;
+        }
+        if (have) {
+            if (nf >= 1 && nf < kWide) { it.state = f0; it.len = nlen; rec = nrec; have_rec = true; }
+            else have = false;
+        }
+        if (!__all_sync(0xFFFFFFFFu, ring_ok)) {             // an unread slot was overwritten: abandon the run, the host regrows the ring
+            if (lane == 0) { atomicMax(&ctrl[kRxStatus], 1ull); atomicExch(&ctrl[kRxDone], 1ull); }
+            break;
+        }
+    }
+    for (int o = 16; o; o >>= 1) max_len = max(max_len, __shfl_xor_sync(0xFFFFFFFFu, max_len, o));
+    for (int o = 16; o; o >>= 1) nsteps += __shfl_xor_sync(0xFFFFFFFFu, nsteps, o);
+    if (lane == 0 && max_len) atomicMax(&ctrl[kRxMaxLen], (unsigned long long)max_len);
+    if (lane == 0 && nsteps) atomicAdd(&ctrl[kRxSteps], (unsigned long long)nsteps);       // backward steps taken = items processed
+}
+
+cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, const RegexTables &rt, const uint32_t *d_first, int64_t n_first,
+                                FrontierItem *d_ring, int64_t ring_cap, RegexResult *d_res, int64_t cap_res, unsigned long long *d_ctrl,
+                                cudaStream_t st) {
+    if (ring_cap < n_first || (ring_cap & (ring_cap - 1))) return cudaErrorInvalidValue;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    regex_seed_kernel<<<(unsigned)std::min<int64_t>((n_first + 255) / 256 + 1, sms * 8), 256, 0, st>>>(d_first, n_first, ix.n, d_ring, d_ctrl);
+    if (n_first <= 0) return cudaGetLastError();
+#define CALL(G, LAY)                                                                                                  \
+    {                                                                                                                 \
+        auto k = regex_queue_kernel<G, LAY>;                                                                          \
+        int per_sm = 0;                                                                                               \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0);                                   \
+        if (e == cudaSuccess) {                                                                                       \
+            if (per_sm <= 0) e = cudaErrorLaunchOutOfResources;                                                       \
+            else k<<<(unsigned)(sms * per_sm), kThreads, 0, st>>>(ix, rt, d_ring, (unsigned long long)(ring_cap - 1), d_res, cap_res, d_ctrl); \
+        }                                                                                                             \
+    }
+    if (cfg.layout == FMX_LAYOUT_PLANES) {
+        if (cfg.lanes == 1) { CALL(1, FMX_LAYOUT_PLANES); } else if (cfg.lanes == 2) { CALL(2, FMX_LAYOUT_PLANES); } else { CALL(4, FMX_LAYOUT_PLANES); }
+    } else {
+        if (cfg.lanes == 1) { CALL(1, FMX_LAYOUT_WM); } else if (cfg.lanes == 2) { CALL(2, FMX_LAYOUT_WM); } else { CALL(4, FMX_LAYOUT_WM); }
+    }
+#undef CALL
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+// ---- result ordering and per-regex offsets on the device -------------------------------------------------------------------------
+__device__ __forceinline__ bool res_less(const RegexResult &a, const RegexResult &b) {
+    if (a.regex != b.regex) return a.regex < b.regex;
+    if (a.len != b.len) return a.len < b.len;
+    if (a.sp != b.sp) return a.sp < b.sp;
+    return a.ep < b.ep;
+}
+
+// up to kSmallSort results: one CTA, bitonic network in shared memory (a handful of results does not pay for device-wide radix passes)
+__global__ void __launch_bounds__(1024)
+sort_results_small_kernel(RegexResult *res, int n) {
+    extern __shared__ __align__(16) uint8_t raw[];
+    RegexResult *s = reinterpret_cast<RegexResult *>(raw);
+    int p = 1;
+    while (p < n) p <<= 1;
+    for (int i = threadIdx.x; i < p; i += blockDim.x) s[i] = i < n ? res[i] : RegexResult{0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    __syncthreads();
+    for (int k = 2; k <= p; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < p; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const RegexResult x = s[i], y = s[l];
+                    if (res_less(y, x) == up) { s[i] = y; s[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) res[i] = s[i];
+}
+cudaError_t sort_results_small(RegexResult *d_res, int64_t n, cudaStream_t st) {
+    if (n <= 1) return cudaSuccess;
+    if (n > kSmallSort) return cudaErrorInvalidValue;
+    int p = 1;
+    while (p < n) p <<= 1;
+    const size_t smem = (size_t)p * sizeof(RegexResult);
+    cudaError_t e = cudaFuncSetAttribute(sort_results_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    sort_results_small_kernel<<<1, (unsigned)std::min<int>(1024, std::max(32, p / 2)), smem, st>>>(d_res, (int)n);
+    return cudaGetLastError();
+}
+
+// off[r] = index of the first result of regex r in the sorted results (lower bound), off[m] = n
+__global__ void result_offsets_kernel(const RegexResult *__restrict__ res, long long n, long long m, long long *__restrict__ off) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > m) return;
+    long long lo = 0, hi = n;
+    while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((long long)res[mid].regex < r) lo = mid + 1; else hi = mid; }
+    off[r] = lo;
+}
+__global__ void split_results_kernel(const RegexResult *__restrict__ res, long long n, int *__restrict__ len, long long *__restrict__ sp, long long *__restrict__ ep) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RegexResult r = res[i];
+    len[i] = (int)r.len; sp[i] = (long long)r.sp; ep[i] = (long long)r.ep;
+}
+cudaError_t launch_result_offsets(const RegexResult *d_res, int64_t n, int64_t m, int64_t *d_off, cudaStream_t st) {
+    result_offsets_kernel<<<(unsigned)((m + 1 + 255) / 256), 256, 0, st>>>(d_res, n, m, (long long *)d_off);
+    return cudaGetLastError();
+}
+cudaError_t launch_split_results(const RegexResult *d_res, int64_t n, int32_t *d_len, int64_t *d_sp, int64_t *d_ep, cudaStream_t st) {
+    if (n > 0) split_results_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_res, n, d_len, (long long *)d_sp, (long long *)d_ep);
+    return cudaGetLastError();
+}
+
+}  // namespace fmx

@@ -78,6 +78,7 @@ def lib():
     L.fmx_count_fixed.argtypes = [p, p, i32, i64, p, p]
     L.fmx_count_only_fixed.argtypes = [p, p, i32, i64, p]
     L.fmx_count_fixed_i32.argtypes = [p, p, i32, i64, p, p]
+    L.fmx_count_fixed_packed2.argtypes = [p, p, p, i32, i64, p, p, i32]
     L.fmx_count_fixed_dev.argtypes = [p, p, i32, i64, p, p, p]
     L.fmx_count_fixed_dev_gather.argtypes = [p, p, i32, i64, p, p, p, i32, i64, p]
     L.fmx_dev_alloc.argtypes = [pp, i64]
@@ -87,6 +88,15 @@ def lib():
     L.fmx_ipc_close.argtypes = [p]
     L.fmx_memcpy_d2h.argtypes = [p, p, i64]
     L.fmx_locate_batch.argtypes = [p, p, p, i64, i64, p, p]
+    L.fmx_locate_dev.argtypes = [p, p, p, i64, p, p, i64, C.POINTER(i64), p]
+    L.fmx_last_locate_ms.argtypes = [p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.fmx_scatter_dev.argtypes = [p, i64, p, i32, i64, p, i64, p]
+    L.fmx_regex_set_search_dev.argtypes = [p, p, p, i64, p, C.POINTER(i64)]
+    L.fmx_regex_set_ring.argtypes = [p, i64]
+    L.fmx_set_locate_slab.argtypes = [i64]
+    L.fmx_set_stats.argtypes = [p, i32]
+    L.fmx_last_steps.argtypes = [p]
+    L.fmx_last_steps.restype = i64
     L.fmx_get_prev_i_batch.argtypes = [p, p, i64, p]
     L.fmx_get_next_i_batch.argtypes = [p, p, i64, p]
     L.fmx_pos2char.argtypes = [p, i64, C.POINTER(i32)]
@@ -222,6 +232,15 @@ class RegexSet:
                 continue
             _check(rc)
             return off, ln[:off[m]], sp[:off[m]], ep[:off[m]]
+
+    def set_ring(self, slots):
+        _check(lib().fmx_regex_set_ring(self.h, slots))
+
+    def search_dev(self, searcher, d_res, cap, d_off=0):
+        """device-resident results: {regex, len, sp, ep} uint32 records ordered by (regex, len, sp, ep); returns their number"""
+        total = C.c_int64()
+        _check(lib().fmx_regex_set_search_dev(searcher.h, self.h, C.c_void_p(d_res), cap, C.c_void_p(d_off), C.byref(total)))
+        return total.value
 
     def close(self):
         if getattr(self, "h", None):
@@ -381,6 +400,27 @@ class GpuFMSearcher:
         _check(lib().fmx_locate_batch(self.h, _ptr(sp), _ptr(ep), m, total, _ptr(off), _ptr(pos)))
         return off, pos[:total]
 
+    def locate_dev(self, d_sp, d_ep, m, d_off, d_pos, cap, stream=0):
+        """Device-resident locate (raw device pointers as ints): uint32 sp/ep in, int64 offsets [m+1] and uint32 positions out.
+        Returns the number of positions; raises FmxError(FMX_E_CAPACITY) when cap is too small."""
+        total = C.c_int64()
+        _check(lib().fmx_locate_dev(self.h, C.c_void_p(d_sp), C.c_void_p(d_ep), m, C.c_void_p(d_off), C.c_void_p(d_pos), cap, C.byref(total),
+                                    C.c_void_p(stream)))
+        return total.value
+
+    def set_stats(self, on):
+        _check(lib().fmx_set_stats(self.h, int(on)))
+
+    def last_steps(self):
+        """LF steps of the last locate call (with set_stats(True)) / items of the last regex search"""
+        return lib().fmx_last_steps(self.h)
+
+    def last_locate_ms(self):
+        """(LF-walk ms, per-query sort ms) of the last locate call"""
+        a, b = C.c_double(), C.c_double()
+        _check(lib().fmx_last_locate_ms(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def get_prev_i_batch(self, rows):
         rows = _i64(rows)
         out = np.zeros(len(rows), np.int64)
@@ -456,6 +496,27 @@ class GpuFMSearcher:
             _check(lib().fmx_count_fixed_i32(self.h, _ptr(pat2d), ln, m, _ptr(sp), _ptr(ep)))
         else:
             _check(lib().fmx_count_fixed(self.h, _ptr(pat2d), ln, m, _ptr(sp), _ptr(ep)))
+
+    def pack2(self, pat2d):
+        """2-bit codes of patterns over this index's (<= 4 symbol) alphabet, ceil(len/4) bytes per pattern; sets self.alphabet4"""
+        syms = np.flatnonzero(np.diff(np.append(self._C, self.n))[1:] > 0) + 1          # bytes that occur in the text
+        assert len(syms) <= 4, "packed upload needs an alphabet of at most 4 symbols"
+        self.alphabet4 = np.zeros(4, np.uint8)
+        self.alphabet4[:len(syms)] = syms
+        lut = np.zeros(256, np.uint8)
+        lut[syms] = np.arange(len(syms), dtype=np.uint8)
+        m, ln = pat2d.shape
+        pb = (ln + 3) // 4
+        codes = np.zeros((m, pb * 4), np.uint8)
+        codes[:, :ln] = lut[pat2d]
+        c4 = codes.reshape(m, pb, 4)
+        return (c4[:, :, 0] | (c4[:, :, 1] << 2) | (c4[:, :, 2] << 4) | (c4[:, :, 3] << 6)).astype(np.uint8)
+
+    def count_packed2_into(self, codes, ln, sp, ep):
+        """fmx_count_fixed_packed2: codes from pack2(); sp/ep uint32/int32 (4-byte rows) or int64"""
+        m = codes.shape[0]
+        assert codes.flags.c_contiguous and codes.dtype == np.uint8 and codes.shape[1] == (ln + 3) // 4 and sp.dtype == ep.dtype and len(sp) == m and len(ep) == m
+        _check(lib().fmx_count_fixed_packed2(self.h, _ptr(codes), _ptr(self.alphabet4), ln, m, _ptr(sp), _ptr(ep), sp.dtype.itemsize))
 
     def count_only_fixed(self, pat2d, out=None):
         """Number of occurrences per pattern (ep - sp, uint32) without the interval."""
@@ -540,6 +601,12 @@ class SharedDeviceBuffer:
         if self.ptr:
             lib().fmx_dev_free(C.c_void_p(self.ptr))
             self.ptr = None
+
+
+def scatter_dev(d_src, count_words, sinks, offset_words=0, d_dst_off=0, dst_scale=1, stream=0):
+    """fmx_scatter_dev: `count_words` 4-byte words at d_src go to every sink at word offset offset_words + (*d_dst_off) * dst_scale"""
+    arr = (C.c_void_p * max(len(sinks), 1))(*sinks)
+    _check(lib().fmx_scatter_dev(C.c_void_p(d_src), count_words, arr, len(sinks), offset_words, C.c_void_p(d_dst_off), dst_scale, C.c_void_p(stream)))
 
 
 def set_l2_fetch_granularity(nbytes=0):

@@ -118,3 +118,126 @@ def allgather_fixed_pairs(local_flat, m_global, group=None):
     out = torch.empty(pad * world, dtype=local_flat.dtype, device=local_flat.device)
     dist.all_gather_into_tensor(out, buf, group=group)
     return torch.cat([out[r * pad:r * pad + 2 * sizes[r]] for r in range(world)]).reshape(-1, 2)
+
+
+# ------------------------------------------------------------------------------------------------ device-resident exchange (GPU)
+class GpuExchange:
+    """The exchange step of the multi-GPU path with everything resident in HBM: hit counts, located positions and regex
+    result records of this rank's shard are STORED by kernels straight into every rank's gathered buffers (cudaMalloc'ed, shared
+    through CUDA IPC, i.e. peer memory over NVLink/NVSwitch) at their scanned offsets; NCCL is left with one 4-byte all-reduce per
+    exchange as the "every rank's stores have landed" barrier.  No value ever visits the host.
+
+        counts : uint32[M]        per-query hit counts / per-regex result counts of the whole batch
+        values : uint32[cap]      located positions (1 word each) or regex records {regex, len, sp, ep} (4 words each)
+
+    `peers` may be given explicitly (lists of device pointers, this rank's own buffers included, in rank order) so that one GPU can
+    play several ranks in tests; otherwise the handles are exchanged over torch.distributed."""
+
+    def __init__(self, g, rank, world, m_global, value_words_cap, device, group=None, peers=None, barrier=None):
+        from . import fmindex as fx
+        self.fx, self.g, self.rank, self.world, self.M, self.cap = fx, g, rank, world, m_global, value_words_cap
+        self.device, self.group = device, group
+        self.counts = fx.SharedDeviceBuffer(max(m_global, 1))
+        self.values = fx.SharedDeviceBuffer(max(value_words_cap, 4))
+        if peers is None and world > 1:
+            mine = (self.counts.export_handle(), self.values.export_handle())
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine, group=group)
+            self.count_sinks = [self.counts.ptr if r == rank else self.counts.import_peer(r, everyone[r][0]) for r in range(world)]
+            self.value_sinks = [self.values.ptr if r == rank else self.values.import_peer(r, everyone[r][1]) for r in range(world)]
+        elif peers is None:
+            self.count_sinks, self.value_sinks = [self.counts.ptr], [self.values.ptr]
+        else:
+            self.count_sinks, self.value_sinks = peers
+        self.flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self._barrier = barrier
+
+    def set_peers(self, count_sinks, value_sinks):
+        self.count_sinks, self.value_sinks = list(count_sinks), list(value_sinks)
+
+    def barrier(self):
+        """after this, every rank's stores issued before it have landed everywhere (stream-ordered on the current stream)"""
+        if self._barrier is not None:
+            return self._barrier()
+        if self.world > 1:
+            dist.all_reduce(self.flag, group=self.group)
+
+    def _view(self, buf, n, dtype=torch.int32):
+        """torch view over a SharedDeviceBuffer (no copy)"""
+        class _Ptr:
+            pass
+        holder = _Ptr()
+        holder.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (buf.ptr, False), "version": 3}
+        return torch.as_tensor(holder, device=self.device)
+
+    def offsets(self):
+        """exclusive scan of the gathered counts -> int64[M+1] on the device"""
+        c = self._view(self.counts, self.M).to(torch.int64) & 0xFFFFFFFF
+        off = torch.zeros(self.M + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(c, 0, out=off[1:])
+        return off
+
+    # ---- locate: count (fused gather of the counts) -> scan -> LF walks + sort -> peer stores of the position slab
+    def locate_count(self, d_pat, ln, lo, hi):
+        """phase 1: count this rank's shard; the hit counts land in every rank's gathered count buffer (fused into the count kernel)"""
+        m = hi - lo
+        st = torch.cuda.current_stream().cuda_stream
+        self._sp = torch.empty(max(m, 1), dtype=torch.int32, device=self.device)
+        self._ep = torch.empty(max(m, 1), dtype=torch.int32, device=self.device)
+        self.g.count_fixed_dev_gather(d_pat.data_ptr(), ln, m, self._sp.data_ptr(), self._ep.data_ptr(), self.count_sinks, lo, st)
+
+    def locate_values(self, lo, hi, scratch_cap):
+        """phase 2 (after the barrier): scan of all counts, LF walks + per-query sort of this shard, peer stores of its positions at the
+        scanned offset.  Returns (off[M+1] int64 on the device, number of positions of this shard)."""
+        m = hi - lo
+        st = torch.cuda.current_stream().cuda_stream
+        off = self.offsets()
+        d_off_local = torch.empty(m + 1, dtype=torch.int64, device=self.device)
+        d_pos_local = torch.empty(max(scratch_cap, 1), dtype=torch.int32, device=self.device)
+        total_local = self.g.locate_dev(self._sp.data_ptr(), self._ep.data_ptr(), m, d_off_local.data_ptr(), d_pos_local.data_ptr(), scratch_cap, st)
+        self.fx.scatter_dev(d_pos_local.data_ptr(), total_local, self.value_sinks, 0, off.data_ptr() + 8 * lo, 1, st)
+        self._keep = (off, d_pos_local)                      # alive until the stores have been issued and waited for
+        return off, total_local
+
+    def locate(self, d_pat, ln, lo, hi, scratch_cap):
+        """d_pat: device uint8 tensor [hi-lo, ln] = this rank's shard of the batch.  Returns (off[M+1], number of positions of this shard);
+        the positions of the WHOLE batch are then in gathered_values(off[M]) on every rank."""
+        self.locate_count(d_pat, ln, lo, hi)
+        self.barrier()
+        out = self.locate_values(lo, hi, scratch_cap)
+        self.barrier()
+        return out
+
+    def gathered_values(self, n_words):
+        return self._view(self.values, n_words)
+
+    # ---- regex: traversal + ordering on the device -> peer stores of the per-regex counts -> scan -> peer stores of the records
+    def regex_count(self, rset, lo, hi, scratch_cap):
+        m = hi - lo
+        st = torch.cuda.current_stream().cuda_stream
+        self._res = torch.empty((max(scratch_cap, 1), 4), dtype=torch.int32, device=self.device)
+        d_off = torch.zeros(m + 1, dtype=torch.int64, device=self.device)
+        self._total = rset.search_dev(self.g, self._res.data_ptr(), scratch_cap, d_off.data_ptr())
+        self._cnt = (d_off[1:] - d_off[:-1]).to(torch.int32).contiguous()
+        self._res[:self._total, 0] += lo                     # batch-wide regex ids
+        self.fx.scatter_dev(self._cnt.data_ptr(), m, self.count_sinks, lo, 0, 1, st)
+
+    def regex_values(self, lo, hi):
+        st = torch.cuda.current_stream().cuda_stream
+        off = self.offsets()
+        self.fx.scatter_dev(self._res.data_ptr(), 4 * self._total, self.value_sinks, 0, off.data_ptr() + 8 * lo, 4, st)
+        self._keep = (off,)
+        return off, self._total
+
+    def regex(self, rset, lo, hi, scratch_cap):
+        """this rank's shard [lo, hi) of the regex batch (rset holds exactly those).  Returns (off[M+1], results of this shard); the
+        {regex, len, sp, ep} records of the WHOLE batch are then in gathered_values(4 * off[M]) on every rank."""
+        self.regex_count(rset, lo, hi, scratch_cap)
+        self.barrier()
+        out = self.regex_values(lo, hi)
+        self.barrier()
+        return out
+
+    def close(self):
+        self.counts.close()
+        self.values.close()

@@ -119,6 +119,10 @@ int fmx_count_batch(fmx_index *ix, const uint8_t *pat, const int64_t *off, int64
 int fmx_count_fixed(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, int64_t *sp, int64_t *ep);
 /* Same with the reference's own result width, Option[(Int, Int)]: 32-bit rows (n must be < 2^31, else FMX_E_UNSUPPORTED).   */
 int fmx_count_fixed_i32(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, int32_t *sp, int32_t *ep);
+/* Alphabets of <= 4 symbols (DNA): the patterns cross PCIe as 2-bit codes — pattern q occupies ceil(len/4) bytes, symbol j =
+ * alphabet[(byte[j/4] >> 2(j%4)) & 3] — and are expanded on the device; rows come back as uint32 (row_bytes = 4; n < 2^32) or int64
+ * (row_bytes = 8).  Results equal fmx_count_fixed on the expanded patterns.  A len-32 read costs 8 + 8 bytes of PCIe instead of 32 + 16. */
+int fmx_count_fixed_packed2(fmx_index *ix, const uint8_t *codes, const uint8_t alphabet[4], int32_t len, int64_t m, void *sp, void *ep, int32_t row_bytes);
 /* Count only: counts[q] = ep - sp (0 for None), uint32 — the number of occurrences without the interval.    */
 int fmx_count_only_fixed(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, uint32_t *counts);
 /* Device-pointer variant (asynchronous on `stream`): d_pat holds m*len bytes, d_sp/d_ep are uint32[m]. */
@@ -145,6 +149,27 @@ int fmx_memcpy_d2h(void *dst, const void *src, int64_t bytes);
  * if the total exceeds cap_total, FMX_E_CAPACITY is returned and out_off[m] holds the required total.  */
 int fmx_locate_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, int64_t m, int64_t cap_total,
                      int64_t *out_off, int64_t *pos);
+
+/* Device-resident locate (asynchronous pieces on `stream`, one synchronisation to learn the total): d_sp/d_ep = uint32 rows of m
+ * intervals exactly as fmx_count_fixed_dev leaves them (None = (0,0)); d_off (int64[m+1]) receives the exclusive offsets, d_pos
+ * (uint32[cap]) the positions, ascending inside each query, T' coordinates.  FMX_E_CAPACITY with *total_out set when cap is small.   */
+int fmx_locate_dev(fmx_index *ix, const void *d_sp_u32, const void *d_ep_u32, int64_t m, void *d_off_i64, void *d_pos_u32, int64_t cap,
+                   int64_t *total_out, void *stream);
+/* Occurrences per internal slab of the locate calls (default 2^30; 0 restores it).  A batch may hold any number of occurrences; it is
+ * processed slab by slab.  Exposed so that tests can exercise the slab seams on small inputs.                                       */
+int fmx_set_locate_slab(int64_t occurrences);
+/* Roofline accounting: fmx_set_stats(ix, 1) makes locate calls count the LF steps of their walks (untimed runs only); regex searches
+ * always count the items they process (one backward step each).  fmx_last_steps = that count for the last locate / regex call.      */
+int     fmx_set_stats(fmx_index *ix, int32_t on);
+int64_t fmx_last_steps(const fmx_index *ix);
+/* Split of the last locate call's device time: LF walks vs the per-query sort.                              */
+int fmx_last_locate_ms(const fmx_index *ix, double *walk_ms, double *sort_ms);
+/* Exchange step of the variable-length results on the multi-GPU path (located positions, regex triples): this rank's slab of `count`
+ * 4-byte words is stored into each of the n_sinks (<= 8) gathered buffers — this rank's and, via CUDA IPC, its peers' — at word offset
+ * `offset` + (*d_dst_off) * dst_scale, where d_dst_off is a DEVICE int64 (the scanned offset of this rank's first result; no host
+ * round trip between the scan and the stores) or NULL.  Asynchronous on `stream`.                              */
+int fmx_scatter_dev(const void *d_src, int64_t count, void *const *sinks, int32_t n_sinks, int64_t offset, const void *d_dst_off,
+                    int64_t dst_scale, void *stream);
 
 /* ---- LF / FL steps and extraction  M/bwtmerger.scala:376-419 --------------------------------------- */
 int fmx_get_prev_i_batch(fmx_index *ix, const int64_t *row, int64_t m, int64_t *out);   /* getPrevI :386 */
@@ -210,6 +235,13 @@ int fmx_dfa_match_string(const fmx_regex *dfa, const uint8_t *s, int64_t len, in
 typedef struct fmx_regex_set fmx_regex_set;
 int  fmx_regex_set_create(fmx_index *ix, fmx_regex *const *rx, int64_t m, fmx_regex_set **out);
 int  fmx_regex_set_search(fmx_index *ix, fmx_regex_set *set, int64_t cap_total, int64_t *out_off, int32_t *len, int64_t *sp, int64_t *ep);
+/* Device-resident form: the results stay on the index's device as {regex, len, sp, ep} records (4 x uint32) ordered by (regex, len, sp, ep)
+ * in d_res[cap]; d_off (int64[m+1], may be NULL) receives the index of every regex's first result; *total_out the number of results
+ * (FMX_E_CAPACITY when it exceeds cap).  What a multi-GPU caller exchanges, and what fmx_regex_set_search copies out.        */
+int  fmx_regex_set_search_dev(fmx_index *ix, fmx_regex_set *set, void *d_res, int64_t cap, void *d_off_i64, int64_t *total_out);
+/* Sizes the set's device work ring to `slots` items (power of two, >= the number of start positions; default: 4x the start positions,
+ * at least 2^20).  A traversal that overflows its ring is abandoned and rerun with a 4x larger one — results never change.            */
+int  fmx_regex_set_ring(fmx_regex_set *set, int64_t slots);
 void fmx_regex_set_free(fmx_regex_set *set);
 
 /* ---- instrumentation for the roofline accounting (not on the timed path) ---------------------------
@@ -241,7 +273,7 @@ int fmx_set_lanes(fmx_index *ix, int32_t lanes_per_query);
 int fmx_get_lanes(const fmx_index *ix);                      /* lanes per query of the count kernels (may differ from the other kernels' by default) */
 double fmx_last_kernel_ms(const fmx_index *ix);
 int64_t fmx_last_kernel_launches(const fmx_index *ix);
-/* Breadth-first levels the last regex search walked (all inside one cooperative launch).                 */
+/* Length of the longest (len, sp, ep) item the last regex search produced (the depth of the traversal).  */
 int64_t fmx_last_regex_levels(const fmx_index *ix);
 
 /* ---- index construction on the device (tooling for synthetic configs) -----------

@@ -30,6 +30,16 @@ def test_reference_arm_prints_one_contract_line():
     assert d["gpu_launches"] == 0
 
 
+def test_reference_arm_other_workloads():
+    """--workload cfg3 (count + sorted sa[sp..ep)) and cfg4 (ReTree._matchSA) through the oracle, scaled down"""
+    for w, extra, unit in (("cfg3", ["--queries", "3000"], "queries/s"), ("cfg4", ["--queries", "200"], "regexes/s")):
+        out = _run(["--impl", "reference", "--workload", w, "--text-bytes", "200000", "--steps", "1", "--warmup", "1"] + extra)
+        assert out.returncode == 0, out.stderr[-2000:]
+        d = json.loads([ln for ln in out.stdout.splitlines() if ln.strip()][-1])
+        assert d["impl"] == "reference" and d["unit"] == unit and d["value"] > 0 and d["config"]["workload"].startswith(w)
+        assert d["cpu_baseline"]["kind"] == "port"
+
+
 def test_our_arm_needs_a_gpu_and_says_so():
     import torch
     if torch.cuda.is_available():

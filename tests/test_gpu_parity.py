@@ -387,19 +387,138 @@ def test_synthetic_parity(kind, cfg, words, tmp_path):
     o.close()
 
 
-def test_regex_frontier_growth_and_replay(ref_dir, o1024):
-    """6000 '.'-regexes expand to > 2^20 frontier items in one level: the frontier buffer must grow and the level be replayed
-    without duplicating or losing results."""
-    g = _open(os.path.join(ref_dir, "test1024.cmp.bwt"), (fx.LAYOUT_PLANES, 2))
+@pytest.mark.parametrize("lanes", [1, 2, 4])
+def test_regex_ring_overflow_and_rerun(ref_dir, o1024, lanes):
+    """6000 '.'-regexes push > 10^6 items through a work ring of 8192 slots: the traversal must notice the overflow, be rerun with
+    larger rings and return every result exactly once; later searches of the same set reuse the grown ring."""
+    g = _open(os.path.join(ref_dir, "test1024.cmp.bwt"), (fx.LAYOUT_PLANES, lanes))
     rxs = ["%c.%c" % (97 + i % 26, 97 + (i // 26) % 26) for i in range(6000)]
-    got = g.regex_search_batch([fx.ReTree(r) for r in rxs], cap_total=64)
+    trees = [fx.ReTree(r) for r in rxs]
     memo = {}
-    for rx, res in zip(rxs, got):
-        if rx not in memo:
-            memo[rx] = o1024.regex_match(rx)
-        assert res == memo[rx], rx
-    assert sum(len(r) for r in got) > 1000
+    rset = g.regex_set(trees)
+    rset.set_ring(8192)
+    for rep in range(3):
+        off, ln, sp, ep = rset.search(g, cap_total=64 if rep == 0 else 1 << 20)
+        assert g.last_kernel_launches() >= (4 if rep == 0 else 2)             # rep 0: at least one abandoned run (seed + traversal each)
+        assert g.last_regex_levels() == 3
+        for i, rx in enumerate(rxs):
+            if rx not in memo:
+                memo[rx] = o1024.regex_match(rx)
+            assert list(zip(ln[off[i]:off[i + 1]].tolist(), sp[off[i]:off[i + 1]].tolist(), ep[off[i]:off[i + 1]].tolist())) == memo[rx], rx
+        assert off[-1] > 1000
+    rset.close()
     g.close()
+
+
+def test_regex_device_resident_results(ref_dir, o1024):
+    """fmx_regex_set_search_dev: the ordered {regex, len, sp, ep} records and per-regex offsets, left on the device, equal what the host call
+    returns — for a handful of results (one CTA's bitonic network) and for many (radix passes)."""
+    import torch
+    g = _open(os.path.join(ref_dir, "test1024.cmp.bwt"), (fx.LAYOUT_WM, 2))
+    for rxs in (["ab.", "q(u|a)x?", "zz", "a", "x\\w\\w"], ["%c.%c?" % (97 + i % 26, 97 + (i // 26) % 26) for i in range(676)]):
+        trees = [fx.ReTree(r) for r in rxs]
+        rset = g.regex_set(trees)
+        off, ln, sp, ep = rset.search(g)
+        cap = int(off[-1]) + 5
+        d_res = torch.zeros((cap, 4), dtype=torch.int32, device="cuda")
+        d_off = torch.zeros(len(rxs) + 1, dtype=torch.int64, device="cuda")
+        total = rset.search_dev(g, d_res.data_ptr(), cap, d_off.data_ptr())
+        torch.cuda.synchronize()
+        assert total == off[-1] and np.array_equal(d_off.cpu().numpy(), off)
+        r = d_res.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+        assert np.array_equal(r[:total, 1], ln) and np.array_equal(r[:total, 2], sp) and np.array_equal(r[:total, 3], ep)
+        assert np.array_equal(r[:total, 0], np.repeat(np.arange(len(rxs)), np.diff(off)))
+        with pytest.raises(fx.FmxError) as ei:
+            rset.search_dev(g, d_res.data_ptr(), max(total - 1, 0), 0)
+        assert ei.value.code == fx.FMX_E_CAPACITY or total == 0
+        for i, rx in enumerate(rxs[:40]):
+            assert list(zip(ln[off[i]:off[i + 1]].tolist(), sp[off[i]:off[i + 1]].tolist(), ep[off[i]:off[i + 1]].tolist())) == o1024.regex_match(rx), rx
+        rset.close()
+    g.close()
+
+
+@pytest.mark.parametrize("rate,accel", [(4, fx.ACCEL_NONE), (32, fx.ACCEL_KMER), (0, fx.ACCEL_AUTO)])
+def test_locate_device_resident_and_slabs(ref_dir, rate, accel):
+    """fmx_locate_dev (uint32 rows in, int64 offsets + uint32 positions out, all on the device) equals fmx_locate_batch and the oracle's
+    sorted sa[sp..ep); with slabs of 1000 occurrences the batch is cut at query boundaries (one query alone exceeds a slab)."""
+    import torch
+    text = open(os.path.join(ref_dir, "test.txt"), "rb").read()
+    o = fo.OracleIndex.load(os.path.join(ref_dir, "test.cmp"), big_endian=False)
+    sa = o.sa().astype(np.int64)
+    g = fx.GpuFMSearcher(os.path.join(ref_dir, "test.cmp.bwt"), bigEndian=False, sa_sample_rate=rate, accel=accel)
+    rng = np.random.default_rng(8)
+    pats = [b"", b"a", b"e"] + [text[s:s + int(rng.integers(1, 4))][::-1] for s in rng.integers(0, len(text) - 4, 400)] + [b"zzzz", b"qq"]
+    sp, ep = g.count_batch(pats)
+    want = [np.sort(sa[a:b]) for a, b in zip(sp, ep)]
+    try:
+        for slab in (0, 1000, 7):
+            fx.lib().fmx_set_locate_slab(slab)
+            off, pos = g.locate_batch(sp, ep)
+            assert off[-1] == (ep - sp).sum() > 10241
+            for k in range(len(pats)):
+                assert np.array_equal(pos[off[k]:off[k + 1]], want[k]), (slab, k)
+            d_sp = torch.from_numpy(sp.astype(np.uint32).view(np.int32)).cuda()
+            d_ep = torch.from_numpy(ep.astype(np.uint32).view(np.int32)).cuda()
+            d_off = torch.zeros(len(pats) + 1, dtype=torch.int64, device="cuda")
+            d_pos = torch.zeros(int(off[-1]) + 3, dtype=torch.int32, device="cuda")
+            st = torch.cuda.current_stream().cuda_stream
+            with pytest.raises(fx.FmxError) as ei:
+                g.locate_dev(d_sp.data_ptr(), d_ep.data_ptr(), len(pats), d_off.data_ptr(), d_pos.data_ptr(), int(off[-1]) - 1, st)
+            assert ei.value.code == fx.FMX_E_CAPACITY
+            total = g.locate_dev(d_sp.data_ptr(), d_ep.data_ptr(), len(pats), d_off.data_ptr(), d_pos.data_ptr(), d_pos.numel(), st)
+            torch.cuda.synchronize()
+            assert total == off[-1] and np.array_equal(d_off.cpu().numpy(), off)
+            assert np.array_equal(d_pos.cpu().numpy()[:total].astype(np.int64) & 0xFFFFFFFF, pos)
+            walk, sort = g.last_locate_ms()
+            assert walk > 0 and sort > 0
+    finally:
+        fx.lib().fmx_set_locate_slab(0)
+    g.close()
+    o.close()
+
+
+@pytest.mark.parametrize("sigma", [2, 4])
+def test_packed_two_bit_upload(sigma):
+    """fmx_count_fixed_packed2: 2-bit codes on the wire, expanded on the device — same (sp, ep) as the byte patterns, uint32 and int64 rows,
+    lengths that are not multiples of 4, batches spanning several pipeline chunks"""
+    rng = np.random.default_rng(40 + sigma)
+    alpha = np.frombuffer(b"ACGT", np.uint8)[:sigma]
+    text = alpha[rng.integers(0, sigma, 60_000)].tobytes()
+    tp = bytes(fo.file_to_text_rev(text))
+    bwt, eof, cnt = fo.build_bwt(fo.file_to_text_rev(text))
+    o = fo.OracleIndex.from_bwt(bwt, eof, cnt)
+    g = fx.GpuFMSearcher(bwt=bwt, eof=eof, counts=cnt)
+    g.set_chunk(1000)
+    for ln in (1, 7, 16, 32, 45):
+        offs = rng.integers(0, len(tp) - ln, 3500)
+        arr = np.stack([np.frombuffer(tp[s:s + ln], np.uint8) for s in offs]).copy()
+        arr[::6, ln // 2] = alpha[rng.integers(0, sigma, len(arr[::6]))]
+        osp, oep = o.count_batch(arr.reshape(-1), np.arange(0, arr.size + 1, ln, dtype=np.int64))
+        codes = g.pack2(arr)
+        assert codes.shape == (len(arr), (ln + 3) // 4)
+        for dt in (np.uint32, np.int64):
+            sp, ep = np.full(len(arr), 7, dt), np.full(len(arr), 7, dt)
+            g.count_packed2_into(codes, ln, sp, ep)
+            assert np.array_equal(sp.astype(np.int64), osp) and np.array_equal(ep.astype(np.int64), oep), (ln, dt)
+    g.close()
+    o.close()
+
+
+def test_scatter_dev_single_gpu():
+    """fmx_scatter_dev with this GPU playing three ranks: every rank's slab lands in every gathered buffer at the offset read from the device"""
+    import torch
+    rng = np.random.default_rng(1)
+    sizes = [1001, 0, 4099]
+    slabs = [torch.from_numpy(rng.integers(0, 2 ** 31, s).astype(np.int32)).cuda() for s in sizes]
+    bufs = [torch.full((sum(sizes) + 8,), -1, dtype=torch.int32, device="cuda") for _ in range(3)]
+    offs = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for r in range(3):
+        fx.scatter_dev(slabs[r].data_ptr(), sizes[r], [b.data_ptr() for b in bufs], 3, offs.data_ptr() + 8 * r, 1, st)
+    torch.cuda.synchronize()
+    want = np.concatenate([np.full(3, -1, np.int32)] + [s.cpu().numpy() for s in slabs] + [np.full(5, -1, np.int32)])
+    for b in bufs:
+        assert np.array_equal(b.cpu().numpy(), want)
 
 
 @pytest.mark.parametrize("m,lanes", [(3000, 2), (3003, 2), (3000, 1), (3003, 4)])
