@@ -599,7 +599,7 @@ def count_workload(cx, workload, n, m, ln, extras):
 
     # ---- roofline inputs, outside the timed region
     requests, steps_exec = g.count_fixed_stats(pats)
-    r_rand_gbs, _ = g.gather_bench(64, 2, 1 << 25, 16, 3)            # K4: random 64-B requests (two lanes x one 256-bit load) over this index
+    r_rand_gbs, _ = g.gather_bench(64, 4, 1 << 25, 16, 3)            # K4: random 64-B requests (four lanes x one 128-bit load = one request) over this index
     r_rand_req = r_rand_gbs * 1e9 / 64
 
     ms_total, clocks = cx.timed(step, args.steps, args.warmup, drain=drain)
@@ -760,64 +760,93 @@ def english_open(cx, n):
     return text, base, g, dict(info, open_s=time.time() - t0)
 
 
-def locate_leg(cx, g, text, n, m_total, ln, orc, steps, full_e2e):
-    """cfg 3: m_total len-`ln` text substrings (seed 5) in all, sharded over the ranks (strong scaling); count -> locate every occurrence
-    (sampled SA, rate 32) -> positions ascending per query.  Device-resident: counts, scanned offsets and positions stay in HBM and are
-    exchanged by kernel stores into every rank's gathered buffers (sharded.GpuExchange)."""
+def locate_leg(cx, g, text, n, m_total, ln, orc, steps, chunk_q=4000):
+    """cfg 3: m_total len-`ln` text substrings (seed 5) in all, sharded over the ranks (strong scaling); count -> locate EVERY occurrence
+    (sampled SA, rate 32) -> positions ascending per query.  On English-like text a len-12 pattern has ~10^5 occurrences on average
+    (up to millions), so the batch is walked in chunks of `chunk_q` queries whose positions fit one device buffer; inside a chunk
+    everything is device-resident: counts, scanned offsets and positions stay in HBM and, with N > 1, are exchanged by kernel stores
+    into every rank's gathered buffers (sharded.GpuExchange)."""
     from findex_b200 import sharded
     torch, fx, world, rank = cx.torch, cx.fx, cx.world, cx.rank
     pats_all, _ = make_queries(text, m_total, ln, 5, 0, workload="cfg3")
-    lo, hi = sharded.shard_bounds(m_total, rank, world)
-    pats = np.ascontiguousarray(pats_all[lo:hi])
-    m = hi - lo
-    d_pat = torch.from_numpy(pats).to(cx.dev)
-    d_sp = torch.zeros(m, dtype=torch.int32, device=cx.dev)
-    d_ep = torch.zeros(m, dtype=torch.int32, device=cx.dev)
-    d_off = torch.zeros(m + 1, dtype=torch.int64, device=cx.dev)
     st = torch.cuda.current_stream().cuda_stream
-    g.count_fixed_dev(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), st)
-    torch.cuda.synchronize()
-    sp = d_sp.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
-    ep = d_ep.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
-    occ = ep - sp
-    assert (occ >= 1).all(), "a text substring was not found"
-    total_local = int(occ.sum())
-    total_all = int(cx.sum_over_ranks(total_local))
-    d_pos = torch.zeros(total_local + 16, dtype=torch.int32, device=cx.dev)
-    ex = sharded.GpuExchange(g, rank, world, m_total, total_all + 16, cx.dev) if world > 1 else None
+    nchunk = (m_total + chunk_q - 1) // chunk_q
+    chunks = []                                            # (global lo, global hi, device patterns of this rank's part)
+    for c in range(nchunk):
+        c0, c1 = c * chunk_q, min(m_total, (c + 1) * chunk_q)
+        lo, hi = sharded.shard_bounds(c1 - c0, rank, world)
+        chunks.append((c0 + lo, c0 + hi, c0, c1, torch.from_numpy(np.ascontiguousarray(pats_all[c0 + lo:c0 + hi])).to(cx.dev)))
+    mloc = max(hi - lo for lo, hi, _, _, _ in chunks)
+    d_sp = torch.zeros(max(mloc, 1), dtype=torch.int32, device=cx.dev)
+    d_ep = torch.zeros(max(mloc, 1), dtype=torch.int32, device=cx.dev)
+    d_off = torch.zeros(mloc + 1, dtype=torch.int64, device=cx.dev)
+    # pre-pass (setup): hit counts of every chunk, to size the position buffers once
+    loc_tot, sp_all, ep_all = [], [], []
+    for lo, hi, _, _, d_pat in chunks:
+        g.count_fixed_dev(d_pat.data_ptr(), ln, hi - lo, d_sp.data_ptr(), d_ep.data_ptr(), st)
+        torch.cuda.synchronize()
+        sp_all.append(d_sp[:hi - lo].cpu().numpy().astype(np.int64) & 0xFFFFFFFF)
+        ep_all.append(d_ep[:hi - lo].cpu().numpy().astype(np.int64) & 0xFFFFFFFF)
+        assert (ep_all[-1] > sp_all[-1]).all(), "a text substring was not found"
+        loc_tot.append(int((ep_all[-1] - sp_all[-1]).sum()))
+    tt = torch.tensor(loc_tot, dtype=torch.float64, device=cx.dev)
+    if world > 1:
+        cx.dist.all_reduce(tt)
+    glob_tot = [int(x) for x in tt.cpu().tolist()]
+    total_local, total_all = sum(loc_tot), sum(glob_tot)
+    cap_local = max(loc_tot) + 16
+    d_pos = torch.zeros(cap_local, dtype=torch.int32, device=cx.dev)
+    ex = sharded.GpuExchange(g, rank, world, chunk_q, max(glob_tot) + 16, cx.dev) if world > 1 else None
+    last = {}
 
     def step():
-        if ex is not None:
-            ex.locate(d_pat, ln, lo, hi, total_local + 16)
-        else:
-            g.count_fixed_dev(d_pat.data_ptr(), ln, m, d_sp.data_ptr(), d_ep.data_ptr(), st)
-            g.locate_dev(d_sp.data_ptr(), d_ep.data_ptr(), m, d_off.data_ptr(), d_pos.data_ptr(), total_local + 16, st)
+        for ci, (lo, hi, c0, c1, d_pat) in enumerate(chunks):
+            if ex is not None:
+                last["off"], _ = ex.locate(d_pat, ln, lo - c0, hi - c0, cap_local)
+            else:
+                g.count_fixed_dev(d_pat.data_ptr(), ln, hi - lo, d_sp.data_ptr(), d_ep.data_ptr(), st)
+                g.locate_dev(d_sp.data_ptr(), d_ep.data_ptr(), hi - lo, d_off.data_ptr(), d_pos.data_ptr(), cap_local, st)
     g.set_stats(True)
-    step()
-    torch.cuda.synchronize()
-    lf_steps = g.last_steps()
+    lf_steps = 0
+    walk_ms = sort_ms = 0.0
+    for ci, (lo, hi, c0, c1, d_pat) in enumerate(chunks):     # instrumented pass (untimed): LF steps per occurrence, walk/sort split
+        g.count_fixed_dev(d_pat.data_ptr(), ln, hi - lo, d_sp.data_ptr(), d_ep.data_ptr(), st)
+        g.locate_dev(d_sp.data_ptr(), d_ep.data_ptr(), hi - lo, d_off.data_ptr(), d_pos.data_ptr(), cap_local, st)
+        lf_steps += g.last_steps()
+        if nchunk > 8 and ci >= 3:                             # a sample of the chunks is enough for the per-occurrence figures
+            break
+    stat_occ = sum(loc_tot[:ci + 1])
     g.set_stats(False)
-    ms, clocks = cx.timed(step, steps, 2)
-    walk_ms, sort_ms = g.last_locate_ms()
+    for ci2, (lo, hi, c0, c1, d_pat) in enumerate(chunks[:ci + 1]):
+        g.count_fixed_dev(d_pat.data_ptr(), ln, hi - lo, d_sp.data_ptr(), d_ep.data_ptr(), st)
+        g.locate_dev(d_sp.data_ptr(), d_ep.data_ptr(), hi - lo, d_off.data_ptr(), d_pos.data_ptr(), cap_local, st)
+        a, b = g.last_locate_ms()
+        walk_ms += a
+        sort_ms += b
+    ms, clocks = cx.timed(step, steps, 1 if nchunk > 8 else 2)
     launches = int(g.last_kernel_launches())
-    cx.launches += (steps + 3) * (launches * 4 + 1)
-    # ---- parity: count vs the oracle on a sample; positions: complete (count matches), ascending, and every one a real occurrence of the
+    cx.launches += (steps + 2) * nchunk * (launches * 8 + 2)
+    # ---- parity (last chunk): count vs the oracle; positions complete (count matches), ascending, and every one a real occurrence of the
     # pattern in the text — which makes them exactly sorted { sa[r] : r in [sp, ep) } (util.scala:213-224)
+    lo, hi, c0, c1, d_pat = chunks[-1]
+    sp, ep = sp_all[-1], ep_all[-1]
+    occ = ep - sp
+    pats = pats_all[lo:hi]
     if ex is not None:
-        off_all = ex.offsets().cpu().numpy()
-        pos_view = ex.gathered_values(int(off_all[-1]))
-        off_local = off_all[lo:hi + 1] - off_all[lo]
-        pos_local = pos_view[int(off_all[lo]):int(off_all[hi])]
+        off_all = last["off"].cpu().numpy()
+        pos_view = ex.gathered_values(int(off_all[c1 - c0]))
+        off_local = off_all[lo - c0:hi - c0 + 1] - off_all[lo - c0]
+        pos_local = pos_view[int(off_all[lo - c0]):int(off_all[hi - c0])]
     else:
-        off_local = d_off.cpu().numpy()
-        pos_local = d_pos[:total_local]
-    assert off_local[-1] == total_local and np.array_equal(np.diff(off_local), occ)
+        off_local = d_off[:hi - lo + 1].cpu().numpy()
+        pos_local = d_pos[:loc_tot[-1]]
+    assert off_local[-1] == loc_tot[-1] and np.array_equal(np.diff(off_local), occ)
     rng = np.random.default_rng(99)
     bad = 0
-    chk = rng.choice(m, min(3000, m), replace=False)
+    chk = rng.choice(hi - lo, min(1500, hi - lo), replace=False)
     n1 = g.n
     for j in chk:
-        q = pos_local[int(off_local[j]):int(off_local[j]) + min(int(occ[j]), 4096)].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+        q = pos_local[int(off_local[j]):int(off_local[j]) + min(int(occ[j]), 8192)].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
         if len(q) > 1 and not (np.diff(q) > 0).all():
             bad += 1
             continue
@@ -830,42 +859,46 @@ def locate_leg(cx, g, text, n, m_total, ln, orc, steps, full_e2e):
     if orc is not None:
         parity["count_parity_on_sample"], parity["count_parity_sample"] = oracle_parity(orc, pats, sp, ep, 100_000)
         assert parity["count_parity_on_sample"]
-    # ---- e2e: host (sp, ep) in, host int64 positions out through fmx_locate_batch (pinned buffers), on a time-bounded slice unless asked
-    k = m if full_e2e else min(m, max(1000, int(m * min(1.0, 150e6 / max(total_local, 1)))))
-    tot_k = int(occ[:k].sum())
+    # ---- e2e: host (sp, ep) in, host int64 positions out through fmx_locate_batch (pinned buffers), on a time-bounded slice of the shard
+    sp0, ep0 = sp_all[0], ep_all[0]
+    k = int(min(len(sp0), max(1, np.searchsorted(np.cumsum(ep0 - sp0), 120e6))))
+    tot_k = int((ep0[:k] - sp0[:k]).sum())
     h_pos = fx.PinnedArray((max(tot_k, 1),), np.int64)
     h_off = np.zeros(k + 1, np.int64)
-    sp_k, ep_k = np.ascontiguousarray(sp[:k]), np.ascontiguousarray(ep[:k])
+    sp_k, ep_k = np.ascontiguousarray(sp0[:k]), np.ascontiguousarray(ep0[:k])
 
     def e2e_step():
         rc = fx.lib().fmx_locate_batch(g.h, sp_k.ctypes.data, ep_k.ctypes.data, k, tot_k, h_off.ctypes.data, h_pos.array.ctypes.data)
         assert rc == 0, fx.lib().fmx_last_error()
-    ms_e2e, _ = cx.timed(e2e_step, max(2, min(steps, 5)), 1, wall=True, sample_clocks=False)
     e2e_steps = max(2, min(steps, 5))
-    if ex is None:
-        assert np.array_equal(h_pos.array[:tot_k], pos_local[:tot_k].cpu().numpy().astype(np.int64) & 0xFFFFFFFF), "host locate differs from device locate"
+    ms_e2e, _ = cx.timed(e2e_step, e2e_steps, 1, wall=True, sample_clocks=False)
+    hp = h_pos.array[:tot_k]
+    assert all((np.diff(hp[h_off[j]:h_off[j + 1]]) > 0).all() for j in range(0, k, max(1, k // 50))), "host locate: positions not ascending"
     h_pos.free()
     per = ms / steps
     # one LF step of the sampled walk = one walk block (BWT byte + mark bit) + one rank block; plus the mark-rank block and the sample
-    req_occ = 2.0 * lf_steps / max(total_local, 1) + 2.0
-    r_rand_gbs, _ = g.gather_bench(64, 2, 1 << 25, 16, 3)
+    req_occ = 2.0 * lf_steps / max(stat_occ, 1) + 2.0
+    r_rand_gbs, _ = g.gather_bench(64, 4, 1 << 25, 16, 3)
     peak, peak_src = measured_peaks()
     L = max(1, int(np.ceil(np.log2(max(g.info()["sigma"], 2)))))
+    kern_ms = max(walk_ms + sort_ms, 1e-9)
     out = {"value": m_total / (per * 1e-3), "unit": UNIT, "positions_per_s": total_all / (per * 1e-3), "ms_per_step": per, "steps": steps, "queries": m_total,
-           "occurrences": total_all, "pattern_len": ln, "sa_sample_rate": 32, "scaling": "strong", "walk_ms": walk_ms, "sort_ms": sort_ms,
-           "sort_share_of_locate": sort_ms / max(walk_ms + sort_ms, 1e-9), "clocks": clocks, "parity_on_sample": bad == 0 and parity.get("count_parity_on_sample", True),
-           "parity": parity,
-           "exchange": "none" if ex is None else "kernel stores of counts + position slabs into every rank's gathered buffer (CUDA IPC) + 2 x 4-byte NCCL barrier",
+           "occurrences": total_all, "occurrences_per_query": total_all / m_total, "pattern_len": ln, "sa_sample_rate": 32, "scaling": "strong",
+           "chunks": nchunk, "queries_per_chunk": chunk_q, "walk_ms_sampled_chunks": walk_ms, "sort_ms_sampled_chunks": sort_ms,
+           "sort_share_of_locate": sort_ms / kern_ms, "clocks": clocks, "parity_on_sample": bad == 0 and parity.get("count_parity_on_sample", True), "parity": parity,
+           "exchange": "none" if ex is None else "kernel stores of counts + position slabs into every rank's gathered buffer (CUDA IPC) + 2 x 4-byte NCCL barrier per chunk",
            "e2e": {"value": cx.world * k / (ms_e2e / e2e_steps * 1e-3), "unit": UNIT, "positions_per_s": cx.world * tot_k / (ms_e2e / e2e_steps * 1e-3),
-                   "ms_per_step": ms_e2e / e2e_steps, "queries": k, "h2d_bytes_per_step": k * 16, "d2h_bytes_per_step": tot_k * 8 + (k + 1) * 8,
-                   "api": "fmx_locate_batch (host int64 intervals in, pinned int64 positions out)", "slice": "all queries" if k == m else "first %d queries of the shard (time-bounded)" % k},
-           "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": req_occ * 64 * total_local / ((walk_ms + sort_ms) * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src,
-                        "frac": req_occ * 64 * total_local / ((walk_ms + sort_ms) * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "locate_kernel (+ per-query sort)",
-                        "kernel_ms": walk_ms + sort_ms, "lf_steps_per_occurrence": lf_steps / max(total_local, 1), "requests_per_occurrence": req_occ,
-                        "request_rate": {"achieved_requests_per_s": req_occ * total_local / (walk_ms * 1e-3), "r_rand_requests_per_s": r_rand_gbs * 1e9 / 64,
-                                         "frac": req_occ * total_local / (walk_ms * 1e-3) / (r_rand_gbs * 1e9 / 64)},
+                   "ms_per_step": ms_e2e / e2e_steps, "queries": k, "h2d_bytes_per_step": k * 12 + 8, "d2h_bytes_per_step": tot_k * 8,
+                   "api": "fmx_locate_batch (host int64 intervals in, pinned int64 positions out)", "slice": "first %d queries of the shard (%d positions; time-bounded)" % (k, tot_k)},
+           "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": req_occ * 64 * stat_occ / (kern_ms * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src,
+                        "frac": req_occ * 64 * stat_occ / (kern_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "locate_kernel (+ radix sort of the (query, position) keys)",
+                        "kernel_ms": kern_ms, "lf_steps_per_occurrence": lf_steps / max(stat_occ, 1), "requests_per_occurrence": req_occ,
+                        "request_rate": {"achieved_requests_per_s": req_occ * stat_occ / (max(walk_ms, 1e-9) * 1e-3), "r_rand_requests_per_s": r_rand_gbs * 1e9 / 64,
+                                         "frac": req_occ * stat_occ / (max(walk_ms, 1e-9) * 1e-3) / (r_rand_gbs * 1e9 / 64)},
                         "survey_units": {"bytes_per_occurrence": 15.5 * L * 64 + 32, "note": "SURVEY 8(d): (rate-1)/2 LF steps x L x 64 B + one 32-B sample"}}}
     if ex is not None:
+        ex.close_peers()
+        cx.barrier()
         ex.close()
     return out
 
@@ -932,7 +965,7 @@ def regex_leg(cx, g, text, n_regexes, orc, steps):
            "e2e": {"value": cx.world * mr * steps / (ms_e2e * 1e-3), "unit": "regexes/s", "ms_per_step": ms_e2e / steps, "h2d_bytes_per_step": 0,
                    "d2h_bytes_per_step": total * 20 + (mr + 1) * 8, "api": "fmx_regex_set_search (device-resident set, host result buffers)"}}
     # one item = one backward step = at most two rank-block requests + the 16-byte state record and the ring slot
-    r_rand_gbs, _ = g.gather_bench(64, 2, 1 << 25, 16, 3)
+    r_rand_gbs, _ = g.gather_bench(64, 4, 1 << 25, 16, 3)
     peak, peak_src = measured_peaks()
     out["roofline"] = {"bound": "hbm", "unit": "GB/s", "achieved": items * 2 * 64 / (float(np.mean(kms)) * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src,
                        "frac": items * 2 * 64 / (float(np.mean(kms)) * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "regex_queue_kernel", "kernel_ms": float(np.mean(kms)),
@@ -1029,8 +1062,8 @@ def run_default(cx):
                 res = {"index": {k: info_e[k] for k in ("layout", "index_bytes", "kmer_k", "ctx_depth", "sigma", "sa_sample_rate", "open_s")}}
                 mq = max(1000, min(m, int(4_000_000 * min(1.0, scale * 10))))
                 res["count"] = guarded("english count", lambda: sweep_leg(cx, ge, text_e, [12, 16], mq, 5, orc_e, "cfg3 English-like, all accelerators", workload="cfg3"))
-                ml = max(1000, int(200_000 * min(1.0, scale * 10)))
-                res["locate"] = guarded("locate", lambda: locate_leg(cx, ge, text_e, ne, ml * cx.world if args.locate_weak else ml, 12, orc_e, max(2, min(args.steps, 5)), False))
+                ml = max(400, int(4000 * min(1.0, scale * 10)))      # ~5 x 10^8 occurrences at full size: one chunk, a fraction of a second per step
+                res["locate"] = guarded("locate", lambda: locate_leg(cx, ge, text_e, ne, ml, 12, orc_e, max(2, min(args.steps, 5)), chunk_q=ml))
                 res["regex"] = guarded("regex", lambda: regex_leg(cx, ge, text_e, args.regexes, orc_e, args.steps))
                 if orc_e is not None:
                     orc_e.close()
@@ -1097,10 +1130,10 @@ def run_workload(cx):
         return out
     text, base, g, info = english_open(cx, n)
     orc = load_oracle(base, w) if (cx.world == 1 and cx.rank == 0 and not args.no_cpu) else None
-    common = {"n_gpus": cx.world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+    common = {"n_gpus": cx.world, "steps": args.steps if w != "cfg3" else max(1, min(args.steps, 2 if m > 50_000 else args.steps)), "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
               "config": workload_config(args), "impl_config": {k: info[k] for k in ("layout", "index_bytes", "kmer_k", "ctx_depth", "sigma", "sa_sample_rate", "open_s")}}
     if w == "cfg3":
-        leg = locate_leg(cx, g, text, n, m, ln, orc, max(2, args.steps), True)
+        leg = locate_leg(cx, g, text, n, m, ln, orc, max(1, min(args.steps, 2 if m > 50_000 else args.steps)), chunk_q=4000)
         out = dict(common, metric=METRICS[w], value=leg["value"], unit=UNIT, ms_per_step=leg["ms_per_step"], scaling="strong", clocks=leg["clocks"], e2e=leg["e2e"],
                    roofline=leg["roofline"], locate={k: v for k, v in leg.items() if k not in ("e2e", "roofline", "clocks")})
         if orc is not None:
@@ -1155,7 +1188,6 @@ def main():
     ap.add_argument("--max-total-bytes", type=int, default=0, help="fmx_opts.max_total_bytes: cap on everything resident for an index")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1 count: fused peer-memory stores (default) or NCCL all-gather")
     ap.add_argument("--regexes", type=int, default=100_000, help="regexes per GPU of the regex leg")
-    ap.add_argument("--locate-weak", action="store_true", help="default line's locate leg: the same number of queries per GPU instead of in all")
     ap.add_argument("--chunk", type=int, default=0, help="queries per pipeline chunk of the host-buffer calls (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

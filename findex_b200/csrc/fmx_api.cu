@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -973,48 +974,56 @@ int fmx_extract_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t len,
 
 // ---- locate ---------------------------------------------------------------------------------------------------
 namespace {
-// Occurrences are processed in slabs of whole queries (<= 2^30 occurrences each, or one query of any size): LF walks into a
-// slab-sized scratch, then an ascending sort inside each query straight into d_pos (indexed by the batch-wide offsets).  No limit on
-// the number of occurrences of a batch other than the caller's buffer.
-std::atomic<int64_t> g_locate_slab{1ll << 30};               // occurrences per slab (fmx_set_locate_slab: tests exercise the slab seams)
+bool debug_sync() { static const bool on = std::getenv("FMX_DEBUG_SYNC") != nullptr; return on; }     // synchronise + check after each stage
+// Occurrences are processed in slabs of whole queries (<= 2^27 occurrences each, or one query of any size): the LF walks emit
+// (query, position) sort keys into slab-sized scratch, one radix sort orders the slab — ascending positions inside every query,
+// whatever the spread of the query sizes (English-like text: from 1 to millions of occurrences per pattern) — and the slab is handed
+// to the caller's sink.  A batch may hold any number of occurrences; device memory is bounded by the slab, not by the batch.
+std::atomic<int64_t> g_locate_slab{1ll << 27};
 int64_t locate_slab() { return g_locate_slab.load(); }
 
-int locate_core(fmx_index *ix, const uint32_t *d_sp, const int64_t *d_off, const int64_t *h_off, int64_t m, int64_t total, uint32_t *d_pos,
-                cudaStream_t st) {
+// sink(t0, cnt, d_keys): the cnt sorted keys of the occurrences [t0, t0 + cnt) of the batch (low 32 bits = position); is_u32 = the slab
+// was a single query and d_keys holds plain uint32 positions instead
+using SlabSink = std::function<int(int64_t, int64_t, const void *, bool)>;
+int locate_core(fmx_index *ix, const uint32_t *d_sp, const int64_t *d_off, const int64_t *h_off, int64_t m, int64_t total, cudaStream_t st, const SlabSink &sink) {
     ix->locate_walk_ms = ix->locate_sort_ms = 0.0;
     if (total <= 0) return FMX_OK;
-    const int64_t kLocateSlab = locate_slab();
+    const int64_t slab = locate_slab();
     std::vector<int64_t> cuts{0};                              // query indices where slabs begin
-    if (total > kLocateSlab) {
+    if (total > slab) {
         for (int64_t q = 0, t0 = 0; q < m; ++q)
-            if (h_off[q + 1] - t0 > kLocateSlab && q > cuts.back()) { cuts.push_back(q); t0 = h_off[q]; }
+            if (h_off[q + 1] - t0 > slab && q > cuts.back()) { cuts.push_back(q); t0 = h_off[q]; }
     }
     cuts.push_back(m);
     int64_t largest = 0;
     std::vector<int64_t> hb(cuts.size());
-    for (size_t k = 0; k < cuts.size(); ++k) hb[k] = (total > kLocateSlab) ? h_off[cuts[k]] : (k == 0 ? 0 : total);
+    for (size_t k = 0; k < cuts.size(); ++k) hb[k] = (total > slab) ? h_off[cuts[k]] : (k == 0 ? 0 : total);
     for (size_t k = 0; k + 1 < cuts.size(); ++k) largest = std::max(largest, hb[k + 1] - hb[k]);
-    DBuf tmp(st), dsteps(st);
-    CU(tmp.alloc((size_t)largest * 4));
+    DBuf ka(st), kb(st), dsteps(st);
+    CU(ka.alloc((size_t)largest * 8)); CU(kb.alloc((size_t)largest * 8));
     if (ix->stats) { CU(dsteps.alloc(8)); CU(cudaMemsetAsync(dsteps.p, 0, 8, st)); }
+    unsigned long long *steps = ix->stats ? dsteps.as<unsigned long long>() : nullptr;
     cudaEvent_t ev[3];
     for (auto &e : ev) CU(cudaEventCreate(&e));
     struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 3; ++i) cudaEventDestroy(e[i]); } } eg{ev};
     for (size_t k = 0; k + 1 < cuts.size(); ++k) {
         const int64_t q0 = cuts[k], q1 = cuts[k + 1], t0 = hb[k], cnt = hb[k + 1] - t0;
         if (cnt <= 0) continue;
+        const bool single = (q1 - q0 == 1);                    // one query: plain 32-bit positions
         CU(cudaEventRecord(ev[0], st));
-        CU(launch_locate(ix->d, ix->cfg, d_sp, d_off, q0, q1, t0, cnt, tmp.as<uint32_t>(), ix->stats ? dsteps.as<unsigned long long>() : nullptr, st));
+        CU(launch_locate(ix->d, ix->cfg, d_sp, d_off, q0, q1, t0, cnt, single ? ka.as<uint32_t>() : nullptr, single ? nullptr : ka.as<uint64_t>(), steps, st));
         CU(cudaEventRecord(ev[1], st));
-        // the sort reads/writes through the batch-wide offsets: both key pointers are biased by the slab's first occurrence
-        if (q1 - q0 == 1 || cnt >= (1ll << 31)) {
-            if (q1 - q0 != 1) return fail(FMX_E_LIMIT, "internal: slab of %lld occurrences over several queries", (long long)cnt);
-            CU(radix_sort_u32(tmp.as<uint32_t>(), d_pos + t0, cnt, st));
-        } else {
-            CU(segmented_sort_u32(tmp.as<uint32_t>() - t0, d_pos, cnt, q1 - q0, d_off + q0, st));
+        if (debug_sync()) { cudaError_t de = cudaStreamSynchronize(st); if (de != cudaSuccess) return fail(FMX_E_CUDA, "locate walk kernel failed: %s (slab %zu, queries %lld..%lld, %lld occurrences)", cudaGetErrorString(de), k, (long long)q0, (long long)q1, (long long)cnt); }
+        if (single) CU(radix_sort_u32(ka.as<uint32_t>(), kb.as<uint32_t>(), cnt, st));
+        else {
+            int seg_bits = 1;
+            while ((1ll << seg_bits) < q1 - q0) ++seg_bits;
+            CU(radix_sort_u64(ka.as<uint64_t>(), kb.as<uint64_t>(), cnt, 32 + seg_bits, st));
         }
         CU(cudaEventRecord(ev[2], st));
-        CU(cudaStreamSynchronize(st));
+        int rc = sink(t0, cnt, kb.p, single);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(st));                         // the scratch is reused by the next slab
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]);
         ix->locate_walk_ms += a; ix->locate_sort_ms += b;
@@ -1033,7 +1042,7 @@ int locate_core(fmx_index *ix, const uint32_t *d_sp, const int64_t *d_off, const
 
 // Device-resident locate: d_sp/d_ep = uint32 rows of m intervals (as fmx_count_fixed_dev leaves them; an empty interval has sp >= ep),
 // d_off[m+1] receives the exclusive offsets, d_pos[cap] the positions (uint32, ascending inside each query).  Synchronises `stream`
-// once to learn the total.  FMX_E_CAPACITY with *total_out set when cap is too small.
+// to learn the total (and once per slab).  FMX_E_CAPACITY with *total_out set when cap is too small.
 int fmx_locate_dev(fmx_index *ix, const void *d_sp, const void *d_ep, int64_t m, void *d_off, void *d_pos, int64_t cap, int64_t *total_out, void *stream) {
     CHECK_IX(ix);
     if (m < 0 || !d_off || !total_out || (m && (!d_sp || !d_ep))) return fail(FMX_E_ARG, "bad argument");
@@ -1059,7 +1068,13 @@ int fmx_locate_dev(fmx_index *ix, const void *d_sp, const void *d_ep, int64_t m,
         CU(cudaMemcpyAsync(h_off.data(), d_off, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
-    return locate_core(ix, (const uint32_t *)d_sp, (const int64_t *)d_off, h_off.empty() ? nullptr : h_off.data(), m, total, (uint32_t *)d_pos, st);
+    uint32_t *out = (uint32_t *)d_pos;
+    return locate_core(ix, (const uint32_t *)d_sp, (const int64_t *)d_off, h_off.empty() ? nullptr : h_off.data(), m, total, st,
+                       [&](int64_t t0, int64_t cnt, const void *keys, bool is_u32) -> int {
+                           if (is_u32) CU(cudaMemcpyAsync(out + t0, keys, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, st));
+                           else CU(launch_key_positions((const uint64_t *)keys, cnt, out + t0, nullptr, st));
+                           return FMX_OK;
+                       });
 }
 
 // Instrumentation for the roofline accounting: with stats on, locate calls also count the LF steps of their walks (one atomic per
@@ -1068,7 +1083,7 @@ int fmx_set_stats(fmx_index *ix, int32_t on) { CHECK_IX(ix); std::lock_guard<std
 int64_t fmx_last_steps(const fmx_index *ix) { return ix ? ix->last_steps : 0; }
 
 int fmx_set_locate_slab(int64_t occurrences) {
-    g_locate_slab = occurrences > 0 ? occurrences : (1ll << 30);
+    g_locate_slab = occurrences > 0 ? occurrences : (1ll << 27);
     return FMX_OK;
 }
 
@@ -1099,35 +1114,37 @@ int fmx_locate_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, int64_
     DeviceGuard g(ix->device);
     cudaStream_t st = ix->stream;
     ix->last_launches = 0;
-    DBuf dsp(st), doff(st), dsorted(st);
-    CU(dsp.alloc(m * 4)); CU(doff.alloc((m + 1) * 8)); CU(dsorted.alloc(total * 4));
+    DBuf dsp(st), doff(st), w0(st), w1(st);
+    CU(dsp.alloc(m * 4)); CU(doff.alloc((m + 1) * 8));
     CU(cudaMemcpyAsync(dsp.p, sp32.data(), m * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(doff.p, out_off, (m + 1) * 8, cudaMemcpyHostToDevice, st));
-    int rc = locate_core(ix, dsp.as<uint32_t>(), doff.as<int64_t>(), out_off, m, total, dsorted.as<uint32_t>(), st);
-    if (rc) return rc;
-    // widen to the ABI's int64 on the device and stream the slabs straight into the caller's buffer: the widening of
-    // slab k+1 overlaps the D2H of slab k (asynchronous DMA when `pos` is page-locked)
-    const int64_t slab = 32ll << 20;
-    DBuf w0(st), w1(st);
-    CU(w0.alloc((size_t)std::min(slab, total) * 8)); CU(w1.alloc((size_t)std::min(slab, total) * 8));
+    // every sorted slab is widened to the ABI's int64 on the device, in pieces that stream straight into the caller's buffer: the
+    // widening of piece k+1 overlaps the D2H of piece k (asynchronous DMA when `pos` is page-locked), and the copies of a slab overlap
+    // the LF walks of the next one
+    const int64_t piece = 32ll << 20;
+    CU(w0.alloc((size_t)std::min(piece, total) * 8)); CU(w1.alloc((size_t)std::min(piece, total) * 8));
     CU(cudaEventRecord(ix->ev_alloc, st));
     CU(cudaStreamWaitEvent(ix->d2h, ix->ev_alloc, 0));
     cudaEvent_t done[2];
     CU(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
-    for (int64_t o = 0, k = 0; o < total && rc == FMX_OK; o += slab, ++k) {
-        const int64_t cnt = std::min(slab, total - o);
-        int64_t *w = (k & 1) ? w1.as<int64_t>() : w0.as<int64_t>();
-        cudaError_t e = cudaSuccess;
-        if (k >= 2) e = cudaStreamWaitEvent(st, done[k & 1], 0);              // the slab buffer is free again
-        if (e == cudaSuccess) e = widen_u32_i64(dsorted.as<uint32_t>() + o, w, cnt, st);
-        if (e == cudaSuccess) e = cudaEventRecord(ix->ev1, st);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ix->d2h, ix->ev1, 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(pos + o, w, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ix->d2h);
-        if (e == cudaSuccess) e = cudaEventRecord(done[k & 1], ix->d2h);
-        if (e != cudaSuccess) rc = fail(FMX_E_CUDA, "CUDA error %s in the locate copy-out (%s)", cudaGetErrorName(e), cudaGetErrorString(e));
-    }
+    struct Ev2 { cudaEvent_t *e; ~Ev2() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } ev2{done};
+    int64_t pieces = 0;
+    int rc = locate_core(ix, dsp.as<uint32_t>(), doff.as<int64_t>(), out_off, m, total, st,
+                         [&](int64_t t0, int64_t cnt, const void *keys, bool is_u32) -> int {
+                             for (int64_t o = 0; o < cnt; o += piece, ++pieces) {
+                                 const int64_t c = std::min(piece, cnt - o);
+                                 int64_t *w = (pieces & 1) ? w1.as<int64_t>() : w0.as<int64_t>();
+                                 if (pieces >= 2) CU(cudaStreamWaitEvent(st, done[pieces & 1], 0));          // the piece buffer is free again
+                                 if (is_u32) CU(widen_u32_i64((const uint32_t *)keys + o, w, c, st));
+                                 else CU(launch_key_positions((const uint64_t *)keys + o, c, nullptr, w, st));
+                                 CU(cudaEventRecord(ix->ev1, st));
+                                 CU(cudaStreamWaitEvent(ix->d2h, ix->ev1, 0));
+                                 CU(cudaMemcpyAsync(pos + t0 + o, w, (size_t)c * 8, cudaMemcpyDeviceToHost, ix->d2h));
+                                 CU(cudaEventRecord(done[pieces & 1], ix->d2h));
+                             }
+                             return FMX_OK;
+                         });
     cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(ix->d2h);
-    cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
     if (rc == FMX_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) rc = fail(FMX_E_CUDA, "CUDA error while draining the locate copy-out");
     return rc;
 }
@@ -1547,6 +1564,54 @@ int fmx_build_index_files(const uint8_t *text, int64_t len, const char *base, in
     int rc = build_bwt_impl(text, len, device, bwt, &eof, counts, write_fm ? &fm : nullptr);
     if (rc) return rc;
     return write_index_files(strip_extension(base), bwt.data(), (int64_t)bwt.size(), eof, counts, big_endian != 0, write_fm ? fm.data() : nullptr);
+}
+
+// bwtFm2LCP (util.scala:153-212): lcp[r] = longest common prefix of the suffixes of rows r and r+1 (lcp[n-1] = 0), computed on the device
+// from the suffix array, its inverse and T' (built for the call by the parallel LF chain walks).
+int fmx_build_lcp(fmx_index *ix, int32_t *lcp_out) {
+    CHECK_IX(ix);
+    if (!lcp_out) return fail(FMX_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    const int64_t n = ix->n;
+    if (n <= 2) { for (int64_t r = 0; r < n; ++r) lcp_out[r] = 0; return FMX_OK; }
+    DBuf sa(st), isa(st), text(st), lcp(st);
+    CU(sa.alloc((size_t)n * 4)); CU(isa.alloc((size_t)n * 4)); CU(text.alloc((size_t)n + 16)); CU(lcp.alloc((size_t)n * 4));
+    std::string err;
+    cudaError_t e = build_full_sa(ix->d_full, ix->cfg.layout, sa.as<uint32_t>(), isa.as<uint32_t>(), text.as<uint8_t>(), st, err);
+    if (e != cudaSuccess) return fail(err.empty() ? FMX_E_CUDA : FMX_E_FORMAT, "suffix array construction failed: %s", err.empty() ? cudaGetErrorString(e) : err.c_str());
+    CU(build_lcp(sa.as<uint32_t>(), isa.as<uint32_t>(), text.as<uint8_t>(), n, lcp.as<int32_t>(), st));
+    CU(cudaMemcpyAsync(lcp_out, lcp.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FMX_OK;
+}
+
+// LCPCreator(filename).create()  (bwtmerger.scala:558-652): <base>.lcp = big-endian int32, no header; entry k-1 is written for every row
+// k >= 1 (and entry 0 for row 0), so the file holds max(n-1, 1) entries — LCPLoader (:176-211) reads them back.
+int fmx_write_lcp_file(fmx_index *ix, const char *path) {
+    CHECK_IX(ix);
+    if (!path) return fail(FMX_E_ARG, "null argument");
+    std::vector<int32_t> h((size_t)ix->n);
+    int rc = fmx_build_lcp(ix, h.data());
+    if (rc) return rc;
+    const int64_t entries = std::max<int64_t>(ix->n - 1, 1);
+    const std::string file = strip_extension(path) + ".lcp";
+    FILE *f = std::fopen(file.c_str(), "wb");
+    if (!f) return fail(FMX_E_IO, "cannot create %s", file.c_str());
+    std::vector<uint8_t> buf(1 << 20);
+    bool ok = true;
+    for (int64_t i = 0; ok && i < entries;) {
+        size_t k = 0;
+        for (; k + 4 <= buf.size() && i < entries; ++i, k += 4) {
+            const uint32_t v = (uint32_t)h[(size_t)i];
+            buf[k] = (uint8_t)(v >> 24); buf[k + 1] = (uint8_t)(v >> 16); buf[k + 2] = (uint8_t)(v >> 8); buf[k + 3] = (uint8_t)v;
+        }
+        ok = std::fwrite(buf.data(), 1, k, f) == k;
+    }
+    std::fclose(f);
+    if (!ok) return fail(FMX_E_IO, "short write %s", file.c_str());
+    return FMX_OK;
 }
 
 // SACreator.create (bwtmerger.scala:535-556): <base>.sa = n x int32 big-endian, no header, sa[r] as bwtFm2sa (util.scala:213-224).

@@ -419,6 +419,37 @@ cudaError_t build_full_sa(const DevIndex &ix, int layout, uint32_t *d_sa, uint32
     return cudaGetLastError();
 }
 
+// LCP array = bwtFm2LCP (util.scala:153-212) / LCPCreator.create (bwtmerger.scala:583-650): lcp[r] = longest common prefix of the suffixes
+// of rows r and r+1.  The reference walks the text positions in order carrying h-1 from one to the next (Kasai et al.); here every
+// thread owns a run of kLcpRun consecutive text positions and does the same inside its run (h restarts at 0 at the run's first
+// position, which only costs that one comparison its head start).  Characters are compared through T' directly; like the reference's
+// fm walk, the neighbour's characters wrap around the end of T' (the unique '$' always stops the comparison first).
+constexpr int kLcpRun = 64;
+__global__ void lcp_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ isa, const uint8_t *__restrict__ text, int64_t n,
+                           int32_t *__restrict__ lcp) {
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kLcpRun;
+    int64_t h = 0;
+    for (int64_t i = i0; i < i0 + kLcpRun && i < n; ++i) {
+        const uint32_t k = isa[i];
+        if (k == 0) { h = 0; continue; }                    // row 0 ('$'): the reference stores LCP(0) = 0, row 1 stores it again
+        const int64_t j = sa[k - 1];
+        while (i + h < n) {
+            int64_t q = j + h;
+            if (q >= n) q -= n;
+            if (text[i + h] != text[q]) break;
+            ++h;
+        }
+        lcp[k - 1] = (int32_t)h;
+        if (h > 0) --h;
+    }
+}
+cudaError_t build_lcp(const uint32_t *d_sa, const uint32_t *d_isa, const uint8_t *d_text, int64_t n, int32_t *d_lcp, cudaStream_t st) {
+    CK(cudaMemsetAsync(d_lcp, 0, (size_t)n * 4, st));
+    const int64_t threads = (n + kLcpRun - 1) / kLcpRun;
+    lcp_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(d_sa, d_isa, d_text, n, d_lcp);
+    return cudaGetLastError();
+}
+
 // k-mer table: entry idx <-> the K-byte pattern P with P[K-1-j] = sym[digit_j(idx)] (digit 0 most significant = the byte search()
 // consumes first, i.e. the LAST pattern byte); entry = (sp,ep) after those K backward steps, (0,0) when the interval is empty.
 // Built level by level: level 1 is (C[c], C[c+1]); an entry of level j+1 is one backward step from its parent idx/sigma of level j

@@ -28,6 +28,8 @@ cudaError_t build_ctx(const uint32_t *d_sa, const uint32_t *d_isa, const uint8_t
                       int raw, const CtxHops &hops, uint4 *d_ctx, cudaStream_t st);
 cudaError_t build_ctx8(const uint32_t *d_sa, const uint32_t *d_isa, const uint8_t *d_text, const uint8_t *d_code, int64_t n, int J,
                        uint2 *d_ctx8, cudaStream_t st);
+// d_lcp[r] = lcp(suffix of row r, suffix of row r+1), d_lcp[n-1] = 0   (bwtFm2LCP, util.scala:153-212)
+cudaError_t build_lcp(const uint32_t *d_sa, const uint32_t *d_isa, const uint8_t *d_text, int64_t n, int32_t *d_lcp, cudaStream_t st);
 // (sp,ep) after the first K backward steps for every K-mer over the sigma occurring symbols
 cudaError_t build_kmer_table(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, uint32_t sigma, int K, uint2 *d_table, cudaStream_t st);
 // suffix sort of t+'$' (t has no zero bytes) -> BWT, eof row, byte counts; optionally the suffix array

@@ -53,12 +53,9 @@ cudaError_t sort_pairs_u8_u32(const uint8_t *k_in, uint8_t *k_out, const uint32_
     FMX_CUB2(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k_in, k_out, v_in, v_out, n, 0, 8, st),
              cub::DeviceRadixSort::SortPairs(tp, bytes, k_in, k_out, v_in, v_out, n, 0, 8, st));
 }
-cudaError_t segmented_sort_u32(const uint32_t *k_in, uint32_t *k_out, int64_t n, int64_t nseg, const int64_t *d_off,
-                               cudaStream_t st) {
-    if (n >= (1ll << 31) || nseg >= (1ll << 31)) return cudaErrorInvalidValue;
-    const long long *o = reinterpret_cast<const long long *>(d_off);
-    FMX_CUB2(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, k_in, k_out, (int)n, (int)nseg, o, o + 1, st),
-             cub::DeviceSegmentedSort::SortKeys(tp, bytes, k_in, k_out, (int)n, (int)nseg, o, o + 1, st));
+cudaError_t radix_sort_u64(const uint64_t *k_in, uint64_t *k_out, int64_t n, int end_bit, cudaStream_t st) {
+    FMX_CUB2(cub::DeviceRadixSort::SortKeys(nullptr, bytes, k_in, k_out, n, 0, end_bit, st),
+             cub::DeviceRadixSort::SortKeys(tp, bytes, k_in, k_out, n, 0, end_bit, st));
 }
 cudaError_t radix_sort_u32(const uint32_t *k_in, uint32_t *k_out, int64_t n, cudaStream_t st) {
     FMX_CUB2(cub::DeviceRadixSort::SortKeys(nullptr, bytes, k_in, k_out, n, 0, 32, st),

@@ -18,9 +18,8 @@ cudaError_t sort_pairs_u64_u32(const uint64_t *k_in, uint64_t *k_out, const uint
                                int begin_bit, int end_bit, cudaStream_t st);
 cudaError_t sort_pairs_u8_u32(const uint8_t *k_in, uint8_t *k_out, const uint32_t *v_in, uint32_t *v_out, int64_t n,
                               cudaStream_t st);
-// ascending sort inside each segment; offsets has nseg+1 int64 entries
-cudaError_t segmented_sort_u32(const uint32_t *k_in, uint32_t *k_out, int64_t n, int64_t nseg, const int64_t *d_off,
-                               cudaStream_t st);
+// ascending sort of 64-bit keys on bits [0, end_bit): the (query, position) keys of a locate slab
+cudaError_t radix_sort_u64(const uint64_t *k_in, uint64_t *k_out, int64_t n, int end_bit, cudaStream_t st);
 // plain ascending sort (one segment of any size)
 cudaError_t radix_sort_u32(const uint32_t *k_in, uint32_t *k_out, int64_t n, cudaStream_t st);
 cudaError_t widen_u32_i64(const uint32_t *d_in, int64_t *d_out, int64_t n, cudaStream_t st);

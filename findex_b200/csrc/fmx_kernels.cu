@@ -268,7 +268,8 @@ next_substr_kernel(const __grid_constant__ DevIndex ix, const long long *__restr
 template <int G, int LAYOUT>
 __global__ void __launch_bounds__(kThreads)
 locate_kernel(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ sp, const long long *__restrict__ off,
-              long long q0, long long q1, long long t0, long long count, uint32_t *__restrict__ pos, unsigned long long *steps_out) {
+              long long q0, long long q1, long long t0, long long count, uint32_t *__restrict__ pos, unsigned long long *__restrict__ key,
+              unsigned long long *steps_out) {
     __shared__ SharedTables tb;
     load_tables(tb, ix);
     __syncthreads();
@@ -279,8 +280,11 @@ locate_kernel(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ 
     long long lo = q0, hi = q1;
     while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (off[mid] <= T) lo = mid; else hi = mid; }
     uint32_t r = sp[lo] + (uint32_t)(T - off[lo]);
+    // output: the position alone (a slab that is one query), or the sort key (query index inside the slab, position) of the per-query ordering
+    const unsigned long long seg = (unsigned long long)(lo - q0) << 32;
+#define FMX_EMIT(P) do { if ((threadIdx.x % G) == 0) { if (key) key[t] = seg | (unsigned long long)(P); else pos[t] = (P); } } while (0)
     if (ix.sa != nullptr) {                                    // full suffix array resident: one load per occurrence
-        if ((threadIdx.x % G) == 0) pos[t] = ix.sa[r];
+        FMX_EMIT(ix.sa[r]);
         return;
     }
     uint32_t k = 0;
@@ -290,23 +294,41 @@ locate_kernel(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ 
             walk_block<G>(ix.bm, r, c, marked);
             if (marked) {
                 const uint32_t mr = rank_one<G>(ix.mark, r, nullptr);
-                if ((threadIdx.x % G) == 0) { pos[t] = ix.samples[mr] + k; if (steps_out) atomicAdd(steps_out, (unsigned long long)k); }
+                FMX_EMIT(ix.samples[mr] + k);
+                if ((threadIdx.x % G) == 0 && steps_out) atomicAdd(steps_out, (unsigned long long)k);
                 return;
             }
             r = lf_value<G, LAYOUT>(ix, tb, c, r);
-            if (++k > ix.n) { if ((threadIdx.x % G) == 0) pos[t] = 0xFFFFFFFFu; return; }      // cannot happen on a consistent index (fmx_open checks)
+            if (++k > ix.n) { FMX_EMIT(0xFFFFFFFFu); return; }      // cannot happen on a consistent index (fmx_open checks)
         }
     }
     for (;;) {
         uint32_t bit;
         const uint32_t mr = rank_one<G>(ix.mark, r, &bit);
         if (bit) {                                         // row eof (sa = 0) is always sampled, so '$' is never stepped over
-            if ((threadIdx.x % G) == 0) { pos[t] = ix.samples[mr] + k; if (steps_out) atomicAdd(steps_out, (unsigned long long)k); }
+            FMX_EMIT(ix.samples[mr] + k);
+            if ((threadIdx.x % G) == 0 && steps_out) atomicAdd(steps_out, (unsigned long long)k);
             return;
         }
         r = lf_value<G, LAYOUT>(ix, tb, ix.bwt[r], r);
-        if (++k > ix.n) { if ((threadIdx.x % G) == 0) pos[t] = 0xFFFFFFFFu; return; }
+        if (++k > ix.n) { FMX_EMIT(0xFFFFFFFFu); return; }
     }
+#undef FMX_EMIT
+}
+
+// low words of the sorted (query, position) keys: the positions, ascending inside each query — as uint32 (device callers) or widened
+// to the ABI's int64 (host callers)
+template <typename OutT>
+__global__ void key_positions_kernel(const unsigned long long *__restrict__ key, long long n, OutT *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (OutT)(key[i] & 0xFFFFFFFFull);
+}
+cudaError_t launch_key_positions(const uint64_t *d_key, int64_t n, uint32_t *d_out32, int64_t *d_out64, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (d_out32) key_positions_kernel<uint32_t><<<grid, 256, 0, st>>>((const unsigned long long *)d_key, n, d_out32);
+    else key_positions_kernel<long long><<<grid, 256, 0, st>>>((const unsigned long long *)d_key, n, (long long *)d_out64);
+    return cudaGetLastError();
 }
 
 // 2-bit symbol codes -> pattern bytes: thread t writes four consecutive bytes of one pattern (its packed byte t % ceil(len/4))
@@ -529,9 +551,9 @@ cudaError_t launch_next_substr(const DevIndex &ix, LaunchCfg cfg, const int64_t 
 }
 
 cudaError_t launch_locate(const DevIndex &ix, LaunchCfg cfg, const uint32_t *d_sp, const int64_t *d_off, int64_t q0, int64_t q1,
-                          int64_t t0, int64_t count, uint32_t *d_pos, unsigned long long *d_steps, cudaStream_t st) {
+                          int64_t t0, int64_t count, uint32_t *d_pos, uint64_t *d_key, unsigned long long *d_steps, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-#define CALL(G, LAY) locate_kernel<G, LAY><<<grid_for(count, G), kThreads, 0, st>>>(ix, d_sp, (const long long *)d_off, q0, q1, t0, count, d_pos, d_steps)
+#define CALL(G, LAY) locate_kernel<G, LAY><<<grid_for(count, G), kThreads, 0, st>>>(ix, d_sp, (const long long *)d_off, q0, q1, t0, count, d_pos, (unsigned long long *)d_key, d_steps)
     FMX_DISPATCH(cfg, CALL);
 #undef CALL
     return cudaGetLastError();

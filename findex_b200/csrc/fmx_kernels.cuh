@@ -45,9 +45,12 @@ cudaError_t launch_next_substr(const DevIndex &ix, LaunchCfg cfg, const int64_t 
 cudaError_t launch_prev_substr(const DevIndex &ix, LaunchCfg cfg, const int64_t *d_row, int64_t m, int len,
                                uint8_t *d_out, cudaStream_t st);
 // locate: one work item per occurrence of the queries [q0, q1) — occurrences [t0, t0 + count) of the batch, d_off[m+1] = exclusive
-// offsets over the whole batch; writes the unsorted sa values of the slab to d_pos[0 .. count)
+// offsets over the whole batch; writes the unsorted sa values of the slab to d_pos[0 .. count), or — d_key != nullptr — the sort keys
+// ((query - q0) << 32 | sa value) of the per-query ordering to d_key[0 .. count)
 cudaError_t launch_locate(const DevIndex &ix, LaunchCfg cfg, const uint32_t *d_sp, const int64_t *d_off, int64_t q0, int64_t q1,
-                          int64_t t0, int64_t count, uint32_t *d_pos, unsigned long long *d_steps_or_null, cudaStream_t st);
+                          int64_t t0, int64_t count, uint32_t *d_pos, uint64_t *d_key, unsigned long long *d_steps_or_null, cudaStream_t st);
+// low 32 bits of n sorted keys -> uint32 (d_out32) or int64 (d_out64)
+cudaError_t launch_key_positions(const uint64_t *d_key, int64_t n, uint32_t *d_out32, int64_t *d_out64, cudaStream_t st);
 // m patterns of `len` 2-bit codes ((len+3)/4 bytes each) -> m x len bytes; alpha4 = the four symbols, symbol i in byte i
 cudaError_t launch_unpack2(const uint8_t *d_codes, int len, int64_t m, uint32_t alpha4, uint8_t *d_out, cudaStream_t st);
 // d_out[q] = ep[q] - sp[q] (0 when empty) for q < m, d_out[m] = 0

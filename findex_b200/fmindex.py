@@ -532,6 +532,18 @@ class GpuFMSearcher:
         lib().fmx_write_sa_file.argtypes = [C.c_void_p, C.c_char_p]
         _check(lib().fmx_write_sa_file(self.h, os.fsencode(path)))
 
+    def build_lcp(self):
+        """bwtFm2LCP: int32[n], lcp[r] = lcp(suffix of row r, suffix of row r+1)"""
+        lib().fmx_build_lcp.argtypes = [C.c_void_p, C.c_void_p]
+        out = np.zeros(self.n, np.int32)
+        _check(lib().fmx_build_lcp(self.h, _ptr(out)))
+        return out
+
+    def write_lcp_file(self, path):
+        """LCPCreator(path).create(): <base>.lcp, max(n-1, 1) x int32 big-endian"""
+        lib().fmx_write_lcp_file.argtypes = [C.c_void_p, C.c_char_p]
+        _check(lib().fmx_write_lcp_file(self.h, os.fsencode(path)))
+
     def set_accel_mask(self, mask):
         """keep only the accelerators in `mask` (ACCEL_* bits; ACCEL_NONE = plain rank steps, ACCEL_AUTO = all built) for later calls"""
         _check(lib().fmx_set_accel_mask(self.h, mask))
@@ -547,6 +559,42 @@ class GpuFMSearcher:
 
     def last_regex_levels(self):
         return lib().fmx_last_regex_levels(self.h)
+
+
+class LCPSearcher(GpuFMSearcher):
+    """new LCPSearcher(filename, bigEndian) — bwtmerger.scala:322-333: a NaiveFMSearcher that also opens <base>.lcp and <base>.sa
+    (LCPLoader :176-211, SALoader :214-249; both created on demand here, by the GPU, when absent) and offers LCPSuffixWalkingAlgo's
+    getLCP(i) and getStringOn(i).  The reference's getStringOn reads the cached forward text file from offset fsize - sa[i] up to
+    the next 0 byte, i.e. the characters T'[sa[i]-1], T'[sa[i]-2], ... — the same bytes an LF walk from row i emits, which is how
+    they are produced here (no .data file needed)."""
+
+    def __init__(self, filename, bigEndian=True, **opts):
+        super().__init__(filename, bigEndian, **opts)
+        base = os.path.splitext(filename)[0]
+        if not os.path.exists(base + ".lcp"):
+            self.write_lcp_file(base)
+        if not os.path.exists(base + ".sa"):
+            self.write_sa_file(base)
+        self._lcp = np.memmap(base + ".lcp", dtype=">i4", mode="r")
+        self._sa = np.memmap(base + ".sa", dtype=">i4", mode="r")
+
+    def getLCP(self, i):
+        return int(self._lcp[i])
+
+    def getSA(self, i):
+        return int(self._sa[i])
+
+    def getStringOn(self, i, chunk=256):
+        """iterator over the characters the reference's StringPosReader yields: up to (not including) the first 0 byte"""
+        done = 0
+        while True:
+            s = self.prev_substr_batch([i], chunk)[0]              # one LF walk of `chunk` steps on the GPU; grown until the '\0' shows
+            z = s.find(b"\0")
+            for ch in s[done:(z if z >= 0 else len(s))]:
+                yield chr(ch)
+            if z >= 0 or chunk >= self.n:
+                return
+            done, chunk = len(s), min(self.n, chunk * 4)
 
 
 class PinnedArray:

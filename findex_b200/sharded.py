@@ -238,6 +238,14 @@ class GpuExchange:
         self.barrier()
         return out
 
+    def close_peers(self):
+        """unmap the peers' buffers (every rank does this, then a barrier, before anyone frees its own)"""
+        for buf in (self.counts, self.values):
+            for p in list(buf.peers.values()):
+                self.fx.lib().fmx_ipc_close(p)
+            buf.peers = {}
+
     def close(self):
+        self.close_peers()
         self.counts.close()
         self.values.close()

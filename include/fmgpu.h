@@ -291,6 +291,13 @@ int fmx_build_bwt(const uint8_t *text, int64_t len, uint8_t *bwt_out, int64_t *n
  * sa[r] as bwtFm2sa (M/util.scala:213-224).  Uses the resident suffix array when the index has one, else builds it for the call.      */
 int fmx_write_sa_file(fmx_index *ix, const char *path);
 
+/* LCPCreator(filename).create()  M/bwtmerger.scala:558-652 == Util.bwtstring.bwtFm2LCP  M/util.scala:153-212 (the consistency the reference's
+ * LCPLoaderTest asserts, T/Indexer.scala:1017-1042): lcp[r] = longest common prefix of the suffixes of rows r and r+1, computed on the device.
+ * fmx_build_lcp fills lcp_out[n] (lcp[n-1] = 0, never written by the reference); fmx_write_lcp_file writes <base>.lcp as the reference does —
+ * big-endian int32, no header, the first max(n-1, 1) entries (LCPLoader :176-211; LCPSearcher.getLCP(i) :328 reads entry i).           */
+int fmx_build_lcp(fmx_index *ix, int32_t *lcp_out);
+int fmx_write_lcp_file(fmx_index *ix, const char *path);
+
 #ifdef __cplusplus
 }
 #endif

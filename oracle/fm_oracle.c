@@ -238,6 +238,48 @@ const uint32_t *fmo_build_sa(fmo_index *ix) {
     return ix->sa;
 }
 
+/* bwtFm2LCP: M/util.scala:153-212 (== LCPCreator.create M/bwtmerger.scala:583-650, which writes the same values to <base>.lcp).
+ * Walks the text positions i = 0..n-1 through k = fm(k) starting at the eof row; for row k it compares the suffix of row k with the
+ * suffix of row j = k-1 character by character — ibs2c(row) = the F-column character of a row, iterChar advancing both rows by fm —
+ * carrying h-1 over to the next text position, and stores h at LCP(k-1); row 0 stores LCP(0) = 0.  out[n]: LCP(n-1) is never written
+ * (stays 0); the file holds the first max(n-1, 1) entries. */
+static int ibs2c(const fmo_index *ix, int64_t i) {           /* bs.indexWhere(i < _, 0) - 1 ; no such index: -1 - 1 */
+    for (int j = 0; j < ALPHA; j++) if (i < ix->bs[j]) return j - 1;
+    return -2;
+}
+static int iter_char(const fmo_index *ix, int64_t j, int64_t h, int64_t *temp) {
+    if (h != 0 && *temp == -1) {
+        while (h > 0) { j = ix->fm[j]; h--; }
+        *temp = j;
+    } else if (*temp != -1) {
+        j = ix->fm[*temp];
+        *temp = j;
+    }
+    return ibs2c(ix, j);
+}
+void fmo_build_lcp(const fmo_index *ix, int32_t *out) {
+    const int64_t n = ix->n;
+    for (int64_t r = 0; r < n; r++) out[r] = 0;
+    int64_t i = 0, k = ix->eof, h = 0;
+    while (i < n) {
+        if (k == 0) out[k] = 0;
+        else {
+            int64_t temp1 = -1, temp2 = -1, j = k - 1;
+            int stop = 0;
+            while (i + h < n && !stop) {
+                int64_t t1 = temp1, t2 = temp2;
+                const int c1 = iter_char(ix, k, h, &t1), c2 = iter_char(ix, j, h, &t2);
+                if (c1 == c2) { temp1 = t1; temp2 = t2; h++; }
+                else stop = 1;
+            }
+            out[k - 1] = (int32_t)h;
+        }
+        if (h > 0) h--;
+        k = ix->fm[k];
+        i++;
+    }
+}
+
 static int cmp_i64(const void *a, const void *b) { int64_t x = *(const int64_t *)a, y = *(const int64_t *)b; return (x > y) - (x < y); }
 
 /* locate(sp,ep) := sorted { sa[r] : r in [sp,ep) }   (T' coordinates) */

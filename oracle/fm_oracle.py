@@ -75,6 +75,8 @@ def lib():
         L.fmo_prev_substr.argtypes = [p, i64, i64, p]
         L.fmo_build_sa.restype = p
         L.fmo_build_sa.argtypes = [p]
+        L.fmo_build_lcp.argtypes = [p, p]
+        L.fmo_build_lcp.restype = None
         L.fmo_locate.restype = i64
         L.fmo_locate.argtypes = [p, i64, i64, p]
         L.fmo_count_batch.argtypes = [p, p, p, i64, p, p, C.c_int]
@@ -218,6 +220,13 @@ class OracleIndex:
 
     def sa(self):
         return np.ctypeslib.as_array(C.cast(lib().fmo_build_sa(self.h), C.POINTER(C.c_uint32)), shape=(self.n,))
+
+    def lcp(self):
+        """bwtFm2LCP (M/util.scala:153-212): int32[n], LCP[r] = lcp(suffix of row r, suffix of row r+1), LCP[n-1] = 0 (never written);
+        LCPCreator's .lcp file holds the first max(n-1, 1) entries, big-endian int32 (M/bwtmerger.scala:583-650, LCPLoader :176-211)."""
+        out = np.zeros(self.n, np.int32)
+        lib().fmo_build_lcp(self.h, _ptr(out))
+        return out
 
     def locate(self, sp, ep):
         out = np.zeros(max(ep - sp, 1), np.int64)

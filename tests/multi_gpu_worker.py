@@ -55,6 +55,9 @@ def main():
     assert [tuple(x) for x in rec.tolist()] == [(i, l, s, e) for i, w in enumerate(want) for (l, s, e) in w]
     dist.barrier()
     rset.close()
+    ex.close_peers()
+    ex2.close_peers()
+    dist.barrier()
     ex.close()
     ex2.close()
     g.close()

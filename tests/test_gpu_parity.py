@@ -504,6 +504,45 @@ def test_packed_two_bit_upload(sigma):
     o.close()
 
 
+def test_lcp_creator_and_searcher(ref_dir, tmp_path):
+    """fmx_build_lcp == bwtFm2LCP (util.scala:153-212) and fmx_write_lcp_file == LCPCreator.create's file (the equality the reference's
+    LCPLoaderTest asserts, T/Indexer.scala:1017-1042: file == bwtFm2LCP sliced to the file's length), on the reference's fixtures and on the
+    kind of text that test indexes (testdata/t2: digits); LCPSearcher.getLCP / getStringOn over the files."""
+    import shutil
+    rng = np.random.default_rng(21)
+    digits = bytes(rng.integers(48, 58, 5000, dtype=np.uint8)) + b"0123456789" * 40 + bytes(rng.integers(48, 58, 700, dtype=np.uint8))
+    cases = [("test1024.cmp", None), ("test.cmp", None), (None, digits), (None, b"a"), (None, b"ab"), (None, b"aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaa" * 20)]
+    for name, text in cases:
+        if name:
+            o = fo.OracleIndex.load(os.path.join(ref_dir, name), big_endian=False)
+            for ext in (".bwt", ".aux"):
+                shutil.copy(os.path.join(ref_dir, name + ext), tmp_path / ("c" + ext))
+            g = fx.GpuFMSearcher(str(tmp_path / "c.bwt"), bigEndian=False)
+        else:
+            bwt, eof, cnt = fo.build_bwt(fo.file_to_text_rev(text))
+            o = fo.OracleIndex.from_bwt(bwt, eof, cnt)
+            g = fx.GpuFMSearcher(bwt=bwt, eof=eof, counts=cnt, accel=fx.ACCEL_NONE)
+        want = o.lcp()
+        assert np.array_equal(g.build_lcp(), want), name or text[:20]
+        g.write_lcp_file(str(tmp_path / "c"))
+        f = np.fromfile(tmp_path / "c.lcp", dtype=">i4")
+        assert len(f) == max(o.n - 1, 1) and np.array_equal(f, want[:len(f)])
+        g.close()
+        o.close()
+    o = fo.OracleIndex.load(os.path.join(ref_dir, "test1024.cmp"), big_endian=False)
+    for ext in (".bwt", ".aux"):
+        shutil.copy(os.path.join(ref_dir, "test1024.cmp" + ext), tmp_path / ("s" + ext))
+    ls = fx.LCPSearcher(str(tmp_path / "s.bwt"), bigEndian=False)
+    sa, lcp = o.sa(), o.lcp()
+    text = open(os.path.join(ref_dir, "test1024.txt"), "rb").read()
+    for i in (0, 1, 5, 462, 700, 1023):
+        assert ls.getLCP(i) == lcp[i] and ls.getSA(i) == sa[i]
+        # the reference reads the forward text file from offset fsize - sa[i] up to a 0 byte (bwtmerger.scala:329-332)
+        assert "".join(ls.getStringOn(i, chunk=64)) == text[len(text) - int(sa[i]):].decode("latin-1")
+    ls.close()
+    o.close()
+
+
 def test_scatter_dev_single_gpu():
     """fmx_scatter_dev with this GPU playing three ranks: every rank's slab lands in every gathered buffer at the offset read from the device"""
     import torch
