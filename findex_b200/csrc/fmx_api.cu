@@ -1264,6 +1264,7 @@ struct fmx_regex_set {
     void *d_rec = nullptr, *d_rx = nullptr, *d_f = nullptr, *d_first = nullptr;
     void *d_ring = nullptr, *d_ctrl = nullptr;     // work ring (all slots empty between searches) and the traversal's control words
     int64_t ring_cap = 0;
+    uint32_t max_len = 0;                          // fmx_regex_set_limits
     std::mutex mu;                                 // one traversal at a time per set (they share the ring)
 };
 
@@ -1325,6 +1326,17 @@ int fmx_regex_set_create(fmx_index *ix, fmx_regex *const *rx, int64_t m, fmx_reg
     return FMX_OK;
 }
 
+// max_len = the maxLength of REParser.matchSA (re2.scala:568, :636-641): an item's follow positions are enqueued only while their len stays
+// below it; matches are emitted whatever their length; 0 = no limit.  Does not depend on the order in which items are taken, so the result
+// is still a well-defined multiset.  (The order-dependent caps — maxIterations, ReTree.matchSA's maxBranching — are not offered: which
+// results survive them depends on the reference's priority-queue tie order.)
+int fmx_regex_set_limits(fmx_regex_set *set, int64_t max_len) {
+    if (!set || max_len < 0 || max_len > 0xFFFFFFFFll) return fail(FMX_E_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(set->mu);
+    set->max_len = (uint32_t)max_len;
+    return FMX_OK;
+}
+
 // Pre-sizes (or shrinks) the set's work ring to `slots` (rounded up to a power of two, at least the number of start items): a ring that
 // turns out too small is abandoned and the traversal rerun with a 4x larger one, which this lets tests and memory-tight callers provoke.
 int fmx_regex_set_ring(fmx_regex_set *set, int64_t slots) {
@@ -1369,7 +1381,7 @@ int regex_search_core(fmx_index *ix, fmx_regex_set *set, RegexResult *d_res, int
     unsigned long long h[8] = {0};
     for (;;) {
         CU(launch_regex_search(ix->d, ix->cfg, rt, (const uint32_t *)set->d_first, n_first, (FrontierItem *)set->d_ring, set->ring_cap, d_res, cap_res,
-                               (unsigned long long *)set->d_ctrl, st));
+                               (unsigned long long *)set->d_ctrl, set->max_len, st));
         launches += 2;
         CU(cudaMemcpyAsync(h, set->d_ctrl, 64, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));

@@ -80,7 +80,7 @@ __global__ void regex_seed_kernel(const uint32_t *__restrict__ first, long long 
 template <int G, int LAYOUT>
 __global__ void __launch_bounds__(kThreads)
 regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ RegexTables rt, FrontierItem *ring, unsigned long long ring_mask,
-                   RegexResult *__restrict__ res, long long cap_res, unsigned long long *ctrl) {
+                   RegexResult *__restrict__ res, long long cap_res, unsigned long long *ctrl, uint32_t len_cap) {
     __shared__ SharedTables tb;
     load_tables(tb, ix);
     __syncthreads();
@@ -147,7 +147,8 @@ regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ 
         const bool emits = alive && (flags & 1u);
         const bool stop = emits && (flags & 2u);            // Glushkov: a last position emits and is not expanded (retree.scala:640-643)
         const bool too_deep = alive && nlen > ix.n;         // cannot happen for a match inside the text; guards runaway automata
-        const uint32_t nf = (alive && !stop && !too_deep) ? nf_all : 0u;
+        // REParser.matchSA's maxLength (re2.scala:636-641): follow positions are enqueued only while their len stays below it
+        const uint32_t nf = (alive && !stop && !too_deep && (len_cap == 0u || nlen < len_cap)) ? nf_all : 0u;
         if (too_deep && leader) atomicMax(&ctrl[kRxStatus], 2ull);
         if (alive && nlen > max_len) max_len = nlen;
 
@@ -252,7 +253,7 @@ regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ 
 
 cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, const RegexTables &rt, const uint32_t *d_first, int64_t n_first,
                                 FrontierItem *d_ring, int64_t ring_cap, RegexResult *d_res, int64_t cap_res, unsigned long long *d_ctrl,
-                                cudaStream_t st) {
+                                uint32_t max_len, cudaStream_t st) {
     if (ring_cap < n_first || (ring_cap & (ring_cap - 1))) return cudaErrorInvalidValue;
     int dev = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -267,7 +268,7 @@ cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, const RegexTa
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0);                                   \
         if (e == cudaSuccess) {                                                                                       \
             if (per_sm <= 0) e = cudaErrorLaunchOutOfResources;                                                       \
-            else k<<<(unsigned)(sms * per_sm), kThreads, 0, st>>>(ix, rt, d_ring, (unsigned long long)(ring_cap - 1), d_res, cap_res, d_ctrl); \
+            else k<<<(unsigned)(sms * per_sm), kThreads, 0, st>>>(ix, rt, d_ring, (unsigned long long)(ring_cap - 1), d_res, cap_res, d_ctrl, max_len); \
         }                                                                                                             \
     }
     if (cfg.layout == FMX_LAYOUT_PLANES) {

@@ -93,6 +93,7 @@ def lib():
     L.fmx_scatter_dev.argtypes = [p, i64, p, i32, i64, p, i64, p]
     L.fmx_regex_set_search_dev.argtypes = [p, p, p, i64, p, C.POINTER(i64)]
     L.fmx_regex_set_ring.argtypes = [p, i64]
+    L.fmx_regex_set_limits.argtypes = [p, i64]
     L.fmx_set_locate_slab.argtypes = [i64]
     L.fmx_set_stats.argtypes = [p, i32]
     L.fmx_last_steps.argtypes = [p]
@@ -232,6 +233,10 @@ class RegexSet:
                 continue
             _check(rc)
             return off, ln[:off[m]], sp[:off[m]], ep[:off[m]]
+
+    def set_limits(self, max_len=0):
+        """REParser.matchSA's maxLength for later searches of this set (0 = off)"""
+        _check(lib().fmx_regex_set_limits(self.h, max_len))
 
     def set_ring(self, slots):
         _check(lib().fmx_regex_set_ring(self.h, slots))

@@ -239,6 +239,12 @@ int  fmx_regex_set_search(fmx_index *ix, fmx_regex_set *set, int64_t cap_total, 
  * in d_res[cap]; d_off (int64[m+1], may be NULL) receives the index of every regex's first result; *total_out the number of results
  * (FMX_E_CAPACITY when it exceeds cap).  What a multi-GPU caller exchanges, and what fmx_regex_set_search copies out.        */
 int  fmx_regex_set_search_dev(fmx_index *ix, fmx_regex_set *set, void *d_res, int64_t cap, void *d_off_i64, int64_t *total_out);
+/* Length cap of later searches of the set: max_len = the maxLength argument of REParser.matchSA (M/re2/re2.scala:568, applied at :636-641) —
+ * an item's follow positions are enqueued only while their len stays below max_len, matches are emitted whatever their length; 0 = off.
+ * Order-independent, so the result is still a well-defined multiset (for the Glushkov engine, whose matchSA has no such argument, it is
+ * an extension with the same meaning).  The reference's order-dependent caps (maxIterations; ReTree.matchSA's maxBranching = 1024,
+ * maxIterations = 1000 defaults, retree.scala:570, :628) are not offered: what survives them depends on Scala's PriorityQueue tie order. */
+int  fmx_regex_set_limits(fmx_regex_set *set, int64_t max_len);
 /* Sizes the set's device work ring to `slots` items (power of two, >= the number of start positions; default: 4x the start positions,
  * at least 2^20).  A traversal that overflows its ring is abandoned and rerun with a 4x larger one — results never change.            */
 int  fmx_regex_set_ring(fmx_regex_set *set, int64_t slots);

@@ -323,7 +323,9 @@ typedef struct { int32_t st; int32_t len; int64_t sp, ep; } item_t;
 int64_t fmo_regex_match(const fmo_index *ix, int32_t nstates, const uint8_t *st_c, const uint8_t *st_last,
                         const int32_t *fol_off, const int32_t *fol, const int32_t *firsts, int32_t nfirsts,
                         int64_t cap, int32_t *out_len, int64_t *out_sp, int64_t *out_ep, int64_t max_expansions,
-                        int64_t *n_expansions, int stop_on_emit) {
+                        int64_t *n_expansions, int stop_on_emit, int64_t max_len) {
+    /* max_len = REParser.matchSA's maxLength (re2.scala:636-641): a new non-match state point is enqueued only while its len < maxLength
+     * (0 = no limit); matches are emitted whatever their length.  Independent of the order in which items are taken. */
     (void)nstates;
     size_t scap = 1024, top = 0; item_t *stk = (item_t *)malloc(scap * sizeof *stk);
     for (int32_t i = 0; i < nfirsts; i++) {
@@ -343,7 +345,7 @@ int64_t fmo_regex_match(const fmo_index *ix, int32_t nstates, const uint8_t *st_
             }
             /* Glushkov (retree.scala:638-645): a last position emits and is not expanded.  Thompson (re2.scala:636-641): the
              * MatchState of the closure emits, the other states of the same closure are still enqueued. */
-            if (!(st_last[q.st] && stop_on_emit)) {
+            if (!(st_last[q.st] && stop_on_emit) && (max_len == 0 || q.len + 1 < max_len)) {
                 for (int32_t k = fol_off[q.st]; k < fol_off[q.st + 1]; k++) {
                     if (top == scap) { scap *= 2; stk = (item_t *)realloc(stk, scap * sizeof *stk); }
                     stk[top++] = (item_t){ fol[k], q.len + 1, sp1, ep1 };

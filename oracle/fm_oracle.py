@@ -81,7 +81,7 @@ def lib():
         L.fmo_locate.argtypes = [p, i64, i64, p]
         L.fmo_count_batch.argtypes = [p, p, p, i64, p, p, C.c_int]
         L.fmo_regex_match.restype = i64
-        L.fmo_regex_match.argtypes = [p, i32, p, p, p, p, p, i32, i64, p, p, p, i64, C.POINTER(i64), C.c_int]
+        L.fmo_regex_match.argtypes = [p, i32, p, p, p, p, p, i32, i64, p, p, p, i64, C.POINTER(i64), C.c_int, i64]
         L.fmo_build_bwt.restype = C.c_int
         L.fmo_build_bwt.argtypes = [p, i64, p, C.POINTER(i64), p]
         _lib = L
@@ -245,7 +245,7 @@ class OracleIndex:
         return sp, ep
 
     # ---- Glushkov regex over the index: ReTree.matchSA uncapped (M/re2/retree.scala:570-653)
-    def regex_match_tables(self, tb, max_expansions=0, stop_on_emit=True):
+    def regex_match_tables(self, tb, max_expansions=0, stop_on_emit=True, max_len=0):
         nst = len(tb["c"])
         if nst == 0 or not tb["firsts"]:
             return [], 0
@@ -263,7 +263,7 @@ class OracleIndex:
             oep = np.zeros(cap, np.int64)
             nexp = C.c_int64(0)
             k = lib().fmo_regex_match(self.h, nst, _ptr(c), _ptr(last), _ptr(off), _ptr(fol), _ptr(fst), len(fst),
-                                      cap, _ptr(ol), _ptr(osp), _ptr(oep), max_expansions, C.byref(nexp), 1 if stop_on_emit else 0)
+                                      cap, _ptr(ol), _ptr(osp), _ptr(oep), max_expansions, C.byref(nexp), 1 if stop_on_emit else 0, max_len)
             if k == -2:
                 raise RuntimeError("regex traversal exceeded max_expansions")
             if k <= cap:
@@ -277,7 +277,8 @@ class OracleIndex:
         t = retree.compile_regex(regex, line_only)
         return self.regex_match_tables(t.tables(), max_expansions)[0]
 
-    def regex_match_thompson(self, regex, line_only=False, max_expansions=0):
-        """REParser.matchSA(createNFA(re2post(regex)), sa) uncapped (M/re2/re2.scala:568-693): sorted (len, sp, ep)."""
+    def regex_match_thompson(self, regex, line_only=False, max_expansions=0, max_len=0):
+        """REParser.matchSA(createNFA(re2post(regex)), sa, maxIterations = 0, maxLength = max_len) (M/re2/re2.scala:568-693): sorted
+        (len, sp, ep)."""
         tb = retree.compile_thompson(regex, line_only)
-        return self.regex_match_tables(tb, max_expansions, stop_on_emit=False)[0]
+        return self.regex_match_tables(tb, max_expansions, stop_on_emit=False, max_len=max_len)[0]

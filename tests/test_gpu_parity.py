@@ -410,6 +410,33 @@ def test_regex_ring_overflow_and_rerun(ref_dir, o1024, lanes):
     g.close()
 
 
+def test_thompson_max_length(ref_dir, o1024):
+    """REParser.matchSA(nfa, sa, maxLength = L) (re2.scala:568, :636-641): follow positions are enqueued only while len < L, matches are
+    emitted whatever their length — same multiset as the oracle for L = 1..6 and unlimited, Thompson engine; same meaning on Glushkov sets"""
+    g = _open(os.path.join(ref_dir, "test1024.cmp.bwt"), (fx.LAYOUT_PLANES, 2))
+    rxs = ["ab*c", "a.*b", "(a|b)c*d", "x.y.z", "qu*", "a(b|c)*d"]
+    trees = [fx.ThompsonNFA(r) for r in rxs]
+    rset = g.regex_set(trees)
+    for L in (1, 2, 3, 4, 6, 0):
+        rset.set_limits(L)
+        off, ln, sp, ep = rset.search(g)
+        for i, rx in enumerate(rxs):
+            got = list(zip(ln[off[i]:off[i + 1]].tolist(), sp[off[i]:off[i + 1]].tolist(), ep[off[i]:off[i + 1]].tolist()))
+            assert got == o1024.regex_match_thompson(rx, max_expansions=5_000_000, max_len=L), (rx, L)
+    rset.close()
+    gl = ["ab*c", "a.*b", "x(a|b)c*d"]
+    rset = g.regex_set([fx.ReTree(r) for r in gl])
+    from oracle import retree as _rt
+    for L in (2, 3, 0):
+        rset.set_limits(L)
+        off, ln, sp, ep = rset.search(g)
+        for i, rx in enumerate(gl):
+            got = list(zip(ln[off[i]:off[i + 1]].tolist(), sp[off[i]:off[i + 1]].tolist(), ep[off[i]:off[i + 1]].tolist()))
+            assert got == o1024.regex_match_tables(_rt.compile_regex(rx).tables(), 5_000_000, True, L)[0], (rx, L)
+    rset.close()
+    g.close()
+
+
 def test_regex_device_resident_results(ref_dir, o1024):
     """fmx_regex_set_search_dev: the ordered {regex, len, sp, ep} records and per-regex offsets, left on the device, equal what the host call
     returns — for a handful of results (one CTA's bitonic network) and for many (radix passes)."""
