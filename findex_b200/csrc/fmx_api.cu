@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstdio>
+#include <condition_variable>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -38,11 +39,16 @@ struct fmx_index {
     int sigma = 0, levels = 0, sample_rate = 0;
     int64_t nblk = 0, index_bytes = 0, n_samples = 0;
     std::vector<void *> owned;         // device allocations freed at close
-    double last_ms = 0.0, locate_walk_ms = 0.0, locate_sort_ms = 0.0;
+    std::atomic<double> last_ms{0.0}, locate_walk_ms{0.0}, locate_sort_ms{0.0};      // diagnostics of the most recent call
     bool stats = false;                // fmx_set_stats: the next locate / regex calls also count their LF steps / items
-    int64_t last_steps = 0;
-    int64_t last_launches = 0, total_launches = 0, last_levels = 0;
-    std::mutex mu;
+    std::atomic<int64_t> last_steps{0}, last_launches{0}, total_launches{0}, last_levels{0};
+    std::mutex mu;                     // guards cfg / d / chunk_queries / stats and the pool below; never held across GPU work
+    // Batch calls run concurrently: each takes one of kCallSets private stream sets for its duration (copies and kernels of different
+    // host threads overlap; the index itself is read-only).  `stream`/`h2d`/`d2h` above belong to fmx_open and the rare whole-index calls.
+    struct StreamSet { cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_alloc = nullptr; bool busy = false; };
+    static constexpr int kCallSets = 4;
+    StreamSet sets[kCallSets];
+    std::condition_variable cv;
 };
 
 namespace {
@@ -69,11 +75,53 @@ struct SaBuf {
     template <typename T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
+// One batch call's view of the index: a private stream set (taken from the pool for the call's duration) and a snapshot of the
+// settings, so that calls of different host threads neither serialise nor race with fmx_set_*.
+struct CallCtx {
+    fmx_index *ix;
+    fmx_index::StreamSet *set = nullptr;
+    cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_alloc = nullptr;
+    DevIndex d;
+    LaunchCfg cfg;
+    int64_t chunk_queries;
+    bool stats, ok = true;
+    explicit CallCtx(fmx_index *i) : ix(i) {
+        std::unique_lock<std::mutex> lk(ix->mu);
+        for (;;) {
+            for (auto &s : ix->sets) if (!s.busy) { set = &s; break; }
+            if (set) break;
+            ix->cv.wait(lk);
+        }
+        set->busy = true;
+        d = ix->d; cfg = ix->cfg; chunk_queries = ix->chunk_queries; stats = ix->stats;
+        if (!set->stream) {                                  // first use of this set
+            int prev = -1;
+            cudaGetDevice(&prev);
+            if (prev != ix->device) cudaSetDevice(ix->device);
+            ok = cudaStreamCreateWithFlags(&set->stream, cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaStreamCreateWithFlags(&set->h2d, cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaStreamCreateWithFlags(&set->d2h, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreate(&set->ev0) == cudaSuccess &&
+                 cudaEventCreate(&set->ev1) == cudaSuccess && cudaEventCreateWithFlags(&set->ev_alloc, cudaEventDisableTiming) == cudaSuccess;
+            if (prev >= 0 && prev != ix->device) cudaSetDevice(prev);
+        }
+        stream = set->stream; h2d = set->h2d; d2h = set->d2h; ev0 = set->ev0; ev1 = set->ev1; ev_alloc = set->ev_alloc;
+    }
+    ~CallCtx() {
+        { std::lock_guard<std::mutex> lk(ix->mu); set->busy = false; }
+        ix->cv.notify_one();
+    }
+    CallCtx(const CallCtx &) = delete;
+    CallCtx &operator=(const CallCtx &) = delete;
+};
+#define CHECK_CC(cc) do { if (!(cc).ok) return fail(FMX_E_CUDA, "cannot create CUDA streams/events for the call"); } while (0)
+
 struct Timed {
     fmx_index *ix;
-    explicit Timed(fmx_index *i) : ix(i) { cudaEventRecord(ix->ev0, ix->stream); ix->last_launches = 0; }
-    void stop() { cudaEventRecord(ix->ev1, ix->stream); }
-    void collect() { float ms = 0; if (cudaEventElapsedTime(&ms, ix->ev0, ix->ev1) == cudaSuccess) ix->last_ms = ms; }
+    CallCtx &cc;
+    Timed(fmx_index *i, CallCtx &c) : ix(i), cc(c) { cudaEventRecord(cc.ev0, cc.stream); ix->last_launches = 0; }
+    void stop() { cudaEventRecord(cc.ev1, cc.stream); }
+    void collect() { float ms = 0; if (cudaEventElapsedTime(&ms, cc.ev0, cc.ev1) == cudaSuccess) ix->last_ms = ms; }
 };
 
 int ensure_device(int device, int *chosen) {
@@ -473,6 +521,14 @@ int fmx_close(fmx_index *ix) {
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (void *p : ix->owned) cudaFree(p);
+    for (auto &st : ix->sets) {
+        if (st.stream) { cudaStreamSynchronize(st.stream); cudaStreamDestroy(st.stream); }
+        if (st.h2d) cudaStreamDestroy(st.h2d);
+        if (st.d2h) cudaStreamDestroy(st.d2h);
+        if (st.ev0) cudaEventDestroy(st.ev0);
+        if (st.ev1) cudaEventDestroy(st.ev1);
+        if (st.ev_alloc) cudaEventDestroy(st.ev_alloc);
+    }
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);
     if (ix->ev_alloc) cudaEventDestroy(ix->ev_alloc);
@@ -564,9 +620,9 @@ int fmx_host_free(void *p) {
     return FMX_OK;
 }
 int fmx_get_lanes(const fmx_index *ix) { return ix ? (ix->cfg.count_lanes ? ix->cfg.count_lanes : ix->cfg.lanes) : 0; }
-double fmx_last_kernel_ms(const fmx_index *ix) { return ix ? ix->last_ms : 0.0; }
-int64_t fmx_last_kernel_launches(const fmx_index *ix) { return ix ? ix->last_launches : 0; }
-int64_t fmx_last_regex_levels(const fmx_index *ix) { return ix ? ix->last_levels : 0; }
+double fmx_last_kernel_ms(const fmx_index *ix) { return ix ? ix->last_ms.load() : 0.0; }
+int64_t fmx_last_kernel_launches(const fmx_index *ix) { return ix ? ix->last_launches.load() : 0; }
+int64_t fmx_last_regex_levels(const fmx_index *ix) { return ix ? ix->last_levels.load() : 0; }
 
 // pos2char: bwtmerger.scala:376-385 (bucketStarts0 = prefix sums of the raw counts)
 int fmx_pos2char(const fmx_index *ix, int64_t key, int32_t *c) {
@@ -586,15 +642,16 @@ int fmx_occ_batch(fmx_index *ix, const uint8_t *c, const int64_t *key, int64_t m
     CHECK_IX(ix);
     if (m < 0 || (m && (!c || !key || !out))) return fail(FMX_E_ARG, "bad argument");
     if (m == 0) return FMX_OK;
-    std::lock_guard<std::mutex> lk(ix->mu);
+    CallCtx cc(ix);
+    CHECK_CC(cc);
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = cc.stream;
     DBuf dc(st), dk(st), dout(st);
     CU(dc.alloc(m)); CU(dk.alloc(m * 8)); CU(dout.alloc(m * 8));
     CU(cudaMemcpyAsync(dc.p, c, m, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(dk.p, key, m * 8, cudaMemcpyHostToDevice, st));
-    Timed t(ix);
-    CU(launch_occ(ix->d, ix->cfg, dc.as<uint8_t>(), dk.as<int64_t>(), m, dout.as<int64_t>(), st));
+    Timed t(ix, cc);
+    CU(launch_occ(cc.d, cc.cfg, dc.as<uint8_t>(), dk.as<int64_t>(), m, dout.as<int64_t>(), st));
     ix->last_launches = 1; ix->total_launches += 1;
     t.stop();
     CU(cudaMemcpyAsync(out, dout.p, m * 8, cudaMemcpyDeviceToHost, st));
@@ -609,16 +666,17 @@ int fmx_prev_range_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, co
     if (m == 0) return FMX_OK;
     for (int64_t i = 0; i < m; ++i)
         if (sp[i] < 0 || ep[i] < 0 || sp[i] > ix->n || ep[i] > ix->n) return fail(FMX_E_ARG, "row out of range at %lld", (long long)i);
-    std::lock_guard<std::mutex> lk(ix->mu);
+    CallCtx cc(ix);
+    CHECK_CC(cc);
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = cc.stream;
     DBuf dsp(st), dep(st), dc(st), o1(st), o2(st);
     CU(dsp.alloc(m * 8)); CU(dep.alloc(m * 8)); CU(dc.alloc(m)); CU(o1.alloc(m * 8)); CU(o2.alloc(m * 8));
     CU(cudaMemcpyAsync(dsp.p, sp, m * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(dep.p, ep, m * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(dc.p, c, m, cudaMemcpyHostToDevice, st));
-    Timed t(ix);
-    CU(launch_prev_range(ix->d, ix->cfg, dsp.as<int64_t>(), dep.as<int64_t>(), dc.as<uint8_t>(), m, o1.as<int64_t>(), o2.as<int64_t>(), st));
+    Timed t(ix, cc);
+    CU(launch_prev_range(cc.d, cc.cfg, dsp.as<int64_t>(), dep.as<int64_t>(), dc.as<uint8_t>(), m, o1.as<int64_t>(), o2.as<int64_t>(), st));
     ix->last_launches = 1; ix->total_launches += 1;
     t.stop();
     CU(cudaMemcpyAsync(sp1, o1.p, m * 8, cudaMemcpyDeviceToHost, st));
@@ -637,13 +695,14 @@ int fmx_interval_prev_range(fmx_index *ix, int64_t sp, int64_t ep, int cstart, i
     const int m = cend - cstart + 1;
     if (m <= 0) return FMX_OK;
     if (!out_c || !out_sp || !out_ep) return fail(FMX_E_ARG, "null argument");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    CallCtx cc(ix);
+    CHECK_CC(cc);
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = cc.stream;
     DBuf o1(st), o2(st);
     CU(o1.alloc(m * 8)); CU(o2.alloc(m * 8));
-    Timed t(ix);
-    CU(launch_interval_prev_range(ix->d, ix->cfg, sp, ep, cstart, cend, o1.as<int64_t>(), o2.as<int64_t>(), st));
+    Timed t(ix, cc);
+    CU(launch_interval_prev_range(cc.d, cc.cfg, sp, ep, cstart, cend, o1.as<int64_t>(), o2.as<int64_t>(), st));
     ix->last_launches = 1; ix->total_launches += 1;
     t.stop();
     std::vector<int64_t> a(m), b(m);
@@ -662,9 +721,10 @@ int fmx_interval_prev_range(fmx_index *ix, int64_t sp, int64_t ep, int cstart, i
 int fmx_count_fixed_dev(fmx_index *ix, const void *d_pat, int32_t len, int64_t m, void *d_sp, void *d_ep, void *stream) {
     CHECK_IX(ix);
     if (len < 0 || m < 0 || (m && (!d_sp || !d_ep || (len && !d_pat)))) return fail(FMX_E_ARG, "bad argument");
-    std::lock_guard<std::mutex> lk(ix->mu);                    // cfg and the launch counters are shared with the host-buffer calls; the launch is asynchronous
+    CallCtx cc(ix);
+    CHECK_CC(cc);                    // cfg and the launch counters are shared with the host-buffer calls; the launch is asynchronous
     DeviceGuard g(ix->device);
-    CU(launch_count_fixed(ix->d, ix->cfg, (const uint8_t *)d_pat, len, m, d_sp, d_ep, false, nullptr, (cudaStream_t)stream));
+    CU(launch_count_fixed(cc.d, cc.cfg, (const uint8_t *)d_pat, len, m, d_sp, d_ep, false, nullptr, (cudaStream_t)stream));
     ix->last_launches = 1; ix->total_launches += 1;
     return FMX_OK;
 }
@@ -685,9 +745,10 @@ int fmx_count_fixed_dev_gather(fmx_index *ix, const void *d_pat, int32_t len, in
     ps.n = n_sinks;
     ps.offset = offset;
     for (int j = 0; j < n_sinks; ++j) { if (!sinks[j]) return fail(FMX_E_ARG, "null sink %d", j); ps.p[j] = (uint32_t *)sinks[j]; }
-    std::lock_guard<std::mutex> lk(ix->mu);
+    CallCtx cc(ix);
+    CHECK_CC(cc);
     DeviceGuard g(ix->device);
-    CU(launch_count_fixed(ix->d, ix->cfg, (const uint8_t *)d_pat, len, m, d_sp, d_ep, false, nullptr, (cudaStream_t)stream, &ps));
+    CU(launch_count_fixed(cc.d, cc.cfg, (const uint8_t *)d_pat, len, m, d_sp, d_ep, false, nullptr, (cudaStream_t)stream, &ps));
     ix->last_launches = 1; ix->total_launches += 1;
     return FMX_OK;
 }
@@ -727,9 +788,10 @@ int fmx_memcpy_d2h(void *dst, const void *src, int64_t bytes) {
 // expanded to the alphabet's bytes on the device after crossing PCIe at a quarter of the size
 static int count_fixed_pipeline(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, int64_t *sp, int64_t *ep, uint32_t *counts,
                                 int32_t *sp32 = nullptr, int32_t *ep32 = nullptr, const uint8_t *packed2_alphabet = nullptr) {
-    std::lock_guard<std::mutex> lk(ix->mu);
+    CallCtx cc(ix);
+    CHECK_CC(cc);
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = cc.stream;
     const bool only_counts = counts != nullptr, narrow = sp32 != nullptr;     // narrow: 32-bit rows out (the reference's Int / uint32 rows)
     const bool packed = packed2_alphabet != nullptr;
     const int64_t wire_len = packed ? (len + 3) / 4 : len;                    // bytes per pattern on the wire
@@ -740,7 +802,7 @@ static int count_fixed_pipeline(fmx_index *ix, const uint8_t *pat, int32_t len, 
     if (packed) CU(dwire.alloc((size_t)m * wire_len));
     CU(dsp.alloc(m * ((only_counts || narrow) ? 4 : 8))); CU(dep.alloc(m * ((only_counts || narrow) ? 4 : 8)));
     if (only_counts) CU(dcnt.alloc(m * 4));
-    const int64_t chunk = ix->chunk_queries > 0 ? ix->chunk_queries : (1 << 20);
+    const int64_t chunk = cc.chunk_queries > 0 ? cc.chunk_queries : (1 << 20);
     const int64_t nchunks = (m + chunk - 1) / chunk;
     struct Events {                                            // destroyed on every exit path
         std::vector<cudaEvent_t> v;
@@ -750,46 +812,46 @@ static int count_fixed_pipeline(fmx_index *ix, const uint8_t *pat, int32_t len, 
     CU(evs_in.make((size_t)nchunks)); CU(evs_k.make((size_t)nchunks));
     std::vector<cudaEvent_t> &ev_in = evs_in.v, &ev_k = evs_k.v;
     // the copy streams may touch the stream-ordered allocations only after the allocating stream reached this point
-    CU(cudaEventRecord(ix->ev_alloc, st));
-    CU(cudaStreamWaitEvent(ix->h2d, ix->ev_alloc, 0));
-    CU(cudaStreamWaitEvent(ix->d2h, ix->ev_alloc, 0));
-    Timed t(ix);
+    CU(cudaEventRecord(cc.ev_alloc, st));
+    CU(cudaStreamWaitEvent(cc.h2d, cc.ev_alloc, 0));
+    CU(cudaStreamWaitEvent(cc.d2h, cc.ev_alloc, 0));
+    Timed t(ix, cc);
     int rc = FMX_OK;
     for (int64_t k = 0; k < nchunks && rc == FMX_OK; ++k) {
         const int64_t q0 = k * chunk, nq = std::min(chunk, m - q0);
         cudaError_t e = cudaSuccess;
         uint8_t *wire_dst = packed ? dwire.as<uint8_t>() + q0 * wire_len : dp.as<uint8_t>() + q0 * len;
-        if (len) e = cudaMemcpyAsync(wire_dst, pat + q0 * wire_len, (size_t)nq * wire_len, cudaMemcpyHostToDevice, ix->h2d);
-        if (e == cudaSuccess) e = cudaEventRecord(ev_in[(size_t)k], ix->h2d);
+        if (len) e = cudaMemcpyAsync(wire_dst, pat + q0 * wire_len, (size_t)nq * wire_len, cudaMemcpyHostToDevice, cc.h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_in[(size_t)k], cc.h2d);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev_in[(size_t)k], 0);
         if (e == cudaSuccess && packed && len) e = launch_unpack2(wire_dst, len, nq, alpha4, dp.as<uint8_t>() + q0 * len, st);
         if (e == cudaSuccess) {
             if (only_counts) {                       // ep-sp lands in dcnt through the kernel's fused-exchange sink; only that goes back
                 PeerSinks ps{};
                 ps.n = 1; ps.offset = q0; ps.p[0] = dcnt.as<uint32_t>();
-                e = launch_count_fixed(ix->d, ix->cfg, dp.as<uint8_t>() + q0 * len, len, nq, dsp.as<uint32_t>() + q0, dep.as<uint32_t>() + q0, false, nullptr, st, &ps);
+                e = launch_count_fixed(cc.d, cc.cfg, dp.as<uint8_t>() + q0 * len, len, nq, dsp.as<uint32_t>() + q0, dep.as<uint32_t>() + q0, false, nullptr, st, &ps);
             } else if (narrow) {
-                e = launch_count_fixed(ix->d, ix->cfg, dp.as<uint8_t>() + q0 * len, len, nq, dsp.as<uint32_t>() + q0, dep.as<uint32_t>() + q0, false, nullptr, st);
+                e = launch_count_fixed(cc.d, cc.cfg, dp.as<uint8_t>() + q0 * len, len, nq, dsp.as<uint32_t>() + q0, dep.as<uint32_t>() + q0, false, nullptr, st);
             } else {
-                e = launch_count_fixed(ix->d, ix->cfg, dp.as<uint8_t>() + q0 * len, len, nq, dsp.as<int64_t>() + q0, dep.as<int64_t>() + q0, true, nullptr, st);
+                e = launch_count_fixed(cc.d, cc.cfg, dp.as<uint8_t>() + q0 * len, len, nq, dsp.as<int64_t>() + q0, dep.as<int64_t>() + q0, true, nullptr, st);
             }
         }
         if (e == cudaSuccess) e = cudaEventRecord(ev_k[(size_t)k], st);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ix->d2h, ev_k[(size_t)k], 0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(cc.d2h, ev_k[(size_t)k], 0);
         if (only_counts) {
-            if (e == cudaSuccess) e = cudaMemcpyAsync(counts + q0, dcnt.as<uint32_t>() + q0, (size_t)nq * 4, cudaMemcpyDeviceToHost, ix->d2h);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(counts + q0, dcnt.as<uint32_t>() + q0, (size_t)nq * 4, cudaMemcpyDeviceToHost, cc.d2h);
         } else if (narrow) {
-            if (e == cudaSuccess) e = cudaMemcpyAsync(sp32 + q0, dsp.as<uint32_t>() + q0, (size_t)nq * 4, cudaMemcpyDeviceToHost, ix->d2h);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(ep32 + q0, dep.as<uint32_t>() + q0, (size_t)nq * 4, cudaMemcpyDeviceToHost, ix->d2h);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(sp32 + q0, dsp.as<uint32_t>() + q0, (size_t)nq * 4, cudaMemcpyDeviceToHost, cc.d2h);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(ep32 + q0, dep.as<uint32_t>() + q0, (size_t)nq * 4, cudaMemcpyDeviceToHost, cc.d2h);
         } else {
-            if (e == cudaSuccess) e = cudaMemcpyAsync(sp + q0, dsp.as<int64_t>() + q0, (size_t)nq * 8, cudaMemcpyDeviceToHost, ix->d2h);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(ep + q0, dep.as<int64_t>() + q0, (size_t)nq * 8, cudaMemcpyDeviceToHost, ix->d2h);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(sp + q0, dsp.as<int64_t>() + q0, (size_t)nq * 8, cudaMemcpyDeviceToHost, cc.d2h);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(ep + q0, dep.as<int64_t>() + q0, (size_t)nq * 8, cudaMemcpyDeviceToHost, cc.d2h);
         }
         if (e != cudaSuccess) rc = fail(FMX_E_CUDA, "CUDA error %s in the count pipeline (%s)", cudaGetErrorName(e), cudaGetErrorString(e));
     }
     ix->last_launches = nchunks * (packed ? 2 : 1); ix->total_launches += nchunks * (packed ? 2 : 1);
     t.stop();
-    cudaError_t e1 = cudaStreamSynchronize(ix->h2d), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(ix->d2h);
+    cudaError_t e1 = cudaStreamSynchronize(cc.h2d), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(cc.d2h);
     if (rc == FMX_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess))
         rc = fail(FMX_E_CUDA, "CUDA error while draining the count pipeline");
     t.collect();
@@ -839,15 +901,16 @@ int fmx_count_batch(fmx_index *ix, const uint8_t *pat, const int64_t *off, int64
     for (int64_t i = 0; i < m; ++i) if (off[i + 1] < off[i] || off[i] < 0) return fail(FMX_E_ARG, "offsets must be non-decreasing");
     const int64_t nbytes = off[m];
     if (nbytes && !pat) return fail(FMX_E_ARG, "null pattern buffer");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    CallCtx cc(ix);
+    CHECK_CC(cc);
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = cc.stream;
     DBuf dp(st), doff(st), dsp(st), dep(st);
     CU(dp.alloc(nbytes)); CU(doff.alloc((m + 1) * 8)); CU(dsp.alloc(m * 8)); CU(dep.alloc(m * 8));
     if (nbytes) CU(cudaMemcpyAsync(dp.p, pat, nbytes, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(doff.p, off, (m + 1) * 8, cudaMemcpyHostToDevice, st));
-    Timed t(ix);
-    CU(launch_count_var(ix->d, ix->cfg, dp.as<uint8_t>(), doff.as<int64_t>(), m, dsp.as<int64_t>(), dep.as<int64_t>(), st));
+    Timed t(ix, cc);
+    CU(launch_count_var(cc.d, cc.cfg, dp.as<uint8_t>(), doff.as<int64_t>(), m, dsp.as<int64_t>(), dep.as<int64_t>(), st));
     ix->last_launches = 1; ix->total_launches += 1;
     t.stop();
     CU(cudaMemcpyAsync(sp, dsp.p, m * 8, cudaMemcpyDeviceToHost, st));
@@ -860,14 +923,15 @@ int fmx_count_batch(fmx_index *ix, const uint8_t *pat, const int64_t *off, int64
 int fmx_count_fixed_stats(fmx_index *ix, const uint8_t *pat, int32_t len, int64_t m, int64_t *blocks, int64_t *steps) {
     CHECK_IX(ix);
     if (len < 0 || m < 0 || (m && len && !pat)) return fail(FMX_E_ARG, "bad argument");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    CallCtx cc(ix);
+    CHECK_CC(cc);
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = cc.stream;
     DBuf dp(st), dsp(st), dep(st), ds(st);
     CU(dp.alloc((size_t)m * len)); CU(dsp.alloc(m * 4)); CU(dep.alloc(m * 4)); CU(ds.alloc(16));
     if (m && len) CU(cudaMemcpyAsync(dp.p, pat, (size_t)m * len, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(ds.p, 0, 16, st));
-    CU(launch_count_fixed(ix->d, ix->cfg, dp.as<uint8_t>(), len, m, dsp.p, dep.p, false, ds.as<unsigned long long>(), st));
+    CU(launch_count_fixed(cc.d, cc.cfg, dp.as<uint8_t>(), len, m, dsp.p, dep.p, false, ds.as<unsigned long long>(), st));
     unsigned long long h[2] = {0, 0};
     CU(cudaMemcpyAsync(h, ds.p, 16, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -882,14 +946,15 @@ int fmx_get_prev_i_batch(fmx_index *ix, const int64_t *row, int64_t m, int64_t *
     if (m < 0 || (m && (!row || !out))) return fail(FMX_E_ARG, "bad argument");
     if (m == 0) return FMX_OK;
     for (int64_t i = 0; i < m; ++i) if (row[i] < 0 || row[i] >= ix->n) return fail(FMX_E_ARG, "row out of range at %lld", (long long)i);
-    std::lock_guard<std::mutex> lk(ix->mu);
+    CallCtx cc(ix);
+    CHECK_CC(cc);
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = cc.stream;
     DBuf dr(st), dout(st);
     CU(dr.alloc(m * 8)); CU(dout.alloc(m * 8));
     CU(cudaMemcpyAsync(dr.p, row, m * 8, cudaMemcpyHostToDevice, st));
-    Timed t(ix);
-    CU(launch_lf(ix->d, ix->cfg, dr.as<int64_t>(), m, dout.as<int64_t>(), st));
+    Timed t(ix, cc);
+    CU(launch_lf(cc.d, cc.cfg, dr.as<int64_t>(), m, dout.as<int64_t>(), st));
     ix->last_launches = 1; ix->total_launches += 1;
     t.stop();
     CU(cudaMemcpyAsync(out, dout.p, m * 8, cudaMemcpyDeviceToHost, st));
@@ -905,14 +970,15 @@ int fmx_prev_substr_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t 
     for (int64_t i = 0; i < m; ++i) if (row[i] < 0 || row[i] >= ix->n) return fail(FMX_E_ARG, "row out of range at %lld", (long long)i);
     if (out_len) for (int64_t i = 0; i < m; ++i) out_len[i] = len;      // prevSubstr never stops early (its eof flag is never set)
     if (len == 0) return FMX_OK;
-    std::lock_guard<std::mutex> lk(ix->mu);
+    CallCtx cc(ix);
+    CHECK_CC(cc);
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = cc.stream;
     DBuf dr(st), dout(st);
     CU(dr.alloc(m * 8)); CU(dout.alloc((size_t)m * len));
     CU(cudaMemcpyAsync(dr.p, row, m * 8, cudaMemcpyHostToDevice, st));
-    Timed t(ix);
-    CU(launch_prev_substr(ix->d, ix->cfg, dr.as<int64_t>(), m, len, dout.as<uint8_t>(), st));
+    Timed t(ix, cc);
+    CU(launch_prev_substr(cc.d, cc.cfg, dr.as<int64_t>(), m, len, dout.as<uint8_t>(), st));
     ix->last_launches = 1; ix->total_launches += 1;
     t.stop();
     CU(cudaMemcpyAsync(out, dout.p, (size_t)m * len, cudaMemcpyDeviceToHost, st));
@@ -926,14 +992,15 @@ int fmx_get_next_i_batch(fmx_index *ix, const int64_t *row, int64_t m, int64_t *
     if (m < 0 || (m && (!row || !out))) return fail(FMX_E_ARG, "bad argument");
     if (m == 0) return FMX_OK;
     for (int64_t i = 0; i < m; ++i) if (row[i] < 0 || row[i] >= ix->n) return fail(FMX_E_ARG, "row out of range at %lld", (long long)i);
-    std::lock_guard<std::mutex> lk(ix->mu);
+    CallCtx cc(ix);
+    CHECK_CC(cc);
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = cc.stream;
     DBuf dr(st), dout(st);
     CU(dr.alloc(m * 8)); CU(dout.alloc(m * 8));
     CU(cudaMemcpyAsync(dr.p, row, m * 8, cudaMemcpyHostToDevice, st));
-    Timed t(ix);
-    CU(launch_fl(ix->d, ix->cfg, dr.as<int64_t>(), m, dout.as<int64_t>(), st));
+    Timed t(ix, cc);
+    CU(launch_fl(cc.d, cc.cfg, dr.as<int64_t>(), m, dout.as<int64_t>(), st));
     ix->last_launches = 1; ix->total_launches += 1;
     t.stop();
     CU(cudaMemcpyAsync(out, dout.p, m * 8, cudaMemcpyDeviceToHost, st));
@@ -948,15 +1015,16 @@ int fmx_next_substr_batch(fmx_index *ix, const int64_t *row, int64_t m, int32_t 
     if (m == 0) return FMX_OK;
     for (int64_t i = 0; i < m; ++i) if (row[i] < 0 || row[i] >= ix->n) return fail(FMX_E_ARG, "row out of range at %lld", (long long)i);
     if (len == 0) { for (int64_t i = 0; i < m; ++i) out_len[i] = 0; return FMX_OK; }
-    std::lock_guard<std::mutex> lk(ix->mu);
+    CallCtx cc(ix);
+    CHECK_CC(cc);
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = cc.stream;
     DBuf dr(st), dout(st), dlen(st);
     CU(dr.alloc(m * 8)); CU(dout.alloc((size_t)m * len)); CU(dlen.alloc(m * 4));
     CU(cudaMemcpyAsync(dr.p, row, m * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(dout.p, 0, (size_t)m * len, st));
-    Timed t(ix);
-    CU(launch_next_substr(ix->d, ix->cfg, dr.as<int64_t>(), m, len, dout.as<uint8_t>(), dlen.as<int>(), st));
+    Timed t(ix, cc);
+    CU(launch_next_substr(cc.d, cc.cfg, dr.as<int64_t>(), m, len, dout.as<uint8_t>(), dlen.as<int>(), st));
     ix->last_launches = 1; ix->total_launches += 1;
     t.stop();
     CU(cudaMemcpyAsync(out, dout.p, (size_t)m * len, cudaMemcpyDeviceToHost, st));
@@ -985,8 +1053,9 @@ int64_t locate_slab() { return g_locate_slab.load(); }
 // sink(t0, cnt, d_keys): the cnt sorted keys of the occurrences [t0, t0 + cnt) of the batch (low 32 bits = position); is_u32 = the slab
 // was a single query and d_keys holds plain uint32 positions instead
 using SlabSink = std::function<int(int64_t, int64_t, const void *, bool)>;
-int locate_core(fmx_index *ix, const uint32_t *d_sp, const int64_t *d_off, const int64_t *h_off, int64_t m, int64_t total, cudaStream_t st, const SlabSink &sink) {
-    ix->locate_walk_ms = ix->locate_sort_ms = 0.0;
+int locate_core(fmx_index *ix, CallCtx &cc, const uint32_t *d_sp, const int64_t *d_off, const int64_t *h_off, int64_t m, int64_t total, cudaStream_t st, const SlabSink &sink) {
+    ix->locate_walk_ms = 0.0; ix->locate_sort_ms = 0.0;
+    double walk_ms = 0.0, sort_ms = 0.0;
     if (total <= 0) return FMX_OK;
     const int64_t slab = locate_slab();
     std::vector<int64_t> cuts{0};                              // query indices where slabs begin
@@ -1001,8 +1070,8 @@ int locate_core(fmx_index *ix, const uint32_t *d_sp, const int64_t *d_off, const
     for (size_t k = 0; k + 1 < cuts.size(); ++k) largest = std::max(largest, hb[k + 1] - hb[k]);
     DBuf ka(st), kb(st), dsteps(st);
     CU(ka.alloc((size_t)largest * 8)); CU(kb.alloc((size_t)largest * 8));
-    if (ix->stats) { CU(dsteps.alloc(8)); CU(cudaMemsetAsync(dsteps.p, 0, 8, st)); }
-    unsigned long long *steps = ix->stats ? dsteps.as<unsigned long long>() : nullptr;
+    if (cc.stats) { CU(dsteps.alloc(8)); CU(cudaMemsetAsync(dsteps.p, 0, 8, st)); }
+    unsigned long long *steps = cc.stats ? dsteps.as<unsigned long long>() : nullptr;
     cudaEvent_t ev[3];
     for (auto &e : ev) CU(cudaEventCreate(&e));
     struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 3; ++i) cudaEventDestroy(e[i]); } } eg{ev};
@@ -1011,7 +1080,7 @@ int locate_core(fmx_index *ix, const uint32_t *d_sp, const int64_t *d_off, const
         if (cnt <= 0) continue;
         const bool single = (q1 - q0 == 1);                    // one query: plain 32-bit positions
         CU(cudaEventRecord(ev[0], st));
-        CU(launch_locate(ix->d, ix->cfg, d_sp, d_off, q0, q1, t0, cnt, single ? ka.as<uint32_t>() : nullptr, single ? nullptr : ka.as<uint64_t>(), steps, st));
+        CU(launch_locate(cc.d, cc.cfg, d_sp, d_off, q0, q1, t0, cnt, single ? ka.as<uint32_t>() : nullptr, single ? nullptr : ka.as<uint64_t>(), steps, st));
         CU(cudaEventRecord(ev[1], st));
         if (debug_sync()) { cudaError_t de = cudaStreamSynchronize(st); if (de != cudaSuccess) return fail(FMX_E_CUDA, "locate walk kernel failed: %s (slab %zu, queries %lld..%lld, %lld occurrences)", cudaGetErrorString(de), k, (long long)q0, (long long)q1, (long long)cnt); }
         if (single) CU(radix_sort_u32(ka.as<uint32_t>(), kb.as<uint32_t>(), cnt, st));
@@ -1026,11 +1095,12 @@ int locate_core(fmx_index *ix, const uint32_t *d_sp, const int64_t *d_off, const
         CU(cudaStreamSynchronize(st));                         // the scratch is reused by the next slab
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]);
-        ix->locate_walk_ms += a; ix->locate_sort_ms += b;
+        walk_ms += a; sort_ms += b;
         ix->last_launches += 1; ix->total_launches += 1;
     }
-    ix->last_ms = ix->locate_walk_ms + ix->locate_sort_ms;
-    if (ix->stats) {
+    ix->locate_walk_ms = walk_ms; ix->locate_sort_ms = sort_ms;
+    ix->last_ms = walk_ms + sort_ms;
+    if (cc.stats) {
         unsigned long long hs = 0;
         CU(cudaMemcpyAsync(&hs, dsteps.p, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -1046,8 +1116,9 @@ int locate_core(fmx_index *ix, const uint32_t *d_sp, const int64_t *d_off, const
 int fmx_locate_dev(fmx_index *ix, const void *d_sp, const void *d_ep, int64_t m, void *d_off, void *d_pos, int64_t cap, int64_t *total_out, void *stream) {
     CHECK_IX(ix);
     if (m < 0 || !d_off || !total_out || (m && (!d_sp || !d_ep))) return fail(FMX_E_ARG, "bad argument");
-    if (ix->sample_rate <= 0 && ix->d.sa == nullptr) return fail(FMX_E_ARG, "index was opened without sa_sample_rate (and without a resident suffix array); locate unavailable");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    if (ix->sample_rate <= 0 && ix->d_full.sa == nullptr) return fail(FMX_E_ARG, "index was opened without sa_sample_rate (and without a resident suffix array); locate unavailable");
+    CallCtx cc(ix);
+    CHECK_CC(cc);
     DeviceGuard g(ix->device);
     cudaStream_t st = (cudaStream_t)stream;
     ix->last_launches = 0;
@@ -1069,7 +1140,7 @@ int fmx_locate_dev(fmx_index *ix, const void *d_sp, const void *d_ep, int64_t m,
         CU(cudaStreamSynchronize(st));
     }
     uint32_t *out = (uint32_t *)d_pos;
-    return locate_core(ix, (const uint32_t *)d_sp, (const int64_t *)d_off, h_off.empty() ? nullptr : h_off.data(), m, total, st,
+    return locate_core(ix, cc, (const uint32_t *)d_sp, (const int64_t *)d_off, h_off.empty() ? nullptr : h_off.data(), m, total, st,
                        [&](int64_t t0, int64_t cnt, const void *keys, bool is_u32) -> int {
                            if (is_u32) CU(cudaMemcpyAsync(out + t0, keys, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, st));
                            else CU(launch_key_positions((const uint64_t *)keys, cnt, out + t0, nullptr, st));
@@ -1079,8 +1150,9 @@ int fmx_locate_dev(fmx_index *ix, const void *d_sp, const void *d_ep, int64_t m,
 
 // Instrumentation for the roofline accounting: with stats on, locate calls also count the LF steps of their walks (one atomic per
 // occurrence — not for timed runs); regex searches always count their items.  fmx_last_steps returns the count of the last such call.
-int fmx_set_stats(fmx_index *ix, int32_t on) { CHECK_IX(ix); std::lock_guard<std::mutex> lk(ix->mu); ix->stats = on != 0; return FMX_OK; }
-int64_t fmx_last_steps(const fmx_index *ix) { return ix ? ix->last_steps : 0; }
+int fmx_set_stats(fmx_index *ix, int32_t on) { CHECK_IX(ix); CallCtx cc(ix);
+    CHECK_CC(cc); cc.stats = on != 0; return FMX_OK; }
+int64_t fmx_last_steps(const fmx_index *ix) { return ix ? ix->last_steps.load() : 0; }
 
 int fmx_set_locate_slab(int64_t occurrences) {
     g_locate_slab = occurrences > 0 ? occurrences : (1ll << 27);
@@ -1089,15 +1161,15 @@ int fmx_set_locate_slab(int64_t occurrences) {
 
 int fmx_last_locate_ms(const fmx_index *ix, double *walk_ms, double *sort_ms) {
     CHECK_IX(ix);
-    if (walk_ms) *walk_ms = ix->locate_walk_ms;
-    if (sort_ms) *sort_ms = ix->locate_sort_ms;
+    if (walk_ms) *walk_ms = ix->locate_walk_ms.load();
+    if (sort_ms) *sort_ms = ix->locate_sort_ms.load();
     return FMX_OK;
 }
 
 int fmx_locate_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, int64_t m, int64_t cap_total, int64_t *out_off, int64_t *pos) {
     CHECK_IX(ix);
     if (m < 0 || !out_off || (m && (!sp || !ep))) return fail(FMX_E_ARG, "bad argument");
-    if (ix->sample_rate <= 0 && ix->d.sa == nullptr) return fail(FMX_E_ARG, "index was opened without sa_sample_rate (and without a resident suffix array); locate unavailable");
+    if (ix->sample_rate <= 0 && ix->d_full.sa == nullptr) return fail(FMX_E_ARG, "index was opened without sa_sample_rate (and without a resident suffix array); locate unavailable");
     int64_t total = 0;
     std::vector<uint32_t> sp32((size_t)m);
     for (int64_t i = 0; i < m; ++i) {
@@ -1110,9 +1182,10 @@ int fmx_locate_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, int64_
     if (total > cap_total) return fail(FMX_E_CAPACITY, "locate needs %lld output slots, capacity %lld", (long long)total, (long long)cap_total);
     if (total == 0) return FMX_OK;
     if (!pos) return fail(FMX_E_ARG, "null output");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    CallCtx cc(ix);
+    CHECK_CC(cc);
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = cc.stream;
     ix->last_launches = 0;
     DBuf dsp(st), doff(st), w0(st), w1(st);
     CU(dsp.alloc(m * 4)); CU(doff.alloc((m + 1) * 8));
@@ -1123,13 +1196,13 @@ int fmx_locate_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, int64_
     // the LF walks of the next one
     const int64_t piece = 32ll << 20;
     CU(w0.alloc((size_t)std::min(piece, total) * 8)); CU(w1.alloc((size_t)std::min(piece, total) * 8));
-    CU(cudaEventRecord(ix->ev_alloc, st));
-    CU(cudaStreamWaitEvent(ix->d2h, ix->ev_alloc, 0));
+    CU(cudaEventRecord(cc.ev_alloc, st));
+    CU(cudaStreamWaitEvent(cc.d2h, cc.ev_alloc, 0));
     cudaEvent_t done[2];
     CU(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
     struct Ev2 { cudaEvent_t *e; ~Ev2() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } ev2{done};
     int64_t pieces = 0;
-    int rc = locate_core(ix, dsp.as<uint32_t>(), doff.as<int64_t>(), out_off, m, total, st,
+    int rc = locate_core(ix, cc, dsp.as<uint32_t>(), doff.as<int64_t>(), out_off, m, total, st,
                          [&](int64_t t0, int64_t cnt, const void *keys, bool is_u32) -> int {
                              for (int64_t o = 0; o < cnt; o += piece, ++pieces) {
                                  const int64_t c = std::min(piece, cnt - o);
@@ -1137,14 +1210,14 @@ int fmx_locate_batch(fmx_index *ix, const int64_t *sp, const int64_t *ep, int64_
                                  if (pieces >= 2) CU(cudaStreamWaitEvent(st, done[pieces & 1], 0));          // the piece buffer is free again
                                  if (is_u32) CU(widen_u32_i64((const uint32_t *)keys + o, w, c, st));
                                  else CU(launch_key_positions((const uint64_t *)keys + o, c, nullptr, w, st));
-                                 CU(cudaEventRecord(ix->ev1, st));
-                                 CU(cudaStreamWaitEvent(ix->d2h, ix->ev1, 0));
-                                 CU(cudaMemcpyAsync(pos + t0 + o, w, (size_t)c * 8, cudaMemcpyDeviceToHost, ix->d2h));
-                                 CU(cudaEventRecord(done[pieces & 1], ix->d2h));
+                                 CU(cudaEventRecord(cc.ev1, st));
+                                 CU(cudaStreamWaitEvent(cc.d2h, cc.ev1, 0));
+                                 CU(cudaMemcpyAsync(pos + t0 + o, w, (size_t)c * 8, cudaMemcpyDeviceToHost, cc.d2h));
+                                 CU(cudaEventRecord(done[pieces & 1], cc.d2h));
                              }
                              return FMX_OK;
                          });
-    cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(ix->d2h);
+    cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(cc.d2h);
     if (rc == FMX_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) rc = fail(FMX_E_CUDA, "CUDA error while draining the locate copy-out");
     return rc;
 }
@@ -1354,8 +1427,8 @@ int fmx_regex_set_ring(fmx_regex_set *set, int64_t slots) {
 
 namespace {
 // Runs the traversal of a set and leaves its results, ordered by (regex, len, sp, ep), in d_res (capacity cap_res).  *total_out = number of
-// results (also when it exceeds cap_res: then nothing is ordered and FMX_E_CAPACITY is returned).  Caller holds ix->mu and set->mu.
-int regex_search_core(fmx_index *ix, fmx_regex_set *set, RegexResult *d_res, int64_t cap_res, int64_t *total_out, cudaStream_t st) {
+// results (also when it exceeds cap_res: then nothing is ordered and FMX_E_CAPACITY is returned).  Caller holds a CallCtx and set->mu.
+int regex_search_core(fmx_index *ix, CallCtx &cc, fmx_regex_set *set, RegexResult *d_res, int64_t cap_res, int64_t *total_out, cudaStream_t st) {
     const int64_t n_first = (int64_t)set->n_first;
     *total_out = 0;
     if (set->m == 0 || n_first == 0) return FMX_OK;
@@ -1376,11 +1449,11 @@ int regex_search_core(fmx_index *ix, fmx_regex_set *set, RegexResult *d_res, int
         return FMX_OK;
     };
     if (set->ring_cap < n_first || set->d_ring == nullptr) { int rc = grow_ring(4 * n_first); if (rc) return rc; }
-    Timed t(ix);
+    Timed t(ix, cc);
     int64_t launches = 0;
     unsigned long long h[8] = {0};
     for (;;) {
-        CU(launch_regex_search(ix->d, ix->cfg, rt, (const uint32_t *)set->d_first, n_first, (FrontierItem *)set->d_ring, set->ring_cap, d_res, cap_res,
+        CU(launch_regex_search(cc.d, cc.cfg, rt, (const uint32_t *)set->d_first, n_first, (FrontierItem *)set->d_ring, set->ring_cap, d_res, cap_res,
                                (unsigned long long *)set->d_ctrl, set->max_len, st));
         launches += 2;
         CU(cudaMemcpyAsync(h, set->d_ctrl, 64, cudaMemcpyDeviceToHost, st));
@@ -1419,14 +1492,15 @@ int fmx_regex_set_search_dev(fmx_index *ix, fmx_regex_set *set, void *d_res, int
     CHECK_IX(ix);
     if (!set || !total_out || cap < 0 || (cap && !d_res)) return fail(FMX_E_ARG, "bad argument");
     if (set->device != ix->device) return fail(FMX_E_ARG, "regex set lives on device %d, index on device %d", set->device, ix->device);
-    std::lock_guard<std::mutex> lk(ix->mu);
+    CallCtx cc(ix);
+    CHECK_CC(cc);
     std::lock_guard<std::mutex> lk2(set->mu);
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = cc.stream;
     DBuf dummy(st);
     RegexResult *res = (RegexResult *)d_res;
     if (!res) { CU(dummy.alloc(sizeof(RegexResult))); res = dummy.as<RegexResult>(); }
-    int rc = regex_search_core(ix, set, res, cap, total_out, st);
+    int rc = regex_search_core(ix, cc, set, res, cap, total_out, st);
     if (rc) return rc;
     if (d_off) {
         CU(launch_result_offsets(res, *total_out, set->m, (int64_t *)d_off, st));
@@ -1442,15 +1516,16 @@ int fmx_regex_set_search(fmx_index *ix, fmx_regex_set *set, int64_t cap_total, i
     const int64_t m = set->m;
     if (m == 0 || set->n_first == 0) { for (int64_t i = 0; i <= m; ++i) out_off[i] = 0; return FMX_OK; }
     Phases ph("regex_set_search");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    CallCtx cc(ix);
+    CHECK_CC(cc);
     std::lock_guard<std::mutex> lk2(set->mu);
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = cc.stream;
     const int64_t cap_res = std::max<int64_t>(cap_total, 1 << 16);
     DBuf d_res(st), d_off(st), d_len(st), d_sp(st), d_ep(st);
     CU(d_res.alloc(cap_res * sizeof(RegexResult))); CU(d_off.alloc((m + 1) * 8));
     int64_t total = 0;
-    int rc = regex_search_core(ix, set, d_res.as<RegexResult>(), cap_res, &total, st);
+    int rc = regex_search_core(ix, cc, set, d_res.as<RegexResult>(), cap_res, &total, st);
     ph.mark("traversal + order");
     if (rc == FMX_E_CAPACITY || total > cap_total) {
         for (int64_t i = 0; i < m; ++i) out_off[i] = 0;

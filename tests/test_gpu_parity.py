@@ -570,6 +570,53 @@ def test_lcp_creator_and_searcher(ref_dir, tmp_path):
     o.close()
 
 
+def test_concurrent_host_threads(ref_dir):
+    """An opened index is immutable: batch calls of several host threads run concurrently (each on its own stream set) and every one
+    returns exactly what it returns alone — count (all three widths), locate, regex, LF/extraction mixed over 8 threads."""
+    import threading
+    text = open(os.path.join(ref_dir, "test.txt"), "rb").read()
+    o = fo.OracleIndex.load(os.path.join(ref_dir, "test.cmp"), big_endian=False)
+    g = fx.GpuFMSearcher(os.path.join(ref_dir, "test.cmp.bwt"), bigEndian=False, sa_sample_rate=8)
+    g.set_chunk(500)
+    rng = np.random.default_rng(77)
+    arr = np.stack([np.frombuffer(text[::-1][s:s + 9], np.uint8) for s in rng.integers(0, len(text) - 9, 4000)]).copy()
+    arr[::4, 3] = ord("#")
+    osp, oep = o.count_batch(arr.reshape(-1), np.arange(0, arr.size + 1, 9, dtype=np.int64))
+    sa = o.sa().astype(np.int64)
+    want_loc = np.concatenate([np.sort(sa[a:b]) for a, b in zip(osp[:300], oep[:300])])
+    rxs = ["ab.", "q(u|a)x?", "a.*b", "x[a-f]y"]
+    want_rx = [o.regex_match(r) for r in rxs]
+    rows = rng.integers(0, o.n, 200)
+    want_lf = g.get_prev_i_batch(rows)
+    errs = []
+
+    def worker(kind):
+        try:
+            for _ in range(6):
+                if kind == 0:
+                    sp, ep = g.count_fixed(arr)
+                    assert np.array_equal(sp, osp) and np.array_equal(ep, oep)
+                elif kind == 1:
+                    assert np.array_equal(g.count_only_fixed(arr).astype(np.int64), oep - osp)
+                elif kind == 2:
+                    off, pos = g.locate_batch(osp[:300], oep[:300])
+                    assert np.array_equal(pos, want_loc)
+                elif kind == 3:
+                    assert g.regex_search_batch([fx.ReTree(r) for r in rxs]) == want_rx
+                else:
+                    assert np.array_equal(g.get_prev_i_batch(rows), want_lf)
+        except Exception as e:                              # noqa: BLE001
+            errs.append((kind, repr(e)))
+    ths = [threading.Thread(target=worker, args=(k % 5,)) for k in range(8)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    g.close()
+    o.close()
+
+
 def test_scatter_dev_single_gpu():
     """fmx_scatter_dev with this GPU playing three ranks: every rank's slab lands in every gathered buffer at the offset read from the device"""
     import torch
