@@ -327,6 +327,9 @@ class Ctx:
     def ensure_index(self, workload, n):
         """text (every rank) + index files (rank 0 builds them on the GPU when absent)"""
         t0 = time.time()
+        import gc
+        gc.collect()
+        self.torch.cuda.empty_cache()                      # the suffix sort of a 4 GB text needs most of the device
         text = make_text(n, workload)
         base = index_base(n, workload)
         if self.rank == 0 and not (os.path.exists(base + ".bwt") and os.path.exists(base + ".aux")):
@@ -1033,17 +1036,22 @@ def run_default(cx):
     g.close()
     if "sweep" in extras and cx.rank == 0:
         def wm():
-            gw = fx.GpuFMSearcher(base + ".bwt", bigEndian=True, device=cx.local, layout=fx.LAYOUT_WM, accel=fx.ACCEL_NONE)
-            try:
-                info = gw.info()
-                recs = sweep_leg(cx, gw, text, [16], max(1000, min(m, int(2_000_000 * min(1.0, scale * 10)))), 3, orc,
-                                 "cfg2, wavelet matrix alone (north_star's structure, %.2f GB)" % (info["index_bytes"] / 1e9))
-                for r in recs:
+            recs = []
+            for lay, name in ((fx.LAYOUT_WM, "wavelet matrix alone (north_star's structure: binary levels, 64-byte blocks"),
+                              (fx.LAYOUT_WMX, "multi-ary wavelet matrix alone (16-ary levels, 128-byte blocks")):
+                gw = fx.GpuFMSearcher(base + ".bwt", bigEndian=True, device=cx.local, layout=lay, accel=fx.ACCEL_NONE)
+                try:
+                    info = gw.info()
+                    r = sweep_leg(cx, gw, text, [16], max(1000, min(m, int(2_000_000 * min(1.0, scale * 10)))), 3, orc,
+                                  "cfg2, %s; %.2f GB)" % (name, info["index_bytes"] / 1e9))[0]
                     r["index_bytes"] = info["index_bytes"]
-                    r["dedup_bytes_per_query"] = r["requests_per_query"] * 64          # SURVEY 8(d)'s dedup figure: distinct 64-B blocks of a WM search
-                return recs
-            finally:
-                gw.close()
+                    r["lanes_per_query"] = info["lanes_per_query"]
+                    if lay == fx.LAYOUT_WM:
+                        r["dedup_bytes_per_query"] = r["requests_per_query"] * 64          # SURVEY 8(d)'s dedup figure: distinct 64-B blocks of a WM search
+                    recs.append(r)
+                finally:
+                    gw.close()
+            return recs
         wm_recs = guarded("wm", wm)
         if isinstance(out.get("sweep"), list) and isinstance(wm_recs, list):
             out["sweep"] += wm_recs

@@ -37,7 +37,8 @@ struct fmx_index {
     int64_t C[257] = {0};
     int64_t counts0[256] = {0};        // raw counts (bucketStarts0 / pos2char)
     int sigma = 0, levels = 0, sample_rate = 0;
-    int64_t nblk = 0, index_bytes = 0, n_samples = 0;
+    int64_t nblk = 0, index_bytes = 0, n_samples = 0, rank_units64 = 0;
+    int api_layout = FMX_LAYOUT_WM;    // what fmx_info reports
     std::vector<void *> owned;         // device allocations freed at close
     std::atomic<double> last_ms{0.0}, locate_walk_ms{0.0}, locate_sort_ms{0.0};      // diagnostics of the most recent call
     bool stats = false;                // fmx_set_stats: the next locate / regex calls also count their LF steps / items
@@ -185,27 +186,54 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     const int64_t budget = o.max_index_bytes > 0 ? o.max_index_bytes : (64ll << 30);
     // max_total_bytes bounds EVERYTHING resident for this index (rank structure, BWT, sampled SA, accelerators); 0 = what the device holds
     const int64_t total_cap = o.max_total_bytes > 0 ? o.max_total_bytes : (1ll << 62);
-    if (o.max_total_bytes > 0 && wm_bytes + n > total_cap && layout != FMX_LAYOUT_PLANES)
+    if (o.max_total_bytes > 0 && wm_bytes + n > total_cap && layout != FMX_LAYOUT_PLANES && layout != FMX_LAYOUT_WMX)
         return fail(FMX_E_ARG, "max_total_bytes = %lld is below the smallest index of this text (%lld bytes: wavelet matrix + BWT)", (long long)total_cap, (long long)(wm_bytes + n));
+    // multi-ary wavelet matrix: 16-ary digits (4-ary when at most 4 symbols occur), 128-byte blocks
+    const int xb = sigma <= 4 ? 2 : 4, xlevels = sigma <= (1 << xb) ? 1 : 2;
+    const int64_t xrows = xb == 4 ? 128 : 448, nblkx = n / xrows + 1, wmx_bytes = (int64_t)xlevels * nblkx * 128;
     if (layout == FMX_LAYOUT_AUTO) {
         size_t fr = 0, to = 0;
         cudaMemGetInfo(&fr, &to);
         const int64_t sampled = o.sa_sample_rate > 0 ? nblk * 64 + (n / o.sa_sample_rate + 1) * 4 + (n / kRowsPerWalkBlock + 1) * 64 : 0;
-        layout = (planes_bytes <= budget && planes_bytes + n + sampled <= total_cap && planes_bytes + (6ll << 30) + 2 * n < (int64_t)fr) ? FMX_LAYOUT_PLANES : FMX_LAYOUT_WM;
+        layout = (planes_bytes <= budget && planes_bytes + n + sampled <= total_cap && planes_bytes + (6ll << 30) + 2 * n < (int64_t)fr) ? FMX_LAYOUT_PLANES
+                 : (wmx_bytes + n + sampled <= total_cap ? FMX_LAYOUT_WMX : FMX_LAYOUT_WM);
     }
-    if (layout != FMX_LAYOUT_WM && layout != FMX_LAYOUT_PLANES) return fail(FMX_E_ARG, "bad layout %d", layout);
-    int lanes = o.lanes_per_query ? o.lanes_per_query : 2;      // re-tuned below once the accelerators are known
+    if (layout != FMX_LAYOUT_WM && layout != FMX_LAYOUT_PLANES && layout != FMX_LAYOUT_WMX) return fail(FMX_E_ARG, "bad layout %d", layout);
+    const bool wmx = layout == FMX_LAYOUT_WMX;
+    ix->api_layout = layout;
+    int lanes = o.lanes_per_query ? o.lanes_per_query : (wmx ? 4 : 2);      // re-tuned below once the accelerators are known
     if (lanes != 1 && lanes != 2 && lanes != 4) return fail(FMX_E_ARG, "lanes_per_query must be 1, 2 or 4");
     ix->cfg = LaunchCfg{layout, lanes};
     if (const char *mb = std::getenv("FMX_MINB")) ix->cfg.min_blocks = std::atoi(mb);      // occupancy experiment (profiles/r01_count_design_sweep.jsonl)
-    ix->index_bytes = (layout == FMX_LAYOUT_PLANES ? planes_bytes : wm_bytes) + n;
+    ix->index_bytes = (layout == FMX_LAYOUT_PLANES ? planes_bytes : wmx ? wmx_bytes : wm_bytes) + n;
 
     // base[c]: PLANES: C[c].  WM: C[c] - start_final[code], where after `levels` stable bit partitions the
     // symbols are ordered by bit-reversed code; the '$' row travels with code 0.
-    uint32_t C32[257], base[256], z[8] = {0};
+    uint32_t C32[257], base[256], z[8] = {0}, zx[2][16] = {{0}};
     for (int c = 0; c <= 256; ++c) C32[c] = (uint32_t)ix->C[c];
     for (int c = 0; c < 256; ++c) base[c] = C32[c];
-    if (layout == FMX_LAYOUT_WM) {
+    if (wmx) {
+        // after the stable partitions by digit 0 (most significant), then digit 1, ... the codes are ordered by their digits read in
+        // reverse; zx[l][v] = rows whose digit at level l is below v
+        const int ncodes = 1 << (xb * xlevels), dm = (1 << xb) - 1;
+        std::vector<int64_t> cc((size_t)ncodes, 0);
+        for (int s = 0; s < sigma; ++s) cc[(size_t)s] = counts[sym[s]];
+        cc[0] += 1;                                              // the '$' row is filed under code 0
+        for (int l = 0; l < xlevels; ++l) {
+            int64_t per[16] = {0};
+            for (int s = 0; s < ncodes; ++s) per[(s >> (xb * (xlevels - 1 - l))) & dm] += cc[(size_t)s];
+            int64_t acc = 0;
+            for (int v = 0; v <= dm; ++v) { zx[l][v] = (uint32_t)acc; acc += per[v]; }
+        }
+        auto rev = [&](int s) { int r = 0; for (int l = 0; l < xlevels; ++l) r = (r << xb) | ((s >> (xb * l)) & dm); return r; };
+        std::vector<int> order((size_t)ncodes);
+        for (int s = 0; s < ncodes; ++s) order[(size_t)s] = s;
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return rev(a) < rev(b); });
+        std::vector<int64_t> start((size_t)ncodes, 0);
+        int64_t acc = 0;
+        for (int s : order) { start[(size_t)s] = acc; acc += cc[(size_t)s]; }
+        for (int s = 0; s < sigma; ++s) base[sym[s]] = (uint32_t)(ix->C[sym[s]] - start[(size_t)s]);
+    } else if (layout == FMX_LAYOUT_WM) {
         std::vector<int64_t> cc(1 << levels, 0);                 // occurrences per code ('$' under code 0)
         for (int s = 0; s < sigma; ++s) cc[s] = counts[sym[s]];
         cc[0] += 1;
@@ -240,11 +268,14 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     uint8_t *d_sym = dev_upload(ix, sym, 256, &e); CU(e);
     void *blocks = nullptr;
     const int64_t nplanes = layout == FMX_LAYOUT_PLANES ? std::max(sigma, 1) : levels;
-    e = cudaMalloc(&blocks, (size_t)nplanes * nblk * 64);
-    if (e != cudaSuccess) return fail(FMX_E_CUDA, "cannot allocate %lld bytes for the rank structure: %s", (long long)(nplanes * nblk * 64), cudaGetErrorString(e));
+    const int64_t rank_alloc = wmx ? wmx_bytes : nplanes * nblk * 64;
+    ix->rank_units64 = rank_alloc / 64;
+    e = cudaMalloc(&blocks, (size_t)rank_alloc);
+    if (e != cudaSuccess) return fail(FMX_E_CUDA, "cannot allocate %lld bytes for the rank structure: %s", (long long)rank_alloc, cudaGetErrorString(e));
     ix->owned.push_back(blocks);
-    CU(cudaMemsetAsync(blocks, 0, (size_t)nplanes * nblk * 64, ix->stream));
+    CU(cudaMemsetAsync(blocks, 0, (size_t)rank_alloc, ix->stream));
     if (layout == FMX_LAYOUT_PLANES) CU(build_planes(d_bwt, n, (uint32_t)eof, d_sym, sigma, (uint32_t *)blocks, nblk, ix->stream));
+    else if (wmx) CU(build_wmx(d_bwt, n, (uint32_t)eof, d_code, xb, xlevels, (uint32_t *)blocks, nblkx, ix->stream));
     else CU(build_wm(d_bwt, n, (uint32_t)eof, d_code, levels, (uint32_t *)blocks, nblk, ix->stream));
 
     DevIndex &d = ix->d;
@@ -254,6 +285,8 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     for (int t = 0; t < 8; ++t) d.ctx_S[t] = 0;
     d.mark = nullptr; d.samples = nullptr; d.n = (uint32_t)n; d.eof = (uint32_t)eof; d.layout = layout; d.levels = levels;
     for (int l = 0; l < 8; ++l) d.z[l] = z[l];
+    d.wmx_b = wmx ? xb : 0; d.wmx_levels = wmx ? xlevels : 0; d.wmx_stride = (uint64_t)nblkx;
+    for (int l = 0; l < 2; ++l) for (int v = 0; v < 16; ++v) d.zx[l][v] = zx[l][v];
 
     ix->sample_rate = o.sa_sample_rate;
     if (o.sa_sample_rate > 0) {
@@ -290,7 +323,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     cudaMemGetInfo(&fr, &to);
     double reach = 68e9;
     if (const char *env = std::getenv("FMX_TLB_REACH_GB")) { const double v = std::atof(env); if (v > 0) reach = v * 1e9; }
-    const int64_t rank_bytes = (layout == FMX_LAYOUT_PLANES ? planes_bytes : wm_bytes);
+    const int64_t rank_bytes = (layout == FMX_LAYOUT_PLANES ? planes_bytes : wmx ? wmx_bytes : wm_bytes);
     if ((accel & FMX_ACCEL_CTX8) && accel != FMX_ACCEL_NONE && sigma > 4)
         return fail(FMX_E_UNSUPPORTED, "FMX_ACCEL_CTX8 stores 2-bit symbols: the text has %d distinct symbols (at most 4 fit)", sigma);
     auto room = [&]() { return total_cap - ix->index_bytes; };          // bytes the cap still allows
@@ -521,6 +554,7 @@ int fmx_close(fmx_index *ix) {
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (void *p : ix->owned) cudaFree(p);
+    trim_pool(ix->device);                                     // hand the cached stream-ordered scratch back: the next open (or suffix sort) may need all of it
     for (auto &st : ix->sets) {
         if (st.stream) { cudaStreamSynchronize(st.stream); cudaStreamDestroy(st.stream); }
         if (st.h2d) cudaStreamDestroy(st.h2d);
@@ -557,8 +591,8 @@ int fmx_ctx_depth(const fmx_index *ix) { return !ix ? 0 : ix->d.ctx ? ix->d.ctx_
 int fmx_ctx_entry_bytes(const fmx_index *ix) { return !ix ? 0 : ix->d.ctx ? 32 : ix->d.ctx8 ? 8 : 0; }
 int fmx_info(const fmx_index *ix, int32_t *layout, int32_t *levels, int32_t *sigma, int64_t *index_bytes, int32_t *rate) {
     CHECK_IX(ix);
-    if (layout) *layout = ix->cfg.layout;
-    if (levels) *levels = ix->cfg.layout == FMX_LAYOUT_WM ? ix->levels : 1;
+    if (layout) *layout = ix->api_layout;
+    if (levels) *levels = ix->api_layout == FMX_LAYOUT_WM ? ix->levels : ix->api_layout == FMX_LAYOUT_WMX ? ix->d_full.wmx_levels : 1;
     if (sigma) *sigma = ix->sigma;
     if (index_bytes) *index_bytes = ix->index_bytes;
     if (rate) *rate = ix->sample_rate;
@@ -1150,8 +1184,7 @@ int fmx_locate_dev(fmx_index *ix, const void *d_sp, const void *d_ep, int64_t m,
 
 // Instrumentation for the roofline accounting: with stats on, locate calls also count the LF steps of their walks (one atomic per
 // occurrence — not for timed runs); regex searches always count their items.  fmx_last_steps returns the count of the last such call.
-int fmx_set_stats(fmx_index *ix, int32_t on) { CHECK_IX(ix); CallCtx cc(ix);
-    CHECK_CC(cc); cc.stats = on != 0; return FMX_OK; }
+int fmx_set_stats(fmx_index *ix, int32_t on) { CHECK_IX(ix); std::lock_guard<std::mutex> lk(ix->mu); ix->stats = on != 0; return FMX_OK; }
 int64_t fmx_last_steps(const fmx_index *ix) { return ix ? ix->last_steps.load() : 0; }
 
 int fmx_set_locate_slab(int64_t occurrences) {
@@ -1572,8 +1605,7 @@ int fmx_gather_bench(fmx_index *ix, int32_t bytes, int32_t lanes, int64_t gather
     DBuf sink(st);
     CU(sink.alloc(8));
     CU(cudaMemsetAsync(sink.p, 0, 8, st));
-    const uint64_t nplanes = ix->cfg.layout == FMX_LAYOUT_PLANES ? (uint64_t)std::max(ix->sigma, 1) : (uint64_t)ix->levels;
-    const uint64_t nb = nplanes * (uint64_t)ix->nblk;
+    const uint64_t nb = (uint64_t)ix->rank_units64;
     CU(launch_gather_bench(ix->d.blocks, nb, bytes, lanes, gathers, chain, 1u, sink.as<unsigned long long>(), st));   // warm-up
     float best = 1e30f;
     for (int it = 0; it < std::max(iters, 1); ++it) {
@@ -1610,6 +1642,8 @@ static int build_bwt_impl(const uint8_t *text, int64_t len, int device, std::vec
     if (n >= (1ll << 32) - 1) return fail(FMX_E_UNSUPPORTED, "text too long for 32-bit rows");
     cudaStream_t st;
     CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CU(cudaDeviceSynchronize());
+    trim_pool(dev);                                            // the prefix-doubling sort wants ~35 bytes of scratch per text byte
     uint8_t *d_fwd = nullptr, *d_rev = nullptr, *d_bwt = nullptr;
     CU(cudaMalloc(&d_fwd, flen + 16)); CU(cudaMalloc(&d_rev, flen + 16)); CU(cudaMalloc(&d_bwt, n));
     if (flen) CU(cudaMemcpyAsync(d_fwd, src, flen, cudaMemcpyHostToDevice, st));

@@ -122,6 +122,69 @@ cudaError_t build_wm(const uint8_t *d_bwt, int64_t n, uint32_t eof, const uint8_
     return cudaGetLastError();
 }
 
+// ---- multi-ary wavelet matrix (FMX_LAYOUT_WMX) ---------------------------------------------------------------------------------------
+// one thread per payload word of one level: digit j of the word = (codes[first + j] >> shift) & (2^b - 1)
+__global__ void pack_digits_kernel(const uint8_t *__restrict__ codes, int64_t n, int shift, int b, uint32_t *__restrict__ blocks, int64_t nblk) {
+    const int H = 1 << b, per = 32 / b, pw = 32 - H;            // header words, digits per word, payload words per block
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nblk * pw) return;
+    const int64_t blk = w / pw;
+    const int k = (int)(w - blk * pw);
+    const int64_t p0 = (blk * pw + k) * per;
+    uint32_t word = 0;
+    const uint32_t m = (1u << b) - 1u;
+    for (int j = 0; j < per && p0 + j < n; ++j) word |= (((uint32_t)codes[p0 + j] >> shift) & m) << (j * b);
+    blocks[blk * 32 + H + k] = word;
+}
+// cnt[v * nblk + blk] = occurrences of digit v among the rows of block blk (rows beyond n do not count)
+__global__ void digit_counts_kernel(const uint8_t *__restrict__ codes, int64_t n, int shift, int b, uint32_t *__restrict__ cnt, int64_t nblk) {
+    const int H = 1 << b, R = (32 - H) * (32 / b);
+    const int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk >= nblk) return;
+    uint32_t c[16];
+#pragma unroll
+    for (int v = 0; v < 16; ++v) c[v] = 0;
+    const uint32_t m = (1u << b) - 1u;
+    const int64_t p0 = blk * R;
+    for (int j = 0; j < R && p0 + j < n; ++j) {
+        const uint32_t d = ((uint32_t)codes[p0 + j] >> shift) & m;
+#pragma unroll
+        for (int v = 0; v < 16; ++v) c[v] += (d == (uint32_t)v);
+    }
+    for (int v = 0; v < H; ++v) cnt[(int64_t)v * nblk + blk] = c[v];
+}
+__global__ void write_headers_x_kernel(uint32_t *__restrict__ blocks, const uint32_t *__restrict__ pre, int64_t nblk, int H) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nblk * H) return;
+    const int64_t v = t / nblk, blk = t - v * nblk;
+    blocks[blk * 32 + v] = pre[t] - pre[v * nblk];
+}
+cudaError_t build_wmx(const uint8_t *d_bwt, int64_t n, uint32_t eof, const uint8_t *d_code, int b, int levels, uint32_t *d_blocks, int64_t nblk,
+                      cudaStream_t st) {
+    const int H = 1 << b;
+    uint8_t *cur = nullptr, *nxt = nullptr;
+    uint32_t *cnt = nullptr, *pre = nullptr;
+    CK(cudaMallocAsync(&cur, n + 64, st));
+    CK(cudaMallocAsync(&nxt, n + 64, st));
+    CK(cudaMallocAsync(&cnt, (size_t)nblk * H * 4, st));
+    CK(cudaMallocAsync(&pre, (size_t)nblk * H * 4, st));
+    map_codes_kernel<<<148 * 8, 256, 0, st>>>(d_bwt, n, eof, d_code, cur);
+    for (int l = 0; l < levels; ++l) {
+        const int shift = b * (levels - 1 - l);
+        uint32_t *lv = d_blocks + (int64_t)l * nblk * 32;
+        pack_digits_kernel<<<(unsigned)((nblk * (32 - H) + 255) / 256), 256, 0, st>>>(cur, n, shift, b, lv, nblk);
+        digit_counts_kernel<<<(unsigned)((nblk + 127) / 128), 128, 0, st>>>(cur, n, shift, b, cnt, nblk);
+        CK(exclusive_sum_u32(cnt, pre, nblk * H, st));          // total digits = n < 2^32: no overflow
+        write_headers_x_kernel<<<(unsigned)((nblk * H + 255) / 256), 256, 0, st>>>(lv, pre, nblk, H);
+        if (l + 1 < levels) {
+            CK(stable_partition_digit_u8(cur, nxt, n, shift, shift + b, st));
+            uint8_t *t = cur; cur = nxt; nxt = t;
+        }
+    }
+    cudaFreeAsync(cur, st); cudaFreeAsync(nxt, st); cudaFreeAsync(cnt, st); cudaFreeAsync(pre, st);
+    return cudaGetLastError();
+}
+
 cudaError_t build_planes(const uint8_t *d_bwt, int64_t n, uint32_t eof, const uint8_t *d_sym, int sigma, uint32_t *d_blocks,
                          int64_t nblk, cudaStream_t st) {
     constexpr int TB = 8;
@@ -234,6 +297,7 @@ cudaError_t prepare_chains(const DevIndex &ix, int layout, Chains &ch, cudaStrea
     CK(cudaMallocAsync(&ch.d_start, nchains * 4ull, st));
     const unsigned grid = (nchains + kThreads - 1) / kThreads;
     if (layout == FMX_LAYOUT_PLANES) chain_len_kernel<FMX_LAYOUT_PLANES><<<grid, kThreads, 0, st>>>(ix, S, nchains, ch.eof_chain, d_next, d_len);
+    else if (layout == FMX_LAYOUT_WMX) chain_len_kernel<FMX_LAYOUT_WMX><<<grid, kThreads, 0, st>>>(ix, S, nchains, ch.eof_chain, d_next, d_len);
     else chain_len_kernel<FMX_LAYOUT_WM><<<grid, kThreads, 0, st>>>(ix, S, nchains, ch.eof_chain, d_next, d_len);
     std::vector<uint32_t> nx(nchains), ln(nchains), sv(nchains, 0);
     CK(cudaMemcpyAsync(nx.data(), d_next, nchains * 4ull, cudaMemcpyDeviceToHost, st));
@@ -273,6 +337,7 @@ cudaError_t build_sa_samples(const DevIndex &ix, int layout, int rate, uint32_t 
     CK(cudaMemsetAsync(d_np, 0, 8, st));
     CK(cudaMemsetAsync(d_mark_blocks, 0, (size_t)nblk * 64, st));
     if (layout == FMX_LAYOUT_PLANES) chain_mark_kernel<FMX_LAYOUT_PLANES><<<grid, kThreads, 0, st>>>(ix, ch.S, ch.nchains, ch.eof_chain, ch.d_start, (uint32_t)rate, d_mark_blocks, d_pairs, d_np);
+    else if (layout == FMX_LAYOUT_WMX) chain_mark_kernel<FMX_LAYOUT_WMX><<<grid, kThreads, 0, st>>>(ix, ch.S, ch.nchains, ch.eof_chain, ch.d_start, (uint32_t)rate, d_mark_blocks, d_pairs, d_np);
     else chain_mark_kernel<FMX_LAYOUT_WM><<<grid, kThreads, 0, st>>>(ix, ch.S, ch.nchains, ch.eof_chain, ch.d_start, (uint32_t)rate, d_mark_blocks, d_pairs, d_np);
     CK(finish_headers(d_mark_blocks, nblk, 1, st));
     unsigned long long np = 0;
@@ -414,6 +479,7 @@ cudaError_t build_full_sa(const DevIndex &ix, int layout, uint32_t *d_sa, uint32
     CK(prepare_chains(ix, layout, ch, st, err));
     const unsigned grid = (ch.nchains + kThreads - 1) / kThreads;
     if (layout == FMX_LAYOUT_PLANES) chain_fullsa_kernel<FMX_LAYOUT_PLANES><<<grid, kThreads, 0, st>>>(ix, ch.S, ch.nchains, ch.eof_chain, ch.d_start, d_sa, d_isa, d_text);
+    else if (layout == FMX_LAYOUT_WMX) chain_fullsa_kernel<FMX_LAYOUT_WMX><<<grid, kThreads, 0, st>>>(ix, ch.S, ch.nchains, ch.eof_chain, ch.d_start, d_sa, d_isa, d_text);
     else chain_fullsa_kernel<FMX_LAYOUT_WM><<<grid, kThreads, 0, st>>>(ix, ch.S, ch.nchains, ch.eof_chain, ch.d_start, d_sa, d_isa, d_text);
     cudaFreeAsync(ch.d_start, st);
     return cudaGetLastError();
@@ -490,6 +556,7 @@ cudaError_t build_kmer_table(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d
         const unsigned grid = (unsigned)((cnt + per - 1) / per);
 #define CALL(GG, LAY) kmer_extend_kernel<GG, LAY><<<grid, kThreads, 0, st>>>(ix, d_sym, sigma, buf(j - 1), cnt, buf(j))
         if (ix.layout == FMX_LAYOUT_PLANES) { if (G == 1) CALL(1, FMX_LAYOUT_PLANES); else if (G == 2) CALL(2, FMX_LAYOUT_PLANES); else CALL(4, FMX_LAYOUT_PLANES); }
+        else if (ix.layout == FMX_LAYOUT_WMX) { if (G == 1) CALL(1, FMX_LAYOUT_WMX); else if (G == 2) CALL(2, FMX_LAYOUT_WMX); else CALL(4, FMX_LAYOUT_WMX); }
         else { if (G == 1) CALL(1, FMX_LAYOUT_WM); else if (G == 2) CALL(2, FMX_LAYOUT_WM); else CALL(4, FMX_LAYOUT_WM); }
 #undef CALL
         CK(cudaGetLastError());

@@ -10,6 +10,10 @@ namespace fmx {
 // wavelet matrix: d_blocks holds levels*nblk rank blocks (64 B each), nblk = n/480 + 1
 cudaError_t build_wm(const uint8_t *d_bwt, int64_t n, uint32_t eof, const uint8_t *d_code, int levels, uint32_t *d_blocks,
                      int64_t nblk, cudaStream_t st);
+// multi-ary wavelet matrix: b bits per digit (2 or 4), `levels` digits per code; d_blocks holds levels*nblk 128-byte blocks,
+// nblk = n / rows_per_block + 1 with rows_per_block = 128 (b = 4) or 448 (b = 2)
+cudaError_t build_wmx(const uint8_t *d_bwt, int64_t n, uint32_t eof, const uint8_t *d_code, int b, int levels, uint32_t *d_blocks, int64_t nblk,
+                      cudaStream_t st);
 // per-symbol planes: d_blocks holds sigma*nblk rank blocks; d_sym[code] = byte value
 cudaError_t build_planes(const uint8_t *d_bwt, int64_t n, uint32_t eof, const uint8_t *d_sym, int sigma, uint32_t *d_blocks,
                          int64_t nblk, cudaStream_t st);

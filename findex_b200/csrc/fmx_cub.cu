@@ -43,6 +43,10 @@ cudaError_t stable_partition_bit_u8(const uint8_t *d_in, uint8_t *d_out, int64_t
     FMX_CUB2(cub::DeviceRadixSort::SortKeys(nullptr, bytes, d_in, d_out, n, bit, bit + 1, st),
              cub::DeviceRadixSort::SortKeys(tp, bytes, d_in, d_out, n, bit, bit + 1, st));
 }
+cudaError_t stable_partition_digit_u8(const uint8_t *d_in, uint8_t *d_out, int64_t n, int begin_bit, int end_bit, cudaStream_t st) {
+    FMX_CUB2(cub::DeviceRadixSort::SortKeys(nullptr, bytes, d_in, d_out, n, begin_bit, end_bit, st),
+             cub::DeviceRadixSort::SortKeys(tp, bytes, d_in, d_out, n, begin_bit, end_bit, st));
+}
 cudaError_t sort_pairs_u64_u32(const uint64_t *k_in, uint64_t *k_out, const uint32_t *v_in, uint32_t *v_out, int64_t n,
                                int begin_bit, int end_bit, cudaStream_t st) {
     FMX_CUB2(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k_in, k_out, v_in, v_out, n, begin_bit, end_bit, st),

@@ -14,6 +14,8 @@ cudaError_t exclusive_sum_i64(const int64_t *d_in, int64_t *d_out, int64_t n, cu
 cudaError_t inclusive_max_u32(const uint32_t *d_in, uint32_t *d_out, int64_t n, cudaStream_t st);
 // stable sort of byte keys on one bit: zeros first (the wavelet-matrix level permutation)
 cudaError_t stable_partition_bit_u8(const uint8_t *d_in, uint8_t *d_out, int64_t n, int bit, cudaStream_t st);
+// stable sort of byte keys on the digit [begin_bit, end_bit): the multi-ary wavelet-matrix level permutation
+cudaError_t stable_partition_digit_u8(const uint8_t *d_in, uint8_t *d_out, int64_t n, int begin_bit, int end_bit, cudaStream_t st);
 cudaError_t sort_pairs_u64_u32(const uint64_t *k_in, uint64_t *k_out, const uint32_t *v_in, uint32_t *v_out, int64_t n,
                                int begin_bit, int end_bit, cudaStream_t st);
 cudaError_t sort_pairs_u8_u32(const uint8_t *k_in, uint8_t *k_out, const uint32_t *v_in, uint32_t *v_out, int64_t n,

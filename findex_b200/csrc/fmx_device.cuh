@@ -9,6 +9,8 @@
 //            block per level per rank (the structure north_star names);
 //   PLANES : one bitvector per symbol, one block per rank — trades HBM capacity (sigma*n/7.5 bytes)
 //            for 1/levels of the random fetches.
+//   WMX    : multi-ary wavelet matrix, 16-ary (4-ary for <= 4 symbols) levels of 128-byte blocks: a 128-byte request costs what a
+//            64-byte one does, so a byte alphabet needs 2 requests per rank instead of 8 at about the same size.
 // The '$' row (eof) is not a symbol: WM stores it under code 0 and subtracts it back out, PLANES never
 // sets it; rank of byte 0 is (pos > eof).
 #pragma once
@@ -35,6 +37,11 @@ struct DevIndex {
     uint32_t n, eof;
     int32_t  layout, levels;
     uint32_t z[8];              // WM: zeros per level
+    // multi-ary wavelet matrix (FMX_LAYOUT_WMX): wmx_b = bits per digit (4: 16-ary, 2: 4-ary; 0 = another layout), wmx_levels = digits per code.  Level l is an array of 128-BYTE blocks = one request: 2^b cumulative counts
+    // (occurrences of every digit value before the block) + the digits of (128 - 4*2^b)*8/b rows.  zx[l][v] = rows whose digit at level l is < v.
+    int32_t  wmx_b, wmx_levels;
+    uint64_t wmx_stride;        // blocks per level
+    uint32_t zx[2][16];
     // ---- optional accelerators (bit-exact shortcuts that spend HBM capacity) ----
     const uint2   *kmer;        // sigma^kmer_k entries: (sp,ep) after the first kmer_k backward steps, (0,0) if empty
     int32_t        kmer_k;
@@ -288,6 +295,73 @@ __device__ __forceinline__ void walk_block(const uint4 *bm, uint32_t r, uint32_t
     marked = mm;
 }
 
+// ---- multi-ary wavelet-matrix blocks (128 B = 32 words, one request from four lanes x 256 bits) -------------------------------------
+// rows per block: b = 4: 16 count words + 16 payload words x 8 digits = 128 ; b = 2: 4 count words + 28 payload words x 16 digits = 448
+__device__ __forceinline__ uint32_t wmx_rows_per_block(int b) { return b == 4 ? 128u : 448u; }
+
+template <int G> struct LaneBlockX { uint4 v[8 / G]; };          // a lane's 32/G consecutive words of the block
+
+template <int G>
+__device__ __forceinline__ LaneBlockX<G> load_block_x(const uint4 *lv, uint32_t blk, int lane) {
+    LaneBlockX<G> r;
+    const uint4 *p = lv + (uint64_t)blk * 8 + lane * (8 / G);
+#pragma unroll
+    for (int i = 0; i < 8 / G; i += 2) ldg256(p + i, r.v[i], r.v[i + 1]);       // G = 4: one 256-bit load per lane = one request per block
+    return r;
+}
+
+// lane-local part of rank_d(off): the count word of digit d if this lane holds it, plus matches among this lane's payload digits < off
+template <int G>
+__device__ __forceinline__ uint32_t lane_rank_x(const LaneBlockX<G> &blkv, uint32_t off, uint32_t d, int b, int lane) {
+    const int H = 1 << b, per = 32 / b;                           // header words, digits per payload word
+    const uint32_t rep = b == 4 ? 0x11111111u : 0x55555555u;
+    const uint32_t pat = d * rep;
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8 / G; ++i) {
+        const uint32_t w4[4] = {blkv.v[i].x, blkv.v[i].y, blkv.v[i].z, blkv.v[i].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int wi = (lane * (8 / G) + i) * 4 + k;          // word index inside the block
+            if (wi < H) { if ((uint32_t)wi == d) s += w4[k]; continue; }
+            const int first = (wi - H) * per;                     // first row of this payload word
+            int t = (int)off - first;
+            if (t <= 0) continue;
+            const uint32_t x = w4[k] ^ pat;
+            const uint32_t nz = b == 4 ? ((x | (x >> 1) | (x >> 2) | (x >> 3)) & rep) : ((x | (x >> 1)) & rep);   // low bit of every non-matching digit
+            uint32_t eq = ~nz & rep;
+            if (t < per) eq &= (1u << (t * b)) - 1u;
+            s += __popc(eq);
+        }
+    }
+    return s;
+}
+
+// rank_d at two positions of one level; one block fetch when they share a block
+template <int G, bool STATS>
+__device__ __forceinline__ void rank_pair_x(const uint4 *lv, int b, uint32_t d, uint32_t pa, uint32_t pb, uint32_t &ra, uint32_t &rb, uint32_t &touched) {
+    const int lane = (G == 1) ? 0 : (threadIdx.x & (G - 1));
+    const uint32_t mask = group_mask<G>();
+    const uint32_t R = wmx_rows_per_block(b);
+    const uint32_t ba = pa / R, oa = pa - ba * R, bb = pb / R, ob = pb - bb * R;
+    LaneBlockX<G> A = load_block_x<G>(lv, ba, lane);
+    LaneBlockX<G> B = A;
+    if (bb != ba) B = load_block_x<G>(lv, bb, lane);
+    if (STATS) touched += (bb != ba) ? 2u : 1u;
+    uint32_t sa = lane_rank_x<G>(A, oa, d, b, lane), sb = lane_rank_x<G>(B, ob, d, b, lane);
+    if (G > 1) { sa = group_sum<G>(sa, mask); sb = group_sum<G>(sb, mask); }
+    ra = sa; rb = sb;
+}
+template <int G>
+__device__ __forceinline__ uint32_t rank_one_x(const uint4 *lv, int b, uint32_t d, uint32_t p) {
+    const int lane = (G == 1) ? 0 : (threadIdx.x & (G - 1));
+    const uint32_t R = wmx_rows_per_block(b);
+    const uint32_t blk = p / R, o = p - blk * R;
+    uint32_t s = lane_rank_x<G>(load_block_x<G>(lv, blk, lane), o, d, b, lane);
+    if (G > 1) s = group_sum<G>(s, group_mask<G>());
+    return s;
+}
+
 // ---- one backward step: (sp,ep) -> (C[c]+rank_c(sp), C[c]+rank_c(ep))   findex.scala:32-36 ------------
 template <int G, int LAYOUT, bool STATS>
 __device__ __forceinline__ void backward_step(const DevIndex &ix, const SharedTables &t, uint32_t c, uint32_t &sp,
@@ -304,6 +378,19 @@ __device__ __forceinline__ void backward_step(const DevIndex &ix, const SharedTa
         rank_pair<G, STATS>(ix.blocks + (uint64_t)code * ix.stride * 4, sp, ep, ra, rb, touched);
         sp = t.base[c] + ra;
         ep = t.base[c] + rb;
+    } else if (LAYOUT == FMX_LAYOUT_WMX) {         // multi-ary wavelet matrix: one 128-byte request per digit
+        uint32_t p = sp, q = ep;
+        const int b = ix.wmx_b, L = ix.wmx_levels;
+        for (int l = 0; l < L; ++l) {
+            const uint32_t d = (code >> (b * (L - 1 - l))) & ((1u << b) - 1u);
+            uint32_t ra, rb;
+            rank_pair_x<G, STATS>(ix.blocks + (uint64_t)l * ix.wmx_stride * 8, b, d, p, q, ra, rb, touched);
+            p = ix.zx[l][d] + ra;
+            q = ix.zx[l][d] + rb;
+        }
+        if (code == 0) { p -= (sp > ix.eof); q -= (ep > ix.eof); }     // the '$' row is filed under code 0
+        sp = t.base[c] + p;
+        ep = t.base[c] + q;
     } else {
         uint32_t p = sp, q = ep;
         const int L = ix.levels;
@@ -502,6 +589,15 @@ __device__ __forceinline__ uint32_t lf_value(const DevIndex &ix, const SharedTab
     if (code == kCodeAbsent) return t.C[c];
     if (LAYOUT == FMX_LAYOUT_PLANES) {
         return t.base[c] + rank_one<G>(ix.blocks + (uint64_t)code * ix.stride * 4, pos, nullptr);
+    } else if (LAYOUT == FMX_LAYOUT_WMX) {
+        uint32_t p = pos;
+        const int b = ix.wmx_b, L = ix.wmx_levels;
+        for (int l = 0; l < L; ++l) {
+            const uint32_t d = (code >> (b * (L - 1 - l))) & ((1u << b) - 1u);
+            p = ix.zx[l][d] + rank_one_x<G>(ix.blocks + (uint64_t)l * ix.wmx_stride * 8, b, d, p);
+        }
+        if (code == 0) p -= (pos > ix.eof);
+        return t.base[c] + p;
     } else {
         uint32_t p = pos;
         const int L = ix.levels;

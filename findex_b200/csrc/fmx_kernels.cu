@@ -22,7 +22,9 @@ namespace fmx {
 // =====================================================================================================
 // K1: count
 // =====================================================================================================
-template <int G, int LAYOUT, bool STATS, typename OutT, int MINB = ((G == 1) ? 6 : 8)>
+// resident CTAs per SM the count kernel is compiled for: 8 (32 registers) for the bitvector layouts at 2/4 lanes, 6 at one lane; the
+// multi-ary blocks hold twice the words per lane and get 5 (48 registers, no spills)
+template <int G, int LAYOUT, bool STATS, typename OutT, int MINB = (LAYOUT == FMX_LAYOUT_WMX ? 5 : (G == 1) ? 6 : 8)>
 __global__ void __launch_bounds__(kThreads, MINB)
 count_fixed_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, int len, long long m,
                    OutT *__restrict__ sp_out, OutT *__restrict__ ep_out, unsigned long long *stats, const __grid_constant__ PeerSinks sinks) {
@@ -425,6 +427,10 @@ gather_kernel(const uint4 *__restrict__ base, unsigned long long n_units, long l
             if ((cfg).lanes == 1) { CALL(1, FMX_LAYOUT_PLANES); }                                    \
             else if ((cfg).lanes == 2) { CALL(2, FMX_LAYOUT_PLANES); }                               \
             else { CALL(4, FMX_LAYOUT_PLANES); }                                                     \
+        } else if ((cfg).layout == FMX_LAYOUT_WMX) {                                                 \
+            if ((cfg).lanes == 1) { CALL(1, FMX_LAYOUT_WMX); }                                       \
+            else if ((cfg).lanes == 2) { CALL(2, FMX_LAYOUT_WMX); }                                  \
+            else { CALL(4, FMX_LAYOUT_WMX); }                                                        \
         } else {                                                                                     \
             if ((cfg).lanes == 1) { CALL(1, FMX_LAYOUT_WM); }                                        \
             else if ((cfg).lanes == 2) { CALL(2, FMX_LAYOUT_WM); }                                   \

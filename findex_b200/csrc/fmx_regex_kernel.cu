@@ -8,7 +8,11 @@
 // state's character and either emits a result or pushes the state's follow positions.  With the caps off the result is a multiset
 // that does not depend on the order in which items are taken, so nothing here is level-synchronous:
 //
-//   * a persistent grid of workers (G lanes per item) owns a global RING of items in HBM.  Consumers take tickets from `head` with one
+//   * every warp keeps a stack of items in shared memory: children go there (no atomics, nobody else sees them) and idle lanes pop it
+//     first; only what does not fit spills to the global ring, and only a warp whose stack is empty takes work from it.  The balance
+//     of births and deaths a warp has not reported to `pending` is flushed whenever it turns positive (before a child could become
+//     visible to others) and when the warp runs dry, so `pending` never undercounts and most iterations touch no global counter.
+//   * a persistent grid of workers (G lanes per item) owns a global RING of items in HBM (start items, overflow of the stacks).  Consumers take tickets from `head` with one
 //     warp-aggregated atomic and wait for their slot to be filled; producers reserve tickets from `tail` the same way, write the
 //     payload and publish it with a release exchange on the slot's state word (an occupied slot = the ring is too small: the run is
 //     abandoned and the host reruns it with a larger ring).  `pending` counts live items; the worker that brings it to zero raises `done`.
@@ -77,16 +81,20 @@ __global__ void regex_seed_kernel(const uint32_t *__restrict__ first, long long 
     }
 }
 
+constexpr int kLocalSlots = 256;           // per-warp stack of items in shared memory (one '.' expansion = 253 children fits)
+
 template <int G, int LAYOUT>
 __global__ void __launch_bounds__(kThreads)
 regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ RegexTables rt, FrontierItem *ring, unsigned long long ring_mask,
                    RegexResult *__restrict__ res, long long cap_res, unsigned long long *ctrl, uint32_t len_cap) {
     __shared__ SharedTables tb;
+    __shared__ __align__(16) FrontierItem lstack[kThreads / 32][kLocalSlots];
     load_tables(tb, ix);
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
     const bool leader = (threadIdx.x % G) == 0;
     const int lead_lane = (int)(lane & ~(uint32_t)(G - 1));
+    FrontierItem *mine = lstack[threadIdx.x >> 5];
     constexpr uint32_t kWide = 4, kFilterRows = 32;
     constexpr unsigned long long kNoTicket = ~0ull;
 
@@ -95,27 +103,53 @@ regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ 
     FrontierItem it = {0, 0, 0, 0};
     uint4 rec = {0, 0, 0, 0};
     uint32_t max_len = 0, idle_rounds = 0, nsteps = 0;
+    uint32_t ltop = 0;                                     // items on this warp's stack (warp-uniform)
+    long long ldelta = 0;                                  // births - deaths this warp has not told `pending` about yet (never left > 0)
     bool ring_ok = true;
 
+    // children of this iteration go to the warp's own stack while it has room (no atomics, nobody else sees them) and to the global ring
+    // beyond that; `idx` = position of the child among the `total` children pushed together
+    auto place = [&](uint32_t idx, unsigned long long tbase, uint32_t room, uint32_t state, uint32_t len, uint32_t sp, uint32_t ep) {
+        if (idx < room) mine[ltop + idx] = FrontierItem{state, len, sp, ep};
+        else ring_ok = ring_publish(ring, ring_mask, tbase + (idx - room), state, len, sp, ep) && ring_ok;
+    };
+
     for (;;) {
-        // ---- refill: groups without an item take a ticket (one atomic per warp) and look at their slot
-        const uint32_t want = __ballot_sync(0xFFFFFFFFu, leader && !have && ticket == kNoTicket);
-        if (want) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&ctrl[kRxHead], (unsigned long long)__popc(want));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (leader && !have && ticket == kNoTicket) ticket = base + __popc(want & ((1u << lane) - 1u));
+        // ---- refill: (1) a lane that holds a ticket of the global ring looks at its slot; (2) lanes still without an item pop the warp's
+        // own stack (a ticket holder too — its ring item, should it arrive meanwhile, waits for the lane's next refill); (3) lanes
+        // without item and ticket take tickets (one atomic per warp) once the stack is empty
+        auto poll = [&]() {
+            if (leader && !have && ticket != kNoTicket) {
+                FrontierItem *s = ring + (ticket & ring_mask);
+                const uint32_t st = ld_acquire(&s->state);
+                if (st != kSlotEmpty) {
+                    const uint4 raw = ld_cg(reinterpret_cast<const uint4 *>(s));
+                    it = FrontierItem{st, raw.y, raw.z, raw.w};
+                    st_release(&s->state, kSlotEmpty);     // the slot may be written again (after this lane's reads of it)
+                    have = true;
+                    have_rec = false;
+                    ticket = kNoTicket;
+                }
+            }
+        };
+        poll();
+        {
+            const uint32_t want = __ballot_sync(0xFFFFFFFFu, leader && !have);
+            if (want && ltop) {
+                const uint32_t rank = __popc(want & ((1u << lane) - 1u));
+                const uint32_t take = min((uint32_t)__popc(want), ltop);
+                if (leader && !have && rank < take) { it = mine[ltop - 1 - rank]; have = true; have_rec = false; }
+                ltop -= take;
+            }
         }
-        if (leader && !have && ticket != kNoTicket) {
-            FrontierItem *s = ring + (ticket & ring_mask);
-            const uint32_t st = ld_acquire(&s->state);
-            if (st != kSlotEmpty) {
-                const uint4 raw = ld_cg(reinterpret_cast<const uint4 *>(s));
-                it = FrontierItem{st, raw.y, raw.z, raw.w};
-                st_release(&s->state, kSlotEmpty);         // the slot may be written again (after this rank's reads of it)
-                have = true;
-                have_rec = false;
-                ticket = kNoTicket;
+        if (ltop == 0) {
+            const uint32_t want = __ballot_sync(0xFFFFFFFFu, leader && !have && ticket == kNoTicket);
+            if (want) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&ctrl[kRxHead], (unsigned long long)__popc(want));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (leader && !have && ticket == kNoTicket) ticket = base + __popc(want & ((1u << lane) - 1u));
+                poll();
             }
         }
         if (G > 1) {                                       // the group works on its leader's item
@@ -124,7 +158,14 @@ regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ 
             it.sp = __shfl_sync(0xFFFFFFFFu, it.sp, lead_lane); it.ep = __shfl_sync(0xFFFFFFFFu, it.ep, lead_lane);
             have_rec = __shfl_sync(0xFFFFFFFFu, (int)have_rec, lead_lane) != 0;
         }
-        if (!__any_sync(0xFFFFFFFFu, have)) {              // nothing to do in this warp: done, or wait for producers
+        if (!__any_sync(0xFFFFFFFFu, have)) {              // nothing to do in this warp (its stack is empty too): report, then done or wait
+            if (ldelta != 0) {
+                if (lane == 0) {
+                    const unsigned long long old = atomicAdd(&ctrl[kRxPending], (unsigned long long)ldelta);
+                    if (old + (unsigned long long)ldelta == 0ull) atomicExch(&ctrl[kRxDone], 1ull);      // the last live item ended here
+                }
+                ldelta = 0;
+            }
             if (ld_volatile_u64(&ctrl[kRxDone]) != 0) break;
             if (++idle_rounds > 4) __nanosleep(idle_rounds > 64 ? 400 : 100);
             continue;
@@ -164,8 +205,16 @@ regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ 
             }
         }
 
-        // ---- wide follow lists: the whole warp expands one parent at a time, filtered by the bytes present in BWT[sp..ep)
+        // deaths of this iteration: items that neither go on in their lane nor were expanded (wide parents end after their expansion)
+        const bool narrow = leader && nf >= 1 && nf < kWide;
+        const uint32_t np = narrow ? nf - 1 : 0u;            // children this group pushes (its first follow stays in the lane)
+        uint32_t incl = np;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+        const uint32_t pushes = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const uint32_t finished = __popc(__ballot_sync(0xFFFFFFFFu, leader && have && !(nf >= 1 && nf < kWide)));
         uint32_t wide = __ballot_sync(0xFFFFFFFFu, leader && nf >= kWide);
+
+        // ---- wide follow lists: the whole warp expands one parent at a time, filtered by the bytes present in BWT[sp..ep)
         while (wide) {
             const int src = __ffs(wide) - 1;
             wide &= wide - 1;
@@ -193,12 +242,17 @@ regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ 
                 }
             }
             if (kept_total == 0) continue;                  // warp-uniform
-            unsigned long long b = 0;
-            if (lane == 0) {                                // children are counted before they can be seen
-                atomicAdd(&ctrl[kRxPending], (unsigned long long)kept_total);
-                b = atomicAdd(&ctrl[kRxTail], (unsigned long long)kept_total);
+            // births are counted before anybody else can see them: the running balance is flushed whenever it turns positive
+            ldelta += kept_total;
+            const uint32_t room = min((uint32_t)kLocalSlots - ltop, kept_total);
+            unsigned long long tb0 = 0;
+            if (lane == 0) {
+                if (ldelta > 0) atomicAdd(&ctrl[kRxPending], (unsigned long long)ldelta);
+                if (kept_total > room) tb0 = atomicAdd(&ctrl[kRxTail], (unsigned long long)(kept_total - room));
             }
-            b = __shfl_sync(0xFFFFFFFFu, b, 0);
+            if (ldelta > 0) ldelta = 0;
+            tb0 = __shfl_sync(0xFFFFFFFFu, tb0, 0);
+            uint32_t done_cnt = 0;
             for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
                 const uint32_t j = j0 + lane;
                 const uint32_t fstate = j < cnt ? rt.fol[fs + j] : 0u;
@@ -209,32 +263,29 @@ regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ 
                     keep = keep && ((word >> (ch & 31u)) & 1u);
                 }
                 const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
-                if (keep) ring_ok = ring_publish(ring, ring_mask, b + __popc(km & ((1u << lane) - 1u)), fstate, ln, a, e) && ring_ok;
-                b += __popc(km);
+                if (keep) place(done_cnt + __popc(km & ((1u << lane) - 1u)), tb0, room, fstate, ln, a, e);
+                done_cnt += __popc(km);
             }
+            ltop += room;
+            __syncwarp();
         }
 
-        // ---- short follow lists: go on with the first follow in registers, push the others; account for finished items
-        const bool narrow = leader && nf >= 1 && nf < kWide;
-        const uint32_t np = narrow ? nf - 1 : 0u;            // items this group pushes
-        uint32_t incl = np;
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += v; }
-        const uint32_t pushes = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        const uint32_t finished = __popc(__ballot_sync(0xFFFFFFFFu, leader && have && !(nf >= 1 && nf < kWide)));
-        unsigned long long tbase = 0;
-        if (lane == 0) {
-            if (pushes != finished) {
-                const long long delta = (long long)pushes - (long long)finished;
-                const unsigned long long old = atomicAdd(&ctrl[kRxPending], (unsigned long long)delta);
-                if (old + (unsigned long long)delta == 0ull) atomicExch(&ctrl[kRxDone], 1ull);      // the last live item just ended
+        // ---- short follow lists: go on with the first follow in registers, push the others; settle the balance
+        ldelta += (long long)pushes - (long long)finished;
+        {
+            const uint32_t room = min((uint32_t)kLocalSlots - ltop, pushes);
+            unsigned long long tb0 = 0;
+            if (lane == 0) {
+                if (ldelta > 0) atomicAdd(&ctrl[kRxPending], (unsigned long long)ldelta);
+                if (pushes > room) tb0 = atomicAdd(&ctrl[kRxTail], (unsigned long long)(pushes - room));
             }
-            if (pushes) tbase = atomicAdd(&ctrl[kRxTail], (unsigned long long)pushes);
-        }
-        if (pushes) {
-            tbase = __shfl_sync(0xFFFFFFFFu, tbase, 0);
-            const unsigned long long my = tbase + (incl - np);
-            for (uint32_t j = 0; j < np; ++j)
-                ring_ok = ring_publish(ring, ring_mask, my + j, rt.fol[fo + 1 + j], nlen, it.sp, it.ep) && ring_ok;
+            if (ldelta > 0) ldelta = 0;
+            if (pushes) {
+                tb0 = __shfl_sync(0xFFFFFFFFu, tb0, 0);
+                for (uint32_t j = 0; j < np; ++j) place(incl - np + j, tb0, room, rt.fol[fo + 1 + j], nlen, it.sp, it.ep);
+                ltop += room;
+                __syncwarp();
+            }
         }
         if (have) {
             if (nf >= 1 && nf < kWide) { it.state = f0; it.len = nlen; rec = nrec; have_rec = true; }
@@ -273,6 +324,8 @@ cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, const RegexTa
     }
     if (cfg.layout == FMX_LAYOUT_PLANES) {
         if (cfg.lanes == 1) { CALL(1, FMX_LAYOUT_PLANES); } else if (cfg.lanes == 2) { CALL(2, FMX_LAYOUT_PLANES); } else { CALL(4, FMX_LAYOUT_PLANES); }
+    } else if (cfg.layout == FMX_LAYOUT_WMX) {
+        if (cfg.lanes == 1) { CALL(1, FMX_LAYOUT_WMX); } else if (cfg.lanes == 2) { CALL(2, FMX_LAYOUT_WMX); } else { CALL(4, FMX_LAYOUT_WMX); }
     } else {
         if (cfg.lanes == 1) { CALL(1, FMX_LAYOUT_WM); } else if (cfg.lanes == 2) { CALL(2, FMX_LAYOUT_WM); } else { CALL(4, FMX_LAYOUT_WM); }
     }

@@ -18,7 +18,7 @@ _SO = os.path.join(_HERE, "libfmgpu.so")
 
 FMX_OK, FMX_E_IO, FMX_E_FORMAT, FMX_E_CUDA, FMX_E_ARG = 0, -1, -2, -3, -4
 FMX_E_CAPACITY, FMX_E_SYNTAX, FMX_E_UNSUPPORTED, FMX_E_LIMIT = -5, -6, -7, -8
-LAYOUT_AUTO, LAYOUT_WM, LAYOUT_PLANES = 0, 1, 2
+LAYOUT_AUTO, LAYOUT_WM, LAYOUT_PLANES, LAYOUT_WMX = 0, 1, 2, 3
 ACCEL_AUTO, ACCEL_KMER, ACCEL_TEXT, ACCEL_CTX, ACCEL_NONE, ACCEL_CTX8, ACCEL_NO_SA = 0, 1, 2, 4, 8, 16, 32
 
 
@@ -299,7 +299,7 @@ class GpuFMSearcher:
         _check(lib().fmx_info(self.h, C.byref(lay), C.byref(lev), C.byref(sig), C.byref(nb), C.byref(rate)))
         k, t = C.c_int32(), C.c_int32()
         _check(lib().fmx_accel_info(self.h, C.byref(k), C.byref(t)))
-        return {"layout": {1: "wm", 2: "planes"}[lay.value], "levels": lev.value, "sigma": sig.value,
+        return {"layout": {1: "wm", 2: "planes", 3: "wmx"}[lay.value], "levels": lev.value, "sigma": sig.value,
                 "index_bytes": nb.value, "sa_sample_rate": rate.value, "kmer_k": k.value, "text_shortcut": bool(t.value),
                 "ctx_depth": lib().fmx_ctx_depth(self.h), "ctx_entry_bytes": lib().fmx_ctx_entry_bytes(self.h),
                 "lanes_per_query": lib().fmx_get_lanes(self.h)}

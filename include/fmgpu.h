@@ -39,9 +39,11 @@ extern "C" {
 #define FMX_E_LIMIT        -8   /* regex traversal exceeded the configured frontier / length limits     */
 
 /* Rank-structure layouts (fmx_opts.layout) */
-#define FMX_LAYOUT_AUTO     0   /* planes if it fits fmx_opts.max_index_bytes (default 64 GiB), else WM  */
+#define FMX_LAYOUT_AUTO     0   /* planes if it fits fmx_opts.max_index_bytes (default 64 GiB) and max_total_bytes, else WMX, else WM */
 #define FMX_LAYOUT_WM       1   /* byte-alphabet wavelet matrix, ceil(log2 sigma) levels, 64-B rank blocks */
 #define FMX_LAYOUT_PLANES   2   /* one 64-B-rank-block bitvector per symbol (1 block fetch per rank)     */
+#define FMX_LAYOUT_WMX      3   /* multi-ary wavelet matrix: 16-ary digits (4-ary for <= 4 symbols) in 128-byte blocks = one request per digit:
+                                   2 requests per rank for a byte alphabet (1 for <= 16 symbols) at ~2n bytes (0.29n for DNA)        */
 
 /* Bit-exact accelerators of the count path (fmx_opts.accel); they spend HBM capacity, never change results */
 #define FMX_ACCEL_AUTO      0
