@@ -438,7 +438,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     // two lanes per query: with the 256-bit load a 64-B rank block is one request from two lanes (as from four lanes with 128-bit
     // loads), and twice as many queries are in flight per SM
     if (!o.lanes_per_query) {
-        ix->cfg.lanes = 2;
+        ix->cfg.lanes = wmx ? 4 : 2;                        // a 128-byte multi-ary block is one request from four lanes x 256 bits
         // count kernels: one lane per query once a deep table + row contexts answer most queries in two single-lane requests
         // (measured on cfg 2: 19.96 vs 18.69 G q/s; the kernel at two lanes is issue-bound, 80 % of the issue slots)
         const bool saturating = (d.ctx != nullptr || d.ctx8 != nullptr) && d.kmer != nullptr && std::pow((double)sigma, d.kmer_k) >= n / 2.0;
@@ -1506,7 +1506,7 @@ int regex_search_core(fmx_index *ix, CallCtx &cc, fmx_regex_set *set, RegexResul
     if (total > kSmallSort) {
         DBuf tmp(st);
         CU(tmp.alloc(total * sizeof(RegexResult)));
-        CU(sort_regex_results(d_res, tmp.as<RegexResult>(), total, st));
+        CU(sort_regex_results(d_res, tmp.as<RegexResult>(), total, (uint32_t)set->m, (uint32_t)h[kRxMaxLen], st));
         ix->last_launches += 6; ix->total_launches += 6;
     } else if (total > 1) {
         CU(sort_results_small(d_res, total, st));

@@ -92,17 +92,44 @@ cudaError_t widen_u32_i64(const uint32_t *d_in, int64_t *d_out, int64_t n, cudaS
     return cudaGetLastError();
 }
 
-cudaError_t sort_regex_results(RegexResult *d_res, RegexResult *d_tmp, int64_t n, cudaStream_t st) {
+// one-key form: (regex, len, sp) packed into 64 bits orders the results completely — two results of one regex with the same length and
+// the same sp are the same string, hence the same interval — and only the used bits are sorted
+__global__ void pack_keys_kernel(const RegexResult *r, int64_t n, int len_bits, uint64_t *key, uint32_t *idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RegexResult v = r[i];
+    key[i] = ((((uint64_t)v.regex << len_bits) | v.len) << 32) | v.sp;
+    idx[i] = (uint32_t)i;
+}
+cudaError_t sort_regex_results(RegexResult *d_res, RegexResult *d_tmp, int64_t n, uint32_t n_regex, uint32_t max_len, cudaStream_t st) {
     if (n <= 1) return cudaSuccess;
     if (n >= (1ll << 32)) return cudaErrorInvalidValue;
-    uint64_t *hi, *lo, *k2; uint32_t *i0, *i1;
+    int rb = 1, lb = 1;
+    while ((1ull << rb) < (uint64_t)n_regex) ++rb;
+    while ((1ull << lb) <= (uint64_t)max_len) ++lb;
+    const unsigned grid = (unsigned)((n + 255) / 256);
     cudaError_t e;
+    if (rb + lb <= 32) {
+        uint64_t *k0, *k1; uint32_t *i0, *i1;
+        if ((e = cudaMallocAsync(&k0, n * 8, st)) != cudaSuccess) return e;
+        if ((e = cudaMallocAsync(&k1, n * 8, st)) != cudaSuccess) return e;
+        if ((e = cudaMallocAsync(&i0, n * 4, st)) != cudaSuccess) return e;
+        if ((e = cudaMallocAsync(&i1, n * 4, st)) != cudaSuccess) return e;
+        pack_keys_kernel<<<grid, 256, 0, st>>>(d_res, n, lb, k0, i0);
+        e = sort_pairs_u64_u32(k0, k1, i0, i1, n, 0, 32 + rb + lb, st);
+        if (e == cudaSuccess) {
+            gather_res_kernel<<<grid, 256, 0, st>>>(d_res, i1, n, d_tmp);
+            e = cudaMemcpyAsync(d_res, d_tmp, n * sizeof(RegexResult), cudaMemcpyDeviceToDevice, st);
+        }
+        cudaFreeAsync(k0, st); cudaFreeAsync(k1, st); cudaFreeAsync(i0, st); cudaFreeAsync(i1, st);
+        return e;
+    }
+    uint64_t *hi, *lo, *k2; uint32_t *i0, *i1;
     if ((e = cudaMallocAsync(&hi, n * 8, st)) != cudaSuccess) return e;
     if ((e = cudaMallocAsync(&lo, n * 8, st)) != cudaSuccess) return e;
     if ((e = cudaMallocAsync(&k2, n * 8, st)) != cudaSuccess) return e;
     if ((e = cudaMallocAsync(&i0, n * 4, st)) != cudaSuccess) return e;
     if ((e = cudaMallocAsync(&i1, n * 4, st)) != cudaSuccess) return e;
-    const unsigned grid = (unsigned)((n + 255) / 256);
     split_keys_kernel<<<grid, 256, 0, st>>>(d_res, n, hi, lo, i0);
     e = sort_pairs_u64_u32(lo, k2, i0, i1, n, 0, 64, st);                 // by (sp,ep)
     if (e == cudaSuccess) {

@@ -26,6 +26,6 @@ cudaError_t radix_sort_u64(const uint64_t *k_in, uint64_t *k_out, int64_t n, int
 cudaError_t radix_sort_u32(const uint32_t *k_in, uint32_t *k_out, int64_t n, cudaStream_t st);
 cudaError_t widen_u32_i64(const uint32_t *d_in, int64_t *d_out, int64_t n, cudaStream_t st);
 // sort regex results by (regex, len, sp, ep); d_tmp is scratch of the same size
-cudaError_t sort_regex_results(RegexResult *d_res, RegexResult *d_tmp, int64_t n, cudaStream_t st);
+cudaError_t sort_regex_results(RegexResult *d_res, RegexResult *d_tmp, int64_t n, uint32_t n_regex, uint32_t max_len, cudaStream_t st);
 
 }  // namespace fmx
