@@ -923,6 +923,9 @@ def regex_leg(cx, g, text, n_regexes, orc, steps):
             pass
     compile_s = time.time() - t0
     mr = len(trees)
+    if cx.world > 1:                                       # equal shards: every rank searches the same number of regexes
+        mr = int(-cx.max_over_ranks(-mr))
+        trees, kept = trees[:mr], kept[:mr]
     t0 = time.time()
     rset = g.regex_set(trees)
     upload_s = time.time() - t0
@@ -932,9 +935,21 @@ def regex_leg(cx, g, text, n_regexes, orc, steps):
     d_res = torch.zeros((cap, 4), dtype=torch.int32, device=cx.dev)
     d_off = torch.zeros(mr + 1, dtype=torch.int64, device=cx.dev)
     totals = []
+    ex = None
+    if cx.world > 1:
+        # N > 1: the records of every rank's shard are exchanged on the device (sharded.GpuExchange): per-regex counts and the
+        # {regex, len, sp, ep} slabs go by kernel stores into every rank's gathered buffers, 2 x 4-byte NCCL barrier
+        from findex_b200 import sharded
+        first = rset.search_dev(g, d_res.data_ptr(), cap, d_off.data_ptr())
+        all_res = int(cx.sum_over_ranks(first))
+        ex = sharded.GpuExchange(g, cx.rank, cx.world, cx.world * mr, 4 * all_res + 64, cx.dev)
 
     def dev_step():
-        totals.append(rset.search_dev(g, d_res.data_ptr(), cap, d_off.data_ptr()))
+        if ex is not None:
+            _, t_ = ex.regex(rset, cx.rank * mr, (cx.rank + 1) * mr, cap)
+            totals.append(t_)
+        else:
+            totals.append(rset.search_dev(g, d_res.data_ptr(), cap, d_off.data_ptr()))
 
     def host_step():
         rc = fx.lib().fmx_regex_set_search(g.h, rset.h, cap, off.ctypes.data_as(C.c_void_p), C.c_void_p(ln_.array.ctypes.data),
@@ -955,12 +970,21 @@ def regex_leg(cx, g, text, n_regexes, orc, steps):
     cx.launches += (2 * steps + 5) * launches
     total = int(off[mr])
     assert total == totals[-1], "device-resident and host searches disagree on the number of results"
-    rec = d_res[:total].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    if ex is not None:                                     # this rank's records inside the gathered buffer
+        goff = ex.offsets().cpu().numpy()
+        lo_w, hi_w = int(goff[cx.rank * mr]), int(goff[(cx.rank + 1) * mr])
+        rec = ex.gathered_values(4 * int(goff[-1])).reshape(-1, 4)[lo_w:hi_w].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+        assert hi_w - lo_w == total and np.array_equal(rec[:, 0], np.repeat(np.arange(cx.rank * mr, (cx.rank + 1) * mr), np.diff(off)))
+    else:
+        rec = d_res[:total].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
     assert np.array_equal(rec[:, 1], ln_.array[:total]) and np.array_equal(rec[:, 2], sp_.array[:total]) and np.array_equal(rec[:, 3], ep_.array[:total])
     occurrences = int((ep_.array[:total] - sp_.array[:total]).sum())
     sample = [(kept[i], sorted(zip(ln_.array[off[i]:off[i + 1]].tolist(), sp_.array[off[i]:off[i + 1]].tolist(), ep_.array[off[i]:off[i + 1]].tolist())))
               for i in np.random.default_rng(9).choice(mr, min(200, mr), replace=False)]
-    out = {"value": cx.world * mr / (float(np.mean(kms)) * 1e-3), "unit": "regexes/s", "ms_per_step": float(np.mean(kms)), "steps": steps,
+    dev_ms = float(np.mean(kms)) if ex is None else ms_dev / steps          # N > 1: the step includes the exchange (wall clock, max over ranks)
+    out = {"value": cx.world * mr / (dev_ms * 1e-3), "unit": "regexes/s", "ms_per_step": dev_ms, "steps": steps,
+           "exchange": "none" if ex is None else "kernel stores of per-regex counts + record slabs into every rank's gathered buffer (CUDA IPC) + 2 x 4-byte NCCL barrier",
+           "kernel_ms_per_step": float(np.mean(kms)),
            "what": "fmx_regex_set_search_dev: Glushkov engine, caps off, device-resident regex set; traversal (work-queue kernel) + ordering on the device, CUDA-event time",
            "call_value": cx.world * mr * steps / (ms_dev * 1e-3), "call_ms_per_step": ms_dev / steps,
            "regexes_per_gpu": mr, "rejected_by_compiler": len(rxs) - mr, "result_triples": total, "occurrences_covered": occurrences, "items_processed": int(items),
@@ -988,6 +1012,10 @@ def regex_leg(cx, g, text, n_regexes, orc, steps):
         out["cpu_baseline"] = {"value": len(sample) / dtr, "unit": "regexes/s", "cores": cores, "kind": "port",
                                "sample": "%d regexes of the batch (ReTree._matchSA, caps off, automata precompiled), %d threads, %.2f s" % (len(sample), cores, dtr),
                                "parity_on_sample": bool(ok)}
+    if ex is not None:
+        ex.close_peers()
+        cx.barrier()
+        ex.close()
     rset.close()
     for a in (ln_, sp_, ep_):
         a.free()

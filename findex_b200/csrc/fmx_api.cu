@@ -1443,6 +1443,10 @@ int fmx_regex_set_limits(fmx_regex_set *set, int64_t max_len) {
     return FMX_OK;
 }
 
+// Tuning hook of the traversal kernel: how many children a warp keeps on its own shared-memory stack (0..256, default 64) before the
+// rest goes to the global ring, where idle warps pick it up.  Results never change.
+int fmx_set_regex_local_keep(int32_t items) { set_regex_local_keep(items); return FMX_OK; }
+
 // Pre-sizes (or shrinks) the set's work ring to `slots` (rounded up to a power of two, at least the number of start items): a ring that
 // turns out too small is abandoned and the traversal rerun with a 4x larger one, which this lets tests and memory-tight callers provoke.
 int fmx_regex_set_ring(fmx_regex_set *set, int64_t slots) {

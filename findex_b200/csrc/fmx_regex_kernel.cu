@@ -28,6 +28,7 @@
 #include "fmx_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 
 namespace fmx {
 
@@ -86,7 +87,7 @@ constexpr int kLocalSlots = 256;           // per-warp stack of items in shared 
 template <int G, int LAYOUT>
 __global__ void __launch_bounds__(kThreads)
 regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ RegexTables rt, FrontierItem *ring, unsigned long long ring_mask,
-                   RegexResult *__restrict__ res, long long cap_res, unsigned long long *ctrl, uint32_t len_cap) {
+                   RegexResult *__restrict__ res, long long cap_res, unsigned long long *ctrl, uint32_t len_cap, uint32_t local_keep) {
     __shared__ SharedTables tb;
     __shared__ __align__(16) FrontierItem lstack[kThreads / 32][kLocalSlots];
     load_tables(tb, ix);
@@ -244,7 +245,7 @@ regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ 
             if (kept_total == 0) continue;                  // warp-uniform
             // births are counted before anybody else can see them: the running balance is flushed whenever it turns positive
             ldelta += kept_total;
-            const uint32_t room = min((uint32_t)kLocalSlots - ltop, kept_total);
+            const uint32_t room = min(local_keep > ltop ? local_keep - ltop : 0u, kept_total);
             unsigned long long tb0 = 0;
             if (lane == 0) {
                 if (ldelta > 0) atomicAdd(&ctrl[kRxPending], (unsigned long long)ldelta);
@@ -273,7 +274,7 @@ regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ 
         // ---- short follow lists: go on with the first follow in registers, push the others; settle the balance
         ldelta += (long long)pushes - (long long)finished;
         {
-            const uint32_t room = min((uint32_t)kLocalSlots - ltop, pushes);
+            const uint32_t room = min(local_keep > ltop ? local_keep - ltop : 0u, pushes);
             unsigned long long tb0 = 0;
             if (lane == 0) {
                 if (ldelta > 0) atomicAdd(&ctrl[kRxPending], (unsigned long long)ldelta);
@@ -302,6 +303,9 @@ regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ 
     if (lane == 0 && nsteps) atomicAdd(&ctrl[kRxSteps], (unsigned long long)nsteps);       // backward steps taken = items processed
 }
 
+std::atomic<int> g_regex_local_keep{64};
+void set_regex_local_keep(int v) { g_regex_local_keep = v; }
+
 cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, const RegexTables &rt, const uint32_t *d_first, int64_t n_first,
                                 FrontierItem *d_ring, int64_t ring_cap, RegexResult *d_res, int64_t cap_res, unsigned long long *d_ctrl,
                                 uint32_t max_len, cudaStream_t st) {
@@ -312,6 +316,9 @@ cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, const RegexTa
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     regex_seed_kernel<<<(unsigned)std::min<int64_t>((n_first + 255) / 256 + 1, sms * 8), 256, 0, st>>>(d_first, n_first, ix.n, d_ring, d_ctrl);
     if (n_first <= 0) return cudaGetLastError();
+    // children a warp keeps on its own stack; what exceeds it goes to the global ring where idle warps find it (a '.' expansion is 253
+    // children: all-local leaves the other warps idle, all-global pays an atomic round trip per child)
+    const uint32_t local_keep = (uint32_t)std::min(std::max(g_regex_local_keep.load(), 0), kLocalSlots);
 #define CALL(G, LAY)                                                                                                  \
     {                                                                                                                 \
         auto k = regex_queue_kernel<G, LAY>;                                                                          \
@@ -319,7 +326,7 @@ cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, const RegexTa
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0);                                   \
         if (e == cudaSuccess) {                                                                                       \
             if (per_sm <= 0) e = cudaErrorLaunchOutOfResources;                                                       \
-            else k<<<(unsigned)(sms * per_sm), kThreads, 0, st>>>(ix, rt, d_ring, (unsigned long long)(ring_cap - 1), d_res, cap_res, d_ctrl, max_len); \
+            else k<<<(unsigned)(sms * per_sm), kThreads, 0, st>>>(ix, rt, d_ring, (unsigned long long)(ring_cap - 1), d_res, cap_res, d_ctrl, max_len, local_keep); \
         }                                                                                                             \
     }
     if (cfg.layout == FMX_LAYOUT_PLANES) {

@@ -134,7 +134,12 @@ int fmx_count_fixed_dev(fmx_index *ix, const void *d_pat, int32_t len, int64_t m
 /* Fused count + exchange for the multi-GPU path (index replicated, batch sharded): besides d_sp/d_ep, the hit
  * count (ep-sp, uint32) of local query q is stored to sinks[j][offset+q] for each of the n_sinks (<= 8) gathered
  * buffers — this rank's and, via CUDA IPC, its peers' — so the all-gather of counts happens inside the kernel over
- * NVLink/NVSwitch peer memory instead of in a separate collective.                                          */
+ * NVLink/NVSwitch peer memory instead of in a separate collective.
+ * Protocol the caller owns (bench.py::FusedExchange is the reference form): after the kernel, a cross-rank barrier on the stream (a
+ * 4-byte all-reduce) makes every rank's stores of the step visible everywhere; consumers of step s read the gathered buffer behind
+ * that barrier.  A buffer set may be written again only after every rank's consumers of its previous use have finished: rotate THREE
+ * sets and launch kernel s (set s mod 3) behind the barrier of step s-2 — every rank enqueued the consumers of step s-3 ahead of its
+ * kernel s-2, so that barrier's completion proves they are done.  Two sets with only the same-set barrier are not enough.        */
 int fmx_count_fixed_dev_gather(fmx_index *ix, const void *d_pat, int32_t len, int64_t m, void *d_sp_u32, void *d_ep_u32,
                                void *const *sinks, int32_t n_sinks, int64_t offset, void *stream);
 /* cudaMalloc'ed, zeroed buffers that the ranks of one node can map into each other (cudaIpc*).               */
@@ -247,6 +252,9 @@ int  fmx_regex_set_search_dev(fmx_index *ix, fmx_regex_set *set, void *d_res, in
  * an extension with the same meaning).  The reference's order-dependent caps (maxIterations; ReTree.matchSA's maxBranching = 1024,
  * maxIterations = 1000 defaults, retree.scala:570, :628) are not offered: what survives them depends on Scala's PriorityQueue tie order. */
 int  fmx_regex_set_limits(fmx_regex_set *set, int64_t max_len);
+/* Tuning hook of the traversal kernel: children a warp keeps on its own shared-memory stack (0..256, default 64) before spilling to
+ * the global ring where idle warps find them.  Results never change.                                                                 */
+int  fmx_set_regex_local_keep(int32_t items);
 /* Sizes the set's device work ring to `slots` items (power of two, >= the number of start positions; default: 4x the start positions,
  * at least 2^20).  A traversal that overflows its ring is abandoned and rerun with a 4x larger one — results never change.            */
 int  fmx_regex_set_ring(fmx_regex_set *set, int64_t slots);

@@ -10,6 +10,8 @@ cap() {   # name kernel-regex launch-skip what
   ncu -i /tmp/$1.ncu-rep --page raw --csv > gpurun_out/$1_raw.csv 2>/dev/null
   ls -la /tmp/$1.ncu-rep
 }
+timeout 400 python tools/profile_legs.py --what regex --reps 5 --rx-local 0,16,32,64,128,256 2>&1 | grep what > gpurun_out/r02_regex_local_keep_sweep.jsonl
+cat gpurun_out/r02_regex_local_keep_sweep.jsonl
 cap r02_regex_queue_english regex_queue_kernel 1 regex
 cp /tmp/r02_regex_queue_english.ncu-rep gpurun_out/ 2>/dev/null
 cap r02_locate_english locate_kernel 1 locate

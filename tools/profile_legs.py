@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--what", default="regex")
     ap.add_argument("--n", type=int, default=1_000_000_000)
     ap.add_argument("--reps", type=int, default=4)
+    ap.add_argument("--rx-local", default="", help="comma list of fmx_set_regex_local_keep values to time the regex search with")
     args = ap.parse_args()
     import torch
     fbuild.build()
@@ -90,12 +91,18 @@ def main():
             rset = g.regex_set(trees)
             cap = 1 << 22
             d_res = torch.zeros((cap, 4), dtype=torch.int32, device="cuda")
-            for _ in range(args.reps):
-                t0 = time.time()
-                total = rset.search_dev(g, d_res.data_ptr(), cap, 0)
-                wall = time.time() - t0
-            print(json.dumps({"what": "regex", "results": total, "kernel_ms": g.last_kernel_ms(), "call_ms": wall * 1e3, "items": g.last_steps(),
-                              "launches": g.last_kernel_launches()}), flush=True)
+            fx.lib().fmx_set_regex_local_keep.argtypes = [__import__("ctypes").c_int32]
+            for keep in ([int(x) for x in args.rx_local.split(",")] if args.rx_local else [64]):
+                fx.lib().fmx_set_regex_local_keep(keep)
+                ms = []
+                for _ in range(args.reps):
+                    t0 = time.time()
+                    total = rset.search_dev(g, d_res.data_ptr(), cap, 0)
+                    wall = time.time() - t0
+                    ms.append(g.last_kernel_ms())
+                print(json.dumps({"what": "regex", "local_keep": keep, "results": total, "kernel_ms_best": min(ms), "kernel_ms_last": ms[-1], "call_ms": wall * 1e3,
+                                  "items": g.last_steps(), "launches": g.last_kernel_launches()}), flush=True)
+            fx.lib().fmx_set_regex_local_keep(64)
             rset.close()
         g.close()
 
