@@ -1371,6 +1371,7 @@ struct fmx_regex_set {
     void *d_ring = nullptr, *d_ctrl = nullptr;     // work ring (all slots empty between searches) and the traversal's control words
     int64_t ring_cap = 0;
     uint32_t max_len = 0;                          // fmx_regex_set_limits
+    bool present[256] = {false};                   // the alphabet the follow lists were pruned for
     std::mutex mu;                                 // one traversal at a time per set (they share the ring)
 };
 
@@ -1393,29 +1394,42 @@ int fmx_regex_set_create(fmx_index *ix, fmx_regex *const *rx, int64_t m, fmx_reg
         n_states += rx[r]->a.c.size(); n_fol += rx[r]->a.follows.size(); n_first += rx[r]->a.firsts.size();
     }
     if (n_states >= (1ull << 32) - 1 || n_fol >= (1ull << 32)) return fail(FMX_E_LIMIT, "regex batch has too many states; split the batch");
+    // A follow position whose character does not occur in the indexed text can never survive its backward step (getPrevRange of an
+    // absent byte is None), so it is left out of the device follow lists: '.' = 253 positions in the reference costs sigma items here
+    // (28 on English text), '\\d' over a text without digits none.  Results are unchanged; the set remembers the alphabet it was pruned
+    // for and refuses an index that has other symbols.
+    bool present[256];
+    present[0] = true;                                        // a step with byte 0 is defined (the '$' row), keep it
+    for (int c = 1; c < 256; ++c) present[c] = ix->counts0[c] > 0;
     std::vector<uint4> rec(n_states);
-    std::vector<uint32_t> st_regex(n_states), fol(n_fol), first(n_first);
+    std::vector<uint32_t> st_regex(n_states), fol, first(n_first);
+    fol.reserve(n_fol);
     {
-        size_t so = 0, fo = 0, io = 0;
+        size_t so = 0, io = 0;
         for (int64_t r = 0; r < m; ++r) {
             const CompiledRegex &a = rx[r]->a;
-            const uint32_t base = (uint32_t)so, fbase = (uint32_t)fo;
+            const uint32_t base = (uint32_t)so;
             const size_t ns = a.c.size();
             const uint32_t stop = a.stop_on_emit ? 2u : 0u;
-            for (size_t k = 0; k < a.follows.size(); ++k) fol[fo + k] = base + (uint32_t)a.follows[k];
             for (size_t s = 0; s < ns; ++s) {
-                const uint32_t f0 = (uint32_t)a.follows_off[s], nf = (uint32_t)(a.follows_off[s + 1] - a.follows_off[s]);
-                rec[so + s] = make_uint4((uint32_t)a.c[s] | (((uint32_t)a.is_last[s] | stop) << 8), fbase + f0, nf, nf ? fol[fo + f0] : 0u);
+                const uint32_t f0 = (uint32_t)fol.size();
+                for (int32_t k = a.follows_off[s]; k < a.follows_off[s + 1]; ++k)
+                    if (present[a.c[(size_t)a.follows[(size_t)k]]]) fol.push_back(base + (uint32_t)a.follows[(size_t)k]);
+                const uint32_t nf = (uint32_t)fol.size() - f0;
+                rec[so + s] = make_uint4((uint32_t)a.c[s] | (((uint32_t)a.is_last[s] | stop) << 8), f0, nf, nf ? fol[f0] : 0u);
                 st_regex[so + s] = (uint32_t)r;
             }
             for (int32_t f : a.firsts) first[io++] = base + (uint32_t)f;
-            so += ns; fo += a.follows.size();
+            so += ns;
         }
     }
+    n_fol = fol.size();
+    if (fol.empty()) fol.push_back(0);
     ph.mark("concatenate tables");
     DeviceGuard g(ix->device);
     fmx_regex_set *s = new fmx_regex_set();
     s->device = ix->device; s->m = m; s->n_states = n_states; s->n_fol = n_fol; s->n_first = n_first;
+    for (int c = 0; c < 256; ++c) s->present[c] = present[c];
     auto up = [&](void **d, const void *h, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(d, bytes ? bytes : 16);
         if (e == cudaSuccess && bytes) e = cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
@@ -1423,7 +1437,7 @@ int fmx_regex_set_create(fmx_index *ix, fmx_regex *const *rx, int64_t m, fmx_reg
     };
     cudaError_t e = up(&s->d_rec, rec.data(), n_states * sizeof(uint4));
     if (e == cudaSuccess) e = up(&s->d_rx, st_regex.data(), n_states * 4);
-    if (e == cudaSuccess) e = up(&s->d_f, fol.data(), n_fol * 4);
+    if (e == cudaSuccess) e = up(&s->d_f, fol.data(), fol.size() * 4);
     if (e == cudaSuccess) e = up(&s->d_first, first.data(), n_first * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_ctrl, 64);
     if (e != cudaSuccess) { fmx_regex_set_free(s); return fail(FMX_E_CUDA, "regex set upload failed: %s", cudaGetErrorString(e)); }
@@ -1443,7 +1457,7 @@ int fmx_regex_set_limits(fmx_regex_set *set, int64_t max_len) {
     return FMX_OK;
 }
 
-// Tuning hook of the traversal kernel: how many children a warp keeps on its own shared-memory stack (0..256, default 64) before the
+// Tuning hook of the traversal kernel: how many children a warp keeps on its own shared-memory stack (0..256, default 256) before the
 // rest goes to the global ring, where idle warps pick it up.  Results never change.
 int fmx_set_regex_local_keep(int32_t items) { set_regex_local_keep(items); return FMX_OK; }
 
@@ -1469,6 +1483,9 @@ int regex_search_core(fmx_index *ix, CallCtx &cc, fmx_regex_set *set, RegexResul
     const int64_t n_first = (int64_t)set->n_first;
     *total_out = 0;
     if (set->m == 0 || n_first == 0) return FMX_OK;
+    for (int c = 1; c < 256; ++c)
+        if (ix->counts0[c] > 0 && !set->present[c])
+            return fail(FMX_E_ARG, "the regex set was created for an index without byte %d, which this index contains; create the set against this index", c);
     size_t fr = 0, to = 0;
     RegexTables rt{(const uint4 *)set->d_rec, (const uint32_t *)set->d_rx, (const uint32_t *)set->d_f};
     auto grow_ring = [&](int64_t want) -> int {

@@ -267,6 +267,10 @@ next_substr_kernel(const __grid_constant__ DevIndex ix, const long long *__restr
 // =====================================================================================================
 // K2: locate — one group per occurrence, LF-walk to the nearest sampled row
 // =====================================================================================================
+// A warp owns kLocateChunk consecutive occurrences of the slab and its lane groups REFILL: a group whose walk has reached a sampled row
+// takes the warp's next occurrence at once, so the groups stay busy although walks differ in length (0 .. rate-1 steps, half the
+// maximum on average: without the refill half of every warp idles while its longest walk finishes).
+constexpr int kLocateChunk = 1024;
 template <int G, int LAYOUT>
 __global__ void __launch_bounds__(kThreads)
 locate_kernel(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ sp, const long long *__restrict__ off,
@@ -275,47 +279,74 @@ locate_kernel(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ 
     __shared__ SharedTables tb;
     load_tables(tb, ix);
     __syncthreads();
-    const long long t = (long long)blockIdx.x * (kThreads / G) + threadIdx.x / G;      // slab-local occurrence
-    if (t >= count) return;
-    const long long T = t0 + t;                                                          // its place in the whole batch
-    // owning query: last q in [q0, q1) with off[q] <= T (queries without occurrences share their offset with the next one)
-    long long lo = q0, hi = q1;
-    while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (off[mid] <= T) lo = mid; else hi = mid; }
-    uint32_t r = sp[lo] + (uint32_t)(T - off[lo]);
-    // output: the position alone (a slab that is one query), or the sort key (query index inside the slab, position) of the per-query ordering
-    const unsigned long long seg = (unsigned long long)(lo - q0) << 32;
-#define FMX_EMIT(P) do { if ((threadIdx.x % G) == 0) { if (key) key[t] = seg | (unsigned long long)(P); else pos[t] = (P); } } while (0)
-    if (ix.sa != nullptr) {                                    // full suffix array resident: one load per occurrence
-        FMX_EMIT(ix.sa[r]);
-        return;
-    }
-    uint32_t k = 0;
-    if (ix.bm != nullptr) {                                    // fused walk blocks: BWT byte + mark bit in one fetch per step
-        for (;;) {
-            uint32_t c, marked;
-            walk_block<G>(ix.bm, r, c, marked);
-            if (marked) {
-                const uint32_t mr = rank_one<G>(ix.mark, r, nullptr);
-                FMX_EMIT(ix.samples[mr] + k);
-                if ((threadIdx.x % G) == 0 && steps_out) atomicAdd(steps_out, (unsigned long long)k);
-                return;
-            }
-            r = lf_value<G, LAYOUT>(ix, tb, c, r);
-            if (++k > ix.n) { FMX_EMIT(0xFFFFFFFFu); return; }      // cannot happen on a consistent index (fmx_open checks)
-        }
-    }
+    const uint32_t lane = threadIdx.x & 31;
+    const bool leader = (threadIdx.x % G) == 0;
+    const int lead_lane = (int)(lane & ~(uint32_t)(G - 1));
+    const long long c0 = (((long long)blockIdx.x * kThreads + threadIdx.x) >> 5) * kLocateChunk;      // slab-local, warp-uniform
+    if (c0 >= count) return;
+    const long long c1 = (c0 + kLocateChunk < count) ? c0 + kLocateChunk : count;
+    // owning query of an occurrence T of the batch: last q with off[q] <= T (queries without occurrences share their offset with the
+    // next one).  The chunk's two ends are located in [q0, q1) once; every occurrence of the chunk then searches between them only.
+    auto owner = [&](long long T, long long lo, long long hi) {
+        while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (off[mid] <= T) lo = mid; else hi = mid; }
+        return lo;
+    };
+    long long qa = 0, qb = 0;
+    if (lane == 0) qa = owner(t0 + c0, q0, q1);
+    if (lane == 1) qb = owner(t0 + c1 - 1, q0, q1);
+    qa = __shfl_sync(0xFFFFFFFFu, qa, 0);
+    qb = __shfl_sync(0xFFFFFFFFu, qb, 1);
+#define FMX_EMIT(P) do { if (key) key[t] = seg | (unsigned long long)(P); else pos[t] = (P); } while (0)
+    long long next = c0;                                       // the warp's next unassigned occurrence (warp-uniform)
+    bool active = false;
+    long long t = 0;
+    unsigned long long seg = 0;
+    uint32_t r = 0, k = 0;
+    unsigned long long my_steps = 0;
     for (;;) {
-        uint32_t bit;
-        const uint32_t mr = rank_one<G>(ix.mark, r, &bit);
-        if (bit) {                                         // row eof (sa = 0) is always sampled, so '$' is never stepped over
-            FMX_EMIT(ix.samples[mr] + k);
-            if ((threadIdx.x % G) == 0 && steps_out) atomicAdd(steps_out, (unsigned long long)k);
-            return;
+        // ---- refill: idle groups take the next occurrences of the chunk
+        const uint32_t need = __ballot_sync(0xFFFFFFFFu, leader && !active);
+        if (need && next < c1) {
+            const long long avail = c1 - next;
+            const uint32_t rank = __popc(need & ((1u << lane) - 1u));
+            if (leader && !active && (long long)rank < avail) {
+                t = next + rank;
+                const long long T = t0 + t, lo = owner(T, qa, qb + 1);
+                r = sp[lo] + (uint32_t)(T - off[lo]);
+                seg = (unsigned long long)(lo - q0) << 32;     // sort key of the per-query ordering: (query index inside the slab, position)
+                k = 0;
+                active = true;
+            }
+            next += ((long long)__popc(need) < avail) ? (long long)__popc(need) : avail;
         }
-        r = lf_value<G, LAYOUT>(ix, tb, ix.bwt[r], r);
-        if (++k > ix.n) { FMX_EMIT(0xFFFFFFFFu); return; }
+        if (G > 1) {
+            active = __shfl_sync(0xFFFFFFFFu, (int)active, lead_lane) != 0;
+            r = __shfl_sync(0xFFFFFFFFu, r, lead_lane);
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        if (!active) continue;                                  // group-uniform; the warp-wide votes above are taken at the loop top only
+        // ---- one step of the walk
+        if (ix.sa != nullptr) {                                // full suffix array resident: one load per occurrence
+            if (leader) FMX_EMIT(ix.sa[r]);
+            active = false;
+            continue;
+        }
+        uint32_t c, marked;
+        if (ix.bm != nullptr) walk_block<G>(ix.bm, r, c, marked);          // BWT byte + mark bit of the row in one fetch
+        else { marked = 0; c = 0; }
+        uint32_t mr = 0;
+        if (ix.bm == nullptr) { uint32_t bit; mr = rank_one<G>(ix.mark, r, &bit); marked = bit; if (!bit) c = ix.bwt[r]; }
+        if (marked) {                                          // row eof (sa = 0) is always sampled, so '$' is never stepped over
+            if (ix.bm != nullptr) mr = rank_one<G>(ix.mark, r, nullptr);
+            if (leader) { FMX_EMIT(ix.samples[mr] + k); my_steps += k; }
+            active = false;
+            continue;
+        }
+        r = lf_value<G, LAYOUT>(ix, tb, c, r);
+        if (++k > ix.n) { if (leader) FMX_EMIT(0xFFFFFFFFu); active = false; }      // cannot happen on a consistent index (fmx_open checks)
     }
 #undef FMX_EMIT
+    if (steps_out && my_steps) atomicAdd(steps_out, my_steps);
 }
 
 // low words of the sorted (query, position) keys: the positions, ascending inside each query — as uint32 (device callers) or widened
@@ -559,7 +590,9 @@ cudaError_t launch_next_substr(const DevIndex &ix, LaunchCfg cfg, const int64_t 
 cudaError_t launch_locate(const DevIndex &ix, LaunchCfg cfg, const uint32_t *d_sp, const int64_t *d_off, int64_t q0, int64_t q1,
                           int64_t t0, int64_t count, uint32_t *d_pos, uint64_t *d_key, unsigned long long *d_steps, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-#define CALL(G, LAY) locate_kernel<G, LAY><<<grid_for(count, G), kThreads, 0, st>>>(ix, d_sp, (const long long *)d_off, q0, q1, t0, count, d_pos, (unsigned long long *)d_key, d_steps)
+    const int64_t warps = (count + kLocateChunk - 1) / kLocateChunk;
+    const unsigned grid = (unsigned)((warps + kThreads / 32 - 1) / (kThreads / 32));
+#define CALL(G, LAY) locate_kernel<G, LAY><<<grid, kThreads, 0, st>>>(ix, d_sp, (const long long *)d_off, q0, q1, t0, count, d_pos, (unsigned long long *)d_key, d_steps)
     FMX_DISPATCH(cfg, CALL);
 #undef CALL
     return cudaGetLastError();

@@ -76,7 +76,7 @@ enum { kRxHead = 0, kRxTail = 1, kRxPending = 2, kRxMatches = 3, kRxStatus = 4, 
 cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, const RegexTables &rt, const uint32_t *d_first, int64_t n_first,
                                 FrontierItem *d_ring, int64_t ring_cap, RegexResult *d_res, int64_t cap_res, unsigned long long *d_ctrl,
                                 uint32_t max_len, cudaStream_t st);
-void set_regex_local_keep(int items);                    // children a warp keeps on its own stack before spilling to the ring (default 64)
+void set_regex_local_keep(int items);                    // children a warp keeps on its own stack before spilling to the ring (default: all 256)
 constexpr int64_t kSmallSort = 4096;                    // results ordered by one CTA in shared memory up to here
 cudaError_t sort_results_small(RegexResult *d_res, int64_t n, cudaStream_t st);
 cudaError_t launch_result_offsets(const RegexResult *d_res, int64_t n, int64_t m, int64_t *d_off, cudaStream_t st);

@@ -238,7 +238,8 @@ int fmx_dfa_match_string(const fmx_regex *dfa, const uint8_t *s, int64_t len, in
 
 /* Compile once, search many times: a regex set keeps the concatenated automata of a batch resident on the index's device
  * (the batched form of `val t = ReTree(post)` ... `t.matchSA(sa)` ... `t.matchSA(sa2)`).  fmx_regex_search_batch is
- * create + search + free.  A set may be searched against any index on the same device.                          */
+ * create + search + free.  Follow positions whose byte does not occur in `ix`'s text are pruned at creation (they cannot survive their
+ * step; results are unchanged), so a set may be searched against an index on the same device whose symbols all occur in `ix`'s text.                          */
 typedef struct fmx_regex_set fmx_regex_set;
 int  fmx_regex_set_create(fmx_index *ix, fmx_regex *const *rx, int64_t m, fmx_regex_set **out);
 int  fmx_regex_set_search(fmx_index *ix, fmx_regex_set *set, int64_t cap_total, int64_t *out_off, int32_t *len, int64_t *sp, int64_t *ep);
@@ -252,7 +253,7 @@ int  fmx_regex_set_search_dev(fmx_index *ix, fmx_regex_set *set, void *d_res, in
  * an extension with the same meaning).  The reference's order-dependent caps (maxIterations; ReTree.matchSA's maxBranching = 1024,
  * maxIterations = 1000 defaults, retree.scala:570, :628) are not offered: what survives them depends on Scala's PriorityQueue tie order. */
 int  fmx_regex_set_limits(fmx_regex_set *set, int64_t max_len);
-/* Tuning hook of the traversal kernel: children a warp keeps on its own shared-memory stack (0..256, default 64) before spilling to
+/* Tuning hook of the traversal kernel: children a warp keeps on its own shared-memory stack (0..256, default 256) before spilling to
  * the global ring where idle warps find them.  Results never change.                                                                 */
 int  fmx_set_regex_local_keep(int32_t items);
 /* Sizes the set's device work ring to `slots` items (power of two, >= the number of start positions; default: 4x the start positions,
