@@ -1368,7 +1368,7 @@ struct fmx_regex_set {
     int64_t m = 0;
     size_t n_states = 0, n_fol = 0, n_first = 0;
     void *d_rec = nullptr, *d_rx = nullptr, *d_f = nullptr, *d_first = nullptr;
-    void *d_ring = nullptr, *d_ctrl = nullptr;     // work ring (all slots empty between searches) and the traversal's control words
+    void *d_ring = nullptr, *d_seq = nullptr, *d_ctrl = nullptr;     // work ring, its per-slot sequence words, the traversal's control words
     int64_t ring_cap = 0;
     uint32_t max_len = 0;                          // fmx_regex_set_limits
     bool present[256] = {false};                   // the alphabet the follow lists were pruned for
@@ -1378,7 +1378,7 @@ struct fmx_regex_set {
 void fmx_regex_set_free(fmx_regex_set *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    cudaFree(s->d_rec); cudaFree(s->d_rx); cudaFree(s->d_f); cudaFree(s->d_first); cudaFree(s->d_ring); cudaFree(s->d_ctrl);
+    cudaFree(s->d_rec); cudaFree(s->d_rx); cudaFree(s->d_f); cudaFree(s->d_first); cudaFree(s->d_ring); cudaFree(s->d_seq); cudaFree(s->d_ctrl);
     delete s;
 }
 
@@ -1469,9 +1469,9 @@ int fmx_regex_set_ring(fmx_regex_set *set, int64_t slots) {
     cudaSetDevice(set->device);
     int64_t cap = 1024;
     while (cap < slots || cap < (int64_t)set->n_first) cap <<= 1;
-    if (set->d_ring) { CU(cudaDeviceSynchronize()); CU(cudaFree(set->d_ring)); set->d_ring = nullptr; set->ring_cap = 0; }
+    if (set->d_ring) { CU(cudaDeviceSynchronize()); CU(cudaFree(set->d_ring)); CU(cudaFree(set->d_seq)); set->d_ring = set->d_seq = nullptr; set->ring_cap = 0; }
     CU(cudaMalloc(&set->d_ring, (size_t)cap * sizeof(FrontierItem)));
-    CU(cudaMemset(set->d_ring, 0xFF, (size_t)cap * sizeof(FrontierItem)));
+    CU(cudaMalloc(&set->d_seq, (size_t)cap * 4));
     set->ring_cap = cap;
     return FMX_OK;
 }
@@ -1495,25 +1495,25 @@ int regex_search_core(fmx_index *ix, CallCtx &cc, fmx_regex_set *set, RegexResul
         if (cap > set->ring_cap && (size_t)cap * sizeof(FrontierItem) > fr / 2 + (size_t)set->ring_cap * sizeof(FrontierItem))
             return fail(FMX_E_LIMIT, "regex traversal needs a work ring of %lld items, more than half of the free device memory; split the batch", (long long)cap);
         if (cap > set->ring_cap) {
-            if (set->d_ring) { CU(cudaStreamSynchronize(st)); CU(cudaFree(set->d_ring)); set->d_ring = nullptr; set->ring_cap = 0; }
+            if (set->d_ring) { CU(cudaStreamSynchronize(st)); CU(cudaFree(set->d_ring)); CU(cudaFree(set->d_seq)); set->d_ring = set->d_seq = nullptr; set->ring_cap = 0; }
             CU(cudaMalloc(&set->d_ring, (size_t)cap * sizeof(FrontierItem)));
+            CU(cudaMalloc(&set->d_seq, (size_t)cap * 4));
             set->ring_cap = cap;
         }
-        CU(cudaMemsetAsync(set->d_ring, 0xFF, (size_t)set->ring_cap * sizeof(FrontierItem), st));      // every slot empty
-        return FMX_OK;
+        return FMX_OK;                                      // the seed kernel of every traversal initialises the sequence words
     };
     if (set->ring_cap < n_first || set->d_ring == nullptr) { int rc = grow_ring(4 * n_first); if (rc) return rc; }
     Timed t(ix, cc);
     int64_t launches = 0;
     unsigned long long h[8] = {0};
     for (;;) {
-        CU(launch_regex_search(cc.d, cc.cfg, rt, (const uint32_t *)set->d_first, n_first, (FrontierItem *)set->d_ring, set->ring_cap, d_res, cap_res,
+        CU(launch_regex_search(cc.d, cc.cfg, rt, (const uint32_t *)set->d_first, n_first, (FrontierItem *)set->d_ring, (uint32_t *)set->d_seq, set->ring_cap, d_res, cap_res,
                                (unsigned long long *)set->d_ctrl, set->max_len, st));
         launches += 2;
         CU(cudaMemcpyAsync(h, set->d_ctrl, 64, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (h[kRxStatus] == 0) break;
-        if (h[kRxStatus] == 2) { grow_ring(set->ring_cap); return fail(FMX_E_LIMIT, "regex traversal deeper than the text"); }
+        if (h[kRxStatus] == 2) return fail(FMX_E_LIMIT, "regex traversal deeper than the text");
         int rc = grow_ring(set->ring_cap * 4);              // the ring overflowed: abandon, re-empty a larger one, rerun
         if (rc) return rc;
     }

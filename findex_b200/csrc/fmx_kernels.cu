@@ -296,13 +296,34 @@ locate_kernel(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ 
     if (lane == 1) qb = owner(t0 + c1 - 1, q0, q1);
     qa = __shfl_sync(0xFFFFFFFFu, qa, 0);
     qb = __shfl_sync(0xFFFFFFFFu, qb, 1);
-#define FMX_EMIT(P) do { if (key) key[t] = seg | (unsigned long long)(P); else pos[t] = (P); } while (0)
+#define FMX_EMIT_AT(T_, SEG_, P) do { if (key) key[T_] = (SEG_) | (unsigned long long)(P); else pos[T_] = (P); } while (0)
+    constexpr int GPW = 32 / G;                                // lane groups per warp
+    if (ix.sa != nullptr || ix.bm == nullptr) {
+        // full suffix array resident (one load per occurrence), or every row sampled (rate 1: no fused walk blocks): no refill needed
+        for (long long t = c0 + (long long)(lane / G); t < c1; t += GPW) {
+            const long long T = t0 + t, lo = owner(T, qa, qb + 1);
+            uint32_t r = sp[lo] + (uint32_t)(T - off[lo]), k = 0;
+            const unsigned long long seg = (unsigned long long)(lo - q0) << 32;
+            if (ix.sa != nullptr) { if (leader) FMX_EMIT_AT(t, seg, ix.sa[r]); continue; }
+            for (;;) {
+                uint32_t bit;
+                const uint32_t mr = rank_one<G>(ix.mark, r, &bit);
+                if (bit) { if (leader) FMX_EMIT_AT(t, seg, ix.samples[mr] + k); break; }
+                r = lf_value<G, LAYOUT>(ix, tb, ix.bwt[r], r);
+                if (++k > ix.n) { if (leader) FMX_EMIT_AT(t, seg, 0xFFFFFFFFu); break; }
+            }
+        }
+        return;
+    }
+    // Sampled walk, two dependent fetches per round for every group, whatever it is doing:
+    //   A  the walk block of the row (BWT byte + mark bit)            | the sample of a walk that ended last round (deferred emit)
+    //   B  the rank block of that byte's structure -> LF(row)          | the rank block of the mark bitvector -> index of the sample
+    // so a group that reaches a sampled row does not hold the others up with two extra dependent loads.
     long long next = c0;                                       // the warp's next unassigned occurrence (warp-uniform)
-    bool active = false;
-    long long t = 0;
-    unsigned long long seg = 0;
-    uint32_t r = 0, k = 0;
-    unsigned long long my_steps = 0;
+    bool active = false, pending = false;
+    long long t = 0, pt = 0;
+    unsigned long long seg = 0, pseg = 0, my_steps = 0;
+    uint32_t r = 0, k = 0, pmr = 0, pk = 0;
     for (;;) {
         // ---- refill: idle groups take the next occurrences of the chunk
         const uint32_t need = __ballot_sync(0xFFFFFFFFu, leader && !active);
@@ -323,29 +344,36 @@ locate_kernel(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ 
             active = __shfl_sync(0xFFFFFFFFu, (int)active, lead_lane) != 0;
             r = __shfl_sync(0xFFFFFFFFu, r, lead_lane);
         }
-        if (!__any_sync(0xFFFFFFFFu, active)) break;
-        if (!active) continue;                                  // group-uniform; the warp-wide votes above are taken at the loop top only
-        // ---- one step of the walk
-        if (ix.sa != nullptr) {                                // full suffix array resident: one load per occurrence
-            if (leader) FMX_EMIT(ix.sa[r]);
-            active = false;
-            continue;
+        if (!__any_sync(0xFFFFFFFFu, active || pending)) break;
+        // ---- A
+        uint32_t sval = 0, c = 0, marked = 0;
+        if (pending && leader) sval = ldg32(ix.samples + pmr);
+        if (active) walk_block<G>(ix.bm, r, c, marked);
+        if (pending) {
+            if (leader) { FMX_EMIT_AT(pt, pseg, sval + pk); my_steps += pk; }
+            pending = false;
         }
-        uint32_t c, marked;
-        if (ix.bm != nullptr) walk_block<G>(ix.bm, r, c, marked);          // BWT byte + mark bit of the row in one fetch
-        else { marked = 0; c = 0; }
-        uint32_t mr = 0;
-        if (ix.bm == nullptr) { uint32_t bit; mr = rank_one<G>(ix.mark, r, &bit); marked = bit; if (!bit) c = ix.bwt[r]; }
-        if (marked) {                                          // row eof (sa = 0) is always sampled, so '$' is never stepped over
-            if (ix.bm != nullptr) mr = rank_one<G>(ix.mark, r, nullptr);
-            if (leader) { FMX_EMIT(ix.samples[mr] + k); my_steps += k; }
-            active = false;
-            continue;
+        // ---- B
+        if (active) {
+            uint32_t x;
+            if (LAYOUT == FMX_LAYOUT_PLANES) {                 // one rank fetch for every group: mark bitvector or the byte's plane (same block format)
+                const uint4 *bv = marked ? ix.mark : ix.blocks + (uint64_t)tb.code[c] * ix.stride * 4;
+                x = rank_one<G>(bv, r, nullptr);
+                if (!marked) x += tb.base[c];
+            } else {
+                x = marked ? rank_one<G>(ix.mark, r, nullptr) : lf_value<G, LAYOUT>(ix, tb, c, r);
+            }
+            if (marked) {                                      // row eof (sa = 0) is always sampled, so '$' is never stepped over
+                pmr = x; pk = k; pt = t; pseg = seg;
+                pending = true;
+                active = false;
+            } else {
+                r = x;
+                if (++k > ix.n) { if (leader) FMX_EMIT_AT(t, seg, 0xFFFFFFFFu); active = false; }      // cannot happen on a consistent index
+            }
         }
-        r = lf_value<G, LAYOUT>(ix, tb, c, r);
-        if (++k > ix.n) { if (leader) FMX_EMIT(0xFFFFFFFFu); active = false; }      // cannot happen on a consistent index (fmx_open checks)
     }
-#undef FMX_EMIT
+#undef FMX_EMIT_AT
     if (steps_out && my_steps) atomicAdd(steps_out, my_steps);
 }
 

@@ -65,17 +65,17 @@ struct RegexTables {
     const uint32_t *st_regex;    // owning regex index in the batch
     const uint32_t *fol;         // follow lists, global state ids
 };
-struct FrontierItem { uint32_t state, len, sp, ep; };   // a ring slot; state 0xFFFFFFFF = empty
+struct FrontierItem { uint32_t state, len, sp, ep; };   // a ring slot / stack entry
 struct RegexResult  { uint32_t regex, len, sp, ep; };
 // control words of one traversal (8 x u64 on the device, initialised by the seed kernel)
 enum { kRxHead = 0, kRxTail = 1, kRxPending = 2, kRxMatches = 3, kRxStatus = 4, kRxDone = 5, kRxMaxLen = 6, kRxSteps = 7 };
-// The whole traversal: seed kernel + one persistent work-queue kernel.  d_ring: ring_cap (power of two, >= n_first) slots, every state word
-// 0xFFFFFFFF on entry and again on a clean exit.  d_ctrl[kRxMatches] = matches found (may exceed cap_res: writes are dropped, the count
+// The whole traversal: seed kernel (initialises the ring's sequence words and the start items) + one persistent work-queue kernel.
+// d_ring / d_seq: ring_cap (power of two, >= n_first) slots and their sequence words.  d_ctrl[kRxMatches] = matches found (may exceed cap_res: writes are dropped, the count
 // keeps growing), [kRxStatus] = 0 ok, 1 = the ring was too small (rerun with a larger, re-emptied ring), 2 = an item grew longer than the
 // text, [kRxMaxLen] = longest item, [kRxSteps] = items processed (one backward step each).
 cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, const RegexTables &rt, const uint32_t *d_first, int64_t n_first,
-                                FrontierItem *d_ring, int64_t ring_cap, RegexResult *d_res, int64_t cap_res, unsigned long long *d_ctrl,
-                                uint32_t max_len, cudaStream_t st);
+                                FrontierItem *d_ring, uint32_t *d_seq, int64_t ring_cap, RegexResult *d_res, int64_t cap_res,
+                                unsigned long long *d_ctrl, uint32_t max_len, cudaStream_t st);
 void set_regex_local_keep(int items);                    // children a warp keeps on its own stack before spilling to the ring (default: all 256)
 constexpr int64_t kSmallSort = 4096;                    // results ordered by one CTA in shared memory up to here
 cudaError_t sort_results_small(RegexResult *d_res, int64_t n, cudaStream_t st);

@@ -12,7 +12,8 @@
 //     first; only what does not fit spills to the global ring, and only a warp whose stack is empty takes work from it.  The balance
 //     of births and deaths a warp has not reported to `pending` is flushed whenever it turns positive (before a child could become
 //     visible to others) and when the warp runs dry, so `pending` never undercounts and most iterations touch no global counter.
-//   * a persistent grid of workers (G lanes per item) owns a global RING of items in HBM (start items, overflow of the stacks).  Consumers take tickets from `head` with one
+//   * a persistent grid of workers (G lanes per item) owns a global RING of items in HBM (start items, overflow of the stacks): a
+//     bounded MPMC queue with a sequence word per slot.  Consumers take tickets from `head` with one
 //     warp-aggregated atomic and wait for their slot to be filled; producers reserve tickets from `tail` the same way, write the
 //     payload and publish it with a release exchange on the slot's state word (an occupied slot = the ring is too small: the run is
 //     abandoned and the host reruns it with a larger ring).  `pending` counts live items; the worker that brings it to zero raises `done`.
@@ -34,8 +35,11 @@ namespace fmx {
 
 namespace {
 
-constexpr uint32_t kSlotEmpty = 0xFFFFFFFFu;
-
+// The ring is a bounded multi-producer / multi-consumer queue with one sequence word per slot (Vyukov): slot i starts at seq = i; the
+// producer of ticket t may write slot t & mask only while seq == t, and publishes with seq = t + 1; the consumer of ticket t waits for
+// seq == t + 1, reads the item and frees the slot for the next lap with seq = t + capacity.  Tickets that alias a slot (t and
+// t + capacity) can therefore never see each other's item, however many consumers wait; a producer that finds its slot not yet freed
+// reports the ring as too small.
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -46,13 +50,8 @@ __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v) {
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t exch_release(uint32_t *p, uint32_t v) {
-    uint32_t old;
-    asm volatile("atom.release.gpu.global.exch.b32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
-    return old;
+__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint4 ld_cg(const uint4 *p) {
     uint4 r;
@@ -65,22 +64,26 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     return v;
 }
 
-// publish one item at ticket `t`: payload first, then the state word with release semantics.  Returns false if the slot still held
-// an item nobody has read (ring too small).
-__device__ __forceinline__ bool ring_publish(FrontierItem *ring, unsigned long long mask, unsigned long long t, uint32_t state, uint32_t len,
-                                             uint32_t sp, uint32_t ep) {
-    FrontierItem *s = ring + (t & mask);
-    s->len = len; s->sp = sp; s->ep = ep;
-    return exch_release(&s->state, state) == kSlotEmpty;
+// publish one item at ticket `t`.  Returns false if the slot has not been freed by the consumer of the previous lap (ring too small).
+__device__ __forceinline__ bool ring_publish(FrontierItem *ring, uint32_t *seq, unsigned long long mask, unsigned long long t, uint32_t state,
+                                             uint32_t len, uint32_t sp, uint32_t ep) {
+    const unsigned long long i = t & mask;
+    if (ld_acquire(seq + i) != (uint32_t)t) return false;
+    *reinterpret_cast<uint4 *>(ring + i) = make_uint4(state, len, sp, ep);
+    st_release(seq + i, (uint32_t)t + 1u);
+    return true;
 }
 
 }  // namespace
 
 // ctrl (8 x u64, zeroed by the caller): see RegexCtrl in fmx_kernels.cuh
-__global__ void regex_seed_kernel(const uint32_t *__restrict__ first, long long n_first, uint32_t n, FrontierItem *ring, unsigned long long *ctrl) {
-    // level-0 items: StatePoint(0, 0, sa.n, state) for every first position  (retree.scala:576)
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_first; i += (long long)gridDim.x * blockDim.x)
-        ring[i] = FrontierItem{first[i], 0u, 0u, n};
+__global__ void regex_seed_kernel(const uint32_t *__restrict__ first, long long n_first, uint32_t n, FrontierItem *ring, uint32_t *seq, long long cap,
+                                  unsigned long long *ctrl) {
+    // level-0 items: StatePoint(0, 0, sa.n, state) for every first position  (retree.scala:576) = tickets 0 .. n_first-1, already published
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (long long)gridDim.x * blockDim.x) {
+        if (i < n_first) ring[i] = FrontierItem{first[i], 0u, 0u, n};
+        seq[i] = (uint32_t)i + (i < n_first ? 1u : 0u);
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         ctrl[kRxHead] = 0; ctrl[kRxTail] = (unsigned long long)n_first; ctrl[kRxPending] = (unsigned long long)n_first;
         ctrl[kRxMatches] = 0; ctrl[kRxStatus] = 0; ctrl[kRxDone] = n_first == 0 ? 1ull : 0ull; ctrl[kRxMaxLen] = 0; ctrl[kRxSteps] = 0;
@@ -91,7 +94,7 @@ constexpr int kLocalSlots = 256;           // per-warp stack of items in shared 
 
 template <int G, int LAYOUT>
 __global__ void __launch_bounds__(kThreads)
-regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ RegexTables rt, FrontierItem *ring, unsigned long long ring_mask,
+regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ RegexTables rt, FrontierItem *ring, uint32_t *seq, unsigned long long ring_mask,
                    RegexResult *__restrict__ res, long long cap_res, unsigned long long *ctrl, uint32_t len_cap, uint32_t local_keep) {
     __shared__ SharedTables tb;
     __shared__ __align__(16) FrontierItem lstack[kThreads / 32][kLocalSlots];
@@ -117,7 +120,7 @@ regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ 
     // beyond that; `idx` = position of the child among the `total` children pushed together
     auto place = [&](uint32_t idx, unsigned long long tbase, uint32_t room, uint32_t state, uint32_t len, uint32_t sp, uint32_t ep) {
         if (idx < room) mine[ltop + idx] = FrontierItem{state, len, sp, ep};
-        else ring_ok = ring_publish(ring, ring_mask, tbase + (idx - room), state, len, sp, ep) && ring_ok;
+        else ring_ok = ring_publish(ring, seq, ring_mask, tbase + (idx - room), state, len, sp, ep) && ring_ok;
     };
 
     for (;;) {
@@ -126,13 +129,13 @@ regex_queue_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ 
         // without item and ticket take tickets (one atomic per warp) once the stack is empty
         auto poll = [&]() {
             if (leader && !have && ticket != kNoTicket) {
-                FrontierItem *s = ring + (ticket & ring_mask);
+                const unsigned long long i = ticket & ring_mask;
                 // waiting costs a relaxed load per round (no fence); the acquire is paid once, when the slot has been filled
-                if (ld_relaxed(&s->state) != kSlotEmpty) {
-                    const uint32_t st = ld_acquire(&s->state);
-                    const uint4 raw = ld_cg(reinterpret_cast<const uint4 *>(s));
-                    it = FrontierItem{st, raw.y, raw.z, raw.w};
-                    st_relaxed(&s->state, kSlotEmpty);     // same 16 bytes as the load above: cannot pass it; the slot may be written again
+                if (ld_relaxed(seq + i) == (uint32_t)ticket + 1u) {
+                    (void)ld_acquire(seq + i);
+                    const uint4 raw = ld_cg(reinterpret_cast<const uint4 *>(ring + i));
+                    it = FrontierItem{raw.x, raw.y, raw.z, raw.w};
+                    st_release(seq + i, (uint32_t)ticket + (uint32_t)(ring_mask + 1ull));      // the slot is free for the next lap (after the read above)
                     have = true;
                     have_rec = false;
                     ticket = kNoTicket;
@@ -313,14 +316,14 @@ std::atomic<int> g_regex_local_keep{kLocalSlots};          // measured on 100 k 
 void set_regex_local_keep(int v) { g_regex_local_keep = v; }
 
 cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, const RegexTables &rt, const uint32_t *d_first, int64_t n_first,
-                                FrontierItem *d_ring, int64_t ring_cap, RegexResult *d_res, int64_t cap_res, unsigned long long *d_ctrl,
-                                uint32_t max_len, cudaStream_t st) {
+                                FrontierItem *d_ring, uint32_t *d_seq, int64_t ring_cap, RegexResult *d_res, int64_t cap_res,
+                                unsigned long long *d_ctrl, uint32_t max_len, cudaStream_t st) {
     if (ring_cap < n_first || (ring_cap & (ring_cap - 1))) return cudaErrorInvalidValue;
     int dev = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    regex_seed_kernel<<<(unsigned)std::min<int64_t>((n_first + 255) / 256 + 1, sms * 8), 256, 0, st>>>(d_first, n_first, ix.n, d_ring, d_ctrl);
+    regex_seed_kernel<<<(unsigned)std::min<int64_t>((ring_cap + 255) / 256, sms * 8), 256, 0, st>>>(d_first, n_first, ix.n, d_ring, d_seq, ring_cap, d_ctrl);
     if (n_first <= 0) return cudaGetLastError();
     // children a warp keeps on its own stack; what exceeds it goes to the global ring where idle warps find it (a '.' expansion is 253
     // children: all-local leaves the other warps idle, all-global pays an atomic round trip per child)
@@ -332,7 +335,7 @@ cudaError_t launch_regex_search(const DevIndex &ix, LaunchCfg cfg, const RegexTa
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0);                                   \
         if (e == cudaSuccess) {                                                                                       \
             if (per_sm <= 0) e = cudaErrorLaunchOutOfResources;                                                       \
-            else k<<<(unsigned)(sms * per_sm), kThreads, 0, st>>>(ix, rt, d_ring, (unsigned long long)(ring_cap - 1), d_res, cap_res, d_ctrl, max_len, local_keep); \
+            else k<<<(unsigned)(sms * per_sm), kThreads, 0, st>>>(ix, rt, d_ring, d_seq, (unsigned long long)(ring_cap - 1), d_res, cap_res, d_ctrl, max_len, local_keep); \
         }                                                                                                             \
     }
     if (cfg.layout == FMX_LAYOUT_PLANES) {
