@@ -267,10 +267,10 @@ next_substr_kernel(const __grid_constant__ DevIndex ix, const long long *__restr
 // =====================================================================================================
 // K2: locate — one group per occurrence, LF-walk to the nearest sampled row
 // =====================================================================================================
-// A warp owns kLocateChunk consecutive occurrences of the slab and its lane groups REFILL: a group whose walk has reached a sampled row
-// takes the warp's next occurrence at once, so the groups stay busy although walks differ in length (0 .. rate-1 steps, half the
-// maximum on average: without the refill half of every warp idles while its longest walk finishes).
-constexpr int kLocateChunk = 1024;
+// One lane group per occurrence.  (Round 2 also tried a persistent form — a warp owning a chunk of occurrences, groups refilling as their
+// walks end, the sample fetch deferred so that every round costs two dependent fetches: 334 ms instead of 286 ms for 4.9e8 occurrences.
+// The walks are bound by the request rate, not by idle lanes: adjacent lanes start on adjacent rows and share walk / mark blocks,
+// which the refill order gives up.)
 template <int G, int LAYOUT>
 __global__ void __launch_bounds__(kThreads)
 locate_kernel(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ sp, const long long *__restrict__ off,
@@ -279,102 +279,47 @@ locate_kernel(const __grid_constant__ DevIndex ix, const uint32_t *__restrict__ 
     __shared__ SharedTables tb;
     load_tables(tb, ix);
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31;
-    const bool leader = (threadIdx.x % G) == 0;
-    const int lead_lane = (int)(lane & ~(uint32_t)(G - 1));
-    const long long c0 = (((long long)blockIdx.x * kThreads + threadIdx.x) >> 5) * kLocateChunk;      // slab-local, warp-uniform
-    if (c0 >= count) return;
-    const long long c1 = (c0 + kLocateChunk < count) ? c0 + kLocateChunk : count;
-    // owning query of an occurrence T of the batch: last q with off[q] <= T (queries without occurrences share their offset with the
-    // next one).  The chunk's two ends are located in [q0, q1) once; every occurrence of the chunk then searches between them only.
-    auto owner = [&](long long T, long long lo, long long hi) {
-        while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (off[mid] <= T) lo = mid; else hi = mid; }
-        return lo;
-    };
-    long long qa = 0, qb = 0;
-    if (lane == 0) qa = owner(t0 + c0, q0, q1);
-    if (lane == 1) qb = owner(t0 + c1 - 1, q0, q1);
-    qa = __shfl_sync(0xFFFFFFFFu, qa, 0);
-    qb = __shfl_sync(0xFFFFFFFFu, qb, 1);
-#define FMX_EMIT_AT(T_, SEG_, P) do { if (key) key[T_] = (SEG_) | (unsigned long long)(P); else pos[T_] = (P); } while (0)
-    constexpr int GPW = 32 / G;                                // lane groups per warp
-    if (ix.sa != nullptr || ix.bm == nullptr) {
-        // full suffix array resident (one load per occurrence), or every row sampled (rate 1: no fused walk blocks): no refill needed
-        for (long long t = c0 + (long long)(lane / G); t < c1; t += GPW) {
-            const long long T = t0 + t, lo = owner(T, qa, qb + 1);
-            uint32_t r = sp[lo] + (uint32_t)(T - off[lo]), k = 0;
-            const unsigned long long seg = (unsigned long long)(lo - q0) << 32;
-            if (ix.sa != nullptr) { if (leader) FMX_EMIT_AT(t, seg, ix.sa[r]); continue; }
-            for (;;) {
-                uint32_t bit;
-                const uint32_t mr = rank_one<G>(ix.mark, r, &bit);
-                if (bit) { if (leader) FMX_EMIT_AT(t, seg, ix.samples[mr] + k); break; }
-                r = lf_value<G, LAYOUT>(ix, tb, ix.bwt[r], r);
-                if (++k > ix.n) { if (leader) FMX_EMIT_AT(t, seg, 0xFFFFFFFFu); break; }
-            }
-        }
+    const long long t = (long long)blockIdx.x * (kThreads / G) + threadIdx.x / G;      // slab-local occurrence
+    if (t >= count) return;
+    const long long T = t0 + t;                                                          // its place in the whole batch
+    // owning query: last q in [q0, q1) with off[q] <= T (queries without occurrences share their offset with the next one)
+    long long lo = q0, hi = q1;
+    while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (off[mid] <= T) lo = mid; else hi = mid; }
+    uint32_t r = sp[lo] + (uint32_t)(T - off[lo]);
+    // output: the position alone (a slab that is one query), or the sort key (query index inside the slab, position) of the per-query ordering
+    const unsigned long long seg = (unsigned long long)(lo - q0) << 32;
+#define FMX_EMIT(P) do { if ((threadIdx.x % G) == 0) { if (key) key[t] = seg | (unsigned long long)(P); else pos[t] = (P); } } while (0)
+    if (ix.sa != nullptr) {                                    // full suffix array resident: one load per occurrence
+        FMX_EMIT(ix.sa[r]);
         return;
     }
-    // Sampled walk, two dependent fetches per round for every group, whatever it is doing:
-    //   A  the walk block of the row (BWT byte + mark bit)            | the sample of a walk that ended last round (deferred emit)
-    //   B  the rank block of that byte's structure -> LF(row)          | the rank block of the mark bitvector -> index of the sample
-    // so a group that reaches a sampled row does not hold the others up with two extra dependent loads.
-    long long next = c0;                                       // the warp's next unassigned occurrence (warp-uniform)
-    bool active = false, pending = false;
-    long long t = 0, pt = 0;
-    unsigned long long seg = 0, pseg = 0, my_steps = 0;
-    uint32_t r = 0, k = 0, pmr = 0, pk = 0;
-    for (;;) {
-        // ---- refill: idle groups take the next occurrences of the chunk
-        const uint32_t need = __ballot_sync(0xFFFFFFFFu, leader && !active);
-        if (need && next < c1) {
-            const long long avail = c1 - next;
-            const uint32_t rank = __popc(need & ((1u << lane) - 1u));
-            if (leader && !active && (long long)rank < avail) {
-                t = next + rank;
-                const long long T = t0 + t, lo = owner(T, qa, qb + 1);
-                r = sp[lo] + (uint32_t)(T - off[lo]);
-                seg = (unsigned long long)(lo - q0) << 32;     // sort key of the per-query ordering: (query index inside the slab, position)
-                k = 0;
-                active = true;
+    uint32_t k = 0;
+    if (ix.bm != nullptr) {                                    // fused walk blocks: BWT byte + mark bit in one fetch per step
+        for (;;) {
+            uint32_t c, marked;
+            walk_block<G>(ix.bm, r, c, marked);
+            if (marked) {
+                const uint32_t mr = rank_one<G>(ix.mark, r, nullptr);
+                FMX_EMIT(ix.samples[mr] + k);
+                if ((threadIdx.x % G) == 0 && steps_out) atomicAdd(steps_out, (unsigned long long)k);
+                return;
             }
-            next += ((long long)__popc(need) < avail) ? (long long)__popc(need) : avail;
-        }
-        if (G > 1) {
-            active = __shfl_sync(0xFFFFFFFFu, (int)active, lead_lane) != 0;
-            r = __shfl_sync(0xFFFFFFFFu, r, lead_lane);
-        }
-        if (!__any_sync(0xFFFFFFFFu, active || pending)) break;
-        // ---- A
-        uint32_t sval = 0, c = 0, marked = 0;
-        if (pending && leader) sval = ldg32(ix.samples + pmr);
-        if (active) walk_block<G>(ix.bm, r, c, marked);
-        if (pending) {
-            if (leader) { FMX_EMIT_AT(pt, pseg, sval + pk); my_steps += pk; }
-            pending = false;
-        }
-        // ---- B
-        if (active) {
-            uint32_t x;
-            if (LAYOUT == FMX_LAYOUT_PLANES) {                 // one rank fetch for every group: mark bitvector or the byte's plane (same block format)
-                const uint4 *bv = marked ? ix.mark : ix.blocks + (uint64_t)tb.code[c] * ix.stride * 4;
-                x = rank_one<G>(bv, r, nullptr);
-                if (!marked) x += tb.base[c];
-            } else {
-                x = marked ? rank_one<G>(ix.mark, r, nullptr) : lf_value<G, LAYOUT>(ix, tb, c, r);
-            }
-            if (marked) {                                      // row eof (sa = 0) is always sampled, so '$' is never stepped over
-                pmr = x; pk = k; pt = t; pseg = seg;
-                pending = true;
-                active = false;
-            } else {
-                r = x;
-                if (++k > ix.n) { if (leader) FMX_EMIT_AT(t, seg, 0xFFFFFFFFu); active = false; }      // cannot happen on a consistent index
-            }
+            r = lf_value<G, LAYOUT>(ix, tb, c, r);
+            if (++k > ix.n) { FMX_EMIT(0xFFFFFFFFu); return; }      // cannot happen on a consistent index (fmx_open checks)
         }
     }
-#undef FMX_EMIT_AT
-    if (steps_out && my_steps) atomicAdd(steps_out, my_steps);
+    for (;;) {
+        uint32_t bit;
+        const uint32_t mr = rank_one<G>(ix.mark, r, &bit);
+        if (bit) {                                         // row eof (sa = 0) is always sampled, so '$' is never stepped over
+            FMX_EMIT(ix.samples[mr] + k);
+            if ((threadIdx.x % G) == 0 && steps_out) atomicAdd(steps_out, (unsigned long long)k);
+            return;
+        }
+        r = lf_value<G, LAYOUT>(ix, tb, ix.bwt[r], r);
+        if (++k > ix.n) { FMX_EMIT(0xFFFFFFFFu); return; }
+    }
+#undef FMX_EMIT
 }
 
 // low words of the sorted (query, position) keys: the positions, ascending inside each query — as uint32 (device callers) or widened
@@ -618,9 +563,7 @@ cudaError_t launch_next_substr(const DevIndex &ix, LaunchCfg cfg, const int64_t 
 cudaError_t launch_locate(const DevIndex &ix, LaunchCfg cfg, const uint32_t *d_sp, const int64_t *d_off, int64_t q0, int64_t q1,
                           int64_t t0, int64_t count, uint32_t *d_pos, uint64_t *d_key, unsigned long long *d_steps, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    const int64_t warps = (count + kLocateChunk - 1) / kLocateChunk;
-    const unsigned grid = (unsigned)((warps + kThreads / 32 - 1) / (kThreads / 32));
-#define CALL(G, LAY) locate_kernel<G, LAY><<<grid, kThreads, 0, st>>>(ix, d_sp, (const long long *)d_off, q0, q1, t0, count, d_pos, (unsigned long long *)d_key, d_steps)
+#define CALL(G, LAY) locate_kernel<G, LAY><<<grid_for(count, G), kThreads, 0, st>>>(ix, d_sp, (const long long *)d_off, q0, q1, t0, count, d_pos, (unsigned long long *)d_key, d_steps)
     FMX_DISPATCH(cfg, CALL);
 #undef CALL
     return cudaGetLastError();

@@ -1067,24 +1067,31 @@ def test_empty_batches_and_argument_errors(ref_dir):
 
 
 def test_regex_set_is_reusable(ref_dir, o1024, words_base, words):
-    """compile once, search many times: one device-resident regex set searched repeatedly and against two different indexes"""
+    """compile once, search many times: one device-resident regex set searched repeatedly and against two different indexes.  The set's
+    follow lists are pruned by the alphabet of the index it was created for, so it serves any index whose symbols all occur there
+    (test1024's a-z inside words' alphabet) and refuses one with other symbols."""
     g = _open(os.path.join(ref_dir, "test1024.cmp.bwt"), (fx.LAYOUT_PLANES, 2))
+    w = _open(words_base + ".bwt", (fx.LAYOUT_WM, 2), big_endian=True)
     rxs = ["a(a|b|d|e)c", "ab", "q[a-z]q", "a.b", "x\\wy", "zz?z?", "a+b"]
     trees = [fx.ReTree(r) for r in rxs[:5]] + [fx.ThompsonNFA(r) for r in rxs[5:]]
-    rs = g.regex_set(trees)
+    rs = w.regex_set(trees)
     for _ in range(3):
         off, ln, sp, ep = rs.search(g, cap_total=4)                          # also exercises the capacity retry
         for i, rx in enumerate(rxs):
             got = list(zip(ln[off[i]:off[i + 1]].tolist(), sp[off[i]:off[i + 1]].tolist(), ep[off[i]:off[i + 1]].tolist()))
             want = o1024.regex_match(rx) if i < 5 else o1024.regex_match_thompson(rx)
             assert got == want, rx
-    w = _open(words_base + ".bwt", (fx.LAYOUT_WM, 2), big_endian=True)
     off, ln, sp, ep = rs.search(w)
     o, _ = words
     for i, rx in enumerate(rxs):
         got = list(zip(ln[off[i]:off[i + 1]].tolist(), sp[off[i]:off[i + 1]].tolist(), ep[off[i]:off[i + 1]].tolist()))
         assert got == (o.regex_match(rx) if i < 5 else o.regex_match_thompson(rx)), rx
     rs.close()
+    narrow = g.regex_set(trees)                                              # pruned for a-z: words' '\r', '\n' are not covered
+    with pytest.raises(fx.FmxError, match="create the set against this index") as ei:
+        narrow.search(w)
+    assert ei.value.code == fx.FMX_E_ARG
+    narrow.close()
     w.close()
     g.close()
 
