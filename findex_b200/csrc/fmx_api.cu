@@ -1507,9 +1507,11 @@ int regex_search_core(fmx_index *ix, CallCtx &cc, fmx_regex_set *set, RegexResul
     int64_t launches = 0;
     unsigned long long h[8] = {0};
     for (;;) {
+        if (debug_sync()) { cudaError_t de = cudaDeviceSynchronize(); if (de != cudaSuccess) return fail(FMX_E_CUDA, "an earlier asynchronous error surfaced before the regex traversal: %s", cudaGetErrorString(de)); }
         CU(launch_regex_search(cc.d, cc.cfg, rt, (const uint32_t *)set->d_first, n_first, (FrontierItem *)set->d_ring, (uint32_t *)set->d_seq, set->ring_cap, d_res, cap_res,
                                (unsigned long long *)set->d_ctrl, set->max_len, st));
         launches += 2;
+        if (debug_sync()) { cudaError_t de = cudaStreamSynchronize(st); if (de != cudaSuccess) return fail(FMX_E_CUDA, "regex traversal kernels failed: %s (ring %lld slots, %lld start items, device %d)", cudaGetErrorString(de), (long long)set->ring_cap, (long long)n_first, ix->device); }
         CU(cudaMemcpyAsync(h, set->d_ctrl, 64, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (h[kRxStatus] == 0) break;
