@@ -532,14 +532,19 @@ class FusedExchange:
         assert int(lo_) == int(hi_), "ranks disagree on the gathered counts"
 
     def close(self):
-        cx = self.cx
-        cx.torch.cuda.synchronize()
-        cx.dist.barrier()
+        """keeps the mappings until the end of the run (sharded.close_retired): closing the last IPC mapping of a peer takes the lazily
+        enabled peer access down with it, under NCCL's feet"""
+        from findex_b200 import sharded
+        self.cx.torch.cuda.synchronize()
+        sharded._RETIRED.append(self)
+
+    def close_peers(self):
         for gb in self.gath:
             for ptr in list(gb.peers.values()):
-                cx.fx.lib().fmx_ipc_close(ptr)
+                self.cx.fx.lib().fmx_ipc_close(ptr)
             gb.peers = {}
-        cx.dist.barrier()
+
+    def really_close(self):
         for gb in self.gath:
             gb.close()
 
@@ -900,9 +905,7 @@ def locate_leg(cx, g, text, n, m_total, ln, orc, steps, chunk_q=4000):
                                          "frac": req_occ * stat_occ / (max(walk_ms, 1e-9) * 1e-3) / (r_rand_gbs * 1e9 / 64)},
                         "survey_units": {"bytes_per_occurrence": 15.5 * L * 64 + 32, "note": "SURVEY 8(d): (rate-1)/2 LF steps x L x 64 B + one 32-B sample"}}}
     if ex is not None:
-        ex.close_peers()
-        cx.barrier()
-        ex.close()
+        ex.retire()
     return out
 
 
@@ -1013,9 +1016,7 @@ def regex_leg(cx, g, text, n_regexes, orc, steps):
                                "sample": "%d regexes of the batch (ReTree._matchSA, caps off, automata precompiled), %d threads, %.2f s" % (len(sample), cores, dtr),
                                "parity_on_sample": bool(ok)}
     if ex is not None:
-        ex.close_peers()
-        cx.barrier()
-        ex.close()
+        ex.retire()
     rset.close()
     for a in (ln_, sp_, ep_):
         a.free()
@@ -1253,6 +1254,10 @@ def main():
         out = run_default(cx) if args.workload == "cfg2" else run_workload(cx)
         if rank == 0:
             print(json.dumps(out), file=OUT, flush=True)
+        if world > 1:                                        # exchange buffers live as long as the process group: unmap, barrier, free
+            from findex_b200 import sharded
+            torch.cuda.synchronize()
+            sharded.close_retired(cx.barrier)
     finally:
         if world > 1:
             import torch.distributed as dist

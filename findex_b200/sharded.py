@@ -249,3 +249,24 @@ class GpuExchange:
         self.close_peers()
         self.counts.close()
         self.values.close()
+
+    def retire(self):
+        """Done with this exchange, but keep its mappings until the process group goes away (close_retired).  Closing the last CUDA-IPC
+        mapping of a peer tears down the lazily enabled peer access between the two devices, which NCCL in the same process still
+        relies on: a later collective then dies with cudaErrorInvalidAddressSpace (seen on 2 x B200 when an exchange was closed between
+        two legs of a run).  Exchanges therefore live as long as the process group."""
+        _RETIRED.append(self)
+
+
+_RETIRED = []
+
+
+def close_retired(barrier=None):
+    """at the very end of a run: every rank unmaps its peers' buffers, a barrier, then everybody frees its own"""
+    for ex in _RETIRED:
+        ex.close_peers()
+    if barrier is not None:
+        barrier()
+    for ex in list(_RETIRED):
+        (getattr(ex, "really_close", None) or ex.close)()
+    del _RETIRED[:]
