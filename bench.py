@@ -332,11 +332,16 @@ class Ctx:
         self.torch.cuda.empty_cache()                      # the suffix sort of a 4 GB text needs most of the device
         text = make_text(n, workload)
         base = index_base(n, workload)
+        err = None
         if self.rank == 0 and not (os.path.exists(base + ".bwt") and os.path.exists(base + ".aux")):
             tb = time.time()
-            self.fx.build_index_files(text, base, bigEndian=True)
-            log("%s: index files built on the GPU in %.1f s" % (workload, time.time() - tb))
-        self.barrier()
+            try:
+                self.fx.build_index_files(text, base, bigEndian=True)
+                log("%s: index files built on the GPU in %.1f s" % (workload, time.time() - tb))
+            except Exception as e:                           # noqa: BLE001 — every rank must leave this function the same way
+                err = e
+        if self.max_over_ranks(1.0 if err is not None else 0.0) > 0:
+            raise err if err is not None else RuntimeError("rank 0 could not build the %s index files" % workload)
         log("rank %d: %s text + index files ready after %.1f s" % (self.rank, workload, time.time() - t0))
         return text, base
 
@@ -977,7 +982,10 @@ def regex_leg(cx, g, text, n_regexes, orc, steps):
         goff = ex.offsets().cpu().numpy()
         lo_w, hi_w = int(goff[cx.rank * mr]), int(goff[(cx.rank + 1) * mr])
         rec = ex.gathered_values(4 * int(goff[-1])).reshape(-1, 4)[lo_w:hi_w].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
-        assert hi_w - lo_w == total and np.array_equal(rec[:, 0], np.repeat(np.arange(cx.rank * mr, (cx.rank + 1) * mr), np.diff(off)))
+        want_ids = np.repeat(np.arange(cx.rank * mr, (cx.rank + 1) * mr), np.diff(off))
+        assert hi_w - lo_w == total, "gathered offsets give this rank %d records, it produced %d (all ranks: %d)" % (hi_w - lo_w, total, int(goff[-1]))
+        assert np.array_equal(rec[:, 0], want_ids), "regex ids of the gathered records differ at %d of %d places (first: got %s want %s)" % (
+            int((rec[:, 0] != want_ids).sum()), total, rec[:, 0][rec[:, 0] != want_ids][:4].tolist(), want_ids[rec[:, 0] != want_ids][:4].tolist())
     else:
         rec = d_res[:total].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
     assert np.array_equal(rec[:, 1], ln_.array[:total]) and np.array_equal(rec[:, 2], sp_.array[:total]) and np.array_equal(rec[:, 3], ep_.array[:total])

@@ -790,8 +790,12 @@ int fmx_count_fixed_dev_gather(fmx_index *ix, const void *d_pat, int32_t len, in
 // ---- raw device buffers that can be shared between the ranks of one node (CUDA IPC) -----------------------------------
 int fmx_dev_alloc(void **p, int64_t bytes) {
     if (!p || bytes < 0) return fail(FMX_E_ARG, "bad argument");
-    CU(cudaMalloc(p, (size_t)(bytes ? bytes : 1)));
-    CU(cudaMemset(*p, 0, (size_t)(bytes ? bytes : 1)));
+    // Sizes are rounded up to 2 MiB: cudaMalloc packs smaller requests into shared 2 MiB blocks, and CUDA IPC shares (and maps) the
+    // whole underlying block — a peer that opened the handle of the second buffer of a block got the block's base, i.e. the first
+    // buffer (seen on 2 x B200: one exchange's counts landing in an earlier exchange's buffer).
+    const size_t gran = 2u << 20, sz = ((size_t)(bytes ? bytes : 1) + gran - 1) / gran * gran;
+    CU(cudaMalloc(p, sz));
+    CU(cudaMemset(*p, 0, sz));
     return FMX_OK;
 }
 int fmx_dev_free(void *p) { if (p) CU(cudaFree(p)); return FMX_OK; }

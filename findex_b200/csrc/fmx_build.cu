@@ -645,7 +645,8 @@ cudaError_t suffix_sort_bwt(const uint8_t *d_t, int64_t len, uint8_t *d_bwt, int
     uint64_t *k0, *k1; uint32_t *s0, *s1, *rank, *grp; unsigned long long *d_flag, *d_counts;
     CK(cudaMallocAsync(&k0, n * 8, st)); CK(cudaMallocAsync(&k1, n * 8, st));
     CK(cudaMallocAsync(&s0, n * 4, st)); CK(cudaMallocAsync(&s1, n * 4, st));
-    CK(cudaMallocAsync(&rank, n * 4, st)); CK(cudaMallocAsync(&grp, n * 4, st));
+    CK(cudaMallocAsync(&rank, n * 4, st));
+    grp = reinterpret_cast<uint32_t *>(k0);                  // the group heads live in k0, which is dead between a sort and the next doubled_keys (28 bytes per text byte in all)
     CK(cudaMallocAsync(&d_flag, 16, st)); CK(cudaMallocAsync(&d_counts, 256 * 8, st));
     const unsigned grid = (unsigned)((n + 255) / 256);
     init_keys_kernel<<<grid, 256, 0, st>>>(d_t, len, k0, s0);
@@ -679,7 +680,7 @@ cudaError_t suffix_sort_bwt(const uint8_t *d_t, int64_t len, uint8_t *d_bwt, int
     for (int i = 0; i < 256; ++i) counts_out[i] = (int64_t)cnt[i];
     if (rounds_out) *rounds_out = rounds;
     cudaFreeAsync(k0, st); cudaFreeAsync(k1, st); cudaFreeAsync(s0, st); cudaFreeAsync(s1, st);
-    cudaFreeAsync(rank, st); cudaFreeAsync(grp, st); cudaFreeAsync(d_flag, st); cudaFreeAsync(d_counts, st);
+    cudaFreeAsync(rank, st); cudaFreeAsync(d_flag, st); cudaFreeAsync(d_counts, st);
     return cudaGetLastError();
 }
 

@@ -142,7 +142,9 @@ int fmx_count_fixed_dev(fmx_index *ix, const void *d_pat, int32_t len, int64_t m
  * kernel s-2, so that barrier's completion proves they are done.  Two sets with only the same-set barrier are not enough.        */
 int fmx_count_fixed_dev_gather(fmx_index *ix, const void *d_pat, int32_t len, int64_t m, void *d_sp_u32, void *d_ep_u32,
                                void *const *sinks, int32_t n_sinks, int64_t offset, void *stream);
-/* cudaMalloc'ed, zeroed buffers that the ranks of one node can map into each other (cudaIpc*).               */
+/* cudaMalloc'ed, zeroed buffers that the ranks of one node can map into each other (cudaIpc*); sizes are rounded up to 2 MiB so that
+ * no two buffers share an underlying block (CUDA IPC maps whole blocks).  Keep the mappings open for the life of the process group:
+ * closing the last mapping of a peer takes the lazily enabled peer access down with it, which NCCL in the same process relies on.  */
 int fmx_dev_alloc(void **p, int64_t bytes);
 int fmx_dev_free(void *p);
 int fmx_ipc_export(void *p, uint8_t handle[64]);
