@@ -948,9 +948,12 @@ def regex_leg(cx, g, text, n_regexes, orc, steps):
         # N > 1: the records of every rank's shard are exchanged on the device (sharded.GpuExchange): per-regex counts and the
         # {regex, len, sp, ep} slabs go by kernel stores into every rank's gathered buffers, 2 x 4-byte NCCL barrier
         from findex_b200 import sharded
+        torch.cuda.synchronize()                           # d_res/d_off fills are on torch's stream, the search on the library's
         first = rset.search_dev(g, d_res.data_ptr(), cap, d_off.data_ptr())
         all_res = int(cx.sum_over_ranks(first))
         ex = sharded.GpuExchange(g, cx.rank, cx.world, cx.world * mr, 4 * all_res + 64, cx.dev)
+
+    torch.cuda.synchronize()
 
     def dev_step():
         if ex is not None:

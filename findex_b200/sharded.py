@@ -215,8 +215,14 @@ class GpuExchange:
     def regex_count(self, rset, lo, hi, scratch_cap):
         m = hi - lo
         st = torch.cuda.current_stream().cuda_stream
-        self._res = torch.empty((max(scratch_cap, 1), 4), dtype=torch.int32, device=self.device)
-        d_off = torch.zeros(m + 1, dtype=torch.int64, device=self.device)
+        if getattr(self, "_res", None) is None or self._res.shape[0] < max(scratch_cap, 1):
+            self._res = torch.empty((max(scratch_cap, 1), 4), dtype=torch.int32, device=self.device)
+        if getattr(self, "_doff", None) is None or self._doff.numel() != m + 1:
+            self._doff = torch.zeros(m + 1, dtype=torch.int64, device=self.device)
+        d_off = self._doff
+        # the library searches on a private stream of its own and returns when the results are in place: everything this stream still
+        # has in flight on the scratch buffers (the previous step's peer stores read _res; the fill of a fresh d_off) must be over first
+        torch.cuda.current_stream().synchronize()
         self._total = rset.search_dev(self.g, self._res.data_ptr(), scratch_cap, d_off.data_ptr())
         self._cnt = (d_off[1:] - d_off[:-1]).to(torch.int32).contiguous()
         self._res[:self._total, 0] += lo                     # batch-wide regex ids

@@ -247,7 +247,9 @@ int  fmx_regex_set_create(fmx_index *ix, fmx_regex *const *rx, int64_t m, fmx_re
 int  fmx_regex_set_search(fmx_index *ix, fmx_regex_set *set, int64_t cap_total, int64_t *out_off, int32_t *len, int64_t *sp, int64_t *ep);
 /* Device-resident form: the results stay on the index's device as {regex, len, sp, ep} records (4 x uint32) ordered by (regex, len, sp, ep)
  * in d_res[cap]; d_off (int64[m+1], may be NULL) receives the index of every regex's first result; *total_out the number of results
- * (FMX_E_CAPACITY when it exceeds cap).  What a multi-GPU caller exchanges, and what fmx_regex_set_search copies out.        */
+ * (FMX_E_CAPACITY when it exceeds cap).  What a multi-GPU caller exchanges, and what fmx_regex_set_search copies out.
+ * Stream contract: the search runs on a stream of the library and the call returns when d_res/d_off are complete; it does NOT order
+ * itself after work the caller still has in flight on d_res/d_off (a fill, a previous step's readers) — synchronise that first.   */
 int  fmx_regex_set_search_dev(fmx_index *ix, fmx_regex_set *set, void *d_res, int64_t cap, void *d_off_i64, int64_t *total_out);
 /* Length cap of later searches of the set: max_len = the maxLength argument of REParser.matchSA (M/re2/re2.scala:568, applied at :636-641) —
  * an item's follow positions are enqueued only while their len stays below max_len, matches are emitted whatever their length; 0 = off.

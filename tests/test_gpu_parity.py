@@ -453,6 +453,7 @@ def test_regex_device_resident_results(ref_dir, o1024):
         cap = int(off[-1]) + 5
         d_res = torch.zeros((cap, 4), dtype=torch.int32, device="cuda")
         d_off = torch.zeros(len(rxs) + 1, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()                       # stream contract of fmx_regex_set_search_dev (fmgpu.h)
         total = rset.search_dev(g, d_res.data_ptr(), cap, d_off.data_ptr())
         torch.cuda.synchronize()
         assert total == off[-1] and np.array_equal(d_off.cpu().numpy(), off)
