@@ -37,7 +37,7 @@ struct fmx_index {
     int64_t C[257] = {0};
     int64_t counts0[256] = {0};        // raw counts (bucketStarts0 / pos2char)
     int sigma = 0, levels = 0, sample_rate = 0;
-    int64_t nblk = 0, index_bytes = 0, n_samples = 0, rank_units64 = 0;
+    int64_t nblk = 0, index_bytes = 0, n_samples = 0, rank_units64 = 0, dict_entries = 0;
     int api_layout = FMX_LAYOUT_WM;    // what fmx_info reports
     std::vector<void *> owned;         // device allocations freed at close
     std::atomic<double> last_ms{0.0}, locate_walk_ms{0.0}, locate_sort_ms{0.0};      // diagnostics of the most recent call
@@ -282,6 +282,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     d.blocks = (const uint4 *)blocks; d.stride = (uint64_t)nblk; d.bwt = d_bwt; d.C = d_C; d.base = d_base; d.code = d_code;
     d.bm = nullptr;
     d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isat = nullptr; d.isat_bits = 8; d.isat_syms = 12; d.ctx = nullptr; d.ctx_J = 0; d.ctx_raw = 0; d.ctx_plan = nullptr; d.ctx8 = nullptr; d.ctx8_J = 0;
+    d.dict = nullptr; d.dict_buckets = 0; d.dict_D = 0; d.dict_bits = 0;
     for (int t = 0; t < 8; ++t) d.ctx_S[t] = 0;
     d.mark = nullptr; d.samples = nullptr; d.n = (uint32_t)n; d.eof = (uint32_t)eof; d.layout = layout; d.levels = levels;
     for (int l = 0; l < 8; ++l) d.z[l] = z[l];
@@ -338,7 +339,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     const bool want_isat = n > 2 && ((accel & FMX_ACCEL_TEXT) || (is_auto && !want_ctx && !want_ctx8 && 25 * n + (2ll << 30) < (int64_t)fr &&
                                                                  ix->index_bytes + 20 * n <= budget + (24ll << 30) && 20 * n <= room() / 2));
     const bool build_sa = want_isat || want_ctx || want_ctx8;
-    const bool want_kmer = (accel & FMX_ACCEL_KMER) || is_auto;
+    const bool want_kmer = (accel & (FMX_ACCEL_KMER | FMX_ACCEL_DICT)) || is_auto;
     if (build_sa) {
         // isa and the text are scratch that is folded into the isat / context entries; sa stays when it is wanted for locate
         SaBuf sa;                                                 // plain cudaMalloc: it may become a resident part of the index
@@ -434,6 +435,33 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
             d.kmer = (const uint2 *)tab; d.kmer_k = K; d.kmer_sigma = (uint32_t)sigma;
             ix->index_bytes += entries * 8;
         }
+    }
+    // dictionary of wide intervals on top of the dense table: only texts whose k-mers stay frequent beyond the table's depth (natural
+    // language, repeats) have any; the level-wise construction finds out
+    const bool want_dict = d.kmer != nullptr && sigma >= 2 && accel != FMX_ACCEL_NONE && ((accel & FMX_ACCEL_DICT) || is_auto);
+    if (want_dict) {
+        int dbits = 1;
+        while ((1 << dbits) < sigma) ++dbits;
+        const int Dmax = std::min(16, 60 / dbits);
+        size_t fr3 = 0, to3 = 0;
+        cudaMemGetInfo(&fr3, &to3);
+        int64_t dict_budget = o.dict_bytes > 0 ? o.dict_bytes : std::min<int64_t>(8ll << 30, (int64_t)(fr3 / 8));
+        dict_budget = std::min<int64_t>(dict_budget, room());
+        const uint32_t min_rows = o.dict_min_rows > 0 ? (uint32_t)o.dict_min_rows : kCtxMaxRows;
+        if (Dmax > d.kmer_k && dict_budget >= 4096) {
+            void *table = nullptr;
+            int64_t buckets = 0, entries = 0;
+            int depth = 0;
+            e = build_dict(d, ix->cfg, d_sym, (uint32_t)sigma, dbits, Dmax, min_rows, dict_budget / 32, &table, &buckets, &depth, &entries, ix->stream);
+            if (e != cudaSuccess) { cudaGetLastError(); if (accel & FMX_ACCEL_DICT) return fail(FMX_E_CUDA, "dictionary construction failed: %s", cudaGetErrorString(e)); }
+            else if (table) {
+                ix->owned.push_back(table);
+                d.dict = (const uint4 *)table; d.dict_buckets = (uint64_t)buckets; d.dict_D = depth; d.dict_bits = dbits;
+                ix->dict_entries = entries;
+                ix->index_bytes += buckets * 32;
+            }
+        }
+        trim_pool(ix->device);
     }
     // two lanes per query: with the 256-bit load a 64-B rank block is one request from two lanes (as from four lanes with 128-bit
     // loads), and twice as many queries are in flight per SM
@@ -587,6 +615,13 @@ int fmx_accel_info(const fmx_index *ix, int32_t *kmer_k, int32_t *text_shortcut)
     if (text_shortcut) *text_shortcut = ix->accel_text ? 1 : 0;
     return FMX_OK;
 }
+int fmx_dict_info(const fmx_index *ix, int32_t *depth, int64_t *entries, int64_t *bytes) {
+    if (!ix) return fail(FMX_E_ARG, "null index");
+    if (depth) *depth = ix->d.dict ? ix->d.dict_D : 0;
+    if (entries) *entries = ix->d.dict ? ix->dict_entries : 0;
+    if (bytes) *bytes = ix->d.dict ? (int64_t)ix->d.dict_buckets * 32 : 0;
+    return FMX_OK;
+}
 int fmx_ctx_depth(const fmx_index *ix) { return !ix ? 0 : ix->d.ctx ? ix->d.ctx_J : ix->d.ctx8 ? ix->d.ctx8_J : 0; }
 int fmx_ctx_entry_bytes(const fmx_index *ix) { return !ix ? 0 : ix->d.ctx ? 32 : ix->d.ctx8 ? 8 : 0; }
 int fmx_info(const fmx_index *ix, int32_t *layout, int32_t *levels, int32_t *sigma, int64_t *index_bytes, int32_t *rate) {
@@ -617,6 +652,7 @@ int fmx_set_accel_mask(fmx_index *ix, int32_t mask) {
         if ((mask & FMX_ACCEL_NONE) || !(mask & FMX_ACCEL_TEXT)) d.isat = nullptr;
         if ((mask & FMX_ACCEL_NONE) || !(mask & FMX_ACCEL_CTX)) d.ctx = nullptr;
         if ((mask & FMX_ACCEL_NONE) || !(mask & FMX_ACCEL_CTX8)) d.ctx8 = nullptr;
+        if ((mask & FMX_ACCEL_NONE) || !(mask & FMX_ACCEL_DICT) || !d.kmer) d.dict = nullptr;
     }
     ix->d = d;
     ix->cfg.count_lanes = (d.kmer && (d.ctx || d.ctx8)) ? ix->count_lanes_full : 0;

@@ -565,6 +565,125 @@ cudaError_t build_kmer_table(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d
     return cudaGetLastError();
 }
 
+// Dictionary of wide intervals (DevIndex::dict): grown level by level from the dense k-mer table.  Level K = the table's entries of more
+// than `min_rows` rows; level d+1 = one backward step from every level-d item with every symbol, kept when still wider than `min_rows`
+// (a child of a narrow interval is narrow, so nothing is missed).  Items are appended to one array; the levels that fit `max_entries` are
+// then hashed into 32-byte buckets (two {key, sp, ep} slots) at half load.
+struct DictItem { unsigned long long key; uint32_t sp, ep; };
+
+__global__ void dict_seed_kernel(const uint2 *__restrict__ kmer, unsigned long long entries, uint32_t sigma, int K, uint32_t bits, uint32_t min_rows,
+                                 DictItem *__restrict__ out, unsigned long long cap, unsigned long long *__restrict__ counter) {
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= entries) return;
+    const uint2 v = kmer[idx];
+    if (v.y - v.x <= min_rows || v.y <= v.x) return;
+    // digit 0 of idx (most significant) is the first consumed symbol = the key's lowest field
+    unsigned long long key = 0, r = idx;
+    for (int j = K - 1; j >= 0; --j) { key |= (r % sigma) << (bits * (uint32_t)j); r /= sigma; }
+    const unsigned long long slot = atomicAdd(counter, 1ull);
+    if (slot < cap) out[slot] = DictItem{key | ((unsigned long long)(K - 1) << 60), v.x, v.y};
+}
+
+template <int G, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+dict_extend_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ sym, uint32_t sigma, const DictItem *__restrict__ parents,
+                   unsigned long long count, int d, uint32_t bits, uint32_t min_rows, DictItem *__restrict__ out, unsigned long long cap,
+                   unsigned long long *__restrict__ counter) {
+    __shared__ SharedTables tb;
+    load_tables(tb, ix);
+    __syncthreads();
+    const unsigned long long t = (unsigned long long)blockIdx.x * (kThreads / G) + threadIdx.x / G;
+    if (t >= count * sigma) return;                        // group-uniform
+    const DictItem p = parents[t / sigma];
+    const uint32_t code = (uint32_t)(t % sigma);
+    uint32_t sp = p.sp, ep = p.ep, touched = 0;
+    backward_step<G, LAYOUT, false>(ix, tb, (uint32_t)sym[code], sp, ep, touched);
+    if ((threadIdx.x % G) == 0 && sp < ep && ep - sp > min_rows) {
+        const unsigned long long slot = atomicAdd(counter, 1ull);
+        const unsigned long long key = (p.key & ((1ull << 60) - 1ull)) | ((unsigned long long)code << (bits * (uint32_t)(d - 1))) | ((unsigned long long)(d - 1) << 60);
+        if (slot < cap) out[slot] = DictItem{key, sp, ep};
+    }
+}
+
+__global__ void dict_insert_kernel(const DictItem *__restrict__ items, unsigned long long count, unsigned long long *__restrict__ table,
+                                   unsigned long long buckets, unsigned long long *__restrict__ failed) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const DictItem it = items[t];
+    unsigned long long b = __umul64hi(dict_mix(it.key), buckets);
+    for (unsigned long long tries = 0; tries < buckets; ++tries) {
+        for (int s = 0; s < 2; ++s) {
+            unsigned long long *slot = table + (b * 2 + (unsigned long long)s) * 2;      // 16-byte slots: key, then sp | ep << 32
+            if (atomicCAS(slot, 0ull, it.key) == 0ull) { slot[1] = (unsigned long long)it.sp | ((unsigned long long)it.ep << 32); return; }
+        }
+        if (++b == buckets) b = 0;
+    }
+    atomicAdd(failed, 1ull);
+}
+
+cudaError_t build_dict(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, uint32_t sigma, int bits, int Dmax, uint32_t min_rows,
+                       int64_t max_entries, void **d_table_out, int64_t *buckets_out, int *depth_out, int64_t *entries_out, cudaStream_t st) {
+    *d_table_out = nullptr; *buckets_out = 0; *depth_out = 0; *entries_out = 0;
+    const int K = ix.kmer_k;
+    if (!ix.kmer || K < 1 || sigma < 2 || Dmax <= K || max_entries < 1) return cudaSuccess;
+    unsigned long long table_entries = 1;
+    for (int j = 0; j < K; ++j) table_entries *= sigma;
+    unsigned long long *d_cnt = nullptr, h_cnt = 0;
+    CK(cudaMallocAsync(&d_cnt, 16, st));
+    CK(cudaMemsetAsync(d_cnt, 0, 16, st));
+    // the seeds: wide entries of the dense table (disjoint intervals, so at most n / (min_rows + 1)); counted first — a text without any
+    // (uniform symbols under a deep table) gets no dictionary and costs no scratch
+    if ((table_entries + 255) / 256 > 0x7FFFFFFFull) { cudaFreeAsync(d_cnt, st); return cudaSuccess; }
+    dict_seed_kernel<<<(unsigned)((table_entries + 255) / 256), 256, 0, st>>>(ix.kmer, table_entries, sigma, K, (uint32_t)bits, min_rows, nullptr, 0, d_cnt);
+    CK(cudaMemcpyAsync(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const unsigned long long seeds = h_cnt;
+    if (seeds == 0) { cudaFreeAsync(d_cnt, st); return cudaSuccess; }
+    const unsigned long long cap = seeds + (unsigned long long)max_entries;
+    DictItem *items = nullptr;
+    CK(cudaMallocAsync(&items, cap * sizeof(DictItem), st));
+    CK(cudaMemsetAsync(d_cnt, 0, 16, st));
+    dict_seed_kernel<<<(unsigned)((table_entries + 255) / 256), 256, 0, st>>>(ix.kmer, table_entries, sigma, K, (uint32_t)bits, min_rows, items, cap, d_cnt);
+    unsigned long long lvl_begin = 0, lvl_count = seeds, total = seeds;
+    int D = K;
+    const int G = (cfg.lanes == 1 || cfg.lanes == 2 || cfg.lanes == 4) ? cfg.lanes : 2;
+    for (int d = K + 1; d <= Dmax && lvl_count > 0; ++d) {
+        const unsigned long long groups = lvl_count * sigma, per = kThreads / G;
+        if ((groups + per - 1) / per > 0x7FFFFFFFull) break;
+        const unsigned grid = (unsigned)((groups + per - 1) / per);
+#define CALL(GG, LAY) dict_extend_kernel<GG, LAY><<<grid, kThreads, 0, st>>>(ix, d_sym, sigma, items + lvl_begin, lvl_count, d, (uint32_t)bits, min_rows, items, cap, d_cnt)
+        if (ix.layout == FMX_LAYOUT_PLANES) { if (G == 1) CALL(1, FMX_LAYOUT_PLANES); else if (G == 2) CALL(2, FMX_LAYOUT_PLANES); else CALL(4, FMX_LAYOUT_PLANES); }
+        else if (ix.layout == FMX_LAYOUT_WMX) { if (G == 1) CALL(1, FMX_LAYOUT_WMX); else if (G == 2) CALL(2, FMX_LAYOUT_WMX); else CALL(4, FMX_LAYOUT_WMX); }
+        else { if (G == 1) CALL(1, FMX_LAYOUT_WM); else if (G == 2) CALL(2, FMX_LAYOUT_WM); else CALL(4, FMX_LAYOUT_WM); }
+#undef CALL
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_cnt > cap || h_cnt - seeds > (unsigned long long)max_entries) break;      // this level does not fit: the dictionary ends one level up
+        lvl_begin = total;
+        lvl_count = h_cnt - total;
+        total = h_cnt;
+        if (lvl_count > 0) D = d;
+    }
+    const unsigned long long entries = total - seeds;
+    if (entries > 0 && D > K) {
+        unsigned long long buckets = (entries + 3ull) & ~3ull;                          // two slots per bucket: half load
+        if (buckets < 4) buckets = 4;
+        void *table = nullptr;
+        cudaError_t e = cudaMalloc(&table, buckets * 32);
+        if (e != cudaSuccess) { cudaFreeAsync(items, st); cudaFreeAsync(d_cnt, st); return e; }
+        CK(cudaMemsetAsync(table, 0, buckets * 32, st));
+        CK(cudaMemsetAsync(d_cnt, 0, 16, st));
+        dict_insert_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, st>>>(items + seeds, entries, (unsigned long long *)table, buckets, d_cnt);
+        CK(cudaMemcpyAsync(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_cnt != 0) { cudaFree(table); cudaFreeAsync(items, st); cudaFreeAsync(d_cnt, st); return cudaErrorUnknown; }
+        *d_table_out = table; *buckets_out = (int64_t)buckets; *depth_out = D; *entries_out = (int64_t)entries;
+    }
+    cudaFreeAsync(items, st); cudaFreeAsync(d_cnt, st);
+    return cudaGetLastError();
+}
+
 // ======================================================================================================
 // (c) suffix sorting by prefix doubling -> BWT
 // ======================================================================================================

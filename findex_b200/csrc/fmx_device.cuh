@@ -65,6 +65,14 @@ struct DevIndex {
     // at least J bytes remain; rows with fewer than J text positions before them hold row 0xFFFFFFFF
     const uint2    *ctx8;
     int32_t         ctx8_J;
+    // dictionary of WIDE intervals (FMX_ACCEL_DICT): for every depth d in kmer_k+1 .. dict_D, every d-mer whose interval holds more than
+    // dict_min_rows rows — the intervals rank steps are slowest on (sp and ep in different blocks) and row contexts cannot help.  A hash
+    // table of 32-byte buckets = 2 entries { key: 64 bits, sp, ep }; key = the d dense codes (dict_bits each, first consumed symbol lowest)
+    // | (d-1) << 60; 0 = empty slot.  Linear probing over buckets, built at <= half load.  A prefix of a wide d-mer is wide, so the deepest
+    // stored prefix of a pattern is found by bisection over the depth: one request when the whole prefix is wide.
+    const uint4    *dict;
+    uint64_t        dict_buckets;   // multiple of 4
+    int32_t         dict_D, dict_bits;
 };
 
 // Pattern accessors handed to search_pattern: operator()(i) = byte i; word(w) = bytes 4w..4w+3 packed little-endian (bytes at or
@@ -406,6 +414,48 @@ __device__ __forceinline__ void backward_step(const DevIndex &ix, const SharedTa
     }
 }
 
+// ---- wide-interval dictionary probe ----------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t dict_mix(uint64_t x) {
+    x ^= x >> 31; x *= 0x9E3779B97F4A7C15ull; x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+    return x;
+}
+__device__ __forceinline__ uint64_t dict_home(uint64_t key, uint64_t buckets) { return __umul64hi(dict_mix(key), buckets); }
+
+// key of the first d consumed symbols: their dense codes, `bits` each, the first one lowest, | (d-1) << 60
+__device__ __forceinline__ uint64_t dict_key(uint64_t full, int d, uint32_t bits) {
+    return (full & ((1ull << (bits * (uint32_t)d)) - 1ull)) | ((uint64_t)(d - 1) << 60);
+}
+
+// All G lanes of a group call this together with the same key.  Lane l looks at bucket (home rounded down to a multiple of G) + l, i.e.
+// the group reads G consecutive 32-byte buckets = one request per round; a slot that is empty at or after the home bucket ends the search.
+template <int G, bool STATS>
+__device__ __forceinline__ bool dict_probe(const DevIndex &ix, uint64_t key, uint32_t &sp, uint32_t &ep, uint32_t &touched) {
+    const int lane = (G == 1) ? 0 : (threadIdx.x & (G - 1));
+    const uint32_t gmask = group_mask<G>();
+    const uint64_t home = dict_home(key, ix.dict_buckets);
+    uint64_t base = home & ~(uint64_t)(G - 1);
+    bool first = true;
+    for (int round = 0; round < 4096; ++round) {
+        const uint64_t b = base + (uint64_t)lane;
+        uint4 e0, e1;
+        ldg256(ix.dict + b * 2, e0, e1);
+        if (STATS && lane == 0) ++touched;
+        const uint64_t k0 = ((uint64_t)e0.y << 32) | e0.x, k1 = ((uint64_t)e1.y << 32) | e1.x;
+        const bool mine = !first || b >= home;             // buckets before the home bucket are not on this key's probe sequence
+        uint32_t f = 0, s = 0, e = 0;
+        if (mine && k0 == key) { f = 1; s = e0.z; e = e0.w; }
+        else if (mine && k1 == key) { f = 1; s = e1.z; e = e1.w; }
+        uint32_t stop = (mine && (k0 == 0ull || k1 == 0ull)) ? 1u : 0u;
+        if (G > 1) { f = group_sum<G>(f, gmask); s = group_sum<G>(s, gmask); e = group_sum<G>(e, gmask); stop = group_sum<G>(stop, gmask); }
+        if (f) { sp = s; ep = e; return true; }
+        if (stop) return false;
+        base += G;
+        if (base >= ix.dict_buckets) base = 0;
+        first = false;
+    }
+    return false;
+}
+
 // ---- the whole backward search of one pattern: SuffixAlgo.search, findex.scala:15-31 -----------------------
 // pat(i) returns pattern byte i.  Every thread of the warp calls this together (inactive groups pass
 // active=false); groups leave the loop individually, the warp leaves when all are done.
@@ -415,18 +465,56 @@ __device__ __forceinline__ void backward_step(const DevIndex &ix, const SharedTa
 //     are compared with T' in front of position sa[r]; the answer row is isa[sa[r]-remaining].  Identical to
 //     stepping: from a singleton, a step succeeds iff BWT[r] = T'[sa[r]-1] equals the byte, and lands on
 //     LF(r) = isa[sa[r]-1].  Patterns containing byte 0 take the ordinary steps (the '$' row wraps the text).
+// `mode` — how the two-pass count (dictionary first, the rest compacted; fmx_kernels.cu) hands a query over: kSearchFresh = from the
+// start; kSearchTopMissed = the dictionary probe at the deepest possible prefix has been done and missed (bisection goes on below it);
+// kSearchResume = that probe hit, (rsp, rep) is the interval after min(len, dict_D) symbols.
+constexpr int kSearchFresh = 0, kSearchTopMissed = 1, kSearchResume = 2;
 template <int G, int LAYOUT, bool STATS, typename PatFn>
 __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedTables &tb, PatFn pat, int len, bool active,
-                                               uint32_t &sp, uint32_t &ep, uint32_t &touched, uint32_t &steps) {
+                                               uint32_t &sp, uint32_t &ep, uint32_t &touched, uint32_t &steps,
+                                               int mode = kSearchFresh, uint32_t rsp = 0, uint32_t rep = 0) {
     const int lane = (G == 1) ? 0 : (threadIdx.x & (G - 1));
     const uint32_t gmask = group_mask<G>();
     sp = 0;
     ep = active ? ix.n : 0u;
     int i = len - 1;
     bool noshort = (ix.isat == nullptr);
-    if (active && i >= 0) {
+    if (active && mode == kSearchResume) {
+        sp = rsp; ep = rep;
+        i -= len < ix.dict_D ? len : ix.dict_D;
+    } else if (active && i >= 0) {
         bool done = false;
-        if (ix.kmer != nullptr && len >= ix.kmer_k) {
+        if (ix.dict != nullptr && len > ix.kmer_k) {
+            // deepest stored prefix of the pattern (consumption order): first the longest the dictionary could hold, then bisection
+            const int K = ix.kmer_k;
+            const uint32_t bits = (uint32_t)ix.dict_bits;
+            int hi = len < ix.dict_D ? len : ix.dict_D;
+            uint64_t full = 0;
+            bool ok = true;
+            for (int j = 0; j < hi; ++j) {
+                const uint32_t c = pat(len - 1 - j), code = tb.code[c];
+                ok = ok && (code != (uint32_t)kCodeAbsent) && (c != 0);
+                full |= (uint64_t)code << (bits * (uint32_t)j);
+            }
+            if (ok) {
+                int lo = K, d = hi;
+                uint32_t bsp = 0, bep = 0;
+                if (mode == kSearchTopMissed) { --hi; d = (lo + hi + 1) >> 1; }
+                while (lo < hi) {
+                    uint32_t s, e;
+                    if (dict_probe<G, STATS>(ix, dict_key(full, d, bits), s, e, touched)) { lo = d; bsp = s; bep = e; }
+                    else hi = d - 1;
+                    d = (lo + hi + 1) >> 1;
+                }
+                if (lo > K) {
+                    sp = bsp; ep = bep;
+                    i -= lo;
+                    done = true;
+                    if (STATS) steps += lo;
+                }
+            }
+        }
+        if (!done && ix.kmer != nullptr && len >= ix.kmer_k) {
             uint32_t idx = 0;
             bool ok = true;
             for (int j = 0; j < ix.kmer_k; ++j) {

@@ -113,6 +113,107 @@ count_fixed_gmem_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__re
     }
 }
 
+// ---- two-pass count for indexes with a dictionary of wide intervals --------------------------------------------------------------------
+// With a dictionary most queries are ONE request (the probe at their deepest possible prefix) while the rest walk a chain of a dozen; in
+// one kernel a warp waits for its slowest query and the request rate collapses (measured: 17 G requests/s instead of 46).  So the work is
+// split by cost.  Pass 1, one thread per query: that single probe; a hit covering the whole pattern is the answer, everything else is
+// appended to a work list (warp-aggregated) with what is known: the probe missed / the probe hit and (sp, ep) after D symbols is in the
+// output arrays / not probed (absent symbol, byte 0).  Pass 2: the general search over the compacted list, patterns from global memory.
+constexpr uint32_t kListModeShift = 30, kListIdMask = (1u << kListModeShift) - 1u;
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads)
+count_dict_first_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, int len, long long m, OutT *__restrict__ sp_out,
+                        OutT *__restrict__ ep_out, uint32_t *__restrict__ list, unsigned long long *__restrict__ list_count,
+                        const __grid_constant__ PeerSinks sinks) {
+    __shared__ uint8_t scode[256];
+    extern __shared__ __align__(16) uint8_t spat[];
+    for (int i = threadIdx.x; i < 256; i += kThreads) scode[i] = ix.code[i];
+    const int d0 = len < ix.dict_D ? len : ix.dict_D;         // symbols the probe covers: the last d0 bytes of the pattern
+    const long long q0 = (long long)blockIdx.x * kThreads;
+    const int nq = (int)((m - q0) < (long long)kThreads ? (m - q0) : (long long)kThreads);
+    {
+        const uint8_t *src = pat + q0 * len;
+        const int nbytes = nq * len;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            const int nvec = nbytes >> 4;
+            for (int i = threadIdx.x; i < nvec; i += kThreads)
+                reinterpret_cast<uint4 *>(spat)[i] = ldg128(reinterpret_cast<const uint4 *>(src) + i);
+            for (int i = (nvec << 4) + threadIdx.x; i < nbytes; i += kThreads) spat[i] = src[i];
+        } else {
+            for (int i = threadIdx.x; i < nbytes; i += kThreads) spat[i] = src[i];
+        }
+    }
+    __syncthreads();
+    const bool active = (int)threadIdx.x < nq;
+    const long long q = q0 + threadIdx.x;
+    uint32_t entry = 0xFFFFFFFFu;                              // 0xFFFFFFFF = finished here
+    if (active) {
+        const uint8_t *p = spat + (size_t)threadIdx.x * len;
+        const uint32_t bits = (uint32_t)ix.dict_bits;
+        uint64_t full = 0;
+        bool ok = true;
+        for (int j = 0; j < d0; ++j) {
+            const uint32_t c = p[len - 1 - j], code = scode[c];
+            ok = ok && (code != (uint32_t)kCodeAbsent) && (c != 0);
+            full |= (uint64_t)code << (bits * (uint32_t)j);
+        }
+        entry = (uint32_t)threadIdx.x | ((uint32_t)kSearchFresh << kListModeShift);
+        if (ok) {
+            uint32_t s = 0, e = 0, touched = 0;
+            if (dict_probe<1, false>(ix, dict_key(full, d0, bits), s, e, touched)) {
+                sp_out[q] = (OutT)s;
+                ep_out[q] = (OutT)e;
+                if (d0 == len) {
+                    entry = 0xFFFFFFFFu;
+                    for (int j = 0; j < sinks.n; ++j) sinks.p[j][sinks.offset + q] = e - s;
+                } else entry = (uint32_t)threadIdx.x | ((uint32_t)kSearchResume << kListModeShift);
+            } else entry = (uint32_t)threadIdx.x | ((uint32_t)kSearchTopMissed << kListModeShift);
+        }
+    }
+    // append the unfinished queries of the warp with one atomic
+    const uint32_t need = __ballot_sync(0xFFFFFFFFu, entry != 0xFFFFFFFFu);
+    if (need) {
+        const int lane = threadIdx.x & 31, leader = __ffs(need) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(list_count, (unsigned long long)__popc(need));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (entry != 0xFFFFFFFFu) {
+            const uint32_t mode = entry >> kListModeShift;
+            list[base + __popc(need & ((1u << lane) - 1u))] = (uint32_t)(q0 + (entry & kListIdMask)) | (mode << kListModeShift);
+        }
+    }
+}
+
+template <int G, int LAYOUT, typename OutT>
+__global__ void __launch_bounds__(kThreads)
+count_list_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, int len, OutT *__restrict__ sp_out, OutT *__restrict__ ep_out,
+                  const uint32_t *__restrict__ list, const unsigned long long *__restrict__ list_count, const __grid_constant__ PeerSinks sinks) {
+    __shared__ SharedTables tb;
+    constexpr int QPB = kThreads / G;
+    const unsigned long long count = *list_count;
+    if ((unsigned long long)blockIdx.x * QPB >= count) return;
+    load_tables(tb, ix);
+    __syncthreads();
+    for (unsigned long long base = (unsigned long long)blockIdx.x * QPB; base < count; base += (unsigned long long)gridDim.x * QPB) {
+        const unsigned long long t = base + threadIdx.x / G;
+        const bool active = t < count;
+        const uint32_t entry = active ? list[t] : 0u;
+        const long long q = (long long)(entry & kListIdMask);
+        const int mode = (int)(entry >> kListModeShift);
+        uint32_t rsp = 0, rep = 0;
+        if (active && mode == kSearchResume) { rsp = (uint32_t)sp_out[q]; rep = (uint32_t)ep_out[q]; }
+        uint32_t sp, ep, touched = 0, steps = 0;
+        search_pattern<G, LAYOUT, false>(ix, tb, GlobalPattern{pat + q * len, len}, len, active, sp, ep, touched, steps, mode, rsp, rep);
+        if (active && (threadIdx.x % G) == 0) {
+            const bool hit = sp < ep;
+            sp_out[q] = hit ? (OutT)sp : (OutT)0;
+            ep_out[q] = hit ? (OutT)ep : (OutT)0;
+            for (int j = 0; j < sinks.n; ++j) sinks.p[j][sinks.offset + q] = hit ? ep - sp : 0u;
+        }
+    }
+}
+
 template <int G, int LAYOUT>
 __global__ void __launch_bounds__(kThreads)
 count_var_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, const long long *__restrict__ off,
@@ -456,6 +557,38 @@ cudaError_t launch_count_fixed(const DevIndex &ix, LaunchCfg cfg, const uint8_t 
     // + 16: the 12-byte pattern windows of the row-context hops are read as whole words and may run past the last pattern
     const size_t smem = (size_t)(kThreads / cfg.lanes) * (size_t)(len > 0 ? len : 1) + 16;
     const bool too_long = smem > 160 * 1024;             // patterns of more than ~640 bytes per lane: read them from global memory
+    if (ix.dict != nullptr && len > ix.kmer_k && !d_stats && m < (1ll << kListModeShift) && (size_t)kThreads * (size_t)len <= 160 * 1024) {
+        // two passes: the dictionary probe for everybody, the general search for what it leaves (compacted)
+        uint32_t *list = nullptr;
+        unsigned long long *cnt = nullptr;
+        cudaError_t e = cudaMallocAsync(&list, (size_t)m * 4, st);
+        if (e != cudaSuccess) return e;
+        e = cudaMallocAsync(&cnt, 8, st);
+        if (e != cudaSuccess) { cudaFreeAsync(list, st); return e; }
+        cudaMemsetAsync(cnt, 0, 8, st);
+        const size_t smem1 = (size_t)kThreads * (size_t)len;
+        const unsigned grid1 = grid_for(m, 1);
+        if (out64) {
+            auto k = count_dict_first_kernel<long long>;
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+            k<<<grid1, kThreads, smem1, st>>>(ix, d_pat, len, m, (long long *)d_sp, (long long *)d_ep, list, cnt, sinks);
+        } else {
+            auto k = count_dict_first_kernel<uint32_t>;
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+            k<<<grid1, kThreads, smem1, st>>>(ix, d_pat, len, m, (uint32_t *)d_sp, (uint32_t *)d_ep, list, cnt, sinks);
+        }
+        const unsigned grid2 = std::min<unsigned>(grid_for(m, cfg.lanes), 148u * 8u);
+#define CALL2(G, LAY)                                                                                                  \
+        {                                                                                                              \
+            if (out64) count_list_kernel<G, LAY, long long><<<grid2, kThreads, 0, st>>>(ix, d_pat, len, (long long *)d_sp, (long long *)d_ep, list, cnt, sinks); \
+            else count_list_kernel<G, LAY, uint32_t><<<grid2, kThreads, 0, st>>>(ix, d_pat, len, (uint32_t *)d_sp, (uint32_t *)d_ep, list, cnt, sinks); \
+        }
+        FMX_DISPATCH(cfg, CALL2);
+#undef CALL2
+        cudaFreeAsync(list, st);
+        cudaFreeAsync(cnt, st);
+        return cudaGetLastError();
+    }
 #define CALL(G, LAY)                                                                                                  \
     {                                                                                                                 \
         if (too_long && !d_stats) {                                                                                   \

@@ -843,6 +843,104 @@ def test_every_length_hops(sigma):
     o.close()
 
 
+# ----------------------------------------------------------------------------------------------- dictionary of wide intervals
+def _zipf_text(rng, alpha, n_words, n_vocab):
+    """words of 2..9 symbols drawn Zipf(1) over a vocabulary, separated by alpha[0]: k-mers that stay frequent far beyond a shallow table"""
+    vocab = [alpha[1 + rng.integers(0, len(alpha) - 1, int(rng.integers(2, 10)))] for _ in range(n_vocab)]
+    p = 1.0 / np.arange(1, n_vocab + 1)
+    idx = rng.choice(n_vocab, n_words, p=p / p.sum())
+    return np.concatenate([np.concatenate([vocab[i], alpha[:1]]) for i in idx]).tobytes()
+
+
+@pytest.mark.parametrize("sigma,min_rows", [(4, 8), (27, 8), (27, 1), (60, 3), (255, 2)])
+@pytest.mark.parametrize("cfg", [(fx.LAYOUT_PLANES, 2), (fx.LAYOUT_PLANES, 1), (fx.LAYOUT_WM, 4), (fx.LAYOUT_WMX, 4)], ids=_ids)
+def test_wide_interval_dictionary(cfg, sigma, min_rows):
+    """FMX_ACCEL_DICT: (sp, ep) of every wide d-mer beyond the dense table in a hash table, deepest stored prefix by bisection — same
+    intervals as stepping for every pattern length, for hits (wide and narrow), near misses, absent symbols and byte 0; with and
+    without row contexts behind it; 2-, 5-, 6- and 8-bit keys."""
+    rng = np.random.default_rng(900 + sigma + min_rows)
+    alpha = np.arange(1, 256, dtype=np.uint8) if sigma == 255 else rng.choice(np.arange(1, 255), sigma, replace=False).astype(np.uint8)
+    text = _zipf_text(rng, alpha, 6000, 300)
+    tp = bytes(fo.file_to_text_rev(text))
+    bwt, eof, cnt = fo.build_bwt(fo.file_to_text_rev(text))
+    o = fo.OracleIndex.from_bwt(bwt, eof, cnt)
+    bits = max(1, int(np.ceil(np.log2(len(set(text))))))
+    absent = bytes([255]) if sigma < 255 else None
+    for accel in (fx.ACCEL_KMER | fx.ACCEL_DICT, fx.ACCEL_KMER | fx.ACCEL_DICT | fx.ACCEL_CTX):
+        g = fx.GpuFMSearcher(bwt=bwt, eof=eof, counts=cnt, layout=cfg[0], lanes_per_query=cfg[1], accel=accel,
+                             kmer_table_bytes=8 * len(set(text)) ** 2, dict_min_rows=min_rows)
+        info = g.info()
+        assert info["kmer_k"] == 2 and info["dict_depth"] == min(16, 60 // bits) and info["dict_entries"] > 100, info
+        assert info["dict_bytes"] >= 16 * info["dict_entries"] * 2 and info["index_bytes"] > info["dict_bytes"]
+        pats = []
+        for ln in list(range(1, 24)) + [30, 47]:
+            for _ in range(80):
+                s = int(rng.integers(0, len(tp) - ln))
+                q = bytearray(tp[s:s + ln])
+                u = rng.random()
+                if u < 0.25:
+                    q[int(rng.integers(0, ln))] = int(alpha[rng.integers(0, sigma)])       # near miss
+                elif u < 0.30 and absent:
+                    q[int(rng.integers(0, ln))] = absent[0]
+                elif u < 0.33:
+                    q[int(rng.integers(0, ln))] = 0
+                pats.append(bytes(q))
+        sp, ep = g.count_batch(pats)
+        wide = 0
+        for i, q in enumerate(pats):
+            r = o.search(q)
+            assert (int(sp[i]), int(ep[i])) == (r if r else (0, 0)), (q, accel)
+            wide += int(ep[i] - sp[i]) > min_rows and len(q) > 2
+        assert wide > 200
+        for ln in (3, 5, 8, 12, 13, 16, 21):
+            arr = np.frombuffer(b"".join(q[-ln:] for q in pats if len(q) >= ln), np.uint8).reshape(-1, ln)
+            s2, e2 = g.count_fixed(arr)
+            osp, oep = o.count_batch(arr.reshape(-1), np.arange(0, arr.size + 1, ln, dtype=np.int64))
+            assert np.array_equal(s2, osp) and np.array_equal(e2, oep), ln
+        # fewer requests than without the dictionary, and hiding it changes nothing but that
+        arr = np.frombuffer(b"".join(q[-12:] for q in pats if len(q) >= 12), np.uint8).reshape(-1, 12)
+        with_dict, _ = g.count_fixed_stats(arr)
+        g.set_accel_mask(accel & ~fx.ACCEL_DICT)
+        assert g.info()["dict_depth"] == 0
+        without, _ = g.count_fixed_stats(arr)
+        s3, e3 = g.count_fixed(arr)
+        osp, oep = o.count_batch(arr.reshape(-1), np.arange(0, arr.size + 1, 12, dtype=np.int64))
+        assert np.array_equal(s3, osp) and np.array_equal(e3, oep)
+        if min_rows <= 2:                                    # (a high threshold on a text this small stores too little to pay for its probes)
+            assert with_dict < without, (with_dict, without)
+        g.close()
+    o.close()
+
+
+def test_dictionary_budget_and_uniform_text():
+    """dict_bytes bounds the table (whole levels are dropped from the deep end); a uniform text under a saturating table gets no dictionary"""
+    rng = np.random.default_rng(77)
+    alpha = rng.choice(np.arange(1, 255), 27, replace=False).astype(np.uint8)
+    text = _zipf_text(rng, alpha, 6000, 300)
+    bwt, eof, cnt = fo.build_bwt(fo.file_to_text_rev(text))
+    o = fo.OracleIndex.from_bwt(bwt, eof, cnt)
+    tp = bytes(fo.file_to_text_rev(text))
+    full = fx.GpuFMSearcher(bwt=bwt, eof=eof, counts=cnt, accel=fx.ACCEL_KMER | fx.ACCEL_DICT, kmer_table_bytes=8 * 28 ** 2, dict_min_rows=2)
+    fi = full.info()
+    full.close()
+    g = fx.GpuFMSearcher(bwt=bwt, eof=eof, counts=cnt, accel=fx.ACCEL_KMER | fx.ACCEL_DICT, kmer_table_bytes=8 * 28 ** 2, dict_min_rows=2,
+                         dict_bytes=fi["dict_bytes"] // 3)
+    gi = g.info()
+    assert 2 < gi["dict_depth"] < fi["dict_depth"] and gi["dict_bytes"] <= fi["dict_bytes"] // 3 + 128
+    offs = rng.integers(0, len(tp) - 14, 500)
+    arr = np.stack([np.frombuffer(tp[s:s + 14], np.uint8) for s in offs])
+    sp, ep = g.count_fixed(arr)
+    osp, oep = o.count_batch(arr.reshape(-1), np.arange(0, arr.size + 1, 14, dtype=np.int64))
+    assert np.array_equal(sp, osp) and np.array_equal(ep, oep)
+    g.close()
+    o.close()
+    utext = alpha[rng.integers(0, 27, 20000)].tobytes()
+    bwt, eof, cnt = fo.build_bwt(fo.file_to_text_rev(utext))
+    g = fx.GpuFMSearcher(bwt=bwt, eof=eof, counts=cnt)          # AUTO: table depth ~ log_27(8n) => nothing wide beyond it
+    assert g.info()["kmer_k"] >= 3 and g.info()["dict_depth"] == 0
+    g.close()
+
+
 @pytest.mark.parametrize("sigma", [3, 10, 16, 17, 255])
 @pytest.mark.parametrize("lanes", [1, 2, 4])
 def test_multiary_wavelet_matrix(sigma, lanes):
