@@ -1107,9 +1107,19 @@ def run_default(cx):
             text_e, base_e, ge, info_e = english_open(cx, ne)
             try:
                 orc_e = load_oracle(base_e, "cfg3") if (cx.world == 1 and cx.rank == 0 and not args.no_cpu) else None
-                res = {"index": {k: info_e[k] for k in ("layout", "index_bytes", "kmer_k", "ctx_depth", "sigma", "sa_sample_rate", "open_s")}}
+                res = {"index": {k: info_e[k] for k in ("layout", "index_bytes", "kmer_k", "ctx_depth", "dict_depth", "dict_chain_depth", "dict_entries", "dict_bytes",
+                                                        "sigma", "sa_sample_rate", "open_s")}}
                 mq = max(1000, min(m, int(4_000_000 * min(1.0, scale * 10))))
-                res["count"] = guarded("english count", lambda: sweep_leg(cx, ge, text_e, [12, 16], mq, 5, orc_e, "cfg3 English-like, all accelerators", workload="cfg3"))
+
+                def english_count():
+                    recs = sweep_leg(cx, ge, text_e, [8, 12, 16, 24], mq, 5, orc_e, "cfg3 English-like, all accelerators (table + row contexts + dictionary of wide intervals)", workload="cfg3")
+                    ge.set_accel_mask(fx.ACCEL_KMER | fx.ACCEL_CTX)             # the same index without the dictionary
+                    try:
+                        recs += sweep_leg(cx, ge, text_e, [12], mq, 5, orc_e, "cfg3 English-like, table + row contexts only", workload="cfg3")
+                    finally:
+                        ge.set_accel_mask(fx.ACCEL_AUTO)
+                    return recs
+                res["count"] = guarded("english count", english_count)
                 ml = max(400, int(4000 * min(1.0, scale * 10)))      # ~5 x 10^8 occurrences at full size: one chunk, a fraction of a second per step
                 res["locate"] = guarded("locate", lambda: locate_leg(cx, ge, text_e, ne, ml, 12, orc_e, max(2, min(args.steps, 5)), chunk_q=ml))
                 res["regex"] = guarded("regex", lambda: regex_leg(cx, ge, text_e, args.regexes, orc_e, args.steps))

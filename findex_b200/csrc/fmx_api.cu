@@ -282,7 +282,7 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
     d.blocks = (const uint4 *)blocks; d.stride = (uint64_t)nblk; d.bwt = d_bwt; d.C = d_C; d.base = d_base; d.code = d_code;
     d.bm = nullptr;
     d.kmer = nullptr; d.kmer_k = 0; d.kmer_sigma = 0; d.sa = nullptr; d.isat = nullptr; d.isat_bits = 8; d.isat_syms = 12; d.ctx = nullptr; d.ctx_J = 0; d.ctx_raw = 0; d.ctx_plan = nullptr; d.ctx8 = nullptr; d.ctx8_J = 0;
-    d.dict = nullptr; d.dict_buckets = 0; d.dict_D = 0; d.dict_bits = 0;
+    d.dict = nullptr; d.dict_buckets = 0; d.dict_D = 0; d.dict_bits = 0; d.dict_Dx = 0; d.dict_Jc = 1;
     for (int t = 0; t < 8; ++t) d.ctx_S[t] = 0;
     d.mark = nullptr; d.samples = nullptr; d.n = (uint32_t)n; d.eof = (uint32_t)eof; d.layout = layout; d.levels = levels;
     for (int l = 0; l < 8; ++l) d.z[l] = z[l];
@@ -445,18 +445,19 @@ int upload_index(fmx_index *ix, const uint8_t *bwt, int64_t n, int64_t eof, cons
         const int Dmax = std::min(16, 60 / dbits);
         size_t fr3 = 0, to3 = 0;
         cudaMemGetInfo(&fr3, &to3);
-        int64_t dict_budget = o.dict_bytes > 0 ? o.dict_bytes : std::min<int64_t>(8ll << 30, (int64_t)(fr3 / 8));
+        int64_t dict_budget = o.dict_bytes > 0 ? o.dict_bytes : std::min<int64_t>(12ll << 30, (int64_t)(fr3 / 8));
         dict_budget = std::min<int64_t>(dict_budget, room());
-        const uint32_t min_rows = o.dict_min_rows > 0 ? (uint32_t)o.dict_min_rows : kCtxMaxRows;
+        const uint32_t min_rows = o.dict_min_rows > 0 ? (uint32_t)o.dict_min_rows : 2u;
         if (Dmax > d.kmer_k && dict_budget >= 4096) {
             void *table = nullptr;
             int64_t buckets = 0, entries = 0;
-            int depth = 0;
-            e = build_dict(d, ix->cfg, d_sym, (uint32_t)sigma, dbits, Dmax, min_rows, dict_budget / 32, &table, &buckets, &depth, &entries, ix->stream);
+            int depth = 0, depth_x = 0, jc = 1;
+            const uint32_t min_rows_top = o.dict_top_min_rows > 0 ? (uint32_t)o.dict_top_min_rows : 1u;
+            e = build_dict(d, ix->cfg, d_sym, (uint32_t)sigma, dbits, Dmax, min_rows, min_rows_top, dict_budget / 32, &table, &buckets, &depth, &depth_x, &jc, &entries, ix->stream);
             if (e != cudaSuccess) { cudaGetLastError(); if (accel & FMX_ACCEL_DICT) return fail(FMX_E_CUDA, "dictionary construction failed: %s", cudaGetErrorString(e)); }
             else if (table) {
                 ix->owned.push_back(table);
-                d.dict = (const uint4 *)table; d.dict_buckets = (uint64_t)buckets; d.dict_D = depth; d.dict_bits = dbits;
+                d.dict = (const uint4 *)table; d.dict_buckets = (uint64_t)buckets; d.dict_D = depth; d.dict_bits = dbits; d.dict_Dx = depth_x; d.dict_Jc = jc;
                 ix->dict_entries = entries;
                 ix->index_bytes += buckets * 32;
             }
@@ -615,9 +616,10 @@ int fmx_accel_info(const fmx_index *ix, int32_t *kmer_k, int32_t *text_shortcut)
     if (text_shortcut) *text_shortcut = ix->accel_text ? 1 : 0;
     return FMX_OK;
 }
-int fmx_dict_info(const fmx_index *ix, int32_t *depth, int64_t *entries, int64_t *bytes) {
+int fmx_dict_info(const fmx_index *ix, int32_t *depth, int32_t *chain_depth, int64_t *entries, int64_t *bytes) {
     if (!ix) return fail(FMX_E_ARG, "null index");
     if (depth) *depth = ix->d.dict ? ix->d.dict_D : 0;
+    if (chain_depth) *chain_depth = ix->d.dict ? ix->d.dict_Dx : 0;
     if (entries) *entries = ix->d.dict ? ix->dict_entries : 0;
     if (bytes) *bytes = ix->d.dict ? (int64_t)ix->d.dict_buckets * 32 : 0;
     return FMX_OK;

@@ -587,8 +587,8 @@ __global__ void dict_seed_kernel(const uint2 *__restrict__ kmer, unsigned long l
 template <int G, int LAYOUT>
 __global__ void __launch_bounds__(kThreads)
 dict_extend_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ sym, uint32_t sigma, const DictItem *__restrict__ parents,
-                   unsigned long long count, int d, uint32_t bits, uint32_t min_rows, DictItem *__restrict__ out, unsigned long long cap,
-                   unsigned long long *__restrict__ counter) {
+                   unsigned long long count, int d, int D, int Jc, uint32_t bits, uint32_t min_rows, DictItem *__restrict__ out,
+                   unsigned long long cap, unsigned long long *__restrict__ counter) {
     __shared__ SharedTables tb;
     load_tables(tb, ix);
     __syncthreads();
@@ -598,9 +598,27 @@ dict_extend_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restric
     const uint32_t code = (uint32_t)(t % sigma);
     uint32_t sp = p.sp, ep = p.ep, touched = 0;
     backward_step<G, LAYOUT, false>(ix, tb, (uint32_t)sym[code], sp, ep, touched);
-    if ((threadIdx.x % G) == 0 && sp < ep && ep - sp > min_rows) {
-        const unsigned long long slot = atomicAdd(counter, 1ull);
-        const unsigned long long key = (p.key & ((1ull << 60) - 1ull)) | ((unsigned long long)code << (bits * (uint32_t)(d - 1))) | ((unsigned long long)(d - 1) << 60);
+    const bool keepit = (threadIdx.x % G) == 0 && sp < ep && ep - sp > min_rows;
+    const uint32_t act = __activemask(), votes = __ballot_sync(act, keepit);
+    unsigned long long wbase = 0;
+    if (votes) {
+        const int leader = __ffs(votes) - 1, wl = threadIdx.x & 31;
+        if (wl == leader) wbase = atomicAdd(counter, (unsigned long long)__popc(votes));
+        wbase = __shfl_sync(act, wbase, leader);
+    }
+    if (votes) {                                           // counter[1] += rows covered by the kept children (is the level worth having?)
+        const uint32_t rows = __reduce_add_sync(act, keepit ? ep - sp : 0u);
+        if ((int)(threadIdx.x & 31) == __ffs(votes) - 1) atomicAdd(counter + 1, (unsigned long long)rows);
+    }
+    if (keepit) {
+        const unsigned long long slot = wbase + __popc(votes & ((1u << (threadIdx.x & 31)) - 1u));
+        unsigned long long key;
+        if (d <= D) key = (p.key & ((1ull << 60) - 1ull)) | ((unsigned long long)code << (bits * (uint32_t)(d - 1))) | ((unsigned long long)(d - 1) << 60);
+        else {                                             // chain entry: tier t, j-th symbol past the tier's parent interval
+            const int rel = d - D - 1, t = rel / Jc + 1, j = rel % Jc + 1;
+            if (j == 1) key = dict_chain_key(p.sp, 1, t, (unsigned long long)code);
+            else key = (p.key & ~(7ull << 32)) | ((unsigned long long)(j - 1) << 32) | ((unsigned long long)code << (38u + bits * (uint32_t)(j - 1)));
+        }
         if (slot < cap) out[slot] = DictItem{key, sp, ep};
     }
 }
@@ -621,9 +639,12 @@ __global__ void dict_insert_kernel(const DictItem *__restrict__ items, unsigned 
     atomicAdd(failed, 1ull);
 }
 
-cudaError_t build_dict(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, uint32_t sigma, int bits, int Dmax, uint32_t min_rows,
-                       int64_t max_entries, void **d_table_out, int64_t *buckets_out, int *depth_out, int64_t *entries_out, cudaStream_t st) {
-    *d_table_out = nullptr; *buckets_out = 0; *depth_out = 0; *entries_out = 0;
+cudaError_t build_dict(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, uint32_t sigma, int bits, int Dmax, uint32_t min_rows, uint32_t min_rows_top,
+                       int64_t max_entries, void **d_table_out, int64_t *buckets_out, int *depth_out, int *depth_x_out, int *jc_out, int64_t *entries_out,
+                       cudaStream_t st) {
+    *d_table_out = nullptr; *buckets_out = 0; *depth_out = 0; *depth_x_out = 0; *entries_out = 0;
+    const int Jc = std::max(1, std::min(8, 22 / bits));
+    *jc_out = Jc;
     const int K = ix.kmer_k;
     if (!ix.kmer || K < 1 || sigma < 2 || Dmax <= K || max_entries < 1) return cudaSuccess;
     unsigned long long table_entries = 1;
@@ -647,19 +668,39 @@ cudaError_t build_dict(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, 
     unsigned long long lvl_begin = 0, lvl_count = seeds, total = seeds;
     int D = K;
     const int G = (cfg.lanes == 1 || cfg.lanes == 2 || cfg.lanes == 4) ? cfg.lanes : 2;
-    for (int d = K + 1; d <= Dmax && lvl_count > 0; ++d) {
+    for (int d = K + 1; d <= Dmax + kDictMaxTiers * Jc && lvl_count > 0; ++d) {
         const unsigned long long groups = lvl_count * sigma, per = kThreads / G;
         if ((groups + per - 1) / per > 0x7FFFFFFFull) break;
         const unsigned grid = (unsigned)((groups + per - 1) / per);
-#define CALL(GG, LAY) dict_extend_kernel<GG, LAY><<<grid, kThreads, 0, st>>>(ix, d_sym, sigma, items + lvl_begin, lvl_count, d, (uint32_t)bits, min_rows, items, cap, d_cnt)
-        if (ix.layout == FMX_LAYOUT_PLANES) { if (G == 1) CALL(1, FMX_LAYOUT_PLANES); else if (G == 2) CALL(2, FMX_LAYOUT_PLANES); else CALL(4, FMX_LAYOUT_PLANES); }
-        else if (ix.layout == FMX_LAYOUT_WMX) { if (G == 1) CALL(1, FMX_LAYOUT_WMX); else if (G == 2) CALL(2, FMX_LAYOUT_WMX); else CALL(4, FMX_LAYOUT_WMX); }
-        else { if (G == 1) CALL(1, FMX_LAYOUT_WM); else if (G == 2) CALL(2, FMX_LAYOUT_WM); else CALL(4, FMX_LAYOUT_WM); }
+        // the deepest level the key can hold is where every pattern of at least that length probes first and nothing is grown from: it may
+        // take narrower intervals too (min_rows_top < min_rows) when they fit
+        // Chain levels (d > Dmax) keep what row contexts cannot take (more than kCtxMaxRows rows), whatever the threshold of the keyed levels.
+        const uint32_t lvl_rows = d > Dmax ? std::max<uint32_t>(min_rows, kCtxMaxRows) : min_rows;
+        uint32_t keep = (d == Dmax && min_rows_top < min_rows) ? min_rows_top : lvl_rows;
+        for (;;) {
+#define CALL(GG, LAY) dict_extend_kernel<GG, LAY><<<grid, kThreads, 0, st>>>(ix, d_sym, sigma, items + lvl_begin, lvl_count, d, Dmax, Jc, (uint32_t)bits, keep, items, cap, d_cnt)
+            if (ix.layout == FMX_LAYOUT_PLANES) { if (G == 1) CALL(1, FMX_LAYOUT_PLANES); else if (G == 2) CALL(2, FMX_LAYOUT_PLANES); else CALL(4, FMX_LAYOUT_PLANES); }
+            else if (ix.layout == FMX_LAYOUT_WMX) { if (G == 1) CALL(1, FMX_LAYOUT_WMX); else if (G == 2) CALL(2, FMX_LAYOUT_WMX); else CALL(4, FMX_LAYOUT_WMX); }
+            else { if (G == 1) CALL(1, FMX_LAYOUT_WM); else if (G == 2) CALL(2, FMX_LAYOUT_WM); else CALL(4, FMX_LAYOUT_WM); }
 #undef CALL
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const bool fits = h_cnt <= cap && h_cnt - seeds <= (unsigned long long)max_entries;
+            if (fits || keep == lvl_rows) break;
+            keep = lvl_rows;                                                             // the narrow ones do not fit: the level as all others
+            CK(cudaMemcpyAsync(d_cnt, &total, 8, cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));
+        }
         if (h_cnt > cap || h_cnt - seeds > (unsigned long long)max_entries) break;      // this level does not fit: the dictionary ends one level up
+        if (d == K + 1) {
+            // Worth having?  The first level past the table must cover a fair share of the rows: on a uniform text a few k-mers are wide by
+            // chance, and a dictionary of those would make every query pay a probe that almost never hits.
+            unsigned long long covered = 0;
+            CK(cudaMemcpyAsync(&covered, d_cnt + 1, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (covered * 16ull < (unsigned long long)ix.n) { cudaFreeAsync(items, st); cudaFreeAsync(d_cnt, st); return cudaSuccess; }
+        }
         lvl_begin = total;
         lvl_count = h_cnt - total;
         total = h_cnt;
@@ -678,7 +719,7 @@ cudaError_t build_dict(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, 
         CK(cudaMemcpyAsync(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (h_cnt != 0) { cudaFree(table); cudaFreeAsync(items, st); cudaFreeAsync(d_cnt, st); return cudaErrorUnknown; }
-        *d_table_out = table; *buckets_out = (int64_t)buckets; *depth_out = D; *entries_out = (int64_t)entries;
+        *d_table_out = table; *buckets_out = (int64_t)buckets; *depth_out = std::min(D, Dmax); *depth_x_out = D; *entries_out = (int64_t)entries;
     }
     cudaFreeAsync(items, st); cudaFreeAsync(d_cnt, st);
     return cudaGetLastError();

@@ -38,8 +38,10 @@ cudaError_t build_lcp(const uint32_t *d_sa, const uint32_t *d_isa, const uint8_t
 cudaError_t build_kmer_table(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, uint32_t sigma, int K, uint2 *d_table, cudaStream_t st);
 // dictionary of wide intervals (DevIndex::dict) grown from the dense k-mer table of `ix`: depths kmer_k+1 .. <= Dmax, intervals of more than
 // min_rows rows, at most max_entries entries; *d_table_out = nullptr when there is nothing to store (cudaMalloc'ed otherwise, 32 * buckets bytes)
-cudaError_t build_dict(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, uint32_t sigma, int bits, int Dmax, uint32_t min_rows,
-                       int64_t max_entries, void **d_table_out, int64_t *buckets_out, int *depth_out, int64_t *entries_out, cudaStream_t st);
+// (the deepest level, d = Dmax, keeps intervals of more than min_rows_top rows when those fit)
+cudaError_t build_dict(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, uint32_t sigma, int bits, int Dmax, uint32_t min_rows, uint32_t min_rows_top,
+                       int64_t max_entries, void **d_table_out, int64_t *buckets_out, int *depth_out, int *depth_x_out, int *jc_out, int64_t *entries_out,
+                       cudaStream_t st);
 // suffix sort of t+'$' (t has no zero bytes) -> BWT, eof row, byte counts; optionally the suffix array
 cudaError_t suffix_sort_bwt(const uint8_t *d_t, int64_t len, uint8_t *d_bwt, int64_t *eof_out, int64_t counts_out[256],
                             uint32_t *d_sa_out, int *rounds_out, cudaStream_t st);

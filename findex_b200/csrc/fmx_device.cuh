@@ -70,9 +70,13 @@ struct DevIndex {
     // table of 32-byte buckets = 2 entries { key: 64 bits, sp, ep }; key = the d dense codes (dict_bits each, first consumed symbol lowest)
     // | (d-1) << 60; 0 = empty slot.  Linear probing over buckets, built at <= half load.  A prefix of a wide d-mer is wide, so the deepest
     // stored prefix of a pattern is found by bisection over the depth: one request when the whole prefix is wide.
+    // CHAIN entries carry the same idea past depth D, where the symbols no longer fit a key: the interval after D + (t-1) Jc + j symbols
+    // (tier t = 1.., j = 1 .. Jc) is stored under { sp of the interval after D + (t-1) Jc symbols (which identifies it at that depth), j, t,
+    // the j symbols } — bits 0-31 sp, 32-34 j-1, 35-37 t, 38.. the symbols; Jc = min(8, 22 / dict_bits); top four bits 0 (a depth tag is >= 1).
     const uint4    *dict;
     uint64_t        dict_buckets;   // multiple of 4
     int32_t         dict_D, dict_bits;
+    int32_t         dict_Dx, dict_Jc;   // deepest depth stored at all (= dict_D without chain entries); symbols per chain tier
 };
 
 // Pattern accessors handed to search_pattern: operator()(i) = byte i; word(w) = bytes 4w..4w+3 packed little-endian (bytes at or
@@ -426,6 +430,11 @@ __device__ __forceinline__ uint64_t dict_key(uint64_t full, int d, uint32_t bits
     return (full & ((1ull << (bits * (uint32_t)d)) - 1ull)) | ((uint64_t)(d - 1) << 60);
 }
 
+constexpr int kDictMaxTiers = 7;
+__host__ __device__ __forceinline__ uint64_t dict_chain_key(uint32_t parent_sp, int j, int tier, uint64_t syms) {
+    return (uint64_t)parent_sp | ((uint64_t)(j - 1) << 32) | ((uint64_t)tier << 35) | (syms << 38);
+}
+
 // All G lanes of a group call this together with the same key.  Lane l looks at bucket (home rounded down to a multiple of G) + l, i.e.
 // the group reads G consecutive 32-byte buckets = one request per round; a slot that is empty at or after the home bucket ends the search.
 template <int G, bool STATS>
@@ -465,14 +474,42 @@ __device__ __forceinline__ bool dict_probe(const DevIndex &ix, uint64_t key, uin
 //     are compared with T' in front of position sa[r]; the answer row is isa[sa[r]-remaining].  Identical to
 //     stepping: from a singleton, a step succeeds iff BWT[r] = T'[sa[r]-1] equals the byte, and lands on
 //     LF(r) = isa[sa[r]-1].  Patterns containing byte 0 take the ordinary steps (the '$' row wraps the text).
+// From the interval after dict_D symbols (found in the dictionary): go on through the chain entries while the pattern and the stored
+// tiers last.  i = index of the next pattern byte to consume; leaves (sp, ep, i) at the deepest stored prefix reached this way (a miss
+// just ends the chain: the caller goes on with ordinary steps).  Group-uniform.
+template <int G, bool STATS, typename PatFn>
+__device__ __forceinline__ void dict_chain(const DevIndex &ix, const uint8_t *code, PatFn pat, int &i, uint32_t &sp, uint32_t &ep,
+                                           uint32_t &touched, uint32_t &steps) {
+    const int Jc = ix.dict_Jc;
+    const uint32_t bits = (uint32_t)ix.dict_bits;
+    int depth = ix.dict_D;
+    for (int t = 1; t <= kDictMaxTiers && i >= 0 && depth < ix.dict_Dx; ++t) {
+        const int j = (i + 1) < Jc ? (i + 1) : Jc;
+        uint64_t syms = 0;
+        bool ok = true;
+        for (int k = 0; k < j; ++k) {
+            const uint32_t c = pat(i - k), cd = code[c];
+            ok = ok && (cd != (uint32_t)kCodeAbsent) && (c != 0);
+            syms |= (uint64_t)cd << (bits * (uint32_t)k);
+        }
+        uint32_t s, e;
+        if (!ok || !dict_probe<G, STATS>(ix, dict_chain_key(sp, j, t, syms), s, e, touched)) break;
+        sp = s; ep = e;
+        i -= j;
+        depth += j;
+        if (STATS) steps += j;
+        if (j < Jc) break;
+    }
+}
+
 // `mode` — how the two-pass count (dictionary first, the rest compacted; fmx_kernels.cu) hands a query over: kSearchFresh = from the
 // start; kSearchTopMissed = the dictionary probe at the deepest possible prefix has been done and missed (bisection goes on below it);
-// kSearchResume = that probe hit, (rsp, rep) is the interval after min(len, dict_D) symbols.
+// kSearchResume = the dictionary has been followed as far as it goes, (rsp, rep) is the interval after `rconsumed` symbols.
 constexpr int kSearchFresh = 0, kSearchTopMissed = 1, kSearchResume = 2;
 template <int G, int LAYOUT, bool STATS, typename PatFn>
 __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedTables &tb, PatFn pat, int len, bool active,
                                                uint32_t &sp, uint32_t &ep, uint32_t &touched, uint32_t &steps,
-                                               int mode = kSearchFresh, uint32_t rsp = 0, uint32_t rep = 0) {
+                                               int mode = kSearchFresh, uint32_t rsp = 0, uint32_t rep = 0, int rconsumed = 0) {
     const int lane = (G == 1) ? 0 : (threadIdx.x & (G - 1));
     const uint32_t gmask = group_mask<G>();
     sp = 0;
@@ -481,7 +518,7 @@ __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedT
     bool noshort = (ix.isat == nullptr);
     if (active && mode == kSearchResume) {
         sp = rsp; ep = rep;
-        i -= len < ix.dict_D ? len : ix.dict_D;
+        i -= rconsumed;
     } else if (active && i >= 0) {
         bool done = false;
         if (ix.dict != nullptr && len > ix.kmer_k) {
@@ -511,6 +548,7 @@ __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedT
                     i -= lo;
                     done = true;
                     if (STATS) steps += lo;
+                    if (lo == ix.dict_D && ix.dict_Dx > ix.dict_D) dict_chain<G, STATS>(ix, tb.code, pat, i, sp, ep, touched, steps);
                 }
             }
         }

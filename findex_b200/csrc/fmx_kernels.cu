@@ -124,7 +124,7 @@ constexpr uint32_t kListModeShift = 30, kListIdMask = (1u << kListModeShift) - 1
 template <typename OutT>
 __global__ void __launch_bounds__(kThreads)
 count_dict_first_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, int len, long long m, OutT *__restrict__ sp_out,
-                        OutT *__restrict__ ep_out, uint32_t *__restrict__ list, unsigned long long *__restrict__ list_count,
+                        OutT *__restrict__ ep_out, uint2 *__restrict__ list, unsigned long long *__restrict__ list_count,
                         const __grid_constant__ PeerSinks sinks) {
     __shared__ uint8_t scode[256];
     extern __shared__ __align__(16) uint8_t spat[];
@@ -147,7 +147,7 @@ count_dict_first_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__re
     __syncthreads();
     const bool active = (int)threadIdx.x < nq;
     const long long q = q0 + threadIdx.x;
-    uint32_t entry = 0xFFFFFFFFu;                              // 0xFFFFFFFF = finished here
+    uint32_t entry = 0xFFFFFFFFu, consumed = 0;                // 0xFFFFFFFF = finished here
     if (active) {
         const uint8_t *p = spat + (size_t)threadIdx.x * len;
         const uint32_t bits = (uint32_t)ix.dict_bits;
@@ -162,49 +162,73 @@ count_dict_first_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__re
         if (ok) {
             uint32_t s = 0, e = 0, touched = 0;
             if (dict_probe<1, false>(ix, dict_key(full, d0, bits), s, e, touched)) {
+                int i = len - 1 - d0;
+                if (i >= 0 && ix.dict_Dx > ix.dict_D) {          // d0 = dict_D: on through the chain entries
+                    uint32_t steps = 0;
+                    dict_chain<1, false>(ix, scode, SmemPattern{p, len, false}, i, s, e, touched, steps);
+                }
+                consumed = (uint32_t)(len - 1 - i);
                 sp_out[q] = (OutT)s;
                 ep_out[q] = (OutT)e;
-                if (d0 == len) {
+                if (i < 0) {
                     entry = 0xFFFFFFFFu;
                     for (int j = 0; j < sinks.n; ++j) sinks.p[j][sinks.offset + q] = e - s;
                 } else entry = (uint32_t)threadIdx.x | ((uint32_t)kSearchResume << kListModeShift);
             } else entry = (uint32_t)threadIdx.x | ((uint32_t)kSearchTopMissed << kListModeShift);
         }
     }
-    // append the unfinished queries of the warp with one atomic
+    // append the CTA's unfinished queries with ONE atomic (125 k same-address atomics per 4 M queries, one per warp, cost more than the probes)
+    __shared__ uint32_t wcount[kThreads / 32];
+    __shared__ unsigned long long cta_base;
     const uint32_t need = __ballot_sync(0xFFFFFFFFu, entry != 0xFFFFFFFFu);
-    if (need) {
-        const int lane = threadIdx.x & 31, leader = __ffs(need) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(list_count, (unsigned long long)__popc(need));
-        base = __shfl_sync(0xFFFFFFFFu, base, leader);
-        if (entry != 0xFFFFFFFFu) {
-            const uint32_t mode = entry >> kListModeShift;
-            list[base + __popc(need & ((1u << lane) - 1u))] = (uint32_t)(q0 + (entry & kListIdMask)) | (mode << kListModeShift);
-        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) wcount[warp] = (uint32_t)__popc(need);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int w = 0; w < kThreads / 32; ++w) { const uint32_t c = wcount[w]; wcount[w] = total; total += c; }
+        cta_base = total ? atomicAdd(list_count, (unsigned long long)total) : 0ull;
+    }
+    __syncthreads();
+    if (entry != 0xFFFFFFFFu) {
+        const uint32_t mode = entry >> kListModeShift;
+        list[cta_base + wcount[warp] + __popc(need & ((1u << lane) - 1u))] = make_uint2((uint32_t)(q0 + (entry & kListIdMask)) | (mode << kListModeShift), consumed);
     }
 }
 
 template <int G, int LAYOUT, typename OutT>
 __global__ void __launch_bounds__(kThreads)
 count_list_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict__ pat, int len, OutT *__restrict__ sp_out, OutT *__restrict__ ep_out,
-                  const uint32_t *__restrict__ list, const unsigned long long *__restrict__ list_count, const __grid_constant__ PeerSinks sinks) {
+                  const uint2 *__restrict__ list, const unsigned long long *__restrict__ list_count, const __grid_constant__ PeerSinks sinks) {
     __shared__ SharedTables tb;
+    extern __shared__ __align__(16) uint8_t spat[];
     constexpr int QPB = kThreads / G;
     const unsigned long long count = *list_count;
     if ((unsigned long long)blockIdx.x * QPB >= count) return;
     load_tables(tb, ix);
-    __syncthreads();
-    for (unsigned long long base = (unsigned long long)blockIdx.x * QPB; base < count; base += (unsigned long long)gridDim.x * QPB) {
-        const unsigned long long t = base + threadIdx.x / G;
+    const int g = threadIdx.x / G, lane = threadIdx.x % G;
+    const int stride = (len + 3) & ~3;                      // every staged pattern starts on a word
+    {   // one chunk of the list per CTA (CTAs beyond the list's end have left above): the block scheduler balances the chains
+        const unsigned long long t = (unsigned long long)blockIdx.x * QPB + g;
         const bool active = t < count;
-        const uint32_t entry = active ? list[t] : 0u;
+        const uint2 le = active ? list[t] : make_uint2(0u, 0u);
+        const uint32_t entry = le.x;
         const long long q = (long long)(entry & kListIdMask);
         const int mode = (int)(entry >> kListModeShift);
+        __syncthreads();                                    // tables loaded / the previous round is done with spat
+        if (active) {                                       // the group stages its own pattern
+            const uint8_t *src = pat + q * len;
+            uint8_t *dst = spat + (size_t)g * stride;
+            if ((len & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0)
+                for (int w = lane; w < (len >> 2); w += G) reinterpret_cast<uint32_t *>(dst)[w] = __ldg(reinterpret_cast<const uint32_t *>(src) + w);
+            else
+                for (int b = lane; b < len; b += G) dst[b] = __ldg(src + b);
+        }
+        __syncthreads();
         uint32_t rsp = 0, rep = 0;
         if (active && mode == kSearchResume) { rsp = (uint32_t)sp_out[q]; rep = (uint32_t)ep_out[q]; }
         uint32_t sp, ep, touched = 0, steps = 0;
-        search_pattern<G, LAYOUT, false>(ix, tb, GlobalPattern{pat + q * len, len}, len, active, sp, ep, touched, steps, mode, rsp, rep);
+        search_pattern<G, LAYOUT, false>(ix, tb, SmemPattern{spat + (size_t)g * stride, len, true}, len, active, sp, ep, touched, steps, mode, rsp, rep, (int)le.y);
         if (active && (threadIdx.x % G) == 0) {
             const bool hit = sp < ep;
             sp_out[q] = hit ? (OutT)sp : (OutT)0;
@@ -557,14 +581,13 @@ cudaError_t launch_count_fixed(const DevIndex &ix, LaunchCfg cfg, const uint8_t 
     // + 16: the 12-byte pattern windows of the row-context hops are read as whole words and may run past the last pattern
     const size_t smem = (size_t)(kThreads / cfg.lanes) * (size_t)(len > 0 ? len : 1) + 16;
     const bool too_long = smem > 160 * 1024;             // patterns of more than ~640 bytes per lane: read them from global memory
-    if (ix.dict != nullptr && len > ix.kmer_k && !d_stats && m < (1ll << kListModeShift) && (size_t)kThreads * (size_t)len <= 160 * 1024) {
-        // two passes: the dictionary probe for everybody, the general search for what it leaves (compacted)
-        uint32_t *list = nullptr;
-        unsigned long long *cnt = nullptr;
-        cudaError_t e = cudaMallocAsync(&list, (size_t)m * 4, st);
+    if (ix.dict != nullptr && len > ix.kmer_k && len <= ix.dict_Dx && !d_stats && m < (1ll << kListModeShift) && (size_t)kThreads * (size_t)len <= 160 * 1024) {
+        // two passes: the dictionary probe for everybody, the general search for what it leaves (compacted).  Only where the probe can
+        // finish a query (len <= the deepest stored depth): longer patterns all go on with rank steps and the single kernel is balanced enough
+        unsigned long long *cnt = nullptr;                     // [0] = list length, the list behind it
+        cudaError_t e = cudaMallocAsync(&cnt, 16 + (size_t)m * 8, st);
         if (e != cudaSuccess) return e;
-        e = cudaMallocAsync(&cnt, 8, st);
-        if (e != cudaSuccess) { cudaFreeAsync(list, st); return e; }
+        uint2 *list = reinterpret_cast<uint2 *>(cnt + 2);
         cudaMemsetAsync(cnt, 0, 8, st);
         const size_t smem1 = (size_t)kThreads * (size_t)len;
         const unsigned grid1 = grid_for(m, 1);
@@ -577,15 +600,15 @@ cudaError_t launch_count_fixed(const DevIndex &ix, LaunchCfg cfg, const uint8_t 
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
             k<<<grid1, kThreads, smem1, st>>>(ix, d_pat, len, m, (uint32_t *)d_sp, (uint32_t *)d_ep, list, cnt, sinks);
         }
-        const unsigned grid2 = std::min<unsigned>(grid_for(m, cfg.lanes), 148u * 8u);
+        const unsigned grid2 = grid_for(m, cfg.lanes);
 #define CALL2(G, LAY)                                                                                                  \
         {                                                                                                              \
-            if (out64) count_list_kernel<G, LAY, long long><<<grid2, kThreads, 0, st>>>(ix, d_pat, len, (long long *)d_sp, (long long *)d_ep, list, cnt, sinks); \
-            else count_list_kernel<G, LAY, uint32_t><<<grid2, kThreads, 0, st>>>(ix, d_pat, len, (uint32_t *)d_sp, (uint32_t *)d_ep, list, cnt, sinks); \
+            const size_t smem2 = (size_t)(kThreads / G) * (size_t)((len + 3) & ~3) + 16;                               \
+            if (out64) count_list_kernel<G, LAY, long long><<<grid2, kThreads, smem2, st>>>(ix, d_pat, len, (long long *)d_sp, (long long *)d_ep, list, cnt, sinks); \
+            else count_list_kernel<G, LAY, uint32_t><<<grid2, kThreads, smem2, st>>>(ix, d_pat, len, (uint32_t *)d_sp, (uint32_t *)d_ep, list, cnt, sinks); \
         }
         FMX_DISPATCH(cfg, CALL2);
 #undef CALL2
-        cudaFreeAsync(list, st);
         cudaFreeAsync(cnt, st);
         return cudaGetLastError();
     }

@@ -39,7 +39,7 @@ class ReUnsupported(FmxError):
 class fmx_opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("layout", C.c_int32), ("sa_sample_rate", C.c_int32), ("require_fm", C.c_int32),
                 ("max_index_bytes", C.c_int64), ("lanes_per_query", C.c_int32), ("accel", C.c_int32), ("kmer_table_bytes", C.c_int64),
-                ("max_total_bytes", C.c_int64), ("dict_bytes", C.c_int64), ("dict_min_rows", C.c_int32), ("reserved0", C.c_int32)]
+                ("max_total_bytes", C.c_int64), ("dict_bytes", C.c_int64), ("dict_min_rows", C.c_int32), ("dict_top_min_rows", C.c_int32)]
 
 
 _lib = None
@@ -70,7 +70,7 @@ def lib():
     L.fmx_accel_info.argtypes = [p, C.POINTER(i32), C.POINTER(i32)]
     L.fmx_get_lanes.argtypes = [p]
     L.fmx_ctx_depth.argtypes = [p]
-    L.fmx_dict_info.argtypes = [p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.fmx_dict_info.argtypes = [p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.fmx_ctx_entry_bytes.argtypes = [p]
     L.fmx_occ_batch.argtypes = [p, p, p, i64, p]
     L.fmx_prev_range_batch.argtypes = [p, p, p, p, i64, p, p]
@@ -160,14 +160,14 @@ def _u8(a):
 
 
 def make_opts(device=-1, layout=LAYOUT_AUTO, sa_sample_rate=0, require_fm=False, max_index_bytes=0, lanes_per_query=0, accel=ACCEL_AUTO,
-              kmer_table_bytes=0, max_total_bytes=0, dict_bytes=0, dict_min_rows=0):
+              kmer_table_bytes=0, max_total_bytes=0, dict_bytes=0, dict_min_rows=0, dict_top_min_rows=0):
     o = fmx_opts()
     lib().fmx_opts_default(C.byref(o))
     o.device, o.layout, o.sa_sample_rate = device, layout, sa_sample_rate
     o.require_fm, o.max_index_bytes, o.lanes_per_query, o.accel = int(require_fm), max_index_bytes, lanes_per_query, accel
     o.kmer_table_bytes = kmer_table_bytes
     o.max_total_bytes = max_total_bytes
-    o.dict_bytes, o.dict_min_rows = dict_bytes, dict_min_rows
+    o.dict_bytes, o.dict_min_rows, o.dict_top_min_rows = dict_bytes, dict_min_rows, dict_top_min_rows
     return o
 
 
@@ -301,10 +301,10 @@ class GpuFMSearcher:
         _check(lib().fmx_info(self.h, C.byref(lay), C.byref(lev), C.byref(sig), C.byref(nb), C.byref(rate)))
         k, t = C.c_int32(), C.c_int32()
         _check(lib().fmx_accel_info(self.h, C.byref(k), C.byref(t)))
-        dd, de, db = C.c_int32(), C.c_int64(), C.c_int64()
-        _check(lib().fmx_dict_info(self.h, C.byref(dd), C.byref(de), C.byref(db)))
+        dd, dx, de, db = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
+        _check(lib().fmx_dict_info(self.h, C.byref(dd), C.byref(dx), C.byref(de), C.byref(db)))
         return {"layout": {1: "wm", 2: "planes", 3: "wmx"}[lay.value], "levels": lev.value, "sigma": sig.value,
-                "dict_depth": dd.value, "dict_entries": de.value, "dict_bytes": db.value,
+                "dict_depth": dd.value, "dict_chain_depth": dx.value, "dict_entries": de.value, "dict_bytes": db.value,
                 "index_bytes": nb.value, "sa_sample_rate": rate.value, "kmer_k": k.value, "text_shortcut": bool(t.value),
                 "ctx_depth": lib().fmx_ctx_depth(self.h), "ctx_entry_bytes": lib().fmx_ctx_entry_bytes(self.h),
                 "lanes_per_query": lib().fmx_get_lanes(self.h)}

@@ -55,9 +55,10 @@ extern "C" {
 #define FMX_ACCEL_CTX8     16   /* (alphabets of <= 4 symbols) compact 8-byte row contexts { isa[sa[r]-16], 16 two-bit symbols }: hops of exactly 16 symbols,
                                    the last < 16 by rank steps; chosen automatically when the 32-byte form does not fit (4e9-row DNA index)         */
 #define FMX_ACCEL_DICT     64   /* dictionary of WIDE intervals on top of the k-mer table: a hash table of (sp,ep) for every d-mer, k < d <= D (D = min(16, 60 / bits
-                                   per symbol): 12 for sigma <= 32), whose interval holds more than dict_min_rows (8) rows — where rank steps cost two requests
+                                   per symbol): 12 for sigma <= 32), whose interval holds more than dict_min_rows (2) rows — where rank steps cost two requests
                                    each and row contexts do not apply.  The deepest stored prefix of a pattern is found by bisection over d (a prefix of a wide
-                                   d-mer is wide): one request when the whole prefix is wide.  Texts with frequent k-mers (natural language) get one;
+                                   d-mer is wide): one request when the whole prefix is wide.  Deeper prefixes hang off depth D as chain entries keyed by
+                                   { sp of the interval a tier starts from, up to 22 / bits further symbols }.  Texts with frequent k-mers (natural language) get one;
                                    uniform texts have no wide k-mers beyond the table and get none                                        */
 #define FMX_ACCEL_NONE      8   /* plain backward search only                                                */
 #define FMX_ACCEL_NO_SA    32   /* count-only deployment: do not keep the full suffix array (4n bytes) that the context/shortcut construction produces;
@@ -78,9 +79,11 @@ typedef struct fmx_opts {
                                    the ~64 GB TLB reach, else 256 MiB .. 16 GiB (a sixteenth of free memory)     */
     int64_t  max_total_bytes;   /* cap on EVERYTHING resident for this index (rank structure + BWT + sampled SA + accelerators); 0 = no cap.
                                    FMX_LAYOUT_AUTO / FMX_ACCEL_AUTO pick the fastest combination under it; fmx_info reports what was built  */
-    int64_t  dict_bytes;        /* budget of the wide-interval dictionary (FMX_ACCEL_DICT); 0 = auto: 8 GiB or an eighth of the free memory     */
-    int32_t  dict_min_rows;     /* intervals of more than this many rows are stored; 0 = 8 (what the row contexts handle instead)             */
-    int32_t  reserved0;
+    int64_t  dict_bytes;        /* budget of the wide-interval dictionary (FMX_ACCEL_DICT); 0 = auto: 12 GiB or an eighth of the free memory    */
+    int32_t  dict_min_rows;     /* intervals of more than this many rows are stored; 0 = 2.  (Chain entries past depth D always need more than
+                                   max(this, 8) rows: narrower ones are what the row contexts take in one fetch per row)                      */
+    int32_t  dict_top_min_rows; /* threshold of the deepest keyed level D (where every pattern at least that long probes first); 0 = 1:
+                                   everything that occurs twice, when it fits the budget, else dict_min_rows                                   */
 } fmx_opts;
 
 void        fmx_opts_default(fmx_opts *o);
@@ -104,7 +107,9 @@ int     fmx_info(const fmx_index *ix, int32_t *layout, int32_t *levels, int32_t 
                  int64_t *index_bytes, int32_t *sa_sample_rate);
 
 int     fmx_accel_info(const fmx_index *ix, int32_t *kmer_k, int32_t *text_shortcut);   /* accelerators in effect */
-int     fmx_dict_info(const fmx_index *ix, int32_t *depth, int64_t *entries, int64_t *bytes);   /* wide-interval dictionary in effect (0 = none) */
+/* wide-interval dictionary in effect (0 = none): depth = deepest d-mer stored under its own symbols, chain_depth = deepest prefix reachable
+ * through the chain entries behind it (>= depth)                                                                                     */
+int     fmx_dict_info(const fmx_index *ix, int32_t *depth, int32_t *chain_depth, int64_t *entries, int64_t *bytes);
 int     fmx_ctx_depth(const fmx_index *ix);                  /* J of the row contexts (FMX_ACCEL_CTX / _CTX8), 0 = not built */
 int     fmx_ctx_entry_bytes(const fmx_index *ix);            /* 32, 8 or 0 */
 

@@ -15,7 +15,8 @@ cat gpurun_out/r02_regex_local_keep_sweep.jsonl
 cap r02_regex_queue_english regex_queue_kernel 1 regex
 cp /tmp/r02_regex_queue_english.ncu-rep gpurun_out/ 2>/dev/null
 cap r02_locate_english locate_kernel 1 locate
-cap r02_count_english_len12 count_fixed_kernel 2 count3
+cap r02_count_english_len12_pass1 count_dict_first_kernel 2 count3
+cap r02_count_english_len12_pass2 count_list_kernel 2 count3
 cap r02_count_cfg2_len16 count_fixed_kernel 2 count2
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_bench_launches_gpu_time.csv \
     python bench.py --steps 20 --warmup 5 --legs "" --no-cpu > gpurun_out/r02_bench_under_ncu.json 2> gpurun_out/r02_bench_under_ncu.err
