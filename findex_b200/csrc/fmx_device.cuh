@@ -477,13 +477,16 @@ __device__ __forceinline__ bool dict_probe(const DevIndex &ix, uint64_t key, uin
 // From the interval after dict_D symbols (found in the dictionary): go on through the chain entries while the pattern and the stored
 // tiers last.  i = index of the next pattern byte to consume; leaves (sp, ep, i) at the deepest stored prefix reached this way (a miss
 // just ends the chain: the caller goes on with ordinary steps).  Group-uniform.
-template <int G, bool STATS, typename PatFn>
-__device__ __forceinline__ void dict_chain(const DevIndex &ix, const uint8_t *code, PatFn pat, int &i, uint32_t &sp, uint32_t &ep,
-                                           uint32_t &touched, uint32_t &steps) {
+// `depth` = symbols consumed so far (dict_D + whole tiers).  BISECT: when the probe with all j symbols of a tier misses, the deepest
+// stored prefix inside the tier is found by bisection (stored = more than 8 rows, and a prefix of such a j-mer is one); without it the
+// miss just ends the chain.  Returns false when the chain ended on a miss of the full-j probe and no bisection was done (the two-pass
+// count's first pass: the bisection belongs to the second).
+template <int G, bool STATS, bool BISECT, typename PatFn>
+__device__ __forceinline__ bool dict_chain(const DevIndex &ix, const uint8_t *code, PatFn pat, int &i, uint32_t &sp, uint32_t &ep,
+                                           uint32_t &touched, uint32_t &steps, int depth, bool top_known_missed = false) {
     const int Jc = ix.dict_Jc;
     const uint32_t bits = (uint32_t)ix.dict_bits;
-    int depth = ix.dict_D;
-    for (int t = 1; t <= kDictMaxTiers && i >= 0 && depth < ix.dict_Dx; ++t) {
+    for (int t = (depth - ix.dict_D) / Jc + 1; t <= kDictMaxTiers && i >= 0 && depth < ix.dict_Dx; ++t) {
         const int j = (i + 1) < Jc ? (i + 1) : Jc;
         uint64_t syms = 0;
         bool ok = true;
@@ -492,20 +495,36 @@ __device__ __forceinline__ void dict_chain(const DevIndex &ix, const uint8_t *co
             ok = ok && (cd != (uint32_t)kCodeAbsent) && (c != 0);
             syms |= (uint64_t)cd << (bits * (uint32_t)k);
         }
+        if (!ok) return true;
         uint32_t s, e;
-        if (!ok || !dict_probe<G, STATS>(ix, dict_chain_key(sp, j, t, syms), s, e, touched)) break;
-        sp = s; ep = e;
-        i -= j;
-        depth += j;
-        if (STATS) steps += j;
-        if (j < Jc) break;
+        if (!top_known_missed && dict_probe<G, STATS>(ix, dict_chain_key(sp, j, t, syms), s, e, touched)) {
+            sp = s; ep = e;
+            i -= j;
+            depth += j;
+            if (STATS) steps += j;
+            if (j < Jc) return true;
+            continue;
+        }
+        if (!BISECT) return false;
+        int lo = 0, hi = j - 1;
+        uint32_t bs = 0, be = 0;
+        const uint32_t psp = sp;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (dict_probe<G, STATS>(ix, dict_chain_key(psp, mid, t, syms & ((1ull << (bits * (uint32_t)mid)) - 1ull)), s, e, touched)) { lo = mid; bs = s; be = e; }
+            else hi = mid - 1;
+        }
+        if (lo > 0) { sp = bs; ep = be; i -= lo; if (STATS) steps += lo; }
+        return true;
     }
+    return true;
 }
 
 // `mode` — how the two-pass count (dictionary first, the rest compacted; fmx_kernels.cu) hands a query over: kSearchFresh = from the
 // start; kSearchTopMissed = the dictionary probe at the deepest possible prefix has been done and missed (bisection goes on below it);
-// kSearchResume = the dictionary has been followed as far as it goes, (rsp, rep) is the interval after `rconsumed` symbols.
-constexpr int kSearchFresh = 0, kSearchTopMissed = 1, kSearchResume = 2;
+// kSearchResume = the dictionary has been followed as far as it goes, (rsp, rep) is the interval after `rconsumed` symbols;
+// kSearchChainMissed = the same, and the chain probe with all the symbols of the next tier has missed (bisection inside the tier goes on).
+constexpr int kSearchFresh = 0, kSearchTopMissed = 1, kSearchResume = 2, kSearchChainMissed = 3;
 template <int G, int LAYOUT, bool STATS, typename PatFn>
 __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedTables &tb, PatFn pat, int len, bool active,
                                                uint32_t &sp, uint32_t &ep, uint32_t &touched, uint32_t &steps,
@@ -516,9 +535,10 @@ __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedT
     ep = active ? ix.n : 0u;
     int i = len - 1;
     bool noshort = (ix.isat == nullptr);
-    if (active && mode == kSearchResume) {
+    if (active && (mode == kSearchResume || mode == kSearchChainMissed)) {
         sp = rsp; ep = rep;
         i -= rconsumed;
+        if (mode == kSearchChainMissed) dict_chain<G, STATS, true>(ix, tb.code, pat, i, sp, ep, touched, steps, rconsumed, true);
     } else if (active && i >= 0) {
         bool done = false;
         if (ix.dict != nullptr && len > ix.kmer_k) {
@@ -548,7 +568,7 @@ __device__ __forceinline__ void search_pattern(const DevIndex &ix, const SharedT
                     i -= lo;
                     done = true;
                     if (STATS) steps += lo;
-                    if (lo == ix.dict_D && ix.dict_Dx > ix.dict_D) dict_chain<G, STATS>(ix, tb.code, pat, i, sp, ep, touched, steps);
+                    if (lo == ix.dict_D && ix.dict_Dx > ix.dict_D) dict_chain<G, STATS, true>(ix, tb.code, pat, i, sp, ep, touched, steps, lo);
                 }
             }
         }

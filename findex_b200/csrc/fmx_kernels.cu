@@ -163,9 +163,10 @@ count_dict_first_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__re
             uint32_t s = 0, e = 0, touched = 0;
             if (dict_probe<1, false>(ix, dict_key(full, d0, bits), s, e, touched)) {
                 int i = len - 1 - d0;
+                bool chain_open = true;                          // false: the next tier's full probe missed, its bisection is left to pass 2
                 if (i >= 0 && ix.dict_Dx > ix.dict_D) {          // d0 = dict_D: on through the chain entries
                     uint32_t steps = 0;
-                    dict_chain<1, false>(ix, scode, SmemPattern{p, len, false}, i, s, e, touched, steps);
+                    chain_open = dict_chain<1, false, false>(ix, scode, SmemPattern{p, len, false}, i, s, e, touched, steps, d0);
                 }
                 consumed = (uint32_t)(len - 1 - i);
                 sp_out[q] = (OutT)s;
@@ -173,7 +174,7 @@ count_dict_first_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__re
                 if (i < 0) {
                     entry = 0xFFFFFFFFu;
                     for (int j = 0; j < sinks.n; ++j) sinks.p[j][sinks.offset + q] = e - s;
-                } else entry = (uint32_t)threadIdx.x | ((uint32_t)kSearchResume << kListModeShift);
+                } else entry = (uint32_t)threadIdx.x | ((uint32_t)(chain_open ? kSearchResume : kSearchChainMissed) << kListModeShift);
             } else entry = (uint32_t)threadIdx.x | ((uint32_t)kSearchTopMissed << kListModeShift);
         }
     }
@@ -226,7 +227,7 @@ count_list_kernel(const __grid_constant__ DevIndex ix, const uint8_t *__restrict
         }
         __syncthreads();
         uint32_t rsp = 0, rep = 0;
-        if (active && mode == kSearchResume) { rsp = (uint32_t)sp_out[q]; rep = (uint32_t)ep_out[q]; }
+        if (active && (mode == kSearchResume || mode == kSearchChainMissed)) { rsp = (uint32_t)sp_out[q]; rep = (uint32_t)ep_out[q]; }
         uint32_t sp, ep, touched = 0, steps = 0;
         search_pattern<G, LAYOUT, false>(ix, tb, SmemPattern{spat + (size_t)g * stride, len, true}, len, active, sp, ep, touched, steps, mode, rsp, rep, (int)le.y);
         if (active && (threadIdx.x % G) == 0) {
