@@ -61,11 +61,18 @@ def measured_peaks():
 def vocabulary(via):
     """words.txt vocabulary from the committed words.bwt fixture: through the GPU searcher (prevSubstr(eof, n) walks the whole file,
     T/Indexer.scala:1120) in our arm, through the oracle in the reference arm."""
-    d = "/tmp/fmx_words"
-    os.makedirs(d, exist_ok=True)
+    if via in _VOCAB:
+        return _VOCAB[via]
+    import tempfile
+    d = tempfile.mkdtemp(prefix="fmx_words_%d_" % os.getpid())         # private to this process: N ranks of one box share /tmp
     with lzma.open(os.path.join(ROOT, "tests", "golden", "ref", "words.bwt.xz"), "rb") as f:
-        open(os.path.join(d, "words.bwt"), "wb").write(f.read())
-    open(os.path.join(d, "words.aux"), "wb").write(open(os.path.join(ROOT, "tests", "golden", "ref", "words.aux"), "rb").read())
+        data = f.read()
+    with open(os.path.join(d, "words.bwt"), "wb") as f:
+        f.write(data)
+    with open(os.path.join(ROOT, "tests", "golden", "ref", "words.aux"), "rb") as f:
+        aux = f.read()
+    with open(os.path.join(d, "words.aux"), "wb") as f:
+        f.write(aux)
     if via == "gpu":
         from findex_b200 import fmindex as fx
         g = fx.GpuFMSearcher(os.path.join(d, "words.bwt"), accel=fx.ACCEL_NONE)
@@ -79,7 +86,13 @@ def vocabulary(via):
         tp[(sa.astype(np.int64) - 1) % o.n] = o.bwt()
         text = bytes(tp[:-1][::-1])
         o.close()
-    return [w for w in text.split(b"\r\n") if w]
+    import shutil
+    shutil.rmtree(d, ignore_errors=True)
+    _VOCAB[via] = [w for w in text.split(b"\r\n") if w]
+    return _VOCAB[via]
+
+
+_VOCAB = {}
 
 
 def make_text(n, workload, via="gpu"):
@@ -330,18 +343,19 @@ class Ctx:
         import gc
         gc.collect()
         self.torch.cuda.empty_cache()                      # the suffix sort of a 4 GB text needs most of the device
-        text = make_text(n, workload)
         base = index_base(n, workload)
-        err = None
-        if self.rank == 0 and not (os.path.exists(base + ".bwt") and os.path.exists(base + ".aux")):
-            tb = time.time()
-            try:
+        err, text = None, None
+        try:                                                 # every rank must reach the collective below and leave the same way
+            text = make_text(n, workload)
+            if self.rank == 0 and not (os.path.exists(base + ".bwt") and os.path.exists(base + ".aux")):
+                tb = time.time()
                 self.fx.build_index_files(text, base, bigEndian=True)
                 log("%s: index files built on the GPU in %.1f s" % (workload, time.time() - tb))
-            except Exception as e:                           # noqa: BLE001 — every rank must leave this function the same way
-                err = e
+        except Exception as e:                               # noqa: BLE001
+            err = e
+            log("rank %d: %s text / index files failed: %s: %s" % (self.rank, workload, type(e).__name__, e))
         if self.max_over_ranks(1.0 if err is not None else 0.0) > 0:
-            raise err if err is not None else RuntimeError("rank 0 could not build the %s index files" % workload)
+            raise err if err is not None else RuntimeError("another rank could not make the %s text / index files" % workload)
         log("rank %d: %s text + index files ready after %.1f s" % (self.rank, workload, time.time() - t0))
         return text, base
 
@@ -1035,16 +1049,116 @@ def regex_leg(cx, g, text, n_regexes, orc, steps):
 
 
 # ------------------------------------------------------------------------------------------------ drivers
-def guarded(name, fn):
-    """a secondary leg must not take the headline down with it"""
+class RunGuard:
+    """Keeps a run bounded and its ranks in step across the secondary legs.
+
+    * agreement: at N > 1 every leg ends with the ranks telling each other, through the process group's c10d store (host side, no NCCL
+      stream involved), whether the leg succeeded.  A leg that failed on ANY rank counts as failed on all, and the remaining legs are
+      skipped everywhere — a rank that went on alone would pair its collectives with the wrong ones of its peers and hang the job
+      (seen on 8 x B200: two ranks lost a file race, the other six waited for them inside an all-reduce until the box's time limit).
+    * watchdog: every leg (and the headline, and the teardown) has a time limit.  When one is exceeded — a rank stuck in a collective
+      whose partner is gone — rank 0 prints the JSON line with what has been measured so far and every rank leaves with os._exit."""
+
+    def __init__(self):
+        self.rank, self.world, self.store = 0, 1, None
+        self.broken = None                                   # name of the leg that failed on some rank (N > 1)
+        self.out, self.printed = None, False
+        self.limits = []                                     # stack of (name, deadline)
+        self.seq = 0
+        self.lock = threading.Lock()
+        self.thread = None
+
+    def attach(self, rank, world):
+        self.rank, self.world = rank, world
+        if world > 1:
+            try:
+                from torch.distributed import distributed_c10d as c10d
+                self.store = c10d._get_default_store()
+            except Exception as e:                           # noqa: BLE001
+                log("rank %d: no c10d store for the leg agreement (%s); the watchdog alone bounds the run" % (rank, e))
+        if self.thread is None:
+            self.thread = threading.Thread(target=self._watch, daemon=True)
+            self.thread.start()
+
+    def push(self, name, seconds):
+        with self.lock:
+            self.limits.append((name, time.time() + seconds))
+
+    def pop(self):
+        with self.lock:
+            if self.limits:
+                self.limits.pop()
+
+    def _watch(self):
+        while True:
+            time.sleep(1.0)
+            with self.lock:
+                late = [n for n, d in self.limits if time.time() > d]
+            if late:
+                self._fire(late[0])
+
+    def _fire(self, name):
+        log("rank %d: watchdog: '%s' exceeded its time limit — ending the run with what has been measured" % (self.rank, name))
+        code = 0
+        if self.rank == 0 and not self.printed:
+            if self.out is not None:
+                try:
+                    self.emit(dict(self.out, watchdog="'%s' exceeded its time limit; later legs were not run" % name))
+                except Exception as e:                       # noqa: BLE001
+                    log("watchdog: could not print the partial line: %s" % e)
+                    code = 3
+            else:
+                code = 3                                     # nothing measured yet
+        sys.stderr.flush()
+        os._exit(code)
+
+    def emit(self, out):
+        """the ONE JSON line (rank 0)"""
+        with self.lock:
+            if self.printed:
+                return
+            self.printed = True
+        print(json.dumps(out), file=OUT, flush=True)
+
+    def agree(self, name, ok, timeout_s=180):
+        """True iff the leg succeeded on every rank (same answer on every rank, barring a timeout)"""
+        if self.world == 1 or self.store is None:
+            return ok
+        from datetime import timedelta
+        self.seq += 1
+        keys = ["fmxleg/%d/%d" % (self.seq, r) for r in range(self.world)]
+        try:
+            self.store.set(keys[self.rank], "1" if ok else "0")
+            self.store.wait(keys, timedelta(seconds=timeout_s))
+            return all(bytes(self.store.get(k)) == b"1" for k in keys)
+        except Exception as e:                               # noqa: BLE001 — a peer never got here
+            log("rank %d: leg '%s': no answer from every rank (%s: %s)" % (self.rank, name, type(e).__name__, str(e)[:200]))
+            return False
+
+
+GUARD = RunGuard()
+
+
+def guarded(name, fn, limit_s=480):
+    """a secondary leg must not take the headline down with it — nor, at N > 1, leave the ranks out of step (RunGuard)"""
+    if GUARD.broken is not None:
+        log("leg %s skipped: leg '%s' failed on some rank" % (name, GUARD.broken))
+        return {"skipped": "leg '%s' failed on some rank" % GUARD.broken}
+    GUARD.push(name, limit_s)
+    t0 = time.time()
     try:
-        t0 = time.time()
-        r = fn()
-        log("leg %s done in %.1f s" % (name, time.time() - t0))
-        return r
+        r, ok = fn(), True
     except Exception as e:                                           # noqa: BLE001
         log("leg %s FAILED:\n%s" % (name, traceback.format_exc()))
-        return {"error": "%s: %s" % (type(e).__name__, e)}
+        r, ok = {"error": "%s: %s" % (type(e).__name__, e)}, False
+    if GUARD.world > 1 and not GUARD.agree(name, ok):
+        GUARD.broken = name
+        if ok:
+            r = {"error": "leg failed on another rank", "this_rank": r if isinstance(r, dict) and len(json.dumps(r, default=str)) < 4000 else "ok"}
+    elif ok:
+        log("leg %s done in %.1f s" % (name, time.time() - t0))
+    GUARD.pop()
+    return r
 
 
 def run_default(cx):
@@ -1055,6 +1169,7 @@ def run_default(cx):
     n, m, ln = args.text_bytes, args.queries, args.len
     numa = numa_report(cx.local)
     out, stt = count_workload(cx, "cfg2", n, m, ln, extras)
+    GUARD.out = out                                          # from here on a partial line can be printed
     out["host"] = {"numa": numa, "cores": os.cpu_count()}
     g, text, base = stt["g"], stt["text"], stt["base"]
     scale = n / DEFAULTS["cfg2"][0]
@@ -1270,17 +1385,25 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    GUARD.attach(rank, world)
+    GUARD.push("the whole run", 1500 if args.workload != "cfg3" else 7200)
     try:
         cx = Ctx(args, rank, world, local_rank)
         out = run_default(cx) if args.workload == "cfg2" else run_workload(cx)
         if rank == 0:
-            print(json.dumps(out), file=OUT, flush=True)
-        if world > 1:                                        # exchange buffers live as long as the process group: unmap, barrier, free
+            GUARD.emit(out)
+        GUARD.out = None
+        GUARD.push("teardown", 90)                           # the line is out: nothing below may keep the job alive
+        if world > 1 and GUARD.broken is None:               # exchange buffers live as long as the process group: unmap, barrier, free
             from findex_b200 import sharded
             torch.cuda.synchronize()
             sharded.close_retired(cx.barrier)
     finally:
         if world > 1:
+            if GUARD.broken is not None:                     # ranks possibly out of step: no collective teardown
+                sys.stdout.flush()
+                sys.stderr.flush()
+                os._exit(0 if (GUARD.printed or rank != 0) else 1)
             import torch.distributed as dist
             dist.destroy_process_group()
 
