@@ -649,20 +649,26 @@ cudaError_t build_dict(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, 
     if (!ix.kmer || K < 1 || sigma < 2 || Dmax <= K || max_entries < 1) return cudaSuccess;
     unsigned long long table_entries = 1;
     for (int j = 0; j < K; ++j) table_entries *= sigma;
+    struct Scratch {                                       // stream-ordered scratch, released on every way out
+        void *p = nullptr; cudaStream_t st;
+        explicit Scratch(cudaStream_t s) : st(s) {}
+        ~Scratch() { if (p) cudaFreeAsync(p, st); }
+    } cnt_mem(st), items_mem(st);
     unsigned long long *d_cnt = nullptr, h_cnt = 0;
-    CK(cudaMallocAsync(&d_cnt, 16, st));
+    CK(cudaMallocAsync(&cnt_mem.p, 16, st));
+    d_cnt = (unsigned long long *)cnt_mem.p;
     CK(cudaMemsetAsync(d_cnt, 0, 16, st));
     // the seeds: wide entries of the dense table (disjoint intervals, so at most n / (min_rows + 1)); counted first — a text without any
     // (uniform symbols under a deep table) gets no dictionary and costs no scratch
-    if ((table_entries + 255) / 256 > 0x7FFFFFFFull) { cudaFreeAsync(d_cnt, st); return cudaSuccess; }
+    if ((table_entries + 255) / 256 > 0x7FFFFFFFull) return cudaSuccess;
     dict_seed_kernel<<<(unsigned)((table_entries + 255) / 256), 256, 0, st>>>(ix.kmer, table_entries, sigma, K, (uint32_t)bits, min_rows, nullptr, 0, d_cnt);
     CK(cudaMemcpyAsync(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const unsigned long long seeds = h_cnt;
-    if (seeds == 0) { cudaFreeAsync(d_cnt, st); return cudaSuccess; }
+    if (seeds == 0) return cudaSuccess;
     const unsigned long long cap = seeds + (unsigned long long)max_entries;
-    DictItem *items = nullptr;
-    CK(cudaMallocAsync(&items, cap * sizeof(DictItem), st));
+    CK(cudaMallocAsync(&items_mem.p, cap * sizeof(DictItem), st));
+    DictItem *items = (DictItem *)items_mem.p;
     CK(cudaMemsetAsync(d_cnt, 0, 16, st));
     dict_seed_kernel<<<(unsigned)((table_entries + 255) / 256), 256, 0, st>>>(ix.kmer, table_entries, sigma, K, (uint32_t)bits, min_rows, items, cap, d_cnt);
     unsigned long long lvl_begin = 0, lvl_count = seeds, total = seeds;
@@ -699,7 +705,7 @@ cudaError_t build_dict(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, 
             unsigned long long covered = 0;
             CK(cudaMemcpyAsync(&covered, d_cnt + 1, 8, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            if (covered * 16ull < (unsigned long long)ix.n) { cudaFreeAsync(items, st); cudaFreeAsync(d_cnt, st); return cudaSuccess; }
+            if (covered * 16ull < (unsigned long long)ix.n) return cudaSuccess;
         }
         lvl_begin = total;
         lvl_count = h_cnt - total;
@@ -712,16 +718,15 @@ cudaError_t build_dict(const DevIndex &ix, LaunchCfg cfg, const uint8_t *d_sym, 
         if (buckets < 4) buckets = 4;
         void *table = nullptr;
         cudaError_t e = cudaMalloc(&table, buckets * 32);
-        if (e != cudaSuccess) { cudaFreeAsync(items, st); cudaFreeAsync(d_cnt, st); return e; }
+        if (e != cudaSuccess) return e;
         CK(cudaMemsetAsync(table, 0, buckets * 32, st));
         CK(cudaMemsetAsync(d_cnt, 0, 16, st));
         dict_insert_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, st>>>(items + seeds, entries, (unsigned long long *)table, buckets, d_cnt);
         CK(cudaMemcpyAsync(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        if (h_cnt != 0) { cudaFree(table); cudaFreeAsync(items, st); cudaFreeAsync(d_cnt, st); return cudaErrorUnknown; }
+        if (h_cnt != 0) { cudaFree(table); return cudaErrorUnknown; }
         *d_table_out = table; *buckets_out = (int64_t)buckets; *depth_out = std::min(D, Dmax); *depth_x_out = D; *entries_out = (int64_t)entries;
     }
-    cudaFreeAsync(items, st); cudaFreeAsync(d_cnt, st);
     return cudaGetLastError();
 }
 
