@@ -15,7 +15,8 @@ The same line carries, as extra keys, what bounds and qualifies that number:
     sweep      cfg-2 index at len 8..64, plain PLANES and the wavelet matrix at len 16, each with requests/query and oracle parity
     sustained  >= 2 s of back-to-back launches with the in-window clock / power record
     pcie       the box's concurrent pinned H2D+D2H copy ceiling for this step's bytes (what bounds e2e)
-    english    cfg 3/4: 10^9-byte English-like text — count at len 12 and 16, locate (SA sample rate 32), 100 k Glushkov regexes
+    english    cfg 3/4: 10^9-byte English-like text — count at len 8 / 12 / 16 / 24 with the dictionary of wide intervals and at len 12
+               without it, locate (SA sample rate 32), 100 k Glushkov regexes
     cfg5       4*10^9-byte DNA text, len-32 count queries (2-bit packed upload for e2e)
 
 One JSON line on stdout (rank 0).  Everything else goes to stderr.
